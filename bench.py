@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Benchmark of the CAT-Seg hot path (Aggregator.forward: cost volume -> logits) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4]
+
+A step = one boundary call on one batch of synthetic inputs of the workload
+(default: BASELINE.json's headline config, ViT-L/14 A-847, 16 images of 336x336 per GPU -> cfg4).
+N > 1 (launched by torchrun): images are sharded over ranks (the reference's own data-parallel
+inference mode); no data-path collective, weak scaling.
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from cat_seg_b200.config import BENCH_CONFIGS, vitb, vitl  # noqa: E402
+from cat_seg_b200.synth import make_inputs, make_state_dict  # noqa: E402
+
+METRIC, UNIT = "vitl_a847_aggregator_images_per_sec", "images/s"
+
+
+# ----------------------------------------------------------------------------- work model
+def stage_flops(cfg, B, T):
+    """Reference-algorithm FLOPs (2 x MACs of model.py as written) per boundary call, per stage."""
+    Te = min(T, cfg.pad_len) if cfg.pad_len > 0 else T
+    S = cfg.pad_len if (cfg.pad_len > 0 and Te < cfg.pad_len) else Te
+    C, hw = cfg.text_guidance_dim, 576
+    npix = hw // (cfg.pooling_size[0] * cfg.pooling_size[1])
+    sl = B * Te
+    swin_block = hw * (2 * 256 * 128 + 128 * 128 + 128 * 128 + 2 * 128 * 512) + 4 * 4 * 2 * 144 * 144 * 32
+    class_tok = 2 * 256 * 128 + 128 * 128 + 2 * 128 * 512 + 4 * (32 * 32 + 32 * 32 + 32)
+    dec = 48 * 48 * (96 * 128 + 9 * 64 * 128 + 9 * 64 * 64) + 96 * 96 * (48 * 64 + 9 * 32 * 64 + 9 * 32 * 32 + 9 * 32)
+    corr = B * T * cfg.prompt_channel * hw * C * (2 if T > Te else 1)
+    prep = corr + B * (hw * 128 * C * 9 + 2304 * 32 * 256 * 9 + 9216 * 16 * 128 * 9) + sl * C * 128
+    m = {
+        "prep": prep, "embed": sl * hw * 128 * 49 * cfg.prompt_channel,
+        "swin": sl * swin_block * 2 * cfg.num_layers,
+        "class": B * npix * S * class_tok * cfg.num_layers,
+        "decoder": sl * dec,
+    }
+    return {k: 2.0 * v for k, v in m.items()}
+
+
+def launches_per_stage(cfg):
+    return {"swin": 2 * cfg.num_layers, "class": 2 * cfg.num_layers}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx.append(float(s[1]))
+                for n, v in zip(names, s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- helpers
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops": d.get("bf16_tflops_sustained", 1400.6), "hbm_gbs": d.get("hbm_gbs", 6454.9), "src": "measured"}
+    return {"tflops": 1590.0, "hbm_gbs": 6650.0, "src": "fallback"}
+
+
+def get_cfg(name):
+    w = BENCH_CONFIGS[name]
+    return (vitb() if w["model"] == "vitb" else vitl()), w["B"], w["T"]
+
+
+def cpu_port_rate(cfg, T, seed=0, repeats=1):
+    """The oracle (CPU fp32 port of the reference) on ONE image of the workload, all host threads."""
+    from oracle.aggregator_oracle import aggregator_forward
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = make_state_dict(cfg, seed)
+    img, text, g = make_inputs(cfg, 1, T, seed)
+    ts = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        aggregator_forward(sd, cfg.oracle_cfg(), img, text, g)
+        ts.append(time.perf_counter() - t0)
+    t = statistics.median(ts)
+    return 1.0 / t, t, torch.get_num_threads()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    cfg, B, T = get_cfg(args.workload)
+    steps, warm = args.steps, args.warmup
+    from oracle.aggregator_oracle import aggregator_forward
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = make_state_dict(cfg, 0)
+    img, text, g = make_inputs(cfg, 1, T, 0)
+    for _ in range(min(warm, 1)):
+        aggregator_forward(sd, cfg.oracle_cfg(), img, text, g)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        aggregator_forward(sd, cfg.oracle_cfg(), img, text, g)
+        ts.append(time.perf_counter() - t0)
+    tot = sum(ts)
+    val = steps / tot
+    sample = f"1 image of {args.workload} (B=1,T={T}) per step; CPU fp32 oracle port of model.py:683-725"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(warm, 1), "ms_per_step": 1e3 * tot / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: CAT-Seg ViT-L/14 A-847, T={T}, pool [1,1]", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    rank, local, world = dist_env()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from cat_seg_b200.aggregator import Aggregator
+    from cat_seg_b200 import sliding_window as sw
+
+    cfg, B, T = get_cfg(args.workload)
+    if args.batch:
+        B = args.batch
+    sd = make_state_dict(cfg, 0)
+    model = Aggregator(**cfg.ctor_kwargs(), precision=args.precision)
+    model.load_state_dict(sd, strict=False)
+    model = model.to(dev)
+    img, text, g = make_inputs(cfg, B, T, seed=rank)
+    host = [t.pin_memory() for t in (img, text, g[1], g[2])]
+    d_img, d_text, d_g1, d_g2 = [t.to(dev) for t in host]
+
+    def step_resident():
+        return model(d_img, d_text, [d_img, d_g1, d_g2])
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        y = step_resident()
+    barrier()
+    model.set_profiling(True)
+    model.stage_times(reset=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        y = step_resident()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    stage_ms, calls = model.stage_times(reset=True)
+    model.set_profiling(False)
+    launches = model.last_launch_count() * args.steps
+
+    # ---- end to end: pinned host inputs -> device, boundary call, per-image argmax labels -> host
+    labels_host = torch.empty(B, 96 * 96, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        a, b, c, d = [t.to(dev, non_blocking=True) for t in host]
+        yy = model(a, b, [a, c, d])
+        for i in range(B):
+            labels_host[i].copy_(sw.argmax(yy[i].view(T, -1)), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    t_loc = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t_loc, op=torch.distributed.ReduceOp.MAX)
+    ms, ms_e2e = t_loc.tolist()
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    value = world * B * args.steps / (ms / 1e3)
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    pk = peaks()
+    fl = stage_flops(cfg, B, T)
+    top = max(stage_ms, key=lambda k: stage_ms[k])
+    n_launch = launches_per_stage(cfg).get(top, 1) * max(calls, 1)
+    per_launch_ms = stage_ms[top] / max(n_launch, 1)
+    achieved = fl[top] / launches_per_stage(cfg).get(top, 1) / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
+    roof = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
+            "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+            "ms_per_launch": per_launch_ms,
+            "stage_ms_per_step": {k: v / max(calls, 1) for k, v in stage_ms.items()},
+            "stage_tflops": {k: (fl[k] / (stage_ms[k] / max(calls, 1) * 1e-3) / 1e12 if stage_ms[k] > 0 else None)
+                             for k in stage_ms}}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, sec, cores = cpu_port_rate(cfg, T)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"1 image of {args.workload} (B=1,T={T}), CPU fp32 oracle, {sec:.1f} s"}
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.precision == "exact" else "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: CAT-Seg ViT-L/14 336x336, T={T} classes (Te=256 kept), "
+                               f"B={B} images/GPU, L=2, pool [1,1], P=1",
+                   "precision": args.precision, "parallelism": f"images sharded over {world} rank(s)",
+                   "l2": "activations (1.2 GB/step) exceed the 126 MB L2; no explicit flush",
+                   "e2e_result": "per-image argmax labels [B,96,96] int32"},
+        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": labels_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=sorted(BENCH_CONFIGS))
+    ap.add_argument("--precision", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--batch", type=int, default=0, help="override images per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

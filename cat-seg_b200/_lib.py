@@ -1,0 +1,95 @@
+"""ctypes binding of libcatseg_b200.so (declared in include/catseg_b200.h).
+
+There is no fallback: if the shared library is missing and cannot be built, importing the product
+path raises.  PyTorch is only used by callers for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+
+class CatsegConfig(C.Structure):
+    _fields_ = [
+        ("text_guidance_dim", C.c_int32), ("text_guidance_proj_dim", C.c_int32),
+        ("appearance_guidance_dim", C.c_int32), ("appearance_guidance_proj_dim", C.c_int32),
+        ("decoder_dims", C.c_int32 * 2), ("decoder_guidance_dims", C.c_int32 * 2),
+        ("decoder_guidance_proj_dims", C.c_int32 * 2),
+        ("num_layers", C.c_int32), ("nheads", C.c_int32), ("hidden_dim", C.c_int32),
+        ("pooling_size", C.c_int32 * 2), ("feature_resolution", C.c_int32 * 2),
+        ("window_size", C.c_int32), ("attention_type", C.c_int32), ("prompt_channel", C.c_int32),
+        ("pad_len", C.c_int32), ("precision", C.c_int32),
+    ]
+
+
+class CatsegTaps(C.Structure):
+    _fields_ = [
+        ("corr", C.c_void_p), ("classes", C.c_void_p), ("embed", C.c_void_p),
+        ("app_guidance", C.c_void_p), ("text_guidance", C.c_void_p),
+        ("dec_guidance0", C.c_void_p), ("dec_guidance1", C.c_void_p),
+        ("swin_b1", C.c_void_p * 4), ("swin_b2", C.c_void_p * 4), ("class_out", C.c_void_p * 4),
+        ("up1", C.c_void_p), ("up2", C.c_void_p),
+    ]
+
+
+STAGES = ("prep", "embed", "swin", "class", "decoder")
+PRECISION = {"exact": 0, "fast": 1}
+
+# every symbol include/catseg_b200.h declares: (name, restype, argtypes)
+_SIGS = [
+    ("catseg_version", C.c_char_p, []),
+    ("catseg_create", C.c_int, [C.POINTER(CatsegConfig), C.POINTER(C.c_void_p)]),
+    ("catseg_destroy", C.c_int, [C.c_void_p]),
+    ("catseg_last_error", C.c_char_p, [C.c_void_p]),
+    ("catseg_num_params", C.c_int, [C.c_void_p]),
+    ("catseg_param_name", C.c_char_p, [C.c_void_p, C.c_int]),
+    ("catseg_param_numel", C.c_int64, [C.c_void_p, C.c_int]),
+    ("catseg_set_param", C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int]),
+    ("catseg_finalize_params", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("catseg_kept_classes", C.c_int, [C.c_void_p, C.c_int]),
+    ("catseg_workspace_bytes", C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    ("catseg_forward", C.c_int, [C.c_void_p] + [C.c_void_p] * 7 + [C.c_size_t, C.c_int, C.c_int, C.c_void_p]),
+    ("catseg_forward_taps", C.c_int, [C.c_void_p] + [C.c_void_p] * 7 +
+     [C.c_size_t, C.c_int, C.c_int, C.POINTER(CatsegTaps), C.c_void_p]),
+    ("catseg_set_profiling", C.c_int, [C.c_void_p, C.c_int]),
+    ("catseg_stage_times", C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),
+    ("catseg_last_launch_count", C.c_int, [C.c_void_p]),
+    ("catseg_stitch_argmax", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("catseg_argmax", C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+]
+EXPORTED_SYMBOLS = tuple(s[0] for s in _SIGS)
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True):
+    """Loads (building first if needed) the CUDA library.  Raises if it cannot be had."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if not os.path.exists(path) or (build_if_missing and _build.needs_build() and _can_build()):
+        if not build_if_missing:
+            raise RuntimeError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+        _build.build()
+    lib = C.CDLL(path)
+    for name, res, args in _SIGS:
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+        fn.restype, fn.argtypes = res, args
+    _LIB = lib
+    return lib
+
+
+def _can_build() -> bool:
+    try:
+        _build._nvcc()
+        return True
+    except RuntimeError:
+        return False

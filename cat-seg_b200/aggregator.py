@@ -1,0 +1,260 @@
+"""Drop-in replacement for the reference ``Aggregator`` (the boundary operator).
+
+Reference: ``cat_seg/modeling/transformer/model.py:558-725`` — built at
+``cat_seg/modeling/transformer/cat_seg_predictor.py:97-113`` and called at ``:161`` as
+``self.transformer(img_feats, text_feats, appearance_guidance)``.
+
+Same constructor kwargs, same ``state_dict`` keys/shapes (a reference checkpoint under
+``sem_seg_head.predictor.transformer.*`` loads with ``strict=True``), same forward signature and
+output (``logits [B, T, 4H, 4W]`` fp32, ``-100`` for classes dropped by the top-``pad_len``
+truncation).  All arithmetic happens in ``libcatseg_b200.so`` (hand-written sm_100a CUDA behind a C
+ABI); PyTorch only owns the tensors and the stream.  CPU tensors are rejected: there is no
+fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .config import AggregatorConfig
+from .synth import param_shapes
+
+
+def _shift_mask(H: int, W: int, window: int, shift: int) -> torch.Tensor:
+    """The ``attn_mask`` buffer of the shifted block (model.py:161-183); kept only so that the
+    state_dict matches the reference — the kernels derive the mask from index arithmetic."""
+    band_h = torch.zeros(H, dtype=torch.long)
+    band_h[H - window: H - shift] = 1
+    band_h[H - shift:] = 2
+    band_w = torch.zeros(W, dtype=torch.long)
+    band_w[W - window: W - shift] = 1
+    band_w[W - shift:] = 2
+    ids = band_h[:, None] * 3 + band_w[None, :]
+    ids = ids.reshape(H // window, window, W // window, window).permute(0, 2, 1, 3).reshape(-1, window * window)
+    diff = ids[:, None, :] - ids[:, :, None]
+    return torch.where(diff != 0, torch.tensor(-100.0), torch.tensor(0.0))
+
+
+class _Node(nn.Module):
+    """Anonymous container used to reproduce the reference's nested parameter names."""
+
+
+class Aggregator(nn.Module):
+    def __init__(self, text_guidance_dim=512, text_guidance_proj_dim=128, appearance_guidance_dim=512,
+                 appearance_guidance_proj_dim=128, decoder_dims=(64, 32), decoder_guidance_dims=(256, 128),
+                 decoder_guidance_proj_dims=(32, 16), num_layers=4, nheads=4, hidden_dim=128,
+                 pooling_size=(6, 6), feature_resolution=(24, 24), window_size=12, attention_type="linear",
+                 prompt_channel=1, pad_len=256, precision: str = "exact") -> None:
+        super().__init__()
+        if attention_type != "linear":
+            raise NotImplementedError("attention_type='full' is dead code in every shipped config (SURVEY.md §2.1)")
+        if precision not in _lib.PRECISION:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISION)}")
+        self.cfg = AggregatorConfig(
+            text_guidance_dim=text_guidance_dim, text_guidance_proj_dim=text_guidance_proj_dim,
+            appearance_guidance_dim=appearance_guidance_dim, appearance_guidance_proj_dim=appearance_guidance_proj_dim,
+            decoder_dims=tuple(decoder_dims), decoder_guidance_dims=tuple(decoder_guidance_dims),
+            decoder_guidance_proj_dims=tuple(decoder_guidance_proj_dims), num_layers=num_layers, nheads=nheads,
+            hidden_dim=hidden_dim, pooling_size=tuple(pooling_size), feature_resolution=tuple(feature_resolution),
+            window_size=window_size, attention_type=attention_type, prompt_channel=prompt_channel, pad_len=pad_len)
+        self.num_layers, self.hidden_dim, self.pad_len = num_layers, hidden_dim, pad_len
+        self.precision = precision
+        self._names: List[str] = []
+        for name, shape in param_shapes(self.cfg).items():
+            self._register(name, nn.Parameter(torch.zeros(shape), requires_grad=False))
+            self._names.append(name)
+        H, W = self.cfg.feature_resolution
+        for l in range(num_layers):
+            self._register(f"layers.{l}.swin_block.block_2.attn_mask",
+                           _shift_mask(H, W, window_size, window_size // 2), buffer=True)
+        self._handle: Optional[C.c_void_p] = None
+        self._handle_device: Optional[torch.device] = None
+        self._synced: Dict[str, tuple] = {}
+        self._workspace: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------ parameter tree
+    def _register(self, dotted: str, value, buffer: bool = False) -> None:
+        parts = dotted.split(".")
+        node: nn.Module = self
+        for p in parts[:-1]:
+            if p not in node._modules:
+                node.add_module(p, _Node())
+            node = node._modules[p]
+        if buffer:
+            node.register_buffer(parts[-1], value)
+        else:
+            node.register_parameter(parts[-1], value)
+
+    def _param(self, dotted: str) -> torch.Tensor:
+        node = self
+        for p in dotted.split("."):
+            node = getattr(node, p)
+        return node
+
+    # ------------------------------------------------------------------ library handle
+    def _lib_error(self, code: int) -> RuntimeError:
+        lib = _lib.load()
+        msg = lib.catseg_last_error(self._handle).decode() if self._handle else lib.catseg_last_error(None).decode()
+        return RuntimeError(f"catseg_b200 error {code}: {msg}")
+
+    def _ensure_handle(self, device: torch.device) -> None:
+        lib = _lib.load()
+        if self._handle is not None and self._handle_device == device:
+            return
+        if self._handle is not None:
+            lib.catseg_destroy(self._handle)
+            self._handle = None
+        c = self.cfg
+        cc = _lib.CatsegConfig(
+            c.text_guidance_dim, c.text_guidance_proj_dim, c.appearance_guidance_dim, c.appearance_guidance_proj_dim,
+            (C.c_int32 * 2)(*c.decoder_dims), (C.c_int32 * 2)(*c.decoder_guidance_dims),
+            (C.c_int32 * 2)(*c.decoder_guidance_proj_dims), c.num_layers, c.nheads, c.hidden_dim,
+            (C.c_int32 * 2)(*c.pooling_size), (C.c_int32 * 2)(*c.feature_resolution), c.window_size, 0,
+            c.prompt_channel, c.pad_len, _lib.PRECISION[self.precision])
+        h = C.c_void_p()
+        with torch.cuda.device(device):
+            rc = lib.catseg_create(C.byref(cc), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"catseg_create failed ({rc}): {lib.catseg_last_error(None).decode()}")
+        self._handle, self._handle_device = h, device
+        self._synced = {}
+        n = lib.catseg_num_params(h)
+        names = [lib.catseg_param_name(h, i).decode() for i in range(n)]
+        if names != self._names:
+            raise RuntimeError("parameter table of libcatseg_b200.so does not match the module")
+
+    def sync_weights(self, force: bool = False) -> None:
+        """Pushes changed parameters to the library and re-packs them into kernel layouts."""
+        lib = _lib.load()
+        dirty = False
+        for name in self._names:
+            p = self._param(name)
+            key = (p.data_ptr(), p._version, p.device)
+            if not force and self._synced.get(name) == key:
+                continue
+            src = p.detach().to(dtype=torch.float32).contiguous()
+            rc = lib.catseg_set_param(self._handle, name.encode(), C.c_void_p(src.data_ptr()), src.numel(),
+                                      1 if src.is_cuda else 0)
+            if rc != 0:
+                raise self._lib_error(rc)
+            self._synced[name] = key
+            dirty = True
+        if dirty:
+            rc = lib.catseg_finalize_params(self._handle, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            if rc != 0:
+                raise self._lib_error(rc)
+
+    def kept_classes(self, T: int) -> int:
+        return self.pad_len if (self.pad_len > 0 and T > self.pad_len) else T
+
+    # ------------------------------------------------------------------ forward
+    def _check(self, img_feats, text_feats, guidance):
+        if not (torch.is_tensor(img_feats) and img_feats.is_cuda):
+            raise RuntimeError("catseg_b200.Aggregator runs on CUDA tensors only (no CPU fallback)")
+        c = self.cfg
+        B, Cc, H, W = img_feats.shape
+        if (H, W) != tuple(c.feature_resolution):
+            raise ValueError(f"img_feats grid {(H, W)} != feature_resolution {c.feature_resolution}")
+        if text_feats.dim() != 4 or text_feats.shape[0] != B or text_feats.shape[2] != c.prompt_channel \
+                or text_feats.shape[3] != c.text_guidance_dim or Cc != c.text_guidance_dim:
+            raise ValueError(f"text_feats {tuple(text_feats.shape)} / img_feats {tuple(img_feats.shape)} mismatch")
+        if len(guidance) != 3:
+            raise ValueError("appearance_guidance must hold 3 tensors [res3, res4, res5]")
+        exp = [(B, c.appearance_guidance_dim, H, W), (B, c.decoder_guidance_dims[0], 2 * H, 2 * W),
+               (B, c.decoder_guidance_dims[1], 4 * H, 4 * W)]
+        for g, e in zip(guidance, exp):
+            if tuple(g.shape) != e:
+                raise ValueError(f"appearance guidance shape {tuple(g.shape)} != {e}")
+        return B, text_feats.shape[1], H, W
+
+    @staticmethod
+    def _f32c(t: torch.Tensor) -> torch.Tensor:
+        return t.detach().to(dtype=torch.float32).contiguous()
+
+    @torch.no_grad()
+    def forward(self, img_feats: torch.Tensor, text_feats: torch.Tensor, appearance_guidance: Sequence[torch.Tensor],
+                taps: Optional[Sequence[str]] = None):
+        """img_feats (B,C,H,W); text_feats (B,T,P,C); appearance_guidance: 3 tensors (model.py:683-689)."""
+        B, T, H, W = self._check(img_feats, text_feats, appearance_guidance)
+        lib = _lib.load()
+        dev = img_feats.device
+        with torch.cuda.device(dev):
+            self._ensure_handle(dev)
+            self.sync_weights()
+            img, text = self._f32c(img_feats), self._f32c(text_feats)
+            g = [self._f32c(x) for x in appearance_guidance]
+            need = lib.catseg_workspace_bytes(self._handle, B, T)
+            if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
+                self._workspace = None
+                self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+            logits = torch.empty(B, T, 4 * H, 4 * W, dtype=torch.float32, device=dev)
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            args = [self._handle] + [C.c_void_p(t.data_ptr()) for t in (img, text, g[0], g[1], g[2], logits)] + \
+                   [C.c_void_p(self._workspace.data_ptr()), self._workspace.numel(), B, T]
+            if taps is None:
+                rc = lib.catseg_forward(*args, stream)
+                if rc != 0:
+                    raise self._lib_error(rc)
+                return logits
+            tap_struct, out = self._make_taps(taps, B, T, H, W, dev)
+            rc = lib.catseg_forward_taps(*args, C.byref(tap_struct), stream)
+            if rc != 0:
+                raise self._lib_error(rc)
+            return logits, out
+
+    def _make_taps(self, names, B, T, H, W, dev):
+        c = self.cfg
+        Te, HW, hid = self.kept_classes(T), H * W, c.hidden_dim
+        shapes = {
+            "corr": ((B, T, c.prompt_channel, HW), torch.float32), "classes": ((B, Te), torch.int32),
+            "embed": ((B, Te, HW, hid), torch.float32),
+            "app_guidance": ((B, HW, c.appearance_guidance_proj_dim), torch.float32),
+            "text_guidance": ((B, Te, c.text_guidance_proj_dim), torch.float32),
+            "dec_guidance0": ((B, 4 * HW, c.decoder_guidance_proj_dims[0]), torch.float32),
+            "dec_guidance1": ((B, 16 * HW, c.decoder_guidance_proj_dims[1]), torch.float32),
+            "up1": ((B, Te, 4 * HW, c.decoder_dims[0]), torch.float32),
+            "up2": ((B, Te, 16 * HW, c.decoder_dims[1]), torch.float32),
+        }
+        for l in range(c.num_layers):
+            for k in ("swin_l%d_b1", "swin_l%d_b2", "class_l%d"):
+                shapes[k % l] = ((B, Te, HW, hid), torch.float32)
+        ts = _lib.CatsegTaps()
+        out = {}
+        for n in names:
+            shape, dt = shapes[n]
+            t = torch.zeros(shape, dtype=dt, device=dev)
+            out[n] = t
+            if n.startswith("swin_l"):
+                l = int(n[6])
+                getattr(ts, "swin_b1" if n.endswith("b1") else "swin_b2")[l] = t.data_ptr()
+            elif n.startswith("class_l"):
+                ts.class_out[int(n[7:])] = t.data_ptr()
+            else:
+                setattr(ts, n, t.data_ptr())
+        return ts, out
+
+    # ------------------------------------------------------------------ profiling hooks (bench.py)
+    def set_profiling(self, enable: bool) -> None:
+        _lib.load().catseg_set_profiling(self._handle, 1 if enable else 0)
+
+    def stage_times(self, reset: bool = True):
+        ms = (C.c_float * len(_lib.STAGES))()
+        calls = C.c_int(0)
+        rc = _lib.load().catseg_stage_times(self._handle, ms, C.byref(calls), 1 if reset else 0)
+        if rc != 0:
+            raise self._lib_error(rc)
+        return {s: ms[i] for i, s in enumerate(_lib.STAGES)}, calls.value
+
+    def last_launch_count(self) -> int:
+        return _lib.load().catseg_last_launch_count(self._handle)
+
+    def __del__(self):
+        try:
+            if self._handle is not None and _lib._LIB is not None:
+                _lib._LIB.catseg_destroy(self._handle)
+        except Exception:
+            pass

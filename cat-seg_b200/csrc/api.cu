@@ -1,0 +1,706 @@
+// C ABI of the CAT-Seg B200 hot path: handle, parameter table, packing, workspace carving and the
+// stage orchestration of Aggregator.forward (cat_seg/modeling/transformer/model.py:683-725).
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/catseg_b200.h"
+#include "internal.h"
+
+using namespace catseg;
+
+namespace {
+
+struct Param {
+  std::string name;
+  int64_t numel;
+  size_t offset;   // floats into raw
+  bool set;
+};
+
+thread_local std::string g_create_error;
+
+constexpr int kMaxProfForwards = 64;
+constexpr int kMaxSegments = 24;
+
+}  // namespace
+
+struct catseg_handle {
+  catseg_config cfg;
+  std::vector<Param> params;
+  float* raw = nullptr;
+  size_t raw_floats = 0;
+  float* packed = nullptr;
+  size_t packed_floats = 0;
+  bool finalized = false;
+  std::string err;
+  int device = 0;
+
+  // packed views
+  std::vector<SwinBlockW> swin;     // [L*2]
+  std::vector<ClassLayerW> cls;     // [L]
+  std::vector<const float*> gnorm_g, gnorm_b;   // [L]
+  DecoderW dec;
+  const float *conv1_wt = nullptr, *conv1_b = nullptr;       // [P*49][128]
+  const float *gproj_wt = nullptr, *gproj_b = nullptr;       // [Cg*9][Ag]
+  const float *tproj_wt = nullptr, *tproj_b = nullptr;       // [Ct][Tg]
+  const float *dgp_wt[2] = {nullptr, nullptr}, *dgp_b[2] = {nullptr, nullptr};
+
+  // profiling
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev;      // pairs
+  std::vector<int> ev_stage;
+  int ev_used = 0;                  // segments recorded
+  int prof_forwards = 0;
+  int last_launches = 0;
+};
+
+static int fail(catseg_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CUDA_OK(h, call)                                                                          \
+  do {                                                                                            \
+    cudaError_t _e = (call);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return fail(h, CATSEG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+static void add_param(catseg_handle* h, const std::string& name, int64_t numel) {
+  Param p{name, numel, h->raw_floats, false};
+  h->raw_floats += (size_t)((numel + 3) / 4 * 4);
+  h->params.push_back(p);
+}
+
+static void build_param_table(catseg_handle* h) {
+  const catseg_config& c = h->cfg;
+  const int hid = c.hidden_dim, ag = c.appearance_guidance_proj_dim, tg = c.text_guidance_proj_dim;
+  char b[160];
+  for (int l = 0; l < c.num_layers; ++l) {
+    for (int k = 1; k <= 2; ++k) {
+      snprintf(b, sizeof(b), "layers.%d.swin_block.block_%d", l, k);
+      std::string q(b);
+      add_param(h, q + ".norm1.weight", hid); add_param(h, q + ".norm1.bias", hid);
+      add_param(h, q + ".attn.q.weight", (int64_t)hid * (hid + ag)); add_param(h, q + ".attn.q.bias", hid);
+      add_param(h, q + ".attn.k.weight", (int64_t)hid * (hid + ag)); add_param(h, q + ".attn.k.bias", hid);
+      add_param(h, q + ".attn.v.weight", (int64_t)hid * hid); add_param(h, q + ".attn.v.bias", hid);
+      add_param(h, q + ".attn.proj.weight", (int64_t)hid * hid); add_param(h, q + ".attn.proj.bias", hid);
+      add_param(h, q + ".norm2.weight", hid); add_param(h, q + ".norm2.bias", hid);
+      add_param(h, q + ".mlp.fc1.weight", (int64_t)4 * hid * hid); add_param(h, q + ".mlp.fc1.bias", 4 * hid);
+      add_param(h, q + ".mlp.fc2.weight", (int64_t)4 * hid * hid); add_param(h, q + ".mlp.fc2.bias", hid);
+    }
+    snprintf(b, sizeof(b), "layers.%d.swin_block.guidance_norm", l);
+    add_param(h, std::string(b) + ".weight", ag); add_param(h, std::string(b) + ".bias", ag);
+    snprintf(b, sizeof(b), "layers.%d.attention", l);
+    std::string a(b);
+    add_param(h, a + ".padding_tokens", hid);
+    add_param(h, a + ".padding_guidance", tg);
+    add_param(h, a + ".attention.q.weight", (int64_t)hid * (hid + tg)); add_param(h, a + ".attention.q.bias", hid);
+    add_param(h, a + ".attention.k.weight", (int64_t)hid * (hid + tg)); add_param(h, a + ".attention.k.bias", hid);
+    add_param(h, a + ".attention.v.weight", (int64_t)hid * hid); add_param(h, a + ".attention.v.bias", hid);
+    add_param(h, a + ".MLP.0.weight", (int64_t)4 * hid * hid); add_param(h, a + ".MLP.0.bias", 4 * hid);
+    add_param(h, a + ".MLP.2.weight", (int64_t)4 * hid * hid); add_param(h, a + ".MLP.2.bias", hid);
+    add_param(h, a + ".norm1.weight", hid); add_param(h, a + ".norm1.bias", hid);
+    add_param(h, a + ".norm2.weight", hid); add_param(h, a + ".norm2.bias", hid);
+  }
+  add_param(h, "conv1.weight", (int64_t)hid * c.prompt_channel * 49); add_param(h, "conv1.bias", hid);
+  add_param(h, "guidance_projection.0.weight", (int64_t)ag * c.appearance_guidance_dim * 9);
+  add_param(h, "guidance_projection.0.bias", ag);
+  add_param(h, "text_guidance_projection.0.weight", (int64_t)tg * c.text_guidance_dim);
+  add_param(h, "text_guidance_projection.0.bias", tg);
+  for (int i = 0; i < 2; ++i) {
+    snprintf(b, sizeof(b), "decoder_guidance_projection.%d.0", i);
+    add_param(h, std::string(b) + ".weight", (int64_t)c.decoder_guidance_proj_dims[i] * c.decoder_guidance_dims[i] * 9);
+    add_param(h, std::string(b) + ".bias", c.decoder_guidance_proj_dims[i]);
+  }
+  int cin = hid;
+  for (int i = 0; i < 2; ++i) {
+    int cout = c.decoder_dims[i], gp = c.decoder_guidance_proj_dims[i];
+    snprintf(b, sizeof(b), "decoder%d", i + 1);
+    std::string d(b);
+    add_param(h, d + ".up.weight", (int64_t)cin * (cin - gp) * 4); add_param(h, d + ".up.bias", cin - gp);
+    add_param(h, d + ".conv.double_conv.0.weight", (int64_t)cout * cin * 9);
+    add_param(h, d + ".conv.double_conv.1.weight", cout); add_param(h, d + ".conv.double_conv.1.bias", cout);
+    add_param(h, d + ".conv.double_conv.3.weight", (int64_t)cout * cout * 9);
+    add_param(h, d + ".conv.double_conv.4.weight", cout); add_param(h, d + ".conv.double_conv.4.bias", cout);
+    cin = cout;
+  }
+  add_param(h, "head.weight", (int64_t)cin * 9); add_param(h, "head.bias", 1);
+}
+
+static const float* raw_of(const catseg_handle* h, const std::string& name) {
+  for (const Param& p : h->params)
+    if (p.name == name) return h->raw + p.offset;
+  return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* catseg_version(void) { return "catseg_b200 0.1 sm_100a"; }
+
+extern "C" const char* catseg_last_error(const catseg_handle* h) {
+  return h ? h->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int catseg_create(const catseg_config* cfg, catseg_handle** out) {
+  if (!cfg || !out) return fail(nullptr, CATSEG_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const catseg_config& c = *cfg;
+  // The kernels are specialised for the shipped CAT-Seg geometry; anything else fails loudly.
+  if (c.hidden_dim != 128 || c.nheads != 4)
+    return fail(nullptr, CATSEG_ERR_UNSUPPORTED, "hidden_dim=%d nheads=%d: kernels are built for 128/4", c.hidden_dim, c.nheads);
+  if (c.feature_resolution[0] != 24 || c.feature_resolution[1] != 24 || c.window_size != 12)
+    return fail(nullptr, CATSEG_ERR_UNSUPPORTED, "feature_resolution %dx%d window %d: kernels are built for 24x24 / 12",
+                c.feature_resolution[0], c.feature_resolution[1], c.window_size);
+  if (c.attention_type != 0)
+    return fail(nullptr, CATSEG_ERR_UNSUPPORTED, "attention_type 'full' is dead code in every shipped config and is not implemented");
+  if (c.appearance_guidance_proj_dim != 128 || c.text_guidance_proj_dim != 128)
+    return fail(nullptr, CATSEG_ERR_UNSUPPORTED, "guidance projection dims must be 128");
+  if (c.num_layers < 1 || c.num_layers > 4) return fail(nullptr, CATSEG_ERR_UNSUPPORTED, "num_layers must be 1..4");
+  if (c.pooling_size[0] < 1 || c.pooling_size[1] < 1 || 24 % c.pooling_size[0] || 24 % c.pooling_size[1])
+    return fail(nullptr, CATSEG_ERR_UNSUPPORTED, "pooling_size must divide 24");
+  if (c.prompt_channel < 1 || c.pad_len < 0) return fail(nullptr, CATSEG_ERR_INVALID, "bad prompt_channel / pad_len");
+  if (c.decoder_dims[0] % 16 || c.decoder_dims[1] % 16 || c.decoder_dims[0] > 128 || c.decoder_dims[1] > 128)
+    return fail(nullptr, CATSEG_ERR_UNSUPPORTED, "decoder_dims must be multiples of 16 (GroupNorm groups of 16)");
+  if (c.decoder_guidance_proj_dims[0] % 4 || c.decoder_guidance_proj_dims[1] % 4)
+    return fail(nullptr, CATSEG_ERR_UNSUPPORTED, "decoder_guidance_proj_dims must be multiples of 4");
+  if (c.precision != CATSEG_PRECISION_EXACT)
+    return fail(nullptr, CATSEG_ERR_UNSUPPORTED, "precision %d is not available in this build", c.precision);
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) {
+    cudaGetLastError();
+    return fail(nullptr, CATSEG_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  }
+  catseg_handle* h = new catseg_handle();
+  h->cfg = c;
+  cudaGetDevice(&h->device);
+  build_param_table(h);
+  if (cudaMalloc(&h->raw, h->raw_floats * sizeof(float)) != cudaSuccess) {
+    delete h;
+    return fail(nullptr, CATSEG_ERR_CUDA, "cudaMalloc of the parameter store failed");
+  }
+  cudaMemset(h->raw, 0, h->raw_floats * sizeof(float));
+  *out = h;
+  return CATSEG_OK;
+}
+
+extern "C" int catseg_destroy(catseg_handle* h) {
+  if (!h) return CATSEG_OK;
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  if (h->raw) cudaFree(h->raw);
+  if (h->packed) cudaFree(h->packed);
+  delete h;
+  return CATSEG_OK;
+}
+
+extern "C" int catseg_num_params(const catseg_handle* h) { return h ? (int)h->params.size() : 0; }
+extern "C" const char* catseg_param_name(const catseg_handle* h, int i) {
+  return (h && i >= 0 && i < (int)h->params.size()) ? h->params[i].name.c_str() : nullptr;
+}
+extern "C" int64_t catseg_param_numel(const catseg_handle* h, int i) {
+  return (h && i >= 0 && i < (int)h->params.size()) ? h->params[i].numel : -1;
+}
+
+extern "C" int catseg_set_param(catseg_handle* h, const char* name, const float* src, int64_t numel, int src_is_device) {
+  if (!h || !name || !src) return fail(h, CATSEG_ERR_INVALID, "null argument");
+  for (Param& p : h->params) {
+    if (p.name != name) continue;
+    if (p.numel != numel)
+      return fail(h, CATSEG_ERR_WEIGHTS, "parameter %s: expected %lld values, got %lld", name, (long long)p.numel, (long long)numel);
+    CUDA_OK(h, cudaMemcpy(h->raw + p.offset, src, (size_t)numel * sizeof(float),
+                          src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    p.set = true;
+    h->finalized = false;
+    return CATSEG_OK;
+  }
+  return fail(h, CATSEG_ERR_WEIGHTS, "unknown parameter %s", name);
+}
+
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Packer {
+  catseg_handle* h;
+  cudaStream_t st;
+  size_t used = 0;
+  bool dry;
+  cudaError_t err = cudaSuccess;
+  float* alloc(size_t n) {
+    size_t o = used;
+    used += (n + 3) / 4 * 4;
+    return dry ? nullptr : h->packed + o;
+  }
+  void note(cudaError_t e) { if (err == cudaSuccess && e != cudaSuccess) err = e; }
+  const float* copy(const std::string& name, size_t n) {
+    float* d = alloc(n);
+    if (!dry) note(cudaMemcpyAsync(d, raw_of(h, name), n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return d;
+  }
+  // Linear weight [out][ld] columns [col0, col0+in) -> transposed into dst[in][ldd] at column dst_col0
+  void tr(float* dst, int ldd, int dst_col0, const std::string& name, int lds, int src_col0, int out, int in) {
+    if (!dry) note(launch_transpose_pack(dst, ldd, dst_col0, raw_of(h, name), lds, src_col0, out, in, st));
+  }
+};
+
+__global__ void pack_conv3x3_kernel(float* dst, const float* src, int Co, int Ci) {
+  // dst[(tap*Ci + ci)*Co + co] = src[((co*Ci + ci)*9) + tap]
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Co * Ci * 9) return;
+  int co = i % Co, r = i / Co, ci = r % Ci, tap = r / Ci;
+  dst[i] = src[((long long)co * Ci + ci) * 9 + tap];
+}
+__global__ void pack_convT_kernel(float* dst, const float* src, int Ci, int Co) {
+  // dst[ci*(4*Co) + q*Co + co] = src[((ci*Co + co)*4) + q],  q = dy*2+dx
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Ci * Co * 4) return;
+  int co = i % Co, r = i / Co, q = r % 4, ci = r / 4;
+  dst[i] = src[((long long)ci * Co + co) * 4 + q];
+}
+
+void pack_all(Packer& pk) {
+  catseg_handle* h = pk.h;
+  const catseg_config& c = h->cfg;
+  const int ag = c.appearance_guidance_proj_dim, tg = c.text_guidance_proj_dim;
+  char b[160];
+  h->swin.assign(c.num_layers * 2, SwinBlockW{});
+  h->cls.assign(c.num_layers, ClassLayerW{});
+  h->gnorm_g.assign(c.num_layers, nullptr);
+  h->gnorm_b.assign(c.num_layers, nullptr);
+  for (int l = 0; l < c.num_layers; ++l) {
+    for (int k = 0; k < 2; ++k) {
+      snprintf(b, sizeof(b), "layers.%d.swin_block.block_%d", l, k + 1);
+      std::string q(b);
+      SwinBlockW& w = h->swin[l * 2 + k];
+      w.ln1_g = pk.copy(q + ".norm1.weight", 128); w.ln1_b = pk.copy(q + ".norm1.bias", 128);
+      w.ln2_g = pk.copy(q + ".norm2.weight", 128); w.ln2_b = pk.copy(q + ".norm2.bias", 128);
+      float* wqkv = pk.alloc(128 * 384);
+      pk.tr(wqkv, 384, 0, q + ".attn.q.weight", 128 + ag, 0, 128, 128);
+      pk.tr(wqkv, 384, 128, q + ".attn.k.weight", 128 + ag, 0, 128, 128);
+      pk.tr(wqkv, 384, 256, q + ".attn.v.weight", 128, 0, 128, 128);
+      w.wqkv_t = wqkv;
+      w.bv = pk.copy(q + ".attn.v.bias", 128);
+      float* wp = pk.alloc(128 * 128);
+      pk.tr(wp, 128, 0, q + ".attn.proj.weight", 128, 0, 128, 128);
+      w.wproj_t = wp;
+      w.bproj = pk.copy(q + ".attn.proj.bias", 128);
+      float* w1 = pk.alloc(128 * 512);
+      pk.tr(w1, 512, 0, q + ".mlp.fc1.weight", 128, 0, 512, 128);
+      w.w1_t = w1;
+      w.b1 = pk.copy(q + ".mlp.fc1.bias", 512);
+      float* w2 = pk.alloc(512 * 128);
+      pk.tr(w2, 128, 0, q + ".mlp.fc2.weight", 512, 0, 128, 512);
+      w.w2_t = w2;
+      w.b2 = pk.copy(q + ".mlp.fc2.bias", 128);
+      float* wg = pk.alloc((size_t)ag * 256);
+      pk.tr(wg, 256, 0, q + ".attn.q.weight", 128 + ag, 128, 128, ag);
+      pk.tr(wg, 256, 128, q + ".attn.k.weight", 128 + ag, 128, 128, ag);
+      w.wg_qk_t = wg;
+      float* bqk = pk.alloc(256);
+      if (!pk.dry) {
+        pk.note(cudaMemcpyAsync(bqk, raw_of(h, q + ".attn.q.bias"), 512, cudaMemcpyDeviceToDevice, pk.st));
+        pk.note(cudaMemcpyAsync(bqk + 128, raw_of(h, q + ".attn.k.bias"), 512, cudaMemcpyDeviceToDevice, pk.st));
+      }
+      w.bqk = bqk;
+    }
+    snprintf(b, sizeof(b), "layers.%d.swin_block.guidance_norm", l);
+    h->gnorm_g[l] = pk.copy(std::string(b) + ".weight", ag);
+    h->gnorm_b[l] = pk.copy(std::string(b) + ".bias", ag);
+    snprintf(b, sizeof(b), "layers.%d.attention", l);
+    std::string a(b);
+    ClassLayerW& w = h->cls[l];
+    w.ln1_g = pk.copy(a + ".norm1.weight", 128); w.ln1_b = pk.copy(a + ".norm1.bias", 128);
+    w.ln2_g = pk.copy(a + ".norm2.weight", 128); w.ln2_b = pk.copy(a + ".norm2.bias", 128);
+    float* wqkv = pk.alloc(128 * 384);
+    pk.tr(wqkv, 384, 0, a + ".attention.q.weight", 128 + tg, 0, 128, 128);
+    pk.tr(wqkv, 384, 128, a + ".attention.k.weight", 128 + tg, 0, 128, 128);
+    pk.tr(wqkv, 384, 256, a + ".attention.v.weight", 128, 0, 128, 128);
+    w.wqkv_t = wqkv;
+    w.bv = pk.copy(a + ".attention.v.bias", 128);
+    float* wg = pk.alloc((size_t)tg * 256);
+    pk.tr(wg, 256, 0, a + ".attention.q.weight", 128 + tg, 128, 128, tg);
+    pk.tr(wg, 256, 128, a + ".attention.k.weight", 128 + tg, 128, 128, tg);
+    w.wg_qk_t = wg;
+    float* bqk = pk.alloc(256);
+    if (!pk.dry) {
+      pk.note(cudaMemcpyAsync(bqk, raw_of(h, a + ".attention.q.bias"), 512, cudaMemcpyDeviceToDevice, pk.st));
+      pk.note(cudaMemcpyAsync(bqk + 128, raw_of(h, a + ".attention.k.bias"), 512, cudaMemcpyDeviceToDevice, pk.st));
+    }
+    w.bqk = bqk;
+    float* w1 = pk.alloc(128 * 512);
+    pk.tr(w1, 512, 0, a + ".MLP.0.weight", 128, 0, 512, 128);
+    w.w1_t = w1;
+    w.b1 = pk.copy(a + ".MLP.0.bias", 512);
+    float* w2 = pk.alloc(512 * 128);
+    pk.tr(w2, 128, 0, a + ".MLP.2.weight", 512, 0, 128, 512);
+    w.w2_t = w2;
+    w.b2 = pk.copy(a + ".MLP.2.bias", 128);
+    w.pad_tok = pk.copy(a + ".padding_tokens", 128);
+    w.pad_g = pk.copy(a + ".padding_guidance", tg);
+  }
+  // conv1: [128][P*49] -> [P*49][128]
+  {
+    int K = c.prompt_channel * 49;
+    float* d = pk.alloc((size_t)K * 128);
+    pk.tr(d, 128, 0, "conv1.weight", K, 0, 128, K);
+    h->conv1_wt = d;
+    h->conv1_b = pk.copy("conv1.bias", 128);
+  }
+  {
+    int K = c.appearance_guidance_dim * 9;
+    float* d = pk.alloc((size_t)K * ag);
+    pk.tr(d, ag, 0, "guidance_projection.0.weight", K, 0, ag, K);
+    h->gproj_wt = d;
+    h->gproj_b = pk.copy("guidance_projection.0.bias", ag);
+  }
+  {
+    int K = c.text_guidance_dim;
+    float* d = pk.alloc((size_t)K * tg);
+    pk.tr(d, tg, 0, "text_guidance_projection.0.weight", K, 0, tg, K);
+    h->tproj_wt = d;
+    h->tproj_b = pk.copy("text_guidance_projection.0.bias", tg);
+  }
+  for (int i = 0; i < 2; ++i) {
+    snprintf(b, sizeof(b), "decoder_guidance_projection.%d.0", i);
+    int K = c.decoder_guidance_dims[i] * 9, N = c.decoder_guidance_proj_dims[i];
+    float* d = pk.alloc((size_t)K * N);
+    pk.tr(d, N, 0, std::string(b) + ".weight", K, 0, N, K);
+    h->dgp_wt[i] = d;
+    h->dgp_b[i] = pk.copy(std::string(b) + ".bias", N);
+  }
+  // decoder
+  {
+    DecoderW& d = h->dec;
+    int cin = 128;
+    for (int i = 0; i < 2; ++i) {
+      int cout = c.decoder_dims[i], gp = c.decoder_guidance_proj_dims[i], up = cin - gp;
+      snprintf(b, sizeof(b), "decoder%d", i + 1);
+      std::string p(b);
+      float* upw = pk.alloc((size_t)cin * 4 * up);
+      if (!pk.dry) {
+        int n = cin * up * 4;
+        pack_convT_kernel<<<(n + 255) / 256, 256, 0, pk.st>>>(upw, raw_of(h, p + ".up.weight"), cin, up);
+        pk.note(cudaGetLastError());
+      }
+      const float* upb = pk.copy(p + ".up.bias", up);
+      float* ca = pk.alloc((size_t)9 * cin * cout);
+      float* cb = pk.alloc((size_t)9 * cout * cout);
+      if (!pk.dry) {
+        int n = cout * cin * 9;
+        pack_conv3x3_kernel<<<(n + 255) / 256, 256, 0, pk.st>>>(ca, raw_of(h, p + ".conv.double_conv.0.weight"), cout, cin);
+        pk.note(cudaGetLastError());
+        n = cout * cout * 9;
+        pack_conv3x3_kernel<<<(n + 255) / 256, 256, 0, pk.st>>>(cb, raw_of(h, p + ".conv.double_conv.3.weight"), cout, cout);
+        pk.note(cudaGetLastError());
+      }
+      const float* ga = pk.copy(p + ".conv.double_conv.1.weight", cout);
+      const float* ba = pk.copy(p + ".conv.double_conv.1.bias", cout);
+      const float* gb = pk.copy(p + ".conv.double_conv.4.weight", cout);
+      const float* bb = pk.copy(p + ".conv.double_conv.4.bias", cout);
+      if (i == 0) {
+        d.up1_wt = upw; d.up1_b = upb; d.c1a_wt = ca; d.c1b_wt = cb;
+        d.gn1a_g = ga; d.gn1a_b = ba; d.gn1b_g = gb; d.gn1b_b = bb;
+      } else {
+        d.up2_wt = upw; d.up2_b = upb; d.c2a_wt = ca; d.c2b_wt = cb;
+        d.gn2a_g = ga; d.gn2a_b = ba; d.gn2b_g = gb; d.gn2b_b = bb;
+      }
+      cin = cout;
+    }
+    float* hw = pk.alloc((size_t)9 * cin);
+    if (!pk.dry) {
+      int n = cin * 9;
+      pack_conv3x3_kernel<<<(n + 255) / 256, 256, 0, pk.st>>>(hw, raw_of(h, "head.weight"), 1, cin);
+      pk.note(cudaGetLastError());
+    }
+    d.head_w = hw;
+    d.head_b = pk.copy("head.bias", 1);
+  }
+}
+
+}  // namespace
+
+extern "C" int catseg_finalize_params(catseg_handle* h, catseg_stream stream) {
+  if (!h) return CATSEG_ERR_INVALID;
+  for (const Param& p : h->params)
+    if (!p.set) return fail(h, CATSEG_ERR_WEIGHTS, "parameter %s was never set", p.name.c_str());
+  cudaStream_t st = (cudaStream_t)stream;
+  Packer dry{h, st, 0, true};
+  pack_all(dry);
+  if (!h->packed || h->packed_floats < dry.used) {
+    if (h->packed) cudaFree(h->packed);
+    h->packed = nullptr;
+    CUDA_OK(h, cudaMalloc(&h->packed, dry.used * sizeof(float)));
+    h->packed_floats = dry.used;
+  }
+  Packer pk{h, st, 0, false};
+  pack_all(pk);
+  if (pk.err != cudaSuccess) return fail(h, CATSEG_ERR_CUDA, "packing failed: %s", cudaGetErrorString(pk.err));
+  CUDA_OK(h, cudaStreamSynchronize(st));
+  h->finalized = true;
+  return CATSEG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Plan {
+  int B, T, Te, P, C, Ct, Cg, H, W, HW, Hp, Wp, npix, S, n_pad, L;
+  bool truncated, pooled;
+  int dec_chunk;
+  DecoderDims dd;
+  // workspace offsets (floats)
+  size_t imgn, textn, corr, cmax, classes, tmean, text_g, cg_qk, pad_state, app_g, app_gn, ag_qk, dg0, dg1, X,
+      Xp, Xp2, state, dec, total;
+};
+
+Plan make_plan(const catseg_handle* h, int B, int T) {
+  const catseg_config& c = h->cfg;
+  Plan p{};
+  p.B = B; p.T = T; p.P = c.prompt_channel; p.Ct = c.text_guidance_dim; p.C = c.text_guidance_dim;
+  p.Cg = c.appearance_guidance_dim;
+  p.H = c.feature_resolution[0]; p.W = c.feature_resolution[1]; p.HW = p.H * p.W; p.L = c.num_layers;
+  p.truncated = c.pad_len > 0 && T > c.pad_len;
+  p.Te = p.truncated ? c.pad_len : T;
+  p.S = (c.pad_len > 0 && p.Te < c.pad_len) ? c.pad_len : p.Te;
+  p.n_pad = p.S - p.Te;
+  p.pooled = c.pooling_size[0] > 1 || c.pooling_size[1] > 1;
+  p.Hp = p.H / c.pooling_size[0]; p.Wp = p.W / c.pooling_size[1]; p.npix = p.Hp * p.Wp;
+  p.dd = DecoderDims{p.H, p.W, 128, 128 - c.decoder_guidance_proj_dims[0], c.decoder_guidance_proj_dims[0],
+                     c.decoder_dims[0], c.decoder_dims[0] - c.decoder_guidance_proj_dims[1],
+                     c.decoder_guidance_proj_dims[1], c.decoder_dims[1]};
+  int nslice = B * p.Te;
+  p.dec_chunk = nslice < 96 ? nslice : 96;
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += (n + 63) / 64 * 64; return r; };
+  p.imgn = take((size_t)B * p.C * p.HW);
+  p.textn = take((size_t)B * T * p.P * p.Ct);
+  p.corr = take((size_t)B * T * p.P * p.HW);
+  p.cmax = take((size_t)B * T);
+  p.classes = take((size_t)B * p.Te);
+  p.tmean = take((size_t)B * p.Te * p.Ct);
+  p.text_g = take((size_t)B * p.Te * 128);
+  p.cg_qk = take((size_t)p.L * B * p.Te * 256);
+  p.pad_state = take((size_t)p.L * kStateFloats);
+  p.app_g = take((size_t)B * p.HW * 128);
+  p.app_gn = take((size_t)B * p.HW * 128);
+  p.ag_qk = take((size_t)p.L * 2 * B * p.HW * 256);
+  p.dg0 = take((size_t)B * 4 * p.HW * p.dd.G1);
+  p.dg1 = take((size_t)B * 16 * p.HW * p.dd.G2);
+  p.X = take((size_t)nslice * p.HW * 128);
+  if (p.pooled) {
+    p.Xp = take((size_t)nslice * p.npix * 128);
+    p.Xp2 = take((size_t)nslice * p.npix * 128);
+  }
+  p.state = take((size_t)B * p.npix * kStateFloats);
+  p.dec = take(decoder_exact_scratch_floats(p.dd, p.dec_chunk));
+  p.total = o;
+  return p;
+}
+
+struct Seg {   // RAII-less helper for per-stage event timing
+  catseg_handle* h; cudaStream_t st; bool on;
+  void begin(int stage) {
+    if (!on) return;
+    if (h->ev_used >= kMaxProfForwards * kMaxSegments) { on = false; return; }
+    size_t need = (size_t)(h->ev_used + 1) * 2;
+    while (h->ev.size() < need) { cudaEvent_t e; cudaEventCreate(&e); h->ev.push_back(e); }
+    if ((int)h->ev_stage.size() <= h->ev_used) h->ev_stage.resize(h->ev_used + 1);
+    h->ev_stage[h->ev_used] = stage;
+    cudaEventRecord(h->ev[(size_t)h->ev_used * 2], st);
+  }
+  void end() {
+    if (!on) return;
+    cudaEventRecord(h->ev[(size_t)h->ev_used * 2 + 1], st);
+    ++h->ev_used;
+  }
+};
+
+}  // namespace
+
+extern "C" int catseg_kept_classes(const catseg_handle* h, int T) {
+  if (!h || T <= 0) return -1;
+  return (h->cfg.pad_len > 0 && T > h->cfg.pad_len) ? h->cfg.pad_len : T;
+}
+
+extern "C" size_t catseg_workspace_bytes(const catseg_handle* h, int B, int T) {
+  if (!h || B <= 0 || T <= 0) return 0;
+  return make_plan(h, B, T).total * sizeof(float);
+}
+
+#define RUN(call)                                                                                           \
+  do {                                                                                                      \
+    cudaError_t _e = (call);                                                                                \
+    if (_e != cudaSuccess)                                                                                  \
+      return fail(h, CATSEG_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    ++nl;                                                                                                   \
+  } while (0)
+#define TAP(dst, src, nfloats)                                                                              \
+  do {                                                                                                      \
+    if (taps && (dst))                                                                                      \
+      CUDA_OK(h, cudaMemcpyAsync((dst), (src), (size_t)(nfloats) * sizeof(float), cudaMemcpyDeviceToDevice, st)); \
+  } while (0)
+
+extern "C" int catseg_forward_taps(catseg_handle* h, const float* img, const float* text, const float* g0,
+                                   const float* g1, const float* g2, float* logits, void* workspace,
+                                   size_t workspace_bytes, int B, int T, const catseg_taps* taps,
+                                   catseg_stream stream) {
+  if (!h) return CATSEG_ERR_INVALID;
+  if (!img || !text || !g0 || !g1 || !g2 || !logits || !workspace) return fail(h, CATSEG_ERR_INVALID, "null tensor pointer");
+  if (B <= 0 || T <= 0) return fail(h, CATSEG_ERR_INVALID, "B and T must be positive (got %d, %d)", B, T);
+  if (!h->finalized) return fail(h, CATSEG_ERR_WEIGHTS, "catseg_finalize_params has not been called");
+  if (h->cfg.text_guidance_dim != h->cfg.appearance_guidance_dim)
+    return fail(h, CATSEG_ERR_UNSUPPORTED, "img_feats channels (appearance_guidance_dim) must equal text_guidance_dim");
+  const Plan p = make_plan(h, B, T);
+  if (workspace_bytes < p.total * sizeof(float))
+    return fail(h, CATSEG_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", p.total * sizeof(float), workspace_bytes);
+  if ((long long)B * p.Te > 65535) return fail(h, CATSEG_ERR_UNSUPPORTED, "B*Te > 65535 slices per call");
+  if (T > 6144) return fail(h, CATSEG_ERR_UNSUPPORTED, "T > 6144 classes");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = reinterpret_cast<float*>(workspace);
+  const catseg_config& c = h->cfg;
+  int nl = 0;
+  Seg seg{h, st, h->profiling};
+  const int nslice = B * p.Te;
+  float* X = ws + p.X;
+  int32_t* classes = reinterpret_cast<int32_t*>(ws + p.classes);
+
+  // ---------------- PREP: cost volume, class selection, guidance projections (model.py:693-715)
+  seg.begin(CATSEG_STAGE_PREP);
+  RUN(launch_normalize_img(img, ws + p.imgn, B, p.C, p.HW, st));
+  RUN(launch_normalize_rows(text, ws + p.textn, (long long)B * T * p.P, p.Ct, st));
+  RUN(launch_cost_volume(ws + p.textn, ws + p.imgn, ws + p.corr, B, T * p.P, p.C, p.HW, st));
+  if (p.truncated) {
+    RUN(launch_class_max(ws + p.corr, ws + p.cmax, (long long)B * T, p.P * p.HW, st));
+    RUN(launch_select_classes(ws + p.cmax, classes, B, T, p.Te, st));
+  } else {
+    RUN(launch_iota_classes(classes, B, p.Te, st));
+  }
+  RUN(launch_text_mean(p.truncated ? ws + p.textn : text, classes, ws + p.tmean, B, T, p.Te, p.P, p.Ct, st));
+  RUN(launch_linear(ws + p.tmean, h->tproj_wt, h->tproj_b, ws + p.text_g, (long long)B * p.Te, 128, p.Ct, 1, st));
+  for (int l = 0; l < p.L; ++l) {
+    RUN(launch_linear(ws + p.text_g, h->cls[l].wg_qk_t, h->cls[l].bqk, ws + p.cg_qk + (size_t)l * B * p.Te * 256,
+                      (long long)B * p.Te, 256, 128, 0, st));
+    RUN(launch_class_pad_state(h->cls[l], 128, ws + p.pad_state + (size_t)l * kStateFloats, p.n_pad, p.S, st));
+  }
+  RUN(launch_conv3x3_nchw(g0, h->gproj_wt, h->gproj_b, ws + p.app_g, B, p.Cg, p.H, p.W, 128, st));
+  for (int l = 0; l < p.L; ++l) {
+    RUN(launch_layernorm128(ws + p.app_g, ws + p.app_gn, h->gnorm_g[l], h->gnorm_b[l], (long long)B * p.HW, st));
+    for (int k = 0; k < 2; ++k)
+      RUN(launch_linear(ws + p.app_gn, h->swin[l * 2 + k].wg_qk_t, h->swin[l * 2 + k].bqk,
+                        ws + p.ag_qk + (size_t)(l * 2 + k) * B * p.HW * 256, (long long)B * p.HW, 256, 128, 0, st));
+  }
+  RUN(launch_conv3x3_nchw(g1, h->dgp_wt[0], h->dgp_b[0], ws + p.dg0, B, c.decoder_guidance_dims[0], 2 * p.H, 2 * p.W,
+                          p.dd.G1, st));
+  RUN(launch_conv3x3_nchw(g2, h->dgp_wt[1], h->dgp_b[1], ws + p.dg1, B, c.decoder_guidance_dims[1], 4 * p.H, 4 * p.W,
+                          p.dd.G2, st));
+  seg.end();
+  if (taps) {
+    TAP(taps->corr, ws + p.corr, (size_t)B * T * p.P * p.HW);
+    TAP(taps->classes, ws + p.classes, (size_t)B * p.Te);
+    TAP(taps->app_guidance, ws + p.app_g, (size_t)B * p.HW * 128);
+    TAP(taps->text_guidance, ws + p.text_g, (size_t)B * p.Te * 128);
+    TAP(taps->dec_guidance0, ws + p.dg0, (size_t)B * 4 * p.HW * p.dd.G1);
+    TAP(taps->dec_guidance1, ws + p.dg1, (size_t)B * 16 * p.HW * p.dd.G2);
+  }
+
+  // ---------------- EMBED (model.py:704)
+  seg.begin(CATSEG_STAGE_EMBED);
+  RUN(launch_cost_embed(ws + p.corr, classes, h->conv1_wt, h->conv1_b, X, B, T, p.Te, p.P, p.H, p.W, st));
+  seg.end();
+  TAP(taps->embed, X, (size_t)nslice * p.HW * 128);
+
+  // ---------------- aggregation layers (model.py:717-718)
+  for (int l = 0; l < p.L; ++l) {
+    seg.begin(CATSEG_STAGE_SWIN);
+    for (int k = 0; k < 2; ++k) {
+      RUN(launch_swin_block_exact(X, ws + p.ag_qk + (size_t)(l * 2 + k) * B * p.HW * 256, nslice, p.Te,
+                                  k == 0 ? 0 : c.window_size / 2, h->swin[l * 2 + k], st));
+      if (k == 0) TAP(taps->swin_b1[l], X, (size_t)nslice * p.HW * 128);
+      else TAP(taps->swin_b2[l], X, (size_t)nslice * p.HW * 128);
+    }
+    seg.end();
+    seg.begin(CATSEG_STAGE_CLASS);
+    const float* cg = ws + p.cg_qk + (size_t)l * B * p.Te * 256;
+    const float* pad = ws + p.pad_state + (size_t)l * kStateFloats;
+    if (!p.pooled) {
+      RUN(launch_class_state_exact(X, cg, ws + p.state, B, p.Te, p.npix, p.S, h->cls[l], st));
+      RUN(launch_class_apply_exact(X, X, cg, ws + p.state, pad, B, p.Te, p.npix, p.S, 0, h->cls[l], st));
+    } else {
+      RUN(launch_avgpool_tokens(X, ws + p.Xp, nslice, p.H, p.W, c.pooling_size[0], c.pooling_size[1], st));
+      RUN(launch_class_state_exact(ws + p.Xp, cg, ws + p.state, B, p.Te, p.npix, p.S, h->cls[l], st));
+      RUN(launch_class_apply_exact(ws + p.Xp, ws + p.Xp2, cg, ws + p.state, pad, B, p.Te, p.npix, p.S, 1, h->cls[l], st));
+      RUN(launch_upsample_add(X, ws + p.Xp2, nslice, p.H, p.W, p.Hp, p.Wp, st));
+    }
+    seg.end();
+    TAP(taps->class_out[l], X, (size_t)nslice * p.HW * 128);
+  }
+
+  // ---------------- decoder + scatter (model.py:720-724)
+  seg.begin(CATSEG_STAGE_DECODER);
+  if (p.truncated) RUN(launch_fill(logits, -100.0f, (long long)B * T * 16 * p.HW, st));
+  {
+    cudaError_t e = run_decoder_exact(X, ws + p.dg0, ws + p.dg1, classes, logits, B, T, p.Te, p.dd, h->dec,
+                                      ws + p.dec, p.dec_chunk, taps ? taps->up1 : nullptr,
+                                      taps ? taps->up2 : nullptr, &nl, st);
+    if (e != cudaSuccess) return fail(h, CATSEG_ERR_CUDA, "decoder: %s", cudaGetErrorString(e));
+  }
+  seg.end();
+  if (h->profiling) ++h->prof_forwards;
+  h->last_launches = nl;
+  return CATSEG_OK;
+}
+
+extern "C" int catseg_forward(catseg_handle* h, const float* img, const float* text, const float* g0,
+                              const float* g1, const float* g2, float* logits, void* workspace,
+                              size_t workspace_bytes, int B, int T, catseg_stream stream) {
+  return catseg_forward_taps(h, img, text, g0, g1, g2, logits, workspace, workspace_bytes, B, T, nullptr, stream);
+}
+
+extern "C" int catseg_set_profiling(catseg_handle* h, int enable) {
+  if (!h) return CATSEG_ERR_INVALID;
+  h->profiling = enable != 0;
+  return CATSEG_OK;
+}
+
+extern "C" int catseg_stage_times(catseg_handle* h, float* ms, int* calls, int reset) {
+  if (!h || !ms) return CATSEG_ERR_INVALID;
+  for (int i = 0; i < CATSEG_STAGE_COUNT; ++i) ms[i] = 0.0f;
+  for (int i = 0; i < h->ev_used; ++i) {
+    CUDA_OK(h, cudaEventSynchronize(h->ev[(size_t)i * 2 + 1]));
+    float t = 0.0f;
+    CUDA_OK(h, cudaEventElapsedTime(&t, h->ev[(size_t)i * 2], h->ev[(size_t)i * 2 + 1]));
+    ms[h->ev_stage[i]] += t;
+  }
+  if (calls) *calls = h->prof_forwards;
+  if (reset) { h->ev_used = 0; h->prof_forwards = 0; }
+  return CATSEG_OK;
+}
+
+extern "C" int catseg_last_launch_count(const catseg_handle* h) { return h ? h->last_launches : 0; }
+
+extern "C" int catseg_stitch_argmax(const float* win_logits, int T, int S, int kernel, int stride, int out_res,
+                                    int height, int width, float* probs_out, int32_t* labels_out,
+                                    catseg_stream stream) {
+  if (!win_logits || T <= 0 || S <= 0 || height <= 0 || width <= 0) return CATSEG_ERR_INVALID;
+  if (!probs_out && !labels_out) return CATSEG_ERR_INVALID;
+  cudaError_t e = launch_stitch(win_logits, T, S, kernel, stride, out_res, height, width, probs_out, labels_out,
+                                (cudaStream_t)stream);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return e == cudaErrorInvalidValue ? CATSEG_ERR_INVALID : CATSEG_ERR_CUDA; }
+  return CATSEG_OK;
+}
+
+extern "C" int catseg_argmax(const float* scores, int T, int64_t npix, int32_t* labels_out, catseg_stream stream) {
+  if (!scores || !labels_out || T <= 0 || npix <= 0) return CATSEG_ERR_INVALID;
+  cudaError_t e = launch_argmax(scores, T, npix, labels_out, (cudaStream_t)stream);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return CATSEG_ERR_CUDA; }
+  return CATSEG_OK;
+}

@@ -1,0 +1,112 @@
+// Internal declarations shared by the CAT-Seg B200 translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace catseg {
+
+// Packed parameters of one Swin block (model.py:117-225).  All fp32 device pointers.
+struct SwinBlockW {
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  const float* wqkv_t;   // [128][384]  LN(x)-part of q | k | v, transposed so lanes sweep outputs
+  const float* bv;       // [128]
+  const float* wproj_t;  // [128][128]
+  const float* bproj;    // [128]
+  const float* w1_t;     // [128][512]
+  const float* b1;       // [512]
+  const float* w2_t;     // [512][128]
+  const float* b2;       // [128]
+  const float* wg_qk_t;  // [Ag][256]   guidance-part of q | k (class independent)
+  const float* bqk;      // [256]       q bias | k bias (folded into the guidance term)
+};
+
+// Packed parameters of one class-aggregation layer (model.py:357-424).
+struct ClassLayerW {
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  const float* wqkv_t;   // [128][384]
+  const float* bv;       // [128]
+  const float* wg_qk_t;  // [Tg][256]
+  const float* bqk;      // [256]
+  const float* w1_t;     // [128][512]
+  const float* b1;
+  const float* w2_t;     // [512][128]
+  const float* b2;
+  const float* pad_tok;  // [128]  padding_tokens
+  const float* pad_g;    // [Tg]   padding_guidance
+};
+
+constexpr int kStateFloats = 4 * 32 * 32 + 128;   // per (image, pixel): KV[4][32][32] then Ksum[128]
+
+// ---------------------------------------------------------------- prep.cu
+cudaError_t launch_normalize_img(const float* img, float* out, int B, int C, int HW, cudaStream_t st);
+cudaError_t launch_normalize_rows(const float* in, float* out, long long rows, int C, cudaStream_t st);
+cudaError_t launch_cost_volume(const float* textn, const float* imgn, float* corr, int B, int TP, int C, int HW,
+                               cudaStream_t st);
+cudaError_t launch_class_max(const float* corr, float* cmax, long long rows, int n, cudaStream_t st);
+cudaError_t launch_select_classes(const float* cmax, int32_t* classes, int B, int T, int Te, cudaStream_t st);
+cudaError_t launch_text_mean(const float* src, const int32_t* classes, float* out, int B, int T, int Te, int P,
+                             int C, cudaStream_t st);
+cudaError_t launch_layernorm128(const float* in, float* out, const float* g, const float* b, long long rows,
+                                cudaStream_t st);
+cudaError_t launch_linear(const float* A, const float* Wt, const float* bias, float* out, long long M, int N,
+                          int K, int relu, cudaStream_t st);
+// 3x3 conv, NCHW input -> NHWC output, + bias + ReLU (guidance projections, model.py:615-630)
+cudaError_t launch_conv3x3_nchw(const float* in, const float* Wt, const float* bias, float* out, int B, int Ci,
+                                int H, int W, int Co, cudaStream_t st);
+// 7x7 cost embedding (model.py:654-659): corr [B,T,P,HW] + classes -> X [B,Te,HW,128]
+cudaError_t launch_cost_embed(const float* corr, const int32_t* classes, const float* Wt, const float* bias,
+                              float* X, int B, int T, int Te, int P, int H, int W, cudaStream_t st);
+cudaError_t launch_transpose_pack(float* dst, int ldd, int dst_col0, const float* src, int lds, int src_col0,
+                                  int rows, int cols, cudaStream_t st);
+cudaError_t launch_fill(float* p, float v, long long n, cudaStream_t st);
+cudaError_t launch_iota_classes(int32_t* classes, int B, int Te, cudaStream_t st);
+
+// ---------------------------------------------------------------- swin_exact.cu
+cudaError_t launch_swin_block_exact(float* X, const float* ag_qk, int nslice, int Te, int shift,
+                                    const SwinBlockW& w, cudaStream_t st);
+
+// ---------------------------------------------------------------- class_exact.cu
+cudaError_t launch_class_pad_state(const ClassLayerW& w, int Tg, float* pad_state, int n_pad, int S,
+                                   cudaStream_t st);
+cudaError_t launch_class_state_exact(const float* X, const float* cg_qk, float* state, int B, int Te, int npix,
+                                     int S, const ClassLayerW& w, cudaStream_t st);
+// out_mode 0: Xout[b][t][p] = x + x_pool'   (pool 1x1: model.py:423 fused);  1: Xout = x_pool'
+cudaError_t launch_class_apply_exact(const float* X, float* Xout, const float* cg_qk, const float* state,
+                                     const float* pad_state, int B, int Te, int npix, int S, int out_mode,
+                                     const ClassLayerW& w, cudaStream_t st);
+cudaError_t launch_avgpool_tokens(const float* X, float* Xp, long long nslice, int H, int W, int ph, int pw,
+                                  cudaStream_t st);
+cudaError_t launch_upsample_add(float* X, const float* Xp, long long nslice, int H, int W, int Hp, int Wp,
+                                cudaStream_t st);
+
+// ---------------------------------------------------------------- decoder_exact.cu
+struct DecoderW {
+  const float* up1_wt;   // [128][4*96]   n = (dy*2+dx)*96 + co
+  const float* up1_b;    // [96]
+  const float* c1a_wt;   // [9*128][64]   k = tap*128 + ci
+  const float *gn1a_g, *gn1a_b;
+  const float* c1b_wt;   // [9*64][64]
+  const float *gn1b_g, *gn1b_b;
+  const float* up2_wt;   // [64][4*48]
+  const float* up2_b;
+  const float* c2a_wt;   // [9*64][32]
+  const float *gn2a_g, *gn2a_b;
+  const float* c2b_wt;   // [9*32][32]
+  const float *gn2b_g, *gn2b_b;
+  const float* head_w;   // [9][32]
+  const float* head_b;   // [1]
+};
+struct DecoderDims { int H, W, C0, U1, G1, D1, U2, G2, D2; };  // C0=128 U1=96 G1=32 D1=64 U2=48 G2=16 D2=32
+size_t decoder_exact_scratch_floats(const DecoderDims& d, int chunk);
+// X [nslice][HW][C0]; dg0 [B][4HW][G1]; dg1 [B][16HW][G2]; logits [B][T][16HW] written at class ids.
+cudaError_t run_decoder_exact(const float* X, const float* dg0, const float* dg1, const int32_t* classes,
+                              float* logits, int B, int T, int Te, const DecoderDims& d, const DecoderW& w,
+                              float* scratch, int chunk, float* tap_up1, float* tap_up2, int* launches,
+                              cudaStream_t st);
+
+// ---------------------------------------------------------------- stitch.cu
+cudaError_t launch_stitch(const float* win_logits, int T, int S, int kernel, int stride, int out_res, int height,
+                          int width, float* probs_out, int32_t* labels_out, cudaStream_t st);
+cudaError_t launch_argmax(const float* scores, int T, long long npix, int32_t* labels, cudaStream_t st);
+
+}  // namespace catseg

@@ -1,0 +1,144 @@
+/*
+ * catseg_b200.h — C ABI of the B200-native CAT-Seg cost-aggregation hot path.
+ *
+ * The reference is pure Python and has no FFI; the operator this library replaces is
+ *   Aggregator.forward(img_feats, text_feats, appearance_guidance) -> logits
+ *   (/root/reference/cat_seg/modeling/transformer/model.py:683-725), constructed at
+ *   cat_seg/modeling/transformer/cat_seg_predictor.py:97-113 and called at :161,
+ * plus the sliding-window stitch + argmax of cat_seg/cat_seg_model.py:204-218 and
+ * train_net.py:58.  A maintainer binds these entry points with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - tensors are contiguous fp32 in the reference's own layouts at the boundary:
+ *       img_feats [B,C,H,W]   text_feats [B,T,P,C]   g0 [B,Cg,H,W]  g1 [B,D0,2H,2W]  g2 [B,D1,4H,4W]
+ *       logits [B,T,4H,4W];
+ *   - the caller owns every buffer including the workspace; the handle owns only packed weights;
+ *   - calls are asynchronous on the given stream; a handle belongs to one device, one thread;
+ *   - return value 0 = OK, negative = error (catseg_last_error gives the text).  There is no CPU
+ *     fallback: unsupported configurations fail.
+ */
+#ifndef CATSEG_B200_H
+#define CATSEG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CATSEG_OK 0
+#define CATSEG_ERR_INVALID (-1)     /* bad argument / shape */
+#define CATSEG_ERR_UNSUPPORTED (-2) /* configuration outside what the kernels implement */
+#define CATSEG_ERR_WORKSPACE (-3)   /* workspace too small */
+#define CATSEG_ERR_CUDA (-4)        /* CUDA runtime / launch error */
+#define CATSEG_ERR_WEIGHTS (-5)     /* unknown / missing / mis-sized parameter */
+
+#define CATSEG_PRECISION_EXACT 0 /* fp32 CUDA-core arithmetic end to end (parity gate)        */
+#define CATSEG_PRECISION_FAST 1  /* bf16 tcgen05 operands, fp32 accumulate, fp32 residual stream */
+
+typedef struct catseg_handle catseg_handle;
+typedef void* catseg_stream; /* cudaStream_t */
+
+/* Mirrors Aggregator.__init__ kwargs (model.py:559-576). */
+typedef struct catseg_config {
+  int32_t text_guidance_dim;
+  int32_t text_guidance_proj_dim;
+  int32_t appearance_guidance_dim;
+  int32_t appearance_guidance_proj_dim;
+  int32_t decoder_dims[2];
+  int32_t decoder_guidance_dims[2];
+  int32_t decoder_guidance_proj_dims[2];
+  int32_t num_layers;
+  int32_t nheads;
+  int32_t hidden_dim;
+  int32_t pooling_size[2];
+  int32_t feature_resolution[2];
+  int32_t window_size;
+  int32_t attention_type; /* 0 = "linear"; "full" is dead code in every shipped config */
+  int32_t prompt_channel;
+  int32_t pad_len;
+  int32_t precision;      /* CATSEG_PRECISION_* */
+} catseg_config;
+
+/* Optional taps for stage-wise parity tests: any non-NULL pointer receives a copy of that stage's
+ * output in the kernels' token-major layout.  l = layer index (0..num_layers-1, at most 4). */
+typedef struct catseg_taps {
+  float* corr;           /* [B,T,P,HW]      model.py:648-652 */
+  int32_t* classes;      /* [B,Te]          kept class ids, ascending (model.py:694-696) */
+  float* embed;          /* [B,Te,HW,hid]   model.py:654-659 */
+  float* app_guidance;   /* [B,HW,Ag]       model.py:708 */
+  float* text_guidance;  /* [B,Te,Tg]       model.py:712-715 */
+  float* dec_guidance0;  /* [B,4HW,Dp0]     model.py:710 (NHWC) */
+  float* dec_guidance1;  /* [B,16HW,Dp1] */
+  float* swin_b1[4];     /* [B,Te,HW,hid]   after block_1 of layer l (model.py:250) */
+  float* swin_b2[4];     /* after block_2 (model.py:251) */
+  float* class_out[4];   /* after the class layer (model.py:494) */
+  float* up1;            /* [B,Te,4HW,dec0]  after decoder1 (model.py:677) */
+  float* up2;            /* [B,Te,16HW,dec1] after decoder2 (model.py:678) */
+} catseg_taps;
+
+/* Stage ids for catseg_stage_times */
+enum {
+  CATSEG_STAGE_PREP = 0,   /* normalise, cost volume, top-k, guidance/text projections */
+  CATSEG_STAGE_EMBED = 1,  /* 7x7 cost embedding */
+  CATSEG_STAGE_SWIN = 2,   /* all Swin blocks */
+  CATSEG_STAGE_CLASS = 3,  /* all class-attention layers */
+  CATSEG_STAGE_DECODER = 4,
+  CATSEG_STAGE_COUNT = 5
+};
+
+int catseg_create(const catseg_config* cfg, catseg_handle** out);
+int catseg_destroy(catseg_handle* h);
+const char* catseg_last_error(const catseg_handle* h); /* h may be NULL: last create error */
+
+/* Parameter table: names and sizes are exactly the reference state_dict. */
+int catseg_num_params(const catseg_handle* h);
+const char* catseg_param_name(const catseg_handle* h, int i);
+int64_t catseg_param_numel(const catseg_handle* h, int i);
+/* Copies `numel` fp32 values for parameter `name`; src may be a host or a device pointer. */
+int catseg_set_param(catseg_handle* h, const char* name, const float* src, int64_t numel, int src_is_device);
+/* Packs every parameter into kernel layouts; fails if a parameter is missing. */
+int catseg_finalize_params(catseg_handle* h, catseg_stream stream);
+
+/* Number of kept classes for T input classes: min(T, pad_len) when pad_len > 0 (model.py:694). */
+int catseg_kept_classes(const catseg_handle* h, int T);
+size_t catseg_workspace_bytes(const catseg_handle* h, int B, int T);
+
+/* The boundary call: Aggregator.forward (model.py:683-725). */
+int catseg_forward(catseg_handle* h, const float* img_feats, const float* text_feats, const float* g0,
+                   const float* g1, const float* g2, float* logits, void* workspace, size_t workspace_bytes,
+                   int B, int T, catseg_stream stream);
+/* Same, copying intermediates into `taps` (may be NULL). */
+int catseg_forward_taps(catseg_handle* h, const float* img_feats, const float* text_feats, const float* g0,
+                        const float* g1, const float* g2, float* logits, void* workspace,
+                        size_t workspace_bytes, int B, int T, const catseg_taps* taps, catseg_stream stream);
+
+/* Per-stage CUDA-event timing of catseg_forward on its own stream (for the roofline report). */
+int catseg_set_profiling(catseg_handle* h, int enable);
+/* Synchronises the recorded events; ms[CATSEG_STAGE_COUNT] = total ms per stage since the last
+ * reset, *calls = number of forwards accumulated. */
+int catseg_stage_times(catseg_handle* h, float* ms, int* calls, int reset);
+/* Number of kernel launches issued by the last catseg_forward. */
+int catseg_last_launch_count(const catseg_handle* h);
+
+/* Sliding-window stitch (cat_seg_model.py:204-218) + postprocess resize + argmax (train_net.py:58).
+ *   win_logits [nwin+1, T, S, S]: nwin tile windows in row-major tile order, then the global view.
+ *   kernel/stride/out_res as at cat_seg_model.py:158-164 (384 / 256 / 640).
+ *   probs_out (optional) [T, height, width] fp32: the 'sem_seg' tensor; labels_out (optional)
+ *   [height, width] int32: argmax over classes, first maximum wins.  No [T,kernel,kernel] or
+ *   [T,out_res,out_res] intermediate is materialised. */
+int catseg_stitch_argmax(const float* win_logits, int T, int S, int kernel, int stride, int out_res,
+                         int height, int width, float* probs_out, int32_t* labels_out,
+                         catseg_stream stream);
+/* Plain per-pixel argmax over the class axis of [T, H*W] (first maximum wins). */
+int catseg_argmax(const float* scores, int T, int64_t npix, int32_t* labels_out, catseg_stream stream);
+
+/* Library identity, e.g. "catseg_b200 0.1 sm_100a". */
+const char* catseg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CATSEG_B200_H */

@@ -1,0 +1,106 @@
+"""CPU: the C-ABI library loads and exports every declared symbol; host-side logic; loud failure without a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from helpers import ROOT, load_case
+from cat_seg_b200 import _lib
+from cat_seg_b200.aggregator import Aggregator
+from cat_seg_b200.config import vitb, vitl
+from cat_seg_b200.synth import make_state_dict, param_shapes
+from cat_seg_b200 import sliding_window as sw
+from oracle import stitch_oracle
+from oracle.ref_loader import build_reference_aggregator, reference_available
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "catseg_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(catseg_[a-z_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+    lib = _lib.load()
+    names = _header_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/catseg_b200.h but not exported"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == names
+    assert b"sm_100a" in lib.catseg_version()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    lib = _lib.load()
+    c = vitb()
+    cc = _lib.CatsegConfig(c.text_guidance_dim, 128, c.appearance_guidance_dim, 128, (C.c_int32 * 2)(64, 32),
+                           (C.c_int32 * 2)(256, 128), (C.c_int32 * 2)(32, 16), 2, 4, 128, (C.c_int32 * 2)(1, 1),
+                           (C.c_int32 * 2)(24, 24), 12, 0, 1, 256, 0)
+    h = C.c_void_p()
+    rc = lib.catseg_create(C.byref(cc), C.byref(h))
+    assert rc == -4 and not h.value
+    assert b"no CPU fallback" in lib.catseg_last_error(None)
+    m = Aggregator(**vitb().ctor_kwargs())
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        m(torch.zeros(1, 512, 24, 24), torch.zeros(1, 2, 1, 512),
+          [torch.zeros(1, 512, 24, 24), torch.zeros(1, 256, 48, 48), torch.zeros(1, 128, 96, 96)])
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        sw.stitch(torch.zeros(5, 2, 96, 96))
+
+
+def test_unsupported_configs_fail_loudly():
+    lib = _lib.load()
+    cc = _lib.CatsegConfig(512, 128, 512, 128, (C.c_int32 * 2)(64, 32), (C.c_int32 * 2)(256, 128),
+                           (C.c_int32 * 2)(32, 16), 2, 8, 64, (C.c_int32 * 2)(1, 1), (C.c_int32 * 2)(24, 24), 12, 0, 1,
+                           256, 0)
+    h = C.c_void_p()
+    assert lib.catseg_create(C.byref(cc), C.byref(h)) == -2
+    assert b"128/4" in lib.catseg_last_error(None)
+    with pytest.raises(NotImplementedError):
+        Aggregator(attention_type="full")
+
+
+@pytest.mark.parametrize("cfg", [vitb(), vitl(), vitb(prompt_channel=3, num_layers=1)])
+def test_state_dict_contract(cfg):
+    m = Aggregator(**cfg.ctor_kwargs())
+    sd = make_state_dict(cfg, 0)
+    keys = [k for k in m.state_dict() if not k.endswith("attn_mask")]
+    assert keys == list(param_shapes(cfg))
+    for k, v in m.state_dict().items():
+        if not k.endswith("attn_mask"):
+            assert tuple(v.shape) == tuple(sd[k].shape), k
+    m.load_state_dict(sd, strict=False)
+    if reference_available():
+        ref = build_reference_aggregator(cfg.ctor_kwargs())
+        m.load_state_dict(ref.state_dict(), strict=True)          # a reference checkpoint loads unchanged
+        assert set(ref.state_dict()) == set(m.state_dict())
+        for k, v in ref.state_dict().items():
+            assert torch.equal(m.state_dict()[k], v), k
+
+
+def test_sliding_window_index_logic_matches_oracle():
+    assert sw.window_stride() == 256
+    assert sw.tile_origins() == [(0, 0), (0, 256), (256, 0), (256, 256)]
+    cm = sw.count_map()
+    ref = stitch_oracle.count_map()
+    assert torch.equal(cm.float(), ref) and set(cm.unique().tolist()) == {1, 2, 4}
+    g = torch.Generator().manual_seed(0)
+    image = torch.rand(3, 500, 375, generator=g) * 255
+    a = sw.make_windows(image)
+    b = stitch_oracle.make_windows(image)
+    assert a.shape == (5, 3, 384, 384) and torch.equal(a, b)       # bit-exact tiling
+
+
+def test_stitch_oracle_properties():
+    g = torch.Generator().manual_seed(1)
+    logits = torch.randn(5, 3, 96, 96, generator=g)
+    probs, labels = stitch_oracle.stitch(logits, 640, 640)
+    assert probs.shape == (3, 640, 640) and labels.shape == (640, 640)
+    assert 0.0 <= probs.min() and probs.max() <= 1.0
+    # dropped classes (-100 logits) stitch to exactly 0
+    logits[:, 1] = -100.0
+    probs, _ = stitch_oracle.stitch(logits, 320, 480)
+    assert probs.shape == (3, 320, 480) and float(probs[1].abs().max()) == 0.0

@@ -1,0 +1,72 @@
+"""CPU: pin the oracle against fixtures generated from the unmodified reference (tools/make_golden.py)
+and, when /root/reference is present (build container only), against the live reference."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import (GOLDEN_CASES, STAGES, SUB_CH, SUB_PIX, SUB_TOK, check_inputs_match_golden, fingerprint,
+                     load_case)
+from oracle.aggregator_oracle import aggregator_forward, select_classes, shift_region_ids
+from oracle.ref_loader import build_reference_aggregator, reference_available
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_oracle_matches_reference_golden(name):
+    cfg, B, T, sd, inputs, gold = load_case(name)
+    check_inputs_match_golden(sd, inputs, gold)
+    logits, st = aggregator_forward(sd, cfg.oracle_cfg(), *inputs, return_stages=True)
+    assert tuple(logits.shape) == (B, T, 96, 96)
+    # -100 mask: exactly the classes the reference kept
+    kept = (logits[:, :, 0, 0] != -100.0).numpy()
+    assert (kept == gold["kept_mask"]).all()
+    assert bool(((logits == -100.0).reshape(B, T, -1).all(-1).numpy() == ~gold["kept_mask"]).all())
+    # tolerance: fp32 re-association only (kept-set order differs from topk(sorted=False)); measured <= 2e-6
+    np.testing.assert_allclose(logits[:, :, ::SUB_PIX, ::SUB_PIX].numpy(), gold["logits_sub"], rtol=0, atol=1e-5)
+    if "logits_full" in gold:
+        np.testing.assert_allclose(logits.numpy(), gold["logits_full"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(fingerprint(logits[torch.from_numpy(gold["kept_mask"])]), gold["logits_fp"], rtol=1e-5)
+    for s in STAGES:
+        np.testing.assert_allclose(fingerprint(st[s]), gold[s + "_fp"], rtol=1e-5, err_msg=s)
+        if s + "_sub" in gold:
+            np.testing.assert_allclose(st[s][:, :, ::SUB_TOK, ::SUB_CH].numpy(), gold[s + "_sub"], rtol=0, atol=1e-5,
+                                       err_msg=s)
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference only exists in the build container")
+@pytest.mark.parametrize("name", ["vitb_T5_B1", "vitb_T3_B2_pool2", "vitb_T9_B2_pad4"])
+def test_oracle_matches_live_reference(name):
+    cfg, B, T, sd, inputs, _ = load_case(name)
+    ref = build_reference_aggregator(cfg.ctor_kwargs(), sd)
+    with torch.no_grad():
+        y_ref = ref(*inputs)
+    y = aggregator_forward(sd, cfg.oracle_cfg(), *inputs)
+    assert bool(((y == -100.0) == (y_ref == -100.0)).all())
+    assert (y - y_ref).abs().max().item() <= 1e-5
+
+
+def test_select_classes_semantics():
+    torch.manual_seed(0)
+    corr = torch.randn(3, 11, 1, 7)
+    idx = select_classes(corr, 4)
+    score = corr.reshape(3, 11, -1).max(-1)[0]
+    ref = score.topk(4, dim=-1)[1].sort(dim=-1)[0]
+    assert (idx == ref).all()
+    assert select_classes(corr, 11) is None and select_classes(corr, 0) is None
+    # ties at the cut go to the lower class id
+    corr = torch.zeros(1, 5, 1, 2)
+    assert select_classes(corr, 2).tolist() == [[0, 1]]
+
+
+def test_shift_mask_matches_reference_buffer():
+    ids = shift_region_ids(24, 24, 12, 6)
+    assert ids.unique().numel() == 9
+    assert (ids[:12, :12] == 0).all() and (ids[12:18, 18:] == 5).all() and (ids[18:, 18:] == 8).all()
+    from cat_seg_b200.aggregator import _shift_mask
+    m = _shift_mask(24, 24, 12, 6)
+    assert m.shape == (4, 144, 144) and set(m.unique().tolist()) == {0.0, -100.0}
+    frac = [(m[w] != 0).float().mean().item() for w in range(4)]
+    np.testing.assert_allclose(frac, [0.0, 0.5, 0.5, 0.75])
+    if reference_available():
+        cfg, _, _, sd, _, _ = load_case("vitb_T5_B1")
+        ref = build_reference_aggregator(cfg.ctor_kwargs(), sd)
+        assert torch.equal(ref.layers[0].swin_block.block_2.attn_mask, m)

@@ -1,0 +1,204 @@
+// Probe: validate the hand-built tcgen05 shared-memory / instruction descriptors on a real B200 and
+// measure raw tensor throughput of (a) tcgen05.mma issue loops and (b) legacy mma.sync, to choose
+// the fast-path kernel designs.  Usage: umma_probe <test-id>   (one test per process: a bad descriptor
+// traps the context).
+//   0..7  : correctness, D[128xN] = A[128xK] * B[NxK]^T with the canonical no-swizzle layout
+//           bit0: swap LBO/SBO meaning, bit1: B is MN-major (contract over rows), bit2: A is MN-major
+//   10    : tcgen05 throughput (M=128,N=256,K=16 per instruction, long accumulate chain)
+//   11    : mma.sync m16n8k16 bf16 throughput
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include "../../cat-seg_b200/csrc/umma.cuh"
+
+using namespace catseg::umma;
+
+#define CHECK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
+
+__device__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, int iters) {
+  for (int i = 0; i < iters; ++i) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+
+// A: logical [M=128][K] row-major floats (bf16-representable); B: logical [N][K] row-major.
+// Storage in smem: canonical tiles; for MN-major variants the SAME bytes are described with swapped roles:
+//   K-major  operand X[R][K]:  byte(r, k) = (k/8)*R*16 + r*16 + (k%8)*2          (LBO = R*16, SBO = 128)
+//   MN-major operand X[R][K]:  byte(r, k) = (r/8)*K*16 + k*16 + (r%8)*2          (SBO = K*16, LBO = 128)
+__global__ void gemm_probe(const float* A, const float* B, float* D, int N, int K, int variant, int* status) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int M = 128;
+  const bool swap = variant & 1, b_mn = variant & 2, a_mn = variant & 4;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + M * K * 2;
+  int t = threadIdx.x;
+  for (int i = t; i < M * K; i += blockDim.x) {
+    int r = i / K, k = i % K;
+    uint32_t off = a_mn ? (uint32_t)((r / 8) * K * 16 + k * 16 + (r % 8) * 2)
+                        : (uint32_t)((k / 8) * M * 16 + r * 16 + (k % 8) * 2);
+    *reinterpret_cast<__nv_bfloat16*>(sA + off) = __float2bfloat16(A[i]);
+  }
+  for (int i = t; i < N * K; i += blockDim.x) {
+    int r = i / K, k = i % K;
+    uint32_t off = b_mn ? (uint32_t)((r / 8) * K * 16 + k * 16 + (r % 8) * 2)
+                        : (uint32_t)((k / 8) * N * 16 + r * 16 + (k % 8) * 2);
+    *reinterpret_cast<__nv_bfloat16*>(sB + off) = __float2bfloat16(B[i]);
+  }
+  if (t == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (t < 32) tmem_alloc<256>(&tmem_base);
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  uint32_t tm = tmem_base;
+  if (t == 0) {
+    uint32_t idesc = make_idesc_bf16(M, N, a_mn ? 1 : 0, b_mn ? 1 : 0);
+    for (int k0 = 0; k0 < K; k0 += 16) {
+      // K-major: K-chunk stride = R*16 (the "leading" offset), 8-row-group stride = 128 (the "stride" offset)
+      // MN-major: 8-row(K)-group stride = 128, MN-chunk stride = K*16
+      uint32_t a_addr, a_kdir, a_mndir, b_addr, b_kdir, b_mndir;
+      if (!a_mn) { a_addr = smem_u32(sA) + (k0 / 8) * M * 16; a_kdir = M * 16; a_mndir = 128; }
+      else       { a_addr = smem_u32(sA) + k0 * 16;           a_kdir = 128;    a_mndir = K * 16; }
+      if (!b_mn) { b_addr = smem_u32(sB) + (k0 / 8) * N * 16; b_kdir = N * 16; b_mndir = 128; }
+      else       { b_addr = smem_u32(sB) + k0 * 16;           b_kdir = 128;    b_mndir = K * 16; }
+      uint64_t da = swap ? make_smem_desc(a_addr, a_mndir, a_kdir) : make_smem_desc(a_addr, a_kdir, a_mndir);
+      uint64_t db = swap ? make_smem_desc(b_addr, b_mndir, b_kdir) : make_smem_desc(b_addr, b_kdir, b_mndir);
+      mma_bf16_ss(tm, da, db, idesc, k0 > 0);
+    }
+    mma_commit(&bar);
+  }
+  bool ok = mbar_wait_bounded(&bar, 0, 1 << 22);
+  fence_after_sync();
+  if (!ok) { if (t == 0) *status = 1; }
+  else {
+    int warp = t >> 5, lane = t & 31;
+    if (warp < 4) {
+      for (int c0 = 0; c0 < N; c0 += 16) {
+        float v[16];
+        tmem_ld16(tm + ((uint32_t)(warp * 32) << 16) + c0, v);
+        for (int j = 0; j < 16; ++j) D[(warp * 32 + lane) * N + c0 + j] = v[j];
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (t < 32) tmem_dealloc<256>(tm);
+}
+
+__global__ void tc_throughput(float* out, int iters, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  int t = threadIdx.x;
+  for (int i = t; i < (128 * 64 + 256 * 64) * 2 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (t == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (t < 32) tmem_alloc<512>(&tmem_base);
+  fence_proxy_async(); fence_before_sync(); __syncthreads(); fence_after_sync();
+  uint32_t tm = tmem_base;
+  long long t0 = clock64();
+  if (t == 0) {
+    uint32_t idesc = make_idesc_bf16(128, 256);
+    uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 128 * 64 * 2);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint64_t da = make_smem_desc(a0 + k * 2 * 128 * 16, 128 * 16, 128);
+        uint64_t db = make_smem_desc(b0 + k * 2 * 256 * 16, 256 * 16, 128);
+        mma_bf16_ss(tm + (it & 1) * 256, da, db, idesc, 1);
+      }
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  long long t1 = clock64();
+  fence_after_sync();
+  if (t == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+  float v[16];
+  if (t < 128) { tmem_ld16(tm + ((uint32_t)((t >> 5) * 32) << 16), v); if (v[0] == 12345.f) out[t] = v[0]; }
+  fence_before_sync(); __syncthreads();
+  if (t < 32) tmem_dealloc<512>(tm);
+}
+
+__global__ void mmasync_throughput(float* out, int iters, long long* cycles) {
+  float c[8][4];
+  for (int i = 0; i < 8; ++i) for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
+  uint32_t a0 = 0x3c003c00u + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, b0 = 0x3c003c00u, b1 = b0 + 5;
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                   : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                   : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
+  long long t1 = clock64();
+  float s = 0.f;
+  for (int i = 0; i < 8; ++i) for (int j = 0; j < 4; ++j) s += c[i][j];
+  if (s == 12345.f) out[threadIdx.x] = s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+
+static float bf16r(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+int main(int argc, char** argv) {
+  int id = argc > 1 ? atoi(argv[1]) : 0;
+  cudaDeviceProp prop; CHECK(cudaGetDeviceProperties(&prop, 0));
+  if (id < 8) {
+    const int M = 128, K = 64;
+    const int Ns[3] = {64, 144, 256};
+    for (int ni = 0; ni < 3; ++ni) {
+      int N = Ns[ni];
+      std::vector<float> A(M * K), B(N * K), D(M * N), R(M * N);
+      srand(1 + ni);
+      for (auto& v : A) v = bf16r((rand() % 2001 - 1000) / 1000.f);
+      for (auto& v : B) v = bf16r((rand() % 2001 - 1000) / 1000.f);
+      for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) { double s = 0; for (int k = 0; k < K; ++k) s += (double)A[m * K + k] * B[n * K + k]; R[m * N + n] = (float)s; }
+      float *dA, *dB, *dD; int* dS;
+      CHECK(cudaMalloc(&dA, A.size() * 4)); CHECK(cudaMalloc(&dB, B.size() * 4)); CHECK(cudaMalloc(&dD, D.size() * 4)); CHECK(cudaMalloc(&dS, 4));
+      CHECK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice)); CHECK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+      CHECK(cudaMemset(dD, 0, D.size() * 4)); CHECK(cudaMemset(dS, 0, 4));
+      size_t smem = (size_t)(M + N) * K * 2;
+      CHECK(cudaFuncSetAttribute(gemm_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      gemm_probe<<<1, 128, smem>>>(dA, dB, dD, N, K, id, dS);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("PROBE id=%d N=%d CUDA-ERROR %s\n", id, N, cudaGetErrorString(e)); return 3; }
+      int st; CHECK(cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost)); CHECK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+      double maxerr = 0; for (size_t i = 0; i < D.size(); ++i) maxerr = fmax(maxerr, fabs((double)D[i] - R[i]));
+      printf("PROBE id=%d swap=%d b_mn=%d a_mn=%d N=%d timeout=%d maxerr=%.5f %s\n", id, id & 1, (id >> 1) & 1, (id >> 2) & 1, N, st, maxerr,
+             (!st && maxerr < 1e-3) ? "OK" : "BAD");
+    }
+  } else {
+    float* out; long long* cyc; CHECK(cudaMalloc(&out, 4096)); CHECK(cudaMalloc(&cyc, 8));
+    int iters = 20000;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    if (id == 10) {
+      size_t smem = (128 * 64 + 256 * 64) * 2;
+      CHECK(cudaFuncSetAttribute(tc_throughput, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      tc_throughput<<<prop.multiProcessorCount, 128, smem>>>(out, 100, cyc); CHECK(cudaDeviceSynchronize());
+      cudaEventRecord(e0);
+      tc_throughput<<<prop.multiProcessorCount, 128, smem>>>(out, iters, cyc);
+      cudaEventRecord(e1); CHECK(cudaDeviceSynchronize());
+      float ms; cudaEventElapsedTime(&ms, e0, e1); long long c; CHECK(cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost));
+      double flops = 2.0 * 128 * 256 * 16 * 4 * iters * prop.multiProcessorCount;
+      printf("PROBE tcgen05 M128 N256: %.3f ms, %.1f TFLOP/s, %.1f cycles per MMA(K=16), SMs=%d\n", ms, flops / ms * 1e-9, (double)c / (4.0 * iters), prop.multiProcessorCount);
+    } else {
+      for (int warps = 4; warps <= 16; warps *= 2) {
+        mmasync_throughput<<<prop.multiProcessorCount, warps * 32>>>(out, 100, cyc); CHECK(cudaDeviceSynchronize());
+        cudaEventRecord(e0);
+        mmasync_throughput<<<prop.multiProcessorCount, warps * 32>>>(out, iters, cyc);
+        cudaEventRecord(e1); CHECK(cudaDeviceSynchronize());
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        double flops = 2.0 * 16 * 8 * 16 * 8.0 * iters * warps * prop.multiProcessorCount;
+        printf("PROBE mma.sync m16n8k16 bf16, %d warps/SM: %.3f ms, %.1f TFLOP/s\n", warps, ms, flops / ms * 1e-9);
+      }
+    }
+  }
+  return 0;
+}
