@@ -37,7 +37,21 @@ class CatsegTaps(C.Structure):
 
 
 STAGES = ("prep", "embed", "swin", "class", "decoder")
-PRECISION = {"exact": 0, "fast": 1}
+FAST_BITS = {"swin_mlp": 1, "swin_attn": 2, "class": 4, "decoder": 8}
+
+
+def precision_mask(spec: str) -> int:
+    """'exact' -> 0; 'fast' -> every stage with a tcgen05 kernel; 'fast:swin_mlp,decoder' -> those stages."""
+    if spec == "exact":
+        return 0
+    if spec == "fast":
+        return 0x7FFFFFFF
+    if spec.startswith("fast:"):
+        m = 0
+        for part in spec[5:].split(","):
+            m |= FAST_BITS[part.strip()]
+        return m
+    raise ValueError(f"bad precision {spec!r}: use 'exact', 'fast' or 'fast:<stage>[,<stage>]' with stages {sorted(FAST_BITS)}")
 
 # every symbol include/catseg_b200.h declares: (name, restype, argtypes)
 _SIGS = [

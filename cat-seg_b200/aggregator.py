@@ -52,8 +52,7 @@ class Aggregator(nn.Module):
         super().__init__()
         if attention_type != "linear":
             raise NotImplementedError("attention_type='full' is dead code in every shipped config (SURVEY.md §2.1)")
-        if precision not in _lib.PRECISION:
-            raise ValueError(f"precision must be one of {sorted(_lib.PRECISION)}")
+        _lib.precision_mask(precision)      # validates
         self.cfg = AggregatorConfig(
             text_guidance_dim=text_guidance_dim, text_guidance_proj_dim=text_guidance_proj_dim,
             appearance_guidance_dim=appearance_guidance_dim, appearance_guidance_proj_dim=appearance_guidance_proj_dim,
@@ -114,7 +113,7 @@ class Aggregator(nn.Module):
             (C.c_int32 * 2)(*c.decoder_dims), (C.c_int32 * 2)(*c.decoder_guidance_dims),
             (C.c_int32 * 2)(*c.decoder_guidance_proj_dims), c.num_layers, c.nheads, c.hidden_dim,
             (C.c_int32 * 2)(*c.pooling_size), (C.c_int32 * 2)(*c.feature_resolution), c.window_size, 0,
-            c.prompt_channel, c.pad_len, _lib.PRECISION[self.precision])
+            c.prompt_channel, c.pad_len, _lib.precision_mask(self.precision))
         h = C.c_void_p()
         with torch.cuda.device(device):
             rc = lib.catseg_create(C.byref(cc), C.byref(h))

@@ -24,6 +24,7 @@ struct Param {
 
 thread_local std::string g_create_error;
 
+constexpr int kImplementedFast = CATSEG_FAST_SWIN_MLP;   // stages that have a tcgen05 kernel in this build
 constexpr int kMaxProfForwards = 64;
 constexpr int kMaxSegments = 24;
 
@@ -36,6 +37,11 @@ struct catseg_handle {
   size_t raw_floats = 0;
   float* packed = nullptr;
   size_t packed_floats = 0;
+  __nv_bfloat16* wimg = nullptr;    // bf16 UMMA weight images (FAST path)
+  size_t wimg_elems = 0;
+  int fast_mask = 0;
+  int num_sms = 148;
+  std::vector<MlpFastW> swin_mlp_fast;   // [L*2]
   bool finalized = false;
   std::string err;
   int device = 0;
@@ -174,8 +180,7 @@ extern "C" int catseg_create(const catseg_config* cfg, catseg_handle** out) {
     return fail(nullptr, CATSEG_ERR_UNSUPPORTED, "decoder_dims must be multiples of 16 (GroupNorm groups of 16)");
   if (c.decoder_guidance_proj_dims[0] % 4 || c.decoder_guidance_proj_dims[1] % 4)
     return fail(nullptr, CATSEG_ERR_UNSUPPORTED, "decoder_guidance_proj_dims must be multiples of 4");
-  if (c.precision != CATSEG_PRECISION_EXACT)
-    return fail(nullptr, CATSEG_ERR_UNSUPPORTED, "precision %d is not available in this build", c.precision);
+  if (c.precision < 0) return fail(nullptr, CATSEG_ERR_INVALID, "precision must be 0 (exact) or a mask of CATSEG_FAST_*");
   int dev_count = 0;
   if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) {
     cudaGetLastError();
@@ -183,7 +188,9 @@ extern "C" int catseg_create(const catseg_config* cfg, catseg_handle** out) {
   }
   catseg_handle* h = new catseg_handle();
   h->cfg = c;
+  h->fast_mask = c.precision & kImplementedFast;
   cudaGetDevice(&h->device);
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
   build_param_table(h);
   if (cudaMalloc(&h->raw, h->raw_floats * sizeof(float)) != cudaSuccess) {
     delete h;
@@ -199,6 +206,7 @@ extern "C" int catseg_destroy(catseg_handle* h) {
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->raw) cudaFree(h->raw);
   if (h->packed) cudaFree(h->packed);
+  if (h->wimg) cudaFree(h->wimg);
   delete h;
   return CATSEG_OK;
 }
@@ -444,6 +452,31 @@ extern "C" int catseg_finalize_params(catseg_handle* h, catseg_stream stream) {
   Packer pk{h, st, 0, false};
   pack_all(pk);
   if (pk.err != cudaSuccess) return fail(h, CATSEG_ERR_CUDA, "packing failed: %s", cudaGetErrorString(pk.err));
+  // ---- bf16 UMMA weight images for the FAST kernels
+  if (h->fast_mask) {
+    const int L = h->cfg.num_layers;
+    size_t need = (size_t)L * 2 * 8 * 128 * 128;
+    if (!h->wimg || h->wimg_elems < need) {
+      if (h->wimg) cudaFree(h->wimg);
+      h->wimg = nullptr;
+      CUDA_OK(h, cudaMalloc(&h->wimg, need * sizeof(__nv_bfloat16)));
+      h->wimg_elems = need;
+    }
+    h->swin_mlp_fast.assign(L * 2, MlpFastW{});
+    char b[160];
+    for (int l = 0; l < L; ++l)
+      for (int k = 0; k < 2; ++k) {
+        snprintf(b, sizeof(b), "layers.%d.swin_block.block_%d", l, k + 1);
+        std::string q(b);
+        __nv_bfloat16* img = h->wimg + (size_t)(l * 2 + k) * 8 * 128 * 128;
+        for (int j = 0; j < 4; ++j) {
+          CUDA_OK(h, launch_pack_wimg(img + (size_t)(2 * j) * 128 * 128, raw_of(h, q + ".mlp.fc1.weight"), 128, j * 128, 0, st));
+          CUDA_OK(h, launch_pack_wimg(img + (size_t)(2 * j + 1) * 128 * 128, raw_of(h, q + ".mlp.fc2.weight"), 512, 0, j * 128, st));
+        }
+        const SwinBlockW& sw = h->swin[l * 2 + k];
+        h->swin_mlp_fast[l * 2 + k] = MlpFastW{img, sw.ln2_g, sw.ln2_b, sw.b1, sw.b2};
+      }
+  }
   CUDA_OK(h, cudaStreamSynchronize(st));
   h->finalized = true;
   return CATSEG_OK;
@@ -622,8 +655,11 @@ extern "C" int catseg_forward_taps(catseg_handle* h, const float* img, const flo
   for (int l = 0; l < p.L; ++l) {
     seg.begin(CATSEG_STAGE_SWIN);
     for (int k = 0; k < 2; ++k) {
+      const bool mlp_fast = (h->fast_mask & CATSEG_FAST_SWIN_MLP) != 0;
       RUN(launch_swin_block_exact(X, ws + p.ag_qk + (size_t)(l * 2 + k) * B * p.HW * 256, nslice, p.Te,
-                                  k == 0 ? 0 : c.window_size / 2, h->swin[l * 2 + k], st));
+                                  k == 0 ? 0 : c.window_size / 2, h->swin[l * 2 + k], mlp_fast ? 0 : 1, st));
+      if (mlp_fast)
+        RUN(launch_mlp_fast(X, (long long)nslice * p.HW, h->swin_mlp_fast[l * 2 + k], 0, h->num_sms, st));
       if (k == 0) TAP(taps->swin_b1[l], X, (size_t)nslice * p.HW * 128);
       else TAP(taps->swin_b2[l], X, (size_t)nslice * p.HW * 128);
     }

@@ -1,0 +1,75 @@
+// Building blocks shared by the FAST (bf16 tcgen05, fp32 accumulate) kernels.
+//
+// Conventions
+//   * A "token tile" is 128 rows (tokens) x 128 features.  For the epilogues one thread owns one row:
+//     warp w of a CTA may only touch TMEM lanes 32*(w%4)..+31, so warps w and w+4 share rows and
+//     split the columns.
+//   * bf16 UMMA operands live in shared memory in the canonical no-swizzle K-major layout of
+//     umma.cuh.  Tiles written by threads use a PADDED chunk stride (LBO_T = rows*16 + 16) so that
+//     the 8-byte stores of the warp-per-row LayerNorm prologue are bank-conflict free; weight
+//     images are pre-packed in global memory with the dense stride and arrive by bulk (TMA) copy.
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace catseg {
+namespace fast {
+
+constexpr int TILE = 128;                       // rows per UMMA M tile
+constexpr uint32_t LBO_W = 128 * 16;            // weight images: 128 rows, dense
+constexpr uint32_t LBO_T = 128 * 16 + 16;       // thread-written 128-row tiles, padded
+constexpr uint32_t TILE_BYTES_T = 16 * LBO_T;   // 128 features = 16 chunks
+constexpr uint32_t WIMG_BYTES = 16 * LBO_W;     // one 128x128 bf16 weight image = 32 KiB
+constexpr uint32_t IDESC_128x128 = umma::make_idesc_bf16(128, 128);
+
+// 8 k-steps of a [128 x 128] x [N=128 x 128]^T GEMM; A/B are shared-memory byte addresses
+__device__ __forceinline__ void issue_gemm_k128(uint32_t d_tmem, uint32_t a_addr, uint32_t lbo_a, uint32_t b_addr,
+                                                uint32_t lbo_b, uint32_t idesc, bool acc_first) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    uint64_t da = umma::make_smem_desc(a_addr + k * 2 * lbo_a, lbo_a, 128);
+    uint64_t db = umma::make_smem_desc(b_addr + k * 2 * lbo_b, lbo_b, 128);
+    umma::mma_bf16_ss(d_tmem, da, db, idesc, (k > 0 || acc_first) ? 1u : 0u);
+  }
+}
+
+// LayerNorm(128) of `nrows` token rows (row i at src + i*row_stride floats), written as bf16 into a
+// canonical 128-row tile.  Warp-per-row: coalesced 512-byte loads, shuffle reductions.  Rows
+// >= nvalid are zero-filled.  Called by all `nwarps` warps of the CTA.
+__device__ __forceinline__ void ln_rows_to_tile(const float* __restrict__ src, long long row_stride, int nvalid,
+                                                uint8_t* tile, const float* __restrict__ gamma,
+                                                const float* __restrict__ beta, int warp, int nwarps, int lane) {
+  const float4 g = ld4(gamma + lane * 4), be = ld4(beta + lane * 4);
+  for (int r0 = warp * 4; r0 < TILE; r0 += nwarps * 4) {
+    float4 x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int r = r0 + i;
+      x[i] = (r < nvalid) ? ld4(src + (long long)r * row_stride + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int r = r0 + i;
+      float4 y = warp_layernorm128(x[i], g, be);
+      if (r >= nvalid) y = make_float4(0.f, 0.f, 0.f, 0.f);
+      uint2 p = make_uint2(umma::pack_bf16x2(y.x, y.y), umma::pack_bf16x2(y.z, y.w));
+      *reinterpret_cast<uint2*>(tile + (lane >> 1) * LBO_T + r * 16 + (lane & 1) * 8) = p;
+    }
+  }
+}
+
+// Cheap erf-GELU for the bf16 path: the result is rounded to bf16 (rel. 2^-9) before the next MMA,
+// so erf only needs ~1e-5 absolute accuracy.  Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7):
+//   erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2),  t = 1 / (1 + p z),  z >= 0
+__device__ __forceinline__ float gelu_fast(float x) {
+  float z = fabsf(x) * 0.70710678118654752440f;
+  float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t,
+                    0.254829592f) * t;
+  float e = poly * __expf(-z * z);          // 1 - erf(z)
+  float cdf = x >= 0.0f ? 1.0f - 0.5f * e : 0.5f * e;
+  return x * cdf;
+}
+
+}  // namespace fast
+}  // namespace catseg

@@ -1,0 +1,208 @@
+// FAST token-wise MLP block on tcgen05:  X[row] += fc2(act(fc1(LayerNorm(X[row]))))   (in place)
+//
+// Reference: the FFN half of SwinTransformerBlock.forward (model.py:223, Mlp 128->512 GELU ->128).
+// Persistent CTAs; each pass handles 256 token rows (two 128-row UMMA tiles) so that the 256 KiB of
+// bf16 weights, streamed from L2 through a 3-slot ring of 32 KiB bulk (TMA) copies, are fetched
+// once per 256 tokens.  Per hidden chunk j (128 of the 512 hidden units) and tile t:
+//   MMA1: H_t = LN(x_t) W1_j^T   -> TMEM          (8 x tcgen05.mma M128 N128 K16)
+//   epilogue: TMEM -> +b1 -> GELU -> bf16 -> shared memory (canonical K-major A operand)
+//   MMA2: Y_t += h W2_j^T        -> TMEM
+// and finally Y_t + b2 + x -> global.  TMEM: H_a H_b Y_a Y_b = 4 x 128 columns.
+#include "fast_common.cuh"
+#include "internal.h"
+
+namespace catseg {
+
+using namespace fast;
+
+namespace {
+constexpr int MLP_THREADS = 256;
+constexpr uint32_t SM_RING = 0;                                   // 3 x 32 KiB weight ring
+constexpr uint32_t SM_XN = SM_RING + 3 * WIMG_BYTES;              // 2 tiles LN(x) bf16
+constexpr uint32_t SM_H = SM_XN + 2 * TILE_BYTES_T;               // hidden chunk bf16
+constexpr uint32_t SM_PAR = SM_H + TILE_BYTES_T;                  // b1[512] b2[128] g[128] b[128] floats
+constexpr uint32_t SM_BAR = SM_PAR + (512 + 128 + 128 + 128) * 4; // 7 mbarriers + tmem ptr
+constexpr uint32_t MLP_SMEM = SM_BAR + 8 * 8 + 16;
+}  // namespace
+
+template <int ACT>   // 0 = GELU (Swin), 1 = ReLU (class layer)
+__global__ void __launch_bounds__(MLP_THREADS, 1)
+mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + SM_BAR);       // [3]
+  uint64_t* bar_mma = bar_full + 3;                                       // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 4);
+  float* s_b1 = reinterpret_cast<float*>(smem + SM_PAR);
+  float* s_b2 = s_b1 + 512;
+  float* s_g = s_b2 + 128;
+  float* s_be = s_g + 128;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  const long long npass = (ntok + 255) / 256;
+  long long my_pass = 0;
+  for (long long p = blockIdx.x; p < npass; p += gridDim.x) ++my_pass;
+  const long long total_loads = my_pass * 8;
+
+  for (int i = tid; i < 512; i += MLP_THREADS) s_b1[i] = w.b1[i];
+  if (tid < 128) { s_b2[tid] = w.b2[tid]; s_g[tid] = w.ln_g[tid]; s_be[tid] = w.ln_b[tid]; }
+  if (tid == 0) {
+    for (int i = 0; i < 3; ++i) umma::mbar_init(&bar_full[i], 1);
+    for (int i = 0; i < 4; ++i) umma::mbar_init(&bar_mma[i], 1);
+    umma::mbar_fence_init();
+  }
+  if (warp == 0) umma::tmem_alloc<512>(tmem_slot);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tm = *tmem_slot;
+  const uint32_t smem_base = umma::smem_u32(smem);
+
+  auto issue_load = [&](long long n) {   // thread 0 only
+    if (n < total_loads) {
+      int s = (int)(n % 3);
+      umma::mbar_expect_tx(&bar_full[s], WIMG_BYTES);
+      umma::bulk_g2s(smem + SM_RING + s * WIMG_BYTES, reinterpret_cast<const uint8_t*>(w.wimg) + (n % 8) * WIMG_BYTES,
+                     WIMG_BYTES, &bar_full[s]);
+    }
+  };
+  if (tid == 0) { issue_load(0); issue_load(1); issue_load(2); }
+
+  const int q = warp & 3, half = warp >> 2;
+  const int row = q * 32 + lane;                         // row of the tile owned by this thread
+  const uint32_t lane_addr = tm + ((uint32_t)(q * 32) << 16);
+  long long g = 0;                                       // running hidden-chunk counter of this CTA
+
+  for (long long p = blockIdx.x; p < npass; p += gridDim.x) {
+    const long long row0 = p * 256;
+    // ---- LN prologue: two tiles
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      long long r0 = row0 + t * 128;
+      long long nv = ntok - r0;
+      int nvalid = nv >= 128 ? 128 : (nv > 0 ? (int)nv : 0);
+      ln_rows_to_tile(X + r0 * 128, 128, nvalid, smem + SM_XN + t * TILE_BYTES_T, s_g, s_be, warp, MLP_THREADS / 32, lane);
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+
+    for (int j = 0; j < 4; ++j, ++g) {
+      const uint32_t par = (uint32_t)(g & 1);
+      if (tid == 0) {
+        umma::fence_after_sync();
+        long long n = 2 * g;
+        umma::mbar_wait(&bar_full[n % 3], (uint32_t)((n / 3) & 1));
+        uint32_t wb = smem_base + SM_RING + (uint32_t)(n % 3) * WIMG_BYTES;
+        issue_gemm_k128(tm + 0, smem_base + SM_XN, LBO_T, wb, LBO_W, IDESC_128x128, false);
+        umma::mma_commit(&bar_mma[0]);
+        issue_gemm_k128(tm + 128, smem_base + SM_XN + TILE_BYTES_T, LBO_T, wb, LBO_W, IDESC_128x128, false);
+        umma::mma_commit(&bar_mma[1]);
+      }
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        umma::mbar_wait(&bar_mma[t], par);                 // H_t ready
+        umma::fence_after_sync();
+        if (t == 1 && tid == 0) issue_load(2 * g + 3);     // MMA1(b) done: the W1_j slot is free
+        // ---- H_t -> bias -> act -> bf16 (64 columns per thread)
+        uint4 packed[8];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          float v[32];
+          umma::tmem_ld32(lane_addr + t * 128 + half * 64 + cc * 32, v);
+          const float* bb = s_b1 + j * 128 + half * 64 + cc * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float a = v[i] + bb[i];
+            v[i] = ACT == 0 ? gelu_fast(a) : fmaxf(a, 0.0f);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            packed[cc * 4 + c] = make_uint4(umma::pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]), umma::pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
+                                            umma::pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), umma::pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]));
+        }
+        // ---- the h buffer is free once the previous MMA2 has completed
+        if (t == 0) {
+          if (j > 0) {
+            umma::mbar_wait(&bar_mma[3], (uint32_t)((g - 1) & 1));
+            if (tid == 0) issue_load(2 * g + 2);           // MMA2(b) of chunk g-1 done: its W2 slot is free
+          }
+        } else {
+          umma::mbar_wait(&bar_mma[2], par);
+        }
+        umma::fence_after_sync();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(smem + SM_H + (half * 8 + c) * LBO_T + row * 16) = packed[c];
+        umma::fence_proxy_async();
+        umma::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+          umma::fence_after_sync();
+          long long n = 2 * g + 1;
+          umma::mbar_wait(&bar_full[n % 3], (uint32_t)((n / 3) & 1));
+          uint32_t wb = smem_base + SM_RING + (uint32_t)(n % 3) * WIMG_BYTES;
+          issue_gemm_k128(tm + 256 + t * 128, smem_base + SM_H, LBO_T, wb, LBO_W, IDESC_128x128, j > 0);
+          umma::mma_commit(&bar_mma[2 + t]);
+        }
+      }
+    }
+    // ---- all MMAs of this pass done -> Y epilogue
+    umma::mbar_wait(&bar_mma[3], (uint32_t)((g - 1) & 1));
+    umma::fence_after_sync();
+    if (tid == 0) issue_load(2 * g + 2);
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t) {
+      long long r = row0 + t * 128 + row;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        float v[32];
+        umma::tmem_ld32(lane_addr + 256 + t * 128 + half * 64 + cc * 32, v);
+        if (r < ntok) {
+          float* xp = X + r * 128 + half * 64 + cc * 32;
+          const float* bb = s_b2 + half * 64 + cc * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 x = ld4(xp + i);
+            st4(xp + i, make_float4(x.x + (v[i] + bb[i]), x.y + (v[i + 1] + bb[i + 1]), x.z + (v[i + 2] + bb[i + 2]),
+                                    x.w + (v[i + 3] + bb[i + 3])));
+          }
+        }
+      }
+    }
+    umma::fence_before_sync();
+    __syncthreads();          // TMEM and the LN tiles may be overwritten by the next pass
+    umma::fence_after_sync();
+  }
+  if (warp == 0) umma::tmem_dealloc<512>(tm);
+}
+
+cudaError_t launch_mlp_fast(float* X, long long ntok, const MlpFastW& w, int act, int num_sms, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(mlp_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  long long npass = (ntok + 255) / 256;
+  int grid = (int)(npass < num_sms ? npass : num_sms);
+  if (grid <= 0) return cudaSuccess;
+  if (act == 0) mlp_fast_kernel<0><<<grid, MLP_THREADS, MLP_SMEM, st>>>(X, ntok, w);
+  else mlp_fast_kernel<1><<<grid, MLP_THREADS, MLP_SMEM, st>>>(X, ntok, w);
+  return cudaGetLastError();
+}
+
+// ---- weight image packing: dst image (bf16, canonical dense 128x128) <- W[r0 + r][c0 + k], ld = row stride
+__global__ void pack_wimg_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ W, int ld, int r0, int c0) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 128 * 128) return;
+  int r = i >> 7, k = i & 127;
+  dst[(k >> 3) * (128 * 8) + r * 8 + (k & 7)] = __float2bfloat16(W[(long long)(r0 + r) * ld + c0 + k]);
+}
+cudaError_t launch_pack_wimg(__nv_bfloat16* dst, const float* W, int ld, int r0, int c0, cudaStream_t st) {
+  pack_wimg_kernel<<<64, 256, 0, st>>>(dst, W, ld, r0, c0);
+  return cudaGetLastError();
+}
+
+}  // namespace catseg

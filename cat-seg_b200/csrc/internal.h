@@ -1,5 +1,6 @@
 // Internal declarations shared by the CAT-Seg B200 translation units (not part of the C ABI).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -35,6 +36,13 @@ struct ClassLayerW {
   const float* pad_g;    // [Tg]   padding_guidance
 };
 
+// FAST path: bf16 weight images for the token MLP (fast_mlp.cu).  wimg = 8 canonical 128x128 images
+// in ring order W1_0, W2_0, W1_1, W2_1, ... (hidden chunks of 128).
+struct MlpFastW {
+  const __nv_bfloat16* wimg;
+  const float *ln_g, *ln_b, *b1, *b2;
+};
+
 constexpr int kStateFloats = 4 * 32 * 32 + 128;   // per (image, pixel): KV[4][32][32] then Ksum[128]
 
 // ---------------------------------------------------------------- prep.cu
@@ -62,8 +70,13 @@ cudaError_t launch_fill(float* p, float v, long long n, cudaStream_t st);
 cudaError_t launch_iota_classes(int32_t* classes, int B, int Te, cudaStream_t st);
 
 // ---------------------------------------------------------------- swin_exact.cu
+// with_mlp = 0 stops after x1 = shortcut + proj(attn) (the FFN half then runs in fast_mlp.cu)
 cudaError_t launch_swin_block_exact(float* X, const float* ag_qk, int nslice, int Te, int shift,
-                                    const SwinBlockW& w, cudaStream_t st);
+                                    const SwinBlockW& w, int with_mlp, cudaStream_t st);
+
+// ---------------------------------------------------------------- fast_mlp.cu
+cudaError_t launch_mlp_fast(float* X, long long ntok, const MlpFastW& w, int act, int num_sms, cudaStream_t st);
+cudaError_t launch_pack_wimg(__nv_bfloat16* dst, const float* W, int ld, int r0, int c0, cudaStream_t st);
 
 // ---------------------------------------------------------------- class_exact.cu
 cudaError_t launch_class_pad_state(const ClassLayerW& w, int Tg, float* pad_state, int n_pad, int S,

@@ -24,6 +24,7 @@ constexpr int SM_UNION = (SM_QKV + SM_O) > (NWARP * TPW * 128) ? (SM_QKV + SM_O)
 constexpr size_t SWIN_SMEM = (size_t)(SM_BUFA + SM_UNION) * 4 + NTOK * 2 * sizeof(int);
 }  // namespace
 
+template <bool WITH_MLP>
 __global__ void __launch_bounds__(512, 1)
 swin_block_exact_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, int Te, int shift, SwinBlockW w) {
   extern __shared__ __align__(16) float smem[];
@@ -199,6 +200,7 @@ swin_block_exact_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, 
       st4(bufA + li * 128 + lane * 4, warp_layernorm128(x1, g, be));
     }
   }
+  if (!WITH_MLP) return;
   __syncwarp();
 
   // ---- MLP 128 -> 512 (GELU) -> 128 in four hidden chunks of 128
@@ -267,15 +269,19 @@ swin_block_exact_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, 
 }
 
 cudaError_t launch_swin_block_exact(float* X, const float* ag_qk, int nslice, int Te, int shift,
-                                    const SwinBlockW& w, cudaStream_t st) {
+                                    const SwinBlockW& w, int with_mlp, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(swin_block_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(swin_block_exact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)SWIN_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(swin_block_exact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SWIN_SMEM);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  swin_block_exact_kernel<<<nslice * 4, 512, SWIN_SMEM, st>>>(X, ag_qk, Te, shift, w);
+  if (with_mlp) swin_block_exact_kernel<true><<<nslice * 4, 512, SWIN_SMEM, st>>>(X, ag_qk, Te, shift, w);
+  else swin_block_exact_kernel<false><<<nslice * 4, 512, SWIN_SMEM, st>>>(X, ag_qk, Te, shift, w);
   return cudaGetLastError();
 }
 

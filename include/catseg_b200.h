@@ -35,8 +35,15 @@ extern "C" {
 #define CATSEG_ERR_CUDA (-4)        /* CUDA runtime / launch error */
 #define CATSEG_ERR_WEIGHTS (-5)     /* unknown / missing / mis-sized parameter */
 
-#define CATSEG_PRECISION_EXACT 0 /* fp32 CUDA-core arithmetic end to end (parity gate)        */
-#define CATSEG_PRECISION_FAST 1  /* bf16 tcgen05 operands, fp32 accumulate, fp32 residual stream */
+/* precision: 0 = EXACT (fp32 CUDA-core arithmetic end to end: the parity gate); otherwise a bit mask
+ * of the stages that run on the FAST path (bf16 tcgen05 operands, fp32 accumulate, fp32 residual
+ * stream).  CATSEG_PRECISION_FAST selects every stage that has a fast kernel. */
+#define CATSEG_PRECISION_EXACT 0
+#define CATSEG_FAST_SWIN_MLP 1   /* FFN half of the Swin blocks */
+#define CATSEG_FAST_SWIN_ATTN 2  /* window-attention half of the Swin blocks */
+#define CATSEG_FAST_CLASS 4      /* class-aggregation layers */
+#define CATSEG_FAST_DECODER 8    /* upsampling decoder */
+#define CATSEG_PRECISION_FAST 0x7fffffff
 
 typedef struct catseg_handle catseg_handle;
 typedef void* catseg_stream; /* cudaStream_t */

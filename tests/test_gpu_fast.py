@@ -1,0 +1,48 @@
+"""GPU (-m gpu): the FAST path (bf16 tcgen05 operands, fp32 accumulate, fp32 residual stream).
+
+Stated bf16 tolerance (north_star): logits max-abs <= 6e-2 and rel-L2 <= 3e-2 against the fp32 oracle with the
+synthetic weights of cat_seg_b200.synth; the -100 mask must be exactly equal; argmax agreement on pixels whose
+oracle margin exceeds 2x the max error must be 100 % (SURVEY.md §0.9 explains why raw agreement cannot reach
+99.9 % with bf16 operands on random-init weights — the EXACT path is the 99.9 % gate)."""
+import pytest
+import torch
+
+from helpers import argmax_agreement, rel_l2
+from cat_seg_b200.aggregator import Aggregator
+from cat_seg_b200.config import vitb, vitl
+from cat_seg_b200.synth import make_inputs, make_state_dict
+from oracle.aggregator_oracle import aggregator_forward
+
+pytestmark = pytest.mark.gpu
+FAST_MAXABS, FAST_RELL2 = 6e-2, 3e-2
+
+
+def _run(cfg, B, T, seed, precision, same_text=False):
+    sd = make_state_dict(cfg, seed)
+    img, text, g = make_inputs(cfg, B, T, seed, same_text=same_text)
+    m = Aggregator(**cfg.ctor_kwargs(), precision=precision)
+    m.load_state_dict(sd, strict=False)
+    y = m.cuda()(img.cuda(), text.cuda(), [x.cuda() for x in g]).cpu()
+    ref = aggregator_forward(sd, cfg.oracle_cfg(), img, text, g)
+    return y, ref
+
+
+@pytest.mark.parametrize("precision", ["fast:swin_mlp", "fast:swin_attn", "fast:class", "fast:decoder", "fast"])
+@pytest.mark.parametrize("case", [(vitb(), 2, 5), (vitb(pooling_size=(2, 2)), 1, 3), (vitb(pad_len=4), 1, 9)])
+def test_fast_matches_oracle_within_bf16_tolerance(precision, case):
+    cfg, B, T = case
+    y, ref = _run(cfg, B, T, 21, precision)
+    assert bool(((y == -100.0) == (ref == -100.0)).all())
+    kept = ref != -100.0
+    raw, filt, frac, err = argmax_agreement(y, ref)
+    assert err <= FAST_MAXABS and rel_l2(y[kept], ref[kept]) <= FAST_RELL2, (precision, err, rel_l2(y[kept], ref[kept]))
+    assert filt == 1.0, (raw, filt, frac)
+
+
+def test_fast_large_tile_counts():
+    """More token rows than one persistent wave: exercises the ring/parity logic across many passes."""
+    cfg = vitl()
+    y, ref = _run(cfg, 1, 300, 4, "fast", same_text=True)
+    assert bool(((y == -100.0) == (ref == -100.0)).all())
+    kept = ref != -100.0
+    assert (y[kept] - ref[kept]).abs().max().item() <= FAST_MAXABS and rel_l2(y[kept], ref[kept]) <= FAST_RELL2
