@@ -24,7 +24,7 @@ struct Param {
 
 thread_local std::string g_create_error;
 
-constexpr int kImplementedFast = CATSEG_FAST_SWIN_MLP;   // stages that have a tcgen05 kernel in this build
+constexpr int kImplementedFast = CATSEG_FAST_SWIN_MLP | CATSEG_FAST_SWIN_ATTN;   // stages that have a tcgen05 kernel in this build
 constexpr int kMaxProfForwards = 64;
 constexpr int kMaxSegments = 24;
 
@@ -42,6 +42,7 @@ struct catseg_handle {
   int fast_mask = 0;
   int num_sms = 148;
   std::vector<MlpFastW> swin_mlp_fast;   // [L*2]
+  std::vector<SwinAttnFastW> swin_attn_fast;   // [L*2]
   bool finalized = false;
   std::string err;
   int device = 0;
@@ -455,7 +456,8 @@ extern "C" int catseg_finalize_params(catseg_handle* h, catseg_stream stream) {
   // ---- bf16 UMMA weight images for the FAST kernels
   if (h->fast_mask) {
     const int L = h->cfg.num_layers;
-    size_t need = (size_t)L * 2 * 8 * 128 * 128;
+    const size_t kImg = 128 * 128;
+    size_t need = (size_t)L * 2 * (8 + 5) * kImg;
     if (!h->wimg || h->wimg_elems < need) {
       if (h->wimg) cudaFree(h->wimg);
       h->wimg = nullptr;
@@ -463,18 +465,27 @@ extern "C" int catseg_finalize_params(catseg_handle* h, catseg_stream stream) {
       h->wimg_elems = need;
     }
     h->swin_mlp_fast.assign(L * 2, MlpFastW{});
+    h->swin_attn_fast.assign(L * 2, SwinAttnFastW{});
+    const int ag = h->cfg.appearance_guidance_proj_dim;
     char b[160];
     for (int l = 0; l < L; ++l)
       for (int k = 0; k < 2; ++k) {
         snprintf(b, sizeof(b), "layers.%d.swin_block.block_%d", l, k + 1);
         std::string q(b);
-        __nv_bfloat16* img = h->wimg + (size_t)(l * 2 + k) * 8 * 128 * 128;
+        __nv_bfloat16* img = h->wimg + (size_t)(l * 2 + k) * 13 * kImg;
         for (int j = 0; j < 4; ++j) {
           CUDA_OK(h, launch_pack_wimg(img + (size_t)(2 * j) * 128 * 128, raw_of(h, q + ".mlp.fc1.weight"), 128, j * 128, 0, st));
           CUDA_OK(h, launch_pack_wimg(img + (size_t)(2 * j + 1) * 128 * 128, raw_of(h, q + ".mlp.fc2.weight"), 512, 0, j * 128, st));
         }
         const SwinBlockW& sw = h->swin[l * 2 + k];
         h->swin_mlp_fast[l * 2 + k] = MlpFastW{img, sw.ln2_g, sw.ln2_b, sw.b1, sw.b2};
+        __nv_bfloat16* aimg = img + 8 * kImg;
+        for (int hh = 0; hh < 4; ++hh)
+          CUDA_OK(h, launch_pack_qkv_head_img(aimg + (size_t)hh * kImg, raw_of(h, q + ".attn.q.weight"),
+                                              raw_of(h, q + ".attn.k.weight"), raw_of(h, q + ".attn.v.weight"),
+                                              128 + ag, hh, st));
+        CUDA_OK(h, launch_pack_wimg(aimg + 4 * kImg, raw_of(h, q + ".attn.proj.weight"), 128, 0, 0, st));
+        h->swin_attn_fast[l * 2 + k] = SwinAttnFastW{aimg, sw.ln1_g, sw.ln1_b, sw.bv, sw.bproj};
       }
   }
   CUDA_OK(h, cudaStreamSynchronize(st));
@@ -655,9 +666,12 @@ extern "C" int catseg_forward_taps(catseg_handle* h, const float* img, const flo
   for (int l = 0; l < p.L; ++l) {
     seg.begin(CATSEG_STAGE_SWIN);
     for (int k = 0; k < 2; ++k) {
-      const bool mlp_fast = (h->fast_mask & CATSEG_FAST_SWIN_MLP) != 0;
-      RUN(launch_swin_block_exact(X, ws + p.ag_qk + (size_t)(l * 2 + k) * B * p.HW * 256, nslice, p.Te,
-                                  k == 0 ? 0 : c.window_size / 2, h->swin[l * 2 + k], mlp_fast ? 0 : 1, st));
+      const bool attn_fast = (h->fast_mask & CATSEG_FAST_SWIN_ATTN) != 0;
+      const bool mlp_fast = attn_fast || (h->fast_mask & CATSEG_FAST_SWIN_MLP) != 0;
+      const float* agk = ws + p.ag_qk + (size_t)(l * 2 + k) * B * p.HW * 256;
+      const int shift = k == 0 ? 0 : c.window_size / 2;
+      if (attn_fast) RUN(launch_swin_attn_fast(X, agk, nslice, p.Te, shift, h->swin_attn_fast[l * 2 + k], h->num_sms, st));
+      else RUN(launch_swin_block_exact(X, agk, nslice, p.Te, shift, h->swin[l * 2 + k], mlp_fast ? 0 : 1, st));
       if (mlp_fast)
         RUN(launch_mlp_fast(X, (long long)nslice * p.HW, h->swin_mlp_fast[l * 2 + k], 0, h->num_sms, st));
       if (k == 0) TAP(taps->swin_b1[l], X, (size_t)nslice * p.HW * 128);

@@ -1,0 +1,335 @@
+// FAST window-attention half of the Swin block on tcgen05 (one 12x12 window = 144 tokens per pass):
+//   x1 = x + proj( softmax( (LN1(x) Wq^T + gq) s (LN1(x) Wk^T + gk)^T + mask ) (LN1(x) Wv^T + bv) )
+// Reference: SwinTransformerBlock.forward (model.py:185-222), WindowAttention.forward (:86-114).
+//
+// Orientation.  Token-wise GEMMs are computed TRANSPOSED (features on the UMMA M axis, the 144
+// window tokens on the N axis) so the 144-token window needs no M padding:
+//   per head h :  [q_h; k_h; v_h; 0]^T (128 x 144) = Wqkv_h (128 x 128) . LN1(x)^T        8 MMAs N=144
+//   the TMEM rows of q_h/k_h/v_h are read by "feature" threads and stored as [token-group][d][8 tok]
+//   images, which are simultaneously the MN-major A/B operands of  S = Q K^T  (M = queries: 2 tiles,
+//   the second holds only 16 valid rows) and the K-major B operand of  O = P V.
+//   softmax runs with two threads per query row (72 keys each), P goes back to shared memory as the
+//   K-major A operand, O_h (TMEM) is normalised and stored into the [token][128] image that is the
+//   B operand of the transposed projection  Y^T (128 x 144) = Wp . O^T.
+// The guidance half of q/k (class independent, biases included) is gathered from ag_qk.
+// Weights stream from L2 through a 2-slot ring of 32 KiB bulk (TMA) copies (5 images per window).
+// TMEM columns: [0,144) QKV_h^T / Y^T   [160,304) S tile 0   [304,448) S tile 1   [448,512) O_h tiles.
+#include "fast_common.cuh"
+#include "internal.h"
+
+namespace catseg {
+
+using namespace fast;
+
+namespace {
+constexpr int SA_THREADS = 256;
+constexpr int NTOK = 144, WIN = 12, GRID = 24;
+constexpr uint32_t LBO_X = NTOK * 16 + 16;                 // 2320: thread-written 144-row K-major tiles
+constexpr uint32_t SM_RING = 0;                            // 2 x 32 KiB
+constexpr uint32_t SM_XN = SM_RING + 2 * WIMG_BYTES;       // LN1(x): [144 tok x 128] K-major   16 chunks
+constexpr uint32_t SM_QH = SM_XN + 16 * LBO_X;             // q_h image  [18][32][8] bf16 = 9216 B
+constexpr uint32_t SM_KH = SM_QH + 9216;
+constexpr uint32_t SM_VH = SM_KH + 9216;
+constexpr uint32_t SM_P = SM_VH + 9216;                    // P: [rows x 144 keys] K-major, 18 chunks
+constexpr uint32_t SM_O = SM_P + 18 * LBO_X;               // O: [144 tok x 128] K-major, 16 chunks
+constexpr uint32_t SM_MISC = SM_O + 16 * LBO_X;
+// misc: tokpix[144] tokreg[144] (int) | red[2][2][144] (float) | ln g,b [256] | bv[128] | bproj[128]
+constexpr uint32_t SM_BAR = SM_MISC + (144 * 2 + 2 * 2 * 144 + 256 + 128 + 128) * 4;
+constexpr uint32_t SA_SMEM = SM_BAR + 8 * 8 + 16;
+constexpr uint32_t TM_QKV = 0, TM_S0 = 160, TM_S1 = 304, TM_O0 = 448, TM_O1 = 480;
+constexpr uint32_t IDESC_T = umma::make_idesc_bf16(128, 144, 0, 0);     // QKV^T, proj^T
+constexpr uint32_t IDESC_S = umma::make_idesc_bf16(128, 144, 1, 1);     // S = Q K^T (both MN-major images)
+constexpr uint32_t IDESC_PV = umma::make_idesc_bf16(128, 32, 0, 0);     // O = P V
+static_assert(SA_SMEM <= 232448, "shared memory budget");
+}  // namespace
+
+__global__ void __launch_bounds__(SA_THREADS, 1)
+swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, int nwin_total, int Te, int shift,
+                      SwinAttnFastW w) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  int* tokpix = reinterpret_cast<int*>(smem + SM_MISC);
+  int* tokreg = tokpix + 144;
+  float* red = reinterpret_cast<float*>(tokreg + 144);        // [2 (max|sum)][2 (key half)][144]
+  float* s_g = red + 2 * 2 * 144;
+  float* s_be = s_g + 128;
+  float* s_bv = s_be + 128;
+  float* s_bp = s_bv + 128;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + SM_BAR);   // [2]
+  uint64_t* bar_a = bar_full + 2;                                     // QKV_h done
+  uint64_t* bar_s = bar_full + 3;                                     // S done
+  uint64_t* bar_o = bar_full + 4;                                     // O_h done
+  uint64_t* bar_y = bar_full + 5;                                     // proj done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 6);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q4 = warp & 3, half = warp >> 2;
+
+  long long mine = 0;
+  for (long long i = blockIdx.x; i < nwin_total; i += gridDim.x) ++mine;
+  const long long total_loads = mine * 5;
+
+  if (tid < 128) { s_g[tid] = w.ln_g[tid]; s_be[tid] = w.ln_b[tid]; s_bv[tid] = w.bv[tid]; s_bp[tid] = w.bproj[tid]; }
+  if (tid == 0) {
+    for (int i = 0; i < 6; ++i) umma::mbar_init(&bar_full[i], 1);
+    umma::mbar_fence_init();
+  }
+  if (warp == 0) umma::tmem_alloc<512>(tmem_slot);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tm = *tmem_slot;
+  const uint32_t sb = umma::smem_u32(smem);
+  const uint32_t lane_addr = tm + ((uint32_t)(q4 * 32) << 16);
+
+  auto issue_load = [&](long long n) {      // thread 0 only
+    if (n < total_loads) {
+      int s = (int)(n & 1);
+      umma::mbar_expect_tx(&bar_full[s], WIMG_BYTES);
+      umma::bulk_g2s(smem + SM_RING + s * WIMG_BYTES, reinterpret_cast<const uint8_t*>(w.wimg) + (n % 5) * WIMG_BYTES,
+                     WIMG_BYTES, &bar_full[s]);
+    }
+  };
+  if (tid == 0) { issue_load(0); issue_load(1); }
+
+  long long nload = 0;          // index of the next weight image to be consumed by this CTA
+  uint32_t ph_a = 0, ph_s = 0, ph_o = 0, ph_y = 0;
+  const float scale = 0.17677669529663688110f;
+
+  for (long long wi = blockIdx.x; wi < nwin_total; wi += gridDim.x) {
+    const int slice = (int)(wi >> 2), win = (int)(wi & 3);
+    const int wy = win >> 1, wx = win & 1;
+    const int b = slice / Te;
+    float* Xs = X + (long long)slice * (GRID * GRID) * 128;
+    const float* ag = ag_qk + (long long)b * (GRID * GRID) * 256;
+    if (tid < NTOK) {
+      int sy = wy * WIN + tid / WIN, sx = wx * WIN + tid % WIN;
+      tokpix[tid] = ((sy + shift) % GRID) * GRID + (sx + shift) % GRID;
+      int rh = sy < GRID - WIN ? 0 : (sy < GRID - shift ? 1 : 2);
+      int rw = sx < GRID - WIN ? 0 : (sx < GRID - shift ? 1 : 2);
+      tokreg[tid] = rh * 3 + rw;
+    }
+    __syncthreads();
+    // ---- LN1 -> XN (warp per row, 4 rows in flight)
+    {
+      const float4 g = ld4(s_g + lane * 4), be = ld4(s_be + lane * 4);
+      for (int r0 = warp * 4; r0 < NTOK; r0 += 32) {
+        float4 x[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = ld4(Xs + (long long)tokpix[r0 + i] * 128 + lane * 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 y = warp_layernorm128(x[i], g, be);
+          uint2 pk = make_uint2(umma::pack_bf16x2(y.x, y.y), umma::pack_bf16x2(y.z, y.w));
+          *reinterpret_cast<uint2*>(smem + SM_XN + (lane >> 1) * LBO_X + (r0 + i) * 16 + (lane & 1) * 8) = pk;
+        }
+      }
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+
+    for (int h = 0; h < 4; ++h) {
+      // ---- [q_h;k_h;v_h]^T = Wqkv_h . XN^T
+      if (tid == 0) {
+        umma::fence_after_sync();
+        umma::mbar_wait(&bar_full[nload & 1], (uint32_t)((nload >> 1) & 1));
+        uint32_t wb = sb + SM_RING + (uint32_t)(nload & 1) * WIMG_BYTES;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma::mma_bf16_ss(tm + TM_QKV, umma::make_smem_desc(wb + k * 2 * LBO_W, LBO_W, 128),
+                            umma::make_smem_desc(sb + SM_XN + k * 2 * LBO_X, LBO_X, 128), IDESC_T, k > 0);
+        umma::mma_commit(bar_a);
+      }
+      umma::mbar_wait(bar_a, ph_a); ph_a ^= 1;
+      umma::fence_after_sync();
+      if (tid == 0) issue_load(nload + 2);
+      ++nload;
+      // ---- epilogue: feature threads (lane quarter 0:q 1:k 2:v) write the per-head images
+      if (q4 < 3) {
+        const int d = lane;
+        uint8_t* img = smem + (q4 == 0 ? SM_QH : (q4 == 1 ? SM_KH : SM_VH));
+        const float bvv = s_bv[h * 32 + d];
+        const float* agp = ag + (q4 == 1 ? 128 : 0) + h * 32 + d;
+#pragma unroll 1
+        for (int tg = half * 9; tg < half * 9 + 9; ++tg) {
+          float v[8];
+          umma::tmem_ld8(lane_addr + TM_QKV + tg * 8, v);
+          if (q4 == 2) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += bvv;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += __ldg(agp + (long long)tokpix[tg * 8 + i] * 256);
+            if (q4 == 0) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] *= scale;
+            }
+          }
+          *reinterpret_cast<uint4*>(img + tg * 512 + d * 16) =
+              make_uint4(umma::pack_bf16x2(v[0], v[1]), umma::pack_bf16x2(v[2], v[3]), umma::pack_bf16x2(v[4], v[5]),
+                         umma::pack_bf16x2(v[6], v[7]));
+        }
+      }
+      umma::fence_proxy_async();
+      umma::fence_before_sync();
+      __syncthreads();
+      // ---- S = Q K^T : two query tiles, K = 32 (two k-steps)
+      if (tid == 0) {
+        umma::fence_after_sync();
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma::mma_bf16_ss(tm + (mt ? TM_S1 : TM_S0),
+                              umma::make_smem_desc(sb + SM_QH + mt * 16 * 512 + k * 256, 128, 512),
+                              umma::make_smem_desc(sb + SM_KH + k * 256, 128, 512), IDESC_S, k > 0);
+        umma::mma_commit(bar_s);
+      }
+      umma::mbar_wait(bar_s, ph_s); ph_s ^= 1;
+      umma::fence_after_sync();
+      // ---- softmax: two threads per query row (keys [72*half, 72*half+72)); tile 1 rows by quarter 0, lanes < 16
+#pragma unroll 1
+      for (int mt = 0; mt < 2; ++mt) {
+        const int row = mt * 128 + q4 * 32 + lane;
+        const bool active = row < NTOK;                       // tile 1: only rows 128..143
+        float s[72];
+        float mx = -INFINITY;
+        if (active) {
+          const int rq = tokreg[row];
+#pragma unroll
+          for (int c = 0; c < 9; ++c) {
+            umma::tmem_ld8(lane_addr + (mt ? TM_S1 : TM_S0) + half * 72 + c * 8, &s[c * 8]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float v = s[c * 8 + i];
+              if (shift > 0 && tokreg[half * 72 + c * 8 + i] != rq) v += -100.0f;
+              s[c * 8 + i] = v;
+              mx = fmaxf(mx, v);
+            }
+          }
+          red[half * 144 + row] = mx;
+        }
+        __syncthreads();
+        float sum = 0.0f;
+        if (active) {
+          mx = fmaxf(red[row], red[144 + row]);
+#pragma unroll
+          for (int c = 0; c < 9; ++c) {
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { e[i] = __expf(s[c * 8 + i] - mx); sum += e[i]; }
+            *reinterpret_cast<uint4*>(smem + SM_P + (half * 9 + c) * LBO_X + row * 16) =
+                make_uint4(umma::pack_bf16x2(e[0], e[1]), umma::pack_bf16x2(e[2], e[3]), umma::pack_bf16x2(e[4], e[5]),
+                           umma::pack_bf16x2(e[6], e[7]));
+          }
+          red[288 + half * 144 + row] = sum;
+        }
+        // (the next __syncthreads orders the red[] reuse of the second tile after these reads)
+        __syncthreads();
+      }
+      umma::fence_proxy_async();
+      umma::fence_before_sync();
+      __syncthreads();
+      // ---- O_h = P V : K = 144 keys (9 k-steps), N = 32
+      if (tid == 0) {
+        umma::fence_after_sync();
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int k = 0; k < 9; ++k)
+            umma::mma_bf16_ss(tm + (mt ? TM_O1 : TM_O0),
+                              umma::make_smem_desc(sb + SM_P + mt * 128 * 16 + k * 2 * LBO_X, LBO_X, 128),
+                              umma::make_smem_desc(sb + SM_VH + k * 1024, 512, 128), IDESC_PV, k > 0);
+        umma::mma_commit(bar_o);
+      }
+      umma::mbar_wait(bar_o, ph_o); ph_o ^= 1;
+      umma::fence_after_sync();
+      // ---- O epilogue: thread = query row (tile 0: warps 0-3, tile 1: warp 4 lanes < 16)
+      {
+        const int mt = half;
+        const int row = mt * 128 + q4 * 32 + lane;
+        if (row < NTOK) {
+          float v[32];
+          umma::tmem_ld32(lane_addr + (mt ? TM_O1 : TM_O0), v);
+          const float inv = 1.0f / (red[288 + row] + red[288 + 144 + row]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(smem + SM_O + (h * 4 + c) * LBO_X + row * 16) =
+                make_uint4(umma::pack_bf16x2(v[c * 8 + 0] * inv, v[c * 8 + 1] * inv), umma::pack_bf16x2(v[c * 8 + 2] * inv, v[c * 8 + 3] * inv),
+                           umma::pack_bf16x2(v[c * 8 + 4] * inv, v[c * 8 + 5] * inv), umma::pack_bf16x2(v[c * 8 + 6] * inv, v[c * 8 + 7] * inv));
+        }
+      }
+      umma::fence_proxy_async();
+      umma::fence_before_sync();
+      __syncthreads();
+    }
+    // ---- Y^T = Wp . O^T
+    if (tid == 0) {
+      umma::fence_after_sync();
+      umma::mbar_wait(&bar_full[nload & 1], (uint32_t)((nload >> 1) & 1));
+      uint32_t wb = sb + SM_RING + (uint32_t)(nload & 1) * WIMG_BYTES;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma::mma_bf16_ss(tm + TM_QKV, umma::make_smem_desc(wb + k * 2 * LBO_W, LBO_W, 128),
+                          umma::make_smem_desc(sb + SM_O + k * 2 * LBO_X, LBO_X, 128), IDESC_T, k > 0);
+      umma::mma_commit(bar_y);
+    }
+    umma::mbar_wait(bar_y, ph_y); ph_y ^= 1;
+    umma::fence_after_sync();
+    if (tid == 0) issue_load(nload + 2);
+    ++nload;
+    // ---- x1 = x + Y + bproj : thread = feature, 72 tokens each; a warp touches 128 contiguous bytes per token
+    {
+      const int f = q4 * 32 + lane;
+      const float bp = s_bp[f];
+#pragma unroll 1
+      for (int tg = half * 9; tg < half * 9 + 9; ++tg) {
+        float v[8];
+        umma::tmem_ld8(lane_addr + TM_QKV + tg * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float* xp = Xs + (long long)tokpix[tg * 8 + i] * 128 + f;
+          *xp = *xp + (v[i] + bp);
+        }
+      }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+  }
+  if (warp == 0) umma::tmem_dealloc<512>(tm);
+}
+
+cudaError_t launch_swin_attn_fast(float* X, const float* ag_qk, int nslice, int Te, int shift,
+                                  const SwinAttnFastW& w, int num_sms, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(swin_attn_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  int nwin = nslice * 4;
+  int grid = nwin < num_sms ? nwin : num_sms;
+  if (grid <= 0) return cudaSuccess;
+  swin_attn_fast_kernel<<<grid, SA_THREADS, SA_SMEM, st>>>(X, ag_qk, nwin, Te, shift, w);
+  return cudaGetLastError();
+}
+
+// Per-head QKV weight image: rows [0,32) = Wq[h*32..] (LN(x) columns), [32,64) = Wk, [64,96) = Wv, [96,128) = 0
+__global__ void pack_qkv_head_img_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ Wq,
+                                         const float* __restrict__ Wk, const float* __restrict__ Wv, int ldqk, int h) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 128 * 128) return;
+  int r = i >> 7, k = i & 127;
+  float v = 0.0f;
+  if (r < 32) v = Wq[(long long)(h * 32 + r) * ldqk + k];
+  else if (r < 64) v = Wk[(long long)(h * 32 + r - 32) * ldqk + k];
+  else if (r < 96) v = Wv[(long long)(h * 32 + r - 64) * 128 + k];
+  dst[(k >> 3) * (128 * 8) + r * 8 + (k & 7)] = __float2bfloat16(v);
+}
+cudaError_t launch_pack_qkv_head_img(__nv_bfloat16* dst, const float* Wq, const float* Wk, const float* Wv, int ldqk,
+                                     int h, cudaStream_t st) {
+  pack_qkv_head_img_kernel<<<64, 256, 0, st>>>(dst, Wq, Wk, Wv, ldqk, h);
+  return cudaGetLastError();
+}
+
+}  // namespace catseg

@@ -43,6 +43,12 @@ struct MlpFastW {
   const float *ln_g, *ln_b, *b1, *b2;
 };
 
+// FAST window attention (fast_swin_attn.cu): 5 images per block: Wqkv_h (h = 0..3), Wproj.
+struct SwinAttnFastW {
+  const __nv_bfloat16* wimg;
+  const float *ln_g, *ln_b, *bv, *bproj;
+};
+
 constexpr int kStateFloats = 4 * 32 * 32 + 128;   // per (image, pixel): KV[4][32][32] then Ksum[128]
 
 // ---------------------------------------------------------------- prep.cu
@@ -77,6 +83,12 @@ cudaError_t launch_swin_block_exact(float* X, const float* ag_qk, int nslice, in
 // ---------------------------------------------------------------- fast_mlp.cu
 cudaError_t launch_mlp_fast(float* X, long long ntok, const MlpFastW& w, int act, int num_sms, cudaStream_t st);
 cudaError_t launch_pack_wimg(__nv_bfloat16* dst, const float* W, int ld, int r0, int c0, cudaStream_t st);
+
+// ---------------------------------------------------------------- fast_swin_attn.cu
+cudaError_t launch_swin_attn_fast(float* X, const float* ag_qk, int nslice, int Te, int shift,
+                                  const SwinAttnFastW& w, int num_sms, cudaStream_t st);
+cudaError_t launch_pack_qkv_head_img(__nv_bfloat16* dst, const float* Wq, const float* Wk, const float* Wv, int ldqk,
+                                     int h, cudaStream_t st);
 
 // ---------------------------------------------------------------- class_exact.cu
 cudaError_t launch_class_pad_state(const ClassLayerW& w, int Tg, float* pad_state, int n_pad, int S,
