@@ -190,11 +190,12 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
 #pragma unroll 1
       for (int mt = 0; mt < 2; ++mt) {
         const int row = mt * 128 + q4 * 32 + lane;
-        const bool active = row < NTOK;                       // tile 1: only rows 128..143
+        const bool warp_on = (mt == 0) || (q4 == 0);          // warp-uniform: tcgen05.ld is .sync.aligned
+        const bool active = row < NTOK;                       // tile 1: only rows 128..143 are real
         float s[72];
         float mx = -INFINITY;
-        if (active) {
-          const int rq = tokreg[row];
+        if (warp_on) {
+          const int rq = tokreg[active ? row : 0];
 #pragma unroll
           for (int c = 0; c < 9; ++c) {
             umma::tmem_ld8(lane_addr + (mt ? TM_S1 : TM_S0) + half * 72 + c * 8, &s[c * 8]);
@@ -206,11 +207,11 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
               mx = fmaxf(mx, v);
             }
           }
-          red[half * 144 + row] = mx;
+          if (active) red[half * 144 + row] = mx;
         }
         __syncthreads();
-        float sum = 0.0f;
-        if (active) {
+        if (warp_on && active) {
+          float sum = 0.0f;
           mx = fmaxf(red[row], red[144 + row]);
 #pragma unroll
           for (int c = 0; c < 9; ++c) {
@@ -223,7 +224,6 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
           }
           red[288 + half * 144 + row] = sum;
         }
-        // (the next __syncthreads orders the red[] reuse of the second tile after these reads)
         __syncthreads();
       }
       umma::fence_proxy_async();
@@ -247,15 +247,17 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
       {
         const int mt = half;
         const int row = mt * 128 + q4 * 32 + lane;
-        if (row < NTOK) {
+        if (mt == 0 || q4 == 0) {                             // warp-uniform (tcgen05.ld is .sync.aligned)
           float v[32];
           umma::tmem_ld32(lane_addr + (mt ? TM_O1 : TM_O0), v);
+          if (row < NTOK) {
           const float inv = 1.0f / (red[288 + row] + red[288 + 144 + row]);
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             *reinterpret_cast<uint4*>(smem + SM_O + (h * 4 + c) * LBO_X + row * 16) =
                 make_uint4(umma::pack_bf16x2(v[c * 8 + 0] * inv, v[c * 8 + 1] * inv), umma::pack_bf16x2(v[c * 8 + 2] * inv, v[c * 8 + 3] * inv),
                            umma::pack_bf16x2(v[c * 8 + 4] * inv, v[c * 8 + 5] * inv), umma::pack_bf16x2(v[c * 8 + 6] * inv, v[c * 8 + 7] * inv));
+          }
         }
       }
       umma::fence_proxy_async();
