@@ -24,7 +24,7 @@ struct Param {
 
 thread_local std::string g_create_error;
 
-constexpr int kImplementedFast = CATSEG_FAST_SWIN_MLP | CATSEG_FAST_SWIN_ATTN;   // stages that have a tcgen05 kernel in this build
+constexpr int kImplementedFast = CATSEG_FAST_SWIN_MLP | CATSEG_FAST_SWIN_ATTN | CATSEG_FAST_DECODER;   // stages that have a tcgen05 kernel in this build
 constexpr int kMaxProfForwards = 64;
 constexpr int kMaxSegments = 24;
 
@@ -43,6 +43,9 @@ struct catseg_handle {
   int num_sms = 148;
   std::vector<MlpFastW> swin_mlp_fast;   // [L*2]
   std::vector<SwinAttnFastW> swin_attn_fast;   // [L*2]
+  void* dec_fast_store = nullptr;
+  DecoderFastW dec_fast{};
+  float head_bias_host = 0.0f;
   bool finalized = false;
   std::string err;
   int device = 0;
@@ -208,6 +211,7 @@ extern "C" int catseg_destroy(catseg_handle* h) {
   if (h->raw) cudaFree(h->raw);
   if (h->packed) cudaFree(h->packed);
   if (h->wimg) cudaFree(h->wimg);
+  if (h->dec_fast_store) cudaFree(h->dec_fast_store);
   delete h;
   return CATSEG_OK;
 }
@@ -488,6 +492,23 @@ extern "C" int catseg_finalize_params(catseg_handle* h, catseg_stream stream) {
         h->swin_attn_fast[l * 2 + k] = SwinAttnFastW{aimg, sw.ln1_g, sw.ln1_b, sw.bv, sw.bproj};
       }
   }
+  if (h->fast_mask & CATSEG_FAST_DECODER) {
+    const catseg_config& c = h->cfg;
+    DecoderDims dd{c.feature_resolution[0], c.feature_resolution[1], 128, 128 - c.decoder_guidance_proj_dims[0],
+                   c.decoder_guidance_proj_dims[0], c.decoder_dims[0], c.decoder_dims[0] - c.decoder_guidance_proj_dims[1],
+                   c.decoder_guidance_proj_dims[1], c.decoder_dims[1]};
+    if (dd.D1 != 64 || dd.D2 != 32)
+      return fail(h, CATSEG_ERR_UNSUPPORTED, "the fast decoder is built for decoder_dims (64, 32)");
+    if (!h->dec_fast_store) CUDA_OK(h, cudaMalloc(&h->dec_fast_store, decoder_fast_weight_bytes(dd)));
+    cudaError_t e = decoder_fast_pack(dd, raw_of(h, "decoder1.up.weight"), raw_of(h, "decoder1.up.bias"),
+                                      raw_of(h, "decoder1.conv.double_conv.0.weight"),
+                                      raw_of(h, "decoder1.conv.double_conv.3.weight"), raw_of(h, "decoder2.up.weight"),
+                                      raw_of(h, "decoder2.up.bias"), raw_of(h, "decoder2.conv.double_conv.0.weight"),
+                                      raw_of(h, "decoder2.conv.double_conv.3.weight"), raw_of(h, "head.weight"),
+                                      h->dec_fast_store, &h->dec_fast, st);
+    if (e != cudaSuccess) return fail(h, CATSEG_ERR_CUDA, "decoder_fast_pack: %s", cudaGetErrorString(e));
+    CUDA_OK(h, cudaMemcpyAsync(&h->head_bias_host, raw_of(h, "head.bias"), sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
   CUDA_OK(h, cudaStreamSynchronize(st));
   h->finalized = true;
   return CATSEG_OK;
@@ -545,7 +566,14 @@ Plan make_plan(const catseg_handle* h, int B, int T) {
     p.Xp2 = take((size_t)nslice * p.npix * 128);
   }
   p.state = take((size_t)B * p.npix * kStateFloats);
-  p.dec = take(decoder_exact_scratch_floats(p.dd, p.dec_chunk));
+  {
+    size_t fe = decoder_exact_scratch_floats(p.dd, p.dec_chunk);
+    if (h->fast_mask & CATSEG_FAST_DECODER) {
+      p.dec_chunk = nslice < 128 ? nslice : 128;
+      fe = (decoder_fast_scratch_bytes(p.dd, B, p.dec_chunk) + 3) / 4;
+    }
+    p.dec = take(fe);
+  }
   p.total = o;
   return p;
 }
@@ -697,7 +725,13 @@ extern "C" int catseg_forward_taps(catseg_handle* h, const float* img, const flo
   // ---------------- decoder + scatter (model.py:720-724)
   seg.begin(CATSEG_STAGE_DECODER);
   if (p.truncated) RUN(launch_fill(logits, -100.0f, (long long)B * T * 16 * p.HW, st));
-  {
+  if (h->fast_mask & CATSEG_FAST_DECODER) {
+    if (taps && (taps->up1 || taps->up2))
+      return fail(h, CATSEG_ERR_UNSUPPORTED, "up1/up2 taps are only available with the exact decoder");
+    cudaError_t e = run_decoder_fast(X, ws + p.dg0, ws + p.dg1, classes, logits, B, T, p.Te, p.dd, h->dec_fast, h->dec,
+                                     h->head_bias_host, ws + p.dec, p.dec_chunk, h->num_sms, &nl, st);
+    if (e != cudaSuccess) return fail(h, CATSEG_ERR_CUDA, "fast decoder: %s", cudaGetErrorString(e));
+  } else {
     cudaError_t e = run_decoder_exact(X, ws + p.dg0, ws + p.dg1, classes, logits, B, T, p.Te, p.dd, h->dec,
                                       ws + p.dec, p.dec_chunk, taps ? taps->up1 : nullptr,
                                       taps ? taps->up2 : nullptr, &nl, st);

@@ -1,0 +1,503 @@
+// FAST guided upsampling decoder on tcgen05: implicit-GEMM "band convolution".
+//
+// Reference: Aggregator.conv_decoder (model.py:674-681), Up.forward (:549-555), DoubleConv (:520-537).
+//
+// One CTA processes a band of BR input rows of one (image, class) slice.  The band (plus a 1-pixel
+// halo, zero padded) is staged ONCE in shared memory as a bf16 canonical K-major image whose rows
+// are the padded raster positions; every convolution tap is then just a row-shifted view of that
+// image (descriptor start address + offset*16 bytes), so a 3x3 conv is 9 x (CIN/16) accumulating
+// tcgen05.mma per 128-row tile with no im2col copy.  GroupNorm+ReLU of the producer is applied
+// while staging (statistics come from the producer's epilogue as per-band partial sums, reduced in
+// a fixed order: deterministic); this kernel's epilogue emits the statistics of its own output.
+//
+// Results-preserving algebra (verified in fp64 there):
+//   * ConvTranspose2d(k2,s2) followed by conv3x3 is composed at load time into, per output parity
+//     (a,b), a 2x2-tap convolution on the LOW-resolution grid with CIN = channels before the
+//     transposed conv (128 -> 64 at 48^2, 64 -> 32 at 96^2): 43 % fewer MACs and no upsampled tensor;
+//   * the guidance channels of the concatenated input and the transposed-conv bias only depend on
+//     the image (resp. only on the weights): they enter as an additive per-image map E.
+// Stages: D1 x(24^2,128) -> c1a(48^2,64) | D2 c1a -> c1b | D3 c1b -> c2a(96^2,32) | D4 c2a -> c2b |
+//         D5 head c2b -> logits (N padded to 16, column 0 real).
+#include "fast_common.cuh"
+#include "igemm.cuh"
+#include "internal.h"
+
+namespace catseg {
+
+using namespace fast;
+
+struct BandConvParams {
+  const void* in;            // [S][Win*Win][CIN]  fp32 (IN_F32) or bf16
+  const float* in_stats;     // [S][nb_in][G_in][2] partial (sum, sumsq); nullptr: no GroupNorm on the input
+  int nb_in;
+  float in_count;            // elements per (slice, group)
+  const float *gamma, *beta; // [CIN]
+  const __nv_bfloat16* wimg; // NIMG images [NOUT x CIN], canonical dense
+  const float* emap;         // [B][Wout*Wout][NREAL] fp32 or nullptr
+  int Te;
+  __nv_bfloat16* out;        // [S][Wout*Wout][NREAL]
+  float* out_stats;          // [S][NB][G_out][2]
+  float* logits;             // HEAD: [B][T][Wout*Wout]
+  const int32_t* classes;    // HEAD: [B*Te] (absolute slice index)
+  int T;
+  float head_bias;
+  int slice0;                // absolute index of local slice 0 (for b = (slice0+s)/Te and classes)
+  int nslice;                // local slices in this launch
+};
+
+template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD>
+struct BandCfg {
+  static constexpr int PW = WIN_ + 2, NP = (BR + 2) * PW, P0 = PW + 1;
+  static constexpr int MROWS = (BR - 1) * PW + WIN_, NTILES = (MROWS + 127) / 128;
+  static constexpr int KCH = CIN / 8, KSTEPS = CIN / 16;
+  static constexpr uint32_t LBO_I = NP * 16 + ((16 + 128 - (NP * 16) % 128) % 128);   // LBO_I % 128 == 16
+  static constexpr int OVER = P0 + NTILES * 128 + PW + 2 - NP;
+  static constexpr uint32_t IMG_BYTES = ((KCH * LBO_I + (OVER > 0 ? OVER * 16 : 0)) + 127) / 128 * 128;
+  static constexpr int NTAP = UPS ? 4 : 9, NPG = UPS ? 4 : 1, NIMG = NTAP * NPG;
+  static constexpr uint32_t WBYTES = NOUT * CIN * 2, LBO_WT = NOUT * 16;
+  static constexpr bool RESIDENT = NIMG * WBYTES <= 80 * 1024;
+  static constexpr int NSLOT = RESIDENT ? NIMG : 4;
+  static constexpr int NB = WIN_ / BR;                 // bands per slice
+  static constexpr int WOUT = UPS ? 2 * WIN_ : WIN_;
+  static constexpr int GOUT = HEAD ? 1 : NREAL / 16;
+  static constexpr uint32_t SM_W = IMG_BYTES;
+  static constexpr uint32_t SM_SC = SM_W + NSLOT * WBYTES;            // scale[CIN], shift[CIN]
+  static constexpr uint32_t SM_ST = SM_SC + 2 * CIN * 4;              // [8 warps][GOUT][2]
+  static constexpr uint32_t SM_BAR = (SM_ST + 8 * GOUT * 2 * 4 + 15) / 16 * 16;
+  static constexpr uint32_t SMEM = SM_BAR + (2 * NSLOT + 2) * 8 + 16;
+  static constexpr uint32_t IDESC = umma::make_idesc_bf16(128, NOUT);
+  static_assert(NTILES * NOUT <= 512, "TMEM columns");
+  static_assert(SMEM <= 232448, "shared memory budget");
+  static_assert(WIN_ % BR == 0 && CIN % 16 == 0 && NOUT % 16 == 0, "shape");
+};
+
+template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD>
+__global__ void __launch_bounds__(256, 1) band_conv_kernel(BandConvParams p) {
+  using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* s_scale = reinterpret_cast<float*>(smem + C::SM_SC);
+  float* s_shift = s_scale + CIN;
+  float* s_part = reinterpret_cast<float*>(smem + C::SM_ST);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + C::SM_BAR);   // [NSLOT]
+  uint64_t* bar_empty = bar_full + C::NSLOT;                             // [NSLOT]
+  uint64_t* bar_acc = bar_empty + C::NSLOT;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q4 = warp & 3, half = warp >> 2;
+
+  const long long nitems = (long long)p.nslice * C::NB;
+  long long mine = 0;
+  for (long long i = blockIdx.x; i < nitems; i += gridDim.x) ++mine;
+  const long long total_loads = C::RESIDENT ? 1 : mine * C::NIMG;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2 * C::NSLOT + 1; ++i) umma::mbar_init(&bar_full[i], 1);
+    umma::mbar_fence_init();
+  }
+  if (warp == 0) umma::tmem_alloc<512>(tmem_slot);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tm = *tmem_slot;
+  const uint32_t sb = umma::smem_u32(smem);
+  const uint32_t lane_addr = tm + ((uint32_t)(q4 * 32) << 16);
+
+  auto issue_load = [&](long long n) {      // thread 0 only (streaming mode)
+    if (n < total_loads) {
+      int s = (int)(n % C::NSLOT);
+      umma::mbar_expect_tx(&bar_full[s], C::WBYTES);
+      umma::bulk_g2s(smem + C::SM_W + s * C::WBYTES,
+                     reinterpret_cast<const uint8_t*>(p.wimg) + (n % C::NIMG) * C::WBYTES, C::WBYTES, &bar_full[s]);
+    }
+  };
+  if (tid == 0) {
+    if (C::RESIDENT) {
+      umma::mbar_expect_tx(&bar_full[0], C::NIMG * C::WBYTES);
+      umma::bulk_g2s(smem + C::SM_W, p.wimg, C::NIMG * C::WBYTES, &bar_full[0]);
+    } else {
+      for (int i = 0; i < C::NSLOT - 1; ++i) issue_load(i);
+    }
+  }
+  long long nimg = 0;          // streaming: images consumed so far by this CTA
+  uint32_t ph_acc = 0;
+  bool w_ready = false;
+
+  for (long long it = blockIdx.x; it < nitems; it += gridDim.x) {
+    const int sl = (int)(it / C::NB), band = (int)(it % C::NB);
+    const int gslice = p.slice0 + sl;
+    const int b = gslice / p.Te;
+    // ---- GroupNorm parameters of the input (fixed-order reduction of the producer's band partials)
+    if (p.in_stats != nullptr) {
+      if (tid < CIN) {
+        const int g = tid >> 4, G = CIN / 16;
+        float s = 0.f, ss = 0.f;
+        for (int i = 0; i < p.nb_in; ++i) {
+          const float* st = p.in_stats + (((long long)sl * p.nb_in + i) * G + g) * 2;
+          s += st[0]; ss += st[1];
+        }
+        float mean = s / p.in_count;
+        float var = fmaxf(ss / p.in_count - mean * mean, 0.0f);
+        float rstd = rsqrtf(var + 1e-5f);
+        float sc = rstd * p.gamma[tid];
+        s_scale[tid] = sc;
+        s_shift[tid] = p.beta[tid] - mean * sc;
+      }
+      __syncthreads();
+    }
+    // ---- stage the padded band image (bf16, canonical K-major, rows = padded raster positions)
+    {
+      const int y_first = band * BR - 1;
+#pragma unroll 4
+      for (int idx = tid; idx < C::NP * C::KCH; idx += 256) {
+        const int pp = idx / C::KCH, c = idx % C::KCH;
+        const int yy = y_first + pp / C::PW, xx = pp % C::PW - 1;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (yy >= 0 && yy < WIN_ && xx >= 0 && xx < WIN_) {
+          float v[8];
+          const long long off = (((long long)sl * WIN_ + yy) * WIN_ + xx) * CIN + c * 8;
+          if (IN_F32) {
+            const float* src = reinterpret_cast<const float*>(p.in) + off;
+            float4 a = ld4(src), bq = ld4(src + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = bq.x; v[5] = bq.y; v[6] = bq.z; v[7] = bq.w;
+          } else {
+            uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.in) + off);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h2[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+          }
+          if (p.in_stats != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], s_scale[c * 8 + j], s_shift[c * 8 + j]), 0.0f);
+          }
+          val = make_uint4(umma::pack_bf16x2(v[0], v[1]), umma::pack_bf16x2(v[2], v[3]), umma::pack_bf16x2(v[4], v[5]),
+                           umma::pack_bf16x2(v[6], v[7]));
+        }
+        *reinterpret_cast<uint4*>(smem + c * C::LBO_I + pp * 16) = val;
+      }
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+
+    float st_sum[C::GOUT], st_sq[C::GOUT];
+#pragma unroll
+    for (int g = 0; g < C::GOUT; ++g) st_sum[g] = st_sq[g] = 0.0f;
+
+#pragma unroll 1
+    for (int pg = 0; pg < C::NPG; ++pg) {
+      const int pa = pg >> 1, pb = pg & 1;
+      if (tid == 0) {
+        umma::fence_after_sync();
+        if (C::RESIDENT && !w_ready) { umma::mbar_wait(&bar_full[0], 0); w_ready = true; }
+#pragma unroll 1
+        for (int tap = 0; tap < C::NTAP; ++tap) {
+          int off;
+          if (UPS) off = ((tap >> 1) + pa - 1) * C::PW + ((tap & 1) + pb - 1);
+          else off = (tap / 3 - 1) * C::PW + (tap % 3 - 1);
+          uint32_t wb;
+          int slot = 0;
+          if (C::RESIDENT) {
+            wb = sb + C::SM_W + (uint32_t)(pg * C::NTAP + tap) * C::WBYTES;
+          } else {
+            slot = (int)(nimg % C::NSLOT);
+            umma::mbar_wait(&bar_full[slot], (uint32_t)((nimg / C::NSLOT) & 1));
+            wb = sb + C::SM_W + (uint32_t)slot * C::WBYTES;
+          }
+#pragma unroll 1
+          for (int t = 0; t < C::NTILES; ++t) {
+            const uint32_t a0 = sb + (uint32_t)(C::P0 + t * 128 + off) * 16;
+#pragma unroll
+            for (int k = 0; k < C::KSTEPS; ++k)
+              umma::mma_bf16_ss(tm + t * NOUT, umma::make_smem_desc(a0 + k * 2 * C::LBO_I, C::LBO_I, 128),
+                                umma::make_smem_desc(wb + k * 2 * C::LBO_WT, C::LBO_WT, 128), C::IDESC,
+                                (tap > 0 || k > 0) ? 1u : 0u);
+          }
+          if (!C::RESIDENT) {
+            umma::mma_commit(&bar_empty[slot]);
+            // refill the slot of the PREVIOUS image (its MMAs were committed one step ago)
+            long long nn = nimg + C::NSLOT - 1;
+            if (nimg > 0 && nn < total_loads)
+              umma::mbar_wait(&bar_empty[(nimg - 1) % C::NSLOT], (uint32_t)(((nimg - 1) / C::NSLOT) & 1));
+            issue_load(nn);
+            ++nimg;
+          }
+        }
+        umma::mma_commit(bar_acc);
+      }
+      umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
+      umma::fence_after_sync();
+      // ---- epilogue: thread = padded raster row; the two warp sets take alternate tiles
+#pragma unroll 1
+      for (int t = half; t < C::NTILES; t += 2) {
+        const int pr = C::P0 + t * 128 + q4 * 32 + lane;
+        const int yl = pr / C::PW - 1, xl = pr % C::PW - 1;
+        const bool valid = (pr < C::P0 + C::MROWS) && xl >= 0 && xl < WIN_;
+        int Yo = band * BR + yl, Xo = xl;
+        if (UPS) { Yo = 2 * Yo + pa; Xo = 2 * Xo + pb; }
+        const long long opix = (long long)Yo * C::WOUT + Xo;
+        if constexpr (HEAD) {
+          float v[8];
+          umma::tmem_ld8(lane_addr + t * NOUT, v);
+          if (valid) {
+            int cls = p.classes[gslice];
+            p.logits[((long long)b * p.T + cls) * (C::WOUT * C::WOUT) + opix] = v[0] + p.head_bias;
+          }
+        } else {
+#pragma unroll
+          for (int c0 = 0; c0 < NREAL; c0 += 32) {
+            float v[32];
+            umma::tmem_ld32(lane_addr + t * NOUT + c0, v);
+            if (valid) {
+              if (p.emap != nullptr) {
+                const float* e = p.emap + ((long long)b * (C::WOUT * C::WOUT) + opix) * NREAL + c0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  float4 e4 = ld4(e + i);
+                  v[i] += e4.x; v[i + 1] += e4.y; v[i + 2] += e4.z; v[i + 3] += e4.w;
+                }
+              }
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {
+                float s = 0.f, ss = 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { float x = v[g * 16 + i]; s += x; ss = fmaf(x, x, ss); }
+                st_sum[c0 / 16 + g] += s; st_sq[c0 / 16 + g] += ss;
+              }
+              __nv_bfloat16* o = p.out + ((long long)sl * (C::WOUT * C::WOUT) + opix) * NREAL + c0;
+#pragma unroll
+              for (int i = 0; i < 32; i += 8)
+                *reinterpret_cast<uint4*>(o + i) =
+                    make_uint4(umma::pack_bf16x2(v[i], v[i + 1]), umma::pack_bf16x2(v[i + 2], v[i + 3]),
+                               umma::pack_bf16x2(v[i + 4], v[i + 5]), umma::pack_bf16x2(v[i + 6], v[i + 7]));
+            }
+          }
+        }
+      }
+      umma::fence_before_sync();
+      __syncthreads();        // accumulators (and, after the last parity, the image) may be overwritten
+    }
+    // ---- output statistics of this band: warp shuffle -> per-warp slots -> fixed-order sum
+    if (!HEAD) {
+#pragma unroll
+      for (int g = 0; g < C::GOUT; ++g) {
+        float s = warp_sum(st_sum[g]), ss = warp_sum(st_sq[g]);
+        if (lane == 0) { s_part[(warp * C::GOUT + g) * 2] = s; s_part[(warp * C::GOUT + g) * 2 + 1] = ss; }
+      }
+      __syncthreads();
+      if (tid < C::GOUT * 2) {
+        float a = 0.f;
+        for (int w8 = 0; w8 < 8; ++w8) a += s_part[w8 * C::GOUT * 2 + tid];
+        p.out_stats[((long long)sl * C::NB + band) * C::GOUT * 2 + tid] = a;
+      }
+      __syncthreads();
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc<512>(tm);
+}
+
+template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD>
+static cudaError_t launch_band(const BandConvParams& p, int num_sms, cudaStream_t st) {
+  using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD>;
+  auto kern = band_conv_kernel<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  long long nitems = (long long)p.nslice * C::NB;
+  int grid = (int)(nitems < num_sms ? nitems : num_sms);
+  if (grid <= 0) return cudaSuccess;
+  kern<<<grid, 256, C::SMEM, st>>>(p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight preparation (runs once in catseg_finalize_params)
+
+// image[(k/8)*NOUT*8 + n*8 + k%8] = W3[n][ci0 + k][tap]   (n < nreal, else 0)
+__global__ void pack_tap_img_kernel(__nv_bfloat16* dst, const float* W3, int Cin3, int ci0, int CIN, int NOUT, int nreal) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int per = NOUT * CIN;
+  if (i >= 9 * per) return;
+  int tap = i / per, r = i % per, n = r / CIN, k = r % CIN;
+  float v = n < nreal ? W3[((long long)n * Cin3 + ci0 + k) * 9 + tap] : 0.0f;
+  dst[(long long)tap * per + (k >> 3) * NOUT * 8 + n * 8 + (k & 7)] = __float2bfloat16(v);
+}
+
+// composed ConvTranspose(k2,s2) o conv3x3:  image index (a*2+b)*4 + (u*2+v), element [co][ci]
+//   Wc = sum_{dy,dx -> (u,v)} sum_cu Wup[ci][cu][a'][b'] * W3[co][cu][dy+1][dx+1]
+__global__ void compose_up_img_kernel(__nv_bfloat16* dst, const float* Wup, const float* W3, int Ci, int Cup, int Cin3,
+                                      int Co) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int per = Co * Ci;
+  if (i >= 16 * per) return;
+  int img = i / per, r = i % per, co = r / Ci, ci = r % Ci;
+  int a = img >> 3, bq = (img >> 2) & 1, u = (img >> 1) & 1, v = img & 1;
+  float acc = 0.0f;
+  for (int dy = -1; dy <= 1; ++dy) {
+    int ty = a + dy, fy = ty < 0 ? -1 : ty >> 1, ay = ty & 1;
+    if (fy - (a - 1) != u) continue;
+    for (int dx = -1; dx <= 1; ++dx) {
+      int tx = bq + dx, fx = tx < 0 ? -1 : tx >> 1, ax = tx & 1;
+      if (fx - (bq - 1) != v) continue;
+      for (int cu = 0; cu < Cup; ++cu)
+        acc = fmaf(Wup[(((long long)ci * Cup + cu) * 2 + ay) * 2 + ax], W3[((long long)co * Cin3 + cu) * 9 + (dy + 1) * 3 + dx + 1], acc);
+    }
+  }
+  dst[(long long)img * per + (ci >> 3) * Co * 8 + co * 8 + (ci & 7)] = __float2bfloat16(acc);
+}
+
+// bias map of the composed conv: Bmap[Y][X][co] = sum_{valid dy,dx} sum_cu bup[cu] W3[co][cu][dy+1][dx+1]
+__global__ void up_bias_map_kernel(float* dst, const float* bup, const float* W3, int Cup, int Cin3, int Co, int Wout) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Wout * Wout * Co) return;
+  int co = i % Co, pix = i / Co, Y = pix / Wout, X = pix % Wout;
+  float acc = 0.0f;
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) {
+      if (Y + dy < 0 || Y + dy >= Wout || X + dx < 0 || X + dx >= Wout) continue;
+      for (int cu = 0; cu < Cup; ++cu) acc = fmaf(bup[cu], W3[((long long)co * Cin3 + cu) * 9 + (dy + 1) * 3 + dx + 1], acc);
+    }
+  dst[i] = acc;
+}
+
+// guidance part of the first conv of an Up block, packed for the fp32 implicit GEMM: Wg[(tap*Cg + cg)][co]
+__global__ void pack_guid_w_kernel(float* dst, const float* W3, int Cup, int Cg, int Cin3, int Co) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * Cg * Co) return;
+  int co = i % Co, r = i / Co, cg = r % Cg, tap = r / Cg;
+  dst[i] = W3[((long long)co * Cin3 + Cup + cg) * 9 + tap];
+}
+
+size_t decoder_fast_weight_bytes(const DecoderDims& d) {
+  size_t b = 0;
+  b += (size_t)16 * d.D1 * d.C0 * 2;      // D1 composed
+  b += (size_t)9 * d.D1 * d.D1 * 2;       // D2
+  b += (size_t)16 * d.D2 * d.D1 * 2;      // D3 composed
+  b += (size_t)9 * d.D2 * d.D2 * 2;       // D4
+  b += (size_t)9 * 16 * d.D2 * 2;         // D5 head (N padded to 16)
+  b += (size_t)(4 * d.H * d.W * d.D1 + 16 * d.H * d.W * d.D2) * 4;   // bias maps
+  b += (size_t)(9 * d.G1 * d.D1 + 9 * d.G2 * d.D2) * 4;              // guidance conv weights
+  return (b + 255) / 256 * 256;
+}
+
+cudaError_t decoder_fast_pack(const DecoderDims& d, const float* up1_w, const float* up1_b, const float* c1a_w,
+                              const float* c1b_w, const float* up2_w, const float* up2_b, const float* c2a_w,
+                              const float* c2b_w, const float* head_w, void* storage, DecoderFastW* out,
+                              cudaStream_t st) {
+  if (d.C0 != 128 || d.D1 != 64 || d.D2 != 32 || d.H != 24 || d.W != 24 || d.G1 % 4 || d.G2 % 4)
+    return cudaErrorInvalidValue;      // the band kernels are instantiated for the shipped decoder geometry
+  uint8_t* ptr = reinterpret_cast<uint8_t*>(storage);
+  auto take = [&](size_t bytes) { uint8_t* r = ptr; ptr += bytes; return r; };
+  __nv_bfloat16* w1 = reinterpret_cast<__nv_bfloat16*>(take((size_t)16 * d.D1 * d.C0 * 2));
+  __nv_bfloat16* w2 = reinterpret_cast<__nv_bfloat16*>(take((size_t)9 * d.D1 * d.D1 * 2));
+  __nv_bfloat16* w3 = reinterpret_cast<__nv_bfloat16*>(take((size_t)16 * d.D2 * d.D1 * 2));
+  __nv_bfloat16* w4 = reinterpret_cast<__nv_bfloat16*>(take((size_t)9 * d.D2 * d.D2 * 2));
+  __nv_bfloat16* w5 = reinterpret_cast<__nv_bfloat16*>(take((size_t)9 * 16 * d.D2 * 2));
+  float* bm1 = reinterpret_cast<float*>(take((size_t)4 * d.H * d.W * d.D1 * 4));
+  float* bm2 = reinterpret_cast<float*>(take((size_t)16 * d.H * d.W * d.D2 * 4));
+  float* wg1 = reinterpret_cast<float*>(take((size_t)9 * d.G1 * d.D1 * 4));
+  float* wg2 = reinterpret_cast<float*>(take((size_t)9 * d.G2 * d.D2 * 4));
+  auto blocks = [](long long n) { return (unsigned)((n + 255) / 256); };
+  compose_up_img_kernel<<<blocks(16LL * d.D1 * d.C0), 256, 0, st>>>(w1, up1_w, c1a_w, d.C0, d.U1, d.U1 + d.G1, d.D1);
+  pack_tap_img_kernel<<<blocks(9LL * d.D1 * d.D1), 256, 0, st>>>(w2, c1b_w, d.D1, 0, d.D1, d.D1, d.D1);
+  compose_up_img_kernel<<<blocks(16LL * d.D2 * d.D1), 256, 0, st>>>(w3, up2_w, c2a_w, d.D1, d.U2, d.U2 + d.G2, d.D2);
+  pack_tap_img_kernel<<<blocks(9LL * d.D2 * d.D2), 256, 0, st>>>(w4, c2b_w, d.D2, 0, d.D2, d.D2, d.D2);
+  pack_tap_img_kernel<<<blocks(9LL * 16 * d.D2), 256, 0, st>>>(w5, head_w, d.D2, 0, d.D2, 16, 1);
+  up_bias_map_kernel<<<blocks(4LL * d.H * d.W * d.D1), 256, 0, st>>>(bm1, up1_b, c1a_w, d.U1, d.U1 + d.G1, d.D1, 2 * d.W);
+  up_bias_map_kernel<<<blocks(16LL * d.H * d.W * d.D2), 256, 0, st>>>(bm2, up2_b, c2a_w, d.U2, d.U2 + d.G2, d.D2, 4 * d.W);
+  pack_guid_w_kernel<<<blocks(9LL * d.G1 * d.D1), 256, 0, st>>>(wg1, c1a_w, d.U1, d.G1, d.U1 + d.G1, d.D1);
+  pack_guid_w_kernel<<<blocks(9LL * d.G2 * d.D2), 256, 0, st>>>(wg2, c2a_w, d.U2, d.G2, d.U2 + d.G2, d.D2);
+  out->w1 = w1; out->w2 = w2; out->w3 = w3; out->w4 = w4; out->w5 = w5;
+  out->bmap1 = bm1; out->bmap2 = bm2; out->wg1 = wg1; out->wg2 = wg2;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-image additive maps  E = Bmap + conv3x3(projected guidance, Wg)   (fp32 implicit GEMM)
+struct GuidConvA {
+  static constexpr bool kMFastest = false;
+  const float* g; int Cg, H, W;
+  __device__ float operator()(int, int m, int k) const {
+    int hw = H * W, img = m / hw, pix = m - img * hw;
+    int tap = k / Cg, cg = k - tap * Cg;
+    int y = pix / W + tap / 3 - 1, x = pix % W + tap % 3 - 1;
+    if (y < 0 || y >= H || x < 0 || x >= W) return 0.0f;
+    return __ldg(g + ((long long)img * hw + y * W + x) * Cg + cg);
+  }
+};
+struct MapAddStore {
+  float* out; const float* bmap; int hw, N;
+  __device__ void operator()(int, int m, int n, float acc) const {
+    out[(long long)m * N + n] = acc + __ldg(bmap + (long long)(m % hw) * N + n);
+  }
+};
+
+size_t decoder_fast_scratch_bytes(const DecoderDims& d, int B, int chunk) {
+  size_t hw = (size_t)d.H * d.W;
+  size_t b = 0;
+  b += (size_t)B * (4 * hw * d.D1 + 16 * hw * d.D2) * 4;                 // E1, E2
+  b += (size_t)chunk * (2 * 4 * hw * d.D1 + 2 * 16 * hw * d.D2) * 2;     // c1a c1b c2a c2b (bf16)
+  b += (size_t)chunk * (2 * 2 * 4 + 4 * 4 + 4 * 2 + 8 * 2) * 2 * 4 + 1024; // band statistics
+  return (b + 255) / 256 * 256;
+}
+
+#define CKF(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return _e; ++nl; } while (0)
+
+cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1, const int32_t* classes,
+                             float* logits, int B, int T, int Te, const DecoderDims& d, const DecoderFastW& w,
+                             const DecoderW& wx, float head_bias, void* scratch, int chunk, int num_sms,
+                             int* launches, cudaStream_t st) {
+  const int hw = d.H * d.W;
+  int nl = 0;
+  uint8_t* ptr = reinterpret_cast<uint8_t*>(scratch);
+  auto take = [&](size_t bytes) { uint8_t* r = ptr; ptr += (bytes + 255) / 256 * 256; return r; };
+  float* E1 = reinterpret_cast<float*>(take((size_t)B * 4 * hw * d.D1 * 4));
+  float* E2 = reinterpret_cast<float*>(take((size_t)B * 16 * hw * d.D2 * 4));
+  __nv_bfloat16* c1a = reinterpret_cast<__nv_bfloat16*>(take((size_t)chunk * 4 * hw * d.D1 * 2));
+  __nv_bfloat16* c1b = reinterpret_cast<__nv_bfloat16*>(take((size_t)chunk * 4 * hw * d.D1 * 2));
+  __nv_bfloat16* c2a = reinterpret_cast<__nv_bfloat16*>(take((size_t)chunk * 16 * hw * d.D2 * 2));
+  __nv_bfloat16* c2b = reinterpret_cast<__nv_bfloat16*>(take((size_t)chunk * 16 * hw * d.D2 * 2));
+  float* s1a = reinterpret_cast<float*>(take((size_t)chunk * 2 * 4 * 2 * 4));   // NB=2 G=4
+  float* s1b = reinterpret_cast<float*>(take((size_t)chunk * 4 * 4 * 2 * 4));   // NB=4 G=4
+  float* s2a = reinterpret_cast<float*>(take((size_t)chunk * 4 * 2 * 2 * 4));   // NB=4 G=2
+  float* s2b = reinterpret_cast<float*>(take((size_t)chunk * 8 * 2 * 2 * 4));   // NB=8 G=2
+
+  {
+    GuidConvA a{dg0, d.G1, 2 * d.H, 2 * d.W};
+    CKF(launch_igemm(a, w.wg1, 0, 1, B * 4 * hw, d.D1, 9 * d.G1, MapAddStore{E1, w.bmap1, 4 * hw, d.D1}, st));
+    GuidConvA a2{dg1, d.G2, 4 * d.H, 4 * d.W};
+    CKF(launch_igemm(a2, w.wg2, 0, 1, B * 16 * hw, d.D2, 9 * d.G2, MapAddStore{E2, w.bmap2, 16 * hw, d.D2}, st));
+  }
+  const int nslice = B * Te;
+  for (int s0 = 0; s0 < nslice; s0 += chunk) {
+    const int n = nslice - s0 < chunk ? nslice - s0 : chunk;
+    BandConvParams p{};
+    p.Te = Te; p.slice0 = s0; p.nslice = n; p.T = T; p.classes = classes; p.logits = logits; p.head_bias = head_bias;
+    // D1: x (24^2 x 128, fp32) -> c1a (48^2 x 64), composed transposed conv + conv
+    p.in = X + (long long)s0 * hw * d.C0; p.in_stats = nullptr; p.wimg = w.w1; p.emap = E1; p.out = c1a; p.out_stats = s1a;
+    CKF((launch_band<128, 64, 64, true, true, 24, 12, false>(p, num_sms, st)));
+    // D2: c1a -> c1b, 3x3 64 -> 64 on relu(gn(c1a))
+    p.in = c1a; p.in_stats = s1a; p.nb_in = 2; p.in_count = (float)(4 * hw * 16); p.gamma = wx.gn1a_g; p.beta = wx.gn1a_b;
+    p.wimg = w.w2; p.emap = nullptr; p.out = c1b; p.out_stats = s1b;
+    CKF((launch_band<64, 64, 64, false, false, 48, 12, false>(p, num_sms, st)));
+    // D3: c1b -> c2a (96^2 x 32), composed
+    p.in = c1b; p.in_stats = s1b; p.nb_in = 4; p.gamma = wx.gn1b_g; p.beta = wx.gn1b_b;
+    p.wimg = w.w3; p.emap = E2; p.out = c2a; p.out_stats = s2a;
+    CKF((launch_band<64, 32, 32, true, false, 48, 12, false>(p, num_sms, st)));
+    // D4: c2a -> c2b, 3x3 32 -> 32
+    p.in = c2a; p.in_stats = s2a; p.nb_in = 4; p.in_count = (float)(16 * hw * 16); p.gamma = wx.gn2a_g; p.beta = wx.gn2a_b;
+    p.wimg = w.w4; p.emap = nullptr; p.out = c2b; p.out_stats = s2b;
+    CKF((launch_band<32, 32, 32, false, false, 96, 12, false>(p, num_sms, st)));
+    // D5: head 3x3 32 -> 1 (+ bias), scattered to logits[b][class]
+    p.in = c2b; p.in_stats = s2b; p.nb_in = 8; p.gamma = wx.gn2b_g; p.beta = wx.gn2b_b;
+    p.wimg = w.w5; p.emap = nullptr; p.out = nullptr; p.out_stats = nullptr;
+    CKF((launch_band<32, 16, 16, false, false, 96, 12, true>(p, num_sms, st)));
+  }
+  if (launches) *launches += nl;
+  return cudaSuccess;
+}
+
+}  // namespace catseg

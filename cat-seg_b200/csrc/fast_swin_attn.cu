@@ -111,12 +111,12 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
     // ---- LN1 -> XN (warp per row, 4 rows in flight)
     {
       const float4 g = ld4(s_g + lane * 4), be = ld4(s_be + lane * 4);
-      for (int r0 = warp * 4; r0 < NTOK; r0 += 32) {
-        float4 x[4];
+      for (int r0 = warp * 6; r0 < NTOK; r0 += 48) {
+        float4 x[6];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) x[i] = ld4(Xs + (long long)tokpix[r0 + i] * 128 + lane * 4);
+        for (int i = 0; i < 6; ++i) x[i] = ld4(Xs + (long long)tokpix[r0 + i] * 128 + lane * 4);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 6; ++i) {
           float4 y = warp_layernorm128(x[i], g, be);
           uint2 pk = make_uint2(umma::pack_bf16x2(y.x, y.y), umma::pack_bf16x2(y.z, y.w));
           *reinterpret_cast<uint2*>(smem + SM_XN + (lane >> 1) * LBO_X + (r0 + i) * 16 + (lane & 1) * 8) = pk;
@@ -139,6 +139,23 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
                             umma::make_smem_desc(sb + SM_XN + k * 2 * LBO_X, LBO_X, 128), IDESC_T, k > 0);
         umma::mma_commit(bar_a);
       }
+      // ---- while the MMA runs: stage this head's guidance terms [144 tok][q 32 | k 32] (fp32) in the P region,
+      //      which is free until the softmax of this head (coalesced 128-byte rows, one latency)
+      {
+        float* stage = reinterpret_cast<float*>(smem + SM_P);
+        float4 t4[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          int idx = tid + i * SA_THREADS, r = idx >> 4, c4 = idx & 15;
+          t4[i] = ld4(ag + (long long)tokpix[r] * 256 + (c4 < 8 ? h * 32 + c4 * 4 : 128 + h * 32 + (c4 - 8) * 4));
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          int idx = tid + i * SA_THREADS;
+          st4(stage + idx * 4, t4[i]);
+        }
+      }
+      __syncthreads();
       umma::mbar_wait(bar_a, ph_a); ph_a ^= 1;
       umma::fence_after_sync();
       if (tid == 0) issue_load(nload + 2);
@@ -148,7 +165,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
         const int d = lane;
         uint8_t* img = smem + (q4 == 0 ? SM_QH : (q4 == 1 ? SM_KH : SM_VH));
         const float bvv = s_bv[h * 32 + d];
-        const float* agp = ag + (q4 == 1 ? 128 : 0) + h * 32 + d;
+        const float* agp = reinterpret_cast<const float*>(smem + SM_P) + (q4 == 1 ? 32 : 0) + d;
 #pragma unroll 1
         for (int tg = half * 9; tg < half * 9 + 9; ++tg) {
           float v[8];
@@ -158,7 +175,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
             for (int i = 0; i < 8; ++i) v[i] += bvv;
           } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += __ldg(agp + (long long)tokpix[tg * 8 + i] * 256);
+            for (int i = 0; i < 8; ++i) v[i] += agp[(tg * 8 + i) * 64];
             if (q4 == 0) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] *= scale;
@@ -284,14 +301,14 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
       const int f = q4 * 32 + lane;
       const float bp = s_bp[f];
 #pragma unroll 1
-      for (int tg = half * 9; tg < half * 9 + 9; ++tg) {
-        float v[8];
-        umma::tmem_ld8(lane_addr + TM_QKV + tg * 8, v);
+      for (int t0 = half * 72; t0 < half * 72 + 72; t0 += 24) {      // 24 shortcut loads in flight per round
+        float xv[24], v[24];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float* xp = Xs + (long long)tokpix[tg * 8 + i] * 128 + f;
-          *xp = *xp + (v[i] + bp);
-        }
+        for (int i = 0; i < 24; ++i) xv[i] = Xs[(long long)tokpix[t0 + i] * 128 + f];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) umma::tmem_ld8(lane_addr + TM_QKV + t0 + c * 8, &v[c * 8]);
+#pragma unroll
+        for (int i = 0; i < 24; ++i) Xs[(long long)tokpix[t0 + i] * 128 + f] = xv[i] + (v[i] + bp);
       }
     }
     umma::fence_before_sync();

@@ -129,6 +129,23 @@ cudaError_t run_decoder_exact(const float* X, const float* dg0, const float* dg1
                               float* scratch, int chunk, float* tap_up1, float* tap_up2, int* launches,
                               cudaStream_t st);
 
+// ---------------------------------------------------------------- fast_decoder.cu
+struct DecoderFastW {
+  const __nv_bfloat16 *w1, *w2, *w3, *w4, *w5;   // UMMA weight images per stage (fast_decoder.cu)
+  const float *bmap1, *bmap2;                    // [4HW][D1], [16HW][D2] transposed-conv bias maps
+  const float *wg1, *wg2;                        // [9*G1][D1], [9*G2][D2] guidance conv weights (fp32 GEMM)
+};
+size_t decoder_fast_weight_bytes(const DecoderDims& d);
+cudaError_t decoder_fast_pack(const DecoderDims& d, const float* up1_w, const float* up1_b, const float* c1a_w,
+                              const float* c1b_w, const float* up2_w, const float* up2_b, const float* c2a_w,
+                              const float* c2b_w, const float* head_w, void* storage, DecoderFastW* out,
+                              cudaStream_t st);
+size_t decoder_fast_scratch_bytes(const DecoderDims& d, int B, int chunk);
+cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1, const int32_t* classes,
+                             float* logits, int B, int T, int Te, const DecoderDims& d, const DecoderFastW& w,
+                             const DecoderW& wx, float head_bias, void* scratch, int chunk, int num_sms,
+                             int* launches, cudaStream_t st);
+
 // ---------------------------------------------------------------- stitch.cu
 cudaError_t launch_stitch(const float* win_logits, int T, int S, int kernel, int stride, int out_res, int height,
                           int width, float* probs_out, int32_t* labels_out, cudaStream_t st);

@@ -37,6 +37,8 @@ def main():
     names = ["embed"] + [f"{k}{l}{s}" for l in range(cfg.num_layers) for k, s in
                          (("swin_l", "_b1"), ("swin_l", "_b2"), ("class_l", ""))] + ["up1", "up2"]
     for prec in ["exact", a.precision]:
+        if prec == "fast" or "decoder" in prec:
+            names = [n for n in names if n not in ("up1", "up2")]
         m = Aggregator(**cfg.ctor_kwargs(), precision=prec)
         m.load_state_dict(sd, strict=False)
         m = m.cuda()

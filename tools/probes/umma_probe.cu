@@ -36,8 +36,10 @@ __global__ void gemm_probe(const float* A, const float* B, float* D, int N, int 
   __shared__ uint32_t tmem_base;
   const int M = 128;
   const bool swap = variant & 1, b_mn = variant & 2, a_mn = variant & 4;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + M * K * 2;
+  // variant bit 3: the A tile starts at a row offset that is NOT a multiple of 8 rows (start address = base + 3*16):
+  // needed by the implicit-GEMM convolutions, whose taps are row-shifted views of one shared-memory image
+  uint8_t* sA = smem + ((variant & 8) ? 48 : 0);
+  uint8_t* sB = smem + M * K * 2 + 128;
   int t = threadIdx.x;
   for (int i = t; i < M * K; i += blockDim.x) {
     int r = i / K, k = i % K;
@@ -150,7 +152,7 @@ static float bf16r(float x) { return __bfloat162float(__float2bfloat16(x)); }
 int main(int argc, char** argv) {
   int id = argc > 1 ? atoi(argv[1]) : 0;
   cudaDeviceProp prop; CHECK(cudaGetDeviceProperties(&prop, 0));
-  if (id < 8) {
+  if (id < 16) {
     const int M = 128, K = 64;
     const int Ns[3] = {64, 144, 256};
     for (int ni = 0; ni < 3; ++ni) {
@@ -164,7 +166,7 @@ int main(int argc, char** argv) {
       CHECK(cudaMalloc(&dA, A.size() * 4)); CHECK(cudaMalloc(&dB, B.size() * 4)); CHECK(cudaMalloc(&dD, D.size() * 4)); CHECK(cudaMalloc(&dS, 4));
       CHECK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice)); CHECK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
       CHECK(cudaMemset(dD, 0, D.size() * 4)); CHECK(cudaMemset(dS, 0, 4));
-      size_t smem = (size_t)(M + N) * K * 2;
+      size_t smem = (size_t)(M + N) * K * 2 + 256;
       CHECK(cudaFuncSetAttribute(gemm_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       gemm_probe<<<1, 128, smem>>>(dA, dB, dD, N, K, id, dS);
       cudaError_t e = cudaDeviceSynchronize();
