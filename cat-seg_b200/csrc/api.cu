@@ -24,7 +24,7 @@ struct Param {
 
 thread_local std::string g_create_error;
 
-constexpr int kImplementedFast = CATSEG_FAST_SWIN_MLP | CATSEG_FAST_SWIN_ATTN | CATSEG_FAST_DECODER;   // stages that have a tcgen05 kernel in this build
+constexpr int kImplementedFast = CATSEG_FAST_SWIN_MLP | CATSEG_FAST_SWIN_ATTN | CATSEG_FAST_DECODER | CATSEG_FAST_CLASS;   // stages that have a tcgen05 kernel in this build
 constexpr int kMaxProfForwards = 64;
 constexpr int kMaxSegments = 24;
 
@@ -43,6 +43,7 @@ struct catseg_handle {
   int num_sms = 148;
   std::vector<MlpFastW> swin_mlp_fast;   // [L*2]
   std::vector<SwinAttnFastW> swin_attn_fast;   // [L*2]
+  std::vector<ClassFastW> class_fast;   // [L]
   void* dec_fast_store = nullptr;
   DecoderFastW dec_fast{};
   float head_bias_host = 0.0f;
@@ -461,7 +462,7 @@ extern "C" int catseg_finalize_params(catseg_handle* h, catseg_stream stream) {
   if (h->fast_mask) {
     const int L = h->cfg.num_layers;
     const size_t kImg = 128 * 128;
-    size_t need = (size_t)L * 2 * (8 + 5) * kImg;
+    size_t need = (size_t)L * 2 * (8 + 5) * kImg + (size_t)L * 13 * kImg;
     if (!h->wimg || h->wimg_elems < need) {
       if (h->wimg) cudaFree(h->wimg);
       h->wimg = nullptr;
@@ -491,6 +492,29 @@ extern "C" int catseg_finalize_params(catseg_handle* h, catseg_stream stream) {
         CUDA_OK(h, launch_pack_wimg(aimg + 4 * kImg, raw_of(h, q + ".attn.proj.weight"), 128, 0, 0, st));
         h->swin_attn_fast[l * 2 + k] = SwinAttnFastW{aimg, sw.ln1_g, sw.ln1_b, sw.bv, sw.bproj};
       }
+  }
+  if (h->fast_mask & CATSEG_FAST_CLASS) {
+    const int L = h->cfg.num_layers, tg = h->cfg.text_guidance_proj_dim;
+    const size_t kImg = 128 * 128;
+    h->class_fast.assign(L, ClassFastW{});
+    char b[160];
+    for (int l = 0; l < L; ++l) {
+      snprintf(b, sizeof(b), "layers.%d.attention", l);
+      std::string a(b);
+      __nv_bfloat16* img = h->wimg + (size_t)L * 2 * 13 * kImg + (size_t)l * 13 * kImg;
+      CUDA_OK(h, launch_pack_wimg(img + 0 * kImg, raw_of(h, a + ".attention.k.weight"), 128 + tg, 0, 0, st));
+      CUDA_OK(h, launch_pack_wimg(img + 1 * kImg, raw_of(h, a + ".attention.k.weight"), 128 + tg, 0, 128, st));
+      CUDA_OK(h, launch_pack_wimg(img + 2 * kImg, raw_of(h, a + ".attention.v.weight"), 128, 0, 0, st));
+      __nv_bfloat16* ap = img + 3 * kImg;
+      CUDA_OK(h, launch_pack_wimg(ap + 0 * kImg, raw_of(h, a + ".attention.q.weight"), 128 + tg, 0, 0, st));
+      CUDA_OK(h, launch_pack_wimg(ap + 1 * kImg, raw_of(h, a + ".attention.q.weight"), 128 + tg, 0, 128, st));
+      for (int j = 0; j < 4; ++j) {
+        CUDA_OK(h, launch_pack_wimg(ap + (size_t)(2 + 2 * j) * kImg, raw_of(h, a + ".MLP.0.weight"), 128, j * 128, 0, st));
+        CUDA_OK(h, launch_pack_wimg(ap + (size_t)(3 + 2 * j) * kImg, raw_of(h, a + ".MLP.2.weight"), 512, 0, j * 128, st));
+      }
+      const ClassLayerW& cw = h->cls[l];
+      h->class_fast[l] = ClassFastW{img, ap, cw.ln1_g, cw.ln1_b, cw.ln2_g, cw.ln2_b, cw.bqk, cw.bv, cw.b1, cw.b2};
+    }
   }
   if (h->fast_mask & CATSEG_FAST_DECODER) {
     const catseg_config& c = h->cfg;
@@ -524,7 +548,7 @@ struct Plan {
   DecoderDims dd;
   // workspace offsets (floats)
   size_t imgn, textn, corr, cmax, classes, tmean, text_g, cg_qk, pad_state, app_g, app_gn, ag_qk, dg0, dg1, X,
-      Xp, Xp2, state, dec, total;
+      Xp, Xp2, state, timg, dec, total;
 };
 
 Plan make_plan(const catseg_handle* h, int B, int T) {
@@ -566,6 +590,7 @@ Plan make_plan(const catseg_handle* h, int B, int T) {
     p.Xp2 = take((size_t)nslice * p.npix * 128);
   }
   p.state = take((size_t)B * p.npix * kStateFloats);
+  p.timg = take((size_t)B * ((p.Te + 127) / 128) * 8192);   // bf16 text-guidance images (FAST class path)
   {
     size_t fe = decoder_exact_scratch_floats(p.dd, p.dec_chunk);
     if (h->fast_mask & CATSEG_FAST_DECODER) {
@@ -663,6 +688,9 @@ extern "C" int catseg_forward_taps(catseg_handle* h, const float* img, const flo
                       (long long)B * p.Te, 256, 128, 0, st));
     RUN(launch_class_pad_state(h->cls[l], 128, ws + p.pad_state + (size_t)l * kStateFloats, p.n_pad, p.S, st));
   }
+  const bool class_fast = (h->fast_mask & CATSEG_FAST_CLASS) != 0;
+  __nv_bfloat16* timg = reinterpret_cast<__nv_bfloat16*>(ws + p.timg);
+  if (class_fast) RUN(launch_pack_text_img(ws + p.text_g, timg, B, p.Te, st));
   RUN(launch_conv3x3_nchw(g0, h->gproj_wt, h->gproj_b, ws + p.app_g, B, p.Cg, p.H, p.W, 128, st));
   for (int l = 0; l < p.L; ++l) {
     RUN(launch_layernorm128(ws + p.app_g, ws + p.app_gn, h->gnorm_g[l], h->gnorm_b[l], (long long)B * p.HW, st));
@@ -709,15 +737,19 @@ extern "C" int catseg_forward_taps(catseg_handle* h, const float* img, const flo
     seg.begin(CATSEG_STAGE_CLASS);
     const float* cg = ws + p.cg_qk + (size_t)l * B * p.Te * 256;
     const float* pad = ws + p.pad_state + (size_t)l * kStateFloats;
-    if (!p.pooled) {
-      RUN(launch_class_state_exact(X, cg, ws + p.state, B, p.Te, p.npix, p.S, h->cls[l], st));
-      RUN(launch_class_apply_exact(X, X, cg, ws + p.state, pad, B, p.Te, p.npix, p.S, 0, h->cls[l], st));
+    if (p.pooled) RUN(launch_avgpool_tokens(X, ws + p.Xp, nslice, p.H, p.W, c.pooling_size[0], c.pooling_size[1], st));
+    const float* xin = p.pooled ? ws + p.Xp : X;
+    float* xout = p.pooled ? ws + p.Xp2 : X;
+    const int omode = p.pooled ? 1 : 0;
+    if (class_fast) {
+      RUN(launch_class_state_fast(xin, timg, ws + p.state, B, p.Te, p.npix, p.S, h->class_fast[l], h->num_sms, st));
+      RUN(launch_class_apply_fast(xin, xout, timg, ws + p.state, pad, B, p.Te, p.npix, p.S, omode, h->class_fast[l],
+                                  h->num_sms, st));
     } else {
-      RUN(launch_avgpool_tokens(X, ws + p.Xp, nslice, p.H, p.W, c.pooling_size[0], c.pooling_size[1], st));
-      RUN(launch_class_state_exact(ws + p.Xp, cg, ws + p.state, B, p.Te, p.npix, p.S, h->cls[l], st));
-      RUN(launch_class_apply_exact(ws + p.Xp, ws + p.Xp2, cg, ws + p.state, pad, B, p.Te, p.npix, p.S, 1, h->cls[l], st));
-      RUN(launch_upsample_add(X, ws + p.Xp2, nslice, p.H, p.W, p.Hp, p.Wp, st));
+      RUN(launch_class_state_exact(xin, cg, ws + p.state, B, p.Te, p.npix, p.S, h->cls[l], st));
+      RUN(launch_class_apply_exact(xin, xout, cg, ws + p.state, pad, B, p.Te, p.npix, p.S, omode, h->cls[l], st));
     }
+    if (p.pooled) RUN(launch_upsample_add(X, ws + p.Xp2, nslice, p.H, p.W, p.Hp, p.Wp, st));
     seg.end();
     TAP(taps->class_out[l], X, (size_t)nslice * p.HW * 128);
   }

@@ -1,0 +1,481 @@
+// FAST class aggregation (linear attention over the class axis at every pixel) on tcgen05.
+//
+// Reference: ClassTransformerLayer.forward (model.py:387-424), AttentionLayer.forward (:338-354),
+// LinearAttention.forward (:266-286).  Same split as the exact path (class_exact.cu):
+//   class_state_fast : per (image, pixel)   KV[h] = sum_t phi(k_t)^T (v_t/S),  Ksum = sum_t phi(k_t)
+//   class_apply_fast : per (image, pixel, 128-class tile)
+//        q -> phi(q) [KV | Ksum] -> x1 = x + att -> LN2 -> MLP (ReLU) -> out
+// Everything that is a contraction runs on the tensor cores:
+//   * q/k projections use K = 256 = [LN1(x) | text guidance]: the guidance half of the A operand is a
+//     ready-made bf16 canonical image per (image, 128-class tile) (built once per forward, fetched by
+//     one bulk copy), so the "concat" of the reference costs no thread work (biases in the epilogue);
+//   * KV = K^T [V | 1] contracts over the TOKEN axis: the [token][feature] images written by the
+//     epilogue are consumed as MN-major A and B operands (the ones column yields Ksum);
+//   * the state is applied as phi(q) . Bstate with Bstate = [blockdiag(KV_h) | Ksum_h columns] (N = 144).
+// Padding classes (T < pad_len) enter as the constant pad_state.
+#include "fast_common.cuh"
+#include "internal.h"
+
+namespace catseg {
+
+using namespace fast;
+
+namespace {
+constexpr uint32_t LBO_V = 128 * 16 + 16;                          // thread-written 128-row tiles (= LBO_T)
+constexpr uint32_t IDESC_N144 = umma::make_idesc_bf16(128, 144, 0, 0);
+constexpr uint32_t IDESC_KV = umma::make_idesc_bf16(128, 144, 1, 1);     // K^T [V|1]: both operands MN-major
+constexpr uint32_t IDESC_APPLY = umma::make_idesc_bf16(128, 144, 0, 1);  // phi(q) (K-major) x Bstate (MN-major)
+
+// ---------------------------------------------------------------- state kernel layout
+constexpr uint32_t ST_W = 0;                                       // Wk_x, Wk_g, Wv images: 3 x 32 KiB resident
+constexpr uint32_t ST_XN = ST_W + 3 * WIMG_BYTES;                  // LN1(x) tile; later the phi(k) image
+constexpr uint32_t ST_G = ST_XN + TILE_BYTES_T;                    // guidance tile (dense, TMA); later the V image
+constexpr uint32_t ST_GV_BYTES = 18 * LBO_V;                       // V image has 18 chunks (128 v + ones + pad)
+constexpr uint32_t ST_PAR = ST_G + ST_GV_BYTES;                    // ln g,b [256] bk[128] bv[128]
+constexpr uint32_t ST_BAR = ST_PAR + 512 * 4;
+constexpr uint32_t ST_SMEM = ST_BAR + 6 * 8 + 16;
+constexpr uint32_t ST_TM_KV = 0, ST_TM_ACC = 256;                  // k|v raw: 256 cols; KV accumulator: 144 cols
+
+// ---------------------------------------------------------------- apply kernel layout
+constexpr uint32_t AP_RING = 0;                                    // 2 x 32 KiB
+constexpr uint32_t AP_XN = AP_RING + 2 * WIMG_BYTES;               // LN1(x) -> later LN2(x1)
+constexpr uint32_t AP_GH = AP_XN + TILE_BYTES_T;                   // guidance tile (TMA) -> later MLP hidden chunk
+constexpr uint32_t AP_Q = AP_GH + TILE_BYTES_T;                    // phi(q) image
+constexpr uint32_t AP_BST = AP_Q + TILE_BYTES_T;                   // Bstate [128 k x 144 n] MN-major, 18 n-groups
+constexpr uint32_t AP_PAR = AP_BST + 18 * LBO_V;                   // ln1 g,b ln2 g,b [512] bq[128] b1[512] b2[128] red[512]
+constexpr uint32_t AP_BAR = AP_PAR + (512 + 128 + 512 + 128 + 512) * 4;
+constexpr uint32_t AP_SMEM = AP_BAR + 10 * 8 + 16;
+constexpr uint32_t AP_TM_Q = 0, AP_TM_ND = 128, AP_TM_Y = 272;     // q / H: [0,128)  num|den: [128,272)  Y: [272,400)
+static_assert(ST_SMEM <= 232448 && AP_SMEM <= 232448, "shared memory budget");
+}  // namespace
+
+// ================================================================================================
+__global__ void __launch_bounds__(256, 1)
+class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __restrict__ timg, float* __restrict__ state,
+                        int B, int Te, int npix, int S, ClassFastW w) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* s_g = reinterpret_cast<float*>(smem + ST_PAR);
+  float* s_be = s_g + 128;
+  float* s_bk = s_be + 128;
+  float* s_bv = s_bk + 128;
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + ST_BAR);
+  uint64_t* bar_g = bar_w + 1;
+  uint64_t* bar_m1 = bar_w + 2;
+  uint64_t* bar_m2 = bar_w + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q4 = warp & 3, half = warp >> 2;
+  const int row = q4 * 32 + lane;
+  const int ntile = (Te + 127) / 128;
+
+  if (tid < 128) { s_g[tid] = w.ln1_g[tid]; s_be[tid] = w.ln1_b[tid]; s_bk[tid] = w.bqk[128 + tid]; s_bv[tid] = w.bv[tid]; }
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) umma::mbar_init(&bar_w[i], 1);
+    umma::mbar_fence_init();
+    umma::mbar_expect_tx(bar_w, 3 * WIMG_BYTES);
+    umma::bulk_g2s(smem + ST_W, w.wimg_kv, 3 * WIMG_BYTES, bar_w);
+  }
+  if (warp == 0) umma::tmem_alloc<512>(tmem_slot);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tm = *tmem_slot, sb = umma::smem_u32(smem);
+  const uint32_t lane_addr = tm + ((uint32_t)(q4 * 32) << 16);
+  uint32_t ph_g = 0, ph_m1 = 0, ph_m2 = 0;
+  bool w_ready = false;
+  const float invS = 1.0f / (float)S;
+
+  const long long nitems = (long long)B * npix;
+  for (long long it = blockIdx.x; it < nitems; it += gridDim.x) {
+    const int b = (int)(it / npix), pix = (int)(it % npix);
+    for (int tl = 0; tl < ntile; ++tl) {
+      const int t0 = tl * 128;
+      const int nvalid = Te - t0 < 128 ? Te - t0 : 128;
+      // guidance tile of (b, tl) -> ST_G (the previous V image there is dead: its MMA2 was waited)
+      if (tid == 0) {
+        umma::mbar_expect_tx(bar_g, WIMG_BYTES);
+        umma::bulk_g2s(smem + ST_G, timg + ((long long)b * ntile + tl) * (128 * 128), WIMG_BYTES, bar_g);
+      }
+      ln_rows_to_tile(X + (((long long)b * Te + t0) * npix + pix) * 128, (long long)npix * 128, nvalid, smem + ST_XN, s_g,
+                      s_be, warp, 8, lane);
+      umma::fence_proxy_async();
+      umma::fence_before_sync();
+      __syncthreads();
+      // ---- k = [xn | g] [Wk_x | Wk_g]^T (cols 0..127), v = xn Wv^T (cols 128..255)
+      if (tid == 0) {
+        umma::fence_after_sync();
+        if (!w_ready) { umma::mbar_wait(bar_w, 0); w_ready = true; }
+        umma::mbar_wait(bar_g, ph_g);
+        issue_gemm_k128(tm + ST_TM_KV, sb + ST_XN, LBO_T, sb + ST_W, LBO_W, IDESC_128x128, false);
+        issue_gemm_k128(tm + ST_TM_KV, sb + ST_G, LBO_W, sb + ST_W + WIMG_BYTES, LBO_W, IDESC_128x128, true);
+        issue_gemm_k128(tm + ST_TM_KV + 128, sb + ST_XN, LBO_T, sb + ST_W + 2 * WIMG_BYTES, LBO_W, IDESC_128x128, false);
+        umma::mma_commit(bar_m1);
+      }
+      ph_g ^= 1;
+      umma::mbar_wait(bar_m1, ph_m1); ph_m1 ^= 1;
+      umma::fence_after_sync();
+      // ---- epilogue: warps 0-3 -> phi(k) image (over the LN tile), warps 4-7 -> [v/S | 1] image (over the g tile)
+      {
+        const bool live = row < nvalid;
+        uint8_t* img = smem + (half == 0 ? ST_XN : ST_G);
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          float v[32];
+          umma::tmem_ld32(lane_addr + ST_TM_KV + half * 128 + cc * 32, v);
+          const float* bb = (half == 0 ? s_bk : s_bv) + cc * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float a = v[i] + bb[i];
+            a = half == 0 ? (a > 0.0f ? a + 1.0f : __expf(a)) : a * invS;
+            v[i] = live ? a : 0.0f;
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(img + (cc * 4 + c) * LBO_V + row * 16) =
+                make_uint4(umma::pack_bf16x2(v[c * 8], v[c * 8 + 1]), umma::pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
+                           umma::pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), umma::pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]));
+        }
+        if (half == 1) {   // ones column (n = 128) and zero padding (n = 129..143)
+          *reinterpret_cast<uint4*>(smem + ST_G + 16 * LBO_V + row * 16) = make_uint4(live ? 0x00003F80u : 0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(smem + ST_G + 17 * LBO_V + row * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      umma::fence_proxy_async();
+      umma::fence_before_sync();
+      __syncthreads();
+      // ---- KV (+)= K^T [V | 1]  (contract over the 128 tokens of this tile)
+      if (tid == 0) {
+        umma::fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma::mma_bf16_ss(tm + ST_TM_ACC, umma::make_smem_desc(sb + ST_XN + k * 256, 128, LBO_V),
+                            umma::make_smem_desc(sb + ST_G + k * 256, 128, LBO_V), IDESC_KV, (tl > 0 || k > 0) ? 1u : 0u);
+        umma::mma_commit(bar_m2);
+      }
+      umma::mbar_wait(bar_m2, ph_m2); ph_m2 ^= 1;
+      umma::fence_after_sync();
+    }
+    // ---- state[b][pix]: thread = k-feature (h, d): KV[h][d][0..31] and Ksum[h*32+d]
+    if (half == 0) {
+      const int h = row >> 5;
+      float v[32], ks[8];
+      umma::tmem_ld32(lane_addr + ST_TM_ACC + h * 32, v);
+      umma::tmem_ld8(lane_addr + ST_TM_ACC + 128, ks);
+      float* o = state + it * kStateFloats;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) st4(o + row * 32 + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+      o[4096 + row] = ks[0];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+  }
+  if (warp == 0) umma::tmem_dealloc<512>(tm);
+}
+
+// ================================================================================================
+// Weight ring of the apply kernel: 10 images per item in consumption order
+//   0: Wq_x  1: Wq_g  2: W1_0  3: W2_0  4: W1_1  5: W2_1  6: W1_2  7: W2_2  8: W1_3  9: W2_3
+__global__ void __launch_bounds__(256, 1)
+class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, const __nv_bfloat16* __restrict__ timg,
+                        const float* __restrict__ state, const float* __restrict__ pad_state, int B, int Te, int npix,
+                        int S, int out_mode, ClassFastW w) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* s_g1 = reinterpret_cast<float*>(smem + AP_PAR);
+  float* s_be1 = s_g1 + 128;
+  float* s_g2 = s_be1 + 128;
+  float* s_be2 = s_g2 + 128;
+  float* s_bq = s_be2 + 128;
+  float* s_b1 = s_bq + 128;
+  float* s_b2 = s_b1 + 512;
+  float* s_red = s_b2 + 128;                       // [2 halves][128 rows][2]
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + AP_BAR);    // [2]
+  uint64_t* bar_empty = bar_full + 2;                                  // [2]
+  uint64_t* bar_g = bar_full + 4;
+  uint64_t* bar_acc = bar_full + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 6);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q4 = warp & 3, half = warp >> 2;
+  const int row = q4 * 32 + lane;
+  const int ntile = (Te + 127) / 128;
+  const long long nitems = (long long)B * npix * ntile;
+  long long mine = 0;
+  for (long long i = blockIdx.x; i < nitems; i += gridDim.x) ++mine;
+  const long long total_loads = mine * 10;
+
+  if (tid < 128) {
+    s_g1[tid] = w.ln1_g[tid]; s_be1[tid] = w.ln1_b[tid]; s_g2[tid] = w.ln2_g[tid]; s_be2[tid] = w.ln2_b[tid];
+    s_bq[tid] = w.bqk[tid]; s_b2[tid] = w.b2[tid];
+  }
+  for (int i = tid; i < 512; i += 256) s_b1[i] = w.b1[i];
+  // Bstate: zero once; only the block-diagonal groups are rewritten per item
+  for (int i = tid; i < (int)(18 * LBO_V / 16); i += 256) reinterpret_cast<uint4*>(smem + AP_BST)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) {
+    for (int i = 0; i < 6; ++i) umma::mbar_init(&bar_full[i], 1);
+    umma::mbar_fence_init();
+  }
+  if (warp == 0) umma::tmem_alloc<512>(tmem_slot);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tm = *tmem_slot, sb = umma::smem_u32(smem);
+  const uint32_t lane_addr = tm + ((uint32_t)(q4 * 32) << 16);
+
+  auto issue_load = [&](long long n) {       // thread 0
+    if (n < total_loads) {
+      int s = (int)(n & 1);
+      umma::mbar_expect_tx(&bar_full[s], WIMG_BYTES);
+      umma::bulk_g2s(smem + AP_RING + s * WIMG_BYTES, reinterpret_cast<const uint8_t*>(w.wimg_apply) + (n % 10) * WIMG_BYTES,
+                     WIMG_BYTES, &bar_full[s]);
+    }
+  };
+  // thread 0: consume ring image `nimg` with an 8-k-step GEMM, then refill the other slot
+  long long nimg = 0;
+  auto ring_gemm = [&](uint32_t d_tmem, uint32_t a_addr, uint32_t lbo_a, bool acc) {
+    int slot = (int)(nimg & 1);
+    umma::mbar_wait(&bar_full[slot], (uint32_t)((nimg >> 1) & 1));
+    issue_gemm_k128(d_tmem, a_addr, lbo_a, sb + AP_RING + slot * WIMG_BYTES, LBO_W, IDESC_128x128, acc);
+    umma::mma_commit(&bar_empty[slot]);
+    if (nimg > 0 && nimg + 1 < total_loads) {
+      umma::mbar_wait(&bar_empty[(nimg - 1) & 1], (uint32_t)(((nimg - 1) >> 1) & 1));
+      issue_load(nimg + 1);
+    }
+    ++nimg;
+  };
+  if (tid == 0) issue_load(0);
+  if (tid == 0) issue_load(1);
+  uint32_t ph_g = 0, ph_acc = 0;
+  const float fS = (float)S;
+
+  for (long long it = blockIdx.x; it < nitems; it += gridDim.x) {
+    const int tl = (int)(it % ntile);
+    const long long bp = it / ntile;
+    const int b = (int)(bp / npix), pix = (int)(bp % npix);
+    const int t0 = tl * 128;
+    const int nvalid = Te - t0 < 128 ? Te - t0 : 128;
+    const float* xrow0 = X + (((long long)b * Te + t0) * npix + pix) * 128;
+    const long long rstride = (long long)npix * 128;
+    if (tid == 0) {
+      umma::mbar_expect_tx(bar_g, WIMG_BYTES);
+      umma::bulk_g2s(smem + AP_GH, timg + ((long long)b * ntile + tl) * (128 * 128), WIMG_BYTES, bar_g);
+    }
+    ln_rows_to_tile(xrow0, rstride, nvalid, smem + AP_XN, s_g1, s_be1, warp, 8, lane);
+    // ---- Bstate block-diagonal groups: thread k = (h, d) owns row k of [128 x 144]
+    if (tid < 128) {
+      const int h = tid >> 5;
+      const float* sp = state + bp * kStateFloats;
+      float kv[32];
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float4 a = ld4(sp + tid * 32 + i), pz = ld4(pad_state + tid * 32 + i);
+        kv[i] = a.x + pz.x; kv[i + 1] = a.y + pz.y; kv[i + 2] = a.z + pz.z; kv[i + 3] = a.w + pz.w;
+      }
+      const float ks = sp[4096 + tid] + pad_state[4096 + tid];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(smem + AP_BST + (h * 4 + j) * LBO_V + tid * 16) =
+            make_uint4(umma::pack_bf16x2(kv[j * 8], kv[j * 8 + 1]), umma::pack_bf16x2(kv[j * 8 + 2], kv[j * 8 + 3]),
+                       umma::pack_bf16x2(kv[j * 8 + 4], kv[j * 8 + 5]), umma::pack_bf16x2(kv[j * 8 + 6], kv[j * 8 + 7]));
+      uint32_t kb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(ks));
+      uint4 dz = make_uint4(0u, 0u, 0u, 0u);                  // n = 128 + h holds Ksum for rows of head h
+      if (h == 0) dz.x = kb; else if (h == 1) dz.x = kb << 16; else if (h == 2) dz.y = kb; else dz.y = kb << 16;
+      *reinterpret_cast<uint4*>(smem + AP_BST + 16 * LBO_V + tid * 16) = dz;
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    // ---- q = [xn | g] [Wq_x | Wq_g]^T
+    if (tid == 0) {
+      umma::fence_after_sync();
+      ring_gemm(tm + AP_TM_Q, sb + AP_XN, LBO_T, false);
+      umma::mbar_wait(bar_g, ph_g);
+      ring_gemm(tm + AP_TM_Q, sb + AP_GH, LBO_W, true);
+      umma::mma_commit(bar_acc);
+    }
+    ph_g ^= 1;
+    umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
+    umma::fence_after_sync();
+    // ---- phi(q) -> Q image (thread = (row, 64-column half))
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      float v[32];
+      umma::tmem_ld32(lane_addr + AP_TM_Q + half * 64 + cc * 32, v);
+      const float* bb = s_bq + half * 64 + cc * 32;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { float a = v[i] + bb[i]; v[i] = a > 0.0f ? a + 1.0f : __expf(a); }
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(smem + AP_Q + (half * 8 + cc * 4 + c) * LBO_V + row * 16) =
+            make_uint4(umma::pack_bf16x2(v[c * 8], v[c * 8 + 1]), umma::pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
+                       umma::pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), umma::pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]));
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    // ---- [num | den] = phi(q) Bstate
+    if (tid == 0) {
+      umma::fence_after_sync();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma::mma_bf16_ss(tm + AP_TM_ND, umma::make_smem_desc(sb + AP_Q + k * 2 * LBO_V, LBO_V, 128),
+                          umma::make_smem_desc(sb + AP_BST + k * 256, 128, LBO_V), IDESC_APPLY, k > 0);
+      umma::mma_commit(bar_acc);
+    }
+    umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
+    umma::fence_after_sync();
+    // ---- x1 = x + num/(den+eps)*S ; z -> global ; LN2(x1) -> AP_XN
+    float x1[64];
+    const bool live = row < nvalid;
+    const long long grow = (((long long)b * Te + t0 + row) * npix + pix) * 128 + half * 64;
+    {
+      float den[8];
+      umma::tmem_ld8(lane_addr + AP_TM_ND + 128, den);
+      float zs[2] = {fS / (den[half * 2] + 1e-6f), fS / (den[half * 2 + 1] + 1e-6f)};
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        float v[32];
+        umma::tmem_ld32(lane_addr + AP_TM_ND + half * 64 + cc * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float4 x = live ? ld4(X + grow + cc * 32 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float a0 = x.x + v[i] * zs[cc], a1 = x.y + v[i + 1] * zs[cc], a2 = x.z + v[i + 2] * zs[cc], a3 = x.w + v[i + 3] * zs[cc];
+          x1[cc * 32 + i] = a0; x1[cc * 32 + i + 1] = a1; x1[cc * 32 + i + 2] = a2; x1[cc * 32 + i + 3] = a3;
+          s1 += (a0 + a1) + (a2 + a3);
+          s2 += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+          if (live) {
+            if (out_mode == 0) st4(Xout + grow + cc * 32 + i, make_float4(x.x + a0, x.y + a1, x.z + a2, x.w + a3));
+            else st4(Xout + grow + cc * 32 + i, make_float4(a0, a1, a2, a3));
+          }
+        }
+      }
+      s_red[(half * 128 + row) * 2] = s1;
+      s_red[(half * 128 + row) * 2 + 1] = s2;
+    }
+    __syncthreads();
+    {
+      float s1 = s_red[row * 2] + s_red[(128 + row) * 2];
+      float s2 = s_red[row * 2 + 1] + s_red[(128 + row) * 2 + 1];
+      float mean = s1 * (1.0f / 128.0f);
+      float var = fmaxf(s2 * (1.0f / 128.0f) - mean * mean, 0.0f);
+      float rstd = rsqrtf(var + 1e-5f);
+      const float* gg = s_g2 + half * 64;
+      const float* bb = s_be2 + half * 64;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float y[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = live ? (x1[c * 8 + i] - mean) * rstd * gg[c * 8 + i] + bb[c * 8 + i] : 0.0f;
+        *reinterpret_cast<uint4*>(smem + AP_XN + (half * 8 + c) * LBO_V + row * 16) =
+            make_uint4(umma::pack_bf16x2(y[0], y[1]), umma::pack_bf16x2(y[2], y[3]), umma::pack_bf16x2(y[4], y[5]),
+                       umma::pack_bf16x2(y[6], y[7]));
+      }
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    // ---- MLP 128 -> 512 (ReLU) -> 128, hidden chunks of 128 (H reuses the q columns)
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      if (tid == 0) {
+        umma::fence_after_sync();
+        ring_gemm(tm + AP_TM_Q, sb + AP_XN, LBO_T, false);
+        umma::mma_commit(bar_acc);
+      }
+      umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
+      umma::fence_after_sync();
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        float v[32];
+        umma::tmem_ld32(lane_addr + AP_TM_Q + half * 64 + cc * 32, v);
+        const float* bb = s_b1 + j * 128 + half * 64 + cc * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bb[i], 0.0f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(smem + AP_GH + (half * 8 + cc * 4 + c) * LBO_V + row * 16) =
+              make_uint4(umma::pack_bf16x2(v[c * 8], v[c * 8 + 1]), umma::pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
+                         umma::pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), umma::pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]));
+      }
+      umma::fence_proxy_async();
+      umma::fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        umma::fence_after_sync();
+        ring_gemm(tm + AP_TM_Y, sb + AP_GH, LBO_V, j > 0);
+        umma::mma_commit(bar_acc);
+      }
+      umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;     // h (and H) may be overwritten by the next chunk
+      umma::fence_after_sync();
+    }
+    // ---- out = z + (Y + b2)
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      float v[32];
+      umma::tmem_ld32(lane_addr + AP_TM_Y + half * 64 + cc * 32, v);
+      if (live) {
+        const float* bb = s_b2 + half * 64 + cc * 32;
+        float* op = Xout + grow + cc * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float4 z = ld4(op + i);
+          st4(op + i, make_float4(z.x + (v[i] + bb[i]), z.y + (v[i + 1] + bb[i + 1]), z.z + (v[i + 2] + bb[i + 2]),
+                                  z.w + (v[i + 3] + bb[i + 3])));
+        }
+      }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+  }
+  if (warp == 0) umma::tmem_dealloc<512>(tm);
+}
+
+// ================================================================================================
+cudaError_t launch_class_state_fast(const float* X, const __nv_bfloat16* timg, float* state, int B, int Te, int npix,
+                                    int S, const ClassFastW& w, int num_sms, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(class_state_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  long long n = (long long)B * npix;
+  int grid = (int)(n < num_sms ? n : num_sms);
+  class_state_fast_kernel<<<grid, 256, ST_SMEM, st>>>(X, timg, state, B, Te, npix, S, w);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_class_apply_fast(const float* X, float* Xout, const __nv_bfloat16* timg, const float* state,
+                                    const float* pad_state, int B, int Te, int npix, int S, int out_mode,
+                                    const ClassFastW& w, int num_sms, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(class_apply_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AP_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  long long n = (long long)B * npix * ((Te + 127) / 128);
+  int grid = (int)(n < num_sms ? n : num_sms);
+  class_apply_fast_kernel<<<grid, 256, AP_SMEM, st>>>(X, Xout, timg, state, pad_state, B, Te, npix, S, out_mode, w);
+  return cudaGetLastError();
+}
+
+// text guidance [B][Te][128] fp32 -> per (image, 128-class tile) canonical dense bf16 images (rows >= Te are zero)
+__global__ void pack_text_img_kernel(const float* __restrict__ tg, __nv_bfloat16* __restrict__ timg, int B, int Te, int ntile) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * ntile * 128 * 128;
+  if (i >= total) return;
+  int k = (int)(i & 127), r = (int)((i >> 7) & 127);
+  long long bt = i >> 14;
+  int tl = (int)(bt % ntile), b = (int)(bt / ntile);
+  int t = tl * 128 + r;
+  float v = t < Te ? tg[((long long)b * Te + t) * 128 + k] : 0.0f;
+  timg[bt * (128 * 128) + (k >> 3) * (128 * 8) + r * 8 + (k & 7)] = __float2bfloat16(v);
+}
+cudaError_t launch_pack_text_img(const float* tg, __nv_bfloat16* timg, int B, int Te, cudaStream_t st) {
+  int ntile = (Te + 127) / 128;
+  long long total = (long long)B * ntile * 128 * 128;
+  pack_text_img_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tg, timg, B, Te, ntile);
+  return cudaGetLastError();
+}
+
+}  // namespace catseg

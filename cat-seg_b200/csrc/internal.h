@@ -129,6 +129,19 @@ cudaError_t run_decoder_exact(const float* X, const float* dg0, const float* dg1
                               float* scratch, int chunk, float* tap_up1, float* tap_up2, int* launches,
                               cudaStream_t st);
 
+// ---------------------------------------------------------------- fast_class.cu
+struct ClassFastW {
+  const __nv_bfloat16* wimg_kv;      // 3 images: Wk (LN(x) part), Wk (guidance part), Wv
+  const __nv_bfloat16* wimg_apply;   // 10 images: Wq_x, Wq_g, then W1_j, W2_j for j = 0..3
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *bqk, *bv, *b1, *b2;
+};
+cudaError_t launch_class_state_fast(const float* X, const __nv_bfloat16* timg, float* state, int B, int Te, int npix,
+                                    int S, const ClassFastW& w, int num_sms, cudaStream_t st);
+cudaError_t launch_class_apply_fast(const float* X, float* Xout, const __nv_bfloat16* timg, const float* state,
+                                    const float* pad_state, int B, int Te, int npix, int S, int out_mode,
+                                    const ClassFastW& w, int num_sms, cudaStream_t st);
+cudaError_t launch_pack_text_img(const float* tg, __nv_bfloat16* timg, int B, int Te, cudaStream_t st);
+
 // ---------------------------------------------------------------- fast_decoder.cu
 struct DecoderFastW {
   const __nv_bfloat16 *w1, *w2, *w3, *w4, *w5;   // UMMA weight images per stage (fast_decoder.cu)
