@@ -293,7 +293,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(BENCH_CONFIGS))
-    ap.add_argument("--precision", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--precision", default="fast", help="exact | fast | fast:<stage>[,<stage>]")
     ap.add_argument("--batch", type=int, default=0, help="override images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
