@@ -110,6 +110,7 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
         issue_gemm_k128(tm + ST_TM_KV + 128, sb + ST_XN, LBO_T, sb + ST_W + 2 * WIMG_BYTES, LBO_W, IDESC_128x128, false);
         umma::mma_commit(bar_m1);
       }
+      __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
       ph_g ^= 1;
       umma::mbar_wait(bar_m1, ph_m1); ph_m1 ^= 1;
       umma::fence_after_sync();
@@ -151,6 +152,7 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
                             umma::make_smem_desc(sb + ST_G + k * 256, 128, LBO_V), IDESC_KV, (tl > 0 || k > 0) ? 1u : 0u);
         umma::mma_commit(bar_m2);
       }
+      __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
       umma::mbar_wait(bar_m2, ph_m2); ph_m2 ^= 1;
       umma::fence_after_sync();
     }
@@ -290,6 +292,7 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
       ring_gemm(tm + AP_TM_Q, sb + AP_GH, LBO_W, true);
       umma::mma_commit(bar_acc);
     }
+    __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
     ph_g ^= 1;
     umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
     umma::fence_after_sync();
@@ -319,6 +322,7 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
                           umma::make_smem_desc(sb + AP_BST + k * 256, 128, LBO_V), IDESC_APPLY, k > 0);
       umma::mma_commit(bar_acc);
     }
+    __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
     umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
     umma::fence_after_sync();
     // ---- x1 = x + num/(den+eps)*S ; z -> global ; LN2(x1) -> AP_XN
@@ -380,6 +384,7 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
         ring_gemm(tm + AP_TM_Q, sb + AP_XN, LBO_T, false);
         umma::mma_commit(bar_acc);
       }
+      __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
       umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       umma::fence_after_sync();
 #pragma unroll 1
@@ -403,6 +408,7 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
         ring_gemm(tm + AP_TM_Y, sb + AP_GH, LBO_V, j > 0);
         umma::mma_commit(bar_acc);
       }
+      __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
       umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;     // h (and H) may be overwritten by the next chunk
       umma::fence_after_sync();
     }

@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(256, 1) band_conv_kernel(BandConvParams p) {
         }
         umma::mma_commit(bar_acc);
       }
+      __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
       umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       umma::fence_after_sync();
       // ---- epilogue: thread = padded raster row; the two warp sets take alternate tiles

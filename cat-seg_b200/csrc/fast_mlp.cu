@@ -98,6 +98,7 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w) {
         issue_gemm_k128(tm + 128, smem_base + SM_XN + TILE_BYTES_T, LBO_T, wb, LBO_W, IDESC_128x128, false);
         umma::mma_commit(&bar_mma[1]);
       }
+      __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
 #pragma unroll 1
       for (int t = 0; t < 2; ++t) {
         umma::mbar_wait(&bar_mma[t], par);                 // H_t ready
@@ -144,6 +145,7 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w) {
           issue_gemm_k128(tm + 256 + t * 128, smem_base + SM_H, LBO_T, wb, LBO_W, IDESC_128x128, j > 0);
           umma::mma_commit(&bar_mma[2 + t]);
         }
+        __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
       }
     }
     // ---- all MMAs of this pass done -> Y epilogue

@@ -139,6 +139,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
                             umma::make_smem_desc(sb + SM_XN + k * 2 * LBO_X, LBO_X, 128), IDESC_T, k > 0);
         umma::mma_commit(bar_a);
       }
+      __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
       // ---- while the MMA runs: stage this head's guidance terms [144 tok][q 32 | k 32] (fp32) in the P region,
       //      which is free until the softmax of this head (coalesced 128-byte rows, one latency)
       {
@@ -201,6 +202,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
                               umma::make_smem_desc(sb + SM_KH + k * 256, 128, 512), IDESC_S, k > 0);
         umma::mma_commit(bar_s);
       }
+      __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
       umma::mbar_wait(bar_s, ph_s); ph_s ^= 1;
       umma::fence_after_sync();
       // ---- softmax: two threads per query row (keys [72*half, 72*half+72)); tile 1 rows by quarter 0, lanes < 16
@@ -258,6 +260,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
                               umma::make_smem_desc(sb + SM_VH + k * 1024, 512, 128), IDESC_PV, k > 0);
         umma::mma_commit(bar_o);
       }
+      __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
       umma::mbar_wait(bar_o, ph_o); ph_o ^= 1;
       umma::fence_after_sync();
       // ---- O epilogue: thread = query row (tile 0: warps 0-3, tile 1: warp 4 lanes < 16)
@@ -292,6 +295,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
                           umma::make_smem_desc(sb + SM_O + k * 2 * LBO_X, LBO_X, 128), IDESC_T, k > 0);
       umma::mma_commit(bar_y);
     }
+    __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
     umma::mbar_wait(bar_y, ph_y); ph_y ^= 1;
     umma::fence_after_sync();
     if (tid == 0) issue_load(nload + 2);
