@@ -43,7 +43,8 @@ constexpr uint32_t AP_GH = AP_XN + TILE_BYTES_T;                   // guidance t
 constexpr uint32_t AP_Q = AP_GH + TILE_BYTES_T;                    // phi(q) image
 constexpr uint32_t AP_BST = AP_Q + TILE_BYTES_T;                   // Bstate [128 k x 144 n] MN-major, 18 n-groups
 constexpr uint32_t AP_PAR = AP_BST + 18 * LBO_V;                   // ln1 g,b ln2 g,b [512] bq[128] b1[512] b2[128] red[512]
-constexpr uint32_t AP_BAR = AP_PAR + (512 + 128 + 512 + 128 + 512) * 4;
+constexpr uint32_t AP_BAR = AP_PAR + (512 + 128 + 512 + 128 + 1024) * 4;
+static_assert(STG_BYTES <= TILE_BYTES_T + 18 * LBO_V, "staging tile must fit over the phi(q) + Bstate buffers");
 constexpr uint32_t AP_SMEM = AP_BAR + 10 * 8 + 16;
 constexpr uint32_t AP_TM_Q = 0, AP_TM_ND = 128, AP_TM_Y = 272;     // q / H: [0,128)  num|den: [128,272)  Y: [272,400)
 static_assert(ST_SMEM <= 232448 && AP_SMEM <= 232448, "shared memory budget");
@@ -177,7 +178,10 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
 // ================================================================================================
 // Weight ring of the apply kernel: 10 images per item in consumption order
 //   0: Wq_x  1: Wq_g  2: W1_0  3: W2_0  4: W1_1  5: W2_1  6: W1_2  7: W2_2  8: W1_3  9: W2_3
-__global__ void __launch_bounds__(256, 1)
+// 16 warps: TMEM lane quarter q4 = warp & 3 (rows), column quarter cq = warp >> 2 (32 columns = one head).
+// Residual I/O is coalesced: x is fetched warp-per-row into an fp32 staging tile (over the dead phi(q) /
+// Bstate buffers), updated in place by the row threads, and written back warp-per-row once per item.
+__global__ void __launch_bounds__(512, 1)
 class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, const __nv_bfloat16* __restrict__ timg,
                         const float* __restrict__ state, const float* __restrict__ pad_state, int B, int Te, int npix,
                         int S, int out_mode, ClassFastW w) {
@@ -189,13 +193,14 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
   float* s_bq = s_be2 + 128;
   float* s_b1 = s_bq + 128;
   float* s_b2 = s_b1 + 512;
-  float* s_red = s_b2 + 128;                       // [2 halves][128 rows][2]
+  float* s_red = s_b2 + 128;                       // [4 column quarters][128 rows][2]
+  float* stage = reinterpret_cast<float*>(smem + AP_Q);   // fp32 [128][STG_LD] over AP_Q + AP_BST
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + AP_BAR);    // [2]
   uint64_t* bar_empty = bar_full + 2;                                  // [2]
   uint64_t* bar_g = bar_full + 4;
   uint64_t* bar_acc = bar_full + 5;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 6);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q4 = warp & 3, half = warp >> 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q4 = warp & 3, cq = warp >> 2;
   const int row = q4 * 32 + lane;
   const int ntile = (Te + 127) / 128;
   const long long nitems = (long long)B * npix * ntile;
@@ -207,9 +212,7 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
     s_g1[tid] = w.ln1_g[tid]; s_be1[tid] = w.ln1_b[tid]; s_g2[tid] = w.ln2_g[tid]; s_be2[tid] = w.ln2_b[tid];
     s_bq[tid] = w.bqk[tid]; s_b2[tid] = w.b2[tid];
   }
-  for (int i = tid; i < 512; i += 256) s_b1[i] = w.b1[i];
-  // Bstate: zero once; only the block-diagonal groups are rewritten per item
-  for (int i = tid; i < (int)(18 * LBO_V / 16); i += 256) reinterpret_cast<uint4*>(smem + AP_BST)[i] = make_uint4(0u, 0u, 0u, 0u);
+  s_b1[tid] = w.b1[tid];
   if (tid == 0) {
     for (int i = 0; i < 6; ++i) umma::mbar_init(&bar_full[i], 1);
     umma::mbar_fence_init();
@@ -242,8 +245,7 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
     }
     ++nimg;
   };
-  if (tid == 0) issue_load(0);
-  if (tid == 0) issue_load(1);
+  if (tid == 0) { issue_load(0); issue_load(1); }
   uint32_t ph_g = 0, ph_acc = 0;
   const float fS = (float)S;
 
@@ -253,14 +255,14 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
     const int b = (int)(bp / npix), pix = (int)(bp % npix);
     const int t0 = tl * 128;
     const int nvalid = Te - t0 < 128 ? Te - t0 : 128;
-    const float* xrow0 = X + (((long long)b * Te + t0) * npix + pix) * 128;
     const long long rstride = (long long)npix * 128;
+    const long long row0off = (((long long)b * Te + t0) * npix + pix) * 128;
     if (tid == 0) {
       umma::mbar_expect_tx(bar_g, WIMG_BYTES);
       umma::bulk_g2s(smem + AP_GH, timg + ((long long)b * ntile + tl) * (128 * 128), WIMG_BYTES, bar_g);
     }
-    ln_rows_to_tile(xrow0, rstride, nvalid, smem + AP_XN, s_g1, s_be1, warp, 8, lane);
-    // ---- Bstate block-diagonal groups: thread k = (h, d) owns row k of [128 x 144]
+    ln_rows_to_tile(X + row0off, rstride, nvalid, smem + AP_XN, s_g1, s_be1, warp, 16, lane);
+    // ---- Bstate [128 k x 144 n] (MN-major, 18 n-groups): thread k = (h, d) writes its whole row
     if (tid < 128) {
       const int h = tid >> 5;
       const float* sp = state + bp * kStateFloats;
@@ -271,15 +273,22 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
         kv[i] = a.x + pz.x; kv[i + 1] = a.y + pz.y; kv[i + 2] = a.z + pz.z; kv[i + 3] = a.w + pz.w;
       }
       const float ks = sp[4096 + tid] + pad_state[4096 + tid];
+      const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<uint4*>(smem + AP_BST + (h * 4 + j) * LBO_V + tid * 16) =
-            make_uint4(umma::pack_bf16x2(kv[j * 8], kv[j * 8 + 1]), umma::pack_bf16x2(kv[j * 8 + 2], kv[j * 8 + 3]),
-                       umma::pack_bf16x2(kv[j * 8 + 4], kv[j * 8 + 5]), umma::pack_bf16x2(kv[j * 8 + 6], kv[j * 8 + 7]));
+      for (int gq = 0; gq < 16; ++gq) {
+        uint4 val = zero4;
+        if ((gq >> 2) == h) {
+          const int j = gq & 3;
+          val = make_uint4(umma::pack_bf16x2(kv[j * 8], kv[j * 8 + 1]), umma::pack_bf16x2(kv[j * 8 + 2], kv[j * 8 + 3]),
+                           umma::pack_bf16x2(kv[j * 8 + 4], kv[j * 8 + 5]), umma::pack_bf16x2(kv[j * 8 + 6], kv[j * 8 + 7]));
+        }
+        *reinterpret_cast<uint4*>(smem + AP_BST + gq * LBO_V + tid * 16) = val;
+      }
       uint32_t kb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(ks));
-      uint4 dz = make_uint4(0u, 0u, 0u, 0u);                  // n = 128 + h holds Ksum for rows of head h
+      uint4 dz = zero4;                                       // n = 128 + h holds Ksum for the rows of head h
       if (h == 0) dz.x = kb; else if (h == 1) dz.x = kb << 16; else if (h == 2) dz.y = kb; else dz.y = kb << 16;
       *reinterpret_cast<uint4*>(smem + AP_BST + 16 * LBO_V + tid * 16) = dz;
+      *reinterpret_cast<uint4*>(smem + AP_BST + 17 * LBO_V + tid * 16) = zero4;
     }
     umma::fence_proxy_async();
     umma::fence_before_sync();
@@ -292,21 +301,20 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
       ring_gemm(tm + AP_TM_Q, sb + AP_GH, LBO_W, true);
       umma::mma_commit(bar_acc);
     }
-    __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
+    __syncwarp();
     ph_g ^= 1;
     umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
     umma::fence_after_sync();
-    // ---- phi(q) -> Q image (thread = (row, 64-column half))
-#pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
+    // ---- phi(q) -> Q image (thread = (row, 32-column quarter))
+    {
       float v[32];
-      umma::tmem_ld32(lane_addr + AP_TM_Q + half * 64 + cc * 32, v);
-      const float* bb = s_bq + half * 64 + cc * 32;
+      umma::tmem_ld32(lane_addr + AP_TM_Q + cq * 32, v);
+      const float* bb = s_bq + cq * 32;
 #pragma unroll
       for (int i = 0; i < 32; ++i) { float a = v[i] + bb[i]; v[i] = a > 0.0f ? a + 1.0f : __expf(a); }
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<uint4*>(smem + AP_Q + (half * 8 + cc * 4 + c) * LBO_V + row * 16) =
+        *reinterpret_cast<uint4*>(smem + AP_Q + (cq * 4 + c) * LBO_V + row * 16) =
             make_uint4(umma::pack_bf16x2(v[c * 8], v[c * 8 + 1]), umma::pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
                        umma::pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), umma::pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]));
     }
@@ -322,53 +330,61 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
                           umma::make_smem_desc(sb + AP_BST + k * 256, 128, LBO_V), IDESC_APPLY, k > 0);
       umma::mma_commit(bar_acc);
     }
-    __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
+    __syncwarp();
     umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
     umma::fence_after_sync();
-    // ---- x1 = x + num/(den+eps)*S ; z -> global ; LN2(x1) -> AP_XN
-    float x1[64];
-    const bool live = row < nvalid;
-    const long long grow = (((long long)b * Te + t0 + row) * npix + pix) * 128 + half * 64;
+    // ---- x tile -> staging (warp per row, coalesced; phi(q) and Bstate are dead now)
     {
-      float den[8];
+      float4 xv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int r = warp * 8 + i;
+        xv[i] = r < nvalid ? ld4(X + row0off + (long long)r * rstride + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) st4(stage + (warp * 8 + i) * STG_LD + lane * 4, xv[i]);
+    }
+    __syncthreads();
+    // ---- x1 = x + num/(den+eps)*S ; z -> staging ; LN2 statistics
+    float x1[32];
+    const bool live = row < nvalid;
+    {
+      float den[8], v[32];
       umma::tmem_ld8(lane_addr + AP_TM_ND + 128, den);
-      float zs[2] = {fS / (den[half * 2] + 1e-6f), fS / (den[half * 2 + 1] + 1e-6f)};
+      umma::tmem_ld32(lane_addr + AP_TM_ND + cq * 32, v);
+      const float dsel = cq == 0 ? den[0] : (cq == 1 ? den[1] : (cq == 2 ? den[2] : den[3]));
+      const float zs = fS / (dsel + 1e-6f);
+      float* sp = stage + row * STG_LD + cq * 32;
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        float v[32];
-        umma::tmem_ld32(lane_addr + AP_TM_ND + half * 64 + cc * 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          float4 x = live ? ld4(X + grow + cc * 32 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-          float a0 = x.x + v[i] * zs[cc], a1 = x.y + v[i + 1] * zs[cc], a2 = x.z + v[i + 2] * zs[cc], a3 = x.w + v[i + 3] * zs[cc];
-          x1[cc * 32 + i] = a0; x1[cc * 32 + i + 1] = a1; x1[cc * 32 + i + 2] = a2; x1[cc * 32 + i + 3] = a3;
-          s1 += (a0 + a1) + (a2 + a3);
-          s2 += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
-          if (live) {
-            if (out_mode == 0) st4(Xout + grow + cc * 32 + i, make_float4(x.x + a0, x.y + a1, x.z + a2, x.w + a3));
-            else st4(Xout + grow + cc * 32 + i, make_float4(a0, a1, a2, a3));
-          }
-        }
+      for (int i = 0; i < 32; i += 4) {
+        float4 x = ld4(sp + i);
+        float a0 = fmaf(v[i], zs, x.x), a1 = fmaf(v[i + 1], zs, x.y), a2 = fmaf(v[i + 2], zs, x.z), a3 = fmaf(v[i + 3], zs, x.w);
+        x1[i] = a0; x1[i + 1] = a1; x1[i + 2] = a2; x1[i + 3] = a3;
+        s1 += (a0 + a1) + (a2 + a3);
+        s2 += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+        if (out_mode == 0) st4(sp + i, make_float4(x.x + a0, x.y + a1, x.z + a2, x.w + a3));
+        else st4(sp + i, make_float4(a0, a1, a2, a3));
       }
-      s_red[(half * 128 + row) * 2] = s1;
-      s_red[(half * 128 + row) * 2 + 1] = s2;
+      s_red[(cq * 128 + row) * 2] = s1;
+      s_red[(cq * 128 + row) * 2 + 1] = s2;
     }
     __syncthreads();
     {
-      float s1 = s_red[row * 2] + s_red[(128 + row) * 2];
-      float s2 = s_red[row * 2 + 1] + s_red[(128 + row) * 2 + 1];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { s1 += s_red[(c * 128 + row) * 2]; s2 += s_red[(c * 128 + row) * 2 + 1]; }
       float mean = s1 * (1.0f / 128.0f);
       float var = fmaxf(s2 * (1.0f / 128.0f) - mean * mean, 0.0f);
       float rstd = rsqrtf(var + 1e-5f);
-      const float* gg = s_g2 + half * 64;
-      const float* bb = s_be2 + half * 64;
+      const float* gg = s_g2 + cq * 32;
+      const float* bb = s_be2 + cq * 32;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         float y[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) y[i] = live ? (x1[c * 8 + i] - mean) * rstd * gg[c * 8 + i] + bb[c * 8 + i] : 0.0f;
-        *reinterpret_cast<uint4*>(smem + AP_XN + (half * 8 + c) * LBO_V + row * 16) =
+        *reinterpret_cast<uint4*>(smem + AP_XN + (cq * 4 + c) * LBO_V + row * 16) =
             make_uint4(umma::pack_bf16x2(y[0], y[1]), umma::pack_bf16x2(y[2], y[3]), umma::pack_bf16x2(y[4], y[5]),
                        umma::pack_bf16x2(y[6], y[7]));
       }
@@ -384,19 +400,18 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
         ring_gemm(tm + AP_TM_Q, sb + AP_XN, LBO_T, false);
         umma::mma_commit(bar_acc);
       }
-      __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
+      __syncwarp();
       umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       umma::fence_after_sync();
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
+      {
         float v[32];
-        umma::tmem_ld32(lane_addr + AP_TM_Q + half * 64 + cc * 32, v);
-        const float* bb = s_b1 + j * 128 + half * 64 + cc * 32;
+        umma::tmem_ld32(lane_addr + AP_TM_Q + cq * 32, v);
+        const float* bb = s_b1 + j * 128 + cq * 32;
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bb[i], 0.0f);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<uint4*>(smem + AP_GH + (half * 8 + cc * 4 + c) * LBO_V + row * 16) =
+          *reinterpret_cast<uint4*>(smem + AP_GH + (cq * 4 + c) * LBO_V + row * 16) =
               make_uint4(umma::pack_bf16x2(v[c * 8], v[c * 8 + 1]), umma::pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
                          umma::pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), umma::pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]));
       }
@@ -408,29 +423,32 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
         ring_gemm(tm + AP_TM_Y, sb + AP_GH, LBO_V, j > 0);
         umma::mma_commit(bar_acc);
       }
-      __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
+      __syncwarp();
       umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;     // h (and H) may be overwritten by the next chunk
       umma::fence_after_sync();
     }
-    // ---- out = z + (Y + b2)
-#pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
+    // ---- out = z + (Y + b2): finish in the staging tile, then one coalesced store per row
+    {
       float v[32];
-      umma::tmem_ld32(lane_addr + AP_TM_Y + half * 64 + cc * 32, v);
-      if (live) {
-        const float* bb = s_b2 + half * 64 + cc * 32;
-        float* op = Xout + grow + cc * 32;
+      umma::tmem_ld32(lane_addr + AP_TM_Y + cq * 32, v);
+      const float* bb = s_b2 + cq * 32;
+      float* sp = stage + row * STG_LD + cq * 32;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          float4 z = ld4(op + i);
-          st4(op + i, make_float4(z.x + (v[i] + bb[i]), z.y + (v[i + 1] + bb[i + 1]), z.z + (v[i + 2] + bb[i + 2]),
-                                  z.w + (v[i + 3] + bb[i + 3])));
-        }
+      for (int i = 0; i < 32; i += 4) {
+        float4 z = ld4(sp + i);
+        st4(sp + i, make_float4(z.x + (v[i] + bb[i]), z.y + (v[i + 1] + bb[i + 1]), z.z + (v[i + 2] + bb[i + 2]),
+                                z.w + (v[i + 3] + bb[i + 3])));
       }
     }
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int r = warp * 8 + i;
+      if (r < nvalid) st4(Xout + row0off + (long long)r * rstride + lane * 4, ld4(stage + r * STG_LD + lane * 4));
+    }
+    __syncthreads();      // the staging tile (phi(q) / Bstate buffers) is rebuilt by the next item
   }
   if (warp == 0) umma::tmem_dealloc<512>(tm);
 }
@@ -461,7 +479,7 @@ cudaError_t launch_class_apply_fast(const float* X, float* Xout, const __nv_bflo
   }
   long long n = (long long)B * npix * ((Te + 127) / 128);
   int grid = (int)(n < num_sms ? n : num_sms);
-  class_apply_fast_kernel<<<grid, 256, AP_SMEM, st>>>(X, Xout, timg, state, pad_state, B, Te, npix, S, out_mode, w);
+  class_apply_fast_kernel<<<grid, 512, AP_SMEM, st>>>(X, Xout, timg, state, pad_state, B, Te, npix, S, out_mode, w);
   return cudaGetLastError();
 }
 

@@ -16,13 +16,14 @@ namespace catseg {
 using namespace fast;
 
 namespace {
-constexpr int MLP_THREADS = 256;
+constexpr int MLP_THREADS = 512;                                 // 16 warps: 4 lane quarters x 4 column quarters
 constexpr uint32_t SM_RING = 0;                                   // 3 x 32 KiB weight ring
 constexpr uint32_t SM_XN = SM_RING + 3 * WIMG_BYTES;              // 2 tiles LN(x) bf16
 constexpr uint32_t SM_H = SM_XN + 2 * TILE_BYTES_T;               // hidden chunk bf16
 constexpr uint32_t SM_PAR = SM_H + TILE_BYTES_T;                  // b1[512] b2[128] g[128] b[128] floats
 constexpr uint32_t SM_BAR = SM_PAR + (512 + 128 + 128 + 128) * 4; // 7 mbarriers + tmem ptr
 constexpr uint32_t MLP_SMEM = SM_BAR + 8 * 8 + 16;
+static_assert(STG_BYTES <= 3 * TILE_BYTES_T, "the fp32 staging tile aliases the LN tiles + hidden chunk");
 }  // namespace
 
 template <int ACT>   // 0 = GELU (Swin), 1 = ReLU (class layer)
@@ -67,8 +68,9 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w) {
   };
   if (tid == 0) { issue_load(0); issue_load(1); issue_load(2); }
 
-  const int q = warp & 3, half = warp >> 2;
+  const int q = warp & 3, cq = warp >> 2;                // TMEM lane quarter, column quarter (32 columns)
   const int row = q * 32 + lane;                         // row of the tile owned by this thread
+  float* stage = reinterpret_cast<float*>(smem + SM_XN); // fp32 staging tile (LN tiles + h are dead by then)
   const uint32_t lane_addr = tm + ((uint32_t)(q * 32) << 16);
   long long g = 0;                                       // running hidden-chunk counter of this CTA
 
@@ -104,13 +106,12 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w) {
         umma::mbar_wait(&bar_mma[t], par);                 // H_t ready
         umma::fence_after_sync();
         if (t == 1 && tid == 0) issue_load(2 * g + 3);     // MMA1(b) done: the W1_j slot is free
-        // ---- H_t -> bias -> act -> bf16 (64 columns per thread)
-        uint4 packed[8];
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
+        // ---- H_t -> bias -> act -> bf16 (32 columns per thread)
+        uint4 packed[4];
+        {
           float v[32];
-          umma::tmem_ld32(lane_addr + t * 128 + half * 64 + cc * 32, v);
-          const float* bb = s_b1 + j * 128 + half * 64 + cc * 32;
+          umma::tmem_ld32(lane_addr + t * 128 + cq * 32, v);
+          const float* bb = s_b1 + j * 128 + cq * 32;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             float a = v[i] + bb[i];
@@ -118,8 +119,8 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w) {
           }
 #pragma unroll
           for (int c = 0; c < 4; ++c)
-            packed[cc * 4 + c] = make_uint4(umma::pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]), umma::pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
-                                            umma::pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), umma::pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]));
+            packed[c] = make_uint4(umma::pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]), umma::pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
+                                   umma::pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), umma::pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]));
         }
         // ---- the h buffer is free once the previous MMA2 has completed
         if (t == 0) {
@@ -132,8 +133,8 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w) {
         }
         umma::fence_after_sync();
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(smem + SM_H + (half * 8 + c) * LBO_T + row * 16) = packed[c];
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(smem + SM_H + (cq * 4 + c) * LBO_T + row * 16) = packed[c];
         umma::fence_proxy_async();
         umma::fence_before_sync();
         __syncthreads();
@@ -152,24 +153,34 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w) {
     umma::mbar_wait(&bar_mma[3], (uint32_t)((g - 1) & 1));
     umma::fence_after_sync();
     if (tid == 0) issue_load(2 * g + 2);
+    // Y_t + b2 -> fp32 staging tile (thread = row), then X[row] += stage[row] with warp-per-row coalesced
+    // 512-byte accesses (a per-thread-row global read-modify-write serialises on memory latency).
 #pragma unroll 1
     for (int t = 0; t < 2; ++t) {
-      long long r = row0 + t * 128 + row;
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
+      {
         float v[32];
-        umma::tmem_ld32(lane_addr + 256 + t * 128 + half * 64 + cc * 32, v);
-        if (r < ntok) {
-          float* xp = X + r * 128 + half * 64 + cc * 32;
-          const float* bb = s_b2 + half * 64 + cc * 32;
+        umma::tmem_ld32(lane_addr + 256 + t * 128 + cq * 32, v);
+        const float* bb = s_b2 + cq * 32;
+        float* sp = stage + row * STG_LD + cq * 32;
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float4 x = ld4(xp + i);
-            st4(xp + i, make_float4(x.x + (v[i] + bb[i]), x.y + (v[i + 1] + bb[i + 1]), x.z + (v[i + 2] + bb[i + 2]),
-                                    x.w + (v[i + 3] + bb[i + 3])));
-          }
+        for (int i = 0; i < 32; i += 4) st4(sp + i, make_float4(v[i] + bb[i], v[i + 1] + bb[i + 1], v[i + 2] + bb[i + 2], v[i + 3] + bb[i + 3]));
+      }
+      __syncthreads();
+      {
+        const long long rbase = row0 + t * 128;
+        float4 xv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          long long r = rbase + warp * 8 + i;
+          xv[i] = r < ntok ? ld4(X + r * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          long long r = rbase + warp * 8 + i;
+          if (r < ntok) st4(X + r * 128 + lane * 4, f4add(xv[i], ld4(stage + (warp * 8 + i) * STG_LD + lane * 4)));
         }
       }
+      __syncthreads();
     }
     umma::fence_before_sync();
     __syncthreads();          // TMEM and the LN tiles may be overwritten by the next pass
