@@ -62,8 +62,8 @@ struct BandCfg {
   static constexpr int GOUT = HEAD ? 1 : NREAL / 16;
   static constexpr uint32_t SM_W = IMG_BYTES;
   static constexpr uint32_t SM_SC = SM_W + NSLOT * WBYTES;            // scale[CIN], shift[CIN]
-  static constexpr uint32_t SM_ST = SM_SC + 2 * CIN * 4;              // [8 warps][GOUT][2]
-  static constexpr uint32_t SM_BAR = (SM_ST + 8 * GOUT * 2 * 4 + 15) / 16 * 16;
+  static constexpr uint32_t SM_ST = SM_SC + 2 * CIN * 4;              // [16 warps][GOUT][2]
+  static constexpr uint32_t SM_BAR = (SM_ST + 16 * GOUT * 2 * 4 + 15) / 16 * 16;
   static constexpr uint32_t SMEM = SM_BAR + (2 * NSLOT + 2) * 8 + 16;
   static constexpr uint32_t IDESC = umma::make_idesc_bf16(128, NOUT);
   static_assert(NTILES * NOUT <= 512, "TMEM columns");
@@ -72,7 +72,7 @@ struct BandCfg {
 };
 
 template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD>
-__global__ void __launch_bounds__(256, 1) band_conv_kernel(BandConvParams p) {
+__global__ void __launch_bounds__(512, 1) band_conv_kernel(BandConvParams p) {
   using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD>;
   extern __shared__ __align__(1024) uint8_t smem[];
   float* s_scale = reinterpret_cast<float*>(smem + C::SM_SC);
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256, 1) band_conv_kernel(BandConvParams p) {
   uint64_t* bar_empty = bar_full + C::NSLOT;                             // [NSLOT]
   uint64_t* bar_acc = bar_empty + C::NSLOT;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 1);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q4 = warp & 3, half = warp >> 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q4 = warp & 3, tgrp = warp >> 2;   // 16 warps
 
   const long long nitems = (long long)p.nslice * C::NB;
   long long mine = 0;
@@ -146,8 +146,8 @@ __global__ void __launch_bounds__(256, 1) band_conv_kernel(BandConvParams p) {
     // ---- stage the padded band image (bf16, canonical K-major, rows = padded raster positions)
     {
       const int y_first = band * BR - 1;
-#pragma unroll 4
-      for (int idx = tid; idx < C::NP * C::KCH; idx += 256) {
+#pragma unroll 8
+      for (int idx = tid; idx < C::NP * C::KCH; idx += 512) {
         const int pp = idx / C::KCH, c = idx % C::KCH;
         const int yy = y_first + pp / C::PW, xx = pp % C::PW - 1;
         uint4 val = make_uint4(0u, 0u, 0u, 0u);
@@ -226,9 +226,9 @@ __global__ void __launch_bounds__(256, 1) band_conv_kernel(BandConvParams p) {
       __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
       umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       umma::fence_after_sync();
-      // ---- epilogue: thread = padded raster row; the two warp sets take alternate tiles
+      // ---- epilogue: thread = padded raster row; the four warp sets take tiles round-robin
 #pragma unroll 1
-      for (int t = half; t < C::NTILES; t += 2) {
+      for (int t = tgrp; t < C::NTILES; t += 4) {
         const int pr = C::P0 + t * 128 + q4 * 32 + lane;
         const int yl = pr / C::PW - 1, xl = pr % C::PW - 1;
         const bool valid = (pr < C::P0 + C::MROWS) && xl >= 0 && xl < WIN_;
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(256, 1) band_conv_kernel(BandConvParams p) {
       __syncthreads();
       if (tid < C::GOUT * 2) {
         float a = 0.f;
-        for (int w8 = 0; w8 < 8; ++w8) a += s_part[w8 * C::GOUT * 2 + tid];
+        for (int w8 = 0; w8 < 16; ++w8) a += s_part[w8 * C::GOUT * 2 + tid];
         p.out_stats[((long long)sl * C::NB + band) * C::GOUT * 2 + tid] = a;
       }
       __syncthreads();
@@ -310,7 +310,7 @@ static cudaError_t launch_band(const BandConvParams& p, int num_sms, cudaStream_
   long long nitems = (long long)p.nslice * C::NB;
   int grid = (int)(nitems < num_sms ? nitems : num_sms);
   if (grid <= 0) return cudaSuccess;
-  kern<<<grid, 256, C::SMEM, st>>>(p);
+  kern<<<grid, 512, C::SMEM, st>>>(p);
   return cudaGetLastError();
 }
 

@@ -22,7 +22,7 @@ namespace catseg {
 using namespace fast;
 
 namespace {
-constexpr int SA_THREADS = 256;
+constexpr int SA_THREADS = 512;    // 16 warps: TMEM lane quarter q4 = warp & 3, work group grp = warp >> 2
 constexpr int NTOK = 144, WIN = 12, GRID = 24;
 constexpr uint32_t LBO_X = NTOK * 16 + 16;                 // 2320: thread-written 144-row K-major tiles
 constexpr uint32_t SM_RING = 0;                            // 2 x 32 KiB
@@ -61,7 +61,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
   uint64_t* bar_y = bar_full + 5;                                     // proj done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 6);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q4 = warp & 3, half = warp >> 2;
+  const int q4 = warp & 3, grp = warp >> 2;
 
   long long mine = 0;
   for (long long i = blockIdx.x; i < nwin_total; i += gridDim.x) ++mine;
@@ -111,12 +111,13 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
     // ---- LN1 -> XN (warp per row, 4 rows in flight)
     {
       const float4 g = ld4(s_g + lane * 4), be = ld4(s_be + lane * 4);
-      for (int r0 = warp * 6; r0 < NTOK; r0 += 48) {
-        float4 x[6];
+      {
+        const int r0 = warp * 9;                       // 16 warps x 9 rows, all 9 loads in flight
+        float4 x[9];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) x[i] = ld4(Xs + (long long)tokpix[r0 + i] * 128 + lane * 4);
+        for (int i = 0; i < 9; ++i) x[i] = ld4(Xs + (long long)tokpix[r0 + i] * 128 + lane * 4);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
+        for (int i = 0; i < 9; ++i) {
           float4 y = warp_layernorm128(x[i], g, be);
           uint2 pk = make_uint2(umma::pack_bf16x2(y.x, y.y), umma::pack_bf16x2(y.z, y.w));
           *reinterpret_cast<uint2*>(smem + SM_XN + (lane >> 1) * LBO_X + (r0 + i) * 16 + (lane & 1) * 8) = pk;
@@ -144,16 +145,17 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
       //      which is free until the softmax of this head (coalesced 128-byte rows, one latency)
       {
         float* stage = reinterpret_cast<float*>(smem + SM_P);
-        float4 t4[9];
+        float4 t4[5];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) {
+        for (int i = 0; i < 5; ++i) {
           int idx = tid + i * SA_THREADS, r = idx >> 4, c4 = idx & 15;
-          t4[i] = ld4(ag + (long long)tokpix[r] * 256 + (c4 < 8 ? h * 32 + c4 * 4 : 128 + h * 32 + (c4 - 8) * 4));
+          if (idx < NTOK * 16)
+            t4[i] = ld4(ag + (long long)tokpix[r] * 256 + (c4 < 8 ? h * 32 + c4 * 4 : 128 + h * 32 + (c4 - 8) * 4));
         }
 #pragma unroll
-        for (int i = 0; i < 9; ++i) {
+        for (int i = 0; i < 5; ++i) {
           int idx = tid + i * SA_THREADS;
-          st4(stage + idx * 4, t4[i]);
+          if (idx < NTOK * 16) st4(stage + idx * 4, t4[i]);
         }
       }
       __syncthreads();
@@ -168,7 +170,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
         const float bvv = s_bv[h * 32 + d];
         const float* agp = reinterpret_cast<const float*>(smem + SM_P) + (q4 == 1 ? 32 : 0) + d;
 #pragma unroll 1
-        for (int tg = half * 9; tg < half * 9 + 9; ++tg) {
+        for (int tg = grp * 18 / 4; tg < (grp + 1) * 18 / 4; ++tg) {
           float v[8];
           umma::tmem_ld8(lane_addr + TM_QKV + tg * 8, v);
           if (q4 == 2) {
@@ -205,45 +207,52 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
       __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
       umma::mbar_wait(bar_s, ph_s); ph_s ^= 1;
       umma::fence_after_sync();
-      // ---- softmax: two threads per query row (keys [72*half, 72*half+72)); tile 1 rows by quarter 0, lanes < 16
-#pragma unroll 1
-      for (int mt = 0; mt < 2; ++mt) {
+      // ---- softmax: two threads per query row (keys [72*kh, 72*kh+72)); groups 0,1 -> tile 0, groups 2,3 -> tile 1
+      //      (only its lane quarter 0 holds real rows 128..143).  Two passes over TMEM keep the register set small.
+      {
+        const int mt = grp >> 1, kh = grp & 1;
         const int row = mt * 128 + q4 * 32 + lane;
         const bool warp_on = (mt == 0) || (q4 == 0);          // warp-uniform: tcgen05.ld is .sync.aligned
-        const bool active = row < NTOK;                       // tile 1: only rows 128..143 are real
-        float s[72];
+        const bool active = row < NTOK;
+        const uint32_t s_addr = lane_addr + (mt ? TM_S1 : TM_S0) + kh * 72;
+        const int rq = tokreg[active ? row : 0];
         float mx = -INFINITY;
         if (warp_on) {
-          const int rq = tokreg[active ? row : 0];
-#pragma unroll
+#pragma unroll 1
           for (int c = 0; c < 9; ++c) {
-            umma::tmem_ld8(lane_addr + (mt ? TM_S1 : TM_S0) + half * 72 + c * 8, &s[c * 8]);
+            float v[8];
+            umma::tmem_ld8(s_addr + c * 8, v);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              float v = s[c * 8 + i];
-              if (shift > 0 && tokreg[half * 72 + c * 8 + i] != rq) v += -100.0f;
-              s[c * 8 + i] = v;
-              mx = fmaxf(mx, v);
+              float a = v[i];
+              if (shift > 0 && tokreg[kh * 72 + c * 8 + i] != rq) a += -100.0f;
+              mx = fmaxf(mx, a);
             }
           }
-          if (active) red[half * 144 + row] = mx;
+          if (active) red[kh * 144 + row] = mx;
         }
         __syncthreads();
-        if (warp_on && active) {
+        if (warp_on) {
           float sum = 0.0f;
-          mx = fmaxf(red[row], red[144 + row]);
-#pragma unroll
+          mx = active ? fmaxf(red[row], red[144 + row]) : 0.0f;
+#pragma unroll 1
           for (int c = 0; c < 9; ++c) {
-            float e[8];
+            float v[8];
+            umma::tmem_ld8(s_addr + c * 8, v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { e[i] = __expf(s[c * 8 + i] - mx); sum += e[i]; }
-            *reinterpret_cast<uint4*>(smem + SM_P + (half * 9 + c) * LBO_X + row * 16) =
-                make_uint4(umma::pack_bf16x2(e[0], e[1]), umma::pack_bf16x2(e[2], e[3]), umma::pack_bf16x2(e[4], e[5]),
-                           umma::pack_bf16x2(e[6], e[7]));
+            for (int i = 0; i < 8; ++i) {
+              float a = v[i];
+              if (shift > 0 && tokreg[kh * 72 + c * 8 + i] != rq) a += -100.0f;
+              v[i] = __expf(a - mx);
+              sum += v[i];
+            }
+            if (active)
+              *reinterpret_cast<uint4*>(smem + SM_P + (kh * 9 + c) * LBO_X + row * 16) =
+                  make_uint4(umma::pack_bf16x2(v[0], v[1]), umma::pack_bf16x2(v[2], v[3]), umma::pack_bf16x2(v[4], v[5]),
+                             umma::pack_bf16x2(v[6], v[7]));
           }
-          red[288 + half * 144 + row] = sum;
+          if (active) red[288 + kh * 144 + row] = sum;
         }
-        __syncthreads();
       }
       umma::fence_proxy_async();
       umma::fence_before_sync();
@@ -265,9 +274,9 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
       umma::fence_after_sync();
       // ---- O epilogue: thread = query row (tile 0: warps 0-3, tile 1: warp 4 lanes < 16)
       {
-        const int mt = half;
+        const int mt = grp;                                   // group 0: tile 0, group 1 (lane quarter 0): tile 1
         const int row = mt * 128 + q4 * 32 + lane;
-        if (mt == 0 || q4 == 0) {                             // warp-uniform (tcgen05.ld is .sync.aligned)
+        if (grp == 0 || (grp == 1 && q4 == 0)) {              // warp-uniform (tcgen05.ld is .sync.aligned)
           float v[32];
           umma::tmem_ld32(lane_addr + (mt ? TM_O1 : TM_O0), v);
           if (row < NTOK) {
@@ -305,14 +314,13 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
       const int f = q4 * 32 + lane;
       const float bp = s_bp[f];
 #pragma unroll 1
-      for (int t0 = half * 72; t0 < half * 72 + 72; t0 += 24) {      // 24 shortcut loads in flight per round
-        float xv[24], v[24];
+      for (int tg = grp * 18 / 4; tg < (grp + 1) * 18 / 4; ++tg) {     // 8 shortcut loads in flight per round
+        float xv[8], v[8];
 #pragma unroll
-        for (int i = 0; i < 24; ++i) xv[i] = Xs[(long long)tokpix[t0 + i] * 128 + f];
+        for (int i = 0; i < 8; ++i) xv[i] = Xs[(long long)tokpix[tg * 8 + i] * 128 + f];
+        umma::tmem_ld8(lane_addr + TM_QKV + tg * 8, v);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) umma::tmem_ld8(lane_addr + TM_QKV + t0 + c * 8, &v[c * 8]);
-#pragma unroll
-        for (int i = 0; i < 24; ++i) Xs[(long long)tokpix[t0 + i] * 128 + f] = xv[i] + (v[i] + bp);
+        for (int i = 0; i < 8; ++i) Xs[(long long)tokpix[tg * 8 + i] * 128 + f] = xv[i] + (v[i] + bp);
       }
     }
     umma::fence_before_sync();
