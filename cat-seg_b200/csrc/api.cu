@@ -594,7 +594,7 @@ Plan make_plan(const catseg_handle* h, int B, int T) {
   {
     size_t fe = decoder_exact_scratch_floats(p.dd, p.dec_chunk);
     if (h->fast_mask & CATSEG_FAST_DECODER) {
-      p.dec_chunk = nslice < 128 ? nslice : 128;
+      p.dec_chunk = nslice < 1024 ? nslice : 1024;
       fe = (decoder_fast_scratch_bytes(p.dd, B, p.dec_chunk) + 3) / 4;
     }
     p.dec = take(fe);

@@ -55,24 +55,26 @@ struct BandCfg {
   static constexpr uint32_t IMG_BYTES = ((KCH * LBO_I + (OVER > 0 ? OVER * 16 : 0)) + 127) / 128 * 128;
   static constexpr int NTAP = UPS ? 4 : 9, NPG = UPS ? 4 : 1, NIMG = NTAP * NPG;
   static constexpr uint32_t WBYTES = NOUT * CIN * 2, LBO_WT = NOUT * 16;
-  static constexpr bool RESIDENT = NIMG * WBYTES <= 80 * 1024;
-  static constexpr int NSLOT = RESIDENT ? NIMG : 4;
+  // two CTAs per SM (half-height bands, <= 113 KiB and <= 256 TMEM columns each): one CTA's staging / epilogue
+  // overlaps the other's MMAs.  Small weight sets stay resident, larger ones stream through a ring.
+  static constexpr bool RESIDENT = NIMG * WBYTES <= 24 * 1024;
+  static constexpr int NSLOT = RESIDENT ? NIMG : (WBYTES >= 16384 ? 3 : 4);
   static constexpr int NB = WIN_ / BR;                 // bands per slice
   static constexpr int WOUT = UPS ? 2 * WIN_ : WIN_;
   static constexpr int GOUT = HEAD ? 1 : NREAL / 16;
   static constexpr uint32_t SM_W = IMG_BYTES;
   static constexpr uint32_t SM_SC = SM_W + NSLOT * WBYTES;            // scale[CIN], shift[CIN]
-  static constexpr uint32_t SM_ST = SM_SC + 2 * CIN * 4;              // [16 warps][GOUT][2]
-  static constexpr uint32_t SM_BAR = (SM_ST + 16 * GOUT * 2 * 4 + 15) / 16 * 16;
+  static constexpr uint32_t SM_ST = SM_SC + 2 * CIN * 4;              // [8 warps][GOUT][2]
+  static constexpr uint32_t SM_BAR = (SM_ST + 8 * GOUT * 2 * 4 + 15) / 16 * 16;
   static constexpr uint32_t SMEM = SM_BAR + (2 * NSLOT + 2) * 8 + 16;
   static constexpr uint32_t IDESC = umma::make_idesc_bf16(128, NOUT);
-  static_assert(NTILES * NOUT <= 512, "TMEM columns");
-  static_assert(SMEM <= 232448, "shared memory budget");
+  static_assert(NTILES * NOUT <= 256, "TMEM columns (two CTAs per SM)");
+  static_assert(SMEM <= 113 * 1024, "shared memory budget (two CTAs per SM)");
   static_assert(WIN_ % BR == 0 && CIN % 16 == 0 && NOUT % 16 == 0, "shape");
 };
 
 template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD>
-__global__ void __launch_bounds__(512, 1) band_conv_kernel(BandConvParams p) {
+__global__ void __launch_bounds__(256, 2) band_conv_kernel(BandConvParams p) {
   using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD>;
   extern __shared__ __align__(1024) uint8_t smem[];
   float* s_scale = reinterpret_cast<float*>(smem + C::SM_SC);
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(512, 1) band_conv_kernel(BandConvParams p) {
   uint64_t* bar_empty = bar_full + C::NSLOT;                             // [NSLOT]
   uint64_t* bar_acc = bar_empty + C::NSLOT;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 1);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q4 = warp & 3, tgrp = warp >> 2;   // 16 warps
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q4 = warp & 3, tgrp = warp >> 2;   // 8 warps
 
   const long long nitems = (long long)p.nslice * C::NB;
   long long mine = 0;
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(512, 1) band_conv_kernel(BandConvParams p) {
     for (int i = 0; i < 2 * C::NSLOT + 1; ++i) umma::mbar_init(&bar_full[i], 1);
     umma::mbar_fence_init();
   }
-  if (warp == 0) umma::tmem_alloc<512>(tmem_slot);
+  if (warp == 0) umma::tmem_alloc<256>(tmem_slot);
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(512, 1) band_conv_kernel(BandConvParams p) {
     {
       const int y_first = band * BR - 1;
 #pragma unroll 8
-      for (int idx = tid; idx < C::NP * C::KCH; idx += 512) {
+      for (int idx = tid; idx < C::NP * C::KCH; idx += 256) {
         const int pp = idx / C::KCH, c = idx % C::KCH;
         const int yy = y_first + pp / C::PW, xx = pp % C::PW - 1;
         uint4 val = make_uint4(0u, 0u, 0u, 0u);
@@ -226,9 +228,9 @@ __global__ void __launch_bounds__(512, 1) band_conv_kernel(BandConvParams p) {
       __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
       umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       umma::fence_after_sync();
-      // ---- epilogue: thread = padded raster row; the four warp sets take tiles round-robin
+      // ---- epilogue: thread = padded raster row; the two warp sets take alternate tiles
 #pragma unroll 1
-      for (int t = tgrp; t < C::NTILES; t += 4) {
+      for (int t = tgrp; t < C::NTILES; t += 2) {
         const int pr = C::P0 + t * 128 + q4 * 32 + lane;
         const int yl = pr / C::PW - 1, xl = pr % C::PW - 1;
         const bool valid = (pr < C::P0 + C::MROWS) && xl >= 0 && xl < WIN_;
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(512, 1) band_conv_kernel(BandConvParams p) {
       __syncthreads();
       if (tid < C::GOUT * 2) {
         float a = 0.f;
-        for (int w8 = 0; w8 < 16; ++w8) a += s_part[w8 * C::GOUT * 2 + tid];
+        for (int w8 = 0; w8 < 8; ++w8) a += s_part[w8 * C::GOUT * 2 + tid];
         p.out_stats[((long long)sl * C::NB + band) * C::GOUT * 2 + tid] = a;
       }
       __syncthreads();
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(512, 1) band_conv_kernel(BandConvParams p) {
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc<512>(tm);
+  if (warp == 0) umma::tmem_dealloc<256>(tm);
 }
 
 template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD>
@@ -308,9 +310,9 @@ static cudaError_t launch_band(const BandConvParams& p, int num_sms, cudaStream_
     attr_set = true;
   }
   long long nitems = (long long)p.nslice * C::NB;
-  int grid = (int)(nitems < num_sms ? nitems : num_sms);
+  int grid = (int)(nitems < 2LL * num_sms ? nitems : 2LL * num_sms);
   if (grid <= 0) return cudaSuccess;
-  kern<<<grid, 512, C::SMEM, st>>>(p);
+  kern<<<grid, 256, C::SMEM, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -441,7 +443,7 @@ size_t decoder_fast_scratch_bytes(const DecoderDims& d, int B, int chunk) {
   size_t b = 0;
   b += (size_t)B * (4 * hw * d.D1 + 16 * hw * d.D2) * 4;                 // E1, E2
   b += (size_t)chunk * (2 * 4 * hw * d.D1 + 2 * 16 * hw * d.D2) * 2;     // c1a c1b c2a c2b (bf16)
-  b += (size_t)chunk * (2 * 2 * 4 + 4 * 4 + 4 * 2 + 8 * 2) * 2 * 4 + 1024; // band statistics
+  b += (size_t)chunk * (4 * 4 + 8 * 4 + 8 * 2 + 16 * 2) * 2 * 4 + 4096; // band statistics
   return (b + 255) / 256 * 256;
 }
 
@@ -461,10 +463,10 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
   __nv_bfloat16* c1b = reinterpret_cast<__nv_bfloat16*>(take((size_t)chunk * 4 * hw * d.D1 * 2));
   __nv_bfloat16* c2a = reinterpret_cast<__nv_bfloat16*>(take((size_t)chunk * 16 * hw * d.D2 * 2));
   __nv_bfloat16* c2b = reinterpret_cast<__nv_bfloat16*>(take((size_t)chunk * 16 * hw * d.D2 * 2));
-  float* s1a = reinterpret_cast<float*>(take((size_t)chunk * 2 * 4 * 2 * 4));   // NB=2 G=4
-  float* s1b = reinterpret_cast<float*>(take((size_t)chunk * 4 * 4 * 2 * 4));   // NB=4 G=4
-  float* s2a = reinterpret_cast<float*>(take((size_t)chunk * 4 * 2 * 2 * 4));   // NB=4 G=2
-  float* s2b = reinterpret_cast<float*>(take((size_t)chunk * 8 * 2 * 2 * 4));   // NB=8 G=2
+  float* s1a = reinterpret_cast<float*>(take((size_t)chunk * 4 * 4 * 2 * 4));    // NB=4 G=4
+  float* s1b = reinterpret_cast<float*>(take((size_t)chunk * 8 * 4 * 2 * 4));    // NB=8 G=4
+  float* s2a = reinterpret_cast<float*>(take((size_t)chunk * 8 * 2 * 2 * 4));    // NB=8 G=2
+  float* s2b = reinterpret_cast<float*>(take((size_t)chunk * 16 * 2 * 2 * 4));   // NB=16 G=2
 
   {
     GuidConvA a{dg0, d.G1, 2 * d.H, 2 * d.W};
@@ -479,23 +481,23 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
     p.Te = Te; p.slice0 = s0; p.nslice = n; p.T = T; p.classes = classes; p.logits = logits; p.head_bias = head_bias;
     // D1: x (24^2 x 128, fp32) -> c1a (48^2 x 64), composed transposed conv + conv
     p.in = X + (long long)s0 * hw * d.C0; p.in_stats = nullptr; p.wimg = w.w1; p.emap = E1; p.out = c1a; p.out_stats = s1a;
-    CKF((launch_band<128, 64, 64, true, true, 24, 12, false>(p, num_sms, st)));
+    CKF((launch_band<128, 64, 64, true, true, 24, 6, false>(p, num_sms, st)));
     // D2: c1a -> c1b, 3x3 64 -> 64 on relu(gn(c1a))
-    p.in = c1a; p.in_stats = s1a; p.nb_in = 2; p.in_count = (float)(4 * hw * 16); p.gamma = wx.gn1a_g; p.beta = wx.gn1a_b;
+    p.in = c1a; p.in_stats = s1a; p.nb_in = 4; p.in_count = (float)(4 * hw * 16); p.gamma = wx.gn1a_g; p.beta = wx.gn1a_b;
     p.wimg = w.w2; p.emap = nullptr; p.out = c1b; p.out_stats = s1b;
-    CKF((launch_band<64, 64, 64, false, false, 48, 12, false>(p, num_sms, st)));
+    CKF((launch_band<64, 64, 64, false, false, 48, 6, false>(p, num_sms, st)));
     // D3: c1b -> c2a (96^2 x 32), composed
-    p.in = c1b; p.in_stats = s1b; p.nb_in = 4; p.gamma = wx.gn1b_g; p.beta = wx.gn1b_b;
+    p.in = c1b; p.in_stats = s1b; p.nb_in = 8; p.gamma = wx.gn1b_g; p.beta = wx.gn1b_b;
     p.wimg = w.w3; p.emap = E2; p.out = c2a; p.out_stats = s2a;
-    CKF((launch_band<64, 32, 32, true, false, 48, 12, false>(p, num_sms, st)));
+    CKF((launch_band<64, 32, 32, true, false, 48, 6, false>(p, num_sms, st)));
     // D4: c2a -> c2b, 3x3 32 -> 32
-    p.in = c2a; p.in_stats = s2a; p.nb_in = 4; p.in_count = (float)(16 * hw * 16); p.gamma = wx.gn2a_g; p.beta = wx.gn2a_b;
+    p.in = c2a; p.in_stats = s2a; p.nb_in = 8; p.in_count = (float)(16 * hw * 16); p.gamma = wx.gn2a_g; p.beta = wx.gn2a_b;
     p.wimg = w.w4; p.emap = nullptr; p.out = c2b; p.out_stats = s2b;
-    CKF((launch_band<32, 32, 32, false, false, 96, 12, false>(p, num_sms, st)));
+    CKF((launch_band<32, 32, 32, false, false, 96, 6, false>(p, num_sms, st)));
     // D5: head 3x3 32 -> 1 (+ bias), scattered to logits[b][class]
-    p.in = c2b; p.in_stats = s2b; p.nb_in = 8; p.gamma = wx.gn2b_g; p.beta = wx.gn2b_b;
+    p.in = c2b; p.in_stats = s2b; p.nb_in = 16; p.gamma = wx.gn2b_g; p.beta = wx.gn2b_b;
     p.wimg = w.w5; p.emap = nullptr; p.out = nullptr; p.out_stats = nullptr;
-    CKF((launch_band<32, 16, 16, false, false, 96, 12, true>(p, num_sms, st)));
+    CKF((launch_band<32, 16, 16, false, false, 96, 6, true>(p, num_sms, st)));
   }
   if (launches) *launches += nl;
   return cudaSuccess;
