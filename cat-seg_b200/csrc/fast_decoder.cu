@@ -58,7 +58,8 @@ struct BandCfg {
   // two CTAs per SM (half-height bands, <= 113 KiB and <= 256 TMEM columns each): one CTA's staging / epilogue
   // overlaps the other's MMAs.  Small weight sets stay resident, larger ones stream through a ring.
   static constexpr bool RESIDENT = NIMG * WBYTES <= 24 * 1024;
-  static constexpr int NSLOT = RESIDENT ? NIMG : (WBYTES >= 16384 ? 3 : 4);
+  // streaming ring: 48 KiB deep, so that the prefetch distance (in MMA time) exceeds the ~1 us L2->SMEM latency
+  static constexpr int NSLOT = RESIDENT ? NIMG : (int)(48 * 1024 / WBYTES);
   static constexpr int NB = WIN_ / BR;                 // bands per slice
   static constexpr int WOUT = UPS ? 2 * WIN_ : WIN_;
   static constexpr int GOUT = HEAD ? 1 : NREAL / 16;
@@ -226,17 +227,35 @@ __global__ void __launch_bounds__(256, 2) band_conv_kernel(BandConvParams p) {
         umma::mma_commit(bar_acc);
       }
       __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
-      umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
-      umma::fence_after_sync();
-      // ---- epilogue: thread = padded raster row; the two warp sets take alternate tiles
-#pragma unroll 1
-      for (int t = tgrp; t < C::NTILES; t += 2) {
+      // ---- epilogue: thread = padded raster row; the two warp sets take alternate tiles.  The additive map
+      //      of the first tile is fetched BEFORE waiting for the accumulators (hides the global latency).
+      float e_pre[HEAD ? 1 : NREAL];
+      auto tile_geom = [&](int t, bool& valid, long long& opix) {
         const int pr = C::P0 + t * 128 + q4 * 32 + lane;
         const int yl = pr / C::PW - 1, xl = pr % C::PW - 1;
-        const bool valid = (pr < C::P0 + C::MROWS) && xl >= 0 && xl < WIN_;
+        valid = (pr < C::P0 + C::MROWS) && xl >= 0 && xl < WIN_;
         int Yo = band * BR + yl, Xo = xl;
         if (UPS) { Yo = 2 * Yo + pa; Xo = 2 * Xo + pb; }
-        const long long opix = (long long)Yo * C::WOUT + Xo;
+        opix = (long long)Yo * C::WOUT + Xo;
+      };
+      if constexpr (!HEAD) {
+        if (p.emap != nullptr && tgrp < C::NTILES) {
+          bool valid; long long opix;
+          tile_geom(tgrp, valid, opix);
+          const float* e = p.emap + ((long long)b * (C::WOUT * C::WOUT) + (valid ? opix : 0)) * NREAL;
+#pragma unroll
+          for (int i = 0; i < NREAL; i += 4) {
+            float4 e4 = ld4(e + i);
+            e_pre[i] = e4.x; e_pre[i + 1] = e4.y; e_pre[i + 2] = e4.z; e_pre[i + 3] = e4.w;
+          }
+        }
+      }
+      umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
+      umma::fence_after_sync();
+#pragma unroll 1
+      for (int t = tgrp; t < C::NTILES; t += 2) {
+        bool valid; long long opix;
+        tile_geom(t, valid, opix);
         if constexpr (HEAD) {
           float v[8];
           umma::tmem_ld8(lane_addr + t * NOUT, v);
@@ -251,11 +270,16 @@ __global__ void __launch_bounds__(256, 2) band_conv_kernel(BandConvParams p) {
             umma::tmem_ld32(lane_addr + t * NOUT + c0, v);
             if (valid) {
               if (p.emap != nullptr) {
-                const float* e = p.emap + ((long long)b * (C::WOUT * C::WOUT) + opix) * NREAL + c0;
+                if (t == tgrp) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  float4 e4 = ld4(e + i);
-                  v[i] += e4.x; v[i + 1] += e4.y; v[i + 2] += e4.z; v[i + 3] += e4.w;
+                  for (int i = 0; i < 32; ++i) v[i] += e_pre[c0 + i];
+                } else {
+                  const float* e = p.emap + ((long long)b * (C::WOUT * C::WOUT) + opix) * NREAL + c0;
+#pragma unroll
+                  for (int i = 0; i < 32; i += 4) {
+                    float4 e4 = ld4(e + i);
+                    v[i] += e4.x; v[i + 1] += e4.y; v[i + 2] += e4.z; v[i + 3] += e4.w;
+                  }
                 }
               }
 #pragma unroll
