@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(256, 2) band_conv_kernel(BandConvParams p) {
       if (tid == 0) {
         umma::fence_after_sync();
         if (C::RESIDENT && !w_ready) { umma::mbar_wait(&bar_full[0], 0); w_ready = true; }
+        const uint64_t a_desc0 = umma::make_smem_desc(sb, C::LBO_I, 128);
 #pragma unroll 1
         for (int tap = 0; tap < C::NTAP; ++tap) {
           int off;
@@ -205,14 +206,17 @@ __global__ void __launch_bounds__(256, 2) band_conv_kernel(BandConvParams p) {
             umma::mbar_wait(&bar_full[slot], (uint32_t)((nimg / C::NSLOT) & 1));
             wb = sb + C::SM_W + (uint32_t)slot * C::WBYTES;
           }
+          // descriptors are built once and advanced by integer adds on the (address >> 4) field: the single
+          // issuing thread must spend ~10 cycles per MMA, not ~100 (these MMAs are only 8-32 tensor cycles long)
+          const uint64_t b_desc = umma::make_smem_desc(wb, C::LBO_WT, 128);
+          uint64_t a_tile = a_desc0 + (uint64_t)(uint32_t)(C::P0 + off);
 #pragma unroll 1
           for (int t = 0; t < C::NTILES; ++t) {
-            const uint32_t a0 = sb + (uint32_t)(C::P0 + t * 128 + off) * 16;
 #pragma unroll
             for (int k = 0; k < C::KSTEPS; ++k)
-              umma::mma_bf16_ss(tm + t * NOUT, umma::make_smem_desc(a0 + k * 2 * C::LBO_I, C::LBO_I, 128),
-                                umma::make_smem_desc(wb + k * 2 * C::LBO_WT, C::LBO_WT, 128), C::IDESC,
-                                (tap > 0 || k > 0) ? 1u : 0u);
+              umma::mma_bf16_ss(tm + t * NOUT, a_tile + (uint64_t)(k * 2 * (C::LBO_I >> 4)),
+                                b_desc + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC, (tap > 0 || k > 0) ? 1u : 0u);
+            a_tile += 128;
           }
           if (!C::RESIDENT) {
             umma::mma_commit(&bar_empty[slot]);
