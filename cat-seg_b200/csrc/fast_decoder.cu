@@ -146,35 +146,58 @@ __global__ void __launch_bounds__(256, 2) band_conv_kernel(BandConvParams p) {
       }
       __syncthreads();
     }
-    // ---- stage the padded band image (bf16, canonical K-major, rows = padded raster positions)
+    // ---- stage the padded band image (bf16, canonical K-major, rows = padded raster positions).
+    //      Explicitly software-pipelined: U independent 16/32-byte loads are issued before any is consumed
+    //      (ncu showed the compiler serialising load -> convert -> store per chunk: one latency per chunk).
     {
       const int y_first = band * BR - 1;
-#pragma unroll 8
-      for (int idx = tid; idx < C::NP * C::KCH; idx += 256) {
-        const int pp = idx / C::KCH, c = idx % C::KCH;
-        const int yy = y_first + pp / C::PW, xx = pp % C::PW - 1;
-        uint4 val = make_uint4(0u, 0u, 0u, 0u);
-        if (yy >= 0 && yy < WIN_ && xx >= 0 && xx < WIN_) {
-          float v[8];
-          const long long off = (((long long)sl * WIN_ + yy) * WIN_ + xx) * CIN + c * 8;
+      constexpr int U = IN_F32 ? 4 : 8;
+      constexpr int NCHUNK = C::NP * C::KCH;
+#pragma unroll 1
+      for (int base = tid; base < NCHUNK; base += 256 * U) {
+        uint4 raw[U][IN_F32 ? 2 : 1];
+        bool inb[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int idx = base + u * 256;
+          const int pp = idx / C::KCH, c = idx % C::KCH;
+          const int yy = y_first + pp / C::PW, xx = pp % C::PW - 1;
+          inb[u] = idx < NCHUNK && yy >= 0 && yy < WIN_ && xx >= 0 && xx < WIN_;
+          const long long off = inb[u] ? (((long long)sl * WIN_ + yy) * WIN_ + xx) * CIN + c * 8 : 0;
           if (IN_F32) {
-            const float* src = reinterpret_cast<const float*>(p.in) + off;
-            float4 a = ld4(src), bq = ld4(src + 4);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = bq.x; v[5] = bq.y; v[6] = bq.z; v[7] = bq.w;
+            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.in) + off);
+            raw[u][0] = __ldg(src);
+            raw[u][IN_F32 ? 1 : 0] = __ldg(src + 1);
           } else {
-            uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.in) + off);
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h2[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+            raw[u][0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.in) + off));
           }
-          if (p.in_stats != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], s_scale[c * 8 + j], s_shift[c * 8 + j]), 0.0f);
-          }
-          val = make_uint4(umma::pack_bf16x2(v[0], v[1]), umma::pack_bf16x2(v[2], v[3]), umma::pack_bf16x2(v[4], v[5]),
-                           umma::pack_bf16x2(v[6], v[7]));
         }
-        *reinterpret_cast<uint4*>(smem + c * C::LBO_I + pp * 16) = val;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int idx = base + u * 256;
+          if (idx >= NCHUNK) continue;
+          const int pp = idx / C::KCH, c = idx % C::KCH;
+          uint4 val = make_uint4(0u, 0u, 0u, 0u);
+          if (inb[u]) {
+            float v[8];
+            if (IN_F32) {
+              const float* f = reinterpret_cast<const float*>(&raw[u][0]);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = f[j];
+            } else {
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[u][0]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h2[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+            }
+            if (p.in_stats != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], s_scale[c * 8 + j], s_shift[c * 8 + j]), 0.0f);
+            }
+            val = make_uint4(umma::pack_bf16x2(v[0], v[1]), umma::pack_bf16x2(v[2], v[3]), umma::pack_bf16x2(v[4], v[5]),
+                             umma::pack_bf16x2(v[6], v[7]));
+          }
+          *reinterpret_cast<uint4*>(smem + c * C::LBO_I + pp * 16) = val;
+        }
       }
     }
     umma::fence_proxy_async();

@@ -313,15 +313,22 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
     {
       const int f = q4 * 32 + lane;
       const float bp = s_bp[f];
-#pragma unroll 1
-      for (int tg = grp * 18 / 4; tg < (grp + 1) * 18 / 4; ++tg) {     // 8 shortcut loads in flight per round
-        float xv[8], v[8];
+      const int tg0 = grp * 18 / 4, tg1 = (grp + 1) * 18 / 4;        // 4 or 5 token groups of 8
+      float xv[40];                                                  // all shortcut loads in flight at once
 #pragma unroll
-        for (int i = 0; i < 8; ++i) xv[i] = Xs[(long long)tokpix[tg * 8 + i] * 128 + f];
-        umma::tmem_ld8(lane_addr + TM_QKV + tg * 8, v);
+      for (int j = 0; j < 5; ++j)
+        if (tg0 + j < tg1) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) Xs[(long long)tokpix[tg * 8 + i] * 128 + f] = xv[i] + (v[i] + bp);
-      }
+          for (int i = 0; i < 8; ++i) xv[j * 8 + i] = Xs[(long long)tokpix[(tg0 + j) * 8 + i] * 128 + f];
+        }
+#pragma unroll
+      for (int j = 0; j < 5; ++j)
+        if (tg0 + j < tg1) {                                         // warp-uniform
+          float v[8];
+          umma::tmem_ld8(lane_addr + TM_QKV + (tg0 + j) * 8, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) Xs[(long long)tokpix[(tg0 + j) * 8 + i] * 128 + f] = xv[j * 8 + i] + (v[i] + bp);
+        }
     }
     umma::fence_before_sync();
     __syncthreads();
