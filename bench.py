@@ -40,22 +40,39 @@ def stage_flops(cfg, B, T):
     C, hw = cfg.text_guidance_dim, 576
     npix = hw // (cfg.pooling_size[0] * cfg.pooling_size[1])
     sl = B * Te
-    swin_block = hw * (2 * 256 * 128 + 128 * 128 + 128 * 128 + 2 * 128 * 512) + 4 * 4 * 2 * 144 * 144 * 32
+    swin_attn = hw * (2 * 256 * 128 + 128 * 128 + 128 * 128) + 4 * 4 * 2 * 144 * 144 * 32   # q,k (K=256), v, proj, QK^T, PV
+    swin_mlp = hw * 2 * 128 * 512
     class_tok = 2 * 256 * 128 + 128 * 128 + 2 * 128 * 512 + 4 * (32 * 32 + 32 * 32 + 32)
     dec = 48 * 48 * (96 * 128 + 9 * 64 * 128 + 9 * 64 * 64) + 96 * 96 * (48 * 64 + 9 * 32 * 64 + 9 * 32 * 32 + 9 * 32)
     corr = B * T * cfg.prompt_channel * hw * C * (2 if T > Te else 1)
     prep = corr + B * (hw * 128 * C * 9 + 2304 * 32 * 256 * 9 + 9216 * 16 * 128 * 9) + sl * C * 128
     m = {
         "prep": prep, "embed": sl * hw * 128 * 49 * cfg.prompt_channel,
-        "swin": sl * swin_block * 2 * cfg.num_layers,
+        "swin": sl * swin_attn * 2 * cfg.num_layers,
+        "swin_mlp": sl * swin_mlp * 2 * cfg.num_layers,
         "class": B * npix * S * class_tok * cfg.num_layers,
         "decoder": sl * dec,
     }
     return {k: 2.0 * v for k, v in m.items()}
 
 
-def launches_per_stage(cfg):
-    return {"swin": 2 * cfg.num_layers, "class": 2 * cfg.num_layers}
+# (kernel name, launches per boundary call) of the stages whose time is one kernel type launched repeatedly
+STAGE_KERNELS = {
+    "swin": ("swin_attn_fast_kernel", lambda cfg: 2 * cfg.num_layers),
+    "swin_mlp": ("mlp_fast_kernel<GELU>", lambda cfg: 2 * cfg.num_layers),
+    "class": ("class_state_fast_kernel + class_apply_fast_kernel", lambda cfg: cfg.num_layers),
+    "decoder": ("band_conv_kernel x5 (D1..D5)", lambda cfg: 1),
+    "prep": ("prep kernels", lambda cfg: 1), "embed": ("igemm_kernel<EmbedA>", lambda cfg: 1),
+}
+
+
+def ncu_traffic(kernel, workload):
+    """dram__bytes_read+write per launch from the committed ncu capture (profiles/ncu_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(path)).get(workload, {}).get(kernel)
+    except Exception:
+        return None
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -170,9 +187,8 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+    from cat_seg_b200 import distributed as cdist
+    cdist.init_from_env("nccl", dev)
     from cat_seg_b200.aggregator import Aggregator
     from cat_seg_b200 import sliding_window as sw
 
@@ -187,8 +203,13 @@ def run_ours(args):
     host = [t.pin_memory() for t in (img, text, g[1], g[2])]
     d_img, d_text, d_g1, d_g2 = [t.to(dev) for t in host]
 
+    sliding = args.workload == "cfg5"           # 5 windows of one 640x640 image + stitch/argmax per step
+
     def step_resident():
-        return model(d_img, d_text, [d_img, d_g1, d_g2])
+        y = model(d_img, d_text, [d_img, d_g1, d_g2])
+        if sliding:
+            return sw.stitch(y, 640, 640, want_probs=False, want_labels=True)[1]
+        return y
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -218,13 +239,16 @@ def run_ours(args):
     launches = model.last_launch_count() * args.steps
 
     # ---- end to end: pinned host inputs -> device, boundary call, per-image argmax labels -> host
-    labels_host = torch.empty(B, 96 * 96, dtype=torch.int32).pin_memory()
+    labels_host = (torch.empty(640 * 640, dtype=torch.int32) if sliding else torch.empty(B, 96 * 96, dtype=torch.int32)).pin_memory()
 
     def e2e_step():
         a, b, c, d = [t.to(dev, non_blocking=True) for t in host]
         yy = model(a, b, [a, c, d])
-        for i in range(B):
-            labels_host[i].copy_(sw.argmax(yy[i].view(T, -1)), non_blocking=True)
+        if sliding:
+            labels_host.copy_(sw.stitch(yy, 640, 640, want_probs=False, want_labels=True)[1].view(-1), non_blocking=True)
+        else:
+            for i in range(B):
+                labels_host[i].copy_(sw.argmax(yy[i].view(T, -1)), non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
 
     for _ in range(max(1, min(args.warmup, 2))):
@@ -238,25 +262,28 @@ def run_ours(args):
     barrier()
     ms_e2e = f0.elapsed_time(f1)
 
-    t_loc = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(t_loc, op=torch.distributed.ReduceOp.MAX)
-    ms, ms_e2e = t_loc.tolist()
+    ms, ms_e2e = cdist.max_over_ranks([ms, ms_e2e], dev)
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
         return
 
-    value = world * B * args.steps / (ms / 1e3)
-    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    units = 1 if sliding else B                 # images per step per rank
+    value = world * units * args.steps / (ms / 1e3)
+    e2e_value = world * units * args.steps / (ms_e2e / 1e3)
     pk = peaks()
     fl = stage_flops(cfg, B, T)
+    if stage_ms.get("swin_mlp", 0.0) == 0.0:      # exact path: the FFN half runs inside the Swin block kernel
+        fl["swin"] += fl["swin_mlp"]
     top = max(stage_ms, key=lambda k: stage_ms[k])
-    n_launch = launches_per_stage(cfg).get(top, 1) * max(calls, 1)
-    per_launch_ms = stage_ms[top] / max(n_launch, 1)
-    achieved = fl[top] / launches_per_stage(cfg).get(top, 1) / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
-    roof = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-            "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+    kname, nl_fn = STAGE_KERNELS[top]
+    n_per_call = nl_fn(cfg)
+    per_launch_ms = stage_ms[top] / max(calls, 1) / n_per_call
+    achieved = fl[top] / n_per_call / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
+    roof = {"bound": "tensor", "kernel": kname, "stage": top, "launches_per_step": n_per_call, "achieved": achieved,
+            "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
+            "traffic": ncu_traffic(kname, args.workload), "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json)",
+            "flops_per_launch": fl[top] / n_per_call, "flops_basis": "reference algorithm as written (SURVEY.md 6.2)",
             "ms_per_launch": per_launch_ms,
             "stage_ms_per_step": {k: v / max(calls, 1) for k, v in stage_ms.items()},
             "stage_tflops": {k: (fl[k] / (stage_ms[k] / max(calls, 1) * 1e-3) / 1e12 if stage_ms[k] > 0 else None)
@@ -271,11 +298,12 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.precision == "exact" else "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: CAT-Seg ViT-L/14 336x336, T={T} classes (Te=256 kept), "
-                               f"B={B} images/GPU, L=2, pool [1,1], P=1",
+        "config": {"workload": f"{args.workload}: CAT-Seg {'ViT-L/14 336x336' if cfg.text_guidance_dim == 768 else 'ViT-B/16 384x384'}, "
+                               f"T={T} classes (Te={min(T, cfg.pad_len)} kept), B={B} "
+                               f"{'sliding windows of one 640x640 image' if sliding else 'images'}/GPU, L=2, pool [1,1], P=1",
                    "precision": args.precision, "parallelism": f"images sharded over {world} rank(s)",
                    "l2": "activations (1.2 GB/step) exceed the 126 MB L2; no explicit flush",
-                   "e2e_result": "per-image argmax labels [B,96,96] int32"},
+                   "e2e_result": "stitched argmax labels [640,640] int32" if sliding else "per-image argmax labels [B,96,96] int32"},
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": labels_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},

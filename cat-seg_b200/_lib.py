@@ -36,7 +36,7 @@ class CatsegTaps(C.Structure):
     ]
 
 
-STAGES = ("prep", "embed", "swin", "class", "decoder")
+STAGES = ("prep", "embed", "swin", "class", "decoder", "swin_mlp")
 FAST_BITS = {"swin_mlp": 1, "swin_attn": 2, "class": 4, "decoder": 8}
 
 

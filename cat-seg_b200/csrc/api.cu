@@ -26,7 +26,7 @@ thread_local std::string g_create_error;
 
 constexpr int kImplementedFast = CATSEG_FAST_SWIN_MLP | CATSEG_FAST_SWIN_ATTN | CATSEG_FAST_DECODER | CATSEG_FAST_CLASS;   // stages that have a tcgen05 kernel in this build
 constexpr int kMaxProfForwards = 64;
-constexpr int kMaxSegments = 24;
+constexpr int kMaxSegments = 40;
 
 }  // namespace
 
@@ -720,20 +720,23 @@ extern "C" int catseg_forward_taps(catseg_handle* h, const float* img, const flo
 
   // ---------------- aggregation layers (model.py:717-718)
   for (int l = 0; l < p.L; ++l) {
-    seg.begin(CATSEG_STAGE_SWIN);
     for (int k = 0; k < 2; ++k) {
       const bool attn_fast = (h->fast_mask & CATSEG_FAST_SWIN_ATTN) != 0;
       const bool mlp_fast = attn_fast || (h->fast_mask & CATSEG_FAST_SWIN_MLP) != 0;
       const float* agk = ws + p.ag_qk + (size_t)(l * 2 + k) * B * p.HW * 256;
       const int shift = k == 0 ? 0 : c.window_size / 2;
+      seg.begin(CATSEG_STAGE_SWIN);
       if (attn_fast) RUN(launch_swin_attn_fast(X, agk, nslice, p.Te, shift, h->swin_attn_fast[l * 2 + k], h->num_sms, st));
       else RUN(launch_swin_block_exact(X, agk, nslice, p.Te, shift, h->swin[l * 2 + k], mlp_fast ? 0 : 1, st));
-      if (mlp_fast)
+      seg.end();
+      if (mlp_fast) {
+        seg.begin(CATSEG_STAGE_SWIN_MLP);
         RUN(launch_mlp_fast(X, (long long)nslice * p.HW, h->swin_mlp_fast[l * 2 + k], 0, h->num_sms, st));
+        seg.end();
+      }
       if (k == 0) TAP(taps->swin_b1[l], X, (size_t)nslice * p.HW * 128);
       else TAP(taps->swin_b2[l], X, (size_t)nslice * p.HW * 128);
     }
-    seg.end();
     seg.begin(CATSEG_STAGE_CLASS);
     const float* cg = ws + p.cg_qk + (size_t)l * B * p.Te * 256;
     const float* pad = ws + p.pad_state + (size_t)l * kStateFloats;

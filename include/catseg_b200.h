@@ -90,10 +90,11 @@ typedef struct catseg_taps {
 enum {
   CATSEG_STAGE_PREP = 0,   /* normalise, cost volume, top-k, guidance/text projections */
   CATSEG_STAGE_EMBED = 1,  /* 7x7 cost embedding */
-  CATSEG_STAGE_SWIN = 2,   /* all Swin blocks */
+  CATSEG_STAGE_SWIN = 2,   /* window-attention half of all Swin blocks (whole blocks on the exact path) */
   CATSEG_STAGE_CLASS = 3,  /* all class-attention layers */
   CATSEG_STAGE_DECODER = 4,
-  CATSEG_STAGE_COUNT = 5
+  CATSEG_STAGE_SWIN_MLP = 5, /* FFN half of all Swin blocks when it runs as its own kernel (fast path) */
+  CATSEG_STAGE_COUNT = 6
 };
 
 int catseg_create(const catseg_config* cfg, catseg_handle** out);
