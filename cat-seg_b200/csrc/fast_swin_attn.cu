@@ -14,6 +14,9 @@
 // The guidance half of q/k (class independent, biases included) is gathered from ag_qk.
 // Weights stream from L2 through a 2-slot ring of 32 KiB bulk (TMA) copies (5 images per window).
 // TMEM columns: [0,144) QKV_h^T / Y^T   [160,304) S tile 0   [304,448) S tile 1   [448,512) O_h tiles.
+#include <cstdio>
+#include <cstdlib>
+
 #include "fast_common.cuh"
 #include "internal.h"
 
@@ -34,7 +37,7 @@ constexpr uint32_t SM_P = SM_VH + 9216;                    // P: [rows x 144 key
 constexpr uint32_t SM_O = SM_P + 18 * LBO_X;               // O: [144 tok x 128] K-major, 16 chunks
 constexpr uint32_t SM_MISC = SM_O + 16 * LBO_X;
 // misc: tokpix[144] tokreg[144] (int) | red[2][2][144] (float) | ln g,b [256] | bv[128] | bproj[128]
-constexpr uint32_t SM_BAR = SM_MISC + (144 * 2 + 2 * 2 * 144 + 256 + 128 + 128) * 4;
+constexpr uint32_t SM_BAR = SM_MISC + (144 * 2 + 2 * 4 * 144 + 256 + 128 + 128) * 4;
 constexpr uint32_t SA_SMEM = SM_BAR + 8 * 8 + 16;
 constexpr uint32_t TM_QKV = 0, TM_S0 = 160, TM_S1 = 304, TM_O0 = 448, TM_O1 = 480;
 constexpr uint32_t IDESC_T = umma::make_idesc_bf16(128, 144, 0, 0);     // QKV^T, proj^T
@@ -43,14 +46,18 @@ constexpr uint32_t IDESC_PV = umma::make_idesc_bf16(128, 32, 0, 0);     // O = P
 static_assert(SA_SMEM <= 232448, "shared memory budget");
 }  // namespace
 
+// Optional phase timing (CATSEG_PHASE_TIMING=1): thread 0 of CTA 0 accumulates clock64() deltas per phase.
+#define PH(i) do { if (dbg != nullptr && blockIdx.x == 0 && tid == 0) { long long _t = clock64(); dbg[i] += _t - t_last; t_last = _t; } } while (0)
+
 __global__ void __launch_bounds__(SA_THREADS, 1)
 swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, int nwin_total, int Te, int shift,
-                      SwinAttnFastW w) {
+                      SwinAttnFastW w, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   int* tokpix = reinterpret_cast<int*>(smem + SM_MISC);
   int* tokreg = tokpix + 144;
-  float* red = reinterpret_cast<float*>(tokreg + 144);        // [2 (max|sum)][2 (key half)][144]
-  float* s_g = red + 2 * 2 * 144;
+  float* red = reinterpret_cast<float*>(tokreg + 144);        // row max per key quarter [4][144]
+  float* rsum = red + 4 * 144;                                 // row sum per key quarter [4][144]
+  float* s_g = rsum + 4 * 144;
   float* s_be = s_g + 128;
   float* s_bv = s_be + 128;
   float* s_bp = s_bv + 128;
@@ -79,6 +86,10 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
   const uint32_t tm = *tmem_slot;
   const uint32_t sb = umma::smem_u32(smem);
   const uint32_t lane_addr = tm + ((uint32_t)(q4 * 32) << 16);
+  // base descriptors (built once; the issuing thread only adds to the address field afterwards)
+  const uint64_t d_xn = umma::make_smem_desc(sb + SM_XN, LBO_X, 128), d_o = umma::make_smem_desc(sb + SM_O, LBO_X, 128);
+  const uint64_t d_qh = umma::make_smem_desc(sb + SM_QH, 128, 512), d_kh = umma::make_smem_desc(sb + SM_KH, 128, 512);
+  const uint64_t d_p = umma::make_smem_desc(sb + SM_P, LBO_X, 128), d_vh = umma::make_smem_desc(sb + SM_VH, 512, 128);
 
   auto issue_load = [&](long long n) {      // thread 0 only
     if (n < total_loads) {
@@ -90,6 +101,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
   };
   if (tid == 0) { issue_load(0); issue_load(1); }
 
+  long long t_last = clock64();
   long long nload = 0;          // index of the next weight image to be consumed by this CTA
   uint32_t ph_a = 0, ph_s = 0, ph_o = 0, ph_y = 0;
   const float scale = 0.17677669529663688110f;
@@ -108,7 +120,16 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
       tokreg[tid] = rh * 3 + rw;
     }
     __syncthreads();
-    // ---- LN1 -> XN (warp per row, 4 rows in flight)
+    // ---- LN1 -> XN (warp per row, 9 rows in flight); the NEXT window's rows are prefetched into L2 meanwhile
+    {
+      const long long wn = wi + gridDim.x;
+      if (wn < nwin_total && tid < NTOK * 4) {
+        const int nsl = (int)(wn >> 2), nwy = (int)((wn >> 1) & 1), nwx = (int)(wn & 1), r = tid >> 2;
+        const int sy = nwy * WIN + r / WIN, sx = nwx * WIN + r % WIN;
+        const int pix = ((sy + shift) % GRID) * GRID + (sx + shift) % GRID;
+        umma::prefetch_l2(X + ((long long)nsl * (GRID * GRID) + pix) * 128 + (tid & 3) * 32);
+      }
+    }
     {
       const float4 g = ld4(s_g + lane * 4), be = ld4(s_be + lane * 4);
       {
@@ -128,16 +149,17 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
     umma::fence_before_sync();
     __syncthreads();
 
+    PH(0);
     for (int h = 0; h < 4; ++h) {
       // ---- [q_h;k_h;v_h]^T = Wqkv_h . XN^T
       if (tid == 0) {
         umma::fence_after_sync();
         umma::mbar_wait(&bar_full[nload & 1], (uint32_t)((nload >> 1) & 1));
         uint32_t wb = sb + SM_RING + (uint32_t)(nload & 1) * WIMG_BYTES;
+        const uint64_t wd = umma::make_smem_desc(wb, LBO_W, 128);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma::mma_bf16_ss(tm + TM_QKV, umma::make_smem_desc(wb + k * 2 * LBO_W, LBO_W, 128),
-                            umma::make_smem_desc(sb + SM_XN + k * 2 * LBO_X, LBO_X, 128), IDESC_T, k > 0);
+          umma::mma_bf16_ss(tm + TM_QKV, wd + (uint64_t)(k * 2 * (LBO_W >> 4)), d_xn + (uint64_t)(k * 2 * (LBO_X >> 4)), IDESC_T, k > 0);
         umma::mma_commit(bar_a);
       }
       __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
@@ -161,6 +183,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
       __syncthreads();
       umma::mbar_wait(bar_a, ph_a); ph_a ^= 1;
       umma::fence_after_sync();
+      PH(1);
       if (tid == 0) issue_load(nload + 2);
       ++nload;
       // ---- epilogue: feature threads (lane quarter 0:q 1:k 2:v) write the per-head images
@@ -192,6 +215,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
       umma::fence_proxy_async();
       umma::fence_before_sync();
       __syncthreads();
+      PH(2);
       // ---- S = Q K^T : two query tiles, K = 32 (two k-steps)
       if (tid == 0) {
         umma::fence_after_sync();
@@ -199,64 +223,68 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
           for (int k = 0; k < 2; ++k)
-            umma::mma_bf16_ss(tm + (mt ? TM_S1 : TM_S0),
-                              umma::make_smem_desc(sb + SM_QH + mt * 16 * 512 + k * 256, 128, 512),
-                              umma::make_smem_desc(sb + SM_KH + k * 256, 128, 512), IDESC_S, k > 0);
+            umma::mma_bf16_ss(tm + (mt ? TM_S1 : TM_S0), d_qh + (uint64_t)((mt * 16 * 512 + k * 256) >> 4),
+                              d_kh + (uint64_t)((k * 256) >> 4), IDESC_S, k > 0);
         umma::mma_commit(bar_s);
       }
       __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
       umma::mbar_wait(bar_s, ph_s); ph_s ^= 1;
       umma::fence_after_sync();
-      // ---- softmax: two threads per query row (keys [72*kh, 72*kh+72)); groups 0,1 -> tile 0, groups 2,3 -> tile 1
-      //      (only its lane quarter 0 holds real rows 128..143).  Two passes over TMEM keep the register set small.
-      {
-        const int mt = grp >> 1, kh = grp & 1;
-        const int row = mt * 128 + q4 * 32 + lane;
+      PH(3);
+      // ---- softmax: FOUR threads per query row (key quarter kq = grp: keys [36 kq, 36 kq + 36) = 3 window rows).
+      //      Tile 0 (rows 0..127) by all 16 warps, then tile 1 (rows 128..143 = TMEM lanes 0..15) by the four
+      //      lane-quarter-0 warps.  The shifted-window mask needs no lookup: within a key quarter the vertical
+      //      band is constant (ly < 6 <=> kq < 2) and the horizontal band of key j is the compile-time
+      //      pattern (j % 12 >= 6), so the mask is one of two per-thread additive constants.
+#pragma unroll 1
+      for (int mt = 0; mt < 2; ++mt) {
         const bool warp_on = (mt == 0) || (q4 == 0);          // warp-uniform: tcgen05.ld is .sync.aligned
+        const int row = mt * 128 + q4 * 32 + lane;
         const bool active = row < NTOK;
-        const uint32_t s_addr = lane_addr + (mt ? TM_S1 : TM_S0) + kh * 72;
-        const int rq = tokreg[active ? row : 0];
+        const int kq = grp;
+        const uint32_t s_addr = lane_addr + (mt ? TM_S1 : TM_S0) + kq * 36;
+        float add0 = 0.0f, add1 = 0.0f;                       // additive mask for keys with lx < 6 / lx >= 6
+        if (shift > 0) {
+          const int ly = (active ? row : 0) / WIN, lx = (active ? row : 0) % WIN;
+          const bool rowmask = (wy == 1) && ((ly >= 6) != (kq >= 2));
+          add0 = (rowmask || (wx == 1 && lx >= 6)) ? -100.0f : 0.0f;
+          add1 = (rowmask || (wx == 1 && lx < 6)) ? -100.0f : 0.0f;
+        }
+        float sv[36];
         float mx = -INFINITY;
         if (warp_on) {
-#pragma unroll 1
-          for (int c = 0; c < 9; ++c) {
-            float v[8];
-            umma::tmem_ld8(s_addr + c * 8, v);
+          umma::tmem_ld32(s_addr, sv);
+          umma::tmem_ld4(s_addr + 32, sv + 32);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float a = v[i];
-              if (shift > 0 && tokreg[kh * 72 + c * 8 + i] != rq) a += -100.0f;
-              mx = fmaxf(mx, a);
-            }
+          for (int i = 0; i < 36; ++i) {
+            sv[i] += ((i % 12) >= 6) ? add1 : add0;
+            mx = fmaxf(mx, sv[i]);
           }
-          if (active) red[kh * 144 + row] = mx;
+          if (active) red[kq * 144 + row] = mx;
         }
         __syncthreads();
-        if (warp_on) {
+        if (warp_on && active) {
+          mx = fmaxf(fmaxf(red[row], red[144 + row]), fmaxf(red[288 + row], red[432 + row]));
+          const float mb = mx * 1.4426950408889634f;
           float sum = 0.0f;
-          mx = active ? fmaxf(red[row], red[144 + row]) : 0.0f;
-#pragma unroll 1
-          for (int c = 0; c < 9; ++c) {
-            float v[8];
-            umma::tmem_ld8(s_addr + c * 8, v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float a = v[i];
-              if (shift > 0 && tokreg[kh * 72 + c * 8 + i] != rq) a += -100.0f;
-              v[i] = __expf(a - mx);
-              sum += v[i];
-            }
-            if (active)
-              *reinterpret_cast<uint4*>(smem + SM_P + (kh * 9 + c) * LBO_X + row * 16) =
-                  make_uint4(umma::pack_bf16x2(v[0], v[1]), umma::pack_bf16x2(v[2], v[3]), umma::pack_bf16x2(v[4], v[5]),
-                             umma::pack_bf16x2(v[6], v[7]));
+          for (int i = 0; i < 36; ++i) { sv[i] = exp2f(fmaf(sv[i], 1.4426950408889634f, -mb)); sum += sv[i]; }
+          // 36 keys = 4.5 chunks of 8: quarter kq starts at chunk 4.5 kq -> write 72-byte span as 16-byte + 8-byte pieces
+          uint8_t* prow = smem + SM_P + row * 16;
+#pragma unroll
+          for (int i = 0; i < 36; i += 4) {
+            const int key = kq * 36 + i;                      // multiple of 4
+            *reinterpret_cast<uint2*>(prow + (key >> 3) * LBO_X + (key & 7) * 2) =
+                make_uint2(umma::pack_bf16x2(sv[i], sv[i + 1]), umma::pack_bf16x2(sv[i + 2], sv[i + 3]));
           }
-          if (active) red[288 + kh * 144 + row] = sum;
+          rsum[kq * 144 + row] = sum;
         }
+        __syncthreads();
       }
       umma::fence_proxy_async();
       umma::fence_before_sync();
       __syncthreads();
+      PH(4);
       // ---- O_h = P V : K = 144 keys (9 k-steps), N = 32
       if (tid == 0) {
         umma::fence_after_sync();
@@ -264,14 +292,14 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
           for (int k = 0; k < 9; ++k)
-            umma::mma_bf16_ss(tm + (mt ? TM_O1 : TM_O0),
-                              umma::make_smem_desc(sb + SM_P + mt * 128 * 16 + k * 2 * LBO_X, LBO_X, 128),
-                              umma::make_smem_desc(sb + SM_VH + k * 1024, 512, 128), IDESC_PV, k > 0);
+            umma::mma_bf16_ss(tm + (mt ? TM_O1 : TM_O0), d_p + (uint64_t)((mt * 128 * 16 + k * 2 * LBO_X) >> 4),
+                              d_vh + (uint64_t)((k * 1024) >> 4), IDESC_PV, k > 0);
         umma::mma_commit(bar_o);
       }
       __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
       umma::mbar_wait(bar_o, ph_o); ph_o ^= 1;
       umma::fence_after_sync();
+      PH(5);
       // ---- O epilogue: thread = query row (tile 0: warps 0-3, tile 1: warp 4 lanes < 16)
       {
         const int mt = grp;                                   // group 0: tile 0, group 1 (lane quarter 0): tile 1
@@ -280,7 +308,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
           float v[32];
           umma::tmem_ld32(lane_addr + (mt ? TM_O1 : TM_O0), v);
           if (row < NTOK) {
-          const float inv = 1.0f / (red[288 + row] + red[288 + 144 + row]);
+          const float inv = 1.0f / ((rsum[row] + rsum[144 + row]) + (rsum[288 + row] + rsum[432 + row]));
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             *reinterpret_cast<uint4*>(smem + SM_O + (h * 4 + c) * LBO_X + row * 16) =
@@ -292,21 +320,23 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
       umma::fence_proxy_async();
       umma::fence_before_sync();
       __syncthreads();
+      PH(6);
     }
     // ---- Y^T = Wp . O^T
     if (tid == 0) {
       umma::fence_after_sync();
       umma::mbar_wait(&bar_full[nload & 1], (uint32_t)((nload >> 1) & 1));
       uint32_t wb = sb + SM_RING + (uint32_t)(nload & 1) * WIMG_BYTES;
+      const uint64_t wd = umma::make_smem_desc(wb, LBO_W, 128);
 #pragma unroll
       for (int k = 0; k < 8; ++k)
-        umma::mma_bf16_ss(tm + TM_QKV, umma::make_smem_desc(wb + k * 2 * LBO_W, LBO_W, 128),
-                          umma::make_smem_desc(sb + SM_O + k * 2 * LBO_X, LBO_X, 128), IDESC_T, k > 0);
+        umma::mma_bf16_ss(tm + TM_QKV, wd + (uint64_t)(k * 2 * (LBO_W >> 4)), d_o + (uint64_t)(k * 2 * (LBO_X >> 4)), IDESC_T, k > 0);
       umma::mma_commit(bar_y);
     }
     __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
     umma::mbar_wait(bar_y, ph_y); ph_y ^= 1;
     umma::fence_after_sync();
+    PH(7);
     if (tid == 0) issue_load(nload + 2);
     ++nload;
     // ---- x1 = x + Y + bproj : thread = feature, 72 tokens each; a warp touches 128 contiguous bytes per token
@@ -333,6 +363,8 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
+    PH(8);
+    if (dbg != nullptr && blockIdx.x == 0 && tid == 0) dbg[15] += 1;
   }
   if (warp == 0) umma::tmem_dealloc<512>(tm);
 }
@@ -348,7 +380,24 @@ cudaError_t launch_swin_attn_fast(float* X, const float* ag_qk, int nslice, int 
   int nwin = nslice * 4;
   int grid = nwin < num_sms ? nwin : num_sms;
   if (grid <= 0) return cudaSuccess;
-  swin_attn_fast_kernel<<<grid, SA_THREADS, SA_SMEM, st>>>(X, ag_qk, nwin, Te, shift, w);
+  static long long* dbg = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) {
+    const char* e = getenv("CATSEG_PHASE_TIMING");
+    dbg_on = (e && e[0] == '1') ? 1 : 0;
+    if (dbg_on) { cudaMalloc(&dbg, 16 * sizeof(long long)); cudaMemset(dbg, 0, 16 * sizeof(long long)); }
+  }
+  swin_attn_fast_kernel<<<grid, SA_THREADS, SA_SMEM, st>>>(X, ag_qk, nwin, Te, shift, w, dbg_on ? dbg : nullptr);
+  if (dbg_on) {
+    long long hbuf[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hbuf, dbg, sizeof(hbuf), cudaMemcpyDeviceToHost);
+    cudaMemset(dbg, 0, 16 * sizeof(long long));
+    double n = hbuf[15] > 0 ? (double)hbuf[15] : 1.0;
+    fprintf(stderr, "[swin_attn phases, cycles/window over %lld windows] LN %.0f | per head: qkv-mma+stage %.0f qkv-epi %.0f S-mma %.0f softmax %.0f "
+            "PV-mma %.0f O-epi %.0f | proj-mma %.0f Y-epi %.0f\n", hbuf[15], hbuf[0] / n, hbuf[1] / n / 4, hbuf[2] / n / 4, hbuf[3] / n / 4,
+            hbuf[4] / n / 4, hbuf[5] / n / 4, hbuf[6] / n / 4, hbuf[7] / n, hbuf[8] / n);
+  }
   return cudaGetLastError();
 }
 

@@ -74,6 +74,14 @@ __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 // ---- TMEM -> registers: each thread of warp w reads lane 32*(w%4)+lane, 16 or 32 consecutive columns
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
@@ -136,6 +144,9 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+
+// ---- L2 prefetch of a 128-byte line (no register, no dependency)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" :: "l"(p)); }
 
 // ---- pack helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
