@@ -83,6 +83,9 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
   const uint32_t lane_addr = tm + ((uint32_t)(q4 * 32) << 16);
   uint32_t ph_g = 0, ph_m1 = 0, ph_m2 = 0;
   bool w_ready = false;
+  const uint64_t d_xn = umma::make_smem_desc(sb + ST_XN, LBO_T, 128), d_g = umma::make_smem_desc(sb + ST_G, LBO_W, 128);
+  const uint64_t d_w = umma::make_smem_desc(sb + ST_W, LBO_W, 128);
+  const uint64_t d_kT = umma::make_smem_desc(sb + ST_XN, 128, LBO_V), d_vT = umma::make_smem_desc(sb + ST_G, 128, LBO_V);
   const float invS = 1.0f / (float)S;
 
   const long long nitems = (long long)B * npix;
@@ -106,9 +109,9 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
         umma::fence_after_sync();
         if (!w_ready) { umma::mbar_wait(bar_w, 0); w_ready = true; }
         umma::mbar_wait(bar_g, ph_g);
-        issue_gemm_k128(tm + ST_TM_KV, sb + ST_XN, LBO_T, sb + ST_W, LBO_W, IDESC_128x128, false);
-        issue_gemm_k128(tm + ST_TM_KV, sb + ST_G, LBO_W, sb + ST_W + WIMG_BYTES, LBO_W, IDESC_128x128, true);
-        issue_gemm_k128(tm + ST_TM_KV + 128, sb + ST_XN, LBO_T, sb + ST_W + 2 * WIMG_BYTES, LBO_W, IDESC_128x128, false);
+        issue_gemm_k128_desc(tm + ST_TM_KV, d_xn, LBO_T, d_w, LBO_W, IDESC_128x128, false);
+        issue_gemm_k128_desc(tm + ST_TM_KV, d_g, LBO_W, d_w + (uint64_t)(WIMG_BYTES >> 4), LBO_W, IDESC_128x128, true);
+        issue_gemm_k128_desc(tm + ST_TM_KV + 128, d_xn, LBO_T, d_w + (uint64_t)(2 * (WIMG_BYTES >> 4)), LBO_W, IDESC_128x128, false);
         umma::mma_commit(bar_m1);
       }
       __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
@@ -149,8 +152,7 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
         umma::fence_after_sync();
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma::mma_bf16_ss(tm + ST_TM_ACC, umma::make_smem_desc(sb + ST_XN + k * 256, 128, LBO_V),
-                            umma::make_smem_desc(sb + ST_G + k * 256, 128, LBO_V), IDESC_KV, (tl > 0 || k > 0) ? 1u : 0u);
+          umma::mma_bf16_ss(tm + ST_TM_ACC, d_kT + (uint64_t)(k * 16), d_vT + (uint64_t)(k * 16), IDESC_KV, (tl > 0 || k > 0) ? 1u : 0u);
         umma::mma_commit(bar_m2);
       }
       __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
@@ -234,10 +236,14 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
   };
   // thread 0: consume ring image `nimg` with an 8-k-step GEMM, then refill the other slot
   long long nimg = 0;
-  auto ring_gemm = [&](uint32_t d_tmem, uint32_t a_addr, uint32_t lbo_a, bool acc) {
+  const uint64_t d_ring = umma::make_smem_desc(sb + AP_RING, LBO_W, 128);
+  const uint64_t d_axn = umma::make_smem_desc(sb + AP_XN, LBO_T, 128), d_agd = umma::make_smem_desc(sb + AP_GH, LBO_W, 128);
+  const uint64_t d_agh = umma::make_smem_desc(sb + AP_GH, LBO_V, 128);
+  const uint64_t d_aq = umma::make_smem_desc(sb + AP_Q, LBO_V, 128), d_abst = umma::make_smem_desc(sb + AP_BST, 128, LBO_V);
+  auto ring_gemm = [&](uint32_t d_tmem, uint64_t a_desc, uint32_t lbo_a, bool acc) {
     int slot = (int)(nimg & 1);
     umma::mbar_wait(&bar_full[slot], (uint32_t)((nimg >> 1) & 1));
-    issue_gemm_k128(d_tmem, a_addr, lbo_a, sb + AP_RING + slot * WIMG_BYTES, LBO_W, IDESC_128x128, acc);
+    issue_gemm_k128_desc(d_tmem, a_desc, lbo_a, d_ring + (uint64_t)((uint32_t)slot * (WIMG_BYTES >> 4)), LBO_W, IDESC_128x128, acc);
     umma::mma_commit(&bar_empty[slot]);
     if (nimg > 0 && nimg + 1 < total_loads) {
       umma::mbar_wait(&bar_empty[(nimg - 1) & 1], (uint32_t)(((nimg - 1) >> 1) & 1));
@@ -296,9 +302,9 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
     // ---- q = [xn | g] [Wq_x | Wq_g]^T
     if (tid == 0) {
       umma::fence_after_sync();
-      ring_gemm(tm + AP_TM_Q, sb + AP_XN, LBO_T, false);
+      ring_gemm(tm + AP_TM_Q, d_axn, LBO_T, false);
       umma::mbar_wait(bar_g, ph_g);
-      ring_gemm(tm + AP_TM_Q, sb + AP_GH, LBO_W, true);
+      ring_gemm(tm + AP_TM_Q, d_agd, LBO_W, true);
       umma::mma_commit(bar_acc);
     }
     __syncwarp();
@@ -326,8 +332,7 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
       umma::fence_after_sync();
 #pragma unroll
       for (int k = 0; k < 8; ++k)
-        umma::mma_bf16_ss(tm + AP_TM_ND, umma::make_smem_desc(sb + AP_Q + k * 2 * LBO_V, LBO_V, 128),
-                          umma::make_smem_desc(sb + AP_BST + k * 256, 128, LBO_V), IDESC_APPLY, k > 0);
+        umma::mma_bf16_ss(tm + AP_TM_ND, d_aq + (uint64_t)(k * 2 * (LBO_V >> 4)), d_abst + (uint64_t)(k * 16), IDESC_APPLY, k > 0);
       umma::mma_commit(bar_acc);
     }
     __syncwarp();
@@ -397,7 +402,7 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
     for (int j = 0; j < 4; ++j) {
       if (tid == 0) {
         umma::fence_after_sync();
-        ring_gemm(tm + AP_TM_Q, sb + AP_XN, LBO_T, false);
+        ring_gemm(tm + AP_TM_Q, d_axn, LBO_T, false);
         umma::mma_commit(bar_acc);
       }
       __syncwarp();
@@ -420,7 +425,7 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
       __syncthreads();
       if (tid == 0) {
         umma::fence_after_sync();
-        ring_gemm(tm + AP_TM_Y, sb + AP_GH, LBO_V, j > 0);
+        ring_gemm(tm + AP_TM_Y, d_agh, LBO_V, j > 0);
         umma::mma_commit(bar_acc);
       }
       __syncwarp();

@@ -22,6 +22,17 @@ constexpr uint32_t TILE_BYTES_T = 16 * LBO_T;   // 128 features = 16 chunks
 constexpr uint32_t WIMG_BYTES = 16 * LBO_W;     // one 128x128 bf16 weight image = 32 KiB
 constexpr uint32_t IDESC_128x128 = umma::make_idesc_bf16(128, 128);
 
+// 8 k-steps of a [128 x 128] x [N x 128]^T GEMM from PRE-BUILT base descriptors: the issuing thread only adds the
+// K-step offset to the address field (building a descriptor from scratch costs ~50-100 cycles in one thread,
+// longer than the MMA itself; measured with the phase-timing hook).
+__device__ __forceinline__ void issue_gemm_k128_desc(uint32_t d_tmem, uint64_t a_desc, uint32_t lbo_a, uint64_t b_desc,
+                                                     uint32_t lbo_b, uint32_t idesc, bool acc_first) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    umma::mma_bf16_ss(d_tmem, a_desc + (uint64_t)(k * 2 * (lbo_a >> 4)), b_desc + (uint64_t)(k * 2 * (lbo_b >> 4)), idesc,
+                      (k > 0 || acc_first) ? 1u : 0u);
+}
+
 // 8 k-steps of a [128 x 128] x [N=128 x 128]^T GEMM; A/B are shared-memory byte addresses
 __device__ __forceinline__ void issue_gemm_k128(uint32_t d_tmem, uint32_t a_addr, uint32_t lbo_a, uint32_t b_addr,
                                                 uint32_t lbo_b, uint32_t idesc, bool acc_first) {

@@ -8,6 +8,9 @@
 //   epilogue: TMEM -> +b1 -> GELU -> bf16 -> shared memory (canonical K-major A operand)
 //   MMA2: Y_t += h W2_j^T        -> TMEM
 // and finally Y_t + b2 + x -> global.  TMEM: H_a H_b Y_a Y_b = 4 x 128 columns.
+#include <cstdio>
+#include <cstdlib>
+
 #include "fast_common.cuh"
 #include "internal.h"
 
@@ -26,9 +29,11 @@ constexpr uint32_t MLP_SMEM = SM_BAR + 8 * 8 + 16;
 static_assert(STG_BYTES <= 3 * TILE_BYTES_T, "the fp32 staging tile aliases the LN tiles + hidden chunk");
 }  // namespace
 
+#define PH(i) do { if (dbg != nullptr && blockIdx.x == 0 && tid == 0) { long long _t = clock64(); dbg[i] += _t - t_last; t_last = _t; } } while (0)
+
 template <int ACT>   // 0 = GELU (Swin), 1 = ReLU (class layer)
 __global__ void __launch_bounds__(MLP_THREADS, 1)
-mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w) {
+mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + SM_BAR);       // [3]
   uint64_t* bar_mma = bar_full + 3;                                       // [4]
@@ -57,6 +62,11 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w) {
   umma::fence_after_sync();
   const uint32_t tm = *tmem_slot;
   const uint32_t smem_base = umma::smem_u32(smem);
+  // base descriptors, built once
+  const uint64_t d_xn0 = umma::make_smem_desc(smem_base + SM_XN, LBO_T, 128);
+  const uint64_t d_xn1 = umma::make_smem_desc(smem_base + SM_XN + TILE_BYTES_T, LBO_T, 128);
+  const uint64_t d_h = umma::make_smem_desc(smem_base + SM_H, LBO_T, 128);
+  const uint64_t d_w0 = umma::make_smem_desc(smem_base + SM_RING, LBO_W, 128);
 
   auto issue_load = [&](long long n) {   // thread 0 only
     if (n < total_loads) {
@@ -73,6 +83,7 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w) {
   float* stage = reinterpret_cast<float*>(smem + SM_XN); // fp32 staging tile (LN tiles + h are dead by then)
   const uint32_t lane_addr = tm + ((uint32_t)(q * 32) << 16);
   long long g = 0;                                       // running hidden-chunk counter of this CTA
+  long long t_last = clock64();
 
   for (long long p = blockIdx.x; p < npass; p += gridDim.x) {
     const long long row0 = p * 256;
@@ -87,17 +98,20 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w) {
     umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
+    PH(0);
 
     for (int j = 0; j < 4; ++j, ++g) {
       const uint32_t par = (uint32_t)(g & 1);
       if (tid == 0) {
         umma::fence_after_sync();
         long long n = 2 * g;
+        long long tw0 = clock64();
         umma::mbar_wait(&bar_full[n % 3], (uint32_t)((n / 3) & 1));
-        uint32_t wb = smem_base + SM_RING + (uint32_t)(n % 3) * WIMG_BYTES;
-        issue_gemm_k128(tm + 0, smem_base + SM_XN, LBO_T, wb, LBO_W, IDESC_128x128, false);
+        if (dbg != nullptr && blockIdx.x == 0) dbg[6] += clock64() - tw0;
+        const uint64_t wd = d_w0 + (uint64_t)((uint32_t)(n % 3) * (WIMG_BYTES >> 4));
+        issue_gemm_k128_desc(tm + 0, d_xn0, LBO_T, wd, LBO_W, IDESC_128x128, false);
         umma::mma_commit(&bar_mma[0]);
-        issue_gemm_k128(tm + 128, smem_base + SM_XN + TILE_BYTES_T, LBO_T, wb, LBO_W, IDESC_128x128, false);
+        issue_gemm_k128_desc(tm + 128, d_xn1, LBO_T, wd, LBO_W, IDESC_128x128, false);
         umma::mma_commit(&bar_mma[1]);
       }
       __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
@@ -105,6 +119,7 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w) {
       for (int t = 0; t < 2; ++t) {
         umma::mbar_wait(&bar_mma[t], par);                 // H_t ready
         umma::fence_after_sync();
+        PH(1);
         if (t == 1 && tid == 0) issue_load(2 * g + 3);     // MMA1(b) done: the W1_j slot is free
         // ---- H_t -> bias -> act -> bf16 (32 columns per thread)
         uint4 packed[4];
@@ -122,6 +137,7 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w) {
             packed[c] = make_uint4(umma::pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]), umma::pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
                                    umma::pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), umma::pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]));
         }
+        PH(2);
         // ---- the h buffer is free once the previous MMA2 has completed
         if (t == 0) {
           if (j > 0) {
@@ -138,12 +154,15 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w) {
         umma::fence_proxy_async();
         umma::fence_before_sync();
         __syncthreads();
+        PH(3);
         if (tid == 0) {
           umma::fence_after_sync();
           long long n = 2 * g + 1;
+          long long tw0 = clock64();
           umma::mbar_wait(&bar_full[n % 3], (uint32_t)((n / 3) & 1));
-          uint32_t wb = smem_base + SM_RING + (uint32_t)(n % 3) * WIMG_BYTES;
-          issue_gemm_k128(tm + 256 + t * 128, smem_base + SM_H, LBO_T, wb, LBO_W, IDESC_128x128, j > 0);
+          if (dbg != nullptr && blockIdx.x == 0) dbg[7] += clock64() - tw0;
+          const uint64_t wd = d_w0 + (uint64_t)((uint32_t)(n % 3) * (WIMG_BYTES >> 4));
+          issue_gemm_k128_desc(tm + 256 + t * 128, d_h, LBO_T, wd, LBO_W, IDESC_128x128, j > 0);
           umma::mma_commit(&bar_mma[2 + t]);
         }
         __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
@@ -152,6 +171,7 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w) {
     // ---- all MMAs of this pass done -> Y epilogue
     umma::mbar_wait(&bar_mma[3], (uint32_t)((g - 1) & 1));
     umma::fence_after_sync();
+    PH(4);
     if (tid == 0) issue_load(2 * g + 2);
     // Y_t + b2 -> fp32 staging tile (thread = row), then X[row] += stage[row] with warp-per-row coalesced
     // 512-byte accesses (a per-thread-row global read-modify-write serialises on memory latency).
@@ -185,6 +205,8 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w) {
     umma::fence_before_sync();
     __syncthreads();          // TMEM and the LN tiles may be overwritten by the next pass
     umma::fence_after_sync();
+    PH(5);
+    if (dbg != nullptr && blockIdx.x == 0 && tid == 0) dbg[15] += 1;
   }
   if (warp == 0) umma::tmem_dealloc<512>(tm);
 }
@@ -201,8 +223,25 @@ cudaError_t launch_mlp_fast(float* X, long long ntok, const MlpFastW& w, int act
   long long npass = (ntok + 255) / 256;
   int grid = (int)(npass < num_sms ? npass : num_sms);
   if (grid <= 0) return cudaSuccess;
-  if (act == 0) mlp_fast_kernel<0><<<grid, MLP_THREADS, MLP_SMEM, st>>>(X, ntok, w);
-  else mlp_fast_kernel<1><<<grid, MLP_THREADS, MLP_SMEM, st>>>(X, ntok, w);
+  static long long* dbg = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) {
+    const char* e = getenv("CATSEG_PHASE_TIMING");
+    dbg_on = (e && e[0] == '1') ? 1 : 0;
+    if (dbg_on) { cudaMalloc(&dbg, 16 * sizeof(long long)); cudaMemset(dbg, 0, 16 * sizeof(long long)); }
+  }
+  if (act == 0) mlp_fast_kernel<0><<<grid, MLP_THREADS, MLP_SMEM, st>>>(X, ntok, w, dbg_on ? dbg : nullptr);
+  else mlp_fast_kernel<1><<<grid, MLP_THREADS, MLP_SMEM, st>>>(X, ntok, w, dbg_on ? dbg : nullptr);
+  if (dbg_on) {
+    long long hb[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hb, dbg, sizeof(hb), cudaMemcpyDeviceToHost);
+    cudaMemset(dbg, 0, 16 * sizeof(long long));
+    double n = hb[15] > 0 ? (double)hb[15] : 1.0;
+    fprintf(stderr, "[mlp phases, cycles/pass(256 tok) over %lld passes] LN %.0f | per (chunk,tile) x8: wait-H %.0f act %.0f h-free+STS+sync %.0f "
+            "| wait-last %.0f Y-epi %.0f | thread0 weight waits per pass: W1 %.0f W2 %.0f\n", hb[15], hb[0] / n, hb[1] / n / 8, hb[2] / n / 8,
+            hb[3] / n / 8, hb[4] / n, hb[5] / n, hb[6] / n, hb[7] / n);
+  }
   return cudaGetLastError();
 }
 

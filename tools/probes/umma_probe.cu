@@ -94,27 +94,25 @@ __global__ void gemm_probe(const float* A, const float* B, float* D, int N, int 
   if (t < 32) tmem_dealloc<256>(tm);
 }
 
-__global__ void tc_throughput(float* out, int iters, long long* cycles) {
+__global__ void tc_throughput(float* out, int iters, long long* cycles, int N, int lbo_a, int lbo_b) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base;
   int t = threadIdx.x;
-  for (int i = t; i < (128 * 64 + 256 * 64) * 2 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  for (int i = t; i < 20000; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   if (t == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
   if (t < 32) tmem_alloc<512>(&tmem_base);
   fence_proxy_async(); fence_before_sync(); __syncthreads(); fence_after_sync();
   uint32_t tm = tmem_base;
   long long t0 = clock64();
   if (t == 0) {
-    uint32_t idesc = make_idesc_bf16(128, 256);
-    uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 128 * 64 * 2);
+    uint32_t idesc = make_idesc_bf16(128, N);
+    uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 40000);
+    uint64_t da0 = make_smem_desc(a0, lbo_a, 128), db0 = make_smem_desc(b0, lbo_b, 128);
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint64_t da = make_smem_desc(a0 + k * 2 * 128 * 16, 128 * 16, 128);
-        uint64_t db = make_smem_desc(b0 + k * 2 * 256 * 16, 256 * 16, 128);
-        mma_bf16_ss(tm + (it & 1) * 256, da, db, idesc, 1);
-      }
+      for (int k = 0; k < 4; ++k)
+        mma_bf16_ss(tm + (it & 1) * 256, da0 + (uint64_t)(k * 2 * (lbo_a >> 4)), db0 + (uint64_t)(k * 2 * (lbo_b >> 4)), idesc, 1);
     }
     mma_commit(&bar);
   }
@@ -180,16 +178,21 @@ int main(int argc, char** argv) {
     float* out; long long* cyc; CHECK(cudaMalloc(&out, 4096)); CHECK(cudaMalloc(&cyc, 8));
     int iters = 20000;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    if (id == 10) {
-      size_t smem = (128 * 64 + 256 * 64) * 2;
+    if (id == 20) {
+      size_t smem = 100000;
       CHECK(cudaFuncSetAttribute(tc_throughput, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      tc_throughput<<<prop.multiProcessorCount, 128, smem>>>(out, 100, cyc); CHECK(cudaDeviceSynchronize());
-      cudaEventRecord(e0);
-      tc_throughput<<<prop.multiProcessorCount, 128, smem>>>(out, iters, cyc);
-      cudaEventRecord(e1); CHECK(cudaDeviceSynchronize());
-      float ms; cudaEventElapsedTime(&ms, e0, e1); long long c; CHECK(cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost));
-      double flops = 2.0 * 128 * 256 * 16 * 4 * iters * prop.multiProcessorCount;
-      printf("PROBE tcgen05 M128 N256: %.3f ms, %.1f TFLOP/s, %.1f cycles per MMA(K=16), SMs=%d\n", ms, flops / ms * 1e-9, (double)c / (4.0 * iters), prop.multiProcessorCount);
+      // (N, lbo_a, lbo_b): dense vs padded (not 128-byte aligned) K-chunk strides
+      const int cfgs[][3] = {{256, 2048, 4096}, {128, 2048, 2048}, {128, 2064, 2048}, {128, 2064, 2064}, {144, 2048, 2320}, {144, 2048, 2304},
+                             {64, 2048, 1024}, {32, 2048, 512}, {32, 2320, 512}, {16, 2048, 256}};
+      for (auto& c3 : cfgs) {
+        tc_throughput<<<prop.multiProcessorCount, 128, smem>>>(out, 100, cyc, c3[0], c3[1], c3[2]); CHECK(cudaDeviceSynchronize());
+        cudaEventRecord(e0);
+        tc_throughput<<<prop.multiProcessorCount, 128, smem>>>(out, iters, cyc, c3[0], c3[1], c3[2]);
+        cudaEventRecord(e1); CHECK(cudaDeviceSynchronize());
+        float ms; cudaEventElapsedTime(&ms, e0, e1); long long c; CHECK(cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost));
+        double flops = 2.0 * 128 * c3[0] * 16 * 4 * iters * prop.multiProcessorCount;
+        printf("PROBE tcgen05 M128 N%d lboA=%d lboB=%d: %.1f TFLOP/s, %.1f cycles per MMA(K=16)\n", c3[0], c3[1], c3[2], flops / ms * 1e-9, (double)c / (4.0 * iters));
+      }
     } else {
       for (int warps = 4; warps <= 16; warps *= 2) {
         mmasync_throughput<<<prop.multiProcessorCount, warps * 32>>>(out, 100, cyc); CHECK(cudaDeviceSynchronize());
