@@ -65,6 +65,7 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
   uint64_t* bar_m2 = bar_w + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 4);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q4 = warp & 3, half = warp >> 2;
+  const bool issuer = __shfl_sync(0xffffffffu, warp, 0) == 0;   // warp-uniform issue region, one elected lane
   const int row = q4 * 32 + lane;
   const int ntile = (Te + 127) / 128;
 
@@ -95,9 +96,12 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
       const int t0 = tl * 128;
       const int nvalid = Te - t0 < 128 ? Te - t0 : 128;
       // guidance tile of (b, tl) -> ST_G (the previous V image there is dead: its MMA2 was waited)
-      if (tid == 0) {
-        umma::mbar_expect_tx(bar_g, WIMG_BYTES);
-        umma::bulk_g2s(smem + ST_G, timg + ((long long)b * ntile + tl) * (128 * 128), WIMG_BYTES, bar_g);
+      if (issuer) {
+        if (umma::elect_one()) {
+          umma::mbar_expect_tx(bar_g, WIMG_BYTES);
+          umma::bulk_g2s(smem + ST_G, timg + ((long long)b * ntile + tl) * (128 * 128), WIMG_BYTES, bar_g);
+        }
+        __syncwarp();
       }
       ln_rows_to_tile(X + (((long long)b * Te + t0) * npix + pix) * 128, (long long)npix * 128, nvalid, smem + ST_XN, s_g,
                       s_be, warp, 8, lane);
@@ -105,16 +109,18 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
       umma::fence_before_sync();
       __syncthreads();
       // ---- k = [xn | g] [Wk_x | Wk_g]^T (cols 0..127), v = xn Wv^T (cols 128..255)
-      if (tid == 0) {
+      if (issuer) {
         umma::fence_after_sync();
         if (!w_ready) { umma::mbar_wait(bar_w, 0); w_ready = true; }
         umma::mbar_wait(bar_g, ph_g);
-        issue_gemm_k128_desc(tm + ST_TM_KV, d_xn, LBO_T, d_w, LBO_W, IDESC_128x128, false);
-        issue_gemm_k128_desc(tm + ST_TM_KV, d_g, LBO_W, d_w + (uint64_t)(WIMG_BYTES >> 4), LBO_W, IDESC_128x128, true);
-        issue_gemm_k128_desc(tm + ST_TM_KV + 128, d_xn, LBO_T, d_w + (uint64_t)(2 * (WIMG_BYTES >> 4)), LBO_W, IDESC_128x128, false);
-        umma::mma_commit(bar_m1);
+        if (umma::elect_one()) {
+          issue_gemm_k128_desc(tm + ST_TM_KV, d_xn, LBO_T, d_w, LBO_W, IDESC_128x128, false);
+          issue_gemm_k128_desc(tm + ST_TM_KV, d_g, LBO_W, d_w + (uint64_t)(WIMG_BYTES >> 4), LBO_W, IDESC_128x128, true);
+          issue_gemm_k128_desc(tm + ST_TM_KV + 128, d_xn, LBO_T, d_w + (uint64_t)(2 * (WIMG_BYTES >> 4)), LBO_W, IDESC_128x128, false);
+          umma::mma_commit(bar_m1);
+        }
+        __syncwarp();
       }
-      __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
       ph_g ^= 1;
       umma::mbar_wait(bar_m1, ph_m1); ph_m1 ^= 1;
       umma::fence_after_sync();
@@ -148,14 +154,16 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
       umma::fence_before_sync();
       __syncthreads();
       // ---- KV (+)= K^T [V | 1]  (contract over the 128 tokens of this tile)
-      if (tid == 0) {
+      if (issuer) {
         umma::fence_after_sync();
+        if (umma::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma::mma_bf16_ss(tm + ST_TM_ACC, d_kT + (uint64_t)(k * 16), d_vT + (uint64_t)(k * 16), IDESC_KV, (tl > 0 || k > 0) ? 1u : 0u);
-        umma::mma_commit(bar_m2);
+          for (int k = 0; k < 8; ++k)
+            umma::mma_bf16_ss(tm + ST_TM_ACC, d_kT + (uint64_t)(k * 16), d_vT + (uint64_t)(k * 16), IDESC_KV, (tl > 0 || k > 0) ? 1u : 0u);
+          umma::mma_commit(bar_m2);
+        }
+        __syncwarp();
       }
-      __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
       umma::mbar_wait(bar_m2, ph_m2); ph_m2 ^= 1;
       umma::fence_after_sync();
     }
@@ -203,6 +211,7 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
   uint64_t* bar_acc = bar_full + 5;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 6);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q4 = warp & 3, cq = warp >> 2;
+  const bool issuer = __shfl_sync(0xffffffffu, warp, 0) == 0;   // warp-uniform issue region, one elected lane
   const int row = q4 * 32 + lane;
   const int ntile = (Te + 127) / 128;
   const long long nitems = (long long)B * npix * ntile;
@@ -240,18 +249,27 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
   const uint64_t d_axn = umma::make_smem_desc(sb + AP_XN, LBO_T, 128), d_agd = umma::make_smem_desc(sb + AP_GH, LBO_W, 128);
   const uint64_t d_agh = umma::make_smem_desc(sb + AP_GH, LBO_V, 128);
   const uint64_t d_aq = umma::make_smem_desc(sb + AP_Q, LBO_V, 128), d_abst = umma::make_smem_desc(sb + AP_BST, 128, LBO_V);
+  // called by ALL lanes of warp 0 (uniform state); the issue instructions themselves run on one elected lane
   auto ring_gemm = [&](uint32_t d_tmem, uint64_t a_desc, uint32_t lbo_a, bool acc) {
-    int slot = (int)(nimg & 1);
+    const int slot = (int)(nimg & 1);
     umma::mbar_wait(&bar_full[slot], (uint32_t)((nimg >> 1) & 1));
-    issue_gemm_k128_desc(d_tmem, a_desc, lbo_a, d_ring + (uint64_t)((uint32_t)slot * (WIMG_BYTES >> 4)), LBO_W, IDESC_128x128, acc);
-    umma::mma_commit(&bar_empty[slot]);
+    const uint64_t wd = d_ring + (uint64_t)((uint32_t)slot * (WIMG_BYTES >> 4));
+    if (umma::elect_one()) {
+      issue_gemm_k128_desc(d_tmem, a_desc, lbo_a, wd, LBO_W, IDESC_128x128, acc);
+      umma::mma_commit(&bar_empty[slot]);
+    }
+    __syncwarp();
     if (nimg > 0 && nimg + 1 < total_loads) {
       umma::mbar_wait(&bar_empty[(nimg - 1) & 1], (uint32_t)(((nimg - 1) >> 1) & 1));
-      issue_load(nimg + 1);
+      if (umma::elect_one()) issue_load(nimg + 1);
+      __syncwarp();
     }
     ++nimg;
   };
-  if (tid == 0) { issue_load(0); issue_load(1); }
+  if (issuer) {
+    if (umma::elect_one()) { issue_load(0); issue_load(1); }
+    __syncwarp();
+  }
   uint32_t ph_g = 0, ph_acc = 0;
   const float fS = (float)S;
 
@@ -263,9 +281,12 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
     const int nvalid = Te - t0 < 128 ? Te - t0 : 128;
     const long long rstride = (long long)npix * 128;
     const long long row0off = (((long long)b * Te + t0) * npix + pix) * 128;
-    if (tid == 0) {
-      umma::mbar_expect_tx(bar_g, WIMG_BYTES);
-      umma::bulk_g2s(smem + AP_GH, timg + ((long long)b * ntile + tl) * (128 * 128), WIMG_BYTES, bar_g);
+    if (issuer) {
+      if (umma::elect_one()) {
+        umma::mbar_expect_tx(bar_g, WIMG_BYTES);
+        umma::bulk_g2s(smem + AP_GH, timg + ((long long)b * ntile + tl) * (128 * 128), WIMG_BYTES, bar_g);
+      }
+      __syncwarp();
     }
     ln_rows_to_tile(X + row0off, rstride, nvalid, smem + AP_XN, s_g1, s_be1, warp, 16, lane);
     // ---- Bstate [128 k x 144 n] (MN-major, 18 n-groups): thread k = (h, d) writes its whole row
@@ -300,14 +321,14 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
     umma::fence_before_sync();
     __syncthreads();
     // ---- q = [xn | g] [Wq_x | Wq_g]^T
-    if (tid == 0) {
+    if (issuer) {
       umma::fence_after_sync();
       ring_gemm(tm + AP_TM_Q, d_axn, LBO_T, false);
       umma::mbar_wait(bar_g, ph_g);
       ring_gemm(tm + AP_TM_Q, d_agd, LBO_W, true);
-      umma::mma_commit(bar_acc);
+      if (umma::elect_one()) umma::mma_commit(bar_acc);
+      __syncwarp();
     }
-    __syncwarp();
     ph_g ^= 1;
     umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
     umma::fence_after_sync();
@@ -328,14 +349,16 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
     umma::fence_before_sync();
     __syncthreads();
     // ---- [num | den] = phi(q) Bstate
-    if (tid == 0) {
+    if (issuer) {
       umma::fence_after_sync();
+      if (umma::elect_one()) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma::mma_bf16_ss(tm + AP_TM_ND, d_aq + (uint64_t)(k * 2 * (LBO_V >> 4)), d_abst + (uint64_t)(k * 16), IDESC_APPLY, k > 0);
-      umma::mma_commit(bar_acc);
+        for (int k = 0; k < 8; ++k)
+          umma::mma_bf16_ss(tm + AP_TM_ND, d_aq + (uint64_t)(k * 2 * (LBO_V >> 4)), d_abst + (uint64_t)(k * 16), IDESC_APPLY, k > 0);
+        umma::mma_commit(bar_acc);
+      }
+      __syncwarp();
     }
-    __syncwarp();
     umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
     umma::fence_after_sync();
     // ---- x tile -> staging (warp per row, coalesced; phi(q) and Bstate are dead now)
@@ -400,12 +423,12 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
     // ---- MLP 128 -> 512 (ReLU) -> 128, hidden chunks of 128 (H reuses the q columns)
 #pragma unroll 1
     for (int j = 0; j < 4; ++j) {
-      if (tid == 0) {
+      if (issuer) {
         umma::fence_after_sync();
         ring_gemm(tm + AP_TM_Q, d_axn, LBO_T, false);
-        umma::mma_commit(bar_acc);
+        if (umma::elect_one()) umma::mma_commit(bar_acc);
+        __syncwarp();
       }
-      __syncwarp();
       umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       umma::fence_after_sync();
       {
@@ -423,12 +446,12 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
       umma::fence_proxy_async();
       umma::fence_before_sync();
       __syncthreads();
-      if (tid == 0) {
+      if (issuer) {
         umma::fence_after_sync();
         ring_gemm(tm + AP_TM_Y, d_agh, LBO_V, j > 0);
-        umma::mma_commit(bar_acc);
+        if (umma::elect_one()) umma::mma_commit(bar_acc);
+        __syncwarp();
       }
-      __syncwarp();
       umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;     // h (and H) may be overwritten by the next chunk
       umma::fence_after_sync();
     }

@@ -43,6 +43,7 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w, long long* __
   float* s_g = s_b2 + 128;
   float* s_be = s_g + 128;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool issuer = __shfl_sync(0xffffffffu, warp, 0) == 0;   // warp-uniform: all of warp 0 runs the issue code, one lane is elected
 
   const long long npass = (ntok + 255) / 256;
   long long my_pass = 0;
@@ -76,14 +77,17 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w, long long* __
                      WIMG_BYTES, &bar_full[s]);
     }
   };
-  if (tid == 0) { issue_load(0); issue_load(1); issue_load(2); }
+  if (issuer) {
+    if (umma::elect_one()) { issue_load(0); issue_load(1); issue_load(2); }
+    __syncwarp();
+  }
 
   const int q = warp & 3, cq = warp >> 2;                // TMEM lane quarter, column quarter (32 columns)
   const int row = q * 32 + lane;                         // row of the tile owned by this thread
   float* stage = reinterpret_cast<float*>(smem + SM_XN); // fp32 staging tile (LN tiles + h are dead by then)
   const uint32_t lane_addr = tm + ((uint32_t)(q * 32) << 16);
   long long g = 0;                                       // running hidden-chunk counter of this CTA
-  long long t_last = clock64();
+  long long t_last = clock64(), t_issue1 = 0;
 
   for (long long p = blockIdx.x; p < npass; p += gridDim.x) {
     const long long row0 = p * 256;
@@ -102,25 +106,32 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w, long long* __
 
     for (int j = 0; j < 4; ++j, ++g) {
       const uint32_t par = (uint32_t)(g & 1);
-      if (tid == 0) {
+      if (issuer) {
         umma::fence_after_sync();
-        long long n = 2 * g;
+        const long long n = 2 * g;
         long long tw0 = clock64();
         umma::mbar_wait(&bar_full[n % 3], (uint32_t)((n / 3) & 1));
-        if (dbg != nullptr && blockIdx.x == 0) dbg[6] += clock64() - tw0;
+        if (dbg != nullptr && blockIdx.x == 0 && tid == 0) dbg[6] += clock64() - tw0;
+        t_issue1 = clock64();
         const uint64_t wd = d_w0 + (uint64_t)((uint32_t)(n % 3) * (WIMG_BYTES >> 4));
-        issue_gemm_k128_desc(tm + 0, d_xn0, LBO_T, wd, LBO_W, IDESC_128x128, false);
-        umma::mma_commit(&bar_mma[0]);
-        issue_gemm_k128_desc(tm + 128, d_xn1, LBO_T, wd, LBO_W, IDESC_128x128, false);
-        umma::mma_commit(&bar_mma[1]);
+        if (umma::elect_one()) {
+          issue_gemm_k128_desc(tm + 0, d_xn0, LBO_T, wd, LBO_W, IDESC_128x128, false);
+          umma::mma_commit(&bar_mma[0]);
+          issue_gemm_k128_desc(tm + 128, d_xn1, LBO_T, wd, LBO_W, IDESC_128x128, false);
+          umma::mma_commit(&bar_mma[1]);
+        }
+        __syncwarp();
       }
-      __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
 #pragma unroll 1
       for (int t = 0; t < 2; ++t) {
         umma::mbar_wait(&bar_mma[t], par);                 // H_t ready
         umma::fence_after_sync();
+        if (dbg != nullptr && blockIdx.x == 0 && tid == 0) dbg[8 + t] += clock64() - t_issue1;
         PH(1);
-        if (t == 1 && tid == 0) issue_load(2 * g + 3);     // MMA1(b) done: the W1_j slot is free
+        if (t == 1 && issuer) {                            // MMA1(b) done: the W1_j slot is free
+          if (umma::elect_one()) issue_load(2 * g + 3);
+          __syncwarp();
+        }
         // ---- H_t -> bias -> act -> bf16 (32 columns per thread)
         uint4 packed[4];
         {
@@ -142,7 +153,10 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w, long long* __
         if (t == 0) {
           if (j > 0) {
             umma::mbar_wait(&bar_mma[3], (uint32_t)((g - 1) & 1));
-            if (tid == 0) issue_load(2 * g + 2);           // MMA2(b) of chunk g-1 done: its W2 slot is free
+            if (issuer) {                                  // MMA2(b) of chunk g-1 done: its W2 slot is free
+              if (umma::elect_one()) issue_load(2 * g + 2);
+              __syncwarp();
+            }
           }
         } else {
           umma::mbar_wait(&bar_mma[2], par);
@@ -155,24 +169,29 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w, long long* __
         umma::fence_before_sync();
         __syncthreads();
         PH(3);
-        if (tid == 0) {
+        if (issuer) {
           umma::fence_after_sync();
-          long long n = 2 * g + 1;
+          const long long n = 2 * g + 1;
           long long tw0 = clock64();
           umma::mbar_wait(&bar_full[n % 3], (uint32_t)((n / 3) & 1));
-          if (dbg != nullptr && blockIdx.x == 0) dbg[7] += clock64() - tw0;
+          if (dbg != nullptr && blockIdx.x == 0 && tid == 0) dbg[7] += clock64() - tw0;
           const uint64_t wd = d_w0 + (uint64_t)((uint32_t)(n % 3) * (WIMG_BYTES >> 4));
-          issue_gemm_k128_desc(tm + 256 + t * 128, d_h, LBO_T, wd, LBO_W, IDESC_128x128, j > 0);
-          umma::mma_commit(&bar_mma[2 + t]);
+          if (umma::elect_one()) {
+            issue_gemm_k128_desc(tm + 256 + t * 128, d_h, LBO_T, wd, LBO_W, IDESC_128x128, j > 0);
+            umma::mma_commit(&bar_mma[2 + t]);
+          }
+          __syncwarp();
         }
-        __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
       }
     }
     // ---- all MMAs of this pass done -> Y epilogue
     umma::mbar_wait(&bar_mma[3], (uint32_t)((g - 1) & 1));
     umma::fence_after_sync();
     PH(4);
-    if (tid == 0) issue_load(2 * g + 2);
+    if (issuer) {
+      if (umma::elect_one()) issue_load(2 * g + 2);
+      __syncwarp();
+    }
     // Y_t + b2 -> fp32 staging tile (thread = row), then X[row] += stage[row] with warp-per-row coalesced
     // 512-byte accesses (a per-thread-row global read-modify-write serialises on memory latency).
 #pragma unroll 1
@@ -239,8 +258,8 @@ cudaError_t launch_mlp_fast(float* X, long long ntok, const MlpFastW& w, int act
     cudaMemset(dbg, 0, 16 * sizeof(long long));
     double n = hb[15] > 0 ? (double)hb[15] : 1.0;
     fprintf(stderr, "[mlp phases, cycles/pass(256 tok) over %lld passes] LN %.0f | per (chunk,tile) x8: wait-H %.0f act %.0f h-free+STS+sync %.0f "
-            "| wait-last %.0f Y-epi %.0f | thread0 weight waits per pass: W1 %.0f W2 %.0f\n", hb[15], hb[0] / n, hb[1] / n / 8, hb[2] / n / 8,
-            hb[3] / n / 8, hb[4] / n, hb[5] / n, hb[6] / n, hb[7] / n);
+            "| wait-last %.0f Y-epi %.0f | thread0 weight waits per pass: W1 %.0f W2 %.0f | MMA1 issue->H_a ready %.0f, ->H_b ready %.0f (per chunk)\n", hb[15], hb[0] / n, hb[1] / n / 8, hb[2] / n / 8,
+            hb[3] / n / 8, hb[4] / n, hb[5] / n, hb[6] / n, hb[7] / n, hb[8] / n / 4, hb[9] / n / 4);
   }
   return cudaGetLastError();
 }

@@ -69,6 +69,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 6);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q4 = warp & 3, grp = warp >> 2;
+  const bool issuer = __shfl_sync(0xffffffffu, warp, 0) == 0;   // warp-uniform issue region, one elected lane
 
   long long mine = 0;
   for (long long i = blockIdx.x; i < nwin_total; i += gridDim.x) ++mine;
@@ -90,6 +91,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
   const uint64_t d_xn = umma::make_smem_desc(sb + SM_XN, LBO_X, 128), d_o = umma::make_smem_desc(sb + SM_O, LBO_X, 128);
   const uint64_t d_qh = umma::make_smem_desc(sb + SM_QH, 128, 512), d_kh = umma::make_smem_desc(sb + SM_KH, 128, 512);
   const uint64_t d_p = umma::make_smem_desc(sb + SM_P, LBO_X, 128), d_vh = umma::make_smem_desc(sb + SM_VH, 512, 128);
+  const uint64_t d_ring = umma::make_smem_desc(sb + SM_RING, LBO_W, 128);
 
   auto issue_load = [&](long long n) {      // thread 0 only
     if (n < total_loads) {
@@ -99,7 +101,10 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
                      WIMG_BYTES, &bar_full[s]);
     }
   };
-  if (tid == 0) { issue_load(0); issue_load(1); }
+  if (issuer) {
+    if (umma::elect_one()) { issue_load(0); issue_load(1); }
+    __syncwarp();
+  }
 
   long long t_last = clock64();
   long long nload = 0;          // index of the next weight image to be consumed by this CTA
@@ -152,17 +157,18 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
     PH(0);
     for (int h = 0; h < 4; ++h) {
       // ---- [q_h;k_h;v_h]^T = Wqkv_h . XN^T
-      if (tid == 0) {
+      if (issuer) {
         umma::fence_after_sync();
         umma::mbar_wait(&bar_full[nload & 1], (uint32_t)((nload >> 1) & 1));
-        uint32_t wb = sb + SM_RING + (uint32_t)(nload & 1) * WIMG_BYTES;
-        const uint64_t wd = umma::make_smem_desc(wb, LBO_W, 128);
+        const uint64_t wd = d_ring + (uint64_t)((uint32_t)(nload & 1) * (WIMG_BYTES >> 4));
+        if (umma::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma::mma_bf16_ss(tm + TM_QKV, wd + (uint64_t)(k * 2 * (LBO_W >> 4)), d_xn + (uint64_t)(k * 2 * (LBO_X >> 4)), IDESC_T, k > 0);
-        umma::mma_commit(bar_a);
+          for (int k = 0; k < 8; ++k)
+            umma::mma_bf16_ss(tm + TM_QKV, wd + (uint64_t)(k * 2 * (LBO_W >> 4)), d_xn + (uint64_t)(k * 2 * (LBO_X >> 4)), IDESC_T, k > 0);
+          umma::mma_commit(bar_a);
+        }
+        __syncwarp();
       }
-      __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
       // ---- while the MMA runs: stage this head's guidance terms [144 tok][q 32 | k 32] (fp32) in the P region,
       //      which is free until the softmax of this head (coalesced 128-byte rows, one latency)
       {
@@ -184,7 +190,10 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
       umma::mbar_wait(bar_a, ph_a); ph_a ^= 1;
       umma::fence_after_sync();
       PH(1);
-      if (tid == 0) issue_load(nload + 2);
+      if (issuer) {
+        if (umma::elect_one()) issue_load(nload + 2);
+        __syncwarp();
+      }
       ++nload;
       // ---- epilogue: feature threads (lane quarter 0:q 1:k 2:v) write the per-head images
       if (q4 < 3) {
@@ -217,17 +226,19 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
       __syncthreads();
       PH(2);
       // ---- S = Q K^T : two query tiles, K = 32 (two k-steps)
-      if (tid == 0) {
+      if (issuer) {
         umma::fence_after_sync();
+        if (umma::elect_one()) {
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma::mma_bf16_ss(tm + (mt ? TM_S1 : TM_S0), d_qh + (uint64_t)((mt * 16 * 512 + k * 256) >> 4),
-                              d_kh + (uint64_t)((k * 256) >> 4), IDESC_S, k > 0);
-        umma::mma_commit(bar_s);
+            for (int k = 0; k < 2; ++k)
+              umma::mma_bf16_ss(tm + (mt ? TM_S1 : TM_S0), d_qh + (uint64_t)((mt * 16 * 512 + k * 256) >> 4),
+                                d_kh + (uint64_t)((k * 256) >> 4), IDESC_S, k > 0);
+          umma::mma_commit(bar_s);
+        }
+        __syncwarp();
       }
-      __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
       umma::mbar_wait(bar_s, ph_s); ph_s ^= 1;
       umma::fence_after_sync();
       PH(3);
@@ -286,17 +297,19 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
       __syncthreads();
       PH(4);
       // ---- O_h = P V : K = 144 keys (9 k-steps), N = 32
-      if (tid == 0) {
+      if (issuer) {
         umma::fence_after_sync();
+        if (umma::elect_one()) {
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int k = 0; k < 9; ++k)
-            umma::mma_bf16_ss(tm + (mt ? TM_O1 : TM_O0), d_p + (uint64_t)((mt * 128 * 16 + k * 2 * LBO_X) >> 4),
-                              d_vh + (uint64_t)((k * 1024) >> 4), IDESC_PV, k > 0);
-        umma::mma_commit(bar_o);
+            for (int k = 0; k < 9; ++k)
+              umma::mma_bf16_ss(tm + (mt ? TM_O1 : TM_O0), d_p + (uint64_t)((mt * 128 * 16 + k * 2 * LBO_X) >> 4),
+                                d_vh + (uint64_t)((k * 1024) >> 4), IDESC_PV, k > 0);
+          umma::mma_commit(bar_o);
+        }
+        __syncwarp();
       }
-      __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
       umma::mbar_wait(bar_o, ph_o); ph_o ^= 1;
       umma::fence_after_sync();
       PH(5);
@@ -323,21 +336,25 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
       PH(6);
     }
     // ---- Y^T = Wp . O^T
-    if (tid == 0) {
+    if (issuer) {
       umma::fence_after_sync();
       umma::mbar_wait(&bar_full[nload & 1], (uint32_t)((nload >> 1) & 1));
-      uint32_t wb = sb + SM_RING + (uint32_t)(nload & 1) * WIMG_BYTES;
-      const uint64_t wd = umma::make_smem_desc(wb, LBO_W, 128);
+      const uint64_t wd = d_ring + (uint64_t)((uint32_t)(nload & 1) * (WIMG_BYTES >> 4));
+      if (umma::elect_one()) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma::mma_bf16_ss(tm + TM_QKV, wd + (uint64_t)(k * 2 * (LBO_W >> 4)), d_o + (uint64_t)(k * 2 * (LBO_X >> 4)), IDESC_T, k > 0);
-      umma::mma_commit(bar_y);
+        for (int k = 0; k < 8; ++k)
+          umma::mma_bf16_ss(tm + TM_QKV, wd + (uint64_t)(k * 2 * (LBO_W >> 4)), d_o + (uint64_t)(k * 2 * (LBO_X >> 4)), IDESC_T, k > 0);
+        umma::mma_commit(bar_y);
+      }
+      __syncwarp();
     }
-    __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
     umma::mbar_wait(bar_y, ph_y); ph_y ^= 1;
     umma::fence_after_sync();
     PH(7);
-    if (tid == 0) issue_load(nload + 2);
+    if (issuer) {
+      if (umma::elect_one()) issue_load(nload + 2);
+      __syncwarp();
+    }
     ++nload;
     // ---- x1 = x + Y + bproj : thread = feature, 72 tokens each; a warp touches 128 contiguous bytes per token
     {

@@ -148,6 +148,14 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 // ---- L2 prefetch of a 128-byte line (no register, no dependency)
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" :: "l"(p)); }
 
+// ---- elect one lane of a fully converged warp (warp-uniform issue regions: descriptors stay in uniform registers;
+// under `if (threadIdx.x == 0)` ptxas emits an ELECT/R2UR waterfall loop before every UTCHMMA, ~150 cycles per MMA)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- pack helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -94,13 +94,14 @@ __global__ void gemm_probe(const float* A, const float* B, float* D, int N, int 
   if (t < 32) tmem_dealloc<256>(tm);
 }
 
-__global__ void tc_throughput(float* out, int iters, long long* cycles, int N, int lbo_a, int lbo_b) {
+__global__ void tc_throughput(float* out, int iters, long long* cycles, int N, int lbo_a, int lbo_b, int commit_every = 0) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
+  __shared__ uint64_t bar2;
   __shared__ uint32_t tmem_base;
   int t = threadIdx.x;
   for (int i = t; i < 20000; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
-  if (t == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (t == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1); mbar_fence_init(); }
   if (t < 32) tmem_alloc<512>(&tmem_base);
   fence_proxy_async(); fence_before_sync(); __syncthreads(); fence_after_sync();
   uint32_t tm = tmem_base;
@@ -113,6 +114,7 @@ __global__ void tc_throughput(float* out, int iters, long long* cycles, int N, i
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         mma_bf16_ss(tm + (it & 1) * 256, da0 + (uint64_t)(k * 2 * (lbo_a >> 4)), db0 + (uint64_t)(k * 2 * (lbo_b >> 4)), idesc, 1);
+      if (commit_every && (it % commit_every) == commit_every - 1) mma_commit(&bar2);   // nobody waits on bar2
     }
     mma_commit(&bar);
   }
@@ -120,6 +122,64 @@ __global__ void tc_throughput(float* out, int iters, long long* cycles, int N, i
   long long t1 = clock64();
   fence_after_sync();
   if (t == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+  float v[16];
+  if (t < 128) { tmem_ld16(tm + ((uint32_t)((t >> 5) * 32) << 16), v); if (v[0] == 12345.f) out[t] = v[0]; }
+  fence_before_sync(); __syncthreads();
+  if (t < 32) tmem_dealloc<512>(tm);
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+
+// Issue-cost probe: GEMMs of 8 MMAs (N=128) with k-dependent descriptors + a commit per GEMM, issued either by
+// `if (threadIdx.x == 0)` (mode 0) or by warp 0 under elect.sync in a warp-uniform branch (mode 1).
+__global__ void issue_cost(float* out, int ngemm, long long* cycles, int mode, int a_off = 0, int b_off = 40000) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar, bar2;
+  __shared__ uint32_t tmem_base;
+  int t = threadIdx.x;
+  for (int i = t; i < 55000; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (t == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1); mbar_fence_init(); }
+  if (t < 32) tmem_alloc<512>(&tmem_base);
+  fence_proxy_async(); fence_before_sync(); __syncthreads(); fence_after_sync();
+  uint32_t tm = tmem_base;
+  const uint32_t idesc = make_idesc_bf16(128, 128);
+  const uint64_t da0 = make_smem_desc(smem_u32(smem + a_off), 2064, 128), db0 = make_smem_desc(smem_u32(smem + b_off), 2048, 128);
+  const int warp_u = __shfl_sync(0xffffffffu, t >> 5, 0);
+  long long t0 = clock64();
+  if (mode == 0) {
+    if (t == 0) {
+      for (int g = 0; g < ngemm; ++g) {
+        uint64_t wd = db0 + (uint64_t)((uint32_t)(g % 3) * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mma_bf16_ss(tm + (g & 3) * 128, da0 + (uint64_t)(k * 2 * 129), wd + (uint64_t)(k * 2 * 128), idesc, k > 0);
+        mma_commit(&bar2);
+      }
+      mma_commit(&bar);
+    }
+  } else {
+    if (warp_u == 0) {
+      for (int g = 0; g < ngemm; ++g) {
+        uint64_t wd = db0 + (uint64_t)((uint32_t)(g % 3) * 8);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) mma_bf16_ss(tm + (g & 3) * 128, da0 + (uint64_t)(k * 2 * 129), wd + (uint64_t)(k * 2 * 128), idesc, k > 0);
+          mma_commit(&bar2);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) mma_commit(&bar);
+      __syncwarp();
+    }
+  }
+  long long t_issue = clock64();
+  mbar_wait(&bar, 0);
+  long long t1 = clock64();
+  fence_after_sync();
+  if (t == 0 && blockIdx.x == 0) { cycles[0] = t1 - t0; cycles[1] = t_issue - t0; }
   float v[16];
   if (t < 128) { tmem_ld16(tm + ((uint32_t)((t >> 5) * 32) << 16), v); if (v[0] == 12345.f) out[t] = v[0]; }
   fence_before_sync(); __syncthreads();
@@ -178,20 +238,45 @@ int main(int argc, char** argv) {
     float* out; long long* cyc; CHECK(cudaMalloc(&out, 4096)); CHECK(cudaMalloc(&cyc, 8));
     int iters = 20000;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    if (id == 20) {
+    if (id == 23) {
+      size_t smem = 100000;
+      CHECK(cudaFuncSetAttribute(issue_cost, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      long long* cyc2; CHECK(cudaMalloc(&cyc2, 16));
+      smem = 225000;
+      CHECK(cudaFuncSetAttribute(issue_cost, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int offs[][2] = {{0, 40000}, {100000, 40000}, {135168, 40000}, {170000, 40000}, {0, 135168}, {135168, 175104}, {98304, 0}, {131328, 0}, {164352, 32768}};
+      for (auto& o : offs) {
+        issue_cost<<<prop.multiProcessorCount, 512, smem>>>(out, 2000, cyc2, 0, o[0], o[1]); CHECK(cudaDeviceSynchronize());
+        long long c[2]; CHECK(cudaMemcpy(c, cyc2, 16, cudaMemcpyDeviceToHost));
+        printf("PROBE operand placement A@%d B@%d: %.1f cycles per MMA (M128 N128)\n", o[0], o[1], (double)c[0] / (2000.0 * 8));
+      }
+      for (int mode = 0; mode < 2; ++mode) {
+        issue_cost<<<prop.multiProcessorCount, 512, smem>>>(out, 2000, cyc2, mode); CHECK(cudaDeviceSynchronize());
+        long long c[2]; CHECK(cudaMemcpy(c, cyc2, 16, cudaMemcpyDeviceToHost));
+        printf("PROBE issue cost (%s): %.1f cycles per MMA end-to-end, %.1f cycles per MMA spent issuing (8-MMA GEMMs + commit)\n",
+               mode == 0 ? "if (tid == 0)" : "warp 0 + elect.sync", (double)c[0] / (2000.0 * 8), (double)c[1] / (2000.0 * 8));
+      }
+    } else if (id == 20) {
       size_t smem = 100000;
       CHECK(cudaFuncSetAttribute(tc_throughput, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       // (N, lbo_a, lbo_b): dense vs padded (not 128-byte aligned) K-chunk strides
       const int cfgs[][3] = {{256, 2048, 4096}, {128, 2048, 2048}, {128, 2064, 2048}, {128, 2064, 2064}, {144, 2048, 2320}, {144, 2048, 2304},
                              {64, 2048, 1024}, {32, 2048, 512}, {32, 2320, 512}, {16, 2048, 256}};
+      int nthreads = argc > 2 ? atoi(argv[2]) : 128;     // all threads but one spin on the mbarrier while the MMAs run
+      printf("PROBE threads per CTA = %d\n", nthreads);
       for (auto& c3 : cfgs) {
-        tc_throughput<<<prop.multiProcessorCount, 128, smem>>>(out, 100, cyc, c3[0], c3[1], c3[2]); CHECK(cudaDeviceSynchronize());
+        tc_throughput<<<prop.multiProcessorCount, nthreads, smem>>>(out, 100, cyc, c3[0], c3[1], c3[2]); CHECK(cudaDeviceSynchronize());
         cudaEventRecord(e0);
-        tc_throughput<<<prop.multiProcessorCount, 128, smem>>>(out, iters, cyc, c3[0], c3[1], c3[2]);
+        tc_throughput<<<prop.multiProcessorCount, nthreads, smem>>>(out, iters, cyc, c3[0], c3[1], c3[2]);
         cudaEventRecord(e1); CHECK(cudaDeviceSynchronize());
         float ms; cudaEventElapsedTime(&ms, e0, e1); long long c; CHECK(cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost));
         double flops = 2.0 * 128 * c3[0] * 16 * 4 * iters * prop.multiProcessorCount;
         printf("PROBE tcgen05 M128 N%d lboA=%d lboB=%d: %.1f TFLOP/s, %.1f cycles per MMA(K=16)\n", c3[0], c3[1], c3[2], flops / ms * 1e-9, (double)c / (4.0 * iters));
+      }
+      for (int ce = 1; ce <= 4; ce *= 2) {      // a tcgen05.commit after every 4*ce MMAs (as the fused kernels do per GEMM)
+        tc_throughput<<<prop.multiProcessorCount, nthreads, smem>>>(out, iters, cyc, 128, 2064, 2048, ce); CHECK(cudaDeviceSynchronize());
+        long long c; CHECK(cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost));
+        printf("PROBE tcgen05 M128 N128 with a commit every %d MMAs: %.1f cycles per MMA(K=16)\n", 4 * ce, (double)c / (4.0 * iters));
       }
     } else {
       for (int warps = 4; warps <= 16; warps *= 2) {
