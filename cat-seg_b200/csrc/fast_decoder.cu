@@ -86,7 +86,6 @@ __global__ void __launch_bounds__(256, 2) band_conv_kernel(BandConvParams p) {
   uint64_t* bar_acc = bar_empty + C::NSLOT;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q4 = warp & 3, tgrp = warp >> 2;   // 8 warps
-  const bool issuer = __shfl_sync(0xffffffffu, warp, 0) == 0;   // warp-uniform issue region, one elected lane
 
   const long long nitems = (long long)p.nslice * C::NB;
   long long mine = 0;
@@ -113,19 +112,14 @@ __global__ void __launch_bounds__(256, 2) band_conv_kernel(BandConvParams p) {
                      reinterpret_cast<const uint8_t*>(p.wimg) + (n % C::NIMG) * C::WBYTES, C::WBYTES, &bar_full[s]);
     }
   };
-  if (issuer) {
-    if (umma::elect_one()) {
-      if (C::RESIDENT) {
-        umma::mbar_expect_tx(&bar_full[0], C::NIMG * C::WBYTES);
-        umma::bulk_g2s(smem + C::SM_W, p.wimg, C::NIMG * C::WBYTES, &bar_full[0]);
-      } else {
-        for (int i = 0; i < C::NSLOT - 1; ++i) issue_load(i);
-      }
+  if (tid == 0) {
+    if (C::RESIDENT) {
+      umma::mbar_expect_tx(&bar_full[0], C::NIMG * C::WBYTES);
+      umma::bulk_g2s(smem + C::SM_W, p.wimg, C::NIMG * C::WBYTES, &bar_full[0]);
+    } else {
+      for (int i = 0; i < C::NSLOT - 1; ++i) issue_load(i);
     }
-    __syncwarp();
   }
-  const uint64_t a_desc0 = umma::make_smem_desc(sb, C::LBO_I, 128);
-  const uint64_t w_desc0 = umma::make_smem_desc(sb + C::SM_W, C::LBO_WT, 128);
   long long nimg = 0;          // streaming: images consumed so far by this CTA
   uint32_t ph_acc = 0;
   bool w_ready = false;
@@ -217,48 +211,49 @@ __global__ void __launch_bounds__(256, 2) band_conv_kernel(BandConvParams p) {
 #pragma unroll 1
     for (int pg = 0; pg < C::NPG; ++pg) {
       const int pa = pg >> 1, pb = pg & 1;
-      if (issuer) {          // all lanes of warp 0 keep the (uniform) ring state; one elected lane issues
+      if (tid == 0) {
         umma::fence_after_sync();
         if (C::RESIDENT && !w_ready) { umma::mbar_wait(&bar_full[0], 0); w_ready = true; }
+        const uint64_t a_desc0 = umma::make_smem_desc(sb, C::LBO_I, 128);
 #pragma unroll 1
         for (int tap = 0; tap < C::NTAP; ++tap) {
           int off;
           if (UPS) off = ((tap >> 1) + pa - 1) * C::PW + ((tap & 1) + pb - 1);
           else off = (tap / 3 - 1) * C::PW + (tap % 3 - 1);
+          uint32_t wb;
           int slot = 0;
-          uint64_t b_desc;
           if (C::RESIDENT) {
-            b_desc = w_desc0 + (uint64_t)((uint32_t)(pg * C::NTAP + tap) * (C::WBYTES >> 4));
+            wb = sb + C::SM_W + (uint32_t)(pg * C::NTAP + tap) * C::WBYTES;
           } else {
             slot = (int)(nimg % C::NSLOT);
             umma::mbar_wait(&bar_full[slot], (uint32_t)((nimg / C::NSLOT) & 1));
-            b_desc = w_desc0 + (uint64_t)((uint32_t)slot * (C::WBYTES >> 4));
+            wb = sb + C::SM_W + (uint32_t)slot * C::WBYTES;
           }
-          const uint64_t a_tap = a_desc0 + (uint64_t)(uint32_t)(C::P0 + off);
-          if (umma::elect_one()) {
+          // descriptors are built once and advanced by integer adds on the (address >> 4) field: the single
+          // issuing thread must spend ~10 cycles per MMA, not ~100 (these MMAs are only 8-32 tensor cycles long)
+          const uint64_t b_desc = umma::make_smem_desc(wb, C::LBO_WT, 128);
+          uint64_t a_tile = a_desc0 + (uint64_t)(uint32_t)(C::P0 + off);
+#pragma unroll 1
+          for (int t = 0; t < C::NTILES; ++t) {
 #pragma unroll
-            for (int t = 0; t < C::NTILES; ++t) {
-#pragma unroll
-              for (int k = 0; k < C::KSTEPS; ++k)
-                umma::mma_bf16_ss(tm + t * NOUT, a_tap + (uint64_t)(t * 128 + k * 2 * (C::LBO_I >> 4)),
-                                  b_desc + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC, (tap > 0 || k > 0) ? 1u : 0u);
-            }
-            if (!C::RESIDENT) umma::mma_commit(&bar_empty[slot]);
+            for (int k = 0; k < C::KSTEPS; ++k)
+              umma::mma_bf16_ss(tm + t * NOUT, a_tile + (uint64_t)(k * 2 * (C::LBO_I >> 4)),
+                                b_desc + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC, (tap > 0 || k > 0) ? 1u : 0u);
+            a_tile += 128;
           }
-          __syncwarp();
           if (!C::RESIDENT) {
+            umma::mma_commit(&bar_empty[slot]);
             // refill the slot of the PREVIOUS image (its MMAs were committed one step ago)
-            const long long nn = nimg + C::NSLOT - 1;
+            long long nn = nimg + C::NSLOT - 1;
             if (nimg > 0 && nn < total_loads)
               umma::mbar_wait(&bar_empty[(nimg - 1) % C::NSLOT], (uint32_t)(((nimg - 1) / C::NSLOT) & 1));
-            if (umma::elect_one()) issue_load(nn);
-            __syncwarp();
+            issue_load(nn);
             ++nimg;
           }
         }
-        if (umma::elect_one()) umma::mma_commit(bar_acc);
-        __syncwarp();
+        umma::mma_commit(bar_acc);
       }
+      __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
       // ---- epilogue: thread = padded raster row; the two warp sets take alternate tiles.  The additive map
       //      of the first tile is fetched BEFORE waiting for the accumulators (hides the global latency).
       float e_pre[HEAD ? 1 : NREAL];
