@@ -51,15 +51,16 @@ __device__ __forceinline__ void ln_rows_to_tile(const float* __restrict__ src, l
                                                 uint8_t* tile, const float* __restrict__ gamma,
                                                 const float* __restrict__ beta, int warp, int nwarps, int lane) {
   const float4 g = ld4(gamma + lane * 4), be = ld4(beta + lane * 4);
-  for (int r0 = warp * 4; r0 < TILE; r0 += nwarps * 4) {
-    float4 x[4];
+  constexpr int R = 8;                                   // rows in flight per warp (one memory latency per 8 rows)
+  for (int r0 = warp * R; r0 < TILE; r0 += nwarps * R) {
+    float4 x[R];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < R; ++i) {
       int r = r0 + i;
       x[i] = (r < nvalid) ? ld4(src + (long long)r * row_stride + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < R; ++i) {
       int r = r0 + i;
       float4 y = warp_layernorm128(x[i], g, be);
       if (r >= nvalid) y = make_float4(0.f, 0.f, 0.f, 0.f);

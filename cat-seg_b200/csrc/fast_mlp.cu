@@ -29,7 +29,7 @@ constexpr uint32_t MLP_SMEM = SM_BAR + 8 * 8 + 16;
 static_assert(STG_BYTES <= 3 * TILE_BYTES_T, "the fp32 staging tile aliases the LN tiles + hidden chunk");
 }  // namespace
 
-#define PH(i) do { if (dbg != nullptr && blockIdx.x == 0 && tid == 0) { long long _t = clock64(); dbg[i] += _t - t_last; t_last = _t; } } while (0)
+#define PH(i) do { if (dbg != nullptr && blockIdx.x == 0 && tid == 0) { long long _t = clock64(); pacc##i += _t - t_last; t_last = _t; } } while (0)
 
 template <int ACT>   // 0 = GELU (Swin), 1 = ReLU (class layer)
 __global__ void __launch_bounds__(MLP_THREADS, 1)
@@ -87,10 +87,20 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w, long long* __
   float* stage = reinterpret_cast<float*>(smem + SM_XN); // fp32 staging tile (LN tiles + h are dead by then)
   const uint32_t lane_addr = tm + ((uint32_t)(q * 32) << 16);
   long long g = 0;                                       // running hidden-chunk counter of this CTA
-  long long t_last = clock64(), t_issue1 = 0;
+  long long t_last = clock64(), t_issue1 = 0, t_wait0 = 0;
+  long long pacc0 = 0, pacc1 = 0, pacc2 = 0, pacc3 = 0, pacc4 = 0, pacc5 = 0, pacc6 = 0, pacc7 = 0, pacc8 = 0, pacc9 = 0, pacc10 = 0, pacc11 = 0, npass_dbg = 0;
 
   for (long long p = blockIdx.x; p < npass; p += gridDim.x) {
     const long long row0 = p * 256;
+    {   // the NEXT pass's 256 rows (128 KiB) are prefetched into L2 while this pass computes
+      const long long nrow0 = (p + gridDim.x) * 256;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        long long line = (long long)tid + i * MLP_THREADS;          // 1024 lines of 128 bytes
+        long long r = nrow0 + (line >> 2);
+        if (r < ntok) umma::prefetch_l2(X + r * 128 + (line & 3) * 32);
+      }
+    }
     // ---- LN prologue: two tiles
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
@@ -111,7 +121,7 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w, long long* __
         const long long n = 2 * g;
         long long tw0 = clock64();
         umma::mbar_wait(&bar_full[n % 3], (uint32_t)((n / 3) & 1));
-        if (dbg != nullptr && blockIdx.x == 0 && tid == 0) dbg[6] += clock64() - tw0;
+        if (dbg != nullptr && blockIdx.x == 0 && tid == 0) pacc6 += clock64() - tw0;
         t_issue1 = clock64();
         const uint64_t wd = d_w0 + (uint64_t)((uint32_t)(n % 3) * (WIMG_BYTES >> 4));
         if (umma::elect_one()) {
@@ -121,12 +131,13 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w, long long* __
           umma::mma_commit(&bar_mma[1]);
         }
         __syncwarp();
+        if (dbg != nullptr && blockIdx.x == 0 && tid == 0) { long long _t = clock64(); pacc10 += _t - t_issue1; t_wait0 = _t; }
       }
 #pragma unroll 1
       for (int t = 0; t < 2; ++t) {
         umma::mbar_wait(&bar_mma[t], par);                 // H_t ready
         umma::fence_after_sync();
-        if (dbg != nullptr && blockIdx.x == 0 && tid == 0) dbg[8 + t] += clock64() - t_issue1;
+        if (dbg != nullptr && blockIdx.x == 0 && tid == 0) { if (t == 0) { pacc8 += clock64() - t_issue1; pacc11 += clock64() - t_wait0; } else pacc9 += clock64() - t_issue1; }
         PH(1);
         if (t == 1 && issuer) {                            // MMA1(b) done: the W1_j slot is free
           if (umma::elect_one()) issue_load(2 * g + 3);
@@ -174,7 +185,7 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w, long long* __
           const long long n = 2 * g + 1;
           long long tw0 = clock64();
           umma::mbar_wait(&bar_full[n % 3], (uint32_t)((n / 3) & 1));
-          if (dbg != nullptr && blockIdx.x == 0 && tid == 0) dbg[7] += clock64() - tw0;
+          if (dbg != nullptr && blockIdx.x == 0 && tid == 0) pacc7 += clock64() - tw0;
           const uint64_t wd = d_w0 + (uint64_t)((uint32_t)(n % 3) * (WIMG_BYTES >> 4));
           if (umma::elect_one()) {
             issue_gemm_k128_desc(tm + 256 + t * 128, d_h, LBO_T, wd, LBO_W, IDESC_128x128, j > 0);
@@ -184,6 +195,15 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w, long long* __
         }
       }
     }
+    // ---- residual rows of both tiles are fetched (coalesced, 16 loads in flight) BEFORE waiting for the last MMAs
+    float4 xres[2][8];
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        long long r = row0 + t * 128 + warp * 8 + i;
+        xres[t][i] = r < ntok ? ld4(X + r * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     // ---- all MMAs of this pass done -> Y epilogue
     umma::mbar_wait(&bar_mma[3], (uint32_t)((g - 1) & 1));
     umma::fence_after_sync();
@@ -192,9 +212,8 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w, long long* __
       if (umma::elect_one()) issue_load(2 * g + 2);
       __syncwarp();
     }
-    // Y_t + b2 -> fp32 staging tile (thread = row), then X[row] += stage[row] with warp-per-row coalesced
-    // 512-byte accesses (a per-thread-row global read-modify-write serialises on memory latency).
-#pragma unroll 1
+    // Y_t + b2 -> fp32 staging tile (thread = row), then X[row] = x + stage[row] with warp-per-row coalesced stores
+#pragma unroll
     for (int t = 0; t < 2; ++t) {
       {
         float v[32];
@@ -205,19 +224,10 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w, long long* __
         for (int i = 0; i < 32; i += 4) st4(sp + i, make_float4(v[i] + bb[i], v[i + 1] + bb[i + 1], v[i + 2] + bb[i + 2], v[i + 3] + bb[i + 3]));
       }
       __syncthreads();
-      {
-        const long long rbase = row0 + t * 128;
-        float4 xv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          long long r = rbase + warp * 8 + i;
-          xv[i] = r < ntok ? ld4(X + r * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          long long r = rbase + warp * 8 + i;
-          if (r < ntok) st4(X + r * 128 + lane * 4, f4add(xv[i], ld4(stage + (warp * 8 + i) * STG_LD + lane * 4)));
-        }
+      for (int i = 0; i < 8; ++i) {
+        long long r = row0 + t * 128 + warp * 8 + i;
+        if (r < ntok) st4(X + r * 128 + lane * 4, f4add(xres[t][i], ld4(stage + (warp * 8 + i) * STG_LD + lane * 4)));
       }
       __syncthreads();
     }
@@ -225,7 +235,11 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w, long long* __
     __syncthreads();          // TMEM and the LN tiles may be overwritten by the next pass
     umma::fence_after_sync();
     PH(5);
-    if (dbg != nullptr && blockIdx.x == 0 && tid == 0) dbg[15] += 1;
+    ++npass_dbg;
+  }
+  if (dbg != nullptr && blockIdx.x == 0 && tid == 0) {
+    dbg[0] = pacc0; dbg[1] = pacc1; dbg[2] = pacc2; dbg[3] = pacc3; dbg[4] = pacc4; dbg[5] = pacc5; dbg[6] = pacc6; dbg[7] = pacc7;
+    dbg[8] = pacc8; dbg[9] = pacc9; dbg[10] = pacc10; dbg[11] = pacc11; dbg[12] = 0; dbg[13] = 0; dbg[15] = npass_dbg;
   }
   if (warp == 0) umma::tmem_dealloc<512>(tm);
 }
@@ -258,8 +272,8 @@ cudaError_t launch_mlp_fast(float* X, long long ntok, const MlpFastW& w, int act
     cudaMemset(dbg, 0, 16 * sizeof(long long));
     double n = hb[15] > 0 ? (double)hb[15] : 1.0;
     fprintf(stderr, "[mlp phases, cycles/pass(256 tok) over %lld passes] LN %.0f | per (chunk,tile) x8: wait-H %.0f act %.0f h-free+STS+sync %.0f "
-            "| wait-last %.0f Y-epi %.0f | thread0 weight waits per pass: W1 %.0f W2 %.0f | MMA1 issue->H_a ready %.0f, ->H_b ready %.0f (per chunk)\n", hb[15], hb[0] / n, hb[1] / n / 8, hb[2] / n / 8,
-            hb[3] / n / 8, hb[4] / n, hb[5] / n, hb[6] / n, hb[7] / n, hb[8] / n / 4, hb[9] / n / 4);
+            "| wait-last %.0f Y-epi %.0f | thread0 weight waits per pass: W1 %.0f W2 %.0f | MMA1 issue->H_a ready %.0f, ->H_b ready %.0f; issuing 16 MMAs took %.0f, then waited %.0f for H_a (per chunk); isolated GEMM latency: first (after queued MMA2) %.0f, second %.0f\n", hb[15], hb[0] / n, hb[1] / n / 8, hb[2] / n / 8,
+            hb[3] / n / 8, hb[4] / n, hb[5] / n, hb[6] / n, hb[7] / n, hb[8] / n / 4, hb[9] / n / 4, hb[10] / n / 4, hb[11] / n / 4, hb[12] / n / 4, hb[13] / n / 4);
   }
   return cudaGetLastError();
 }

@@ -47,7 +47,7 @@ static_assert(SA_SMEM <= 232448, "shared memory budget");
 }  // namespace
 
 // Optional phase timing (CATSEG_PHASE_TIMING=1): thread 0 of CTA 0 accumulates clock64() deltas per phase.
-#define PH(i) do { if (dbg != nullptr && blockIdx.x == 0 && tid == 0) { long long _t = clock64(); dbg[i] += _t - t_last; t_last = _t; } } while (0)
+#define PH(i) do { if (dbg != nullptr && blockIdx.x == 0 && tid == 0) { long long _t = clock64(); pacc##i += _t - t_last; t_last = _t; } } while (0)
 
 __global__ void __launch_bounds__(SA_THREADS, 1)
 swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, int nwin_total, int Te, int shift,
@@ -107,6 +107,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
   }
 
   long long t_last = clock64();
+  long long pacc0 = 0, pacc1 = 0, pacc2 = 0, pacc3 = 0, pacc4 = 0, pacc5 = 0, pacc6 = 0, pacc7 = 0, pacc8 = 0, nwin_dbg = 0;
   long long nload = 0;          // index of the next weight image to be consumed by this CTA
   uint32_t ph_a = 0, ph_s = 0, ph_o = 0, ph_y = 0;
   const float scale = 0.17677669529663688110f;
@@ -381,7 +382,11 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
     __syncthreads();
     umma::fence_after_sync();
     PH(8);
-    if (dbg != nullptr && blockIdx.x == 0 && tid == 0) dbg[15] += 1;
+    ++nwin_dbg;
+  }
+  if (dbg != nullptr && blockIdx.x == 0 && tid == 0) {
+    dbg[0] = pacc0; dbg[1] = pacc1; dbg[2] = pacc2; dbg[3] = pacc3; dbg[4] = pacc4; dbg[5] = pacc5; dbg[6] = pacc6; dbg[7] = pacc7;
+    dbg[8] = pacc8; dbg[15] = nwin_dbg;
   }
   if (warp == 0) umma::tmem_dealloc<512>(tm);
 }

@@ -128,15 +128,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(bar)) : "memory");
 }
+// Waiting on an mbarrier phase.  `try_wait` may suspend the warp up to a system time limit; measured with the
+// phase-timing hook, waiters of a tcgen05.commit / TMA completion were only resumed ~1.8 K cycles after the
+// phase had completed, so the kernels poll with the non-suspending `test_wait` instead (the polling warps have
+// nothing else to do, and polling does not slow the tensor pipe: tools/probes/umma_probe.cu, test 24).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}\n"
-      :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
 }
 
 // ---- 1-D bulk copy global -> shared (TMA engine, no tensor map), completion on an mbarrier

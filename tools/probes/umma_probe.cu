@@ -128,10 +128,57 @@ __global__ void tc_throughput(float* out, int iters, long long* cycles, int N, i
   if (t < 32) tmem_dealloc<512>(tm);
 }
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
-  return pred != 0;
+// Contention probe: thread 0 issues a long MMA chain (M128 N128) while the other warps generate (mode bit 0) TMEM loads
+// from other columns, (bit 1) shared-memory store+load traffic, (bit 2) global loads.  Reports cycles per MMA.
+__global__ void contention(float* out, const float* gsrc, int nmma, long long* cycles, int mode, int random_data = 0) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  __shared__ volatile int done;
+  int t = threadIdx.x, warp = t >> 5;
+  for (int i = t; i < 30000; i += blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u; h ^= h >> 13; h *= 0x5bd1e995u; h ^= h >> 15;
+    // random bf16 pairs in [-2, 2): sign/mantissa random, exponent in {0x3e..0x3f}
+    uint32_t rnd = (h & 0x807f807fu) | 0x3f003f00u | ((h >> 3) & 0x00800080u);
+    reinterpret_cast<uint32_t*>(smem)[i] = random_data ? rnd : 0x3c003c00u;
+  }
+  if (t == 0) { mbar_init(&bar, 1); mbar_fence_init(); done = 0; }
+  if (t < 32) tmem_alloc<512>(&tmem_base);
+  fence_proxy_async(); fence_before_sync(); __syncthreads(); fence_after_sync();
+  uint32_t tm = tmem_base;
+  const uint32_t idesc = make_idesc_bf16(128, 128);
+  const uint64_t da0 = make_smem_desc(smem_u32(smem), 2064, 128), db0 = make_smem_desc(smem_u32(smem + 40000), 2048, 128);
+  long long t0 = clock64();
+  float acc = 0.f;
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int g = 0; g < nmma / 8; ++g) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mma_bf16_ss(tm + (g & 1) * 128, da0 + (uint64_t)(k * 2 * 129), db0 + (uint64_t)(k * 2 * 128), idesc, 1);
+      }
+      mma_commit(&bar);
+    }
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    if (t == 0) done = 1;
+  } else {
+    const uint32_t lane_addr = tm + ((uint32_t)((warp & 3) * 32) << 16) + 256;
+    float* sp = reinterpret_cast<float*>(smem + 120000) + t * 4;
+    while (!done) {
+      if (mode & 1) { float v[32]; tmem_ld32(lane_addr + ((warp >> 2) & 3) * 32, v); acc += v[0] + v[31]; }
+      if (mode & 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { *reinterpret_cast<float4*>(sp + i * 2048) = make_float4(acc, acc, acc, acc); acc += sp[i * 2048 + 1]; }
+      }
+      if (mode & 4) { acc += __ldg(gsrc + ((t * 32 + (int)acc) & 0xfffff)); }
+    }
+  }
+  long long t1 = clock64();
+  fence_after_sync();
+  if (t == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+  if (acc == 12345.f) out[t] = acc;
+  fence_before_sync(); __syncthreads();
+  if (t < 32) tmem_dealloc<512>(tm);
 }
 
 // Issue-cost probe: GEMMs of 8 MMAs (N=128) with k-dependent descriptors + a commit per GEMM, issued either by
@@ -238,7 +285,23 @@ int main(int argc, char** argv) {
     float* out; long long* cyc; CHECK(cudaMalloc(&out, 4096)); CHECK(cudaMalloc(&cyc, 8));
     int iters = 20000;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    if (id == 23) {
+    if (id == 24) {
+      size_t smem = 200000;
+      CHECK(cudaFuncSetAttribute(contention, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      float* gsrc; CHECK(cudaMalloc(&gsrc, 4 << 20)); CHECK(cudaMemset(gsrc, 0, 4 << 20));
+      long long* cyc2; CHECK(cudaMalloc(&cyc2, 16));
+      const char* names[] = {"idle warps", "TMEM loads", "SMEM st/ld", "TMEM+SMEM", "global loads", "TMEM+global", "SMEM+global", "all"};
+      for (int mode = 0; mode < 8; ++mode) {
+        contention<<<prop.multiProcessorCount, 512, smem>>>(out, gsrc, 16000, cyc2, mode); CHECK(cudaDeviceSynchronize());
+        long long c; CHECK(cudaMemcpy(&c, cyc2, 8, cudaMemcpyDeviceToHost));
+        printf("PROBE contention, 15 other warps doing %-14s: %.1f cycles per MMA (M128 N128 K16)\n", names[mode], (double)c / 16000.0);
+      }
+      for (int rep = 0; rep < 2; ++rep) {
+        contention<<<prop.multiProcessorCount, 512, smem>>>(out, gsrc, 64000, cyc2, 0, 1); CHECK(cudaDeviceSynchronize());
+        long long c; CHECK(cudaMemcpy(&c, cyc2, 8, cudaMemcpyDeviceToHost));
+        printf("PROBE random bf16 operands (idle warps): %.1f cycles per MMA (M128 N128 K16)\n", (double)c / 64000.0);
+      }
+    } else if (id == 23) {
       size_t smem = 100000;
       CHECK(cudaFuncSetAttribute(issue_cost, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       long long* cyc2; CHECK(cudaMalloc(&cyc2, 16));
