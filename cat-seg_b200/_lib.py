@@ -37,7 +37,7 @@ class CatsegTaps(C.Structure):
 
 
 STAGES = ("prep", "embed", "swin", "class", "decoder", "swin_mlp")
-FAST_BITS = {"swin_mlp": 1, "swin_attn": 2, "class": 4, "decoder": 8}
+FAST_BITS = {"swin_mlp": 1, "swin_attn": 2, "class": 4, "decoder": 8, "prep": 16}
 
 
 def precision_mask(spec: str) -> int:

@@ -24,7 +24,7 @@ struct Param {
 
 thread_local std::string g_create_error;
 
-constexpr int kImplementedFast = CATSEG_FAST_SWIN_MLP | CATSEG_FAST_SWIN_ATTN | CATSEG_FAST_DECODER | CATSEG_FAST_CLASS;   // stages that have a tcgen05 kernel in this build
+constexpr int kImplementedFast = CATSEG_FAST_SWIN_MLP | CATSEG_FAST_SWIN_ATTN | CATSEG_FAST_DECODER | CATSEG_FAST_CLASS | CATSEG_FAST_PREP;   // stages that have a tcgen05 kernel in this build
 constexpr int kMaxProfForwards = 64;
 constexpr int kMaxSegments = 40;
 
@@ -47,6 +47,8 @@ struct catseg_handle {
   void* dec_fast_store = nullptr;
   DecoderFastW dec_fast{};
   float head_bias_host = 0.0f;
+  __nv_bfloat16* prep_img = nullptr;            // FAST_PREP: embedding images, then the three guidance-conv image sets
+  const __nv_bfloat16 *embed_img = nullptr, *gconv_img[3] = {nullptr, nullptr, nullptr};   // nullptr: shape not covered -> fp32 kernel
   bool finalized = false;
   std::string err;
   int device = 0;
@@ -213,6 +215,7 @@ extern "C" int catseg_destroy(catseg_handle* h) {
   if (h->packed) cudaFree(h->packed);
   if (h->wimg) cudaFree(h->wimg);
   if (h->dec_fast_store) cudaFree(h->dec_fast_store);
+  if (h->prep_img) cudaFree(h->prep_img);
   delete h;
   return CATSEG_OK;
 }
@@ -533,6 +536,28 @@ extern "C" int catseg_finalize_params(catseg_handle* h, catseg_stream stream) {
     if (e != cudaSuccess) return fail(h, CATSEG_ERR_CUDA, "decoder_fast_pack: %s", cudaGetErrorString(e));
     CUDA_OK(h, cudaMemcpyAsync(&h->head_bias_host, raw_of(h, "head.bias"), sizeof(float), cudaMemcpyDeviceToHost, st));
   }
+  if (h->fast_mask & CATSEG_FAST_PREP) {
+    const catseg_config& c = h->cfg;
+    const int H = c.feature_resolution[0], W = c.feature_resolution[1];
+    const int ci[3] = {c.appearance_guidance_dim, c.decoder_guidance_dims[0], c.decoder_guidance_dims[1]};
+    const int co[3] = {c.appearance_guidance_proj_dim, c.decoder_guidance_proj_dims[0], c.decoder_guidance_proj_dims[1]};
+    const float* wt[3] = {h->gproj_wt, h->dgp_wt[0], h->dgp_wt[1]};
+    size_t off[4] = {14 * 2048, 0, 0, 0}, total = 14 * 2048;
+    for (int i = 0; i < 3; ++i) { off[i] = total; total += (size_t)ci[i] * 9 * co[i]; }
+    if (!h->prep_img) CUDA_OK(h, cudaMalloc(&h->prep_img, total * sizeof(__nv_bfloat16)));
+    h->embed_img = nullptr;
+    if (H == 24 && W == 24 && c.prompt_channel == 1 && c.hidden_dim == 128) {
+      CUDA_OK(h, launch_pack_embed_img(h->prep_img, h->conv1_wt, st));
+      h->embed_img = h->prep_img;
+    }
+    for (int i = 0; i < 3; ++i) {
+      h->gconv_img[i] = nullptr;
+      if (ci[i] > 0 && co[i] > 0 && gconv_fast_supported(i, ci[i], H << i, W << i, co[i])) {
+        CUDA_OK(h, launch_pack_gconv_img(h->prep_img + off[i], wt[i], ci[i], co[i], gconv_fast_kc(i), st));
+        h->gconv_img[i] = h->prep_img + off[i];
+      }
+    }
+  }
   CUDA_OK(h, cudaStreamSynchronize(st));
   h->finalized = true;
   return CATSEG_OK;
@@ -691,17 +716,25 @@ extern "C" int catseg_forward_taps(catseg_handle* h, const float* img, const flo
   const bool class_fast = (h->fast_mask & CATSEG_FAST_CLASS) != 0;
   __nv_bfloat16* timg = reinterpret_cast<__nv_bfloat16*>(ws + p.timg);
   if (class_fast) RUN(launch_pack_text_img(ws + p.text_g, timg, B, p.Te, st));
-  RUN(launch_conv3x3_nchw(g0, h->gproj_wt, h->gproj_b, ws + p.app_g, B, p.Cg, p.H, p.W, 128, st));
+  const bool prep_fast = (h->fast_mask & CATSEG_FAST_PREP) != 0;
+  if (prep_fast && h->gconv_img[0]) RUN(launch_gconv_fast(0, g0, h->gconv_img[0], h->gproj_b, ws + p.app_g, B, p.Cg, st));
+  else RUN(launch_conv3x3_nchw(g0, h->gproj_wt, h->gproj_b, ws + p.app_g, B, p.Cg, p.H, p.W, 128, st));
   for (int l = 0; l < p.L; ++l) {
     RUN(launch_layernorm128(ws + p.app_g, ws + p.app_gn, h->gnorm_g[l], h->gnorm_b[l], (long long)B * p.HW, st));
     for (int k = 0; k < 2; ++k)
       RUN(launch_linear(ws + p.app_gn, h->swin[l * 2 + k].wg_qk_t, h->swin[l * 2 + k].bqk,
                         ws + p.ag_qk + (size_t)(l * 2 + k) * B * p.HW * 256, (long long)B * p.HW, 256, 128, 0, st));
   }
-  RUN(launch_conv3x3_nchw(g1, h->dgp_wt[0], h->dgp_b[0], ws + p.dg0, B, c.decoder_guidance_dims[0], 2 * p.H, 2 * p.W,
-                          p.dd.G1, st));
-  RUN(launch_conv3x3_nchw(g2, h->dgp_wt[1], h->dgp_b[1], ws + p.dg1, B, c.decoder_guidance_dims[1], 4 * p.H, 4 * p.W,
-                          p.dd.G2, st));
+  if (prep_fast && h->gconv_img[1])
+    RUN(launch_gconv_fast(1, g1, h->gconv_img[1], h->dgp_b[0], ws + p.dg0, B, c.decoder_guidance_dims[0], st));
+  else
+    RUN(launch_conv3x3_nchw(g1, h->dgp_wt[0], h->dgp_b[0], ws + p.dg0, B, c.decoder_guidance_dims[0], 2 * p.H, 2 * p.W,
+                            p.dd.G1, st));
+  if (prep_fast && h->gconv_img[2])
+    RUN(launch_gconv_fast(2, g2, h->gconv_img[2], h->dgp_b[1], ws + p.dg1, B, c.decoder_guidance_dims[1], st));
+  else
+    RUN(launch_conv3x3_nchw(g2, h->dgp_wt[1], h->dgp_b[1], ws + p.dg1, B, c.decoder_guidance_dims[1], 4 * p.H, 4 * p.W,
+                            p.dd.G2, st));
   seg.end();
   if (taps) {
     TAP(taps->corr, ws + p.corr, (size_t)B * T * p.P * p.HW);
@@ -714,7 +747,10 @@ extern "C" int catseg_forward_taps(catseg_handle* h, const float* img, const flo
 
   // ---------------- EMBED (model.py:704)
   seg.begin(CATSEG_STAGE_EMBED);
-  RUN(launch_cost_embed(ws + p.corr, classes, h->conv1_wt, h->conv1_b, X, B, T, p.Te, p.P, p.H, p.W, st));
+  if (prep_fast && h->embed_img)
+    RUN(launch_cost_embed_fast(ws + p.corr, classes, h->embed_img, h->conv1_b, X, B, T, p.Te, h->num_sms, st));
+  else
+    RUN(launch_cost_embed(ws + p.corr, classes, h->conv1_wt, h->conv1_b, X, B, T, p.Te, p.P, p.H, p.W, st));
   seg.end();
   TAP(taps->embed, X, (size_t)nslice * p.HW * 128);
 

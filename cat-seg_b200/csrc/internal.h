@@ -75,6 +75,18 @@ cudaError_t launch_transpose_pack(float* dst, int ldd, int dst_col0, const float
 cudaError_t launch_fill(float* p, float v, long long n, cudaStream_t st);
 cudaError_t launch_iota_classes(int32_t* classes, int B, int Te, cudaStream_t st);
 
+// ---------------------------------------------------------------- fast_prep.cu
+// 7x7 cost embedding for P = 1 on a 24x24 grid; bimg = 14 images packed by launch_pack_embed_img from Wt [49][128]
+cudaError_t launch_pack_embed_img(__nv_bfloat16* dst, const float* Wt, cudaStream_t st);
+cudaError_t launch_cost_embed_fast(const float* corr, const int32_t* classes, const __nv_bfloat16* bimg, const float* bias,
+                                   float* X, int B, int T, int Te, int num_sms, cudaStream_t st);
+// 3x3 guidance projections: which = 0 (24^2 -> 128), 1 (48^2 -> 32), 2 (96^2 -> 16); NCHW fp32 in, NHWC fp32 out
+int gconv_fast_kc(int which);
+bool gconv_fast_supported(int which, int Ci, int H, int W, int Co);
+cudaError_t launch_pack_gconv_img(__nv_bfloat16* dst, const float* Wt, int Ci, int Co, int KC, cudaStream_t st);
+cudaError_t launch_gconv_fast(int which, const float* in, const __nv_bfloat16* wimg, const float* bias, float* out, int B,
+                              int Ci, cudaStream_t st);
+
 // ---------------------------------------------------------------- swin_exact.cu
 // with_mlp = 0 stops after x1 = shortcut + proj(attn) (the FFN half then runs in fast_mlp.cu)
 cudaError_t launch_swin_block_exact(float* X, const float* ag_qk, int nslice, int Te, int shift,

@@ -116,20 +116,46 @@ cudaError_t launch_stitch(const float* win_logits, int T, int S, int kernel, int
 }
 
 // labels[i] = argmax_t scores[t][i], first maximum wins (torch.argmax semantics on distinct values;
-// NaN is not expected on this path).
-__global__ void argmax_kernel(const float* __restrict__ scores, int T, long long npix, int32_t* __restrict__ labels) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npix) return;
-  float best = __ldg(scores + i);
-  int bt = 0;
-  for (int t = 1; t < T; ++t) {
-    float v = __ldg(scores + (long long)t * npix + i);
-    if (v > best) { best = v; bt = t; }
+// NaN is not expected on this path).  One CTA owns 32 pixels; its 8 warps split the class axis (t = w, w+8, ...),
+// 8 independent 128-byte loads in flight per warp, then a fixed-order merge (lower class index wins ties).
+__global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ scores, int T, long long npix,
+                                                     int32_t* __restrict__ labels) {
+  __shared__ float s_best[8][32];
+  __shared__ int s_bt[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + lane;
+  float best = -INFINITY;
+  int bt = 0x7fffffff;
+  if (i < npix) {
+    int t = w;
+    for (; t + 56 < T; t += 64) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(scores + (long long)(t + 8 * u) * npix + i);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (v[u] > best || bt == 0x7fffffff) { best = v[u]; bt = t + 8 * u; }
+    }
+    for (; t < T; t += 8) {
+      float v = __ldg(scores + (long long)t * npix + i);
+      if (v > best || bt == 0x7fffffff) { best = v; bt = t; }
+    }
   }
-  labels[i] = bt;
+  s_best[w][lane] = best;
+  s_bt[w][lane] = bt;
+  __syncthreads();
+  if (w == 0 && i < npix) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      float v = s_best[k][lane];
+      int t = s_bt[k][lane];
+      if (t != 0x7fffffff && (bt == 0x7fffffff || v > best || (v == best && t < bt))) { best = v; bt = t; }
+    }
+    labels[i] = bt == 0x7fffffff ? 0 : bt;
+  }
 }
 cudaError_t launch_argmax(const float* scores, int T, long long npix, int32_t* labels, cudaStream_t st) {
-  argmax_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(scores, T, npix, labels);
+  argmax_kernel<<<(unsigned)((npix + 31) / 32), 256, 0, st>>>(scores, T, npix, labels);
   return cudaGetLastError();
 }
 

@@ -43,6 +43,7 @@ extern "C" {
 #define CATSEG_FAST_SWIN_ATTN 2  /* window-attention half of the Swin blocks */
 #define CATSEG_FAST_CLASS 4      /* class-aggregation layers */
 #define CATSEG_FAST_DECODER 8    /* upsampling decoder */
+#define CATSEG_FAST_PREP 16      /* 7x7 cost embedding (fp32-accurate split) and the 3x3 guidance projections */
 #define CATSEG_PRECISION_FAST 0x7fffffff
 
 typedef struct catseg_handle catseg_handle;

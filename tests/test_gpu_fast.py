@@ -27,7 +27,7 @@ def _run(cfg, B, T, seed, precision, same_text=False):
     return y, ref
 
 
-@pytest.mark.parametrize("precision", ["fast:swin_mlp", "fast:swin_attn", "fast:class", "fast:decoder", "fast"])
+@pytest.mark.parametrize("precision", ["fast:swin_mlp", "fast:swin_attn", "fast:class", "fast:decoder", "fast:prep", "fast"])
 @pytest.mark.parametrize("case", [(vitb(), 2, 5), (vitb(pooling_size=(2, 2)), 1, 3), (vitb(pad_len=4), 1, 9)])
 def test_fast_matches_oracle_within_bf16_tolerance(precision, case):
     cfg, B, T = case
@@ -46,3 +46,24 @@ def test_fast_large_tile_counts():
     assert bool(((y == -100.0) == (ref == -100.0)).all())
     kept = ref != -100.0
     assert (y[kept] - ref[kept]).abs().max().item() <= FAST_MAXABS and rel_l2(y[kept], ref[kept]) <= FAST_RELL2
+
+
+@pytest.mark.parametrize("case", [(vitb(), 2, 5), (vitl(), 1, 7)])
+def test_fast_prep_stages(case):
+    """tcgen05 front end: the hi/lo-split 7x7 embedding is fp32-accurate; the bf16 guidance projections are
+    within bf16 operand rounding (rel-L2 <= 1e-2)."""
+    cfg, B, T = case
+    sd = make_state_dict(cfg, 8)
+    img, text, g = make_inputs(cfg, B, T, 8, same_text=False)
+    _, st = aggregator_forward(sd, cfg.oracle_cfg(), img, text, g, return_stages=True)
+    m = Aggregator(**cfg.ctor_kwargs(), precision="fast:prep")
+    m.load_state_dict(sd, strict=False)
+    names = ["embed", "app_guidance", "dec_guidance0", "dec_guidance1"]
+    _, taps = m.cuda()(img.cuda(), text.cuda(), [x.cuda() for x in g], taps=names)
+    emb, ref = taps["embed"].cpu(), st["embed"]
+    assert (emb - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item()), (emb - ref).abs().max().item()
+    for n in names[1:]:
+        got, r = taps[n].cpu(), st[n]
+        if n.startswith("dec_guidance"):
+            r = r.permute(0, 2, 3, 1).reshape(got.shape)            # oracle keeps NCHW, kernels NHWC
+        assert rel_l2(got, r) <= 1e-2, (n, rel_l2(got, r))

@@ -34,7 +34,7 @@ def main():
     sd = make_state_dict(cfg, a.seed)
     img, text, g = make_inputs(cfg, a.B, a.T, a.seed, same_text=False)
     ref, st = aggregator_forward(sd, cfg.oracle_cfg(), img, text, g, return_stages=True)
-    names = ["embed"] + [f"{k}{l}{s}" for l in range(cfg.num_layers) for k, s in
+    names = ["app_guidance", "dec_guidance0", "dec_guidance1", "embed"] + [f"{k}{l}{s}" for l in range(cfg.num_layers) for k, s in
                          (("swin_l", "_b1"), ("swin_l", "_b2"), ("class_l", ""))] + ["up1", "up2"]
     for prec in ["exact", a.precision]:
         if prec == "fast" or "decoder" in prec:
@@ -48,6 +48,8 @@ def main():
         print(f"== precision {prec}")
         for n in names:
             got = taps[n].cpu()
+            if n.startswith("dec_guidance"):
+                st[n] = st[n].permute(0, 2, 3, 1).reshape(got.shape) if st[n].shape != got.shape else st[n]
             print(f"  {n:12s} max-abs {float((got - st[n]).abs().max()):.3e}  rel-L2 {rel_l2(got, st[n]):.3e}  "
                   f"(ref rms {float(st[n].pow(2).mean().sqrt()):.3e})")
         yc = y.cpu()
