@@ -1,0 +1,47 @@
+"""Host-side feeding of the Aggregator: pinned host inputs are uploaded on a copy stream into one of ``depth``
+device slots while the previous batch computes (the data-loader prefetch every serving loop of the reference has
+through Detectron2's loader; here it is explicit because the boundary call takes device tensors).
+
+    pipe = HostPipeline(model, device)
+    t = pipe.upload(host_tensors)            # async H2D on the copy stream
+    y = pipe.run(t)                          # boundary call on the current stream once the upload has landed
+
+Nothing here computes: it orders two CUDA streams with events.
+"""
+from typing import List, Sequence
+
+import torch
+
+
+class HostPipeline:
+    def __init__(self, model, device, depth: int = 2):
+        self.model, self.device, self.depth = model, device, depth
+        self.copy_stream = torch.cuda.Stream(device)
+        self.slots: List = [None] * depth
+        self.uploaded = [torch.cuda.Event() for _ in range(depth)]
+        self.consumed = [None] * depth
+        self.n = 0
+
+    def upload(self, host: Sequence[torch.Tensor]) -> int:
+        """host = (img_feats, text_feats, guidance_1, guidance_2) pinned CPU tensors.  Returns a ticket."""
+        s = self.n % self.depth
+        self.n += 1
+        if self.slots[s] is None:
+            self.slots[s] = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host]
+        with torch.cuda.stream(self.copy_stream):
+            if self.consumed[s] is not None:
+                self.copy_stream.wait_event(self.consumed[s])      # the batch that used this slot has finished
+            for d, h in zip(self.slots[s], host):
+                d.copy_(h, non_blocking=True)
+            self.uploaded[s].record(self.copy_stream)
+        return s
+
+    def run(self, ticket: int) -> torch.Tensor:
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self.uploaded[ticket])
+        a, b, c, d = self.slots[ticket]
+        y = self.model(a, b, [a, c, d])
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.consumed[ticket] = ev
+        return y
