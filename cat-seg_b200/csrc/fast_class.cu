@@ -51,7 +51,9 @@ static_assert(ST_SMEM <= 232448 && AP_SMEM <= 232448, "shared memory budget");
 }  // namespace
 
 // ================================================================================================
-__global__ void __launch_bounds__(256, 1)
+// 16 warps: TMEM lane quarter q4 = warp & 3; group grp = warp >> 2: groups 0,1 take the two 64-column halves of k,
+// groups 2,3 those of v.
+__global__ void __launch_bounds__(512, 1)
 class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __restrict__ timg, float* __restrict__ state,
                         int B, int Te, int npix, int S, ClassFastW w) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -64,7 +66,8 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
   uint64_t* bar_m1 = bar_w + 2;
   uint64_t* bar_m2 = bar_w + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 4);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q4 = warp & 3, half = warp >> 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q4 = warp & 3, grp = warp >> 2;
+  const int half = grp >> 1, chalf = grp & 1;
   const bool issuer = __shfl_sync(0xffffffffu, warp, 0) == 0;   // warp-uniform issue region, one elected lane
   const int row = q4 * 32 + lane;
   const int ntile = (Te + 127) / 128;
@@ -92,6 +95,14 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
   const long long nitems = (long long)B * npix;
   for (long long it = blockIdx.x; it < nitems; it += gridDim.x) {
     const int b = (int)(it / npix), pix = (int)(it % npix);
+    {   // the next item's token rows (Te rows of 512 bytes, one per class) are prefetched into L2 meanwhile
+      const long long itn = it + gridDim.x;
+      if (itn < nitems) {
+        const int bn = (int)(itn / npix), pn = (int)(itn % npix);
+        for (int i = tid; i < Te * 4; i += 512)
+          umma::prefetch_l2(X + (((long long)bn * Te + (i >> 2)) * npix + pn) * 128 + (i & 3) * 32);
+      }
+    }
     for (int tl = 0; tl < ntile; ++tl) {
       const int t0 = tl * 128;
       const int nvalid = Te - t0 < 128 ? Te - t0 : 128;
@@ -104,7 +115,7 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
         __syncwarp();
       }
       ln_rows_to_tile(X + (((long long)b * Te + t0) * npix + pix) * 128, (long long)npix * 128, nvalid, smem + ST_XN, s_g,
-                      s_be, warp, 8, lane);
+                      s_be, warp, 16, lane);
       umma::fence_proxy_async();
       umma::fence_before_sync();
       __syncthreads();
@@ -124,12 +135,12 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
       ph_g ^= 1;
       umma::mbar_wait(bar_m1, ph_m1); ph_m1 ^= 1;
       umma::fence_after_sync();
-      // ---- epilogue: warps 0-3 -> phi(k) image (over the LN tile), warps 4-7 -> [v/S | 1] image (over the g tile)
+      // ---- epilogue: groups 0,1 -> phi(k) image (over the LN tile), groups 2,3 -> [v/S | 1] image (over the g tile)
       {
         const bool live = row < nvalid;
         uint8_t* img = smem + (half == 0 ? ST_XN : ST_G);
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int cc = chalf * 2; cc < chalf * 2 + 2; ++cc) {
           float v[32];
           umma::tmem_ld32(lane_addr + ST_TM_KV + half * 128 + cc * 32, v);
           const float* bb = (half == 0 ? s_bk : s_bv) + cc * 32;
@@ -145,7 +156,7 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
                 make_uint4(umma::pack_bf16x2(v[c * 8], v[c * 8 + 1]), umma::pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
                            umma::pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), umma::pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]));
         }
-        if (half == 1) {   // ones column (n = 128) and zero padding (n = 129..143)
+        if (grp == 2) {    // ones column (n = 128) and zero padding (n = 129..143)
           *reinterpret_cast<uint4*>(smem + ST_G + 16 * LBO_V + row * 16) = make_uint4(live ? 0x00003F80u : 0u, 0u, 0u, 0u);
           *reinterpret_cast<uint4*>(smem + ST_G + 17 * LBO_V + row * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
@@ -167,16 +178,19 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
       umma::mbar_wait(bar_m2, ph_m2); ph_m2 ^= 1;
       umma::fence_after_sync();
     }
-    // ---- state[b][pix]: thread = k-feature (h, d): KV[h][d][0..31] and Ksum[h*32+d]
-    if (half == 0) {
+    // ---- state[b][pix]: thread = k-feature (h, d) x 8 of the 32 columns KV[h][d][grp*8..+8]; group 0 also Ksum[h*32+d]
+    {
       const int h = row >> 5;
-      float v[32], ks[8];
-      umma::tmem_ld32(lane_addr + ST_TM_ACC + h * 32, v);
-      umma::tmem_ld8(lane_addr + ST_TM_ACC + 128, ks);
+      float v[8];
+      umma::tmem_ld8(lane_addr + ST_TM_ACC + h * 32 + grp * 8, v);
       float* o = state + it * kStateFloats;
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) st4(o + row * 32 + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
-      o[4096 + row] = ks[0];
+      st4(o + row * 32 + grp * 8, make_float4(v[0], v[1], v[2], v[3]));
+      st4(o + row * 32 + grp * 8 + 4, make_float4(v[4], v[5], v[6], v[7]));
+      if (grp == 0) {
+        float ks[8];
+        umma::tmem_ld8(lane_addr + ST_TM_ACC + 128, ks);
+        o[4096 + row] = ks[0];
+      }
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -492,7 +506,7 @@ cudaError_t launch_class_state_fast(const float* X, const __nv_bfloat16* timg, f
   }
   long long n = (long long)B * npix;
   int grid = (int)(n < num_sms ? n : num_sms);
-  class_state_fast_kernel<<<grid, 256, ST_SMEM, st>>>(X, timg, state, B, Te, npix, S, w);
+  class_state_fast_kernel<<<grid, 512, ST_SMEM, st>>>(X, timg, state, B, Te, npix, S, w);
   return cudaGetLastError();
 }
 
