@@ -233,6 +233,57 @@ __global__ void issue_cost(float* out, int ngemm, long long* cycles, int mode, i
   if (t < 32) tmem_dealloc<512>(tm);
 }
 
+
+// Commit-latency probe: thread 0 issues NG GEMMs (8 MMAs, N=128), each with its own commit barrier, then every thread
+// polls the barriers in order; thread 0 records when each flip becomes visible.  mode 0: other warps only poll;
+// mode 1: the other warps first run an ALU-bound loop (like an activation epilogue); mode 2: they stream STS.128.
+__global__ void commit_latency(float* out, long long* cycles, int mode, int ng) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bars[8];
+  __shared__ uint32_t tmem_base;
+  int t = threadIdx.x;
+  for (int i = t; i < 40000; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (t == 0) { for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1); mbar_fence_init(); }
+  if (t < 32) tmem_alloc<512>(&tmem_base);
+  fence_proxy_async(); fence_before_sync(); __syncthreads(); fence_after_sync();
+  uint32_t tm = tmem_base;
+  const uint32_t idesc = make_idesc_bf16(128, 128);
+  const uint64_t da0 = make_smem_desc(smem_u32(smem), 2064, 128), db0 = make_smem_desc(smem_u32(smem + 40000), 2048, 128);
+  const int warp_u = __shfl_sync(0xffffffffu, t >> 5, 0);
+  long long t0 = clock64(), tissue = 0;
+  if (warp_u == 0) {
+    if (elect_one()) {
+      for (int g = 0; g < ng; ++g) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mma_bf16_ss(tm + (g & 3) * 128, da0 + (uint64_t)(k * 2 * 129), db0 + (uint64_t)(k * 2 * 128), idesc, k > 0);
+        mma_commit(&bars[g]);
+      }
+    }
+    __syncwarp();
+    tissue = clock64();
+  } else if (mode == 1) {
+    float a[8];
+    for (int i = 0; i < 8; ++i) a[i] = (float)(t + i);
+    for (int it = 0; it < 400; ++it)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fmaf(a[i], 1.0001f, 0.5f);
+    float sacc = 0.f; for (int i = 0; i < 8; ++i) sacc += a[i];
+    if (sacc == 12345.f) out[t] = sacc;
+  } else if (mode == 2) {
+    uint4* dst = reinterpret_cast<uint4*>(smem + 90000);
+    for (int it = 0; it < 200; ++it) dst[(t + it * 32) & 4095] = make_uint4(t, it, 0, 0);
+  }
+  long long tb[8];
+  for (int g = 0; g < ng; ++g) { mbar_wait(&bars[g], 0); tb[g] = clock64(); }
+  fence_after_sync();
+  if (t == 0 && blockIdx.x == 0) cycles[0] = tissue - t0;
+  if (t == 32 && blockIdx.x == 0) for (int g = 0; g < ng; ++g) cycles[1 + g] = tb[g] - t0;   // observed by a warp that does not issue
+  float v[16];
+  if (t < 128) { tmem_ld16(tm + ((uint32_t)((t >> 5) * 32) << 16), v); if (v[0] == 12345.f) out[t] = v[0]; }
+  fence_before_sync(); __syncthreads();
+  if (t < 32) tmem_dealloc<512>(tm);
+}
+
 __global__ void mmasync_throughput(float* out, int iters, long long* cycles) {
   float c[8][4];
   for (int i = 0; i < 8; ++i) for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
@@ -285,7 +336,22 @@ int main(int argc, char** argv) {
     float* out; long long* cyc; CHECK(cudaMalloc(&out, 4096)); CHECK(cudaMalloc(&cyc, 8));
     int iters = 20000;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    if (id == 24) {
+    if (id == 25) {
+      size_t smem = 160000;
+      CHECK(cudaFuncSetAttribute(commit_latency, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      long long* cyc2; CHECK(cudaMalloc(&cyc2, 128));
+      const char* names[] = {"poll only", "ALU loop", "STS stream"};
+      for (int ng = 2; ng <= 4; ng += 2)
+        for (int mode = 0; mode < 3; ++mode)
+          for (int nt = 128; nt <= 512; nt += 384) {
+            commit_latency<<<prop.multiProcessorCount, nt, smem>>>(out, cyc2, mode, ng); CHECK(cudaDeviceSynchronize());
+            commit_latency<<<prop.multiProcessorCount, nt, smem>>>(out, cyc2, mode, ng); CHECK(cudaDeviceSynchronize());
+            long long c[9]; CHECK(cudaMemcpy(c, cyc2, 72, cudaMemcpyDeviceToHost));
+            printf("PROBE commit latency, %d GEMMs x 8 MMAs, %3d threads, others %-10s: issue done %lld |", ng, nt, names[mode], c[0]);
+            for (int g = 0; g < ng; ++g) printf(" bar%d %lld", g, c[1 + g]);
+            printf(" cycles\n");
+          }
+    } else if (id == 24) {
       size_t smem = 200000;
       CHECK(cudaFuncSetAttribute(contention, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       float* gsrc; CHECK(cudaMalloc(&gsrc, 4 << 20)); CHECK(cudaMemset(gsrc, 0, 4 << 20));
