@@ -35,9 +35,10 @@ constexpr uint32_t SM_KH = SM_QH + 9216;
 constexpr uint32_t SM_VH = SM_KH + 9216;
 constexpr uint32_t SM_P = SM_VH + 9216;                    // P: [rows x 144 keys] K-major, 18 chunks
 constexpr uint32_t SM_O = SM_P + 18 * LBO_X;               // O: [144 tok x 128] K-major, 16 chunks
-constexpr uint32_t SM_MISC = SM_O + 16 * LBO_X;
-// misc: tokpix[144] tokreg[144] (int) | red[2][2][144] (float) | ln g,b [256] | bv[128] | bproj[128]
-constexpr uint32_t SM_BAR = SM_MISC + (144 * 2 + 2 * 4 * 144 + 256 + 128 + 128) * 4;
+constexpr uint32_t SM_Q1 = SM_O + 16 * LBO_X;              // queries 128..143 replicated into all four TMEM lane quarters: 16 groups x 512 B
+constexpr uint32_t SM_MISC = SM_Q1 + 16 * 512;
+// misc: tokpix[144] tokreg[144] (int) | red[2][4][144] (float) | red1[2][16][16] | ln g,b [256] | bv[128] | bproj[128]
+constexpr uint32_t SM_BAR = SM_MISC + (144 * 2 + 2 * 4 * 144 + 2 * 256 + 256 + 128 + 128) * 4;
 constexpr uint32_t SA_SMEM = SM_BAR + 8 * 8 + 16;
 constexpr uint32_t TM_QKV = 0, TM_S0 = 160, TM_S1 = 304, TM_O0 = 448, TM_O1 = 480;
 constexpr uint32_t IDESC_T = umma::make_idesc_bf16(128, 144, 0, 0);     // QKV^T, proj^T
@@ -57,7 +58,9 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
   int* tokreg = tokpix + 144;
   float* red = reinterpret_cast<float*>(tokreg + 144);        // row max per key quarter [4][144]
   float* rsum = red + 4 * 144;                                 // row sum per key quarter [4][144]
-  float* s_g = rsum + 4 * 144;
+  float* max1 = rsum + 4 * 144;                                // tile 1 (queries 128..143): row max per 9-key part [16][16]
+  float* sum1 = max1 + 256;                                    //                            row sum per part     [16][16]
+  float* s_g = sum1 + 256;
   float* s_be = s_g + 128;
   float* s_bv = s_be + 128;
   float* s_bp = s_bv + 128;
@@ -92,6 +95,8 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
   const uint64_t d_qh = umma::make_smem_desc(sb + SM_QH, 128, 512), d_kh = umma::make_smem_desc(sb + SM_KH, 128, 512);
   const uint64_t d_p = umma::make_smem_desc(sb + SM_P, LBO_X, 128), d_vh = umma::make_smem_desc(sb + SM_VH, 512, 128);
   const uint64_t d_ring = umma::make_smem_desc(sb + SM_RING, LBO_W, 128);
+  const uint64_t d_q1 = umma::make_smem_desc(sb + SM_Q1, 128, 512);
+  for (int i = tid; i < 16 * 512 / 16; i += SA_THREADS) reinterpret_cast<uint4*>(smem + SM_Q1)[i] = make_uint4(0u, 0u, 0u, 0u);
 
   auto issue_load = [&](long long n) {      // thread 0 only
     if (n < total_loads) {
@@ -217,9 +222,13 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
               for (int i = 0; i < 8; ++i) v[i] *= scale;
             }
           }
-          *reinterpret_cast<uint4*>(img + tg * 512 + d * 16) =
-              make_uint4(umma::pack_bf16x2(v[0], v[1]), umma::pack_bf16x2(v[2], v[3]), umma::pack_bf16x2(v[4], v[5]),
-                         umma::pack_bf16x2(v[6], v[7]));
+          const uint4 pk = make_uint4(umma::pack_bf16x2(v[0], v[1]), umma::pack_bf16x2(v[2], v[3]), umma::pack_bf16x2(v[4], v[5]),
+                                      umma::pack_bf16x2(v[6], v[7]));
+          *reinterpret_cast<uint4*>(img + tg * 512 + d * 16) = pk;
+          if (q4 == 0 && tg >= 16) {                          // queries 128..143 also go to row groups {4c, 4c+1} of the Q1 image
+#pragma unroll
+            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(smem + SM_Q1 + (4 * c + tg - 16) * 512 + d * 16) = pk;
+          }
         }
       }
       umma::fence_proxy_async();
@@ -234,7 +243,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
           for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-              umma::mma_bf16_ss(tm + (mt ? TM_S1 : TM_S0), d_qh + (uint64_t)((mt * 16 * 512 + k * 256) >> 4),
+              umma::mma_bf16_ss(tm + (mt ? TM_S1 : TM_S0), (mt ? d_q1 : d_qh) + (uint64_t)((k * 256) >> 4),
                                 d_kh + (uint64_t)((k * 256) >> 4), IDESC_S, k > 0);
           umma::mma_commit(bar_s);
         }
@@ -243,45 +252,41 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
       umma::mbar_wait(bar_s, ph_s); ph_s ^= 1;
       umma::fence_after_sync();
       PH(3);
-      // ---- softmax: FOUR threads per query row (key quarter kq = grp: keys [36 kq, 36 kq + 36) = 3 window rows).
-      //      Tile 0 (rows 0..127) by all 16 warps, then tile 1 (rows 128..143 = TMEM lanes 0..15) by the four
-      //      lane-quarter-0 warps.  The shifted-window mask needs no lookup: within a key quarter the vertical
-      //      band is constant (ly < 6 <=> kq < 2) and the horizontal band of key j is the compile-time
-      //      pattern (j % 12 >= 6), so the mask is one of two per-thread additive constants.
-#pragma unroll 1
-      for (int mt = 0; mt < 2; ++mt) {
-        const bool warp_on = (mt == 0) || (q4 == 0);          // warp-uniform: tcgen05.ld is .sync.aligned
-        const int row = mt * 128 + q4 * 32 + lane;
-        const bool active = row < NTOK;
+      // ---- softmax.  Tile 0 (queries 0..127): FOUR threads per query row (key quarter kq = grp: keys [36 kq, +36) =
+      //      3 window rows).  The shifted-window mask needs no lookup there: within a key quarter the vertical band is
+      //      constant (ly < 6 <=> kq < 2) and the horizontal band of key j is the compile-time pattern (j % 12 >= 6).
+      //      Tile 1 (queries 128..143) exists in all four TMEM lane quarters (Q1 image), so all 16 warps share it:
+      //      warp (q4, grp) takes the 9 keys of part grp*4 + q4 -- a quarter-0-only pass would keep one scheduler (and
+      //      its MUFU) busy for as long as the whole of tile 0.
+      {
+        const int row = q4 * 32 + lane;
         const int kq = grp;
-        const uint32_t s_addr = lane_addr + (mt ? TM_S1 : TM_S0) + kq * 36;
+        const uint32_t s_addr = lane_addr + TM_S0 + kq * 36;
         float add0 = 0.0f, add1 = 0.0f;                       // additive mask for keys with lx < 6 / lx >= 6
         if (shift > 0) {
-          const int ly = (active ? row : 0) / WIN, lx = (active ? row : 0) % WIN;
+          const int ly = row / WIN, lx = row % WIN;
           const bool rowmask = (wy == 1) && ((ly >= 6) != (kq >= 2));
           add0 = (rowmask || (wx == 1 && lx >= 6)) ? -100.0f : 0.0f;
           add1 = (rowmask || (wx == 1 && lx < 6)) ? -100.0f : 0.0f;
         }
         float sv[36];
         float mx = -INFINITY;
-        if (warp_on) {
-          umma::tmem_ld32(s_addr, sv);
-          umma::tmem_ld4(s_addr + 32, sv + 32);
+        umma::tmem_ld32(s_addr, sv);
+        umma::tmem_ld4(s_addr + 32, sv + 32);
 #pragma unroll
-          for (int i = 0; i < 36; ++i) {
-            sv[i] += ((i % 12) >= 6) ? add1 : add0;
-            mx = fmaxf(mx, sv[i]);
-          }
-          if (active) red[kq * 144 + row] = mx;
+        for (int i = 0; i < 36; ++i) {
+          sv[i] += ((i % 12) >= 6) ? add1 : add0;
+          mx = fmaxf(mx, sv[i]);
         }
+        red[kq * 144 + row] = mx;
         __syncthreads();
-        if (warp_on && active) {
+        {
           mx = fmaxf(fmaxf(red[row], red[144 + row]), fmaxf(red[288 + row], red[432 + row]));
           const float mb = mx * 1.4426950408889634f;
           float sum = 0.0f;
 #pragma unroll
-          for (int i = 0; i < 36; ++i) { sv[i] = exp2f(fmaf(sv[i], 1.4426950408889634f, -mb)); sum += sv[i]; }
-          // 36 keys = 4.5 chunks of 8: quarter kq starts at chunk 4.5 kq -> write 72-byte span as 16-byte + 8-byte pieces
+          for (int i = 0; i < 36; ++i) { sv[i] = umma::ex2_approx(fmaf(sv[i], 1.4426950408889634f, -mb)); sum += sv[i]; }
+          // 36 keys = 4.5 chunks of 8: quarter kq starts at chunk 4.5 kq -> write 72-byte span as 8-byte pieces
           uint8_t* prow = smem + SM_P + row * 16;
 #pragma unroll
           for (int i = 0; i < 36; i += 4) {
@@ -291,7 +296,40 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
           }
           rsum[kq * 144 + row] = sum;
         }
+      }
+      {
+        const int part = grp * 4 + q4, key0 = part * 9, r1 = lane & 15;     // lanes 16..31 mirror 0..15 (results unused)
+        const int qrow = 128 + r1, qly = qrow / WIN, qlx = qrow % WIN;
+        float tv[16];
+        umma::tmem_ld16(lane_addr + TM_S1 + key0, tv);                      // 9 keys used; the rest are other parts' columns
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          if (shift > 0) {
+            const int kly = (key0 + i) / WIN, klx = (key0 + i) % WIN;
+            const bool masked = (wy == 1 && ((qly >= 6) != (kly >= 6))) || (wx == 1 && ((qlx >= 6) != (klx >= 6)));
+            tv[i] += masked ? -100.0f : 0.0f;
+          }
+          mx = fmaxf(mx, tv[i]);
+        }
+        if (lane < 16) max1[part * 16 + r1] = mx;
         __syncthreads();
+        mx = max1[r1];
+#pragma unroll
+        for (int pp = 1; pp < 16; ++pp) mx = fmaxf(mx, max1[pp * 16 + r1]);
+        const float mb = mx * 1.4426950408889634f;
+        float sum = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { tv[i] = umma::ex2_approx(fmaf(tv[i], 1.4426950408889634f, -mb)); sum += tv[i]; }
+        if (lane < 16) {
+          uint8_t* prow = smem + SM_P + qrow * 16;
+#pragma unroll
+          for (int i = 0; i < 9; ++i) {
+            const int key = key0 + i;
+            *reinterpret_cast<__nv_bfloat16*>(prow + (key >> 3) * LBO_X + (key & 7) * 2) = __float2bfloat16(tv[i]);
+          }
+          sum1[part * 16 + r1] = sum;
+        }
       }
       umma::fence_proxy_async();
       umma::fence_before_sync();
@@ -322,7 +360,15 @@ swin_attn_fast_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, in
           float v[32];
           umma::tmem_ld32(lane_addr + (mt ? TM_O1 : TM_O0), v);
           if (row < NTOK) {
-          const float inv = 1.0f / ((rsum[row] + rsum[144 + row]) + (rsum[288 + row] + rsum[432 + row]));
+          float tot;
+          if (mt == 0) {
+            tot = (rsum[row] + rsum[144 + row]) + (rsum[288 + row] + rsum[432 + row]);
+          } else {
+            tot = 0.0f;
+#pragma unroll
+            for (int pp = 0; pp < 16; ++pp) tot += sum1[pp * 16 + row - 128];
+          }
+          const float inv = 1.0f / tot;
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             *reinterpret_cast<uint4*>(smem + SM_O + (h * 4 + c) * LBO_X + row * 16) =

@@ -166,6 +166,13 @@ __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async
 // ... have completed entirely (global writes performed)
 __device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 
+// ---- 2^x on the MUFU pipe, one instruction (exp2f() adds range handling around it)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // ---- L2 prefetch of a 128-byte line (no register, no dependency)
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" :: "l"(p)); }
 
