@@ -573,7 +573,7 @@ struct Plan {
   DecoderDims dd;
   // workspace offsets (floats)
   size_t imgn, textn, corr, cmax, classes, tmean, text_g, cg_qk, pad_state, app_g, app_gn, ag_qk, dg0, dg1, X,
-      Xp, Xp2, state, timg, dec, total;
+      Xp, Xp2, state, timg, dec, agw, total;
 };
 
 Plan make_plan(const catseg_handle* h, int B, int T) {
@@ -607,6 +607,7 @@ Plan make_plan(const catseg_handle* h, int B, int T) {
   p.app_g = take((size_t)B * p.HW * 128);
   p.app_gn = take((size_t)B * p.HW * 128);
   p.ag_qk = take((size_t)p.L * 2 * B * p.HW * 256);
+  p.agw = (h->fast_mask & CATSEG_FAST_SWIN_ATTN) ? take((size_t)p.L * 2 * B * 16 * 144 * 64 / 2) : 0;   // bf16 window tiles
   p.dg0 = take((size_t)B * 4 * p.HW * p.dd.G1);
   p.dg1 = take((size_t)B * 16 * p.HW * p.dd.G2);
   p.X = take((size_t)nslice * p.HW * 128);
@@ -762,7 +763,11 @@ extern "C" int catseg_forward_taps(catseg_handle* h, const float* img, const flo
       const float* agk = ws + p.ag_qk + (size_t)(l * 2 + k) * B * p.HW * 256;
       const int shift = k == 0 ? 0 : c.window_size / 2;
       seg.begin(CATSEG_STAGE_SWIN);
-      if (attn_fast) RUN(launch_swin_attn_fast(X, agk, nslice, p.Te, shift, h->swin_attn_fast[l * 2 + k], h->num_sms, st));
+      if (attn_fast) {
+        __nv_bfloat16* agw = reinterpret_cast<__nv_bfloat16*>(ws + p.agw) + (size_t)(l * 2 + k) * B * 16 * 144 * 64;
+        RUN(launch_pack_ag_windows(agk, agw, B, shift, st));
+        RUN(launch_swin_attn_fast(X, agw, nslice, p.Te, shift, h->swin_attn_fast[l * 2 + k], h->num_sms, st));
+      }
       else RUN(launch_swin_block_exact(X, agk, nslice, p.Te, shift, h->swin[l * 2 + k], mlp_fast ? 0 : 1, st));
       seg.end();
       if (mlp_fast) {

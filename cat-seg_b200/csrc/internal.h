@@ -97,8 +97,10 @@ cudaError_t launch_mlp_fast(float* X, long long ntok, const MlpFastW& w, int act
 cudaError_t launch_pack_wimg(__nv_bfloat16* dst, const float* W, int ld, int r0, int c0, cudaStream_t st);
 
 // ---------------------------------------------------------------- fast_swin_attn.cu
-cudaError_t launch_swin_attn_fast(float* X, const float* ag_qk, int nslice, int Te, int shift,
+// agw: bf16 guidance tiles [B][4 windows][4 heads][144 tok][64] of this block (launch_pack_ag_windows, same shift)
+cudaError_t launch_swin_attn_fast(float* X, const __nv_bfloat16* agw, int nslice, int Te, int shift,
                                   const SwinAttnFastW& w, int num_sms, cudaStream_t st);
+cudaError_t launch_pack_ag_windows(const float* ag_qk, __nv_bfloat16* out, int B, int shift, cudaStream_t st);
 cudaError_t launch_pack_qkv_head_img(__nv_bfloat16* dst, const float* Wq, const float* Wk, const float* Wv, int ldqk,
                                      int h, cudaStream_t st);
 
