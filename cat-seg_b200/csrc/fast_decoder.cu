@@ -18,6 +18,9 @@
 //     the image (resp. only on the weights): they enter as an additive per-image map E.
 // Stages: D1 x(24^2,128) -> c1a(48^2,64) | D2 c1a -> c1b | D3 c1b -> c2a(96^2,32) | D4 c2a -> c2b |
 //         D5 head c2b -> logits (N padded to 16, column 0 real).
+#include <cstdio>
+#include <cstdlib>
+
 #include "fast_common.cuh"
 #include "igemm.cuh"
 #include "internal.h"
@@ -43,6 +46,7 @@ struct BandConvParams {
   float head_bias;
   int slice0;                // absolute index of local slice 0 (for b = (slice0+s)/Te and classes)
   int nslice;                // local slices in this launch
+  long long* dbg;            // optional phase timing (CATSEG_PHASE_TIMING=1)
 };
 
 template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD>
@@ -67,15 +71,22 @@ struct BandCfg {
   static constexpr uint32_t SM_SC = SM_W + NSLOT * WBYTES;            // scale[CIN], shift[CIN]
   static constexpr uint32_t SM_ST = SM_SC + 2 * CIN * 4;              // [8 warps][GOUT][2]
   static constexpr uint32_t SM_BAR = (SM_ST + 8 * GOUT * 2 * 4 + 15) / 16 * 16;
-  static constexpr uint32_t SMEM = SM_BAR + (2 * NSLOT + 2) * 8 + 16;
+  static constexpr uint32_t SMEM = SM_BAR + (2 * NSLOT + 3) * 8 + 16;
   static constexpr uint32_t IDESC = umma::make_idesc_bf16(128, NOUT);
   static_assert(NTILES * NOUT <= 256, "TMEM columns (two CTAs per SM)");
   static_assert(SMEM <= 113 * 1024, "shared memory budget (two CTAs per SM)");
   static_assert(WIN_ % BR == 0 && CIN % 16 == 0 && NOUT % 16 == 0, "shape");
 };
 
+// Roles: warps 0-7 stage the band and run the epilogues (TMEM lane quarter q4 = warp & 3, the two warp sets take
+// alternate tiles); warp 8 only issues (tcgen05.mma, weight ring).  The MMA queue is shallow, so the issuing thread is
+// blocked while its MMAs execute: a worker that also issued would join every epilogue late and hold up its barrier.
+// The composed (UPS) stages compute four output parities from the same staged image: with two accumulator sets the MMAs
+// of parity pg+1 run under the epilogue of parity pg.
+constexpr int BAND_THREADS = 288;
+
 template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD>
-__global__ void __launch_bounds__(256, 2) band_conv_kernel(BandConvParams p) {
+__global__ void __launch_bounds__(BAND_THREADS, 2) band_conv_kernel(BandConvParams p) {
   using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD>;
   extern __shared__ __align__(1024) uint8_t smem[];
   float* s_scale = reinterpret_cast<float*>(smem + C::SM_SC);
@@ -83,9 +94,12 @@ __global__ void __launch_bounds__(256, 2) band_conv_kernel(BandConvParams p) {
   float* s_part = reinterpret_cast<float*>(smem + C::SM_ST);
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + C::SM_BAR);   // [NSLOT]
   uint64_t* bar_empty = bar_full + C::NSLOT;                             // [NSLOT]
-  uint64_t* bar_acc = bar_empty + C::NSLOT;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 1);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q4 = warp & 3, tgrp = warp >> 2;   // 8 warps
+  uint64_t* bar_acc = bar_empty + C::NSLOT;                              // [2] accumulator sets
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q4 = warp & 3, tgrp = (warp >> 2) & 1;
+  const bool issuer = __shfl_sync(0xffffffffu, warp, 0) == 8;           // warp-uniform role
+  constexpr int ACC_COLS = C::NTILES * NOUT;
+  constexpr int SETS = (C::NPG > 1 && 2 * ACC_COLS <= 256) ? 2 : 1;
 
   const long long nitems = (long long)p.nslice * C::NB;
   long long mine = 0;
@@ -93,7 +107,7 @@ __global__ void __launch_bounds__(256, 2) band_conv_kernel(BandConvParams p) {
   const long long total_loads = C::RESIDENT ? 1 : mine * C::NIMG;
 
   if (tid == 0) {
-    for (int i = 0; i < 2 * C::NSLOT + 1; ++i) umma::mbar_init(&bar_full[i], 1);
+    for (int i = 0; i < 2 * C::NSLOT + 2; ++i) umma::mbar_init(&bar_full[i], 1);
     umma::mbar_fence_init();
   }
   if (warp == 0) umma::tmem_alloc<256>(tmem_slot);
@@ -104,7 +118,7 @@ __global__ void __launch_bounds__(256, 2) band_conv_kernel(BandConvParams p) {
   const uint32_t sb = umma::smem_u32(smem);
   const uint32_t lane_addr = tm + ((uint32_t)(q4 * 32) << 16);
 
-  auto issue_load = [&](long long n) {      // thread 0 only (streaming mode)
+  auto issue_load = [&](long long n) {      // one elected lane of the issuing warp (streaming mode)
     if (n < total_loads) {
       int s = (int)(n % C::NSLOT);
       umma::mbar_expect_tx(&bar_full[s], C::WBYTES);
@@ -112,31 +126,100 @@ __global__ void __launch_bounds__(256, 2) band_conv_kernel(BandConvParams p) {
                      reinterpret_cast<const uint8_t*>(p.wimg) + (n % C::NIMG) * C::WBYTES, C::WBYTES, &bar_full[s]);
     }
   };
-  if (tid == 0) {
-    if (C::RESIDENT) {
-      umma::mbar_expect_tx(&bar_full[0], C::NIMG * C::WBYTES);
-      umma::bulk_g2s(smem + C::SM_W, p.wimg, C::NIMG * C::WBYTES, &bar_full[0]);
-    } else {
-      for (int i = 0; i < C::NSLOT - 1; ++i) issue_load(i);
+  if (issuer) {
+    if (umma::elect_one()) {
+      if (C::RESIDENT) {
+        umma::mbar_expect_tx(&bar_full[0], C::NIMG * C::WBYTES);
+        umma::bulk_g2s(smem + C::SM_W, p.wimg, C::NIMG * C::WBYTES, &bar_full[0]);
+      } else {
+        for (int i = 0; i < C::NSLOT - 1; ++i) issue_load(i);
+      }
     }
+    __syncwarp();
   }
-  long long nimg = 0;          // streaming: images consumed so far by this CTA
-  uint32_t ph_acc = 0;
+  long long nimg = 0;          // streaming: images consumed so far by this CTA (issuing warp, all lanes)
+  uint32_t ph_acc[2] = {0, 0};
   bool w_ready = false;
+  long long t_last = clock64(), pacc0 = 0, pacc1 = 0, pacc2 = 0, pacc3 = 0, pacc4 = 0, nit_dbg = 0;
+#define BPH(i) do { if (p.dbg != nullptr && blockIdx.x == 0 && tid == 0) { long long _t = clock64(); pacc##i += _t - t_last; t_last = _t; } } while (0)
+
+  // all MMAs of one parity group into accumulator set `set` (every lane of the issuing warp runs the control flow and
+  // keeps the ring state; one elected lane issues)
+  auto issue_group = [&](int pg, int set) {
+    const int pa = pg >> 1, pb = pg & 1;
+    if (C::RESIDENT && !w_ready) { umma::mbar_wait(&bar_full[0], 0); w_ready = true; }
+    const uint64_t a_desc0 = umma::make_smem_desc(sb, C::LBO_I, 128);
+#pragma unroll 1
+    for (int tap = 0; tap < C::NTAP; ++tap) {
+      int off;
+      if (UPS) off = ((tap >> 1) + pa - 1) * C::PW + ((tap & 1) + pb - 1);
+      else off = (tap / 3 - 1) * C::PW + (tap % 3 - 1);
+      uint32_t wb;
+      int slot = 0;
+      if (C::RESIDENT) {
+        wb = sb + C::SM_W + (uint32_t)(pg * C::NTAP + tap) * C::WBYTES;
+      } else {
+        slot = (int)(nimg % C::NSLOT);
+        umma::mbar_wait(&bar_full[slot], (uint32_t)((nimg / C::NSLOT) & 1));
+        wb = sb + C::SM_W + (uint32_t)slot * C::WBYTES;
+      }
+      // descriptors are built once and advanced by integer adds on the (address >> 4) field
+      const uint64_t b_desc = umma::make_smem_desc(wb, C::LBO_WT, 128);
+      if (umma::elect_one()) {
+        uint64_t a_tile = a_desc0 + (uint64_t)(uint32_t)(C::P0 + off);
+#pragma unroll 1
+        for (int t = 0; t < C::NTILES; ++t) {
+#pragma unroll
+          for (int k = 0; k < C::KSTEPS; ++k)
+            umma::mma_bf16_ss(tm + set * ACC_COLS + t * NOUT, a_tile + (uint64_t)(k * 2 * (C::LBO_I >> 4)),
+                              b_desc + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC, (tap > 0 || k > 0) ? 1u : 0u);
+          a_tile += 128;
+        }
+        if (!C::RESIDENT) umma::mma_commit(&bar_empty[slot]);
+      }
+      __syncwarp();
+      if (!C::RESIDENT) {
+        // refill the slot of the PREVIOUS image (its MMAs were committed one step ago)
+        const long long nn = nimg + C::NSLOT - 1;
+        if (nimg > 0 && nn < total_loads)
+          umma::mbar_wait(&bar_empty[(nimg - 1) % C::NSLOT], (uint32_t)(((nimg - 1) / C::NSLOT) & 1));
+        if (umma::elect_one()) issue_load(nn);
+        __syncwarp();
+        ++nimg;
+      }
+    }
+    if (umma::elect_one()) umma::mma_commit(&bar_acc[set]);
+    __syncwarp();
+  };
 
   for (long long it = blockIdx.x; it < nitems; it += gridDim.x) {
     const int sl = (int)(it / C::NB), band = (int)(it % C::NB);
     const int gslice = p.slice0 + sl;
     const int b = gslice / p.Te;
+    if (!issuer) {   // the input rows of this CTA's NEXT band (one contiguous span) are prefetched into L2 meanwhile
+      const long long itn = it + gridDim.x;
+      if (itn < nitems) {
+        const int sln = (int)(itn / C::NB), bandn = (int)(itn % C::NB);
+        const int y0 = bandn * BR - 1 < 0 ? 0 : bandn * BR - 1, y1 = bandn * BR + BR + 1 > WIN_ ? WIN_ : bandn * BR + BR + 1;
+        constexpr int ESZ = IN_F32 ? 4 : 2;
+        const char* base = reinterpret_cast<const char*>(p.in) + (((long long)sln * WIN_ + y0) * WIN_) * CIN * ESZ;
+        const int nlines = (y1 - y0) * WIN_ * CIN * ESZ / 128;
+        for (int i = tid; i < nlines; i += 256) umma::prefetch_l2(base + (long long)i * 128);
+      }
+    }
     // ---- GroupNorm parameters of the input (fixed-order reduction of the producer's band partials)
     if (p.in_stats != nullptr) {
       if (tid < CIN) {
         const int g = tid >> 4, G = CIN / 16;
         float s = 0.f, ss = 0.f;
-        for (int i = 0; i < p.nb_in; ++i) {
-          const float* st = p.in_stats + (((long long)sl * p.nb_in + i) * G + g) * 2;
-          s += st[0]; ss += st[1];
-        }
+        float2 part[16];                                 // nb_in <= 16: all partials in flight at once, summed in order
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          part[i] = i < p.nb_in ? __ldg(reinterpret_cast<const float2*>(p.in_stats + (((long long)sl * p.nb_in + i) * G + g) * 2))
+                                : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (i < p.nb_in) { s += part[i].x; ss += part[i].y; }
         float mean = s / p.in_count;
         float var = fmaxf(ss / p.in_count - mean * mean, 0.0f);
         float rstd = rsqrtf(var + 1e-5f);
@@ -146,13 +229,22 @@ __global__ void __launch_bounds__(256, 2) band_conv_kernel(BandConvParams p) {
       }
       __syncthreads();
     }
+    BPH(4);
     // ---- stage the padded band image (bf16, canonical K-major, rows = padded raster positions).
     //      Explicitly software-pipelined: U independent 16/32-byte loads are issued before any is consumed
     //      (ncu showed the compiler serialising load -> convert -> store per chunk: one latency per chunk).
-    {
+    //      256 % KCH == 0, so a thread always handles the same 8-channel group: its GroupNorm scale/shift live in registers.
+    if (!issuer) {
       const int y_first = band * BR - 1;
       constexpr int U = IN_F32 ? 4 : 8;
       constexpr int NCHUNK = C::NP * C::KCH;
+      static_assert(256 % C::KCH == 0, "a thread keeps its channel group");
+      const int c = tid % C::KCH;
+      float sc[8], sh[8];
+      if (p.in_stats != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = s_scale[c * 8 + j]; sh[j] = s_shift[c * 8 + j]; }
+      }
 #pragma unroll 1
       for (int base = tid; base < NCHUNK; base += 256 * U) {
         uint4 raw[U][IN_F32 ? 2 : 1];
@@ -160,7 +252,7 @@ __global__ void __launch_bounds__(256, 2) band_conv_kernel(BandConvParams p) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int idx = base + u * 256;
-          const int pp = idx / C::KCH, c = idx % C::KCH;
+          const int pp = idx / C::KCH;
           const int yy = y_first + pp / C::PW, xx = pp % C::PW - 1;
           inb[u] = idx < NCHUNK && yy >= 0 && yy < WIN_ && xx >= 0 && xx < WIN_;
           const long long off = inb[u] ? (((long long)sl * WIN_ + yy) * WIN_ + xx) * CIN + c * 8 : 0;
@@ -176,7 +268,7 @@ __global__ void __launch_bounds__(256, 2) band_conv_kernel(BandConvParams p) {
         for (int u = 0; u < U; ++u) {
           const int idx = base + u * 256;
           if (idx >= NCHUNK) continue;
-          const int pp = idx / C::KCH, c = idx % C::KCH;
+          const int pp = idx / C::KCH;
           uint4 val = make_uint4(0u, 0u, 0u, 0u);
           if (inb[u]) {
             float v[8];
@@ -191,7 +283,7 @@ __global__ void __launch_bounds__(256, 2) band_conv_kernel(BandConvParams p) {
             }
             if (p.in_stats != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], s_scale[c * 8 + j], s_shift[c * 8 + j]), 0.0f);
+              for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.0f);
             }
             val = make_uint4(umma::pack_bf16x2(v[0], v[1]), umma::pack_bf16x2(v[2], v[3]), umma::pack_bf16x2(v[4], v[5]),
                              umma::pack_bf16x2(v[6], v[7]));
@@ -199,10 +291,16 @@ __global__ void __launch_bounds__(256, 2) band_conv_kernel(BandConvParams p) {
           *reinterpret_cast<uint4*>(smem + c * C::LBO_I + pp * 16) = val;
         }
       }
+      umma::fence_proxy_async();
     }
-    umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
+    BPH(0);
+    if (issuer) {
+      umma::fence_after_sync();
+      issue_group(0, 0);
+      if (SETS == 2) issue_group(1, 1);
+    }
 
     float st_sum[C::GOUT], st_sq[C::GOUT];
 #pragma unroll
@@ -211,130 +309,100 @@ __global__ void __launch_bounds__(256, 2) band_conv_kernel(BandConvParams p) {
 #pragma unroll 1
     for (int pg = 0; pg < C::NPG; ++pg) {
       const int pa = pg >> 1, pb = pg & 1;
-      if (tid == 0) {
+      const int set = pg % SETS;
+      const uint32_t acc_addr = lane_addr + set * ACC_COLS;
+      if (!issuer) {
+        // ---- epilogue: thread = padded raster row; the two warp sets take alternate tiles.  The additive map
+        //      of the first tile is fetched BEFORE waiting for the accumulators (hides the global latency).
+        float e_pre[UPS ? 32 : 1];     // additive map (composed stages only): first 32 channels of this warp set's first tile
+        auto tile_geom = [&](int t, bool& valid, long long& opix) {
+          const int pr = C::P0 + t * 128 + q4 * 32 + lane;
+          const int yl = pr / C::PW - 1, xl = pr % C::PW - 1;
+          valid = (pr < C::P0 + C::MROWS) && xl >= 0 && xl < WIN_;
+          int Yo = band * BR + yl, Xo = xl;
+          if (UPS) { Yo = 2 * Yo + pa; Xo = 2 * Xo + pb; }
+          opix = (long long)Yo * C::WOUT + Xo;
+        };
+        if constexpr (UPS) {
+          if (tgrp < C::NTILES) {
+            bool valid; long long opix;
+            tile_geom(tgrp, valid, opix);
+            const float* e = p.emap + ((long long)b * (C::WOUT * C::WOUT) + (valid ? opix : 0)) * NREAL;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float4 e4 = ld4(e + i);
+              e_pre[i] = e4.x; e_pre[i + 1] = e4.y; e_pre[i + 2] = e4.z; e_pre[i + 3] = e4.w;
+            }
+          }
+        }
+        umma::mbar_wait(&bar_acc[set], ph_acc[set]);
         umma::fence_after_sync();
-        if (C::RESIDENT && !w_ready) { umma::mbar_wait(&bar_full[0], 0); w_ready = true; }
-        const uint64_t a_desc0 = umma::make_smem_desc(sb, C::LBO_I, 128);
+        BPH(1);
 #pragma unroll 1
-        for (int tap = 0; tap < C::NTAP; ++tap) {
-          int off;
-          if (UPS) off = ((tap >> 1) + pa - 1) * C::PW + ((tap & 1) + pb - 1);
-          else off = (tap / 3 - 1) * C::PW + (tap % 3 - 1);
-          uint32_t wb;
-          int slot = 0;
-          if (C::RESIDENT) {
-            wb = sb + C::SM_W + (uint32_t)(pg * C::NTAP + tap) * C::WBYTES;
-          } else {
-            slot = (int)(nimg % C::NSLOT);
-            umma::mbar_wait(&bar_full[slot], (uint32_t)((nimg / C::NSLOT) & 1));
-            wb = sb + C::SM_W + (uint32_t)slot * C::WBYTES;
-          }
-          // descriptors are built once and advanced by integer adds on the (address >> 4) field: the single
-          // issuing thread must spend ~10 cycles per MMA, not ~100 (these MMAs are only 8-32 tensor cycles long)
-          const uint64_t b_desc = umma::make_smem_desc(wb, C::LBO_WT, 128);
-          uint64_t a_tile = a_desc0 + (uint64_t)(uint32_t)(C::P0 + off);
-#pragma unroll 1
-          for (int t = 0; t < C::NTILES; ++t) {
-#pragma unroll
-            for (int k = 0; k < C::KSTEPS; ++k)
-              umma::mma_bf16_ss(tm + t * NOUT, a_tile + (uint64_t)(k * 2 * (C::LBO_I >> 4)),
-                                b_desc + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC, (tap > 0 || k > 0) ? 1u : 0u);
-            a_tile += 128;
-          }
-          if (!C::RESIDENT) {
-            umma::mma_commit(&bar_empty[slot]);
-            // refill the slot of the PREVIOUS image (its MMAs were committed one step ago)
-            long long nn = nimg + C::NSLOT - 1;
-            if (nimg > 0 && nn < total_loads)
-              umma::mbar_wait(&bar_empty[(nimg - 1) % C::NSLOT], (uint32_t)(((nimg - 1) / C::NSLOT) & 1));
-            issue_load(nn);
-            ++nimg;
-          }
-        }
-        umma::mma_commit(bar_acc);
-      }
-      __syncwarp();   // park lanes 1-31 of warp 0 while lane 0 issues (they must not spin on an mbarrier)
-      // ---- epilogue: thread = padded raster row; the two warp sets take alternate tiles.  The additive map
-      //      of the first tile is fetched BEFORE waiting for the accumulators (hides the global latency).
-      float e_pre[HEAD ? 1 : NREAL];
-      auto tile_geom = [&](int t, bool& valid, long long& opix) {
-        const int pr = C::P0 + t * 128 + q4 * 32 + lane;
-        const int yl = pr / C::PW - 1, xl = pr % C::PW - 1;
-        valid = (pr < C::P0 + C::MROWS) && xl >= 0 && xl < WIN_;
-        int Yo = band * BR + yl, Xo = xl;
-        if (UPS) { Yo = 2 * Yo + pa; Xo = 2 * Xo + pb; }
-        opix = (long long)Yo * C::WOUT + Xo;
-      };
-      if constexpr (!HEAD) {
-        if (p.emap != nullptr && tgrp < C::NTILES) {
+        for (int t = tgrp; t < C::NTILES; t += 2) {
           bool valid; long long opix;
-          tile_geom(tgrp, valid, opix);
-          const float* e = p.emap + ((long long)b * (C::WOUT * C::WOUT) + (valid ? opix : 0)) * NREAL;
-#pragma unroll
-          for (int i = 0; i < NREAL; i += 4) {
-            float4 e4 = ld4(e + i);
-            e_pre[i] = e4.x; e_pre[i + 1] = e4.y; e_pre[i + 2] = e4.z; e_pre[i + 3] = e4.w;
-          }
-        }
-      }
-      umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
-      umma::fence_after_sync();
-#pragma unroll 1
-      for (int t = tgrp; t < C::NTILES; t += 2) {
-        bool valid; long long opix;
-        tile_geom(t, valid, opix);
-        if constexpr (HEAD) {
-          float v[8];
-          umma::tmem_ld8(lane_addr + t * NOUT, v);
-          if (valid) {
-            int cls = p.classes[gslice];
-            p.logits[((long long)b * p.T + cls) * (C::WOUT * C::WOUT) + opix] = v[0] + p.head_bias;
-          }
-        } else {
-#pragma unroll
-          for (int c0 = 0; c0 < NREAL; c0 += 32) {
-            float v[32];
-            umma::tmem_ld32(lane_addr + t * NOUT + c0, v);
+          tile_geom(t, valid, opix);
+          if constexpr (HEAD) {
+            float v[8];
+            umma::tmem_ld8(acc_addr + t * NOUT, v);
             if (valid) {
-              if (p.emap != nullptr) {
-                if (t == tgrp) {
+              int cls = p.classes[gslice];
+              p.logits[((long long)b * p.T + cls) * (C::WOUT * C::WOUT) + opix] = v[0] + p.head_bias;
+            }
+          } else {
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) v[i] += e_pre[c0 + i];
-                } else {
-                  const float* e = p.emap + ((long long)b * (C::WOUT * C::WOUT) + opix) * NREAL + c0;
+            for (int c0 = 0; c0 < NREAL; c0 += 32) {
+              float v[32];
+              umma::tmem_ld32(acc_addr + t * NOUT + c0, v);
+              if (valid) {
+                if constexpr (UPS) {
+                  if (t == tgrp && c0 == 0) {
 #pragma unroll
-                  for (int i = 0; i < 32; i += 4) {
-                    float4 e4 = ld4(e + i);
-                    v[i] += e4.x; v[i + 1] += e4.y; v[i + 2] += e4.z; v[i + 3] += e4.w;
+                    for (int i = 0; i < 32; ++i) v[i] += e_pre[i];
+                  } else {
+                    const float* e = p.emap + ((long long)b * (C::WOUT * C::WOUT) + opix) * NREAL + c0;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                      float4 e4 = ld4(e + i);
+                      v[i] += e4.x; v[i + 1] += e4.y; v[i + 2] += e4.z; v[i + 3] += e4.w;
+                    }
                   }
                 }
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                  float s = 0.f, ss = 0.f;
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) { float x = v[g * 16 + i]; s += x; ss = fmaf(x, x, ss); }
+                  st_sum[c0 / 16 + g] += s; st_sq[c0 / 16 + g] += ss;
+                }
+                __nv_bfloat16* o = p.out + ((long long)sl * (C::WOUT * C::WOUT) + opix) * NREAL + c0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 8)
+                  *reinterpret_cast<uint4*>(o + i) =
+                      make_uint4(umma::pack_bf16x2(v[i], v[i + 1]), umma::pack_bf16x2(v[i + 2], v[i + 3]),
+                                 umma::pack_bf16x2(v[i + 4], v[i + 5]), umma::pack_bf16x2(v[i + 6], v[i + 7]));
               }
-#pragma unroll
-              for (int g = 0; g < 2; ++g) {
-                float s = 0.f, ss = 0.f;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) { float x = v[g * 16 + i]; s += x; ss = fmaf(x, x, ss); }
-                st_sum[c0 / 16 + g] += s; st_sq[c0 / 16 + g] += ss;
-              }
-              __nv_bfloat16* o = p.out + ((long long)sl * (C::WOUT * C::WOUT) + opix) * NREAL + c0;
-#pragma unroll
-              for (int i = 0; i < 32; i += 8)
-                *reinterpret_cast<uint4*>(o + i) =
-                    make_uint4(umma::pack_bf16x2(v[i], v[i + 1]), umma::pack_bf16x2(v[i + 2], v[i + 3]),
-                               umma::pack_bf16x2(v[i + 4], v[i + 5]), umma::pack_bf16x2(v[i + 6], v[i + 7]));
             }
           }
         }
       }
+      ph_acc[set] ^= 1;
       umma::fence_before_sync();
-      __syncthreads();        // accumulators (and, after the last parity, the image) may be overwritten
+      __syncthreads();        // accumulator set (and, after the last parity, the image) may be overwritten
+      BPH(2);
+      if (issuer && pg + SETS < C::NPG) {
+        umma::fence_after_sync();
+        issue_group(pg + SETS, set);
+      }
     }
     // ---- output statistics of this band: warp shuffle -> per-warp slots -> fixed-order sum
     if (!HEAD) {
+      if (!issuer) {
 #pragma unroll
-      for (int g = 0; g < C::GOUT; ++g) {
-        float s = warp_sum(st_sum[g]), ss = warp_sum(st_sq[g]);
-        if (lane == 0) { s_part[(warp * C::GOUT + g) * 2] = s; s_part[(warp * C::GOUT + g) * 2 + 1] = ss; }
+        for (int g = 0; g < C::GOUT; ++g) {
+          float s = warp_sum(st_sum[g]), ss = warp_sum(st_sq[g]);
+          if (lane == 0) { s_part[(warp * C::GOUT + g) * 2] = s; s_part[(warp * C::GOUT + g) * 2 + 1] = ss; }
+        }
       }
       __syncthreads();
       if (tid < C::GOUT * 2) {
@@ -344,7 +412,11 @@ __global__ void __launch_bounds__(256, 2) band_conv_kernel(BandConvParams p) {
       }
       __syncthreads();
     }
+    BPH(3);
+    ++nit_dbg;
   }
+  if (p.dbg != nullptr && blockIdx.x == 0 && tid == 0) { p.dbg[0] = pacc0; p.dbg[1] = pacc1; p.dbg[2] = pacc2; p.dbg[3] = pacc3; p.dbg[4] = nit_dbg; p.dbg[5] = pacc4; }
+#undef BPH
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc<256>(tm);
@@ -363,7 +435,27 @@ static cudaError_t launch_band(const BandConvParams& p, int num_sms, cudaStream_
   long long nitems = (long long)p.nslice * C::NB;
   int grid = (int)(nitems < 2LL * num_sms ? nitems : 2LL * num_sms);
   if (grid <= 0) return cudaSuccess;
-  kern<<<grid, 256, C::SMEM, st>>>(p);
+  static long long* dbg = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) {
+    const char* e = getenv("CATSEG_PHASE_TIMING");
+    dbg_on = (e && e[0] == '1') ? 1 : 0;
+    if (dbg_on) { cudaMalloc(&dbg, 8 * sizeof(long long)); cudaMemset(dbg, 0, 8 * sizeof(long long)); }
+  }
+  BandConvParams q = p;
+  q.dbg = dbg_on ? dbg : nullptr;
+  kern<<<grid, BAND_THREADS, C::SMEM, st>>>(q);
+  if (dbg_on) {
+    long long hb[8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hb, dbg, sizeof(hb), cudaMemcpyDeviceToHost);
+    double n = hb[4] > 0 ? (double)hb[4] : 1.0;
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BAND_THREADS, C::SMEM);
+    fprintf(stderr, "[occupancy %d CTAs/SM, smem %u] ", occ, (unsigned)C::SMEM);
+    fprintf(stderr, "[band_conv<%d,%d,ups=%d,W=%d> cycles/band over %lld bands, thread 0 (issuer)] stage %.0f | mma issue+wait %.0f (x%d parity groups) "
+            "| epilogue %.0f | stats %.0f | (GN params of the input %.0f, before 'stage')\n", CIN, NOUT, (int)UPS, WIN_, hb[4], hb[0] / n, hb[1] / n, C::NPG, hb[2] / n, hb[3] / n, hb[5] / n);
+  }
   return cudaGetLastError();
 }
 
