@@ -31,6 +31,16 @@ __device__ __forceinline__ float4 warp_layernorm128(float4 x, float4 gamma, floa
                      dz * rstd * gamma.z + beta.z, dw * rstd * gamma.w + beta.w);
 }
 
+// Same, for the bf16 paths: MUFU rsqrt instead of the IEEE sqrt + divide sequence (the result is rounded to bf16).
+__device__ __forceinline__ float4 warp_layernorm128_fast(float4 x, float4 gamma, float4 beta) {
+  float mean = warp_sum(x.x + x.y + x.z + x.w) * (1.0f / 128.0f);
+  float dx = x.x - mean, dy = x.y - mean, dz = x.z - mean, dw = x.w - mean;
+  float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.0f / 128.0f);
+  float rstd = rsqrtf(var + 1e-5f);
+  return make_float4(fmaf(dx * rstd, gamma.x, beta.x), fmaf(dy * rstd, gamma.y, beta.y),
+                     fmaf(dz * rstd, gamma.z, beta.z), fmaf(dw * rstd, gamma.w, beta.w));
+}
+
 __device__ __forceinline__ float gelu_erf(float x) {   // nn.GELU() default (exact erf), model.py:139
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }

@@ -62,7 +62,7 @@ __device__ __forceinline__ void ln_rows_to_tile(const float* __restrict__ src, l
 #pragma unroll
     for (int i = 0; i < R; ++i) {
       int r = r0 + i;
-      float4 y = warp_layernorm128(x[i], g, be);
+      float4 y = warp_layernorm128_fast(x[i], g, be);
       if (r >= nvalid) y = make_float4(0.f, 0.f, 0.f, 0.f);
       uint2 p = make_uint2(umma::pack_bf16x2(y.x, y.y), umma::pack_bf16x2(y.z, y.w));
       *reinterpret_cast<uint2*>(tile + (lane >> 1) * LBO_T + r * 16 + (lane & 1) * 8) = p;
