@@ -284,6 +284,30 @@ swin_attn_fast_kernel(float* __restrict__ X, const __nv_bfloat16* __restrict__ a
       //      warp (q4, grp) takes the 9 keys of part grp*4 + q4 -- a quarter-0-only pass would keep one scheduler (and
       //      its MUFU) busy for as long as the whole of tile 0.
       {
+        // tile 1, pass 1: local max of this warp's 9 keys (the values are re-read from TMEM after the barrier: cheaper
+        // than keeping them live next to the 36 values of tile 0)
+        const int part = grp * 4 + q4, key0 = part * 9, r1 = lane & 15;     // lanes 16..31 mirror 0..15 (results unused)
+        const int qrow = 128 + r1, qly = qrow / WIN, qlx = qrow % WIN;
+        auto load_tile1 = [&](float* tv) {
+          umma::tmem_ld16(lane_addr + TM_S1 + key0, tv);                    // 9 keys used; the rest are other parts' columns
+          if (shift > 0) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+              const int kly = (key0 + i) / WIN, klx = (key0 + i) % WIN;
+              const bool masked = (wy == 1 && ((qly >= 6) != (kly >= 6))) || (wx == 1 && ((qlx >= 6) != (klx >= 6)));
+              tv[i] += masked ? -100.0f : 0.0f;
+            }
+          }
+        };
+        {
+          float tv[16];
+          load_tile1(tv);
+          float mx1 = tv[0];
+#pragma unroll
+          for (int i = 1; i < 9; ++i) mx1 = fmaxf(mx1, tv[i]);
+          if (lane < 16) max1[part * 16 + r1] = mx1;
+        }
+        // tile 0, pass 1
         const int row = q4 * 32 + lane;
         const int kq = grp;
         const uint32_t s_addr = lane_addr + TM_S0 + kq * 36;
@@ -304,7 +328,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const __nv_bfloat16* __restrict__ a
           mx = fmaxf(mx, sv[i]);
         }
         red[kq * 144 + row] = mx;
-        __syncthreads();
+        __syncthreads();                                      // the only exchange barrier: row maxima of both tiles
         {
           mx = fmaxf(fmaxf(red[row], red[144 + row]), fmaxf(red[288 + row], red[432 + row]));
           const float mb = mx * 1.4426950408889634f;
@@ -321,39 +345,26 @@ swin_attn_fast_kernel(float* __restrict__ X, const __nv_bfloat16* __restrict__ a
           }
           rsum[kq * 144 + row] = sum;
         }
-      }
-      {
-        const int part = grp * 4 + q4, key0 = part * 9, r1 = lane & 15;     // lanes 16..31 mirror 0..15 (results unused)
-        const int qrow = 128 + r1, qly = qrow / WIN, qlx = qrow % WIN;
-        float tv[16];
-        umma::tmem_ld16(lane_addr + TM_S1 + key0, tv);                      // 9 keys used; the rest are other parts' columns
-        float mx = -INFINITY;
+        // tile 1, pass 2
+        {
+          float tv[16];
+          load_tile1(tv);
+          float mx1 = max1[r1];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) {
-          if (shift > 0) {
-            const int kly = (key0 + i) / WIN, klx = (key0 + i) % WIN;
-            const bool masked = (wy == 1 && ((qly >= 6) != (kly >= 6))) || (wx == 1 && ((qlx >= 6) != (klx >= 6)));
-            tv[i] += masked ? -100.0f : 0.0f;
+          for (int pp = 1; pp < 16; ++pp) mx1 = fmaxf(mx1, max1[pp * 16 + r1]);
+          const float mb = mx1 * 1.4426950408889634f;
+          float sum = 0.0f;
+#pragma unroll
+          for (int i = 0; i < 9; ++i) { tv[i] = umma::ex2_approx(fmaf(tv[i], 1.4426950408889634f, -mb)); sum += tv[i]; }
+          if (lane < 16) {
+            uint8_t* prow = smem + SM_P + qrow * 16;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+              const int key = key0 + i;
+              *reinterpret_cast<__nv_bfloat16*>(prow + (key >> 3) * LBO_X + (key & 7) * 2) = __float2bfloat16(tv[i]);
+            }
+            sum1[part * 16 + r1] = sum;
           }
-          mx = fmaxf(mx, tv[i]);
-        }
-        if (lane < 16) max1[part * 16 + r1] = mx;
-        __syncthreads();
-        mx = max1[r1];
-#pragma unroll
-        for (int pp = 1; pp < 16; ++pp) mx = fmaxf(mx, max1[pp * 16 + r1]);
-        const float mb = mx * 1.4426950408889634f;
-        float sum = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) { tv[i] = umma::ex2_approx(fmaf(tv[i], 1.4426950408889634f, -mb)); sum += tv[i]; }
-        if (lane < 16) {
-          uint8_t* prow = smem + SM_P + qrow * 16;
-#pragma unroll
-          for (int i = 0; i < 9; ++i) {
-            const int key = key0 + i;
-            *reinterpret_cast<__nv_bfloat16*>(prow + (key >> 3) * LBO_X + (key & 7) * 2) = __float2bfloat16(tv[i]);
-          }
-          sum1[part * 16 + r1] = sum;
         }
       }
       umma::fence_proxy_async();
