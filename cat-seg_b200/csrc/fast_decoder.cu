@@ -314,7 +314,6 @@ __global__ void __launch_bounds__(BAND_THREADS, 2) band_conv_kernel(BandConvPara
       if (!issuer) {
         // ---- epilogue: thread = padded raster row; the two warp sets take alternate tiles.  The additive map
         //      of the first tile is fetched BEFORE waiting for the accumulators (hides the global latency).
-        float e_pre[UPS ? 32 : 1];     // additive map (composed stages only): first 32 channels of this warp set's first tile
         auto tile_geom = [&](int t, bool& valid, long long& opix) {
           const int pr = C::P0 + t * 128 + q4 * 32 + lane;
           const int yl = pr / C::PW - 1, xl = pr % C::PW - 1;
@@ -323,18 +322,6 @@ __global__ void __launch_bounds__(BAND_THREADS, 2) band_conv_kernel(BandConvPara
           if (UPS) { Yo = 2 * Yo + pa; Xo = 2 * Xo + pb; }
           opix = (long long)Yo * C::WOUT + Xo;
         };
-        if constexpr (UPS) {
-          if (tgrp < C::NTILES) {
-            bool valid; long long opix;
-            tile_geom(tgrp, valid, opix);
-            const float* e = p.emap + ((long long)b * (C::WOUT * C::WOUT) + (valid ? opix : 0)) * NREAL;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float4 e4 = ld4(e + i);
-              e_pre[i] = e4.x; e_pre[i + 1] = e4.y; e_pre[i + 2] = e4.z; e_pre[i + 3] = e4.w;
-            }
-          }
-        }
         umma::mbar_wait(&bar_acc[set], ph_acc[set]);
         umma::fence_after_sync();
         BPH(1);
@@ -353,19 +340,18 @@ __global__ void __launch_bounds__(BAND_THREADS, 2) band_conv_kernel(BandConvPara
 #pragma unroll
             for (int c0 = 0; c0 < NREAL; c0 += 32) {
               float v[32];
+              float4 e4[UPS ? 8 : 1];                          // additive map (composed stages): issued before the TMEM load
+              if constexpr (UPS) {
+                const float* e = p.emap + ((long long)b * (C::WOUT * C::WOUT) + (valid ? opix : 0)) * NREAL + c0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) e4[i] = ld4(e + 4 * i);
+              }
               umma::tmem_ld32(acc_addr + t * NOUT + c0, v);
               if (valid) {
                 if constexpr (UPS) {
-                  if (t == tgrp && c0 == 0) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] += e_pre[i];
-                  } else {
-                    const float* e = p.emap + ((long long)b * (C::WOUT * C::WOUT) + opix) * NREAL + c0;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                      float4 e4 = ld4(e + i);
-                      v[i] += e4.x; v[i + 1] += e4.y; v[i + 2] += e4.z; v[i + 3] += e4.w;
-                    }
+                  for (int i = 0; i < 8; ++i) {
+                    v[4 * i] += e4[i].x; v[4 * i + 1] += e4[i].y; v[4 * i + 2] += e4[i].z; v[4 * i + 3] += e4[i].w;
                   }
                 }
 #pragma unroll
