@@ -13,6 +13,9 @@
 //     epilogue are consumed as MN-major A and B operands (the ones column yields Ksum);
 //   * the state is applied as phi(q) . Bstate with Bstate = [blockdiag(KV_h) | Ksum_h columns] (N = 144).
 // Padding classes (T < pad_len) enter as the constant pad_state.
+#include <cstdio>
+#include <cstdlib>
+
 #include "fast_common.cuh"
 #include "internal.h"
 
@@ -208,7 +211,7 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
 __global__ void __launch_bounds__(512, 1)
 class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, const __nv_bfloat16* __restrict__ timg,
                         const float* __restrict__ state, const float* __restrict__ pad_state, int B, int Te, int npix,
-                        int S, int out_mode, ClassFastW w) {
+                        int S, int out_mode, ClassFastW w, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   float* s_g1 = reinterpret_cast<float*>(smem + AP_PAR);
   float* s_be1 = s_g1 + 128;
@@ -286,6 +289,8 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
   }
   uint32_t ph_g = 0, ph_acc = 0;
   const float fS = (float)S;
+  long long t_last = clock64(), pacc0 = 0, pacc1 = 0, pacc2 = 0, pacc3 = 0, pacc4 = 0, pacc5 = 0, pacc6 = 0, pacc7 = 0, nit_dbg = 0;
+#define CPH(i) do { if (dbg != nullptr && blockIdx.x == 0 && tid == 0) { long long _t = clock64(); pacc##i += _t - t_last; t_last = _t; } } while (0)
 
   for (long long it = blockIdx.x; it < nitems; it += gridDim.x) {
     const int tl = (int)(it % ntile);
@@ -295,6 +300,17 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
     const int nvalid = Te - t0 < 128 ? Te - t0 : 128;
     const long long rstride = (long long)npix * 128;
     const long long row0off = (((long long)b * Te + t0) * npix + pix) * 128;
+    {   // the next item's token rows (one 512-byte row per class, 295 KiB apart) and state are prefetched into L2 meanwhile
+      const long long itn = it + gridDim.x;
+      if (itn < nitems) {
+        const int tln = (int)(itn % ntile);
+        const long long bpn = itn / ntile;
+        const int bn = (int)(bpn / npix), pn = (int)(bpn % npix);
+        const int nv = Te - tln * 128 < 128 ? Te - tln * 128 : 128;
+        if (tid < nv * 4) umma::prefetch_l2(X + (((long long)bn * Te + tln * 128 + (tid >> 2)) * npix + pn) * 128 + (tid & 3) * 32);
+        if (tid < 132) umma::prefetch_l2(state + bpn * kStateFloats + tid * 32);
+      }
+    }
     if (issuer) {
       if (umma::elect_one()) {
         umma::mbar_expect_tx(bar_g, WIMG_BYTES);
@@ -302,18 +318,22 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
       }
       __syncwarp();
     }
-    ln_rows_to_tile(X + row0off, rstride, nvalid, smem + AP_XN, s_g1, s_be1, warp, 16, lane);
-    // ---- Bstate [128 k x 144 n] (MN-major, 18 n-groups): thread k = (h, d) writes its whole row
+    // ---- Bstate [128 k x 144 n] (MN-major, 18 n-groups): thread k = (h, d) writes its whole row; its state loads are
+    //      issued before the LayerNorm prologue so that their latency is covered by it
+    float kv[32];
+    float ks = 0.0f;
     if (tid < 128) {
-      const int h = tid >> 5;
       const float* sp = state + bp * kStateFloats;
-      float kv[32];
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
         float4 a = ld4(sp + tid * 32 + i), pz = ld4(pad_state + tid * 32 + i);
         kv[i] = a.x + pz.x; kv[i + 1] = a.y + pz.y; kv[i + 2] = a.z + pz.z; kv[i + 3] = a.w + pz.w;
       }
-      const float ks = sp[4096 + tid] + pad_state[4096 + tid];
+      ks = sp[4096 + tid] + pad_state[4096 + tid];
+    }
+    ln_rows_to_tile(X + row0off, rstride, nvalid, smem + AP_XN, s_g1, s_be1, warp, 16, lane);
+    if (tid < 128) {
+      const int h = tid >> 5;
       const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
       for (int gq = 0; gq < 16; ++gq) {
@@ -334,6 +354,7 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
     umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
+    CPH(0);
     // ---- q = [xn | g] [Wq_x | Wq_g]^T
     if (issuer) {
       umma::fence_after_sync();
@@ -346,6 +367,7 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
     ph_g ^= 1;
     umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
     umma::fence_after_sync();
+    CPH(1);
     // ---- phi(q) -> Q image (thread = (row, 32-column quarter))
     {
       float v[32];
@@ -362,6 +384,7 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
     umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
+    CPH(2);
     // ---- [num | den] = phi(q) Bstate
     if (issuer) {
       umma::fence_after_sync();
@@ -375,6 +398,7 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
     }
     umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
     umma::fence_after_sync();
+    CPH(3);
     // ---- x tile -> staging (warp per row, coalesced; phi(q) and Bstate are dead now)
     {
       float4 xv[8];
@@ -387,6 +411,7 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
       for (int i = 0; i < 8; ++i) st4(stage + (warp * 8 + i) * STG_LD + lane * 4, xv[i]);
     }
     __syncthreads();
+    CPH(4);
     // ---- x1 = x + num/(den+eps)*S ; z -> staging ; LN2 statistics
     float x1[32];
     const bool live = row < nvalid;
@@ -434,6 +459,7 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
     umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
+    CPH(5);
     // ---- MLP 128 -> 512 (ReLU) -> 128, hidden chunks of 128 (H reuses the q columns)
 #pragma unroll 1
     for (int j = 0; j < 4; ++j) {
@@ -469,6 +495,7 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
       umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;     // h (and H) may be overwritten by the next chunk
       umma::fence_after_sync();
     }
+    CPH(6);
     // ---- out = z + (Y + b2): finish in the staging tile, then one coalesced store per row
     {
       float v[32];
@@ -491,6 +518,12 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
       if (r < nvalid) st4(Xout + row0off + (long long)r * rstride + lane * 4, ld4(stage + r * STG_LD + lane * 4));
     }
     __syncthreads();      // the staging tile (phi(q) / Bstate buffers) is rebuilt by the next item
+    CPH(7);
+    ++nit_dbg;
+  }
+#undef CPH
+  if (dbg != nullptr && blockIdx.x == 0 && tid == 0) {
+    dbg[0] = pacc0; dbg[1] = pacc1; dbg[2] = pacc2; dbg[3] = pacc3; dbg[4] = pacc4; dbg[5] = pacc5; dbg[6] = pacc6; dbg[7] = pacc7; dbg[8] = nit_dbg;
   }
   if (warp == 0) umma::tmem_dealloc<512>(tm);
 }
@@ -521,7 +554,23 @@ cudaError_t launch_class_apply_fast(const float* X, float* Xout, const __nv_bflo
   }
   long long n = (long long)B * npix * ((Te + 127) / 128);
   int grid = (int)(n < num_sms ? n : num_sms);
-  class_apply_fast_kernel<<<grid, 512, AP_SMEM, st>>>(X, Xout, timg, state, pad_state, B, Te, npix, S, out_mode, w);
+  static long long* dbg = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) {
+    const char* e = getenv("CATSEG_PHASE_TIMING");
+    dbg_on = (e && e[0] == '1') ? 1 : 0;
+    if (dbg_on) { cudaMalloc(&dbg, 16 * sizeof(long long)); cudaMemset(dbg, 0, 16 * sizeof(long long)); }
+  }
+  class_apply_fast_kernel<<<grid, 512, AP_SMEM, st>>>(X, Xout, timg, state, pad_state, B, Te, npix, S, out_mode, w, dbg_on ? dbg : nullptr);
+  if (dbg_on) {
+    long long hb[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hb, dbg, sizeof(hb), cudaMemcpyDeviceToHost);
+    double nn = hb[8] > 0 ? (double)hb[8] : 1.0;
+    fprintf(stderr, "[class_apply phases, cycles/item(128 classes of one pixel) over %lld items] LN1+Bstate %.0f | q-mma %.0f | phi(q) %.0f | apply-mma %.0f "
+            "| x staging %.0f | x1+LN2 %.0f | MLP (4 chunks) %.0f | out %.0f\n", hb[8], hb[0] / nn, hb[1] / nn, hb[2] / nn, hb[3] / nn, hb[4] / nn,
+            hb[5] / nn, hb[6] / nn, hb[7] / nn);
+  }
   return cudaGetLastError();
 }
 
