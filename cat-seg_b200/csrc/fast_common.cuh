@@ -71,22 +71,20 @@ __device__ __forceinline__ void ln_rows_to_tile(const float* __restrict__ src, l
 }
 
 // erf-GELU for the bf16 path.  The result is rounded to bf16 (relative 2^-9) before the next MMA, so erf only
-// needs ~1e-4 absolute accuracy: odd minimax polynomial erf(z) ~ z P(z^2) on |z| <= 3 (clamped beyond, where
-// |1 - erf| < 2.3e-5); max |erf error| 1.9e-4, GELU error <= 1.4e-4 for |x| < 2.5.  13 FMA-pipe instructions,
-// no MUFU (the exact-erf epilogue was the bottleneck of the FFN kernel: ncu, profiles/r01_*).
+// needs ~1e-4 absolute accuracy: odd minimax polynomial directly in x, erf(x/sqrt 2) ~ x Q(x^2) on |x| <= 3.8
+// (clamped beyond, where 1 - erf < 1.5e-4); max |erf error| 1.3e-4, GELU error <= 2.5e-4 (1.6e-4 for |x| < 2.5).
+// 12 FMA-pipe instructions, no MUFU (the FFN epilogue is issue bound: ncu, profiles/README.md).
 __device__ __forceinline__ float gelu_fast(float x) {
-  float z = x * 0.70710678118654752440f;
-  float zc = fminf(fmaxf(z, -3.0f), 3.0f);
-  float t = zc * zc;
-  float p = fmaf(-4.971512340e-07f, t, 2.025256799e-05f);
-  p = fmaf(p, t, -3.563589707e-04f);
-  p = fmaf(p, t, 3.605931997e-03f);
-  p = fmaf(p, t, -2.374373749e-02f);
-  p = fmaf(p, t, 1.097183898e-01f);
-  p = fmaf(p, t, -3.748996854e-01f);
-  p = fmaf(p, t, 1.128298283e+00f);
-  float h = 0.5f * x;
-  return fmaf(h, zc * p, h);
+  const float xc = fminf(fmaxf(x, -3.8f), 3.8f);
+  const float t = xc * xc;
+  float q = fmaf(7.331543372e-08f, t, -4.544918738e-06f);
+  q = fmaf(q, t, 1.213695141e-04f);
+  q = fmaf(q, t, -1.863094512e-03f);
+  q = fmaf(q, t, 1.863326877e-02f);
+  q = fmaf(q, t, -1.314395666e-01f);
+  q = fmaf(q, t, 7.973535061e-01f);
+  const float h = 0.5f * x;
+  return fmaf(h, xc * q, h);
 }
 
 // fp32 staging tile [128 rows][128 cols] with a 132-float row stride: conflict-free both for "thread = row"
