@@ -61,7 +61,8 @@ struct BandCfg {
   static constexpr uint32_t WBYTES = NOUT * CIN * 2, LBO_WT = NOUT * 16;
   // two CTAs per SM (half-height bands, <= 113 KiB and <= 256 TMEM columns each): one CTA's staging / epilogue
   // overlaps the other's MMAs.  Small weight sets stay resident, larger ones stream through a ring.
-  static constexpr bool RESIDENT = NIMG * WBYTES <= 24 * 1024;
+  // (the whole weight set may stay in shared memory when, together with the band image, it fits half an SM)
+  static constexpr bool RESIDENT = NIMG * WBYTES <= 24 * 1024 || IMG_BYTES + NIMG * WBYTES <= 108 * 1024;
   // streaming ring: 48 KiB deep, so that the prefetch distance (in MMA time) exceeds the ~1 us L2->SMEM latency
   static constexpr int NSLOT = RESIDENT ? NIMG : (int)(48 * 1024 / WBYTES);
   static constexpr int NB = WIN_ / BR;                 // bands per slice
@@ -572,7 +573,7 @@ size_t decoder_fast_scratch_bytes(const DecoderDims& d, int B, int chunk) {
   size_t b = 0;
   b += (size_t)B * (4 * hw * d.D1 + 16 * hw * d.D2) * 4;                 // E1, E2
   b += (size_t)chunk * (2 * 4 * hw * d.D1 + 2 * 16 * hw * d.D2) * 2;     // c1a c1b c2a c2b (bf16)
-  b += (size_t)chunk * (4 * 4 + 8 * 4 + 8 * 2 + 16 * 2) * 2 * 4 + 4096; // band statistics
+  b += (size_t)chunk * (4 * 4 + 8 * 4 + 12 * 2 + 16 * 2) * 2 * 4 + 4096; // band statistics
   return (b + 255) / 256 * 256;
 }
 
@@ -594,7 +595,7 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
   __nv_bfloat16* c2b = reinterpret_cast<__nv_bfloat16*>(take((size_t)chunk * 16 * hw * d.D2 * 2));
   float* s1a = reinterpret_cast<float*>(take((size_t)chunk * 4 * 4 * 2 * 4));    // NB=4 G=4
   float* s1b = reinterpret_cast<float*>(take((size_t)chunk * 8 * 4 * 2 * 4));    // NB=8 G=4
-  float* s2a = reinterpret_cast<float*>(take((size_t)chunk * 8 * 2 * 2 * 4));    // NB=8 G=2
+  float* s2a = reinterpret_cast<float*>(take((size_t)chunk * 12 * 2 * 2 * 4));   // NB=12 G=2
   float* s2b = reinterpret_cast<float*>(take((size_t)chunk * 16 * 2 * 2 * 4));   // NB=16 G=2
 
   {
@@ -618,9 +619,9 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
     // D3: c1b -> c2a (96^2 x 32), composed
     p.in = c1b; p.in_stats = s1b; p.nb_in = 8; p.gamma = wx.gn1b_g; p.beta = wx.gn1b_b;
     p.wimg = w.w3; p.emap = E2; p.out = c2a; p.out_stats = s2a;
-    CKF((launch_band<64, 32, 32, true, false, 48, 6, false>(p, num_sms, st)));
+    CKF((launch_band<64, 32, 32, true, false, 48, 4, false>(p, num_sms, st)));   // 4-row bands: the 64 KiB weight set stays resident
     // D4: c2a -> c2b, 3x3 32 -> 32
-    p.in = c2a; p.in_stats = s2a; p.nb_in = 8; p.in_count = (float)(16 * hw * 16); p.gamma = wx.gn2a_g; p.beta = wx.gn2a_b;
+    p.in = c2a; p.in_stats = s2a; p.nb_in = 12; p.in_count = (float)(16 * hw * 16); p.gamma = wx.gn2a_g; p.beta = wx.gn2a_b;
     p.wimg = w.w4; p.emap = nullptr; p.out = c2b; p.out_stats = s2b;
     CKF((launch_band<32, 32, 32, false, false, 96, 6, false>(p, num_sms, st)));
     // D5: head 3x3 32 -> 1 (+ bias), scattered to logits[b][class]
