@@ -72,7 +72,7 @@ struct BandCfg {
   static constexpr uint32_t SM_SC = SM_W + NSLOT * WBYTES;            // scale[CIN], shift[CIN]
   static constexpr uint32_t SM_ST = SM_SC + 2 * CIN * 4;              // [8 warps][GOUT][2]
   static constexpr uint32_t SM_BAR = (SM_ST + 8 * GOUT * 2 * 4 + 15) / 16 * 16;
-  static constexpr uint32_t SMEM = SM_BAR + (2 * NSLOT + 3) * 8 + 16;
+  static constexpr uint32_t SMEM = SM_BAR + (2 * NSLOT + 17) * 8 + 16;   // ring barriers + [2 sets][8 tiles] accumulator barriers
   static constexpr uint32_t IDESC = umma::make_idesc_bf16(128, NOUT);
   static_assert(NTILES * NOUT <= 256, "TMEM columns (two CTAs per SM)");
   static_assert(SMEM <= 113 * 1024, "shared memory budget (two CTAs per SM)");
@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(BAND_THREADS, 2) band_conv_kernel(BandConvPara
   float* s_part = reinterpret_cast<float*>(smem + C::SM_ST);
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + C::SM_BAR);   // [NSLOT]
   uint64_t* bar_empty = bar_full + C::NSLOT;                             // [NSLOT]
-  uint64_t* bar_acc = bar_empty + C::NSLOT;                              // [2] accumulator sets
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 2);
+  uint64_t* bar_acc = bar_empty + C::NSLOT;                              // [2 accumulator sets][8]: one barrier per M tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 16);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q4 = warp & 3, tgrp = (warp >> 2) & 1;
   const bool issuer = __shfl_sync(0xffffffffu, warp, 0) == 8;           // warp-uniform role
   constexpr int ACC_COLS = C::NTILES * NOUT;
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(BAND_THREADS, 2) band_conv_kernel(BandConvPara
   const long long total_loads = C::RESIDENT ? 1 : mine * C::NIMG;
 
   if (tid == 0) {
-    for (int i = 0; i < 2 * C::NSLOT + 2; ++i) umma::mbar_init(&bar_full[i], 1);
+    for (int i = 0; i < 2 * C::NSLOT + 16; ++i) umma::mbar_init(&bar_full[i], 1);
     umma::mbar_fence_init();
   }
   if (warp == 0) umma::tmem_alloc<256>(tmem_slot);
@@ -150,6 +150,30 @@ __global__ void __launch_bounds__(BAND_THREADS, 2) band_conv_kernel(BandConvPara
     const int pa = pg >> 1, pb = pg & 1;
     if (C::RESIDENT && !w_ready) { umma::mbar_wait(&bar_full[0], 0); w_ready = true; }
     const uint64_t a_desc0 = umma::make_smem_desc(sb, C::LBO_I, 128);
+    if constexpr (C::RESIDENT) {
+      // resident weights: tile-outer order with one commit per M tile, so the epilogue of tile t runs under the MMAs of
+      // the tiles behind it
+      if (umma::elect_one()) {
+#pragma unroll 1
+        for (int t = 0; t < C::NTILES; ++t) {
+#pragma unroll 1
+          for (int tap = 0; tap < C::NTAP; ++tap) {
+            int off;
+            if (UPS) off = ((tap >> 1) + pa - 1) * C::PW + ((tap & 1) + pb - 1);
+            else off = (tap / 3 - 1) * C::PW + (tap % 3 - 1);
+            const uint64_t b_desc = umma::make_smem_desc(sb + C::SM_W + (uint32_t)(pg * C::NTAP + tap) * C::WBYTES, C::LBO_WT, 128);
+            const uint64_t a_tile = a_desc0 + (uint64_t)(uint32_t)(C::P0 + off + t * 128);
+#pragma unroll
+            for (int k = 0; k < C::KSTEPS; ++k)
+              umma::mma_bf16_ss(tm + set * ACC_COLS + t * NOUT, a_tile + (uint64_t)(k * 2 * (C::LBO_I >> 4)),
+                                b_desc + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC, (tap > 0 || k > 0) ? 1u : 0u);
+          }
+          umma::mma_commit(&bar_acc[set * 8 + t]);
+        }
+      }
+      __syncwarp();
+      return;
+    }
 #pragma unroll 1
     for (int tap = 0; tap < C::NTAP; ++tap) {
       int off;
@@ -189,7 +213,10 @@ __global__ void __launch_bounds__(BAND_THREADS, 2) band_conv_kernel(BandConvPara
         ++nimg;
       }
     }
-    if (umma::elect_one()) umma::mma_commit(&bar_acc[set]);
+    if (umma::elect_one()) {
+#pragma unroll
+      for (int t = 0; t < C::NTILES; ++t) umma::mma_commit(&bar_acc[set * 8 + t]);
+    }
     __syncwarp();
   };
 
@@ -323,11 +350,11 @@ __global__ void __launch_bounds__(BAND_THREADS, 2) band_conv_kernel(BandConvPara
           if (UPS) { Yo = 2 * Yo + pa; Xo = 2 * Xo + pb; }
           opix = (long long)Yo * C::WOUT + Xo;
         };
-        umma::mbar_wait(&bar_acc[set], ph_acc[set]);
-        umma::fence_after_sync();
-        BPH(1);
 #pragma unroll 1
         for (int t = tgrp; t < C::NTILES; t += 2) {
+          umma::mbar_wait(&bar_acc[set * 8 + t], ph_acc[set]);
+          umma::fence_after_sync();
+          if (t == tgrp) BPH(1);
           bool valid; long long opix;
           tile_geom(t, valid, opix);
           if constexpr (HEAD) {
