@@ -105,13 +105,162 @@ __global__ void stitch_kernel(const float* __restrict__ win_logits, int T, int S
   if (labels_out) labels_out[i] = best_t;
 }
 
+// Tiled version (the one launched): a CTA owns 16x16 output pixels and walks the classes.  Per class it first
+// evaluates the global-view probabilities on the patch of the `kernel` grid its pixels can touch (phase A), then the
+// stitched value on the patch of the out_res grid they can touch (phase B: covering tiles + bilinear of the phase-A
+// patch), then each thread interpolates its own output pixel from that patch (phase C).  Every value is computed with
+// the same fp32 expression order as stitch_kernel above; what changes is that the four global-view samples per
+// stitched value (and, when postprocess resizes, the four stitched values per output pixel) are shared through shared
+// memory instead of being recomputed by every thread: ~2 instead of 8 sigmoid(bilinear) evaluations per pixel and class.
+constexpr int ST_TILE = 16, ST_RMAX = 36, ST_GMAX = 26, ST_MAXT = 4;
+
+// sigmoid on the MUFU pipe: ex2.approx + rcp.approx.  |error| <= ~1e-7 on a probability (relative 3e-7 on exp for
+// |x| <= 10, damped by p(1-p) <= 1/4); the parity tolerance on stitched probabilities is 2e-6 (tests/test_gpu_parity.py).
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+struct LerpE { int o0, o1; float l0, l1; };      // like Lerp, with the row indices pre-multiplied where useful
+
+__global__ void __launch_bounds__(ST_TILE * ST_TILE)
+stitch_tiled_kernel(const float* __restrict__ win_logits, int T, int S, int kernel, int stride, int out_res, int ntile,
+                    int height, int width, float* __restrict__ probs_out, int32_t* __restrict__ labels_out) {
+  __shared__ float s_g[ST_GMAX * ST_GMAX];
+  __shared__ float s_v[ST_RMAX * ST_RMAX];
+  // class-independent interpolation tables (built once per CTA)
+  __shared__ LerpE s_gy[ST_GMAX], s_gx[ST_GMAX];                     // kernel-grid patch row/col -> source rows (x S) / cols
+  __shared__ LerpE s_ty[ST_RMAX][ST_MAXT], s_tx[ST_RMAX][ST_MAXT];   // out_res patch row/col x tile -> source rows (x S) / cols; o0 < 0: not covered
+  __shared__ LerpE s_vy[ST_RMAX], s_vx[ST_RMAX];                     // out_res patch row/col -> rows (x GX) / cols of the kernel-grid patch
+  const int tid = threadIdx.x, lx = tid % ST_TILE, ly = tid / ST_TILE;
+  const int oy0 = blockIdx.y * ST_TILE, ox0 = blockIdx.x * ST_TILE;
+  const int oy1 = min(oy0 + ST_TILE, height) - 1, ox1 = min(ox0 + ST_TILE, width) - 1;
+  const int oy = oy0 + ly, ox = ox0 + lx;
+  const bool live = oy < height && ox < width;
+  const bool identity = (height == out_res && width == out_res);
+  const float sc_o_y = (float)out_res / (float)height, sc_o_x = (float)out_res / (float)width;
+  // patch of the out_res grid touched by this CTA (bilinear source indices are monotone in the destination index)
+  int Ya, Yb, Xa, Xb;
+  if (identity) { Ya = oy0; Yb = oy1; Xa = ox0; Xb = ox1; }
+  else {
+    Ya = make_lerp(oy0, sc_o_y, out_res).i0; Yb = make_lerp(oy1, sc_o_y, out_res).i1;
+    Xa = make_lerp(ox0, sc_o_x, out_res).i0; Xb = make_lerp(ox1, sc_o_x, out_res).i1;
+  }
+  const int RY = Yb - Ya + 1, RX = Xb - Xa + 1;
+  // patch of the kernel grid touched by the global view of that patch
+  const float sc_g = (float)kernel / (float)out_res;
+  const int Ga = make_lerp(Ya, sc_g, kernel).i0, Gb = make_lerp(Yb, sc_g, kernel).i1;
+  const int Ha = make_lerp(Xa, sc_g, kernel).i0, Hb = make_lerp(Xb, sc_g, kernel).i1;
+  const int GY = Gb - Ga + 1, GX = Hb - Ha + 1;
+  const long long plane = (long long)S * S;
+  const float sc_win = (float)S / (float)kernel;
+  for (int i = tid; i < GY; i += ST_TILE * ST_TILE) { Lerp a = make_lerp(Ga + i, sc_win, S); s_gy[i] = LerpE{a.i0 * S, a.i1 * S, a.l0, a.l1}; }
+  for (int i = tid; i < GX; i += ST_TILE * ST_TILE) { Lerp a = make_lerp(Ha + i, sc_win, S); s_gx[i] = LerpE{a.i0, a.i1, a.l0, a.l1}; }
+  for (int i = tid; i < RY * ntile; i += ST_TILE * ST_TILE) {
+    const int r = i / ntile, ty = i % ntile, ky = Ya + r - ty * stride;
+    LerpE e{-1, -1, 0.f, 0.f};
+    if (ky >= 0 && ky < kernel) { Lerp a = make_lerp(ky, sc_win, S); e = LerpE{a.i0 * S, a.i1 * S, a.l0, a.l1}; }
+    s_ty[r][ty] = e;
+  }
+  for (int i = tid; i < RX * ntile; i += ST_TILE * ST_TILE) {
+    const int r = i / ntile, tx = i % ntile, kx = Xa + r - tx * stride;
+    LerpE e{-1, -1, 0.f, 0.f};
+    if (kx >= 0 && kx < kernel) { Lerp a = make_lerp(kx, sc_win, S); e = LerpE{a.i0, a.i1, a.l0, a.l1}; }
+    s_tx[r][tx] = e;
+  }
+  for (int i = tid; i < RY; i += ST_TILE * ST_TILE) { Lerp a = make_lerp(Ya + i, sc_g, kernel); s_vy[i] = LerpE{(a.i0 - Ga) * GX, (a.i1 - Ga) * GX, a.l0, a.l1}; }
+  for (int i = tid; i < RX; i += ST_TILE * ST_TILE) { Lerp a = make_lerp(Xa + i, sc_g, kernel); s_vx[i] = LerpE{a.i0 - Ha, a.i1 - Ha, a.l0, a.l1}; }
+  Lerp pa, pb;                                   // this thread's output pixel on the out_res grid
+  if (live && !identity) { pa = make_lerp(oy, sc_o_y, out_res); pb = make_lerp(ox, sc_o_x, out_res); }
+  __syncthreads();
+  auto sample = [&](const float* __restrict__ pl, const LerpE& a, const LerpE& b) {
+    const float v00 = __ldg(pl + a.o0 + b.o0), v01 = __ldg(pl + a.o0 + b.o1);
+    const float v10 = __ldg(pl + a.o1 + b.o0), v11 = __ldg(pl + a.o1 + b.o1);
+    return sigmoid_fast(a.l0 * (b.l0 * v00 + b.l1 * v01) + a.l1 * (b.l0 * v10 + b.l1 * v11));
+  };
+  // per-thread work lists (class independent): <= 3 phase-A samples, <= 6 phase-B patch pixels
+  constexpr int NA = (ST_GMAX * ST_GMAX + ST_TILE * ST_TILE - 1) / (ST_TILE * ST_TILE);
+  constexpr int NB = (ST_RMAX * ST_RMAX + ST_TILE * ST_TILE - 1) / (ST_TILE * ST_TILE);
+  int ea[NA], eb[NB];
+  float einv[NB];                                // 1/cnt when the tile count is a power of two (exact), else -cnt
+#pragma unroll
+  for (int k = 0; k < NA; ++k) { const int i = tid + k * ST_TILE * ST_TILE; ea[k] = i < GY * GX ? ((i / GX) << 8 | (i % GX)) : -1; }
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    const int i = tid + k * ST_TILE * ST_TILE;
+    eb[k] = -1; einv[k] = 1.0f;
+    if (i < RY * RX) {
+      const int ry = i / RX, rx = i % RX;
+      int cy = 0, cx = 0;
+      for (int ty = 0; ty < ntile; ++ty) cy += s_ty[ry][ty].o0 >= 0;
+      for (int tx = 0; tx < ntile; ++tx) cx += s_tx[rx][tx].o0 >= 0;
+      const int cnt = cy * cx;
+      eb[k] = ry << 8 | rx;
+      einv[k] = (cnt & (cnt - 1)) == 0 ? 1.0f / (float)cnt : -(float)cnt;
+    }
+  }
+  float best = -INFINITY;
+  int best_t = 0;
+  for (int t = 0; t < T; ++t) {
+    // ---- phase A: global view on the kernel grid
+    const float* gp = win_logits + ((long long)(ntile * ntile) * T + t) * plane;
+#pragma unroll
+    for (int k = 0; k < NA; ++k)
+      if (ea[k] >= 0) s_g[tid + k * ST_TILE * ST_TILE] = sample(gp, s_gy[ea[k] >> 8], s_gx[ea[k] & 255]);
+    __syncthreads();
+    // ---- phase B: stitched value on the out_res grid
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      if (eb[k] < 0) continue;
+      const int ry = eb[k] >> 8, rx = eb[k] & 255;
+      float acc = 0.0f;
+      for (int ty = ntile - 1; ty >= 0; --ty) {
+        const LerpE a = s_ty[ry][ty];
+        if (a.o0 < 0) continue;
+        for (int tx = ntile - 1; tx >= 0; --tx) {
+          const LerpE b = s_tx[rx][tx];
+          if (b.o0 < 0) continue;
+          acc += sample(win_logits + ((long long)(ty * ntile + tx) * T + t) * plane, a, b);
+        }
+      }
+      acc = einv[k] > 0.0f ? acc * einv[k] : acc / -einv[k];
+      const LerpE a = s_vy[ry], b = s_vx[rx];
+      const float g = a.l0 * (b.l0 * s_g[a.o0 + b.o0] + b.l1 * s_g[a.o0 + b.o1]) + a.l1 * (b.l0 * s_g[a.o1 + b.o0] + b.l1 * s_g[a.o1 + b.o1]);
+      s_v[tid + k * ST_TILE * ST_TILE] = (acc + g) * 0.5f;
+    }
+    __syncthreads();
+    // ---- phase C: this thread's output pixel
+    if (live) {
+      float v;
+      if (identity) {
+        v = s_v[(oy - Ya) * RX + (ox - Xa)];
+      } else {
+        const float* v0 = s_v + (pa.i0 - Ya) * RX - Xa;
+        const float* v1 = s_v + (pa.i1 - Ya) * RX - Xa;
+        v = pa.l0 * (pb.l0 * v0[pb.i0] + pb.l1 * v0[pb.i1]) + pa.l1 * (pb.l0 * v1[pb.i0] + pb.l1 * v1[pb.i1]);
+      }
+      if (probs_out) probs_out[(long long)t * height * width + (long long)oy * width + ox] = v;
+      if (v > best) { best = v; best_t = t; }
+    }
+  }
+  if (live && labels_out) labels_out[(long long)oy * width + ox] = best_t;
+}
+
 cudaError_t launch_stitch(const float* win_logits, int T, int S, int kernel, int stride, int out_res, int height,
                           int width, float* probs_out, int32_t* labels_out, cudaStream_t st) {
   if (kernel > out_res || stride <= 0 || (out_res - kernel) % stride != 0) return cudaErrorInvalidValue;
   int ntile = (out_res - kernel) / stride + 1;
   long long n = (long long)height * width;
-  stitch_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(win_logits, T, S, kernel, stride, out_res, ntile,
-                                                             height, width, probs_out, labels_out);
+  // patch bounds of the tiled kernel: 16 output pixels span at most 16*scale + 2 source pixels per axis
+  const double so = (double)out_res / (double)(height < width ? height : width);
+  const bool identity = height == out_res && width == out_res;
+  const int rmax = identity ? ST_TILE : (int)(ST_TILE * so) + 3;
+  const int gmax = (int)(rmax * (double)kernel / (double)out_res) + 3;
+  if (rmax <= ST_RMAX && gmax <= ST_GMAX && ntile <= ST_MAXT) {
+    dim3 grid((unsigned)((width + ST_TILE - 1) / ST_TILE), (unsigned)((height + ST_TILE - 1) / ST_TILE));
+    stitch_tiled_kernel<<<grid, ST_TILE * ST_TILE, 0, st>>>(win_logits, T, S, kernel, stride, out_res, ntile, height, width,
+                                                           probs_out, labels_out);
+  } else {                                       // extreme down-scaling: one thread per pixel recomputes everything
+    stitch_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(win_logits, T, S, kernel, stride, out_res, ntile,
+                                                               height, width, probs_out, labels_out);
+  }
   return cudaGetLastError();
 }
 
