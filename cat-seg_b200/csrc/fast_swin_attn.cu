@@ -155,7 +155,6 @@ swin_attn_fast_kernel(float* __restrict__ X, const __nv_bfloat16* __restrict__ a
     __syncwarp();
   }
 
-  const int getenv_noprefetch = (dbg != nullptr && dbg[14] != 0) ? 1 : 0;   // experiment switch (phase-timing mode only)
   long long t_last = clock64();
   long long pacc0 = 0, pacc1 = 0, pacc2 = 0, pacc3 = 0, pacc4 = 0, pacc5 = 0, pacc6 = 0, pacc7 = 0, nwin_dbg = 0;
   long long nwin_done = 0;
@@ -216,7 +215,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const __nv_bfloat16* __restrict__ a
         const int nsl = (int)(wn >> 2), nwy = (int)((wn >> 1) & 1), nwx = (int)(wn & 1), r = tid >> 2;
         const int sy = nwy * WIN + r / WIN, sx = nwx * WIN + r % WIN;
         const int pix = ((sy + shift) % GRID) * GRID + (sx + shift) % GRID;
-        if (getenv_noprefetch == 0) umma::prefetch_l2(X + ((long long)nsl * (GRID * GRID) + pix) * 128 + (tid & 3) * 32);
+        umma::prefetch_l2(X + ((long long)nsl * (GRID * GRID) + pix) * 128 + (tid & 3) * 32);
       }
     }
     {
@@ -486,7 +485,6 @@ cudaError_t launch_swin_attn_fast(float* X, const __nv_bfloat16* agw, int nslice
     dbg_on = (e && e[0] == '1') ? 1 : 0;
     if (dbg_on) { cudaMalloc(&dbg, 16 * sizeof(long long)); cudaMemset(dbg, 0, 16 * sizeof(long long)); }
   }
-  if (dbg_on) { long long np = getenv("CATSEG_NOPREFETCH") ? 1 : 0; cudaMemcpyAsync(dbg + 14, &np, sizeof(np), cudaMemcpyHostToDevice, st); cudaStreamSynchronize(st); }
   swin_attn_fast_kernel<<<grid, SA_THREADS, SA_SMEM, st>>>(X, agw, nwin, Te, shift, w, dbg_on ? dbg : nullptr);
   if (dbg_on) {
     long long hbuf[16];
