@@ -67,3 +67,31 @@ def test_fast_prep_stages(case):
         if n.startswith("dec_guidance"):
             r = r.permute(0, 2, 3, 1).reshape(got.shape)            # oracle keeps NCHW, kernels NHWC
         assert rel_l2(got, r) <= 1e-2, (n, rel_l2(got, r))
+
+
+def test_fast_full_size_properties():
+    """Size-independent properties at the bench geometry (ViT-L/14, T = 847 -> 256 kept classes), where the CPU oracle
+    is too slow to be the checker for every image: run-to-run determinism (fixed-order reductions, no atomics),
+    independence of the images of a batch, -100 exactly on the dropped classes and nowhere else, and agreement of the
+    kept-class set with the EXACT path (the top-k decision is fp32 in every precision mode)."""
+    cfg = vitl()
+    sd = make_state_dict(cfg, 3)
+    img, text, g = make_inputs(cfg, 2, 847, 3, same_text=True)
+    m = Aggregator(**cfg.ctor_kwargs(), precision="fast")
+    m.load_state_dict(sd, strict=False)
+    m = m.cuda()
+    cu = (img.cuda(), text.cuda(), [x.cuda() for x in g])
+    y1 = m(*cu).clone()
+    y2 = m(*cu)
+    assert torch.equal(y1, y2)
+    y_first = m(cu[0][:1].contiguous(), cu[1][:1].contiguous(), [x[:1].contiguous() for x in cu[2]])
+    assert torch.equal(y_first, y1[:1])
+    kept = (y1 != -100.0).flatten(2).any(dim=2)                      # [B, T]
+    assert kept.sum(dim=1).tolist() == [256, 256]
+    dropped_rows = y1[~kept]
+    assert bool((dropped_rows == -100.0).all())
+    e = Aggregator(**cfg.ctor_kwargs(), precision="exact")
+    e.load_state_dict(sd, strict=False)
+    ye = e.cuda()(*cu)
+    assert torch.equal((ye != -100.0).flatten(2).any(dim=2), kept)
+    assert rel_l2(y1[kept].cpu(), ye[kept].cpu()) <= FAST_RELL2
