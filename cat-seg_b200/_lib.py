@@ -69,6 +69,8 @@ _SIGS = [
     ("catseg_forward", C.c_int, [C.c_void_p] + [C.c_void_p] * 7 + [C.c_size_t, C.c_int, C.c_int, C.c_void_p]),
     ("catseg_forward_taps", C.c_int, [C.c_void_p] + [C.c_void_p] * 7 +
      [C.c_size_t, C.c_int, C.c_int, C.POINTER(CatsegTaps), C.c_void_p]),
+    ("catseg_forward_class_sharded", C.c_int, [C.c_void_p] + [C.c_void_p] * 8 +
+     [C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("catseg_set_profiling", C.c_int, [C.c_void_p, C.c_int]),
     ("catseg_stage_times", C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),
     ("catseg_last_launch_count", C.c_int, [C.c_void_p]),
@@ -76,6 +78,8 @@ _SIGS = [
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     ("catseg_argmax", C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
 ]
+# int (*catseg_allreduce_fn)(void* ctx, float* buf, size_t count, catseg_stream stream)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
 EXPORTED_SYMBOLS = tuple(s[0] for s in _SIGS)
 
 

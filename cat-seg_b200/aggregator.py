@@ -205,6 +205,57 @@ class Aggregator(nn.Module):
                 raise self._lib_error(rc)
             return logits, out
 
+    def forward_class_sharded(self, img_feats: torch.Tensor, text_feats: torch.Tensor,
+                              appearance_guidance: Sequence[torch.Tensor], group=None) -> torch.Tensor:
+        """Class-sharded forward over a torch.distributed process group (NCCL): every rank passes the SAME inputs,
+        computes the kept classes [r*Te/world, (r+1)*Te/world) and receives the full [B,T,4H,4W] logits.  The only
+        exchange inside the path is one all-reduce (sum) of the linear-attention state per class layer
+        (model.py:282-283), issued from the library through a callback on the current stream; the
+        local logit planes are all-gathered and scattered to their class ids afterwards."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        B, T, H, W = self._check(img_feats, text_feats, appearance_guidance)
+        Te = self.kept_classes(T)
+        if Te % world:
+            raise RuntimeError(f"kept classes ({Te}) must be a multiple of the shard group size ({world})")
+        lib = _lib.load()
+        dev = img_feats.device
+        with torch.cuda.device(dev):
+            self._ensure_handle(dev)
+            self.sync_weights()
+            img, text = self._f32c(img_feats), self._f32c(text_feats)
+            g = [self._f32c(x) for x in appearance_guidance]
+            need = lib.catseg_workspace_bytes(self._handle, B, T)
+            if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
+                self._workspace = None
+                self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+            ws = self._workspace
+            local = torch.empty(B, Te // world, 4 * H, 4 * W, dtype=torch.float32, device=dev)
+            kept = torch.empty(B, Te, dtype=torch.int32, device=dev)
+            errors = []
+
+            def _allreduce(_ctx, buf, count, _stream):      # called by the library between class_state and class_apply
+                try:
+                    off = int(buf) - ws.data_ptr()
+                    dist.all_reduce(ws[off:off + 4 * count].view(torch.float32), op=dist.ReduceOp.SUM, group=group)
+                    return 0
+                except Exception as e:                      # never let an exception cross the C ABI
+                    errors.append(e)
+                    return 1
+
+            cb = _lib.ALLREDUCE_FN(_allreduce)
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            rc = lib.catseg_forward_class_sharded(
+                self._handle, *[C.c_void_p(t.data_ptr()) for t in (img, text, g[0], g[1], g[2], local, kept)],
+                C.c_void_p(ws.data_ptr()), ws.numel(), B, T, rank, world, C.cast(cb, C.c_void_p), None, stream)
+            if errors:
+                raise errors[0]
+            if rc != 0:
+                raise self._lib_error(rc)
+            gathered = torch.empty(world, *local.shape, dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(gathered, local, group=group)
+            return assemble_class_sharded(gathered, kept, T)
+
     def _make_taps(self, names, B, T, H, W, dev):
         c = self.cfg
         Te, HW, hid = self.kept_classes(T), H * W, c.hidden_dim
@@ -257,3 +308,13 @@ class Aggregator(nn.Module):
                 _lib._LIB.catseg_destroy(self._handle)
         except Exception:
             pass
+
+
+def assemble_class_sharded(gathered: torch.Tensor, kept: torch.Tensor, T: int) -> torch.Tensor:
+    """gathered [world, B, Te/world, h, w]: rank r's planes are the kept classes kept[:, r*Te/world:(r+1)*Te/world];
+    kept [B, Te] class ids.  Returns [B, T, h, w] with -100 for classes that were not kept (model.py:721-724)."""
+    world, B, tl, h, w = gathered.shape
+    planes = gathered.permute(1, 0, 2, 3, 4).reshape(B, world * tl, h, w)
+    out = torch.full((B, T, h, w), -100.0, dtype=gathered.dtype, device=gathered.device)
+    out[torch.arange(B, device=gathered.device)[:, None], kept.long()] = planes
+    return out

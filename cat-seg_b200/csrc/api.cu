@@ -573,7 +573,7 @@ struct Plan {
   DecoderDims dd;
   // workspace offsets (floats)
   size_t imgn, textn, corr, cmax, classes, tmean, text_g, cg_qk, pad_state, app_g, app_gn, ag_qk, dg0, dg1, X,
-      Xp, Xp2, state, timg, dec, agw, total;
+      Xp, Xp2, state, timg, dec, agw, classes_loc, total;
 };
 
 Plan make_plan(const catseg_handle* h, int B, int T) {
@@ -600,6 +600,7 @@ Plan make_plan(const catseg_handle* h, int B, int T) {
   p.corr = take((size_t)B * T * p.P * p.HW);
   p.cmax = take((size_t)B * T);
   p.classes = take((size_t)B * p.Te);
+  p.classes_loc = take((size_t)2 * B * p.Te);   // class-sharded mode: local slice of the kept list, then local plane ids
   p.tmean = take((size_t)B * p.Te * p.Ct);
   p.text_g = take((size_t)B * p.Te * 128);
   p.cg_qk = take((size_t)p.L * B * p.Te * 256);
@@ -672,10 +673,13 @@ extern "C" size_t catseg_workspace_bytes(const catseg_handle* h, int B, int T) {
       CUDA_OK(h, cudaMemcpyAsync((dst), (src), (size_t)(nfloats) * sizeof(float), cudaMemcpyDeviceToDevice, st)); \
   } while (0)
 
-extern "C" int catseg_forward_taps(catseg_handle* h, const float* img, const float* text, const float* g0,
-                                   const float* g1, const float* g2, float* logits, void* workspace,
-                                   size_t workspace_bytes, int B, int T, const catseg_taps* taps,
-                                   catseg_stream stream) {
+// The forward proper.  shard_world == 1: logits is [B,T,4H,4W].  shard_world > 1 (class-sharded): logits is the compact
+// local buffer [B, Te/world, 4H, 4W], every per-(image, class) stage runs on this rank's slice of the kept classes and the
+// linear-attention state is summed over the group through `allreduce` between the state and apply kernels.
+static int forward_impl(catseg_handle* h, const float* img, const float* text, const float* g0, const float* g1,
+                        const float* g2, float* logits, void* workspace, size_t workspace_bytes, int B, int T,
+                        const catseg_taps* taps, int shard_rank, int shard_world, catseg_allreduce_fn allreduce, void* ar_ctx,
+                        int32_t* kept_out, catseg_stream stream) {
   if (!h) return CATSEG_ERR_INVALID;
   if (!img || !text || !g0 || !g1 || !g2 || !logits || !workspace) return fail(h, CATSEG_ERR_INVALID, "null tensor pointer");
   if (B <= 0 || T <= 0) return fail(h, CATSEG_ERR_INVALID, "B and T must be positive (got %d, %d)", B, T);
@@ -692,9 +696,17 @@ extern "C" int catseg_forward_taps(catseg_handle* h, const float* img, const flo
   const catseg_config& c = h->cfg;
   int nl = 0;
   Seg seg{h, st, h->profiling};
-  const int nslice = B * p.Te;
+  const bool sharded = shard_world > 1;
+  if (sharded) {
+    if (shard_rank < 0 || shard_rank >= shard_world || !allreduce) return fail(h, CATSEG_ERR_INVALID, "bad shard rank/world/allreduce");
+    if (p.Te % shard_world) return fail(h, CATSEG_ERR_UNSUPPORTED, "kept classes (%d) must be a multiple of the shard group size (%d)", p.Te, shard_world);
+    if (taps) return fail(h, CATSEG_ERR_UNSUPPORTED, "taps are not available in class-sharded mode");
+  }
+  const int Te = p.Te / shard_world;                     // classes processed by this rank
+  const int nslice = B * Te;
   float* X = ws + p.X;
-  int32_t* classes = reinterpret_cast<int32_t*>(ws + p.classes);
+  int32_t* classes_all = reinterpret_cast<int32_t*>(ws + p.classes);          // [B][p.Te] kept class ids (ascending)
+  int32_t* classes = sharded ? reinterpret_cast<int32_t*>(ws + p.classes_loc) : classes_all;   // [B][Te]
 
   // ---------------- PREP: cost volume, class selection, guidance projections (model.py:693-715)
   seg.begin(CATSEG_STAGE_PREP);
@@ -703,20 +715,22 @@ extern "C" int catseg_forward_taps(catseg_handle* h, const float* img, const flo
   RUN(launch_cost_volume(ws + p.textn, ws + p.imgn, ws + p.corr, B, T * p.P, p.C, p.HW, st));
   if (p.truncated) {
     RUN(launch_class_max(ws + p.corr, ws + p.cmax, (long long)B * T, p.P * p.HW, st));
-    RUN(launch_select_classes(ws + p.cmax, classes, B, T, p.Te, st));
+    RUN(launch_select_classes(ws + p.cmax, classes_all, B, T, p.Te, st));
   } else {
-    RUN(launch_iota_classes(classes, B, p.Te, st));
+    RUN(launch_iota_classes(classes_all, B, p.Te, st));
   }
-  RUN(launch_text_mean(p.truncated ? ws + p.textn : text, classes, ws + p.tmean, B, T, p.Te, p.P, p.Ct, st));
-  RUN(launch_linear(ws + p.tmean, h->tproj_wt, h->tproj_b, ws + p.text_g, (long long)B * p.Te, 128, p.Ct, 1, st));
+  if (sharded) RUN(launch_slice_classes(classes_all, classes, B, p.Te, shard_rank * Te, Te, st));
+  if (kept_out) CUDA_OK(h, cudaMemcpyAsync(kept_out, classes_all, (size_t)B * p.Te * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  RUN(launch_text_mean(p.truncated ? ws + p.textn : text, classes, ws + p.tmean, B, T, Te, p.P, p.Ct, st));
+  RUN(launch_linear(ws + p.tmean, h->tproj_wt, h->tproj_b, ws + p.text_g, (long long)B * Te, 128, p.Ct, 1, st));
   for (int l = 0; l < p.L; ++l) {
-    RUN(launch_linear(ws + p.text_g, h->cls[l].wg_qk_t, h->cls[l].bqk, ws + p.cg_qk + (size_t)l * B * p.Te * 256,
-                      (long long)B * p.Te, 256, 128, 0, st));
+    RUN(launch_linear(ws + p.text_g, h->cls[l].wg_qk_t, h->cls[l].bqk, ws + p.cg_qk + (size_t)l * B * Te * 256,
+                      (long long)B * Te, 256, 128, 0, st));
     RUN(launch_class_pad_state(h->cls[l], 128, ws + p.pad_state + (size_t)l * kStateFloats, p.n_pad, p.S, st));
   }
   const bool class_fast = (h->fast_mask & CATSEG_FAST_CLASS) != 0;
   __nv_bfloat16* timg = reinterpret_cast<__nv_bfloat16*>(ws + p.timg);
-  if (class_fast) RUN(launch_pack_text_img(ws + p.text_g, timg, B, p.Te, st));
+  if (class_fast) RUN(launch_pack_text_img(ws + p.text_g, timg, B, Te, st));
   const bool prep_fast = (h->fast_mask & CATSEG_FAST_PREP) != 0;
   if (prep_fast && h->gconv_img[0]) RUN(launch_gconv_fast(0, g0, h->gconv_img[0], h->gproj_b, ws + p.app_g, B, p.Cg, st));
   else RUN(launch_conv3x3_nchw(g0, h->gproj_wt, h->gproj_b, ws + p.app_g, B, p.Cg, p.H, p.W, 128, st));
@@ -739,9 +753,9 @@ extern "C" int catseg_forward_taps(catseg_handle* h, const float* img, const flo
   seg.end();
   if (taps) {
     TAP(taps->corr, ws + p.corr, (size_t)B * T * p.P * p.HW);
-    TAP(taps->classes, ws + p.classes, (size_t)B * p.Te);
+    TAP(taps->classes, ws + p.classes, (size_t)B * Te);
     TAP(taps->app_guidance, ws + p.app_g, (size_t)B * p.HW * 128);
-    TAP(taps->text_guidance, ws + p.text_g, (size_t)B * p.Te * 128);
+    TAP(taps->text_guidance, ws + p.text_g, (size_t)B * Te * 128);
     TAP(taps->dec_guidance0, ws + p.dg0, (size_t)B * 4 * p.HW * p.dd.G1);
     TAP(taps->dec_guidance1, ws + p.dg1, (size_t)B * 16 * p.HW * p.dd.G2);
   }
@@ -749,9 +763,9 @@ extern "C" int catseg_forward_taps(catseg_handle* h, const float* img, const flo
   // ---------------- EMBED (model.py:704)
   seg.begin(CATSEG_STAGE_EMBED);
   if (prep_fast && h->embed_img)
-    RUN(launch_cost_embed_fast(ws + p.corr, classes, h->embed_img, h->conv1_b, X, B, T, p.Te, h->num_sms, st));
+    RUN(launch_cost_embed_fast(ws + p.corr, classes, h->embed_img, h->conv1_b, X, B, T, Te, h->num_sms, st));
   else
-    RUN(launch_cost_embed(ws + p.corr, classes, h->conv1_wt, h->conv1_b, X, B, T, p.Te, p.P, p.H, p.W, st));
+    RUN(launch_cost_embed(ws + p.corr, classes, h->conv1_wt, h->conv1_b, X, B, T, Te, p.P, p.H, p.W, st));
   seg.end();
   TAP(taps->embed, X, (size_t)nslice * p.HW * 128);
 
@@ -766,9 +780,9 @@ extern "C" int catseg_forward_taps(catseg_handle* h, const float* img, const flo
       if (attn_fast) {
         __nv_bfloat16* agw = reinterpret_cast<__nv_bfloat16*>(ws + p.agw) + (size_t)(l * 2 + k) * B * 16 * 144 * 64;
         RUN(launch_pack_ag_windows(agk, agw, B, shift, st));
-        RUN(launch_swin_attn_fast(X, agw, nslice, p.Te, shift, h->swin_attn_fast[l * 2 + k], h->num_sms, st));
+        RUN(launch_swin_attn_fast(X, agw, nslice, Te, shift, h->swin_attn_fast[l * 2 + k], h->num_sms, st));
       }
-      else RUN(launch_swin_block_exact(X, agk, nslice, p.Te, shift, h->swin[l * 2 + k], mlp_fast ? 0 : 1, st));
+      else RUN(launch_swin_block_exact(X, agk, nslice, Te, shift, h->swin[l * 2 + k], mlp_fast ? 0 : 1, st));
       seg.end();
       if (mlp_fast) {
         seg.begin(CATSEG_STAGE_SWIN_MLP);
@@ -779,20 +793,22 @@ extern "C" int catseg_forward_taps(catseg_handle* h, const float* img, const flo
       else TAP(taps->swin_b2[l], X, (size_t)nslice * p.HW * 128);
     }
     seg.begin(CATSEG_STAGE_CLASS);
-    const float* cg = ws + p.cg_qk + (size_t)l * B * p.Te * 256;
+    const float* cg = ws + p.cg_qk + (size_t)l * B * Te * 256;
     const float* pad = ws + p.pad_state + (size_t)l * kStateFloats;
     if (p.pooled) RUN(launch_avgpool_tokens(X, ws + p.Xp, nslice, p.H, p.W, c.pooling_size[0], c.pooling_size[1], st));
     const float* xin = p.pooled ? ws + p.Xp : X;
     float* xout = p.pooled ? ws + p.Xp2 : X;
     const int omode = p.pooled ? 1 : 0;
-    if (class_fast) {
-      RUN(launch_class_state_fast(xin, timg, ws + p.state, B, p.Te, p.npix, p.S, h->class_fast[l], h->num_sms, st));
-      RUN(launch_class_apply_fast(xin, xout, timg, ws + p.state, pad, B, p.Te, p.npix, p.S, omode, h->class_fast[l],
-                                  h->num_sms, st));
-    } else {
-      RUN(launch_class_state_exact(xin, cg, ws + p.state, B, p.Te, p.npix, p.S, h->cls[l], st));
-      RUN(launch_class_apply_exact(xin, xout, cg, ws + p.state, pad, B, p.Te, p.npix, p.S, omode, h->cls[l], st));
+    if (class_fast) RUN(launch_class_state_fast(xin, timg, ws + p.state, B, Te, p.npix, p.S, h->class_fast[l], h->num_sms, st));
+    else RUN(launch_class_state_exact(xin, cg, ws + p.state, B, Te, p.npix, p.S, h->cls[l], st));
+    if (sharded) {                                         // the only exchange step of the path: sum of the per-pixel state
+      int rc = allreduce(ar_ctx, ws + p.state, (size_t)B * p.npix * kStateFloats, stream);
+      if (rc != 0) return fail(h, CATSEG_ERR_CUDA, "class-shard all-reduce callback failed (%d)", rc);
     }
+    if (class_fast)
+      RUN(launch_class_apply_fast(xin, xout, timg, ws + p.state, pad, B, Te, p.npix, p.S, omode, h->class_fast[l], h->num_sms, st));
+    else
+      RUN(launch_class_apply_exact(xin, xout, cg, ws + p.state, pad, B, Te, p.npix, p.S, omode, h->cls[l], st));
     if (p.pooled) RUN(launch_upsample_add(X, ws + p.Xp2, nslice, p.H, p.W, p.Hp, p.Wp, st));
     seg.end();
     TAP(taps->class_out[l], X, (size_t)nslice * p.HW * 128);
@@ -800,15 +816,25 @@ extern "C" int catseg_forward_taps(catseg_handle* h, const float* img, const flo
 
   // ---------------- decoder + scatter (model.py:720-724)
   seg.begin(CATSEG_STAGE_DECODER);
-  if (p.truncated) RUN(launch_fill(logits, -100.0f, (long long)B * T * 16 * p.HW, st));
+  // class-sharded: the output is the compact local buffer [B][Te][16 HW]: plane ids are 0..Te-1 and T_out = Te
+  const int32_t* out_ids = classes;
+  int T_out = T;
+  if (sharded) {
+    int32_t* ids = reinterpret_cast<int32_t*>(ws + p.classes_loc) + (size_t)B * p.Te;
+    RUN(launch_iota_classes(ids, B, Te, st));
+    out_ids = ids;
+    T_out = Te;
+  } else if (p.truncated) {
+    RUN(launch_fill(logits, -100.0f, (long long)B * T * 16 * p.HW, st));
+  }
   if (h->fast_mask & CATSEG_FAST_DECODER) {
     if (taps && (taps->up1 || taps->up2))
       return fail(h, CATSEG_ERR_UNSUPPORTED, "up1/up2 taps are only available with the exact decoder");
-    cudaError_t e = run_decoder_fast(X, ws + p.dg0, ws + p.dg1, classes, logits, B, T, p.Te, p.dd, h->dec_fast, h->dec,
+    cudaError_t e = run_decoder_fast(X, ws + p.dg0, ws + p.dg1, out_ids, logits, B, T_out, Te, p.dd, h->dec_fast, h->dec,
                                      h->head_bias_host, ws + p.dec, p.dec_chunk, h->num_sms, &nl, st);
     if (e != cudaSuccess) return fail(h, CATSEG_ERR_CUDA, "fast decoder: %s", cudaGetErrorString(e));
   } else {
-    cudaError_t e = run_decoder_exact(X, ws + p.dg0, ws + p.dg1, classes, logits, B, T, p.Te, p.dd, h->dec,
+    cudaError_t e = run_decoder_exact(X, ws + p.dg0, ws + p.dg1, out_ids, logits, B, T_out, Te, p.dd, h->dec,
                                       ws + p.dec, p.dec_chunk, taps ? taps->up1 : nullptr,
                                       taps ? taps->up2 : nullptr, &nl, st);
     if (e != cudaSuccess) return fail(h, CATSEG_ERR_CUDA, "decoder: %s", cudaGetErrorString(e));
@@ -817,6 +843,24 @@ extern "C" int catseg_forward_taps(catseg_handle* h, const float* img, const flo
   if (h->profiling) ++h->prof_forwards;
   h->last_launches = nl;
   return CATSEG_OK;
+}
+
+extern "C" int catseg_forward_taps(catseg_handle* h, const float* img, const float* text, const float* g0,
+                                   const float* g1, const float* g2, float* logits, void* workspace,
+                                   size_t workspace_bytes, int B, int T, const catseg_taps* taps,
+                                   catseg_stream stream) {
+  return forward_impl(h, img, text, g0, g1, g2, logits, workspace, workspace_bytes, B, T, taps, 0, 1, nullptr, nullptr, nullptr,
+                      stream);
+}
+
+extern "C" int catseg_forward_class_sharded(catseg_handle* h, const float* img, const float* text, const float* g0,
+                                            const float* g1, const float* g2, float* logits_local,
+                                            int32_t* kept_classes_out, void* workspace, size_t workspace_bytes, int B, int T,
+                                            int shard_rank, int shard_world, catseg_allreduce_fn allreduce, void* ctx,
+                                            catseg_stream stream) {
+  if (shard_world < 1) return CATSEG_ERR_INVALID;
+  return forward_impl(h, img, text, g0, g1, g2, logits_local, workspace, workspace_bytes, B, T, nullptr, shard_rank, shard_world,
+                      allreduce, ctx, kept_classes_out, stream);
 }
 
 extern "C" int catseg_forward(catseg_handle* h, const float* img, const float* text, const float* g0,

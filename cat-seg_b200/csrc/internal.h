@@ -74,6 +74,8 @@ cudaError_t launch_transpose_pack(float* dst, int ldd, int dst_col0, const float
                                   int rows, int cols, cudaStream_t st);
 cudaError_t launch_fill(float* p, float v, long long n, cudaStream_t st);
 cudaError_t launch_iota_classes(int32_t* classes, int B, int Te, cudaStream_t st);
+// dst[b][j] = src[b][first + j], j < n (class-sharded mode: this rank's slice of the kept-class list)
+cudaError_t launch_slice_classes(const int32_t* src, int32_t* dst, int B, int Te, int first, int n, cudaStream_t st);
 
 // ---------------------------------------------------------------- fast_prep.cu
 // 7x7 cost embedding for P = 1 on a 24x24 grid; bimg = 14 images packed by launch_pack_embed_img from Wt [49][128]

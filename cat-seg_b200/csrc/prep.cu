@@ -105,6 +105,15 @@ cudaError_t launch_iota_classes(int32_t* classes, int B, int Te, cudaStream_t st
   return cudaGetLastError();
 }
 
+__global__ void slice_classes_kernel(const int32_t* __restrict__ src, int32_t* __restrict__ dst, int B, int Te, int first, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * n) dst[i] = src[(i / n) * Te + first + i % n];
+}
+cudaError_t launch_slice_classes(const int32_t* src, int32_t* dst, int B, int Te, int first, int n, cudaStream_t st) {
+  slice_classes_kernel<<<(B * n + 255) / 256, 256, 0, st>>>(src, dst, B, Te, first, n);
+  return cudaGetLastError();
+}
+
 // ---- text guidance input (model.py:713-714): mean over P of the kept classes' text rows, then
 // divide by the L2 norm (no eps).  src is the raw text when not truncated and the normalised text
 // when truncated (model.py:701).  One block per (b, i).

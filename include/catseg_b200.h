@@ -124,6 +124,22 @@ int catseg_forward_taps(catseg_handle* h, const float* img_feats, const float* t
                         const float* g1, const float* g2, float* logits, void* workspace,
                         size_t workspace_bytes, int B, int T, const catseg_taps* taps, catseg_stream stream);
 
+/* Class-sharded multi-GPU mode (spatial aggregation and the decoder are independent per class; the
+ * class layers couple classes only through the linear-attention state, model.py:282-283).  Every rank of the shard
+ * group receives the SAME images and text; rank r computes the kept classes [r*Te/world, (r+1)*Te/world) of the
+ * ascending kept-class list (Te = catseg_kept_classes(T) must be a multiple of world).  Between the state and apply
+ * kernels of each class layer the library calls `allreduce(ctx, state, count, stream)`, which must sum `count` fp32
+ * values in place over the shard group, ordered on `stream` (e.g. ncclAllReduce / torch.distributed.all_reduce).
+ *   logits_local     [B, Te/world, 4H, 4W] fp32: this rank's kept classes, compact.
+ *   kept_classes_out [B, Te] int32 (may be NULL): the kept class ids, identical on every rank; the caller all-gathers
+ *                    logits_local over the group and scatters plane (r, j) to class kept[b][r*Te/world + j]; classes not
+ *                    kept are -100 (model.py:721-724). */
+typedef int (*catseg_allreduce_fn)(void* ctx, float* buf, size_t count, catseg_stream stream);
+int catseg_forward_class_sharded(catseg_handle* h, const float* img_feats, const float* text_feats, const float* g0,
+                                 const float* g1, const float* g2, float* logits_local, int32_t* kept_classes_out,
+                                 void* workspace, size_t workspace_bytes, int B, int T, int shard_rank, int shard_world,
+                                 catseg_allreduce_fn allreduce, void* ctx, catseg_stream stream);
+
 /* Per-stage CUDA-event timing of catseg_forward on its own stream (for the roofline report). */
 int catseg_set_profiling(catseg_handle* h, int enable);
 /* Synchronises the recorded events; ms[CATSEG_STAGE_COUNT] = total ms per stage since the last

@@ -57,3 +57,20 @@ def test_shard_range_covers_everything():
             assert seen == list(range(n))
             sizes = [len(shard_range(n, r, world)) for r in range(world)]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_assemble_class_sharded_scatter():
+    """Host logic of the class-sharded mode: rank-major planes go back to their kept class ids, the rest is -100."""
+    import torch
+    from cat_seg_b200.aggregator import assemble_class_sharded
+    world, B, tl, T = 2, 2, 3, 10
+    kept = torch.tensor([[0, 2, 3, 5, 8, 9], [1, 2, 4, 6, 7, 9]], dtype=torch.int32)
+    gathered = torch.arange(world * B * tl * 4, dtype=torch.float32).reshape(world, B, tl, 2, 2)
+    out = assemble_class_sharded(gathered, kept, T)
+    assert out.shape == (B, T, 2, 2)
+    for b in range(B):
+        for r in range(world):
+            for j in range(tl):
+                assert torch.equal(out[b, kept[b, r * tl + j]], gathered[r, b, j])
+        dropped = sorted(set(range(T)) - set(kept[b].tolist()))
+        assert bool((out[b, dropped] == -100.0).all())
