@@ -49,7 +49,7 @@ struct BandConvParams {
   long long* dbg;            // optional phase timing (CATSEG_PHASE_TIMING=1)
 };
 
-template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD>
+template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD, int CTAS = 2>
 struct BandCfg {
   static constexpr int PW = WIN_ + 2, NP = (BR + 2) * PW, P0 = PW + 1;
   static constexpr int MROWS = (BR - 1) * PW + WIN_, NTILES = (MROWS + 127) / 128;
@@ -74,8 +74,11 @@ struct BandCfg {
   static constexpr uint32_t SM_BAR = (SM_ST + 8 * GOUT * 2 * 4 + 15) / 16 * 16;
   static constexpr uint32_t SMEM = SM_BAR + (2 * NSLOT + 17) * 8 + 16;   // ring barriers + [2 sets][8 tiles] accumulator barriers
   static constexpr uint32_t IDESC = umma::make_idesc_bf16(128, NOUT);
-  static_assert(NTILES * NOUT <= 256, "TMEM columns (two CTAs per SM)");
-  static_assert(SMEM <= 113 * 1024, "shared memory budget (two CTAs per SM)");
+  // CTAS = CTAs per SM: 2 (half-height bands; one CTA's staging / epilogue overlaps the other's MMAs) or 1 (a band as
+  // tall as the shared memory allows: fewer M-tile remainders and one pass over a streamed weight set per band)
+  static constexpr int TMEM_COLS = CTAS == 2 ? 256 : 512;
+  static_assert(NTILES * NOUT <= TMEM_COLS, "TMEM columns");
+  static_assert(SMEM <= (CTAS == 2 ? 113 * 1024 : 227 * 1024), "shared memory budget");
   static_assert(WIN_ % BR == 0 && CIN % 16 == 0 && NOUT % 16 == 0, "shape");
 };
 
@@ -86,9 +89,9 @@ struct BandCfg {
 // of parity pg+1 run under the epilogue of parity pg.
 constexpr int BAND_THREADS = 288;
 
-template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD>
-__global__ void __launch_bounds__(BAND_THREADS, 2) band_conv_kernel(BandConvParams p) {
-  using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD>;
+template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD, int CTAS>
+__global__ void __launch_bounds__(BAND_THREADS, CTAS) band_conv_kernel(BandConvParams p) {
+  using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS>;
   extern __shared__ __align__(1024) uint8_t smem[];
   float* s_scale = reinterpret_cast<float*>(smem + C::SM_SC);
   float* s_shift = s_scale + CIN;
@@ -100,7 +103,7 @@ __global__ void __launch_bounds__(BAND_THREADS, 2) band_conv_kernel(BandConvPara
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q4 = warp & 3, tgrp = (warp >> 2) & 1;
   const bool issuer = __shfl_sync(0xffffffffu, warp, 0) == 8;           // warp-uniform role
   constexpr int ACC_COLS = C::NTILES * NOUT;
-  constexpr int SETS = (C::NPG > 1 && 2 * ACC_COLS <= 256) ? 2 : 1;
+  constexpr int SETS = (C::NPG > 1 && 2 * ACC_COLS <= C::TMEM_COLS) ? 2 : 1;
 
   const long long nitems = (long long)p.nslice * C::NB;
   long long mine = 0;
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(BAND_THREADS, 2) band_conv_kernel(BandConvPara
     for (int i = 0; i < 2 * C::NSLOT + 16; ++i) umma::mbar_init(&bar_full[i], 1);
     umma::mbar_fence_init();
   }
-  if (warp == 0) umma::tmem_alloc<256>(tmem_slot);
+  if (warp == 0) umma::tmem_alloc<C::TMEM_COLS>(tmem_slot);
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
@@ -433,13 +436,13 @@ __global__ void __launch_bounds__(BAND_THREADS, 2) band_conv_kernel(BandConvPara
 #undef BPH
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc<256>(tm);
+  if (warp == 0) umma::tmem_dealloc<C::TMEM_COLS>(tm);
 }
 
-template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD>
+template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD, int CTAS = 2>
 static cudaError_t launch_band(const BandConvParams& p, int num_sms, cudaStream_t st) {
-  using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD>;
-  auto kern = band_conv_kernel<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD>;
+  using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS>;
+  auto kern = band_conv_kernel<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
@@ -447,7 +450,7 @@ static cudaError_t launch_band(const BandConvParams& p, int num_sms, cudaStream_
     attr_set = true;
   }
   long long nitems = (long long)p.nslice * C::NB;
-  int grid = (int)(nitems < 2LL * num_sms ? nitems : 2LL * num_sms);
+  int grid = (int)(nitems < (long long)CTAS * num_sms ? nitems : (long long)CTAS * num_sms);
   if (grid <= 0) return cudaSuccess;
   static long long* dbg = nullptr;
   static int dbg_on = -1;
@@ -638,7 +641,7 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
     p.Te = Te; p.slice0 = s0; p.nslice = n; p.T = T; p.classes = classes; p.logits = logits; p.head_bias = head_bias;
     // D1: x (24^2 x 128, fp32) -> c1a (48^2 x 64), composed transposed conv + conv
     p.in = X + (long long)s0 * hw * d.C0; p.in_stats = nullptr; p.wimg = w.w1; p.emap = E1; p.out = c1a; p.out_stats = s1a;
-    CKF((launch_band<128, 64, 64, true, true, 24, 6, false>(p, num_sms, st)));
+    CKF((launch_band<128, 64, 64, true, true, 24, 6, false>(p, num_sms, st)));       // (a whole slice per CTA, <...,24,24,false,1>, was measured: no faster)
     // D2: c1a -> c1b, 3x3 64 -> 64 on relu(gn(c1a))
     p.in = c1a; p.in_stats = s1a; p.nb_in = 4; p.in_count = (float)(4 * hw * 16); p.gamma = wx.gn1a_g; p.beta = wx.gn1a_b;
     p.wimg = w.w2; p.emap = nullptr; p.out = c1b; p.out_stats = s1b;
