@@ -12,7 +12,7 @@ legs may import it.  The product path (``cat-seg_b200/``) never does.
 Parity pinning: the reference ships no tests or golden vectors, so the oracle is
 pinned against the *reference itself*, imported unchanged from ``/root/reference`` in the build
 container (``oracle/ref_loader.py``, ``tests/test_oracle_vs_reference.py``) and against fixtures
-generated from the reference by ``tools/make_golden.py`` (``tests/golden/*.npz``).
+generated from the reference by ``tests/golden/make_golden.py`` (``tests/golden/*.npz``).
 """
 from __future__ import annotations
 

@@ -6,7 +6,7 @@ on the GPU box, so the pin is made here: the reference module is imported from
 synthetic weights/inputs of cat_seg_b200.synth, and its logits plus hook-captured intermediates
 are stored (sub-sampled, with float64 checksums) in the kernels' token-major layout.
 
-    python tools/make_golden.py            # rewrites tests/golden/
+    python tests/golden/make_golden.py            # rewrites tests/golden/
 """
 from __future__ import annotations
 
@@ -16,7 +16,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from cat_seg_b200.config import vitb, vitl  # noqa: E402

@@ -12,7 +12,7 @@ if ROOT not in sys.path:
 from cat_seg_b200.config import vitb, vitl  # noqa: E402
 from cat_seg_b200.synth import make_inputs, make_state_dict  # noqa: E402
 
-# must stay in sync with tools/make_golden.py
+# must stay in sync with tests/golden/make_golden.py
 GOLDEN_CASES = {
     "vitb_T5_B1": (vitb(), 1, 5, 0, True),
     "vitb_T3_B2_pool2": (vitb(pooling_size=(2, 2)), 2, 3, 1, False),

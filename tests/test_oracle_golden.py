@@ -1,4 +1,4 @@
-"""CPU: pin the oracle against fixtures generated from the unmodified reference (tools/make_golden.py)
+"""CPU: pin the oracle against fixtures generated from the unmodified reference (tests/golden/make_golden.py)
 and, when /root/reference is present (build container only), against the live reference."""
 import numpy as np
 import pytest

@@ -1,13 +1,13 @@
 """GPU: per-stage error of a precision spec against the CPU oracle (and timing per stage).
 
-    python tools/check_fast.py --precision fast:swin_mlp [--model vitb --B 1 --T 5 --pool 1]
+    python tests/tools/check_fast.py --precision fast:swin_mlp [--model vitb --B 1 --T 5 --pool 1]
 """
 import argparse
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
