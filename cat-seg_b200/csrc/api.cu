@@ -47,6 +47,8 @@ struct catseg_handle {
   void* dec_fast_store = nullptr;
   DecoderFastW dec_fast{};
   float head_bias_host = 0.0f;
+  cudaStream_t aux_stream = nullptr;            // fork/join inside catseg_forward: guidance projections run beside the cost volume
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   __nv_bfloat16* prep_img = nullptr;            // FAST_PREP: embedding images, then the three guidance-conv image sets
   const __nv_bfloat16 *embed_img = nullptr, *gconv_img[3] = {nullptr, nullptr, nullptr};   // nullptr: shape not covered -> fp32 kernel
   bool finalized = false;
@@ -216,6 +218,9 @@ extern "C" int catseg_destroy(catseg_handle* h) {
   if (h->wimg) cudaFree(h->wimg);
   if (h->dec_fast_store) cudaFree(h->dec_fast_store);
   if (h->prep_img) cudaFree(h->prep_img);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
   return CATSEG_OK;
 }
@@ -710,6 +715,12 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
 
   // ---------------- PREP: cost volume, class selection, guidance projections (model.py:693-715)
   seg.begin(CATSEG_STAGE_PREP);
+  if (!h->aux_stream) {
+    CUDA_OK(h, cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+    CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  }
+  CUDA_OK(h, cudaEventRecord(h->ev_fork, st));
   RUN(launch_normalize_img(img, ws + p.imgn, B, p.C, p.HW, st));
   RUN(launch_normalize_rows(text, ws + p.textn, (long long)B * T * p.P, p.Ct, st));
   RUN(launch_cost_volume(ws + p.textn, ws + p.imgn, ws + p.corr, B, T * p.P, p.C, p.HW, st));
@@ -731,25 +742,35 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
   const bool class_fast = (h->fast_mask & CATSEG_FAST_CLASS) != 0;
   __nv_bfloat16* timg = reinterpret_cast<__nv_bfloat16*>(ws + p.timg);
   if (class_fast) RUN(launch_pack_text_img(ws + p.text_g, timg, B, Te, st));
+  // The guidance projections only depend on the inputs: they run on an internal stream beside the cost volume / class
+  // selection / text chain (small, latency-bound kernels) and are joined before the embedding.  Externally the call is
+  // still ordered on `stream`.
   const bool prep_fast = (h->fast_mask & CATSEG_FAST_PREP) != 0;
-  if (prep_fast && h->gconv_img[0]) RUN(launch_gconv_fast(0, g0, h->gconv_img[0], h->gproj_b, ws + p.app_g, B, p.Cg, st));
-  else RUN(launch_conv3x3_nchw(g0, h->gproj_wt, h->gproj_b, ws + p.app_g, B, p.Cg, p.H, p.W, 128, st));
-  for (int l = 0; l < p.L; ++l) {
-    RUN(launch_layernorm128(ws + p.app_g, ws + p.app_gn, h->gnorm_g[l], h->gnorm_b[l], (long long)B * p.HW, st));
-    for (int k = 0; k < 2; ++k)
-      RUN(launch_linear(ws + p.app_gn, h->swin[l * 2 + k].wg_qk_t, h->swin[l * 2 + k].bqk,
-                        ws + p.ag_qk + (size_t)(l * 2 + k) * B * p.HW * 256, (long long)B * p.HW, 256, 128, 0, st));
+  {
+    cudaStream_t mainst = st;
+    CUDA_OK(h, cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));     // ev_fork was recorded at the start of the stage
+    cudaStream_t st = h->aux_stream;             // shadows: the launches below go to the internal stream
+    if (prep_fast && h->gconv_img[0]) RUN(launch_gconv_fast(0, g0, h->gconv_img[0], h->gproj_b, ws + p.app_g, B, p.Cg, st));
+    else RUN(launch_conv3x3_nchw(g0, h->gproj_wt, h->gproj_b, ws + p.app_g, B, p.Cg, p.H, p.W, 128, st));
+    for (int l = 0; l < p.L; ++l) {
+      RUN(launch_layernorm128(ws + p.app_g, ws + p.app_gn, h->gnorm_g[l], h->gnorm_b[l], (long long)B * p.HW, st));
+      for (int k = 0; k < 2; ++k)
+        RUN(launch_linear(ws + p.app_gn, h->swin[l * 2 + k].wg_qk_t, h->swin[l * 2 + k].bqk,
+                          ws + p.ag_qk + (size_t)(l * 2 + k) * B * p.HW * 256, (long long)B * p.HW, 256, 128, 0, st));
+    }
+    if (prep_fast && h->gconv_img[1])
+      RUN(launch_gconv_fast(1, g1, h->gconv_img[1], h->dgp_b[0], ws + p.dg0, B, c.decoder_guidance_dims[0], st));
+    else
+      RUN(launch_conv3x3_nchw(g1, h->dgp_wt[0], h->dgp_b[0], ws + p.dg0, B, c.decoder_guidance_dims[0], 2 * p.H, 2 * p.W,
+                              p.dd.G1, st));
+    if (prep_fast && h->gconv_img[2])
+      RUN(launch_gconv_fast(2, g2, h->gconv_img[2], h->dgp_b[1], ws + p.dg1, B, c.decoder_guidance_dims[1], st));
+    else
+      RUN(launch_conv3x3_nchw(g2, h->dgp_wt[1], h->dgp_b[1], ws + p.dg1, B, c.decoder_guidance_dims[1], 4 * p.H, 4 * p.W,
+                              p.dd.G2, st));
+    CUDA_OK(h, cudaEventRecord(h->ev_join, st));
+    CUDA_OK(h, cudaStreamWaitEvent(mainst, h->ev_join, 0));
   }
-  if (prep_fast && h->gconv_img[1])
-    RUN(launch_gconv_fast(1, g1, h->gconv_img[1], h->dgp_b[0], ws + p.dg0, B, c.decoder_guidance_dims[0], st));
-  else
-    RUN(launch_conv3x3_nchw(g1, h->dgp_wt[0], h->dgp_b[0], ws + p.dg0, B, c.decoder_guidance_dims[0], 2 * p.H, 2 * p.W,
-                            p.dd.G1, st));
-  if (prep_fast && h->gconv_img[2])
-    RUN(launch_gconv_fast(2, g2, h->gconv_img[2], h->dgp_b[1], ws + p.dg1, B, c.decoder_guidance_dims[1], st));
-  else
-    RUN(launch_conv3x3_nchw(g2, h->dgp_wt[1], h->dgp_b[1], ws + p.dg1, B, c.decoder_guidance_dims[1], 4 * p.H, 4 * p.W,
-                            p.dd.G2, st));
   seg.end();
   if (taps) {
     TAP(taps->corr, ws + p.corr, (size_t)B * T * p.P * p.HW);
