@@ -58,7 +58,7 @@ static_assert(ST_SMEM <= 232448 && AP_SMEM <= 232448, "shared memory budget");
 // groups 2,3 those of v.
 __global__ void __launch_bounds__(512, 1)
 class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __restrict__ timg, float* __restrict__ state,
-                        int B, int Te, int npix, int S, ClassFastW w) {
+                        int B, int Te, int npix, int S, ClassFastW w, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   float* s_g = reinterpret_cast<float*>(smem + ST_PAR);
   float* s_be = s_g + 128;
@@ -96,6 +96,8 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
   const float invS = 1.0f / (float)S;
 
   const long long nitems = (long long)B * npix;
+  long long t_last = clock64(), sacc0 = 0, sacc1 = 0, sacc2 = 0, sacc3 = 0, sacc4 = 0, nt_dbg = 0;
+#define SPH(i) do { if (dbg != nullptr && blockIdx.x == 0 && tid == 0) { long long _t = clock64(); sacc##i += _t - t_last; t_last = _t; } } while (0)
   for (long long it = blockIdx.x; it < nitems; it += gridDim.x) {
     const int b = (int)(it / npix), pix = (int)(it % npix);
     {   // the next item's token rows (Te rows of 512 bytes, one per class) are prefetched into L2 meanwhile
@@ -122,6 +124,7 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
       umma::fence_proxy_async();
       umma::fence_before_sync();
       __syncthreads();
+      SPH(0);
       // ---- k = [xn | g] [Wk_x | Wk_g]^T (cols 0..127), v = xn Wv^T (cols 128..255)
       if (issuer) {
         umma::fence_after_sync();
@@ -138,19 +141,22 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
       ph_g ^= 1;
       umma::mbar_wait(bar_m1, ph_m1); ph_m1 ^= 1;
       umma::fence_after_sync();
+      SPH(1);
       // ---- epilogue: groups 0,1 -> phi(k) image (over the LN tile), groups 2,3 -> [v/S | 1] image (over the g tile)
       {
         const bool live = row < nvalid;
         uint8_t* img = smem + (half == 0 ? ST_XN : ST_G);
-#pragma unroll 1
-        for (int cc = chalf * 2; cc < chalf * 2 + 2; ++cc) {
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const int cc = chalf * 2 + c2;
           float v[32];
           umma::tmem_ld32(lane_addr + ST_TM_KV + half * 128 + cc * 32, v);
           const float* bb = (half == 0 ? s_bk : s_bv) + cc * 32;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             float a = v[i] + bb[i];
-            a = half == 0 ? (a > 0.0f ? a + 1.0f : __expf(a)) : a * invS;
+            const float ex = __expf(fminf(a, 0.0f));          // unconditional: a per-element branch around the exp costs far more than the MUFU
+            a = half == 0 ? (a > 0.0f ? a + 1.0f : ex) : a * invS;
             v[i] = live ? a : 0.0f;
           }
 #pragma unroll
@@ -167,6 +173,7 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
       umma::fence_proxy_async();
       umma::fence_before_sync();
       __syncthreads();
+      SPH(2);
       // ---- KV (+)= K^T [V | 1]  (contract over the 128 tokens of this tile)
       if (issuer) {
         umma::fence_after_sync();
@@ -180,6 +187,8 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
       }
       umma::mbar_wait(bar_m2, ph_m2); ph_m2 ^= 1;
       umma::fence_after_sync();
+      SPH(3);
+      ++nt_dbg;
     }
     // ---- state[b][pix]: thread = k-feature (h, d) x 8 of the 32 columns KV[h][d][grp*8..+8]; group 0 also Ksum[h*32+d]
     {
@@ -198,7 +207,10 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
+    SPH(4);
   }
+#undef SPH
+  if (dbg != nullptr && blockIdx.x == 0 && tid == 0) { dbg[0] = sacc0; dbg[1] = sacc1; dbg[2] = sacc2; dbg[3] = sacc3; dbg[4] = sacc4; dbg[5] = nt_dbg; }
   if (warp == 0) umma::tmem_dealloc<512>(tm);
 }
 
@@ -374,7 +386,7 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
       umma::tmem_ld32(lane_addr + AP_TM_Q + cq * 32, v);
       const float* bb = s_bq + cq * 32;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { float a = v[i] + bb[i]; v[i] = a > 0.0f ? a + 1.0f : __expf(a); }
+      for (int i = 0; i < 32; ++i) { float a = v[i] + bb[i]; const float ex = __expf(fminf(a, 0.0f)); v[i] = a > 0.0f ? a + 1.0f : ex; }
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         *reinterpret_cast<uint4*>(smem + AP_Q + (cq * 4 + c) * LBO_V + row * 16) =
@@ -539,7 +551,22 @@ cudaError_t launch_class_state_fast(const float* X, const __nv_bfloat16* timg, f
   }
   long long n = (long long)B * npix;
   int grid = (int)(n < num_sms ? n : num_sms);
-  class_state_fast_kernel<<<grid, 512, ST_SMEM, st>>>(X, timg, state, B, Te, npix, S, w);
+  static long long* dbg = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) {
+    const char* e = getenv("CATSEG_PHASE_TIMING");
+    dbg_on = (e && e[0] == '1') ? 1 : 0;
+    if (dbg_on) { cudaMalloc(&dbg, 8 * sizeof(long long)); cudaMemset(dbg, 0, 8 * sizeof(long long)); }
+  }
+  class_state_fast_kernel<<<grid, 512, ST_SMEM, st>>>(X, timg, state, B, Te, npix, S, w, dbg_on ? dbg : nullptr);
+  if (dbg_on) {
+    long long hb[8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hb, dbg, sizeof(hb), cudaMemcpyDeviceToHost);
+    double nn = hb[5] > 0 ? (double)hb[5] : 1.0;
+    fprintf(stderr, "[class_state phases, cycles per 128-class tile over %lld tiles] guidance TMA + LN1 %.0f | k,v mma %.0f | phi/pack epilogue %.0f "
+            "| KV mma %.0f | state store (per tile share) %.0f\n", hb[5], hb[0] / nn, hb[1] / nn, hb[2] / nn, hb[3] / nn, hb[4] / nn);
+  }
   return cudaGetLastError();
 }
 
