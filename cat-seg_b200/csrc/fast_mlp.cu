@@ -115,13 +115,10 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w, long long* __
           if (r < ntok) umma::prefetch_l2(X + r * 128 + (line & 3) * 32);
         }
       }
-      // ---- LN prologue: two tiles
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        long long r0 = row0 + t * 128;
-        long long nv = ntok - r0;
-        int nvalid = nv >= 128 ? 128 : (nv > 0 ? (int)nv : 0);
-        ln_rows_to_tile(X + r0 * 128, 128, nvalid, smem + SM_XN + t * TILE_BYTES_T, s_g, s_be, warp, MLP_EPI_WARPS, lane);
+      // ---- LN prologue: two tiles, loads of the next 4 rows in flight under the arithmetic of the current 4
+      {
+        const long long nv = ntok - row0;
+        ln_rows_to_tiles_pipelined<2>(X + row0 * 128, 128, nv >= 256 ? 256 : (int)nv, smem + SM_XN, s_g, s_be, warp, lane);
       }
       umma::fence_proxy_async();
     }
