@@ -219,13 +219,13 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w, long long* __
         const long long r = row0 + warp * 8 + i;
         xres[i] = r < ntok ? ld4(X + r * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      umma::mbar_wait(&bar_mma[3], (uint32_t)((g - 1) & 1));
-      umma::fence_after_sync();
     }
     PH(4);
 #pragma unroll 1
     for (int t = 0; t < 2; ++t) {
       if (!issuer) {
+        umma::mbar_wait(&bar_mma[2 + t], (uint32_t)((g - 1) & 1));   // Y_t complete (tile b's last MMA2 runs under tile a's epilogue)
+        umma::fence_after_sync();
         float v[32];
         umma::tmem_ld32(lane_addr + 256 + t * 128 + cq * 32, v);
         const float* bb = s_b2 + cq * 32;
