@@ -135,3 +135,62 @@ def test_argmax_first_max_wins():
     s[1] = 1.0
     s[3] = 1.0
     assert torch.equal(sw.argmax(s.cuda()).cpu().long(), s.argmax(dim=0))
+
+
+def test_class_sharded_path_emulated_on_one_gpu():
+    """The class-sharded entry point on ONE GPU: the two 'ranks' of a shard group run one after the other and
+    the all-reduce callback is emulated by record/replay -- pass 1 records the layer-0 partial states, pass 2 injects their
+    sum and records layer 1, pass 3 injects both -- so every rank ends with exactly the sums a real all-reduce would give.
+    The assembled logits must match the unsharded forward (fp32 summation order of the state only)."""
+    import ctypes as C
+    from cat_seg_b200 import _lib
+    from cat_seg_b200.aggregator import assemble_class_sharded
+    cfg = vitb(pad_len=4)                                           # T = 9 > pad_len: 4 kept classes, 2 per rank
+    B, T, world = 2, 9, 2
+    sd = make_state_dict(cfg, 13)
+    inputs = _cuda(make_inputs(cfg, B, T, 13, same_text=False))
+    m = _module(cfg, sd)
+    ref = m(*inputs)
+    lib = _lib.load()
+    Te = m.kept_classes(T)
+    assert Te % world == 0
+    img, text, g = inputs
+    ws = torch.empty(lib.catseg_workspace_bytes(m._handle, B, T), dtype=torch.uint8, device="cuda")
+    recorded = {}                                                   # (pass, rank, layer) -> partial state
+    sums = {}
+
+    def run(rank, npass):
+        calls = {"n": 0}
+
+        def cb(_ctx, buf, count, _stream):
+            layer = calls["n"]
+            calls["n"] += 1
+            off = int(buf) - ws.data_ptr()
+            view = ws[off:off + 4 * count].view(torch.float32)
+            recorded[(npass, rank, layer)] = view.clone()
+            if layer in sums:
+                view.copy_(sums[layer])
+            return 0
+
+        fn = _lib.ALLREDUCE_FN(cb)
+        local = torch.empty(B, Te // world, 96, 96, device="cuda")
+        kept = torch.empty(B, Te, dtype=torch.int32, device="cuda")
+        rc = lib.catseg_forward_class_sharded(
+            m._handle, *[C.c_void_p(t.data_ptr()) for t in (img, text, g[0], g[1], g[2], local, kept)],
+            C.c_void_p(ws.data_ptr()), ws.numel(), B, T, rank, world, C.cast(fn, C.c_void_p), None,
+            C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, lib.catseg_last_error(m._handle)
+        torch.cuda.synchronize()
+        return local, kept
+
+    out = None
+    for npass in range(cfg.num_layers + 1):
+        locals_ = [run(r, npass) for r in range(world)]
+        if npass < cfg.num_layers:                                  # layer `npass` partials are now computed from correct inputs
+            sums[npass] = sum(recorded[(npass, r, npass)] for r in range(world))
+        out = locals_
+    gathered = torch.stack([o[0] for o in out])
+    assert torch.equal(out[0][1], out[1][1])                        # every rank reports the same kept-class list
+    y = assemble_class_sharded(gathered, out[0][1], T)
+    assert bool(((y == -100.0) == (ref == -100.0)).all())
+    assert (y - ref).abs().max().item() <= 1e-5
