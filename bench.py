@@ -207,7 +207,12 @@ def run_ours(args):
 
     sliding = args.workload == "cfg5"           # 5 windows of one 640x640 image + stitch/argmax per step
 
+    graph_run = None
+
     def step_resident():
+        if graph_run is not None:
+            y = graph_run(d_img, d_text, [d_img, d_g1, d_g2])
+            return sw.stitch(y, 640, 640, want_probs=False, want_labels=True)[1] if sliding else y
         if class_par:
             y = model.forward_class_sharded(d_img, d_text, [d_img, d_g1, d_g2])
         else:
@@ -222,10 +227,13 @@ def run_ours(args):
             torch.distributed.barrier()
         torch.cuda.synchronize(dev)
 
+    if args.cuda_graph and not class_par:
+        from cat_seg_b200.host_pipeline import GraphRunner
+        graph_run = GraphRunner(model, d_img, d_text, [d_img, d_g1, d_g2])
     for _ in range(args.warmup):
         y = step_resident()
     barrier()
-    model.set_profiling(True)
+    model.set_profiling(graph_run is None)
     model.stage_times(reset=True)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -352,6 +360,7 @@ def main():
     ap.add_argument("--precision", default="fast", help="exact | fast | fast:<stage>[,<stage>]")
     ap.add_argument("--batch", type=int, default=0, help="override images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-graph", action="store_true", help="replay the boundary call from a CUDA graph (value only; small batches)")
     ap.add_argument("--parallel", default="image", choices=["image", "class"],
                     help="image: each rank gets its own images (weak scaling, no exchange); class: every rank gets the SAME "
                          "images and a slice of the kept classes, one state all-reduce per class layer (strong scaling)")

@@ -194,3 +194,21 @@ def test_class_sharded_path_emulated_on_one_gpu():
     y = assemble_class_sharded(gathered, out[0][1], T)
     assert bool(((y == -100.0) == (ref == -100.0)).all())
     assert (y - ref).abs().max().item() <= 1e-5
+
+
+def test_cuda_graph_replay_matches_eager():
+    from cat_seg_b200.host_pipeline import GraphRunner
+    cfg = vitb()
+    sd = make_state_dict(cfg, 2)
+    a = _cuda(make_inputs(cfg, 1, 5, 2))
+    b = _cuda(make_inputs(cfg, 1, 5, 7))
+    for prec in ("exact", "fast"):
+        m = Aggregator(**cfg.ctor_kwargs(), precision=prec)
+        m.load_state_dict(sd, strict=False)
+        m = m.cuda()
+        eager_b = m(*b).clone()
+        run = GraphRunner(m, *a)
+        yb = run(*b).clone()
+        ya = run(*a).clone()
+        assert torch.equal(yb, eager_b), prec                    # same kernels, same order: bit-exact
+        assert torch.equal(ya, m(*a)), prec
