@@ -32,6 +32,7 @@ using namespace fast;
 struct BandConvParams {
   const void* in;            // [S][Win*Win][CIN]  fp32 (IN_F32) or bf16
   const float* in_stats;     // [S][nb_in][G_in][2] partial (sum, sumsq); nullptr: no GroupNorm on the input
+  const float* in_ss;        // [S][CIN][2] GroupNorm (scale, shift) of the input, from gn_finalize_kernel (set when in_stats is)
   int nb_in;
   float in_count;            // elements per (slice, group)
   const float *gamma, *beta; // [CIN]
@@ -241,22 +242,9 @@ __global__ void __launch_bounds__(BAND_THREADS, CTAS) band_conv_kernel(BandConvP
     // ---- GroupNorm parameters of the input (fixed-order reduction of the producer's band partials)
     if (p.in_stats != nullptr) {
       if (tid < CIN) {
-        const int g = tid >> 4, G = CIN / 16;
-        float s = 0.f, ss = 0.f;
-        float2 part[16];                                 // nb_in <= 16: all partials in flight at once, summed in order
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          part[i] = i < p.nb_in ? __ldg(reinterpret_cast<const float2*>(p.in_stats + (((long long)sl * p.nb_in + i) * G + g) * 2))
-                                : make_float2(0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (i < p.nb_in) { s += part[i].x; ss += part[i].y; }
-        float mean = s / p.in_count;
-        float var = fmaxf(ss / p.in_count - mean * mean, 0.0f);
-        float rstd = rsqrtf(var + 1e-5f);
-        float sc = rstd * p.gamma[tid];
-        s_scale[tid] = sc;
-        s_shift[tid] = p.beta[tid] - mean * sc;
+        const float2 v = __ldg(reinterpret_cast<const float2*>(p.in_ss) + (long long)sl * CIN + tid);
+        s_scale[tid] = v.x;
+        s_shift[tid] = v.y;
       }
       __syncthreads();
     }
@@ -439,6 +427,31 @@ __global__ void __launch_bounds__(BAND_THREADS, CTAS) band_conv_kernel(BandConvP
   if (warp == 0) umma::tmem_dealloc<C::TMEM_COLS>(tm);
 }
 
+// GroupNorm coefficients of a producer's output, once per slice: fixed-order sum of the band partials, then
+// scale = rstd * gamma, shift = beta - mean * scale (the band kernels used to redo this per band: ~2 K cycles each).
+__global__ void gn_finalize_kernel(const float* __restrict__ stats, int nb, int cin, float count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ ss, int nslice) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nslice * cin) return;
+  const int sl = i / cin, c = i % cin, g = c >> 4, G = cin / 16;
+  float s = 0.f, q = 0.f;
+  for (int b = 0; b < nb; ++b) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(stats + (((long long)sl * nb + b) * G + g) * 2));
+    s += v.x; q += v.y;
+  }
+  const float mean = s / count;
+  const float var = fmaxf(q / count - mean * mean, 0.0f);
+  const float rstd = rsqrtf(var + 1e-5f);
+  const float sc = rstd * gamma[c];
+  reinterpret_cast<float2*>(ss)[i] = make_float2(sc, beta[c] - mean * sc);
+}
+static cudaError_t launch_gn_finalize(const float* stats, int nb, int cin, float count, const float* gamma, const float* beta,
+                                      float* ss, int nslice, cudaStream_t st) {
+  const int n = nslice * cin;
+  gn_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(stats, nb, cin, count, gamma, beta, ss, nslice);
+  return cudaGetLastError();
+}
+
 template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD, int CTAS = 2>
 static cudaError_t launch_band(const BandConvParams& p, int num_sms, cudaStream_t st) {
   using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS>;
@@ -604,6 +617,7 @@ size_t decoder_fast_scratch_bytes(const DecoderDims& d, int B, int chunk) {
   b += (size_t)B * (4 * hw * d.D1 + 16 * hw * d.D2) * 4;                 // E1, E2
   b += (size_t)chunk * (2 * 4 * hw * d.D1 + 2 * 16 * hw * d.D2) * 2;     // c1a c1b c2a c2b (bf16)
   b += (size_t)chunk * (4 * 4 + 8 * 4 + 12 * 2 + 16 * 2) * 2 * 4 + 4096; // band statistics
+  b += (size_t)chunk * 64 * 2 * 4 + 256;                                  // GroupNorm (scale, shift) of the current producer
   return (b + 255) / 256 * 256;
 }
 
@@ -627,6 +641,7 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
   float* s1b = reinterpret_cast<float*>(take((size_t)chunk * 8 * 4 * 2 * 4));    // NB=8 G=4
   float* s2a = reinterpret_cast<float*>(take((size_t)chunk * 12 * 2 * 2 * 4));   // NB=12 G=2
   float* s2b = reinterpret_cast<float*>(take((size_t)chunk * 16 * 2 * 2 * 4));   // NB=16 G=2
+  float* gss = reinterpret_cast<float*>(take((size_t)chunk * 64 * 2 * 4));       // (scale, shift) [chunk][<=64][2]
 
   {
     GuidConvA a{dg0, d.G1, 2 * d.H, 2 * d.W};
@@ -643,18 +658,22 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
     p.in = X + (long long)s0 * hw * d.C0; p.in_stats = nullptr; p.wimg = w.w1; p.emap = E1; p.out = c1a; p.out_stats = s1a;
     CKF((launch_band<128, 64, 64, true, true, 24, 6, false>(p, num_sms, st)));       // (a whole slice per CTA, <...,24,24,false,1>, was measured: no faster)
     // D2: c1a -> c1b, 3x3 64 -> 64 on relu(gn(c1a))
-    p.in = c1a; p.in_stats = s1a; p.nb_in = 4; p.in_count = (float)(4 * hw * 16); p.gamma = wx.gn1a_g; p.beta = wx.gn1a_b;
+    CKF(launch_gn_finalize(s1a, 4, 64, (float)(4 * hw * 16), wx.gn1a_g, wx.gn1a_b, gss, n, st));
+    p.in = c1a; p.in_stats = s1a; p.in_ss = gss; p.nb_in = 4; p.in_count = (float)(4 * hw * 16); p.gamma = wx.gn1a_g; p.beta = wx.gn1a_b;
     p.wimg = w.w2; p.emap = nullptr; p.out = c1b; p.out_stats = s1b;
     CKF((launch_band<64, 64, 64, false, false, 48, 6, false>(p, num_sms, st)));
     // D3: c1b -> c2a (96^2 x 32), composed
+    CKF(launch_gn_finalize(s1b, 8, 64, (float)(4 * hw * 16), wx.gn1b_g, wx.gn1b_b, gss, n, st));
     p.in = c1b; p.in_stats = s1b; p.nb_in = 8; p.gamma = wx.gn1b_g; p.beta = wx.gn1b_b;
     p.wimg = w.w3; p.emap = E2; p.out = c2a; p.out_stats = s2a;
     CKF((launch_band<64, 32, 32, true, false, 48, 4, false>(p, num_sms, st)));   // 4-row bands: the 64 KiB weight set stays resident
     // D4: c2a -> c2b, 3x3 32 -> 32
+    CKF(launch_gn_finalize(s2a, 12, 32, (float)(16 * hw * 16), wx.gn2a_g, wx.gn2a_b, gss, n, st));
     p.in = c2a; p.in_stats = s2a; p.nb_in = 12; p.in_count = (float)(16 * hw * 16); p.gamma = wx.gn2a_g; p.beta = wx.gn2a_b;
     p.wimg = w.w4; p.emap = nullptr; p.out = c2b; p.out_stats = s2b;
     CKF((launch_band<32, 32, 32, false, false, 96, 6, false>(p, num_sms, st)));
     // D5: head 3x3 32 -> 1 (+ bias), scattered to logits[b][class]
+    CKF(launch_gn_finalize(s2b, 16, 32, (float)(16 * hw * 16), wx.gn2b_g, wx.gn2b_b, gss, n, st));
     p.in = c2b; p.in_stats = s2b; p.nb_in = 16; p.gamma = wx.gn2b_g; p.beta = wx.gn2b_b;
     p.wimg = w.w5; p.emap = nullptr; p.out = nullptr; p.out_stats = nullptr;
     CKF((launch_band<32, 16, 16, false, false, 96, 6, true>(p, num_sms, st)));
