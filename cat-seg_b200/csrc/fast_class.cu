@@ -305,9 +305,10 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
 #define CPH(i) do { if (dbg != nullptr && blockIdx.x == 0 && tid == 0) { long long _t = clock64(); pacc##i += _t - t_last; t_last = _t; } } while (0)
 
   for (long long it = blockIdx.x; it < nitems; it += gridDim.x) {
-    const int tl = (int)(it % ntile);
-    const long long bp = it / ntile;
-    const int b = (int)(bp / npix), pix = (int)(bp % npix);
+    const int it32 = (int)it;                                // B * npix * ntile fits 31 bits: no 64-bit divisions
+    const int tl = it32 % ntile;
+    const int bp = it32 / ntile;
+    const int b = bp / npix, pix = bp % npix;
     const int t0 = tl * 128;
     const int nvalid = Te - t0 < 128 ? Te - t0 : 128;
     const long long rstride = (long long)npix * 128;
@@ -315,12 +316,12 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
     {   // the next item's token rows (one 512-byte row per class, 295 KiB apart) and state are prefetched into L2 meanwhile
       const long long itn = it + gridDim.x;
       if (itn < nitems) {
-        const int tln = (int)(itn % ntile);
-        const long long bpn = itn / ntile;
-        const int bn = (int)(bpn / npix), pn = (int)(bpn % npix);
+        const int tln = (int)itn % ntile;
+        const int bpn = (int)itn / ntile;
+        const int bn = bpn / npix, pn = bpn % npix;
         const int nv = Te - tln * 128 < 128 ? Te - tln * 128 : 128;
         if (tid < nv * 4) umma::prefetch_l2(X + (((long long)bn * Te + tln * 128 + (tid >> 2)) * npix + pn) * 128 + (tid & 3) * 32);
-        if (tid < 132) umma::prefetch_l2(state + bpn * kStateFloats + tid * 32);
+        if (tid < 132) umma::prefetch_l2(state + (long long)bpn * kStateFloats + tid * 32);
       }
     }
     if (issuer) {
@@ -330,38 +331,41 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
       }
       __syncwarp();
     }
-    // ---- Bstate [128 k x 144 n] (MN-major, 18 n-groups): thread k = (h, d) writes its whole row; its state loads are
-    //      issued before the LayerNorm prologue so that their latency is covered by it
-    float kv[32];
+    // ---- Bstate [128 k x 144 n] (MN-major, 18 n-groups).  All 512 threads: thread (k, j) = (tid >> 2, tid & 3) loads the
+    //      8 values KV[k][8j .. 8j+8) (consecutive threads read consecutive 32 bytes: coalesced; the earlier form, one
+    //      128-byte row per thread of four warps, took 4.4 K cycles per item) BEFORE the LayerNorm prologue, which covers
+    //      their latency, and afterwards writes chunk gq = 4h + j of row k plus three of the twelve zero chunks.
+    const int bk = tid >> 2, bj = tid & 3, bh = bk >> 5;
+    float kv[8];
     float ks = 0.0f;
-    if (tid < 128) {
-      const float* sp = state + bp * kStateFloats;
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        float4 a = ld4(sp + tid * 32 + i), pz = ld4(pad_state + tid * 32 + i);
-        kv[i] = a.x + pz.x; kv[i + 1] = a.y + pz.y; kv[i + 2] = a.z + pz.z; kv[i + 3] = a.w + pz.w;
-      }
-      ks = sp[4096 + tid] + pad_state[4096 + tid];
+    {
+      const float* sp = state + (long long)bp * kStateFloats + bk * 32 + bj * 8;
+      const float* pp = pad_state + bk * 32 + bj * 8;
+      const float4 a0 = ld4(sp), a1 = ld4(sp + 4), p0 = ld4(pp), p1 = ld4(pp + 4);
+      kv[0] = a0.x + p0.x; kv[1] = a0.y + p0.y; kv[2] = a0.z + p0.z; kv[3] = a0.w + p0.w;
+      kv[4] = a1.x + p1.x; kv[5] = a1.y + p1.y; kv[6] = a1.z + p1.z; kv[7] = a1.w + p1.w;
+      if (bj == 0) ks = state[(long long)bp * kStateFloats + 4096 + bk] + pad_state[4096 + bk];
     }
     ln_rows_to_tile(X + row0off, rstride, nvalid, smem + AP_XN, s_g1, s_be1, warp, 16, lane);
-    if (tid < 128) {
-      const int h = tid >> 5;
+    {
       const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+      uint8_t* brow = smem + AP_BST + bk * 16;
+      *reinterpret_cast<uint4*>(brow + (4 * bh + bj) * LBO_V) =
+          make_uint4(umma::pack_bf16x2(kv[0], kv[1]), umma::pack_bf16x2(kv[2], kv[3]), umma::pack_bf16x2(kv[4], kv[5]),
+                     umma::pack_bf16x2(kv[6], kv[7]));
 #pragma unroll
-      for (int gq = 0; gq < 16; ++gq) {
-        uint4 val = zero4;
-        if ((gq >> 2) == h) {
-          const int j = gq & 3;
-          val = make_uint4(umma::pack_bf16x2(kv[j * 8], kv[j * 8 + 1]), umma::pack_bf16x2(kv[j * 8 + 2], kv[j * 8 + 3]),
-                           umma::pack_bf16x2(kv[j * 8 + 4], kv[j * 8 + 5]), umma::pack_bf16x2(kv[j * 8 + 6], kv[j * 8 + 7]));
-        }
-        *reinterpret_cast<uint4*>(smem + AP_BST + gq * LBO_V + tid * 16) = val;
+      for (int z = 0; z < 3; ++z) {                           // the 12 chunks of the other three heads are zero
+        const int oh = (bh + 1 + z) & 3;
+        *reinterpret_cast<uint4*>(brow + (4 * oh + bj) * LBO_V) = zero4;
       }
-      uint32_t kb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(ks));
-      uint4 dz = zero4;                                       // n = 128 + h holds Ksum for the rows of head h
-      if (h == 0) dz.x = kb; else if (h == 1) dz.x = kb << 16; else if (h == 2) dz.y = kb; else dz.y = kb << 16;
-      *reinterpret_cast<uint4*>(smem + AP_BST + 16 * LBO_V + tid * 16) = dz;
-      *reinterpret_cast<uint4*>(smem + AP_BST + 17 * LBO_V + tid * 16) = zero4;
+      if (bj == 0) {
+        uint32_t kb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(ks));
+        uint4 dz = zero4;                                     // n = 128 + h holds Ksum for the rows of head h
+        if (bh == 0) dz.x = kb; else if (bh == 1) dz.x = kb << 16; else if (bh == 2) dz.y = kb; else dz.y = kb << 16;
+        *reinterpret_cast<uint4*>(brow + 16 * LBO_V) = dz;
+      } else if (bj == 1) {
+        *reinterpret_cast<uint4*>(brow + 17 * LBO_V) = zero4;
+      }
     }
     umma::fence_proxy_async();
     umma::fence_before_sync();
