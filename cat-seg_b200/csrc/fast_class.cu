@@ -99,11 +99,11 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
   long long t_last = clock64(), sacc0 = 0, sacc1 = 0, sacc2 = 0, sacc3 = 0, sacc4 = 0, nt_dbg = 0;
 #define SPH(i) do { if (dbg != nullptr && blockIdx.x == 0 && tid == 0) { long long _t = clock64(); sacc##i += _t - t_last; t_last = _t; } } while (0)
   for (long long it = blockIdx.x; it < nitems; it += gridDim.x) {
-    const int b = (int)(it / npix), pix = (int)(it % npix);
+    const int b = (int)it / npix, pix = (int)it % npix;         // B * npix fits 31 bits: no 64-bit divisions
     {   // the next item's token rows (Te rows of 512 bytes, one per class) are prefetched into L2 meanwhile
       const long long itn = it + gridDim.x;
       if (itn < nitems) {
-        const int bn = (int)(itn / npix), pn = (int)(itn % npix);
+        const int bn = (int)itn / npix, pn = (int)itn % npix;
         for (int i = tid; i < Te * 4; i += 512)
           umma::prefetch_l2(X + (((long long)bn * Te + (i >> 2)) * npix + pn) * 128 + (i & 3) * 32);
       }
