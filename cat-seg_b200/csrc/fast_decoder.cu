@@ -37,7 +37,8 @@ struct BandConvParams {
   float in_count;            // elements per (slice, group)
   const float *gamma, *beta; // [CIN]
   const __nv_bfloat16* wimg; // NIMG images [NOUT x CIN], canonical dense
-  const float* emap;         // [B][Wout*Wout][NREAL] fp32 or nullptr
+  const float* emap;         // composed stages: the additive map re-laid out per accumulator tile (relayout_emap_kernel):
+                             // [B][NB][4 parities][NTILES][NREAL/4][128 rows][4] fp32, else nullptr
   int Te;
   __nv_bfloat16* out;        // [S][Wout*Wout][NREAL]
   float* out_stats;          // [S][NB][G_out][2]
@@ -361,9 +362,12 @@ __global__ void __launch_bounds__(BAND_THREADS, CTAS) band_conv_kernel(BandConvP
               float v[32];
               float4 e4[UPS ? 8 : 1];                          // additive map (composed stages): issued before the TMEM load
               if constexpr (UPS) {
-                const float* e = p.emap + ((long long)b * (C::WOUT * C::WOUT) + (valid ? opix : 0)) * NREAL + c0;
+                // tile-ordered copy of the map: chunk-major inside a tile, so the 32 lanes (= 32 accumulator rows) of one load
+                // read 512 contiguous bytes (one 128-byte row per THREAD cost 1.7 ms per step: 32 lines per instruction)
+                const float* e = p.emap + ((((long long)b * C::NB + band) * 4 + pg) * C::NTILES + t) * (NREAL * 128) +
+                                 ((c0 >> 2) * 128 + q4 * 32 + lane) * 4;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) e4[i] = ld4(e + 4 * i);
+                for (int i = 0; i < 8; ++i) e4[i] = ld4(e + i * 512);
               }
               umma::tmem_ld32(acc_addr + t * NOUT + c0, v);
               if (valid) {
@@ -449,6 +453,43 @@ static cudaError_t launch_gn_finalize(const float* stats, int nb, int cin, float
                                       float* ss, int nslice, cudaStream_t st) {
   const int n = nslice * cin;
   gn_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(stats, nb, cin, count, gamma, beta, ss, nslice);
+  return cudaGetLastError();
+}
+
+// Additive map E [B][Wout*Wout][NREAL] -> accumulator-tile order of the consuming composed stage (see BandConvParams::emap):
+// rows that are halo columns or beyond the band are zero.
+template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD, int CTAS>
+__global__ void relayout_emap_kernel(const float* __restrict__ E, float* __restrict__ Et, int B) {
+  using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS>;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;          // one float4 each
+  const long long total = (long long)B * C::NB * 4 * C::NTILES * (NREAL / 4) * 128;
+  if (i >= total) return;
+  const int row = (int)(i % 128);
+  long long r = i / 128;
+  const int c = (int)(r % (NREAL / 4)); r /= (NREAL / 4);
+  const int t = (int)(r % C::NTILES); r /= C::NTILES;
+  const int pg = (int)(r % 4); r /= 4;
+  const int band = (int)(r % C::NB);
+  const int b = (int)(r / C::NB);
+  const int pr = C::P0 + t * 128 + row;
+  const int yl = pr / C::PW - 1, xl = pr % C::PW - 1;
+  const bool valid = (pr < C::P0 + C::MROWS) && xl >= 0 && xl < WIN_;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid) {
+    const int Yo = 2 * (band * BR + yl) + (pg >> 1), Xo = 2 * xl + (pg & 1);
+    v = ld4(E + ((long long)b * (C::WOUT * C::WOUT) + (long long)Yo * C::WOUT + Xo) * NREAL + c * 4);
+  }
+  st4(Et + i * 4, v);
+}
+template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD, int CTAS = 2>
+static size_t emap_tiled_floats(int B) {
+  using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS>;
+  return (size_t)B * C::NB * 4 * C::NTILES * NREAL * 128;
+}
+template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD, int CTAS = 2>
+static cudaError_t launch_relayout_emap(const float* E, float* Et, int B, cudaStream_t st) {
+  const long long total = (long long)emap_tiled_floats<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS>(B) / 4;
+  relayout_emap_kernel<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(E, Et, B);
   return cudaGetLastError();
 }
 
@@ -615,6 +656,7 @@ size_t decoder_fast_scratch_bytes(const DecoderDims& d, int B, int chunk) {
   size_t hw = (size_t)d.H * d.W;
   size_t b = 0;
   b += (size_t)B * (4 * hw * d.D1 + 16 * hw * d.D2) * 4;                 // E1, E2
+  b += (emap_tiled_floats<128, 64, 64, true, true, 24, 6, false>(B) + emap_tiled_floats<64, 32, 32, true, false, 48, 4, false>(B)) * 4 + 512;   // tile-ordered copies
   b += (size_t)chunk * (2 * 4 * hw * d.D1 + 2 * 16 * hw * d.D2) * 2;     // c1a c1b c2a c2b (bf16)
   b += (size_t)chunk * (4 * 4 + 8 * 4 + 12 * 2 + 16 * 2) * 2 * 4 + 4096; // band statistics
   b += (size_t)chunk * 64 * 2 * 4 + 256;                                  // GroupNorm (scale, shift) of the current producer
@@ -633,6 +675,8 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
   auto take = [&](size_t bytes) { uint8_t* r = ptr; ptr += (bytes + 255) / 256 * 256; return r; };
   float* E1 = reinterpret_cast<float*>(take((size_t)B * 4 * hw * d.D1 * 4));
   float* E2 = reinterpret_cast<float*>(take((size_t)B * 16 * hw * d.D2 * 4));
+  float* E1t = reinterpret_cast<float*>(take(emap_tiled_floats<128, 64, 64, true, true, 24, 6, false>(B) * 4));
+  float* E2t = reinterpret_cast<float*>(take(emap_tiled_floats<64, 32, 32, true, false, 48, 4, false>(B) * 4));
   __nv_bfloat16* c1a = reinterpret_cast<__nv_bfloat16*>(take((size_t)chunk * 4 * hw * d.D1 * 2));
   __nv_bfloat16* c1b = reinterpret_cast<__nv_bfloat16*>(take((size_t)chunk * 4 * hw * d.D1 * 2));
   __nv_bfloat16* c2a = reinterpret_cast<__nv_bfloat16*>(take((size_t)chunk * 16 * hw * d.D2 * 2));
@@ -648,6 +692,8 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
     CKF(launch_igemm(a, w.wg1, 0, 1, B * 4 * hw, d.D1, 9 * d.G1, MapAddStore{E1, w.bmap1, 4 * hw, d.D1}, st));
     GuidConvA a2{dg1, d.G2, 4 * d.H, 4 * d.W};
     CKF(launch_igemm(a2, w.wg2, 0, 1, B * 16 * hw, d.D2, 9 * d.G2, MapAddStore{E2, w.bmap2, 16 * hw, d.D2}, st));
+    CKF((launch_relayout_emap<128, 64, 64, true, true, 24, 6, false>(E1, E1t, B, st)));
+    CKF((launch_relayout_emap<64, 32, 32, true, false, 48, 4, false>(E2, E2t, B, st)));
   }
   const int nslice = B * Te;
   for (int s0 = 0; s0 < nslice; s0 += chunk) {
@@ -655,7 +701,7 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
     BandConvParams p{};
     p.Te = Te; p.slice0 = s0; p.nslice = n; p.T = T; p.classes = classes; p.logits = logits; p.head_bias = head_bias;
     // D1: x (24^2 x 128, fp32) -> c1a (48^2 x 64), composed transposed conv + conv
-    p.in = X + (long long)s0 * hw * d.C0; p.in_stats = nullptr; p.wimg = w.w1; p.emap = E1; p.out = c1a; p.out_stats = s1a;
+    p.in = X + (long long)s0 * hw * d.C0; p.in_stats = nullptr; p.wimg = w.w1; p.emap = E1t; p.out = c1a; p.out_stats = s1a;
     CKF((launch_band<128, 64, 64, true, true, 24, 6, false>(p, num_sms, st)));       // (a whole slice per CTA, <...,24,24,false,1>, was measured: no faster)
     // D2: c1a -> c1b, 3x3 64 -> 64 on relu(gn(c1a))
     CKF(launch_gn_finalize(s1a, 4, 64, (float)(4 * hw * 16), wx.gn1a_g, wx.gn1a_b, gss, n, st));
@@ -665,7 +711,7 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
     // D3: c1b -> c2a (96^2 x 32), composed
     CKF(launch_gn_finalize(s1b, 8, 64, (float)(4 * hw * 16), wx.gn1b_g, wx.gn1b_b, gss, n, st));
     p.in = c1b; p.in_stats = s1b; p.nb_in = 8; p.gamma = wx.gn1b_g; p.beta = wx.gn1b_b;
-    p.wimg = w.w3; p.emap = E2; p.out = c2a; p.out_stats = s2a;
+    p.wimg = w.w3; p.emap = E2t; p.out = c2a; p.out_stats = s2a;
     CKF((launch_band<64, 32, 32, true, false, 48, 4, false>(p, num_sms, st)));   // 4-row bands: the 64 KiB weight set stays resident
     // D4: c2a -> c2b, 3x3 32 -> 32
     CKF(launch_gn_finalize(s2a, 12, 32, (float)(16 * hw * 16), wx.gn2a_g, wx.gn2a_b, gss, n, st));
