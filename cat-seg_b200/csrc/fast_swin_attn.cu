@@ -211,11 +211,13 @@ swin_attn_fast_kernel(float* __restrict__ X, const __nv_bfloat16* __restrict__ a
     // ---- LN1 -> XN (warp per row, 9 rows in flight); the NEXT window's rows are prefetched into L2 meanwhile
     {
       const long long wn = wi + gridDim.x;
-      if (wn < nwin_total && tid < NTOK * 4) {
-        const int nsl = (int)(wn >> 2), nwy = (int)((wn >> 1) & 1), nwx = (int)(wn & 1), r = tid >> 2;
-        const int sy = nwy * WIN + r / WIN, sx = nwx * WIN + r % WIN;
-        const int pix = ((sy + shift) % GRID) * GRID + (sx + shift) % GRID;
-        umma::prefetch_l2(X + ((long long)nsl * (GRID * GRID) + pix) * 128 + (tid & 3) * 32);
+      if (wn < nwin_total) {
+        const int nsl = (int)(wn >> 2), nwy = (int)((wn >> 1) & 1), nwx = (int)(wn & 1);
+        for (int i = tid; i < NTOK * 4; i += SA_THREADS) {          // 576 lines of 128 bytes
+          const int r = i >> 2, sy = nwy * WIN + r / WIN, sx = nwx * WIN + r % WIN;
+          const int pix = ((sy + shift) % GRID) * GRID + (sx + shift) % GRID;
+          umma::prefetch_l2(X + ((long long)nsl * (GRID * GRID) + pix) * 128 + (i & 3) * 32);
+        }
       }
     }
     {
