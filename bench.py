@@ -274,8 +274,7 @@ def run_ours(args):
             if sliding:
                 labels_host.copy_(sw.stitch(yy, 640, 640, want_probs=False, want_labels=True)[1].view(-1), non_blocking=True)
             else:
-                for j in range(B):
-                    labels_host[j].copy_(sw.argmax(yy[j].view(T, -1)), non_blocking=True)
+                labels_host.copy_(sw.argmax_batched(yy.view(B, T, -1)), non_blocking=True)
             done[i & 1].record()
             if i > 0:
                 done[(i - 1) & 1].synchronize()          # the caller consumes the previous step's labels

@@ -923,9 +923,14 @@ extern "C" int catseg_stitch_argmax(const float* win_logits, int T, int S, int k
   return CATSEG_OK;
 }
 
-extern "C" int catseg_argmax(const float* scores, int T, int64_t npix, int32_t* labels_out, catseg_stream stream) {
-  if (!scores || !labels_out || T <= 0 || npix <= 0) return CATSEG_ERR_INVALID;
-  cudaError_t e = launch_argmax(scores, T, npix, labels_out, (cudaStream_t)stream);
+extern "C" int catseg_argmax_batched(const float* scores, int batch, int T, int64_t npix, int32_t* labels_out,
+                                     catseg_stream stream) {
+  if (!scores || !labels_out || batch <= 0 || batch > 65535 || T <= 0 || npix <= 0) return CATSEG_ERR_INVALID;
+  cudaError_t e = launch_argmax(scores, batch, T, npix, labels_out, (cudaStream_t)stream);
   if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return CATSEG_ERR_CUDA; }
   return CATSEG_OK;
+}
+
+extern "C" int catseg_argmax(const float* scores, int T, int64_t npix, int32_t* labels_out, catseg_stream stream) {
+  return catseg_argmax_batched(scores, 1, T, npix, labels_out, stream);
 }

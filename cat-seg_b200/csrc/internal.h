@@ -178,6 +178,6 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
 // ---------------------------------------------------------------- stitch.cu
 cudaError_t launch_stitch(const float* win_logits, int T, int S, int kernel, int stride, int out_res, int height,
                           int width, float* probs_out, int32_t* labels_out, cudaStream_t st);
-cudaError_t launch_argmax(const float* scores, int T, long long npix, int32_t* labels, cudaStream_t st);
+cudaError_t launch_argmax(const float* scores, int batch, int T, long long npix, int32_t* labels, cudaStream_t st);
 
 }  // namespace catseg

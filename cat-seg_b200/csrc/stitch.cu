@@ -273,6 +273,8 @@ __global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ s
   __shared__ int s_bt[8][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long i = (long long)blockIdx.x * 32 + lane;
+  scores += (long long)blockIdx.y * T * npix;                      // batch of independent [T, npix] problems
+  labels += (long long)blockIdx.y * npix;
   float best = -INFINITY;
   int bt = 0x7fffffff;
   if (i < npix) {
@@ -303,8 +305,8 @@ __global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ s
     labels[i] = bt == 0x7fffffff ? 0 : bt;
   }
 }
-cudaError_t launch_argmax(const float* scores, int T, long long npix, int32_t* labels, cudaStream_t st) {
-  argmax_kernel<<<(unsigned)((npix + 31) / 32), 256, 0, st>>>(scores, T, npix, labels);
+cudaError_t launch_argmax(const float* scores, int batch, int T, long long npix, int32_t* labels, cudaStream_t st) {
+  argmax_kernel<<<dim3((unsigned)((npix + 31) / 32), (unsigned)batch), 256, 0, st>>>(scores, T, npix, labels);
   return cudaGetLastError();
 }
 

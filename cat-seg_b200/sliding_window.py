@@ -91,3 +91,20 @@ def argmax(scores: torch.Tensor) -> torch.Tensor:
     if rc != 0:
         raise RuntimeError(f"catseg_argmax failed ({rc})")
     return out
+
+
+def argmax_batched(scores: torch.Tensor) -> torch.Tensor:
+    """scores [B, T, ...] CUDA fp32 -> int32 labels [B, ...] in one launch (per image: train_net.py:58)."""
+    if not scores.is_cuda:
+        raise RuntimeError("catseg_b200.argmax_batched runs on CUDA tensors only (no CPU fallback)")
+    lib = _lib.load()
+    x = scores.detach().to(torch.float32).contiguous()
+    B, T = x.shape[0], x.shape[1]
+    npix = x[0, 0].numel()
+    out = torch.empty((B,) + tuple(x.shape[2:]), dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.catseg_argmax_batched(C.c_void_p(x.data_ptr()), B, T, npix, C.c_void_p(out.data_ptr()),
+                                       C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"catseg_argmax_batched failed ({rc})")
+    return out

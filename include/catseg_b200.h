@@ -159,6 +159,8 @@ int catseg_stitch_argmax(const float* win_logits, int T, int S, int kernel, int 
                          catseg_stream stream);
 /* Plain per-pixel argmax over the class axis of [T, H*W] (first maximum wins). */
 int catseg_argmax(const float* scores, int T, int64_t npix, int32_t* labels_out, catseg_stream stream);
+/* Same for a batch of independent [T, npix] score sets laid out [batch, T, npix] -> labels [batch, npix] (one launch). */
+int catseg_argmax_batched(const float* scores, int batch, int T, int64_t npix, int32_t* labels_out, catseg_stream stream);
 
 /* Library identity, e.g. "catseg_b200 0.1 sm_100a". */
 const char* catseg_version(void);

@@ -130,6 +130,12 @@ def test_stitch_matches_oracle():
         assert torch.equal(sw.argmax(ref_p.cuda()).cpu().long(), ref_l)
 
 
+def test_argmax_batched_matches_torch():
+    g = torch.Generator().manual_seed(3)
+    s = torch.randn(3, 37, 50, 7, generator=g)
+    assert torch.equal(sw.argmax_batched(s.cuda()).cpu().long(), s.argmax(dim=1))
+
+
 def test_argmax_first_max_wins():
     s = torch.zeros(4, 10, 10)
     s[1] = 1.0
