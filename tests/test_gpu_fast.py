@@ -95,3 +95,15 @@ def test_fast_full_size_properties():
     ye = e.cuda()(*cu)
     assert torch.equal((ye != -100.0).flatten(2).any(dim=2), kept)
     assert rel_l2(y1[kept].cpu(), ye[kept].cpu()) <= FAST_RELL2
+
+
+@pytest.mark.parametrize("case", [(vitb(prompt_channel=3), 1, 4), (vitb(pooling_size=(4, 4), pad_len=5), 1, 7),
+                                  (vitb(pad_len=0), 2, 3)])
+def test_fast_edge_configs(case):
+    """P = 3 prompt templates (the tcgen05 embedding covers P = 1 only: the fp32 embedding kernel takes over, everything
+    else stays on the fast path), 4x4 pooling with truncation, and pad_len = 0."""
+    cfg, B, T = case
+    y, ref = _run(cfg, B, T, 3, "fast")
+    assert bool(((y == -100.0) == (ref == -100.0)).all())
+    kept = ref != -100.0
+    assert (y[kept] - ref[kept]).abs().max().item() <= FAST_MAXABS and rel_l2(y[kept], ref[kept]) <= FAST_RELL2
