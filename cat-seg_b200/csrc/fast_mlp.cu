@@ -154,10 +154,12 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w, long long* __
             float v[32];
             umma::tmem_ld32(lane_addr + t * 128 + cq * 32, v);
             const float* bb = s_b1 + j * 128 + cq * 32;
+            if (ACT == 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float a = v[i] + bb[i];
-              v[i] = ACT == 0 ? gelu_fast(a) : fmaxf(a, 0.0f);
+              for (int i = 0; i < 32; i += 2) gelu_fast_pair(v[i], v[i + 1], bb[i], bb[i + 1]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bb[i], 0.0f);
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c)
