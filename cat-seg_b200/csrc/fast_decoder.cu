@@ -64,22 +64,25 @@ struct BandCfg {
   // two CTAs per SM (half-height bands, <= 113 KiB and <= 256 TMEM columns each): one CTA's staging / epilogue
   // overlaps the other's MMAs.  Small weight sets stay resident, larger ones stream through a ring.
   // (the whole weight set may stay in shared memory when, together with the band image, it fits half an SM)
-  static constexpr bool RESIDENT = NIMG * WBYTES <= 24 * 1024 || IMG_BYTES + NIMG * WBYTES <= 108 * 1024;
-  // streaming ring: 48 KiB deep, so that the prefetch distance (in MMA time) exceeds the ~1 us L2->SMEM latency
-  static constexpr int NSLOT = RESIDENT ? NIMG : (int)(48 * 1024 / WBYTES);
+  static constexpr bool RESIDENT = NIMG * WBYTES <= 24 * 1024 || IMG_BYTES + NIMG * WBYTES <= (CTAS == 2 ? 108 : 200) * 1024;
+  // streaming ring: 48 KiB deep (96 KiB when the CTA owns the SM), so that the prefetch distance (in MMA time) exceeds the
+  // ~1 us L2->SMEM latency
+  static constexpr int NSLOT = RESIDENT ? NIMG : (int)((CTAS == 2 ? 48 : 96) * 1024 / WBYTES);
+  // worker warps (staging + epilogues): 8 per CTA with two CTAs per SM, 16 when the CTA owns the SM; one more warp issues
+  static constexpr int NWW = CTAS == 2 ? 8 : 16, NWT = NWW * 32, THREADS = NWT + 32, NTG = NWW / 4;
   static constexpr int NB = WIN_ / BR;                 // bands per slice
   static constexpr int WOUT = UPS ? 2 * WIN_ : WIN_;
   static constexpr int GOUT = HEAD ? 1 : NREAL / 16;
   static constexpr uint32_t SM_W = IMG_BYTES;
   static constexpr uint32_t SM_SC = SM_W + NSLOT * WBYTES;            // scale[CIN], shift[CIN]
-  static constexpr uint32_t SM_ST = SM_SC + 2 * CIN * 4;              // [8 warps][GOUT][2]
-  static constexpr uint32_t SM_BAR = (SM_ST + 8 * GOUT * 2 * 4 + 15) / 16 * 16;
-  static constexpr uint32_t SMEM = SM_BAR + (2 * NSLOT + 17) * 8 + 16;   // ring barriers + [2 sets][8 tiles] accumulator barriers
+  static constexpr uint32_t SM_ST = SM_SC + 2 * CIN * 4;              // [NWW warps][GOUT][2]
+  static constexpr uint32_t SM_BAR = (SM_ST + NWW * GOUT * 2 * 4 + 15) / 16 * 16;
+  static constexpr uint32_t SMEM = SM_BAR + (2 * NSLOT + 33) * 8 + 16;   // ring barriers + [2 sets][16 tiles] accumulator barriers
   static constexpr uint32_t IDESC = umma::make_idesc_bf16(128, NOUT);
   // CTAS = CTAs per SM: 2 (half-height bands; one CTA's staging / epilogue overlaps the other's MMAs) or 1 (a band as
   // tall as the shared memory allows: fewer M-tile remainders and one pass over a streamed weight set per band)
   static constexpr int TMEM_COLS = CTAS == 2 ? 256 : 512;
-  static_assert(NTILES * NOUT <= TMEM_COLS, "TMEM columns");
+  static_assert(NTILES * NOUT <= TMEM_COLS && NTILES <= 16, "TMEM columns");
   static_assert(SMEM <= (CTAS == 2 ? 113 * 1024 : 227 * 1024), "shared memory budget");
   static_assert(WIN_ % BR == 0 && CIN % 16 == 0 && NOUT % 16 == 0, "shape");
 };
@@ -89,10 +92,9 @@ struct BandCfg {
 // blocked while its MMAs execute: a worker that also issued would join every epilogue late and hold up its barrier.
 // The composed (UPS) stages compute four output parities from the same staged image: with two accumulator sets the MMAs
 // of parity pg+1 run under the epilogue of parity pg.
-constexpr int BAND_THREADS = 288;
 
 template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD, int CTAS>
-__global__ void __launch_bounds__(BAND_THREADS, CTAS) band_conv_kernel(BandConvParams p) {
+__global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_conv_kernel(BandConvParams p) {
   using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS>;
   extern __shared__ __align__(1024) uint8_t smem[];
   float* s_scale = reinterpret_cast<float*>(smem + C::SM_SC);
@@ -101,9 +103,9 @@ __global__ void __launch_bounds__(BAND_THREADS, CTAS) band_conv_kernel(BandConvP
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + C::SM_BAR);   // [NSLOT]
   uint64_t* bar_empty = bar_full + C::NSLOT;                             // [NSLOT]
   uint64_t* bar_acc = bar_empty + C::NSLOT;                              // [2 accumulator sets][8]: one barrier per M tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 16);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q4 = warp & 3, tgrp = (warp >> 2) & 1;
-  const bool issuer = __shfl_sync(0xffffffffu, warp, 0) == 8;           // warp-uniform role
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 32);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q4 = warp & 3, tgrp = (warp >> 2) % C::NTG;
+  const bool issuer = __shfl_sync(0xffffffffu, warp, 0) == C::NWW;           // warp-uniform role
   constexpr int ACC_COLS = C::NTILES * NOUT;
   constexpr int SETS = (C::NPG > 1 && 2 * ACC_COLS <= C::TMEM_COLS) ? 2 : 1;
 
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(BAND_THREADS, CTAS) band_conv_kernel(BandConvP
   const long long total_loads = C::RESIDENT ? 1 : mine * C::NIMG;
 
   if (tid == 0) {
-    for (int i = 0; i < 2 * C::NSLOT + 16; ++i) umma::mbar_init(&bar_full[i], 1);
+    for (int i = 0; i < 2 * C::NSLOT + 32; ++i) umma::mbar_init(&bar_full[i], 1);
     umma::mbar_fence_init();
   }
   if (warp == 0) umma::tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(BAND_THREADS, CTAS) band_conv_kernel(BandConvP
               umma::mma_bf16_ss(tm + set * ACC_COLS + t * NOUT, a_tile + (uint64_t)(k * 2 * (C::LBO_I >> 4)),
                                 b_desc + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC, (tap > 0 || k > 0) ? 1u : 0u);
           }
-          umma::mma_commit(&bar_acc[set * 8 + t]);
+          umma::mma_commit(&bar_acc[set * 16 + t]);
         }
       }
       __syncwarp();
@@ -220,11 +222,25 @@ __global__ void __launch_bounds__(BAND_THREADS, CTAS) band_conv_kernel(BandConvP
     }
     if (umma::elect_one()) {
 #pragma unroll
-      for (int t = 0; t < C::NTILES; ++t) umma::mma_commit(&bar_acc[set * 8 + t]);
+      for (int t = 0; t < C::NTILES; ++t) umma::mma_commit(&bar_acc[set * 16 + t]);
     }
     __syncwarp();
   };
 
+  // band statistics: per-warp partials in s_part, summed in fixed order by 2 GOUT threads one barrier later (while the
+  // other warps already wait for the next band's MMAs)
+  long long stats_item = -1;
+  auto flush_stats = [&]() {
+    if (!HEAD && stats_item >= 0 && tid < C::GOUT * 2) {
+      float a = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < C::NWW; ++w8) a += s_part[w8 * C::GOUT * 2 + tid];
+      p.out_stats[stats_item * (C::GOUT * 2) + tid] = a;
+    }
+  };
+  float2 ss_next = make_float2(0.f, 0.f);
+  if (p.in_stats != nullptr && tid < CIN && (long long)blockIdx.x < nitems)
+    ss_next = __ldg(reinterpret_cast<const float2*>(p.in_ss) + ((long long)blockIdx.x / C::NB) * CIN + tid);
   for (long long it = blockIdx.x; it < nitems; it += gridDim.x) {
     const int sl = (int)(it / C::NB), band = (int)(it % C::NB);
     const int gslice = p.slice0 + sl;
@@ -237,15 +253,17 @@ __global__ void __launch_bounds__(BAND_THREADS, CTAS) band_conv_kernel(BandConvP
         constexpr int ESZ = IN_F32 ? 4 : 2;
         const char* base = reinterpret_cast<const char*>(p.in) + (((long long)sln * WIN_ + y0) * WIN_) * CIN * ESZ;
         const int nlines = (y1 - y0) * WIN_ * CIN * ESZ / 128;
-        for (int i = tid; i < nlines; i += 256) umma::prefetch_l2(base + (long long)i * 128);
+        for (int i = tid; i < nlines; i += C::NWT) umma::prefetch_l2(base + (long long)i * 128);
       }
     }
     // ---- GroupNorm parameters of the input (fixed-order reduction of the producer's band partials)
+    //      (fetched one band ahead: the dependent L2 round trip used to cost ~1.5 K cycles per band)
     if (p.in_stats != nullptr) {
       if (tid < CIN) {
-        const float2 v = __ldg(reinterpret_cast<const float2*>(p.in_ss) + (long long)sl * CIN + tid);
-        s_scale[tid] = v.x;
-        s_shift[tid] = v.y;
+        s_scale[tid] = ss_next.x;
+        s_shift[tid] = ss_next.y;
+        const long long itn = it + gridDim.x;
+        if (itn < nitems) ss_next = __ldg(reinterpret_cast<const float2*>(p.in_ss) + (itn / C::NB) * CIN + tid);
       }
       __syncthreads();
     }
@@ -258,7 +276,7 @@ __global__ void __launch_bounds__(BAND_THREADS, CTAS) band_conv_kernel(BandConvP
       const int y_first = band * BR - 1;
       constexpr int U = IN_F32 ? 4 : 8;
       constexpr int NCHUNK = C::NP * C::KCH;
-      static_assert(256 % C::KCH == 0, "a thread keeps its channel group");
+      static_assert(C::NWT % C::KCH == 0, "a thread keeps its channel group");
       const int c = tid % C::KCH;
       float sc[8], sh[8];
       if (p.in_stats != nullptr) {
@@ -266,12 +284,12 @@ __global__ void __launch_bounds__(BAND_THREADS, CTAS) band_conv_kernel(BandConvP
         for (int j = 0; j < 8; ++j) { sc[j] = s_scale[c * 8 + j]; sh[j] = s_shift[c * 8 + j]; }
       }
 #pragma unroll 1
-      for (int base = tid; base < NCHUNK; base += 256 * U) {
+      for (int base = tid; base < NCHUNK; base += C::NWT * U) {
         uint4 raw[U][IN_F32 ? 2 : 1];
         bool inb[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int idx = base + u * 256;
+          const int idx = base + u * C::NWT;
           const int pp = idx / C::KCH;
           const int yy = y_first + pp / C::PW, xx = pp % C::PW - 1;
           inb[u] = idx < NCHUNK && yy >= 0 && yy < WIN_ && xx >= 0 && xx < WIN_;
@@ -286,7 +304,7 @@ __global__ void __launch_bounds__(BAND_THREADS, CTAS) band_conv_kernel(BandConvP
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int idx = base + u * 256;
+          const int idx = base + u * C::NWT;
           if (idx >= NCHUNK) continue;
           const int pp = idx / C::KCH;
           uint4 val = make_uint4(0u, 0u, 0u, 0u);
@@ -316,6 +334,7 @@ __global__ void __launch_bounds__(BAND_THREADS, CTAS) band_conv_kernel(BandConvP
     umma::fence_before_sync();
     __syncthreads();
     BPH(0);
+    flush_stats();
     if (issuer) {
       umma::fence_after_sync();
       issue_group(0, 0);
@@ -343,10 +362,13 @@ __global__ void __launch_bounds__(BAND_THREADS, CTAS) band_conv_kernel(BandConvP
           opix = (long long)Yo * C::WOUT + Xo;
         };
 #pragma unroll 1
-        for (int t = tgrp; t < C::NTILES; t += 2) {
-          umma::mbar_wait(&bar_acc[set * 8 + t], ph_acc[set]);
+        // work units: whole tiles over the two warp sets, or (tile, 32-channel chunk) pairs over four warp sets
+        constexpr int NCH = HEAD ? 1 : NREAL / 32;
+        constexpr bool SPLIT_CH = C::NTG > 2 && NCH > 1;
+        for (int t = SPLIT_CH ? (tgrp / NCH) % (C::NTG / NCH) : tgrp; t < C::NTILES; t += SPLIT_CH ? C::NTG / NCH : C::NTG) {
+          umma::mbar_wait(&bar_acc[set * 16 + t], ph_acc[set]);
           umma::fence_after_sync();
-          if (t == tgrp) BPH(1);
+          if (t == 0) BPH(1);
           bool valid; long long opix;
           tile_geom(t, valid, opix);
           if constexpr (HEAD) {
@@ -359,6 +381,7 @@ __global__ void __launch_bounds__(BAND_THREADS, CTAS) band_conv_kernel(BandConvP
           } else {
 #pragma unroll
             for (int c0 = 0; c0 < NREAL; c0 += 32) {
+              if (SPLIT_CH && (c0 / 32) != tgrp % NCH) continue;     // warp-uniform
               float v[32];
               float4 e4[UPS ? 8 : 1];                          // additive map (composed stages): issued before the TMEM load
               if constexpr (UPS) {
@@ -413,13 +436,7 @@ __global__ void __launch_bounds__(BAND_THREADS, CTAS) band_conv_kernel(BandConvP
           if (lane == 0) { s_part[(warp * C::GOUT + g) * 2] = s; s_part[(warp * C::GOUT + g) * 2 + 1] = ss; }
         }
       }
-      __syncthreads();
-      if (tid < C::GOUT * 2) {
-        float a = 0.f;
-        for (int w8 = 0; w8 < 8; ++w8) a += s_part[w8 * C::GOUT * 2 + tid];
-        p.out_stats[((long long)sl * C::NB + band) * C::GOUT * 2 + tid] = a;
-      }
-      __syncthreads();
+      stats_item = it;      // summed and stored behind the next band's staging barrier (or after the loop)
     }
     BPH(3);
     ++nit_dbg;
@@ -428,6 +445,7 @@ __global__ void __launch_bounds__(BAND_THREADS, CTAS) band_conv_kernel(BandConvP
 #undef BPH
   umma::fence_before_sync();
   __syncthreads();
+  flush_stats();
   if (warp == 0) umma::tmem_dealloc<C::TMEM_COLS>(tm);
 }
 
@@ -515,14 +533,14 @@ static cudaError_t launch_band(const BandConvParams& p, int num_sms, cudaStream_
   }
   BandConvParams q = p;
   q.dbg = dbg_on ? dbg : nullptr;
-  kern<<<grid, BAND_THREADS, C::SMEM, st>>>(q);
+  kern<<<grid, C::THREADS, C::SMEM, st>>>(q);
   if (dbg_on) {
     long long hb[8];
     cudaStreamSynchronize(st);
     cudaMemcpy(hb, dbg, sizeof(hb), cudaMemcpyDeviceToHost);
     double n = hb[4] > 0 ? (double)hb[4] : 1.0;
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BAND_THREADS, C::SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::THREADS, C::SMEM);
     fprintf(stderr, "[occupancy %d CTAs/SM, smem %u] ", occ, (unsigned)C::SMEM);
     fprintf(stderr, "[band_conv<%d,%d,ups=%d,W=%d> cycles/band over %lld bands, thread 0 (issuer)] stage %.0f | mma issue+wait %.0f (x%d parity groups) "
             "| epilogue %.0f | stats %.0f | (GN params of the input %.0f, before 'stage')\n", CIN, NOUT, (int)UPS, WIN_, hb[4], hb[0] / n, hb[1] / n, C::NPG, hb[2] / n, hb[3] / n, hb[5] / n);
@@ -652,11 +670,34 @@ struct MapAddStore {
   }
 };
 
+// Stage configurations <CIN, NOUT, NREAL, UPS, IN_F32, WIN, BR, HEAD, CTAS>: N = two 9-warp CTAs per SM were intended (but only
+// one fits the register file, see BandCfg::NWW), W = one 17-warp CTA per SM with bands twice as tall.  CATSEG_DEC_WIDE is a
+// bit mask (bit i = stage D(i+1) uses W), read once; it exists for A/B measurements.
+#define D1N 128, 64, 64, true, true, 24, 6, false, 2
+#define D1W 128, 64, 64, true, true, 24, 12, false, 1
+#define D2N 64, 64, 64, false, false, 48, 6, false, 2
+#define D2W 64, 64, 64, false, false, 48, 12, false, 1
+#define D3N 64, 32, 32, true, false, 48, 4, false, 2
+#define D3W 64, 32, 32, true, false, 48, 16, false, 1
+#define D4N 32, 32, 32, false, false, 96, 6, false, 2
+#define D4W 32, 32, 32, false, false, 96, 12, false, 1
+#define D5N 32, 16, 16, false, false, 96, 6, true, 2
+#define D5W 32, 16, 16, false, false, 96, 12, true, 1
+static int dec_wide_mask() {
+  static int m = -1;
+  if (m < 0) {
+    const char* e = getenv("CATSEG_DEC_WIDE");
+    m = e ? atoi(e) & 31 : 6;
+  }
+  return m;
+}
+static size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
+
 size_t decoder_fast_scratch_bytes(const DecoderDims& d, int B, int chunk) {
   size_t hw = (size_t)d.H * d.W;
   size_t b = 0;
   b += (size_t)B * (4 * hw * d.D1 + 16 * hw * d.D2) * 4;                 // E1, E2
-  b += (emap_tiled_floats<128, 64, 64, true, true, 24, 6, false>(B) + emap_tiled_floats<64, 32, 32, true, false, 48, 4, false>(B)) * 4 + 512;   // tile-ordered copies
+  b += (max_sz(emap_tiled_floats<D1N>(B), emap_tiled_floats<D1W>(B)) + max_sz(emap_tiled_floats<D3N>(B), emap_tiled_floats<D3W>(B))) * 4 + 512;   // tile-ordered copies
   b += (size_t)chunk * (2 * 4 * hw * d.D1 + 2 * 16 * hw * d.D2) * 2;     // c1a c1b c2a c2b (bf16)
   b += (size_t)chunk * (4 * 4 + 8 * 4 + 12 * 2 + 16 * 2) * 2 * 4 + 4096; // band statistics
   b += (size_t)chunk * 64 * 2 * 4 + 256;                                  // GroupNorm (scale, shift) of the current producer
@@ -671,12 +712,13 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
                              int* launches, cudaStream_t st) {
   const int hw = d.H * d.W;
   int nl = 0;
+  const int wide = dec_wide_mask();
   uint8_t* ptr = reinterpret_cast<uint8_t*>(scratch);
   auto take = [&](size_t bytes) { uint8_t* r = ptr; ptr += (bytes + 255) / 256 * 256; return r; };
   float* E1 = reinterpret_cast<float*>(take((size_t)B * 4 * hw * d.D1 * 4));
   float* E2 = reinterpret_cast<float*>(take((size_t)B * 16 * hw * d.D2 * 4));
-  float* E1t = reinterpret_cast<float*>(take(emap_tiled_floats<128, 64, 64, true, true, 24, 6, false>(B) * 4));
-  float* E2t = reinterpret_cast<float*>(take(emap_tiled_floats<64, 32, 32, true, false, 48, 4, false>(B) * 4));
+  float* E1t = reinterpret_cast<float*>(take(max_sz(emap_tiled_floats<D1N>(B), emap_tiled_floats<D1W>(B)) * 4));
+  float* E2t = reinterpret_cast<float*>(take(max_sz(emap_tiled_floats<D3N>(B), emap_tiled_floats<D3W>(B)) * 4));
   __nv_bfloat16* c1a = reinterpret_cast<__nv_bfloat16*>(take((size_t)chunk * 4 * hw * d.D1 * 2));
   __nv_bfloat16* c1b = reinterpret_cast<__nv_bfloat16*>(take((size_t)chunk * 4 * hw * d.D1 * 2));
   __nv_bfloat16* c2a = reinterpret_cast<__nv_bfloat16*>(take((size_t)chunk * 16 * hw * d.D2 * 2));
@@ -692,8 +734,8 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
     CKF(launch_igemm(a, w.wg1, 0, 1, B * 4 * hw, d.D1, 9 * d.G1, MapAddStore{E1, w.bmap1, 4 * hw, d.D1}, st));
     GuidConvA a2{dg1, d.G2, 4 * d.H, 4 * d.W};
     CKF(launch_igemm(a2, w.wg2, 0, 1, B * 16 * hw, d.D2, 9 * d.G2, MapAddStore{E2, w.bmap2, 16 * hw, d.D2}, st));
-    CKF((launch_relayout_emap<128, 64, 64, true, true, 24, 6, false>(E1, E1t, B, st)));
-    CKF((launch_relayout_emap<64, 32, 32, true, false, 48, 4, false>(E2, E2t, B, st)));
+    if (wide & 1) CKF((launch_relayout_emap<D1W>(E1, E1t, B, st))); else CKF((launch_relayout_emap<D1N>(E1, E1t, B, st)));
+    if (wide & 4) CKF((launch_relayout_emap<D3W>(E2, E2t, B, st))); else CKF((launch_relayout_emap<D3N>(E2, E2t, B, st)));
   }
   const int nslice = B * Te;
   for (int s0 = 0; s0 < nslice; s0 += chunk) {
@@ -702,27 +744,31 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
     p.Te = Te; p.slice0 = s0; p.nslice = n; p.T = T; p.classes = classes; p.logits = logits; p.head_bias = head_bias;
     // D1: x (24^2 x 128, fp32) -> c1a (48^2 x 64), composed transposed conv + conv
     p.in = X + (long long)s0 * hw * d.C0; p.in_stats = nullptr; p.wimg = w.w1; p.emap = E1t; p.out = c1a; p.out_stats = s1a;
-    CKF((launch_band<128, 64, 64, true, true, 24, 6, false>(p, num_sms, st)));       // (a whole slice per CTA, <...,24,24,false,1>, was measured: no faster)
+    if (wide & 1) CKF((launch_band<D1W>(p, num_sms, st))); else CKF((launch_band<D1N>(p, num_sms, st)));
+    const int nb1 = (wide & 1) ? BandCfg<D1W>::NB : BandCfg<D1N>::NB;
     // D2: c1a -> c1b, 3x3 64 -> 64 on relu(gn(c1a))
-    CKF(launch_gn_finalize(s1a, 4, 64, (float)(4 * hw * 16), wx.gn1a_g, wx.gn1a_b, gss, n, st));
-    p.in = c1a; p.in_stats = s1a; p.in_ss = gss; p.nb_in = 4; p.in_count = (float)(4 * hw * 16); p.gamma = wx.gn1a_g; p.beta = wx.gn1a_b;
+    CKF(launch_gn_finalize(s1a, nb1, 64, (float)(4 * hw * 16), wx.gn1a_g, wx.gn1a_b, gss, n, st));
+    p.in = c1a; p.in_stats = s1a; p.in_ss = gss; p.nb_in = nb1; p.in_count = (float)(4 * hw * 16); p.gamma = wx.gn1a_g; p.beta = wx.gn1a_b;
     p.wimg = w.w2; p.emap = nullptr; p.out = c1b; p.out_stats = s1b;
-    CKF((launch_band<64, 64, 64, false, false, 48, 6, false>(p, num_sms, st)));
+    if (wide & 2) CKF((launch_band<D2W>(p, num_sms, st))); else CKF((launch_band<D2N>(p, num_sms, st)));
+    const int nb2 = (wide & 2) ? BandCfg<D2W>::NB : BandCfg<D2N>::NB;
     // D3: c1b -> c2a (96^2 x 32), composed
-    CKF(launch_gn_finalize(s1b, 8, 64, (float)(4 * hw * 16), wx.gn1b_g, wx.gn1b_b, gss, n, st));
-    p.in = c1b; p.in_stats = s1b; p.nb_in = 8; p.gamma = wx.gn1b_g; p.beta = wx.gn1b_b;
+    CKF(launch_gn_finalize(s1b, nb2, 64, (float)(4 * hw * 16), wx.gn1b_g, wx.gn1b_b, gss, n, st));
+    p.in = c1b; p.in_stats = s1b; p.nb_in = nb2; p.gamma = wx.gn1b_g; p.beta = wx.gn1b_b;
     p.wimg = w.w3; p.emap = E2t; p.out = c2a; p.out_stats = s2a;
-    CKF((launch_band<64, 32, 32, true, false, 48, 4, false>(p, num_sms, st)));   // 4-row bands: the 64 KiB weight set stays resident
+    if (wide & 4) CKF((launch_band<D3W>(p, num_sms, st))); else CKF((launch_band<D3N>(p, num_sms, st)));   // the 64 KiB weight set stays resident
+    const int nb3 = (wide & 4) ? BandCfg<D3W>::NB : BandCfg<D3N>::NB;
     // D4: c2a -> c2b, 3x3 32 -> 32
-    CKF(launch_gn_finalize(s2a, 12, 32, (float)(16 * hw * 16), wx.gn2a_g, wx.gn2a_b, gss, n, st));
-    p.in = c2a; p.in_stats = s2a; p.nb_in = 12; p.in_count = (float)(16 * hw * 16); p.gamma = wx.gn2a_g; p.beta = wx.gn2a_b;
+    CKF(launch_gn_finalize(s2a, nb3, 32, (float)(16 * hw * 16), wx.gn2a_g, wx.gn2a_b, gss, n, st));
+    p.in = c2a; p.in_stats = s2a; p.nb_in = nb3; p.in_count = (float)(16 * hw * 16); p.gamma = wx.gn2a_g; p.beta = wx.gn2a_b;
     p.wimg = w.w4; p.emap = nullptr; p.out = c2b; p.out_stats = s2b;
-    CKF((launch_band<32, 32, 32, false, false, 96, 6, false>(p, num_sms, st)));
+    if (wide & 8) CKF((launch_band<D4W>(p, num_sms, st))); else CKF((launch_band<D4N>(p, num_sms, st)));
+    const int nb4 = (wide & 8) ? BandCfg<D4W>::NB : BandCfg<D4N>::NB;
     // D5: head 3x3 32 -> 1 (+ bias), scattered to logits[b][class]
-    CKF(launch_gn_finalize(s2b, 16, 32, (float)(16 * hw * 16), wx.gn2b_g, wx.gn2b_b, gss, n, st));
-    p.in = c2b; p.in_stats = s2b; p.nb_in = 16; p.gamma = wx.gn2b_g; p.beta = wx.gn2b_b;
+    CKF(launch_gn_finalize(s2b, nb4, 32, (float)(16 * hw * 16), wx.gn2b_g, wx.gn2b_b, gss, n, st));
+    p.in = c2b; p.in_stats = s2b; p.nb_in = nb4; p.gamma = wx.gn2b_g; p.beta = wx.gn2b_b;
     p.wimg = w.w5; p.emap = nullptr; p.out = nullptr; p.out_stats = nullptr;
-    CKF((launch_band<32, 16, 16, false, false, 96, 6, true>(p, num_sms, st)));
+    if (wide & 16) CKF((launch_band<D5W>(p, num_sms, st))); else CKF((launch_band<D5N>(p, num_sms, st)));
   }
   if (launches) *launches += nl;
   return cudaSuccess;
