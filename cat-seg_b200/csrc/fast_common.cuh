@@ -113,14 +113,14 @@ __device__ __forceinline__ void ln_rows_to_tiles_pipelined(const float* __restri
 __device__ __forceinline__ float gelu_fast(float x) {
   const float xc = fminf(fmaxf(x, -3.8f), 3.8f);
   const float t = xc * xc;
-  float q = fmaf(7.331543372e-08f, t, -4.544918738e-06f);
-  q = fmaf(q, t, 1.213695141e-04f);
-  q = fmaf(q, t, -1.863094512e-03f);
-  q = fmaf(q, t, 1.863326877e-02f);
-  q = fmaf(q, t, -1.314395666e-01f);
-  q = fmaf(q, t, 7.973535061e-01f);
-  const float h = 0.5f * x;
-  return fmaf(h, xc * q, h);
+  // gelu = x (0.5 + xc Q(t) / 2): the 1/2 is folded into the coefficients (exact), one instruction fewer than h + h xc Q
+  float q = fmaf(0.5f * 7.331543372e-08f, t, 0.5f * -4.544918738e-06f);
+  q = fmaf(q, t, 0.5f * 1.213695141e-04f);
+  q = fmaf(q, t, 0.5f * -1.863094512e-03f);
+  q = fmaf(q, t, 0.5f * 1.863326877e-02f);
+  q = fmaf(q, t, 0.5f * -1.314395666e-01f);
+  q = fmaf(q, t, 0.5f * 7.973535061e-01f);
+  return x * fmaf(xc, q, 0.5f);
 }
 
 // ---- packed fp32 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 on register pairs).  Same FLOP rate as the scalar forms
@@ -148,21 +148,23 @@ __device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigne
 }
 
 // gelu_fast on two values at once: the same operations in the same order per element (bit-identical results),
-// 7.5 instead of 13 instructions per element.  x0/x1 are updated in place; (b0, b1) is the bias to add first.
+// 7 instead of 12 instructions per element.  x0/x1 are updated in place; (b0, b1) is the bias to add first.
 __device__ __forceinline__ void gelu_fast_pair(float& x0, float& x1, float b0, float b1) {
   const unsigned long long X = add2(pk2(x0, x1), pk2(b0, b1));
   float a0, a1;
   unpk2(X, a0, a1);
   const unsigned long long XC = pk2(fminf(fmaxf(a0, -3.8f), 3.8f), fminf(fmaxf(a1, -3.8f), 3.8f));
   const unsigned long long T = mul2(XC, XC);
-  unsigned long long Q = fma2(pk2(7.331543372e-08f, 7.331543372e-08f), T, pk2(-4.544918738e-06f, -4.544918738e-06f));
-  Q = fma2(Q, T, pk2(1.213695141e-04f, 1.213695141e-04f));
-  Q = fma2(Q, T, pk2(-1.863094512e-03f, -1.863094512e-03f));
-  Q = fma2(Q, T, pk2(1.863326877e-02f, 1.863326877e-02f));
-  Q = fma2(Q, T, pk2(-1.314395666e-01f, -1.314395666e-01f));
-  Q = fma2(Q, T, pk2(7.973535061e-01f, 7.973535061e-01f));
-  const unsigned long long H = mul2(X, pk2(0.5f, 0.5f));
-  unpk2(fma2(H, mul2(XC, Q), H), x0, x1);
+  constexpr float c6 = 0.5f * 7.331543372e-08f, c5 = 0.5f * -4.544918738e-06f, c4 = 0.5f * 1.213695141e-04f,
+                  c3 = 0.5f * -1.863094512e-03f, c2 = 0.5f * 1.863326877e-02f, c1 = 0.5f * -1.314395666e-01f,
+                  c0 = 0.5f * 7.973535061e-01f;
+  unsigned long long Q = fma2(pk2(c6, c6), T, pk2(c5, c5));
+  Q = fma2(Q, T, pk2(c4, c4));
+  Q = fma2(Q, T, pk2(c3, c3));
+  Q = fma2(Q, T, pk2(c2, c2));
+  Q = fma2(Q, T, pk2(c1, c1));
+  Q = fma2(Q, T, pk2(c0, c0));
+  unpk2(mul2(X, fma2(XC, Q, pk2(0.5f, 0.5f))), x0, x1);
 }
 
 // fp32 staging tile [128 rows][128 cols] with a 132-float row stride: conflict-free both for "thread = row"

@@ -432,21 +432,22 @@ swin_attn_fast_kernel(float* __restrict__ X, const __nv_bfloat16* __restrict__ a
       umma::fence_after_sync();
       issue_wgemm(hbase + 8, d_o, bar_y);
     }
-    umma::mbar_wait(bar_y, ph_y); ph_y ^= 1;
-    umma::fence_after_sync();
-    if (issuer) { nconsumed += 2; refill(); }
-    PH(6);
-    // ---- x1 = x + Y + bproj : thread = feature, 36-40 tokens each; a warp touches 128 contiguous bytes per token
+    // ---- x1 = x + Y + bproj : thread = feature, 36-40 tokens each; a warp touches 128 contiguous bytes per token.
+    //      The shortcut loads are issued BEFORE the wait for the projection MMAs (all in flight under them).
     {
       const int f = q4 * 32 + lane;
       const float bp = s_bp[f];
-      float xv[40];                                                  // all shortcut loads in flight at once
+      float xv[40];
 #pragma unroll
       for (int j = 0; j < 5; ++j)
         if (tg0 + j < tg1) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) xv[j * 8 + i] = Xs[(long long)tokpix[(tg0 + j) * 8 + i] * 128 + f];
         }
+      umma::mbar_wait(bar_y, ph_y); ph_y ^= 1;
+      umma::fence_after_sync();
+      if (issuer) { nconsumed += 2; refill(); }
+      PH(6);
 #pragma unroll
       for (int j = 0; j < 5; ++j)
         if (tg0 + j < tg1) {                                         // warp-uniform
