@@ -401,7 +401,13 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
     umma::fence_before_sync();
     __syncthreads();
     CPH(2);
-    // ---- [num | den] = phi(q) Bstate
+    // ---- [num | den] = phi(q) Bstate.  The shortcut rows (warp per row, coalesced) are fetched under these MMAs.
+    float4 xv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int r = warp * 8 + i;
+      xv[i] = r < nvalid ? ld4(X + row0off + (long long)r * rstride + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     if (issuer) {
       umma::fence_after_sync();
       if (umma::elect_one()) {
@@ -415,17 +421,9 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
     umma::mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
     umma::fence_after_sync();
     CPH(3);
-    // ---- x tile -> staging (warp per row, coalesced; phi(q) and Bstate are dead now)
-    {
-      float4 xv[8];
+    // ---- x tile -> staging (phi(q) and Bstate are dead now)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        int r = warp * 8 + i;
-        xv[i] = r < nvalid ? ld4(X + row0off + (long long)r * rstride + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) st4(stage + (warp * 8 + i) * STG_LD + lane * 4, xv[i]);
-    }
+    for (int i = 0; i < 8; ++i) st4(stage + (warp * 8 + i) * STG_LD + lane * 4, xv[i]);
     __syncthreads();
     CPH(4);
     // ---- x1 = x + num/(den+eps)*S ; z -> staging ; LN2 statistics
