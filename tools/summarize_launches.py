@@ -25,10 +25,13 @@ def main(path):
         except ValueError:
             pass
     ids = sorted(L)
-    last = [i for i in ids if "normalize_img" in L[i]["name"]][-1]
+    starts = [i for i in ids if "normalize_img" in L[i]["name"]]
+    last, end = starts[-1], ids[-1] + 1
+    if len(starts) > 1 and end - last < last - starts[-2]:      # the capture stopped inside the last forward: use the one before
+        last, end = starts[-2], starts[-1]
     agg = collections.OrderedDict()
     for i in ids:
-        if i < last:
+        if i < last or i >= end:
             continue
         d = L[i]
         a = agg.setdefault(d["name"], [0, 0.0, 0.0, 0.0, 0.0, 0.0])
