@@ -107,3 +107,19 @@ def test_fast_edge_configs(case):
     assert bool(((y == -100.0) == (ref == -100.0)).all())
     kept = ref != -100.0
     assert (y[kept] - ref[kept]).abs().max().item() <= FAST_MAXABS and rel_l2(y[kept], ref[kept]) <= FAST_RELL2
+
+
+@pytest.mark.parametrize("mask", ["0", "31"])
+def test_decoder_band_shapes_all_pass(mask):
+    """Every decoder stage exists in two shapes (two 9-warp CTAs per SM / one 17-warp CTA with taller bands); the
+    default mixes them by measurement.  CATSEG_DEC_WIDE is read once per process, so the all-narrow and all-wide
+    settings run the decoder parity cases in a child process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CATSEG_DEC_WIDE=mask)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_fast.py"), "-x", "-q", "-m", "gpu",
+                        "-k", "fast_matches_oracle and decoder"], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "3 passed" in r.stdout, r.stdout[-500:]
