@@ -78,6 +78,9 @@ _SIGS = [
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     ("catseg_argmax", C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     ("catseg_argmax_batched", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+    ("catseg_guidance_upsample", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_void_p]),
+    ("catseg_strip_cls_nchw", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 ]
 # int (*catseg_allreduce_fn)(void* ctx, float* buf, size_t count, catseg_stream stream)
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)

@@ -931,6 +931,23 @@ extern "C" int catseg_argmax_batched(const float* scores, int batch, int T, int6
   return CATSEG_OK;
 }
 
+extern "C" int catseg_guidance_upsample(const float* tokens, const float* weight, const float* bias, float* out, int B,
+                                       int width, int cout, int kernel, int grid, catseg_stream stream) {
+  if (!tokens || !weight || !bias || !out || B <= 0 || width <= 0 || cout <= 0 || kernel <= 0 || kernel > 8 || grid <= 0 ||
+      (long long)B * grid * grid > 0x7fffffffLL / 2 || (long long)cout * kernel * kernel > 0x7fffffffLL / 2)
+    return CATSEG_ERR_INVALID;
+  cudaError_t e = launch_guidance_upsample(tokens, weight, bias, out, B, width, cout, kernel, grid, (cudaStream_t)stream);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return CATSEG_ERR_CUDA; }
+  return CATSEG_OK;
+}
+
+extern "C" int catseg_strip_cls_nchw(const float* feats, float* out, int B, int C, int grid, catseg_stream stream) {
+  if (!feats || !out || B <= 0 || B > 65535 || C <= 0 || grid <= 0) return CATSEG_ERR_INVALID;
+  cudaError_t e = launch_strip_cls_nchw(feats, out, B, C, grid, (cudaStream_t)stream);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return CATSEG_ERR_CUDA; }
+  return CATSEG_OK;
+}
+
 extern "C" int catseg_argmax(const float* scores, int T, int64_t npix, int32_t* labels_out, catseg_stream stream) {
   return catseg_argmax_batched(scores, 1, T, npix, labels_out, stream);
 }

@@ -179,5 +179,9 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
 cudaError_t launch_stitch(const float* win_logits, int T, int S, int kernel, int stride, int out_res, int height,
                           int width, float* probs_out, int32_t* labels_out, cudaStream_t st);
 cudaError_t launch_argmax(const float* scores, int batch, int T, long long npix, int32_t* labels, cudaStream_t st);
+// guidance_pyramid.cu: ConvTranspose2d(stride == kernel) from hooked CLIP tokens, CLS strip + NCHW transpose
+cudaError_t launch_guidance_upsample(const float* tokens, const float* weight, const float* bias, float* out, int B,
+                                     int width, int cout, int ks, int grid, cudaStream_t st);
+cudaError_t launch_strip_cls_nchw(const float* feats, float* out, int B, int C, int grid, cudaStream_t st);
 
 }  // namespace catseg

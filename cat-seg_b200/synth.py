@@ -122,3 +122,22 @@ def make_inputs(cfg: AggregatorConfig, B: int, T: int, seed: int = 0, same_text:
     g1 = torch.randn(B, cfg.decoder_guidance_dims[0], 2 * H, 2 * W, generator=g)
     g2 = torch.randn(B, cfg.decoder_guidance_dims[1], 4 * H, 4 * W, generator=g)
     return img, text.contiguous(), [img, g1, g2]
+
+
+def make_pyramid_inputs(width: int, B: int, seed: int = 0, grid: int = 24, feat_dim: int = 0):
+    """Seeded synthetic inputs of the guidance pyramid producers (cat_seg_model.py:176-185): clip_features
+    [B, 1+grid^2, feat_dim or width], two hooked layer outputs [1+grid^2, B, width], and ConvTranspose2d parameters
+    in the module's own layout / default-init scale (upsample1: width->256 k2, upsample2: width->128 k4)."""
+    g = torch.Generator().manual_seed(4321 + seed)
+    L = 1 + grid * grid
+    fd = feat_dim or width
+    clip = torch.randn(B, L, fd, generator=g)
+    la = torch.randn(L, B, width, generator=g)
+    lb = torch.randn(L, B, width, generator=g)
+    def uni(shape, bound):
+        return (torch.rand(shape, generator=g) * 2 - 1) * bound
+    w1 = uni((width, 256, 2, 2), (1.0 / (256 * 4)) ** 0.5)
+    b1 = uni((256,), (1.0 / (256 * 4)) ** 0.5)
+    w2 = uni((width, 128, 4, 4), (1.0 / (128 * 16)) ** 0.5)
+    b2 = uni((128,), (1.0 / (128 * 16)) ** 0.5)
+    return clip, la, lb, w1, b1, w2, b2

@@ -162,6 +162,17 @@ int catseg_argmax(const float* scores, int T, int64_t npix, int32_t* labels_out,
 /* Same for a batch of independent [T, npix] score sets laid out [batch, T, npix] -> labels [batch, npix] (one launch). */
 int catseg_argmax_batched(const float* scores, int batch, int T, int64_t npix, int32_t* labels_out, catseg_stream stream);
 
+/* Guidance pyramid producers, the step before the boundary (cat_seg_model.py:80-82 modules, :176-185 use).
+ *   catseg_guidance_upsample: nn.ConvTranspose2d(width, cout, kernel_size=k, stride=k) applied to a hooked CLIP layer
+ *   output.  tokens [1 + grid*grid][B][width] fp32 (row 0 = CLS, skipped: the "(H W) B C -> B C H W" rearrange of
+ *   :183-184 is index arithmetic), weight [width][cout][k][k] and bias [cout] exactly as the module stores them,
+ *   out [B][cout][grid*k][grid*k] fp32 NCHW = the g1 / g2 argument of catseg_forward.  fp32 arithmetic.
+ *   catseg_strip_cls_nchw: clip_features[:, 1:, :] + "B (H W) C -> B C H W" (:179,182 and cat_seg_head.py:2009):
+ *   feats [B][1 + grid*grid][C] -> out [B][C][grid][grid] = the img_feats / g0 argument. */
+int catseg_guidance_upsample(const float* tokens, const float* weight, const float* bias, float* out, int B, int width,
+                             int cout, int kernel, int grid, catseg_stream stream);
+int catseg_strip_cls_nchw(const float* feats, float* out, int B, int C, int grid, catseg_stream stream);
+
 /* Library identity, e.g. "catseg_b200 0.1 sm_100a". */
 const char* catseg_version(void);
 

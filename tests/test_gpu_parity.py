@@ -218,3 +218,34 @@ def test_cuda_graph_replay_matches_eager():
         ya = run(*a).clone()
         assert torch.equal(yb, eager_b), prec                    # same kernels, same order: bit-exact
         assert torch.equal(ya, m(*a)), prec
+
+
+# ---- guidance pyramid producers: C-ABI kernels vs the oracle
+@pytest.mark.parametrize("width,B,seed", [(64, 2, 0), (1024, 1, 1), (768, 3, 2)])
+def test_guidance_pyramid_matches_oracle(width, B, seed):
+    from cat_seg_b200.guidance import GuidancePyramid
+    from cat_seg_b200.synth import make_pyramid_inputs
+    from oracle.guidance_oracle import guidance_pyramid
+    clip, la, lb, w1, b1, w2, b2 = make_pyramid_inputs(width, B, seed, feat_dim=width // 2 + 3)
+    ref = guidance_pyramid(clip, la, lb, w1, b1, w2, b2)
+    m = GuidancePyramid(proj_dim=width)
+    missing = m.load_state_dict({"upsample1.weight": w1, "upsample1.bias": b1, "upsample2.weight": w2, "upsample2.bias": b2})
+    assert not missing.missing_keys and not missing.unexpected_keys
+    out = m.cuda()(clip.cuda(), la.cuda(), lb.cuda())
+    assert list(out) == ["res5", "res4", "res3"]                      # the reference's dict order (cat_seg_model.py:186)
+    assert torch.equal(out["res3"].cpu(), ref["res3"])                # pure re-layout: bit exact
+    for k in ("res4", "res5"):
+        got = out[k].cpu()
+        assert got.shape == ref[k].shape
+        # fp32 FFMA accumulation over `width` terms vs the float64-accumulated oracle: |err| <= ~width * 2^-24 * |terms|
+        assert (got - ref[k]).abs().max().item() <= 2e-5, (k, (got - ref[k]).abs().max().item())
+
+
+def test_guidance_pyramid_rejects_bad_arguments():
+    from cat_seg_b200.guidance import strip_cls_nchw, upsample_tokens
+    with pytest.raises(RuntimeError):
+        strip_cls_nchw(torch.zeros(1, 577, 8))                        # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        strip_cls_nchw(torch.zeros(1, 500, 8, device="cuda"))
+    with pytest.raises(ValueError):
+        upsample_tokens(torch.zeros(577, 1, 8, device="cuda"), torch.zeros(9, 4, 2, 2), torch.zeros(4))
