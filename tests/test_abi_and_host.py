@@ -104,3 +104,18 @@ def test_stitch_oracle_properties():
     logits[:, 1] = -100.0
     probs, _ = stitch_oracle.stitch(logits, 320, 480)
     assert probs.shape == (3, 320, 480) and float(probs[1].abs().max()) == 0.0
+
+
+def test_committed_launch_summary_is_reproducible():
+    """profiles/r01_ncu_launch_summary_cfg4_b16.txt is what tools/summarize_launches.py prints for the committed ncu list."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csv = os.path.join(root, "profiles", "r01_ncu_launches_cfg4_b16.csv")
+    txt = os.path.join(root, "profiles", "r01_ncu_launch_summary_cfg4_b16.txt")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "summarize_launches.py"), csv], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip() == open(txt).read().strip()
+    # the kernels named in the summary are the ones the library exports today (decoder shapes included)
+    assert "swin_attn_fast_kernel" in r.stdout and "band_conv_kernel<64, 64, 64, 0, 0, 48, 12, 0, 1>" in r.stdout
