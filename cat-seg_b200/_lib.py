@@ -40,18 +40,24 @@ STAGES = ("prep", "embed", "swin", "class", "decoder", "swin_mlp")
 FAST_BITS = {"swin_mlp": 1, "swin_attn": 2, "class": 4, "decoder": 8, "prep": 16}
 
 
+PRECISE_SPLIT = 0x100
+
+
 def precision_mask(spec: str) -> int:
-    """'exact' -> 0; 'fast' -> every stage with a tcgen05 kernel; 'fast:swin_mlp,decoder' -> those stages."""
+    """'exact' -> 0; 'fast' / 'precise' -> every stage with a tcgen05 kernel (single fp16 operands / hi+lo fp16
+    pairs on the value path); 'fast:swin_mlp,decoder' / 'precise:class' -> those stages, the others EXACT."""
     if spec == "exact":
         return 0
-    if spec == "fast":
-        return 0x7FFFFFFF
-    if spec.startswith("fast:"):
-        m = 0
-        for part in spec[5:].split(","):
-            m |= FAST_BITS[part.strip()]
-        return m
-    raise ValueError(f"bad precision {spec!r}: use 'exact', 'fast' or 'fast:<stage>[,<stage>]' with stages {sorted(FAST_BITS)}")
+    for mode, extra in (("fast", 0), ("precise", PRECISE_SPLIT)):
+        if spec == mode:
+            return 0x1F | extra
+        if spec.startswith(mode + ":"):
+            m = extra
+            for part in spec[len(mode) + 1:].split(","):
+                m |= FAST_BITS[part.strip()]
+            return m
+    raise ValueError(f"bad precision {spec!r}: use 'exact', 'fast', 'precise' or '<mode>:<stage>[,<stage>]' with stages "
+                     f"{sorted(FAST_BITS)}")
 
 # every symbol include/catseg_b200.h declares: (name, restype, argtypes)
 _SIGS = [

@@ -25,6 +25,8 @@ struct Param {
 thread_local std::string g_create_error;
 
 constexpr int kImplementedFast = CATSEG_FAST_SWIN_MLP | CATSEG_FAST_SWIN_ATTN | CATSEG_FAST_DECODER | CATSEG_FAST_CLASS | CATSEG_FAST_PREP;   // stages that have a tcgen05 kernel in this build
+// stages that have a PRECISE (hi + lo fp16 operand pair) kernel; the others run the EXACT kernel in that mode
+constexpr int kImplementedSplit = CATSEG_FAST_SWIN_MLP | CATSEG_FAST_PREP;
 constexpr int kMaxProfForwards = 64;
 constexpr int kMaxSegments = 40;
 
@@ -37,9 +39,13 @@ struct catseg_handle {
   size_t raw_floats = 0;
   float* packed = nullptr;
   size_t packed_floats = 0;
-  __nv_bfloat16* wimg = nullptr;    // bf16 UMMA weight images (FAST path)
+  __half* wimg = nullptr;            // fp16 UMMA weight images (FAST path)
   size_t wimg_elems = 0;
   int fast_mask = 0;
+  bool split = false;                // PRECISE: the stages in fast_mask run their hi+lo operand-pair kernels
+  __half* wimg_split = nullptr;      // hi/lo fp16 weight images of the PRECISE kernels
+  size_t wimg_split_elems = 0;
+  std::vector<MlpSplitW> swin_mlp_split;   // [L*2]
   int num_sms = 148;
   std::vector<MlpFastW> swin_mlp_fast;   // [L*2]
   std::vector<SwinAttnFastW> swin_attn_fast;   // [L*2]
@@ -197,7 +203,8 @@ extern "C" int catseg_create(const catseg_config* cfg, catseg_handle** out) {
   }
   catseg_handle* h = new catseg_handle();
   h->cfg = c;
-  h->fast_mask = c.precision & kImplementedFast;
+  h->split = (c.precision & CATSEG_PRECISE_SPLIT) != 0;
+  h->fast_mask = c.precision & (h->split ? kImplementedSplit : kImplementedFast);
   cudaGetDevice(&h->device);
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
   build_param_table(h);
@@ -206,13 +213,22 @@ extern "C" int catseg_create(const catseg_config* cfg, catseg_handle** out) {
     return fail(nullptr, CATSEG_ERR_CUDA, "cudaMalloc of the parameter store failed");
   }
   cudaMemset(h->raw, 0, h->raw_floats * sizeof(float));
+  // everything catseg_forward needs besides the caller's buffers is created here: the library does not allocate on the hot path
+  if (cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    catseg_destroy(h);
+    return fail(nullptr, CATSEG_ERR_CUDA, "stream / event creation failed");
+  }
+  h->ev.resize((size_t)kMaxProfForwards * kMaxSegments * 2, nullptr);     // timing events are created by catseg_set_profiling
   *out = h;
   return CATSEG_OK;
 }
 
 extern "C" int catseg_destroy(catseg_handle* h) {
   if (!h) return CATSEG_OK;
-  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->wimg_split) cudaFree(h->wimg_split);
   if (h->raw) cudaFree(h->raw);
   if (h->packed) cudaFree(h->packed);
   if (h->wimg) cudaFree(h->wimg);
@@ -241,6 +257,9 @@ extern "C" int catseg_set_param(catseg_handle* h, const char* name, const float*
       return fail(h, CATSEG_ERR_WEIGHTS, "parameter %s: expected %lld values, got %lld", name, (long long)p.numel, (long long)numel);
     CUDA_OK(h, cudaMemcpy(h->raw + p.offset, src, (size_t)numel * sizeof(float),
                           src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    // a device-to-device cudaMemcpy does not block the host and the legacy stream is not ordered against the
+    // (non-blocking) stream catseg_finalize_params packs on: wait here, so the caller may also free `src` on return
+    if (src_is_device) CUDA_OK(h, cudaStreamSynchronize(cudaStreamLegacy));
     p.set = true;
     h->finalized = false;
     return CATSEG_OK;
@@ -467,14 +486,14 @@ extern "C" int catseg_finalize_params(catseg_handle* h, catseg_stream stream) {
   pack_all(pk);
   if (pk.err != cudaSuccess) return fail(h, CATSEG_ERR_CUDA, "packing failed: %s", cudaGetErrorString(pk.err));
   // ---- bf16 UMMA weight images for the FAST kernels
-  if (h->fast_mask) {
+  if (h->fast_mask && !h->split) {
     const int L = h->cfg.num_layers;
     const size_t kImg = 128 * 128;
     size_t need = (size_t)L * 2 * (8 + 5) * kImg + (size_t)L * 13 * kImg;
     if (!h->wimg || h->wimg_elems < need) {
       if (h->wimg) cudaFree(h->wimg);
       h->wimg = nullptr;
-      CUDA_OK(h, cudaMalloc(&h->wimg, need * sizeof(__nv_bfloat16)));
+      CUDA_OK(h, cudaMalloc(&h->wimg, need * sizeof(__half)));
       h->wimg_elems = need;
     }
     h->swin_mlp_fast.assign(L * 2, MlpFastW{});
@@ -485,14 +504,14 @@ extern "C" int catseg_finalize_params(catseg_handle* h, catseg_stream stream) {
       for (int k = 0; k < 2; ++k) {
         snprintf(b, sizeof(b), "layers.%d.swin_block.block_%d", l, k + 1);
         std::string q(b);
-        __nv_bfloat16* img = h->wimg + (size_t)(l * 2 + k) * 13 * kImg;
+        __half* img = h->wimg + (size_t)(l * 2 + k) * 13 * kImg;
         for (int j = 0; j < 4; ++j) {
           CUDA_OK(h, launch_pack_wimg(img + (size_t)(2 * j) * 128 * 128, raw_of(h, q + ".mlp.fc1.weight"), 128, j * 128, 0, st));
           CUDA_OK(h, launch_pack_wimg(img + (size_t)(2 * j + 1) * 128 * 128, raw_of(h, q + ".mlp.fc2.weight"), 512, 0, j * 128, st));
         }
         const SwinBlockW& sw = h->swin[l * 2 + k];
         h->swin_mlp_fast[l * 2 + k] = MlpFastW{img, sw.ln2_g, sw.ln2_b, sw.b1, sw.b2};
-        __nv_bfloat16* aimg = img + 8 * kImg;
+        __half* aimg = img + 8 * kImg;
         for (int hh = 0; hh < 4; ++hh)
           CUDA_OK(h, launch_pack_qkv_head_img(aimg + (size_t)hh * kImg, raw_of(h, q + ".attn.q.weight"),
                                               raw_of(h, q + ".attn.k.weight"), raw_of(h, q + ".attn.v.weight"),
@@ -501,7 +520,29 @@ extern "C" int catseg_finalize_params(catseg_handle* h, catseg_stream stream) {
         h->swin_attn_fast[l * 2 + k] = SwinAttnFastW{aimg, sw.ln1_g, sw.ln1_b, sw.bv, sw.bproj};
       }
   }
-  if (h->fast_mask & CATSEG_FAST_CLASS) {
+  if (h->split && h->fast_mask) {
+    const int L = h->cfg.num_layers;
+    const size_t kImg = 128 * 128;
+    const size_t need = (size_t)L * 2 * 16 * kImg;
+    if (!h->wimg_split || h->wimg_split_elems < need) {
+      if (h->wimg_split) cudaFree(h->wimg_split);
+      h->wimg_split = nullptr;
+      CUDA_OK(h, cudaMalloc(&h->wimg_split, need * sizeof(__half)));
+      h->wimg_split_elems = need;
+    }
+    h->swin_mlp_split.assign(L * 2, MlpSplitW{});
+    char b[160];
+    for (int l = 0; l < L; ++l)
+      for (int k = 0; k < 2; ++k) {
+        snprintf(b, sizeof(b), "layers.%d.swin_block.block_%d", l, k + 1);
+        std::string q(b);
+        __half* img = h->wimg_split + (size_t)(l * 2 + k) * 16 * kImg;
+        CUDA_OK(h, pack_mlp_split(img, raw_of(h, q + ".mlp.fc1.weight"), raw_of(h, q + ".mlp.fc2.weight"), st));
+        const SwinBlockW& sw = h->swin[l * 2 + k];
+        h->swin_mlp_split[l * 2 + k] = MlpSplitW{img, sw.ln2_g, sw.ln2_b, sw.b1, sw.b2};
+      }
+  }
+  if ((h->fast_mask & CATSEG_FAST_CLASS) && !h->split) {
     const int L = h->cfg.num_layers, tg = h->cfg.text_guidance_proj_dim;
     const size_t kImg = 128 * 128;
     h->class_fast.assign(L, ClassFastW{});
@@ -509,11 +550,11 @@ extern "C" int catseg_finalize_params(catseg_handle* h, catseg_stream stream) {
     for (int l = 0; l < L; ++l) {
       snprintf(b, sizeof(b), "layers.%d.attention", l);
       std::string a(b);
-      __nv_bfloat16* img = h->wimg + (size_t)L * 2 * 13 * kImg + (size_t)l * 13 * kImg;
+      __half* img = h->wimg + (size_t)L * 2 * 13 * kImg + (size_t)l * 13 * kImg;
       CUDA_OK(h, launch_pack_wimg(img + 0 * kImg, raw_of(h, a + ".attention.k.weight"), 128 + tg, 0, 0, st));
       CUDA_OK(h, launch_pack_wimg(img + 1 * kImg, raw_of(h, a + ".attention.k.weight"), 128 + tg, 0, 128, st));
       CUDA_OK(h, launch_pack_wimg(img + 2 * kImg, raw_of(h, a + ".attention.v.weight"), 128, 0, 0, st));
-      __nv_bfloat16* ap = img + 3 * kImg;
+      __half* ap = img + 3 * kImg;
       CUDA_OK(h, launch_pack_wimg(ap + 0 * kImg, raw_of(h, a + ".attention.q.weight"), 128 + tg, 0, 0, st));
       CUDA_OK(h, launch_pack_wimg(ap + 1 * kImg, raw_of(h, a + ".attention.q.weight"), 128 + tg, 0, 128, st));
       for (int j = 0; j < 4; ++j) {
@@ -524,7 +565,7 @@ extern "C" int catseg_finalize_params(catseg_handle* h, catseg_stream stream) {
       h->class_fast[l] = ClassFastW{img, ap, cw.ln1_g, cw.ln1_b, cw.ln2_g, cw.ln2_b, cw.bqk, cw.bv, cw.b1, cw.b2};
     }
   }
-  if (h->fast_mask & CATSEG_FAST_DECODER) {
+  if ((h->fast_mask & CATSEG_FAST_DECODER) && !h->split) {
     const catseg_config& c = h->cfg;
     DecoderDims dd{c.feature_resolution[0], c.feature_resolution[1], 128, 128 - c.decoder_guidance_proj_dims[0],
                    c.decoder_guidance_proj_dims[0], c.decoder_dims[0], c.decoder_dims[0] - c.decoder_guidance_proj_dims[1],
@@ -640,8 +681,6 @@ struct Seg {   // RAII-less helper for per-stage event timing
   void begin(int stage) {
     if (!on) return;
     if (h->ev_used >= kMaxProfForwards * kMaxSegments) { on = false; return; }
-    size_t need = (size_t)(h->ev_used + 1) * 2;
-    while (h->ev.size() < need) { cudaEvent_t e; cudaEventCreate(&e); h->ev.push_back(e); }
     if ((int)h->ev_stage.size() <= h->ev_used) h->ev_stage.resize(h->ev_used + 1);
     h->ev_stage[h->ev_used] = stage;
     cudaEventRecord(h->ev[(size_t)h->ev_used * 2], st);
@@ -715,11 +754,6 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
 
   // ---------------- PREP: cost volume, class selection, guidance projections (model.py:693-715)
   seg.begin(CATSEG_STAGE_PREP);
-  if (!h->aux_stream) {
-    CUDA_OK(h, cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
-    CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-  }
   CUDA_OK(h, cudaEventRecord(h->ev_fork, st));
   RUN(launch_normalize_img(img, ws + p.imgn, B, p.C, p.HW, st));
   RUN(launch_normalize_rows(text, ws + p.textn, (long long)B * T * p.P, p.Ct, st));
@@ -740,17 +774,20 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
     RUN(launch_class_pad_state(h->cls[l], 128, ws + p.pad_state + (size_t)l * kStateFloats, p.n_pad, p.S, st));
   }
   const bool class_fast = (h->fast_mask & CATSEG_FAST_CLASS) != 0;
-  __nv_bfloat16* timg = reinterpret_cast<__nv_bfloat16*>(ws + p.timg);
+  __half* timg = reinterpret_cast<__half*>(ws + p.timg);
   if (class_fast) RUN(launch_pack_text_img(ws + p.text_g, timg, B, Te, st));
   // The guidance projections only depend on the inputs: they run on an internal stream beside the cost volume / class
   // selection / text chain (small, latency-bound kernels) and are joined before the embedding.  Externally the call is
   // still ordered on `stream`.
   const bool prep_fast = (h->fast_mask & CATSEG_FAST_PREP) != 0;
+  // the single-term guidance projections are class independent (they cancel in the argmax) but would cap the logits
+  // parity of the PRECISE mode at ~1e-2: that mode keeps them on the fp32 kernels
+  const bool gconv_fast = prep_fast && !h->split;
   {
     cudaStream_t mainst = st;
     CUDA_OK(h, cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));     // ev_fork was recorded at the start of the stage
     cudaStream_t st = h->aux_stream;             // shadows: the launches below go to the internal stream
-    if (prep_fast && h->gconv_img[0]) RUN(launch_gconv_fast(0, g0, h->gconv_img[0], h->gproj_b, ws + p.app_g, B, p.Cg, st));
+    if (gconv_fast && h->gconv_img[0]) RUN(launch_gconv_fast(0, g0, h->gconv_img[0], h->gproj_b, ws + p.app_g, B, p.Cg, st));
     else RUN(launch_conv3x3_nchw(g0, h->gproj_wt, h->gproj_b, ws + p.app_g, B, p.Cg, p.H, p.W, 128, st));
     for (int l = 0; l < p.L; ++l) {
       RUN(launch_layernorm128(ws + p.app_g, ws + p.app_gn, h->gnorm_g[l], h->gnorm_b[l], (long long)B * p.HW, st));
@@ -758,12 +795,12 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
         RUN(launch_linear(ws + p.app_gn, h->swin[l * 2 + k].wg_qk_t, h->swin[l * 2 + k].bqk,
                           ws + p.ag_qk + (size_t)(l * 2 + k) * B * p.HW * 256, (long long)B * p.HW, 256, 128, 0, st));
     }
-    if (prep_fast && h->gconv_img[1])
+    if (gconv_fast && h->gconv_img[1])
       RUN(launch_gconv_fast(1, g1, h->gconv_img[1], h->dgp_b[0], ws + p.dg0, B, c.decoder_guidance_dims[0], st));
     else
       RUN(launch_conv3x3_nchw(g1, h->dgp_wt[0], h->dgp_b[0], ws + p.dg0, B, c.decoder_guidance_dims[0], 2 * p.H, 2 * p.W,
                               p.dd.G1, st));
-    if (prep_fast && h->gconv_img[2])
+    if (gconv_fast && h->gconv_img[2])
       RUN(launch_gconv_fast(2, g2, h->gconv_img[2], h->dgp_b[1], ws + p.dg1, B, c.decoder_guidance_dims[1], st));
     else
       RUN(launch_conv3x3_nchw(g2, h->dgp_wt[1], h->dgp_b[1], ws + p.dg1, B, c.decoder_guidance_dims[1], 4 * p.H, 4 * p.W,
@@ -799,7 +836,7 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
       const int shift = k == 0 ? 0 : c.window_size / 2;
       seg.begin(CATSEG_STAGE_SWIN);
       if (attn_fast) {
-        __nv_bfloat16* agw = reinterpret_cast<__nv_bfloat16*>(ws + p.agw) + (size_t)(l * 2 + k) * B * 16 * 144 * 64;
+        __half* agw = reinterpret_cast<__half*>(ws + p.agw) + (size_t)(l * 2 + k) * B * 16 * 144 * 64;
         RUN(launch_pack_ag_windows(agk, agw, B, shift, st));
         RUN(launch_swin_attn_fast(X, agw, nslice, Te, shift, h->swin_attn_fast[l * 2 + k], h->num_sms, st));
       }
@@ -807,7 +844,8 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
       seg.end();
       if (mlp_fast) {
         seg.begin(CATSEG_STAGE_SWIN_MLP);
-        RUN(launch_mlp_fast(X, (long long)nslice * p.HW, h->swin_mlp_fast[l * 2 + k], 0, h->num_sms, st));
+        if (h->split) RUN(launch_mlp_split(X, nullptr, X, (long long)nslice * p.HW, h->swin_mlp_split[l * 2 + k], 0, h->num_sms, st));
+        else RUN(launch_mlp_fast(X, (long long)nslice * p.HW, h->swin_mlp_fast[l * 2 + k], 0, h->num_sms, st));
         seg.end();
       }
       if (k == 0) TAP(taps->swin_b1[l], X, (size_t)nslice * p.HW * 128);
@@ -892,6 +930,9 @@ extern "C" int catseg_forward(catseg_handle* h, const float* img, const float* t
 
 extern "C" int catseg_set_profiling(catseg_handle* h, int enable) {
   if (!h) return CATSEG_ERR_INVALID;
+  if (enable)                                       // the timing events are created here, not inside catseg_forward
+    for (cudaEvent_t& e : h->ev)
+      if (!e) CUDA_OK(h, cudaEventCreate(&e));
   h->profiling = enable != 0;
   return CATSEG_OK;
 }

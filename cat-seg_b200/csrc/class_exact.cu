@@ -155,12 +155,10 @@ class_state_exact_kernel(const float* __restrict__ X, const float* __restrict__ 
 cudaError_t launch_class_state_exact(const float* X, const float* cg_qk, float* state, int B, int Te, int npix,
                                      int S, const ClassLayerW& w, cudaStream_t st) {
   size_t smem = (size_t)(CW * CT * 128 + 2 * CHUNK * 128) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // per-device function attribute: set on every launch (cheap), a process-wide flag would miss other devices
     cudaError_t e = cudaFuncSetAttribute(class_state_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   class_state_exact_kernel<<<B * npix, CW * 32, smem, st>>>(X, cg_qk, state, Te, npix, S, w);
   return cudaGetLastError();
@@ -327,12 +325,10 @@ cudaError_t launch_class_apply_exact(const float* X, float* Xout, const float* c
                                      const float* pad_state, int B, int Te, int npix, int S, int out_mode,
                                      const ClassLayerW& w, cudaStream_t st) {
   size_t smem = (size_t)(kStateFloats + 2 * CW * CT * 128) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // per-device function attribute: set on every launch (cheap), a process-wide flag would miss other devices
     cudaError_t e = cudaFuncSetAttribute(class_apply_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   class_apply_exact_kernel<<<B * npix, CW * 32, smem, st>>>(X, Xout, cg_qk, state, pad_state, Te, npix, S,
                                                            out_mode, w);

@@ -7,7 +7,7 @@
 //        q -> phi(q) [KV | Ksum] -> x1 = x + att -> LN2 -> MLP (ReLU) -> out
 // Everything that is a contraction runs on the tensor cores:
 //   * q/k projections use K = 256 = [LN1(x) | text guidance]: the guidance half of the A operand is a
-//     ready-made bf16 canonical image per (image, 128-class tile) (built once per forward, fetched by
+//     ready-made fp16 canonical image per (image, 128-class tile) (built once per forward, fetched by
 //     one bulk copy), so the "concat" of the reference costs no thread work (biases in the epilogue);
 //   * KV = K^T [V | 1] contracts over the TOKEN axis: the [token][feature] images written by the
 //     epilogue are consumed as MN-major A and B operands (the ones column yields Ksum);
@@ -25,9 +25,9 @@ using namespace fast;
 
 namespace {
 constexpr uint32_t LBO_V = 128 * 16 + 16;                          // thread-written 128-row tiles (= LBO_T)
-constexpr uint32_t IDESC_N144 = umma::make_idesc_bf16(128, 144, 0, 0);
-constexpr uint32_t IDESC_KV = umma::make_idesc_bf16(128, 144, 1, 1);     // K^T [V|1]: both operands MN-major
-constexpr uint32_t IDESC_APPLY = umma::make_idesc_bf16(128, 144, 0, 1);  // phi(q) (K-major) x Bstate (MN-major)
+constexpr uint32_t IDESC_N144 = umma::make_idesc_f16(128, 144, 0, 0);
+constexpr uint32_t IDESC_KV = umma::make_idesc_f16(128, 144, 1, 1);     // K^T [V|1]: both operands MN-major
+constexpr uint32_t IDESC_APPLY = umma::make_idesc_f16(128, 144, 0, 1);  // phi(q) (K-major) x Bstate (MN-major)
 
 // ---------------------------------------------------------------- state kernel layout
 constexpr uint32_t ST_W = 0;                                       // Wk_x, Wk_g, Wv images: 3 x 32 KiB resident
@@ -57,7 +57,7 @@ static_assert(ST_SMEM <= 232448 && AP_SMEM <= 232448, "shared memory budget");
 // 16 warps: TMEM lane quarter q4 = warp & 3; group grp = warp >> 2: groups 0,1 take the two 64-column halves of k,
 // groups 2,3 those of v.
 __global__ void __launch_bounds__(512, 1)
-class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __restrict__ timg, float* __restrict__ state,
+class_state_fast_kernel(const float* __restrict__ X, const __half* __restrict__ timg, float* __restrict__ state,
                         int B, int Te, int npix, int S, ClassFastW w, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   float* s_g = reinterpret_cast<float*>(smem + ST_PAR);
@@ -162,11 +162,11 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             *reinterpret_cast<uint4*>(img + (cc * 4 + c) * LBO_V + row * 16) =
-                make_uint4(umma::pack_bf16x2(v[c * 8], v[c * 8 + 1]), umma::pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
-                           umma::pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), umma::pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]));
+                make_uint4(umma::pack_h2(v[c * 8], v[c * 8 + 1]), umma::pack_h2(v[c * 8 + 2], v[c * 8 + 3]),
+                           umma::pack_h2(v[c * 8 + 4], v[c * 8 + 5]), umma::pack_h2(v[c * 8 + 6], v[c * 8 + 7]));
         }
         if (grp == 2) {    // ones column (n = 128) and zero padding (n = 129..143)
-          *reinterpret_cast<uint4*>(smem + ST_G + 16 * LBO_V + row * 16) = make_uint4(live ? 0x00003F80u : 0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(smem + ST_G + 16 * LBO_V + row * 16) = make_uint4(live ? 0x00003C00u : 0u, 0u, 0u, 0u);
           *reinterpret_cast<uint4*>(smem + ST_G + 17 * LBO_V + row * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
       }
@@ -180,7 +180,7 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
         if (umma::elect_one()) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma::mma_bf16_ss(tm + ST_TM_ACC, d_kT + (uint64_t)(k * 16), d_vT + (uint64_t)(k * 16), IDESC_KV, (tl > 0 || k > 0) ? 1u : 0u);
+            umma::mma_f16_ss(tm + ST_TM_ACC, d_kT + (uint64_t)(k * 16), d_vT + (uint64_t)(k * 16), IDESC_KV, (tl > 0 || k > 0) ? 1u : 0u);
           umma::mma_commit(bar_m2);
         }
         __syncwarp();
@@ -221,7 +221,7 @@ class_state_fast_kernel(const float* __restrict__ X, const __nv_bfloat16* __rest
 // Residual I/O is coalesced: x is fetched warp-per-row into an fp32 staging tile (over the dead phi(q) /
 // Bstate buffers), updated in place by the row threads, and written back warp-per-row once per item.
 __global__ void __launch_bounds__(512, 1)
-class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, const __nv_bfloat16* __restrict__ timg,
+class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, const __half* __restrict__ timg,
                         const float* __restrict__ state, const float* __restrict__ pad_state, int B, int Te, int npix,
                         int S, int out_mode, ClassFastW w, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -351,15 +351,15 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
       const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
       uint8_t* brow = smem + AP_BST + bk * 16;
       *reinterpret_cast<uint4*>(brow + (4 * bh + bj) * LBO_V) =
-          make_uint4(umma::pack_bf16x2(kv[0], kv[1]), umma::pack_bf16x2(kv[2], kv[3]), umma::pack_bf16x2(kv[4], kv[5]),
-                     umma::pack_bf16x2(kv[6], kv[7]));
+          make_uint4(umma::pack_h2(kv[0], kv[1]), umma::pack_h2(kv[2], kv[3]), umma::pack_h2(kv[4], kv[5]),
+                     umma::pack_h2(kv[6], kv[7]));
 #pragma unroll
       for (int z = 0; z < 3; ++z) {                           // the 12 chunks of the other three heads are zero
         const int oh = (bh + 1 + z) & 3;
         *reinterpret_cast<uint4*>(brow + (4 * oh + bj) * LBO_V) = zero4;
       }
       if (bj == 0) {
-        uint32_t kb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(ks));
+        uint32_t kb = (uint32_t)__half_as_ushort(__float2half_rn(ks));
         uint4 dz = zero4;                                     // n = 128 + h holds Ksum for the rows of head h
         if (bh == 0) dz.x = kb; else if (bh == 1) dz.x = kb << 16; else if (bh == 2) dz.y = kb; else dz.y = kb << 16;
         *reinterpret_cast<uint4*>(brow + 16 * LBO_V) = dz;
@@ -394,8 +394,8 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         *reinterpret_cast<uint4*>(smem + AP_Q + (cq * 4 + c) * LBO_V + row * 16) =
-            make_uint4(umma::pack_bf16x2(v[c * 8], v[c * 8 + 1]), umma::pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
-                       umma::pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), umma::pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]));
+            make_uint4(umma::pack_h2(v[c * 8], v[c * 8 + 1]), umma::pack_h2(v[c * 8 + 2], v[c * 8 + 3]),
+                       umma::pack_h2(v[c * 8 + 4], v[c * 8 + 5]), umma::pack_h2(v[c * 8 + 6], v[c * 8 + 7]));
     }
     umma::fence_proxy_async();
     umma::fence_before_sync();
@@ -413,7 +413,7 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
       if (umma::elect_one()) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma::mma_bf16_ss(tm + AP_TM_ND, d_aq + (uint64_t)(k * 2 * (LBO_V >> 4)), d_abst + (uint64_t)(k * 16), IDESC_APPLY, k > 0);
+          umma::mma_f16_ss(tm + AP_TM_ND, d_aq + (uint64_t)(k * 2 * (LBO_V >> 4)), d_abst + (uint64_t)(k * 16), IDESC_APPLY, k > 0);
         umma::mma_commit(bar_acc);
       }
       __syncwarp();
@@ -466,8 +466,8 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
 #pragma unroll
         for (int i = 0; i < 8; ++i) y[i] = live ? (x1[c * 8 + i] - mean) * rstd * gg[c * 8 + i] + bb[c * 8 + i] : 0.0f;
         *reinterpret_cast<uint4*>(smem + AP_XN + (cq * 4 + c) * LBO_V + row * 16) =
-            make_uint4(umma::pack_bf16x2(y[0], y[1]), umma::pack_bf16x2(y[2], y[3]), umma::pack_bf16x2(y[4], y[5]),
-                       umma::pack_bf16x2(y[6], y[7]));
+            make_uint4(umma::pack_h2(y[0], y[1]), umma::pack_h2(y[2], y[3]), umma::pack_h2(y[4], y[5]),
+                       umma::pack_h2(y[6], y[7]));
       }
     }
     umma::fence_proxy_async();
@@ -494,8 +494,8 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           *reinterpret_cast<uint4*>(smem + AP_GH + (cq * 4 + c) * LBO_V + row * 16) =
-              make_uint4(umma::pack_bf16x2(v[c * 8], v[c * 8 + 1]), umma::pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
-                         umma::pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), umma::pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]));
+              make_uint4(umma::pack_h2(v[c * 8], v[c * 8 + 1]), umma::pack_h2(v[c * 8 + 2], v[c * 8 + 3]),
+                         umma::pack_h2(v[c * 8 + 4], v[c * 8 + 5]), umma::pack_h2(v[c * 8 + 6], v[c * 8 + 7]));
       }
       umma::fence_proxy_async();
       umma::fence_before_sync();
@@ -543,13 +543,11 @@ class_apply_fast_kernel(const float* __restrict__ X, float* __restrict__ Xout, c
 }
 
 // ================================================================================================
-cudaError_t launch_class_state_fast(const float* X, const __nv_bfloat16* timg, float* state, int B, int Te, int npix,
+cudaError_t launch_class_state_fast(const float* X, const __half* timg, float* state, int B, int Te, int npix,
                                     int S, const ClassFastW& w, int num_sms, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // per-device function attribute: set on every launch (cheap), a process-wide flag would miss other devices
     cudaError_t e = cudaFuncSetAttribute(class_state_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   long long n = (long long)B * npix;
   int grid = (int)(n < num_sms ? n : num_sms);
@@ -572,14 +570,12 @@ cudaError_t launch_class_state_fast(const float* X, const __nv_bfloat16* timg, f
   return cudaGetLastError();
 }
 
-cudaError_t launch_class_apply_fast(const float* X, float* Xout, const __nv_bfloat16* timg, const float* state,
+cudaError_t launch_class_apply_fast(const float* X, float* Xout, const __half* timg, const float* state,
                                     const float* pad_state, int B, int Te, int npix, int S, int out_mode,
                                     const ClassFastW& w, int num_sms, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // per-device function attribute: set on every launch (cheap), a process-wide flag would miss other devices
     cudaError_t e = cudaFuncSetAttribute(class_apply_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AP_SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   long long n = (long long)B * npix * ((Te + 127) / 128);
   int grid = (int)(n < num_sms ? n : num_sms);
@@ -603,8 +599,8 @@ cudaError_t launch_class_apply_fast(const float* X, float* Xout, const __nv_bflo
   return cudaGetLastError();
 }
 
-// text guidance [B][Te][128] fp32 -> per (image, 128-class tile) canonical dense bf16 images (rows >= Te are zero)
-__global__ void pack_text_img_kernel(const float* __restrict__ tg, __nv_bfloat16* __restrict__ timg, int B, int Te, int ntile) {
+// text guidance [B][Te][128] fp32 -> per (image, 128-class tile) canonical dense fp16 images (rows >= Te are zero)
+__global__ void pack_text_img_kernel(const float* __restrict__ tg, __half* __restrict__ timg, int B, int Te, int ntile) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * ntile * 128 * 128;
   if (i >= total) return;
@@ -613,9 +609,9 @@ __global__ void pack_text_img_kernel(const float* __restrict__ tg, __nv_bfloat16
   int tl = (int)(bt % ntile), b = (int)(bt / ntile);
   int t = tl * 128 + r;
   float v = t < Te ? tg[((long long)b * Te + t) * 128 + k] : 0.0f;
-  timg[bt * (128 * 128) + (k >> 3) * (128 * 8) + r * 8 + (k & 7)] = __float2bfloat16(v);
+  timg[bt * (128 * 128) + (k >> 3) * (128 * 8) + r * 8 + (k & 7)] = __float2half_rn(v);
 }
-cudaError_t launch_pack_text_img(const float* tg, __nv_bfloat16* timg, int B, int Te, cudaStream_t st) {
+cudaError_t launch_pack_text_img(const float* tg, __half* timg, int B, int Te, cudaStream_t st) {
   int ntile = (Te + 127) / 128;
   long long total = (long long)B * ntile * 128 * 128;
   pack_text_img_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tg, timg, B, Te, ntile);

@@ -1,10 +1,10 @@
-// Building blocks shared by the FAST (bf16 tcgen05, fp32 accumulate) kernels.
+// Building blocks shared by the FAST (fp16 tcgen05, fp32 accumulate) kernels.
 //
 // Conventions
 //   * A "token tile" is 128 rows (tokens) x 128 features.  For the epilogues one thread owns one row:
 //     warp w of a CTA may only touch TMEM lanes 32*(w%4)..+31, so warps w and w+4 share rows and
 //     split the columns.
-//   * bf16 UMMA operands live in shared memory in the canonical no-swizzle K-major layout of
+//   * fp16 UMMA operands live in shared memory in the canonical no-swizzle K-major layout of
 //     umma.cuh.  Tiles written by threads use a PADDED chunk stride (LBO_T = rows*16 + 16) so that
 //     the 8-byte stores of the warp-per-row LayerNorm prologue are bank-conflict free; weight
 //     images are pre-packed in global memory with the dense stride and arrive by bulk (TMA) copy.
@@ -19,8 +19,8 @@ constexpr int TILE = 128;                       // rows per UMMA M tile
 constexpr uint32_t LBO_W = 128 * 16;            // weight images: 128 rows, dense
 constexpr uint32_t LBO_T = 128 * 16 + 16;       // thread-written 128-row tiles, padded
 constexpr uint32_t TILE_BYTES_T = 16 * LBO_T;   // 128 features = 16 chunks
-constexpr uint32_t WIMG_BYTES = 16 * LBO_W;     // one 128x128 bf16 weight image = 32 KiB
-constexpr uint32_t IDESC_128x128 = umma::make_idesc_bf16(128, 128);
+constexpr uint32_t WIMG_BYTES = 16 * LBO_W;     // one 128x128 fp16 weight image = 32 KiB
+constexpr uint32_t IDESC_128x128 = umma::make_idesc_f16(128, 128);
 
 // 8 k-steps of a [128 x 128] x [N x 128]^T GEMM from PRE-BUILT base descriptors: the issuing thread only adds the
 // K-step offset to the address field (building a descriptor from scratch costs ~50-100 cycles in one thread,
@@ -29,7 +29,7 @@ __device__ __forceinline__ void issue_gemm_k128_desc(uint32_t d_tmem, uint64_t a
                                                      uint32_t lbo_b, uint32_t idesc, bool acc_first) {
 #pragma unroll
   for (int k = 0; k < 8; ++k)
-    umma::mma_bf16_ss(d_tmem, a_desc + (uint64_t)(k * 2 * (lbo_a >> 4)), b_desc + (uint64_t)(k * 2 * (lbo_b >> 4)), idesc,
+    umma::mma_f16_ss(d_tmem, a_desc + (uint64_t)(k * 2 * (lbo_a >> 4)), b_desc + (uint64_t)(k * 2 * (lbo_b >> 4)), idesc,
                       (k > 0 || acc_first) ? 1u : 0u);
 }
 
@@ -40,11 +40,11 @@ __device__ __forceinline__ void issue_gemm_k128(uint32_t d_tmem, uint32_t a_addr
   for (int k = 0; k < 8; ++k) {
     uint64_t da = umma::make_smem_desc(a_addr + k * 2 * lbo_a, lbo_a, 128);
     uint64_t db = umma::make_smem_desc(b_addr + k * 2 * lbo_b, lbo_b, 128);
-    umma::mma_bf16_ss(d_tmem, da, db, idesc, (k > 0 || acc_first) ? 1u : 0u);
+    umma::mma_f16_ss(d_tmem, da, db, idesc, (k > 0 || acc_first) ? 1u : 0u);
   }
 }
 
-// LayerNorm(128) of `nrows` token rows (row i at src + i*row_stride floats), written as bf16 into a
+// LayerNorm(128) of `nrows` token rows (row i at src + i*row_stride floats), written as fp16 into a
 // canonical 128-row tile.  Warp-per-row: coalesced 512-byte loads, shuffle reductions.  Rows
 // >= nvalid are zero-filled.  Called by all `nwarps` warps of the CTA.
 __device__ __forceinline__ void ln_rows_to_tile(const float* __restrict__ src, long long row_stride, int nvalid,
@@ -64,8 +64,37 @@ __device__ __forceinline__ void ln_rows_to_tile(const float* __restrict__ src, l
       int r = r0 + i;
       float4 y = warp_layernorm128_fast(x[i], g, be);
       if (r >= nvalid) y = make_float4(0.f, 0.f, 0.f, 0.f);
-      uint2 p = make_uint2(umma::pack_bf16x2(y.x, y.y), umma::pack_bf16x2(y.z, y.w));
+      uint2 p = make_uint2(umma::pack_h2(y.x, y.y), umma::pack_h2(y.z, y.w));
       *reinterpret_cast<uint2*>(tile + (lane >> 1) * LBO_T + r * 16 + (lane & 1) * 8) = p;
+    }
+  }
+}
+
+// PRECISE variant: the normalised row is written as a hi + lo fp16 pair into two tiles (umma::split_h2); tile_lo may be
+// nullptr when only the single-term operand is needed (q/k path, tools/precision_study.py).
+__device__ __forceinline__ void ln_rows_to_tile_split(const float* __restrict__ src, long long row_stride, int nvalid,
+                                                      uint8_t* tile_hi, uint8_t* tile_lo, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, int warp, int nwarps, int lane) {
+  const float4 g = ld4(gamma + lane * 4), be = ld4(beta + lane * 4);
+  constexpr int R = 8;
+  for (int r0 = warp * R; r0 < TILE; r0 += nwarps * R) {
+    float4 x[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      int r = r0 + i;
+      x[i] = (r < nvalid) ? ld4(src + (long long)r * row_stride + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      int r = r0 + i;
+      float4 y = warp_layernorm128_fast(x[i], g, be);
+      if (r >= nvalid) y = make_float4(0.f, 0.f, 0.f, 0.f);
+      uint2 hi, lo;
+      umma::split_h2(y.x, y.y, hi.x, lo.x);
+      umma::split_h2(y.z, y.w, hi.y, lo.y);
+      const uint32_t off = (lane >> 1) * LBO_T + r * 16 + (lane & 1) * 8;
+      *reinterpret_cast<uint2*>(tile_hi + off) = hi;
+      if (tile_lo != nullptr) *reinterpret_cast<uint2*>(tile_lo + off) = lo;
     }
   }
 }
@@ -100,13 +129,13 @@ __device__ __forceinline__ void ln_rows_to_tiles_pipelined(const float* __restri
       const int r = rw + b * BATCH + i;
       float4 y = warp_layernorm128_fast(x[b % DEPTH][i], g, be);
       if (r >= nvalid) y = make_float4(0.f, 0.f, 0.f, 0.f);
-      const uint2 pk = make_uint2(umma::pack_bf16x2(y.x, y.y), umma::pack_bf16x2(y.z, y.w));
+      const uint2 pk = make_uint2(umma::pack_h2(y.x, y.y), umma::pack_h2(y.z, y.w));
       *reinterpret_cast<uint2*>(tile + (r >> 7) * TILE_BYTES_T + (lane >> 1) * LBO_T + (r & 127) * 16 + (lane & 1) * 8) = pk;
     }
   }
 }
 
-// erf-GELU for the bf16 path.  The result is rounded to bf16 (relative 2^-9) before the next MMA, so erf only
+// erf-GELU for the fp16 path.  The result is rounded to fp16 (relative 2^-9) before the next MMA, so erf only
 // needs ~1e-4 absolute accuracy: odd minimax polynomial directly in x, erf(x/sqrt 2) ~ x Q(x^2) on |x| <= 3.8
 // (clamped beyond, where 1 - erf < 1.5e-4); max |erf error| 1.3e-4, GELU error <= 2.5e-4 (1.6e-4 for |x| < 2.5).
 // 12 FMA-pipe instructions, no MUFU (the FFN epilogue is issue bound: ncu, profiles/README.md).

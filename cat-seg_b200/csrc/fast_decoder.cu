@@ -3,7 +3,7 @@
 // Reference: Aggregator.conv_decoder (model.py:674-681), Up.forward (:549-555), DoubleConv (:520-537).
 //
 // One CTA processes a band of BR input rows of one (image, class) slice.  The band (plus a 1-pixel
-// halo, zero padded) is staged ONCE in shared memory as a bf16 canonical K-major image whose rows
+// halo, zero padded) is staged ONCE in shared memory as a fp16 canonical K-major image whose rows
 // are the padded raster positions; every convolution tap is then just a row-shifted view of that
 // image (descriptor start address + offset*16 bytes), so a 3x3 conv is 9 x (CIN/16) accumulating
 // tcgen05.mma per 128-row tile with no im2col copy.  GroupNorm+ReLU of the producer is applied
@@ -30,17 +30,17 @@ namespace catseg {
 using namespace fast;
 
 struct BandConvParams {
-  const void* in;            // [S][Win*Win][CIN]  fp32 (IN_F32) or bf16
+  const void* in;            // [S][Win*Win][CIN]  fp32 (IN_F32) or fp16
   const float* in_stats;     // [S][nb_in][G_in][2] partial (sum, sumsq); nullptr: no GroupNorm on the input
   const float* in_ss;        // [S][CIN][2] GroupNorm (scale, shift) of the input, from gn_finalize_kernel (set when in_stats is)
   int nb_in;
   float in_count;            // elements per (slice, group)
   const float *gamma, *beta; // [CIN]
-  const __nv_bfloat16* wimg; // NIMG images [NOUT x CIN], canonical dense
+  const __half* wimg; // NIMG images [NOUT x CIN], canonical dense
   const float* emap;         // composed stages: the additive map re-laid out per accumulator tile (relayout_emap_kernel):
                              // [B][NB][4 parities][NTILES][NREAL/4][128 rows][4] fp32, else nullptr
   int Te;
-  __nv_bfloat16* out;        // [S][Wout*Wout][NREAL]
+  __half* out;        // [S][Wout*Wout][NREAL]
   float* out_stats;          // [S][NB][G_out][2]
   float* logits;             // HEAD: [B][T][Wout*Wout]
   const int32_t* classes;    // HEAD: [B*Te] (absolute slice index)
@@ -78,7 +78,7 @@ struct BandCfg {
   static constexpr uint32_t SM_ST = SM_SC + 2 * CIN * 4;              // [NWW warps][GOUT][2]
   static constexpr uint32_t SM_BAR = (SM_ST + NWW * GOUT * 2 * 4 + 15) / 16 * 16;
   static constexpr uint32_t SMEM = SM_BAR + (2 * NSLOT + 33) * 8 + 16;   // ring barriers + [2 sets][16 tiles] accumulator barriers
-  static constexpr uint32_t IDESC = umma::make_idesc_bf16(128, NOUT);
+  static constexpr uint32_t IDESC = umma::make_idesc_f16(128, NOUT);
   // CTAS = CTAs per SM: 2 (half-height bands; one CTA's staging / epilogue overlaps the other's MMAs) or 1 (a band as
   // tall as the shared memory allows: fewer M-tile remainders and one pass over a streamed weight set per band)
   static constexpr int TMEM_COLS = CTAS == 2 ? 256 : 512;
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
             const uint64_t a_tile = a_desc0 + (uint64_t)(uint32_t)(C::P0 + off + t * 128);
 #pragma unroll
             for (int k = 0; k < C::KSTEPS; ++k)
-              umma::mma_bf16_ss(tm + set * ACC_COLS + t * NOUT, a_tile + (uint64_t)(k * 2 * (C::LBO_I >> 4)),
+              umma::mma_f16_ss(tm + set * ACC_COLS + t * NOUT, a_tile + (uint64_t)(k * 2 * (C::LBO_I >> 4)),
                                 b_desc + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC, (tap > 0 || k > 0) ? 1u : 0u);
           }
           umma::mma_commit(&bar_acc[set * 16 + t]);
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
         for (int t = 0; t < C::NTILES; ++t) {
 #pragma unroll
           for (int k = 0; k < C::KSTEPS; ++k)
-            umma::mma_bf16_ss(tm + set * ACC_COLS + t * NOUT, a_tile + (uint64_t)(k * 2 * (C::LBO_I >> 4)),
+            umma::mma_f16_ss(tm + set * ACC_COLS + t * NOUT, a_tile + (uint64_t)(k * 2 * (C::LBO_I >> 4)),
                               b_desc + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC, (tap > 0 || k > 0) ? 1u : 0u);
           a_tile += 128;
         }
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
       __syncthreads();
     }
     BPH(4);
-    // ---- stage the padded band image (bf16, canonical K-major, rows = padded raster positions).
+    // ---- stage the padded band image (fp16, canonical K-major, rows = padded raster positions).
     //      Explicitly software-pipelined: U independent 16/32-byte loads are issued before any is consumed
     //      (ncu showed the compiler serialising load -> convert -> store per chunk: one latency per chunk).
     //      256 % KCH == 0, so a thread always handles the same 8-channel group: its GroupNorm scale/shift live in registers.
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
             raw[u][0] = __ldg(src);
             raw[u][IN_F32 ? 1 : 0] = __ldg(src + 1);
           } else {
-            raw[u][0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.in) + off));
+            raw[u][0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.in) + off));
           }
         }
 #pragma unroll
@@ -315,16 +315,16 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = f[j];
             } else {
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[u][0]);
+              const __half2* h2 = reinterpret_cast<const __half2*>(&raw[u][0]);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h2[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+              for (int j = 0; j < 4; ++j) { float2 f = __half22float2(h2[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
             }
             if (p.in_stats != nullptr) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.0f);
             }
-            val = make_uint4(umma::pack_bf16x2(v[0], v[1]), umma::pack_bf16x2(v[2], v[3]), umma::pack_bf16x2(v[4], v[5]),
-                             umma::pack_bf16x2(v[6], v[7]));
+            val = make_uint4(umma::pack_h2(v[0], v[1]), umma::pack_h2(v[2], v[3]), umma::pack_h2(v[4], v[5]),
+                             umma::pack_h2(v[6], v[7]));
           }
           *reinterpret_cast<uint4*>(smem + c * C::LBO_I + pp * 16) = val;
         }
@@ -407,12 +407,12 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
                   for (int i = 0; i < 16; ++i) { float x = v[g * 16 + i]; s += x; ss = fmaf(x, x, ss); }
                   st_sum[c0 / 16 + g] += s; st_sq[c0 / 16 + g] += ss;
                 }
-                __nv_bfloat16* o = p.out + ((long long)sl * (C::WOUT * C::WOUT) + opix) * NREAL + c0;
+                __half* o = p.out + ((long long)sl * (C::WOUT * C::WOUT) + opix) * NREAL + c0;
 #pragma unroll
                 for (int i = 0; i < 32; i += 8)
                   *reinterpret_cast<uint4*>(o + i) =
-                      make_uint4(umma::pack_bf16x2(v[i], v[i + 1]), umma::pack_bf16x2(v[i + 2], v[i + 3]),
-                                 umma::pack_bf16x2(v[i + 4], v[i + 5]), umma::pack_bf16x2(v[i + 6], v[i + 7]));
+                      make_uint4(umma::pack_h2(v[i], v[i + 1]), umma::pack_h2(v[i + 2], v[i + 3]),
+                                 umma::pack_h2(v[i + 4], v[i + 5]), umma::pack_h2(v[i + 6], v[i + 7]));
               }
             }
           }
@@ -515,11 +515,9 @@ template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR,
 static cudaError_t launch_band(const BandConvParams& p, int num_sms, cudaStream_t st) {
   using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS>;
   auto kern = band_conv_kernel<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // per-device function attribute: set on every launch (cheap), a process-wide flag would miss other devices
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   long long nitems = (long long)p.nslice * C::NB;
   int grid = (int)(nitems < (long long)CTAS * num_sms ? nitems : (long long)CTAS * num_sms);
@@ -552,18 +550,18 @@ static cudaError_t launch_band(const BandConvParams& p, int num_sms, cudaStream_
 // weight preparation (runs once in catseg_finalize_params)
 
 // image[(k/8)*NOUT*8 + n*8 + k%8] = W3[n][ci0 + k][tap]   (n < nreal, else 0)
-__global__ void pack_tap_img_kernel(__nv_bfloat16* dst, const float* W3, int Cin3, int ci0, int CIN, int NOUT, int nreal) {
+__global__ void pack_tap_img_kernel(__half* dst, const float* W3, int Cin3, int ci0, int CIN, int NOUT, int nreal) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int per = NOUT * CIN;
   if (i >= 9 * per) return;
   int tap = i / per, r = i % per, n = r / CIN, k = r % CIN;
   float v = n < nreal ? W3[((long long)n * Cin3 + ci0 + k) * 9 + tap] : 0.0f;
-  dst[(long long)tap * per + (k >> 3) * NOUT * 8 + n * 8 + (k & 7)] = __float2bfloat16(v);
+  dst[(long long)tap * per + (k >> 3) * NOUT * 8 + n * 8 + (k & 7)] = __float2half_rn(v);
 }
 
 // composed ConvTranspose(k2,s2) o conv3x3:  image index (a*2+b)*4 + (u*2+v), element [co][ci]
 //   Wc = sum_{dy,dx -> (u,v)} sum_cu Wup[ci][cu][a'][b'] * W3[co][cu][dy+1][dx+1]
-__global__ void compose_up_img_kernel(__nv_bfloat16* dst, const float* Wup, const float* W3, int Ci, int Cup, int Cin3,
+__global__ void compose_up_img_kernel(__half* dst, const float* Wup, const float* W3, int Ci, int Cup, int Cin3,
                                       int Co) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int per = Co * Ci;
@@ -581,7 +579,7 @@ __global__ void compose_up_img_kernel(__nv_bfloat16* dst, const float* Wup, cons
         acc = fmaf(Wup[(((long long)ci * Cup + cu) * 2 + ay) * 2 + ax], W3[((long long)co * Cin3 + cu) * 9 + (dy + 1) * 3 + dx + 1], acc);
     }
   }
-  dst[(long long)img * per + (ci >> 3) * Co * 8 + co * 8 + (ci & 7)] = __float2bfloat16(acc);
+  dst[(long long)img * per + (ci >> 3) * Co * 8 + co * 8 + (ci & 7)] = __float2half_rn(acc);
 }
 
 // bias map of the composed conv: Bmap[Y][X][co] = sum_{valid dy,dx} sum_cu bup[cu] W3[co][cu][dy+1][dx+1]
@@ -626,11 +624,11 @@ cudaError_t decoder_fast_pack(const DecoderDims& d, const float* up1_w, const fl
     return cudaErrorInvalidValue;      // the band kernels are instantiated for the shipped decoder geometry
   uint8_t* ptr = reinterpret_cast<uint8_t*>(storage);
   auto take = [&](size_t bytes) { uint8_t* r = ptr; ptr += bytes; return r; };
-  __nv_bfloat16* w1 = reinterpret_cast<__nv_bfloat16*>(take((size_t)16 * d.D1 * d.C0 * 2));
-  __nv_bfloat16* w2 = reinterpret_cast<__nv_bfloat16*>(take((size_t)9 * d.D1 * d.D1 * 2));
-  __nv_bfloat16* w3 = reinterpret_cast<__nv_bfloat16*>(take((size_t)16 * d.D2 * d.D1 * 2));
-  __nv_bfloat16* w4 = reinterpret_cast<__nv_bfloat16*>(take((size_t)9 * d.D2 * d.D2 * 2));
-  __nv_bfloat16* w5 = reinterpret_cast<__nv_bfloat16*>(take((size_t)9 * 16 * d.D2 * 2));
+  __half* w1 = reinterpret_cast<__half*>(take((size_t)16 * d.D1 * d.C0 * 2));
+  __half* w2 = reinterpret_cast<__half*>(take((size_t)9 * d.D1 * d.D1 * 2));
+  __half* w3 = reinterpret_cast<__half*>(take((size_t)16 * d.D2 * d.D1 * 2));
+  __half* w4 = reinterpret_cast<__half*>(take((size_t)9 * d.D2 * d.D2 * 2));
+  __half* w5 = reinterpret_cast<__half*>(take((size_t)9 * 16 * d.D2 * 2));
   float* bm1 = reinterpret_cast<float*>(take((size_t)4 * d.H * d.W * d.D1 * 4));
   float* bm2 = reinterpret_cast<float*>(take((size_t)16 * d.H * d.W * d.D2 * 4));
   float* wg1 = reinterpret_cast<float*>(take((size_t)9 * d.G1 * d.D1 * 4));
@@ -698,7 +696,7 @@ size_t decoder_fast_scratch_bytes(const DecoderDims& d, int B, int chunk) {
   size_t b = 0;
   b += (size_t)B * (4 * hw * d.D1 + 16 * hw * d.D2) * 4;                 // E1, E2
   b += (max_sz(emap_tiled_floats<D1N>(B), emap_tiled_floats<D1W>(B)) + max_sz(emap_tiled_floats<D3N>(B), emap_tiled_floats<D3W>(B))) * 4 + 512;   // tile-ordered copies
-  b += (size_t)chunk * (2 * 4 * hw * d.D1 + 2 * 16 * hw * d.D2) * 2;     // c1a c1b c2a c2b (bf16)
+  b += (size_t)chunk * (2 * 4 * hw * d.D1 + 2 * 16 * hw * d.D2) * 2;     // c1a c1b c2a c2b (fp16)
   b += (size_t)chunk * (4 * 4 + 8 * 4 + 12 * 2 + 16 * 2) * 2 * 4 + 4096; // band statistics
   b += (size_t)chunk * 64 * 2 * 4 + 256;                                  // GroupNorm (scale, shift) of the current producer
   return (b + 255) / 256 * 256;
@@ -719,10 +717,10 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
   float* E2 = reinterpret_cast<float*>(take((size_t)B * 16 * hw * d.D2 * 4));
   float* E1t = reinterpret_cast<float*>(take(max_sz(emap_tiled_floats<D1N>(B), emap_tiled_floats<D1W>(B)) * 4));
   float* E2t = reinterpret_cast<float*>(take(max_sz(emap_tiled_floats<D3N>(B), emap_tiled_floats<D3W>(B)) * 4));
-  __nv_bfloat16* c1a = reinterpret_cast<__nv_bfloat16*>(take((size_t)chunk * 4 * hw * d.D1 * 2));
-  __nv_bfloat16* c1b = reinterpret_cast<__nv_bfloat16*>(take((size_t)chunk * 4 * hw * d.D1 * 2));
-  __nv_bfloat16* c2a = reinterpret_cast<__nv_bfloat16*>(take((size_t)chunk * 16 * hw * d.D2 * 2));
-  __nv_bfloat16* c2b = reinterpret_cast<__nv_bfloat16*>(take((size_t)chunk * 16 * hw * d.D2 * 2));
+  __half* c1a = reinterpret_cast<__half*>(take((size_t)chunk * 4 * hw * d.D1 * 2));
+  __half* c1b = reinterpret_cast<__half*>(take((size_t)chunk * 4 * hw * d.D1 * 2));
+  __half* c2a = reinterpret_cast<__half*>(take((size_t)chunk * 16 * hw * d.D2 * 2));
+  __half* c2b = reinterpret_cast<__half*>(take((size_t)chunk * 16 * hw * d.D2 * 2));
   float* s1a = reinterpret_cast<float*>(take((size_t)chunk * 4 * 4 * 2 * 4));    // NB=4 G=4
   float* s1b = reinterpret_cast<float*>(take((size_t)chunk * 8 * 4 * 2 * 4));    // NB=8 G=4
   float* s2a = reinterpret_cast<float*>(take((size_t)chunk * 12 * 2 * 2 * 4));   // NB=12 G=2

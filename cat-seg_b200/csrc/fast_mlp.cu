@@ -2,10 +2,10 @@
 //
 // Reference: the FFN half of SwinTransformerBlock.forward (model.py:223, Mlp 128->512 GELU ->128).
 // Persistent CTAs; each pass handles 256 token rows (two 128-row UMMA tiles) so that the 256 KiB of
-// bf16 weights, streamed from L2 through a 3-slot ring of 32 KiB bulk (TMA) copies, are fetched
+// fp16 weights, streamed from L2 through a 3-slot ring of 32 KiB bulk (TMA) copies, are fetched
 // once per 256 tokens.  Per hidden chunk j (128 of the 512 hidden units) and tile t:
 //   MMA1: H_t = LN(x_t) W1_j^T   -> TMEM          (8 x tcgen05.mma M128 N128 K16)
-//   epilogue: TMEM -> +b1 -> GELU -> bf16 -> shared memory (canonical K-major A operand)
+//   epilogue: TMEM -> +b1 -> GELU -> fp16 -> shared memory (canonical K-major A operand)
 //   MMA2: Y_t += h W2_j^T        -> TMEM
 // and finally Y_t + b2 + x -> global through an fp32 staging tile (coalesced rows).
 // TMEM: H_a H_b Y_a Y_b = 4 x 128 columns.
@@ -31,8 +31,8 @@ constexpr int MLP_EPI_WARPS = 16;
 constexpr int MLP_EPI_THREADS = MLP_EPI_WARPS * 32;
 constexpr int MLP_THREADS = MLP_EPI_THREADS + 32;                // + the issuing warp
 constexpr uint32_t SM_RING = 0;                                   // 3 x 32 KiB weight ring
-constexpr uint32_t SM_XN = SM_RING + 3 * WIMG_BYTES;              // 2 tiles LN(x) bf16
-constexpr uint32_t SM_H = SM_XN + 2 * TILE_BYTES_T;               // hidden chunk bf16
+constexpr uint32_t SM_XN = SM_RING + 3 * WIMG_BYTES;              // 2 tiles LN(x) fp16
+constexpr uint32_t SM_H = SM_XN + 2 * TILE_BYTES_T;               // hidden chunk fp16
 constexpr uint32_t SM_PAR = SM_H + TILE_BYTES_T;                  // b1[512] b2[128] g[128] b[128] floats
 constexpr uint32_t SM_BAR = SM_PAR + (512 + 128 + 128 + 128) * 4; // 7 mbarriers + tmem ptr
 constexpr uint32_t MLP_SMEM = SM_BAR + 8 * 8 + 16;
@@ -148,7 +148,7 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w, long long* __
           umma::mbar_wait(&bar_mma[t], par);                 // H_t ready
           umma::fence_after_sync();
           PH(1);
-          // ---- H_t -> bias -> act -> bf16 (32 columns per thread)
+          // ---- H_t -> bias -> act -> fp16 (32 columns per thread)
           uint4 packed[4];
           {
             float v[32];
@@ -163,8 +163,8 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w, long long* __
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-              packed[c] = make_uint4(umma::pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]), umma::pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
-                                     umma::pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), umma::pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]));
+              packed[c] = make_uint4(umma::pack_h2(v[c * 8 + 0], v[c * 8 + 1]), umma::pack_h2(v[c * 8 + 2], v[c * 8 + 3]),
+                                     umma::pack_h2(v[c * 8 + 4], v[c * 8 + 5]), umma::pack_h2(v[c * 8 + 6], v[c * 8 + 7]));
           }
           PH(2);
           // ---- the h buffer is free once the previous MMA2 has completed
@@ -265,13 +265,11 @@ mlp_fast_kernel(float* __restrict__ X, long long ntok, MlpFastW w, long long* __
 }
 
 cudaError_t launch_mlp_fast(float* X, long long ntok, const MlpFastW& w, int act, int num_sms, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // per-device function attribute: set on every launch (cheap), a process-wide flag would miss other devices
     cudaError_t e = cudaFuncSetAttribute(mlp_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(mlp_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   long long npass = (ntok + 255) / 256;
   int grid = (int)(npass < num_sms ? npass : num_sms);
@@ -297,14 +295,14 @@ cudaError_t launch_mlp_fast(float* X, long long ntok, const MlpFastW& w, int act
   return cudaGetLastError();
 }
 
-// ---- weight image packing: dst image (bf16, canonical dense 128x128) <- W[r0 + r][c0 + k], ld = row stride
-__global__ void pack_wimg_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ W, int ld, int r0, int c0) {
+// ---- weight image packing: dst image (fp16, canonical dense 128x128) <- W[r0 + r][c0 + k], ld = row stride
+__global__ void pack_wimg_kernel(__half* __restrict__ dst, const float* __restrict__ W, int ld, int r0, int c0) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 128 * 128) return;
   int r = i >> 7, k = i & 127;
-  dst[(k >> 3) * (128 * 8) + r * 8 + (k & 7)] = __float2bfloat16(W[(long long)(r0 + r) * ld + c0 + k]);
+  dst[(k >> 3) * (128 * 8) + r * 8 + (k & 7)] = __float2half_rn(W[(long long)(r0 + r) * ld + c0 + k]);
 }
-cudaError_t launch_pack_wimg(__nv_bfloat16* dst, const float* W, int ld, int r0, int c0, cudaStream_t st) {
+cudaError_t launch_pack_wimg(__half* dst, const float* W, int ld, int r0, int c0, cudaStream_t st) {
   pack_wimg_kernel<<<64, 256, 0, st>>>(dst, W, ld, r0, c0);
   return cudaGetLastError();
 }

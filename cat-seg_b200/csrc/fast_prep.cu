@@ -201,11 +201,9 @@ cudaError_t launch_pack_embed_img(__nv_bfloat16* dst, const float* Wt, cudaStrea
 }
 cudaError_t launch_cost_embed_fast(const float* corr, const int32_t* classes, const __nv_bfloat16* bimg, const float* bias,
                                    float* X, int B, int T, int Te, int num_sms, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // per-device function attribute: set on every launch (cheap), a process-wide flag would miss other devices
     cudaError_t e = cudaFuncSetAttribute(embed_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const int nslice = B * Te;
   const int grid = nslice < num_sms ? nslice : num_sms;
@@ -390,12 +388,10 @@ template <int NOUT, int WIN_, int BR, int KC>
 static cudaError_t run_gconv(const float* in, const __nv_bfloat16* wimg, const float* bias, float* out, int B, int Ci,
                              cudaStream_t st) {
   using C = GConvCfg<NOUT, WIN_, BR, KC>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // per-device function attribute: set on every launch (cheap), a process-wide flag would miss other devices
     cudaError_t e = cudaFuncSetAttribute(gconv_fast_kernel<NOUT, WIN_, BR, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C::SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   if (Ci % KC != 0) return cudaErrorInvalidValue;
   gconv_fast_kernel<NOUT, WIN_, BR, KC><<<B * C::NB, 256, C::SMEM, st>>>(in, wimg, bias, out, Ci);

@@ -13,7 +13,7 @@
 //   shared memory as the K-major A operand, O_h (TMEM) is normalised and stored into the [token][128] image
 //   that is the B operand of the transposed projection  Y^T (128 x 144) = Wp . O^T.
 // The guidance half of q/k (class independent, biases included) arrives per (window, head) as one bulk copy of
-// a bf16 [144 tok][q 32 | k 32] tile prepared by pack_ag_windows (window order, shift applied).
+// a fp16 [144 tok][q 32 | k 32] tile prepared by pack_ag_windows (window order, shift applied).
 // Weights stream from L2 through a 3-slot ring of 16 KiB half images (K halves), 10 halves per window.
 //
 // Software pipeline over the heads (every phase of this kernel is issue/MUFU bound, so the point is to keep
@@ -37,10 +37,10 @@ constexpr int SA_THREADS = 512;    // 16 warps: TMEM lane quarter q4 = warp & 3,
 constexpr int NTOK = 144, WIN = 12, GRID = 24;
 constexpr uint32_t LBO_X = NTOK * 16 + 16;                 // 2320: thread-written 144-row K-major tiles
 constexpr uint32_t WHALF = WIMG_BYTES / 2;                 // 16 KiB: K chunks 0..7 or 8..15 of a weight image
-constexpr uint32_t AG_BYTES = NTOK * 64 * 2;               // bf16 [144][q 32 | k 32]
+constexpr uint32_t AG_BYTES = NTOK * 64 * 2;               // fp16 [144][q 32 | k 32]
 constexpr uint32_t SM_RING = 0;                            // 3 x 16 KiB
 constexpr uint32_t SM_XN = SM_RING + 3 * WHALF;            // LN1(x): [144 tok x 128] K-major   16 chunks
-constexpr uint32_t SM_QH = SM_XN + 16 * LBO_X;             // q_h image  [18][32][8] bf16 = 9216 B
+constexpr uint32_t SM_QH = SM_XN + 16 * LBO_X;             // q_h image  [18][32][8] fp16 = 9216 B
 constexpr uint32_t SM_KH = SM_QH + 9216;
 constexpr uint32_t SM_VH = SM_KH + 9216;
 constexpr uint32_t SM_P = SM_VH + 9216;                    // P: [rows x 144 keys] K-major, 18 chunks
@@ -52,9 +52,9 @@ constexpr uint32_t SM_MISC = SM_AG + AG_BYTES;
 constexpr uint32_t SM_BAR = SM_MISC + (144 + 2 * 4 * 144 + 2 * 256 + 256 + 128 + 128) * 4;
 constexpr uint32_t SA_SMEM = SM_BAR + 10 * 8 + 16;
 constexpr uint32_t TM_QKV = 0, TM_S0 = 160, TM_S1 = 304, TM_O0 = 448, TM_O1 = 480;
-constexpr uint32_t IDESC_T = umma::make_idesc_bf16(128, 144, 0, 0);     // QKV^T, proj^T
-constexpr uint32_t IDESC_S = umma::make_idesc_bf16(128, 144, 1, 1);     // S = Q K^T (both MN-major images)
-constexpr uint32_t IDESC_PV = umma::make_idesc_bf16(128, 32, 0, 0);     // O = P V
+constexpr uint32_t IDESC_T = umma::make_idesc_f16(128, 144, 0, 0);     // QKV^T, proj^T
+constexpr uint32_t IDESC_S = umma::make_idesc_f16(128, 144, 1, 1);     // S = Q K^T (both MN-major images)
+constexpr uint32_t IDESC_PV = umma::make_idesc_f16(128, 32, 0, 0);     // O = P V
 static_assert(SA_SMEM <= 232448, "shared memory budget");
 }  // namespace
 
@@ -62,7 +62,7 @@ static_assert(SA_SMEM <= 232448, "shared memory budget");
 #define PH(i) do { if (dbg != nullptr && blockIdx.x == 0 && tid == 0) { long long _t = clock64(); pacc##i += _t - t_last; t_last = _t; } } while (0)
 
 __global__ void __launch_bounds__(SA_THREADS, 1)
-swin_attn_fast_kernel(float* __restrict__ X, const __nv_bfloat16* __restrict__ agw, int nwin_total, int Te, int shift,
+swin_attn_fast_kernel(float* __restrict__ X, const __half* __restrict__ agw, int nwin_total, int Te, int shift,
                       SwinAttnFastW w, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   int* tokpix = reinterpret_cast<int*>(smem + SM_MISC);
@@ -74,7 +74,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const __nv_bfloat16* __restrict__ a
   float* s_be = s_g + 128;
   float* s_bv = s_be + 128;
   float* s_bp = s_bv + 128;
-  const __nv_bfloat16* agb = reinterpret_cast<const __nv_bfloat16*>(smem + SM_AG);
+  const __half* agb = reinterpret_cast<const __half*>(smem + SM_AG);
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + SM_BAR);   // [3] weight halves
   uint64_t* bar_ag = bar_full + 3;                                    // guidance tile landed
   uint64_t* bar_a = bar_full + 4;                                     // QKV_h done
@@ -136,10 +136,10 @@ swin_attn_fast_kernel(float* __restrict__ X, const __nv_bfloat16* __restrict__ a
     if (umma::elect_one()) {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        umma::mma_bf16_ss(tm + TM_QKV, wa + (uint64_t)(k * 2 * (LBO_W >> 4)), b_desc + (uint64_t)(k * 2 * (LBO_X >> 4)), IDESC_T, k > 0);
+        umma::mma_f16_ss(tm + TM_QKV, wa + (uint64_t)(k * 2 * (LBO_W >> 4)), b_desc + (uint64_t)(k * 2 * (LBO_X >> 4)), IDESC_T, k > 0);
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        umma::mma_bf16_ss(tm + TM_QKV, wb + (uint64_t)(k * 2 * (LBO_W >> 4)), b_desc + (uint64_t)((k + 4) * 2 * (LBO_X >> 4)), IDESC_T, 1u);
+        umma::mma_f16_ss(tm + TM_QKV, wb + (uint64_t)(k * 2 * (LBO_W >> 4)), b_desc + (uint64_t)((k + 4) * 2 * (LBO_X >> 4)), IDESC_T, 1u);
       umma::mma_commit(bar);
     }
     __syncwarp();
@@ -166,19 +166,19 @@ swin_attn_fast_kernel(float* __restrict__ X, const __nv_bfloat16* __restrict__ a
   auto qk_epilogue = [&]() {                     // warps with q4 < 2
     const int d = lane;
     uint8_t* img = smem + (q4 == 0 ? SM_QH : SM_KH);
-    const __nv_bfloat16* agp = agb + (q4 == 1 ? 32 : 0) + d;
+    const __half* agp = agb + (q4 == 1 ? 32 : 0) + d;
 #pragma unroll 1
     for (int tg = tg0; tg < tg1; ++tg) {
       float v[8];
       umma::tmem_ld8(lane_addr + TM_QKV + tg * 8, v);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] += __bfloat162float(agp[(tg * 8 + i) * 64]);
+      for (int i = 0; i < 8; ++i) v[i] += __half2float(agp[(tg * 8 + i) * 64]);
       if (q4 == 0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] *= scale;
       }
-      const uint4 pk = make_uint4(umma::pack_bf16x2(v[0], v[1]), umma::pack_bf16x2(v[2], v[3]), umma::pack_bf16x2(v[4], v[5]),
-                                  umma::pack_bf16x2(v[6], v[7]));
+      const uint4 pk = make_uint4(umma::pack_h2(v[0], v[1]), umma::pack_h2(v[2], v[3]), umma::pack_h2(v[4], v[5]),
+                                  umma::pack_h2(v[6], v[7]));
       *reinterpret_cast<uint4*>(img + tg * 512 + d * 16) = pk;
       if (q4 == 0 && tg >= 16) {                 // queries 128..143 also go to row groups {4c, 4c+1} of the Q1 image
 #pragma unroll
@@ -193,8 +193,8 @@ swin_attn_fast_kernel(float* __restrict__ X, const __nv_bfloat16* __restrict__ a
       float v[8];
       umma::tmem_ld8(lane_addr + TM_QKV + tg * 8, v);
       *reinterpret_cast<uint4*>(smem + SM_VH + tg * 512 + lane * 16) =
-          make_uint4(umma::pack_bf16x2(v[0] + bvv, v[1] + bvv), umma::pack_bf16x2(v[2] + bvv, v[3] + bvv),
-                     umma::pack_bf16x2(v[4] + bvv, v[5] + bvv), umma::pack_bf16x2(v[6] + bvv, v[7] + bvv));
+          make_uint4(umma::pack_h2(v[0] + bvv, v[1] + bvv), umma::pack_h2(v[2] + bvv, v[3] + bvv),
+                     umma::pack_h2(v[4] + bvv, v[5] + bvv), umma::pack_h2(v[6] + bvv, v[7] + bvv));
     }
   };
 
@@ -229,7 +229,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const __nv_bfloat16* __restrict__ a
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
         float4 y = warp_layernorm128_fast(x[i], g, be);
-        uint2 pk = make_uint2(umma::pack_bf16x2(y.x, y.y), umma::pack_bf16x2(y.z, y.w));
+        uint2 pk = make_uint2(umma::pack_h2(y.x, y.y), umma::pack_h2(y.z, y.w));
         *reinterpret_cast<uint2*>(smem + SM_XN + (lane >> 1) * LBO_X + (r0 + i) * 16 + (lane & 1) * 8) = pk;
       }
     }
@@ -262,7 +262,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const __nv_bfloat16* __restrict__ a
           for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-              umma::mma_bf16_ss(tm + (mt ? TM_S1 : TM_S0), (mt ? d_q1 : d_qh) + (uint64_t)((k * 256) >> 4),
+              umma::mma_f16_ss(tm + (mt ? TM_S1 : TM_S0), (mt ? d_q1 : d_qh) + (uint64_t)((k * 256) >> 4),
                                 d_kh + (uint64_t)((k * 256) >> 4), IDESC_S, k > 0);
           umma::mma_commit(bar_s);
         }
@@ -344,7 +344,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const __nv_bfloat16* __restrict__ a
           for (int i = 0; i < 36; i += 4) {
             const int key = kq * 36 + i;                      // multiple of 4
             *reinterpret_cast<uint2*>(prow + (key >> 3) * LBO_X + (key & 7) * 2) =
-                make_uint2(umma::pack_bf16x2(sv[i], sv[i + 1]), umma::pack_bf16x2(sv[i + 2], sv[i + 3]));
+                make_uint2(umma::pack_h2(sv[i], sv[i + 1]), umma::pack_h2(sv[i + 2], sv[i + 3]));
           }
           rsum[kq * 144 + row] = sum;
         }
@@ -367,7 +367,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const __nv_bfloat16* __restrict__ a
 #pragma unroll
             for (int i = 0; i < 9; ++i) {
               const int key = key0 + i;
-              *reinterpret_cast<__nv_bfloat16*>(prow + (key >> 3) * LBO_X + (key & 7) * 2) = __float2bfloat16(tv[i]);
+              *reinterpret_cast<__half*>(prow + (key >> 3) * LBO_X + (key & 7) * 2) = __float2half_rn(tv[i]);
             }
             sum1[part * 16 + r1] = sum;
           }
@@ -385,7 +385,7 @@ swin_attn_fast_kernel(float* __restrict__ X, const __nv_bfloat16* __restrict__ a
           for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int k = 0; k < 9; ++k)
-              umma::mma_bf16_ss(tm + (mt ? TM_O1 : TM_O0), d_p + (uint64_t)((mt * 128 * 16 + k * 2 * LBO_X) >> 4),
+              umma::mma_f16_ss(tm + (mt ? TM_O1 : TM_O0), d_p + (uint64_t)((mt * 128 * 16 + k * 2 * LBO_X) >> 4),
                                 d_vh + (uint64_t)((k * 1024) >> 4), IDESC_PV, k > 0);
           umma::mma_commit(bar_o);
         }
@@ -422,8 +422,8 @@ swin_attn_fast_kernel(float* __restrict__ X, const __nv_bfloat16* __restrict__ a
 #pragma unroll
             for (int c = 0; c < 4; ++c)
               *reinterpret_cast<uint4*>(smem + SM_O + (h * 4 + c) * LBO_X + row * 16) =
-                  make_uint4(umma::pack_bf16x2(v[c * 8 + 0] * inv, v[c * 8 + 1] * inv), umma::pack_bf16x2(v[c * 8 + 2] * inv, v[c * 8 + 3] * inv),
-                             umma::pack_bf16x2(v[c * 8 + 4] * inv, v[c * 8 + 5] * inv), umma::pack_bf16x2(v[c * 8 + 6] * inv, v[c * 8 + 7] * inv));
+                  make_uint4(umma::pack_h2(v[c * 8 + 0] * inv, v[c * 8 + 1] * inv), umma::pack_h2(v[c * 8 + 2] * inv, v[c * 8 + 3] * inv),
+                             umma::pack_h2(v[c * 8 + 4] * inv, v[c * 8 + 5] * inv), umma::pack_h2(v[c * 8 + 6] * inv, v[c * 8 + 7] * inv));
           }
         }
       }
@@ -475,13 +475,11 @@ swin_attn_fast_kernel(float* __restrict__ X, const __nv_bfloat16* __restrict__ a
   if (warp == 0) umma::tmem_dealloc<512>(tm);
 }
 
-cudaError_t launch_swin_attn_fast(float* X, const __nv_bfloat16* agw, int nslice, int Te, int shift,
+cudaError_t launch_swin_attn_fast(float* X, const __half* agw, int nslice, int Te, int shift,
                                   const SwinAttnFastW& w, int num_sms, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // per-device function attribute: set on every launch (cheap), a process-wide flag would miss other devices
     cudaError_t e = cudaFuncSetAttribute(swin_attn_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   int nwin = nslice * 4;
   int grid = nwin < num_sms ? nwin : num_sms;
@@ -507,9 +505,9 @@ cudaError_t launch_swin_attn_fast(float* X, const __nv_bfloat16* agw, int nslice
   return cudaGetLastError();
 }
 
-// ag_qk fp32 [B][576][256] (q 128 | k 128 guidance terms per pixel) -> bf16 tiles [B][4 windows][4 heads][144 tok][q_h 32 | k_h 32]
+// ag_qk fp32 [B][576][256] (q 128 | k 128 guidance terms per pixel) -> fp16 tiles [B][4 windows][4 heads][144 tok][q_h 32 | k_h 32]
 // in window-token order with the cyclic shift applied (SwinTransformerBlock.forward, model.py:195-205).
-__global__ void pack_ag_windows_kernel(const float* __restrict__ ag, __nv_bfloat16* __restrict__ out, int B, int shift) {
+__global__ void pack_ag_windows_kernel(const float* __restrict__ ag, __half* __restrict__ out, int B, int shift) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * 16 * NTOK * 64) return;
   const int c = (int)(i & 63);
@@ -520,16 +518,16 @@ __global__ void pack_ag_windows_kernel(const float* __restrict__ ag, __nv_bfloat
   const int b = (int)(r >> 2);
   const int sy = (win >> 1) * WIN + tok / WIN, sx = (win & 1) * WIN + tok % WIN;
   const int pix = ((sy + shift) % GRID) * GRID + (sx + shift) % GRID;
-  out[i] = __float2bfloat16(ag[((long long)b * (GRID * GRID) + pix) * 256 + (c < 32 ? h * 32 + c : 128 + h * 32 + (c - 32))]);
+  out[i] = __float2half_rn(ag[((long long)b * (GRID * GRID) + pix) * 256 + (c < 32 ? h * 32 + c : 128 + h * 32 + (c - 32))]);
 }
-cudaError_t launch_pack_ag_windows(const float* ag_qk, __nv_bfloat16* out, int B, int shift, cudaStream_t st) {
+cudaError_t launch_pack_ag_windows(const float* ag_qk, __half* out, int B, int shift, cudaStream_t st) {
   const long long n = (long long)B * 16 * NTOK * 64;
   pack_ag_windows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ag_qk, out, B, shift);
   return cudaGetLastError();
 }
 
 // Per-head QKV weight image: rows [0,32) = Wq[h*32..] (LN(x) columns), [32,64) = Wk, [64,96) = Wv, [96,128) = 0
-__global__ void pack_qkv_head_img_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ Wq,
+__global__ void pack_qkv_head_img_kernel(__half* __restrict__ dst, const float* __restrict__ Wq,
                                          const float* __restrict__ Wk, const float* __restrict__ Wv, int ldqk, int h) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 128 * 128) return;
@@ -538,9 +536,9 @@ __global__ void pack_qkv_head_img_kernel(__nv_bfloat16* __restrict__ dst, const 
   if (r < 32) v = Wq[(long long)(h * 32 + r) * ldqk + k];
   else if (r < 64) v = Wk[(long long)(h * 32 + r - 32) * ldqk + k];
   else if (r < 96) v = Wv[(long long)(h * 32 + r - 64) * 128 + k];
-  dst[(k >> 3) * (128 * 8) + r * 8 + (k & 7)] = __float2bfloat16(v);
+  dst[(k >> 3) * (128 * 8) + r * 8 + (k & 7)] = __float2half_rn(v);
 }
-cudaError_t launch_pack_qkv_head_img(__nv_bfloat16* dst, const float* Wq, const float* Wk, const float* Wv, int ldqk,
+cudaError_t launch_pack_qkv_head_img(__half* dst, const float* Wq, const float* Wk, const float* Wv, int ldqk,
                                      int h, cudaStream_t st) {
   pack_qkv_head_img_kernel<<<64, 256, 0, st>>>(dst, Wq, Wk, Wv, ldqk, h);
   return cudaGetLastError();

@@ -1,6 +1,7 @@
 // Internal declarations shared by the CAT-Seg B200 translation units (not part of the C ABI).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -39,13 +40,20 @@ struct ClassLayerW {
 // FAST path: bf16 weight images for the token MLP (fast_mlp.cu).  wimg = 8 canonical 128x128 images
 // in ring order W1_0, W2_0, W1_1, W2_1, ... (hidden chunks of 128).
 struct MlpFastW {
-  const __nv_bfloat16* wimg;
+  const __half* wimg;
+  const float *ln_g, *ln_b, *b1, *b2;
+};
+
+// PRECISE path (split_mlp.cu): 16 fp16 images in consumption order
+//   W1h0 W1l0 W1h1 W1l1 W2h0 W2l0 W1h2 W1l2 W2h1 W2l1 W1h3 W1l3 W2h2 W2l2 W2h3 W2l3   (h = hi, l = lo term)
+struct MlpSplitW {
+  const __half* wimg;
   const float *ln_g, *ln_b, *b1, *b2;
 };
 
 // FAST window attention (fast_swin_attn.cu): 5 images per block: Wqkv_h (h = 0..3), Wproj.
 struct SwinAttnFastW {
-  const __nv_bfloat16* wimg;
+  const __half* wimg;
   const float *ln_g, *ln_b, *bv, *bproj;
 };
 
@@ -96,14 +104,22 @@ cudaError_t launch_swin_block_exact(float* X, const float* ag_qk, int nslice, in
 
 // ---------------------------------------------------------------- fast_mlp.cu
 cudaError_t launch_mlp_fast(float* X, long long ntok, const MlpFastW& w, int act, int num_sms, cudaStream_t st);
-cudaError_t launch_pack_wimg(__nv_bfloat16* dst, const float* W, int ld, int r0, int c0, cudaStream_t st);
+cudaError_t launch_pack_wimg(__half* dst, const float* W, int ld, int r0, int c0, cudaStream_t st);
+
+// ---------------------------------------------------------------- split_mlp.cu (PRECISE: fp16 hi + lo operands)
+// Xout[row] = Xin[row] (+ Xres[row]) + fc2(act(fc1(LN(Xin[row]))));  Xres may be nullptr, Xout may alias Xin
+cudaError_t launch_mlp_split(const float* Xin, const float* Xres, float* Xout, long long ntok, const MlpSplitW& w, int act,
+                             int num_sms, cudaStream_t st);
+cudaError_t launch_pack_wimg_split(__half* dhi, __half* dlo, const float* W, int ld, int r0, int c0, cudaStream_t st);
+// packs the 16 images of MlpSplitW from fc1 [512][128] and fc2 [128][512]
+cudaError_t pack_mlp_split(__half* dst, const float* W1, const float* W2, cudaStream_t st);
 
 // ---------------------------------------------------------------- fast_swin_attn.cu
 // agw: bf16 guidance tiles [B][4 windows][4 heads][144 tok][64] of this block (launch_pack_ag_windows, same shift)
-cudaError_t launch_swin_attn_fast(float* X, const __nv_bfloat16* agw, int nslice, int Te, int shift,
+cudaError_t launch_swin_attn_fast(float* X, const __half* agw, int nslice, int Te, int shift,
                                   const SwinAttnFastW& w, int num_sms, cudaStream_t st);
-cudaError_t launch_pack_ag_windows(const float* ag_qk, __nv_bfloat16* out, int B, int shift, cudaStream_t st);
-cudaError_t launch_pack_qkv_head_img(__nv_bfloat16* dst, const float* Wq, const float* Wk, const float* Wv, int ldqk,
+cudaError_t launch_pack_ag_windows(const float* ag_qk, __half* out, int B, int shift, cudaStream_t st);
+cudaError_t launch_pack_qkv_head_img(__half* dst, const float* Wq, const float* Wk, const float* Wv, int ldqk,
                                      int h, cudaStream_t st);
 
 // ---------------------------------------------------------------- class_exact.cu
@@ -147,20 +163,20 @@ cudaError_t run_decoder_exact(const float* X, const float* dg0, const float* dg1
 
 // ---------------------------------------------------------------- fast_class.cu
 struct ClassFastW {
-  const __nv_bfloat16* wimg_kv;      // 3 images: Wk (LN(x) part), Wk (guidance part), Wv
-  const __nv_bfloat16* wimg_apply;   // 10 images: Wq_x, Wq_g, then W1_j, W2_j for j = 0..3
+  const __half* wimg_kv;      // 3 images: Wk (LN(x) part), Wk (guidance part), Wv
+  const __half* wimg_apply;   // 10 images: Wq_x, Wq_g, then W1_j, W2_j for j = 0..3
   const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *bqk, *bv, *b1, *b2;
 };
-cudaError_t launch_class_state_fast(const float* X, const __nv_bfloat16* timg, float* state, int B, int Te, int npix,
+cudaError_t launch_class_state_fast(const float* X, const __half* timg, float* state, int B, int Te, int npix,
                                     int S, const ClassFastW& w, int num_sms, cudaStream_t st);
-cudaError_t launch_class_apply_fast(const float* X, float* Xout, const __nv_bfloat16* timg, const float* state,
+cudaError_t launch_class_apply_fast(const float* X, float* Xout, const __half* timg, const float* state,
                                     const float* pad_state, int B, int Te, int npix, int S, int out_mode,
                                     const ClassFastW& w, int num_sms, cudaStream_t st);
-cudaError_t launch_pack_text_img(const float* tg, __nv_bfloat16* timg, int B, int Te, cudaStream_t st);
+cudaError_t launch_pack_text_img(const float* tg, __half* timg, int B, int Te, cudaStream_t st);
 
 // ---------------------------------------------------------------- fast_decoder.cu
 struct DecoderFastW {
-  const __nv_bfloat16 *w1, *w2, *w3, *w4, *w5;   // UMMA weight images per stage (fast_decoder.cu)
+  const __half *w1, *w2, *w3, *w4, *w5;   // UMMA weight images per stage (fast_decoder.cu)
   const float *bmap1, *bmap2;                    // [4HW][D1], [16HW][D2] transposed-conv bias maps
   const float *wg1, *wg2;                        // [9*G1][D1], [9*G2][D2] guidance conv weights (fp32 GEMM)
 };

@@ -1,0 +1,255 @@
+// PRECISE token-wise MLP block on tcgen05 (fp16 hi + lo operand pairs, 3 MMAs per product, fp32 accumulate):
+//     Xout[row] = Xin[row] (+ Xres[row]) + fc2(act(fc1(LayerNorm(Xin[row]))))
+// Reference: the FFN half of SwinTransformerBlock.forward (model.py:223, Mlp 128 -> 512 GELU -> 128; Xin = Xout, no Xres)
+// and the MLP of ClassTransformerLayer.forward (model.py:413 + the outer residual :423, ReLU; Xres = the layer input).
+//
+// One pass = 128 token rows (one UMMA M tile).  Shared memory holds LN(x) and one hidden chunk as hi/lo tile pairs
+// (4 x 32.25 KiB) next to a 3-slot ring of 32 KiB weight images (16 images per pass: W1 hi/lo and W2 hi/lo of the four
+// hidden chunks of 128, stored in consumption order).  TMEM: H0 H1 Y (3 x 128 columns): with two hidden accumulators the
+// fc1 MMAs of chunk j+1 and the fc2 MMAs of chunk j-1 run under the activation epilogue of chunk j:
+//     sync(j-1) -> issue MMA2(j-1), MMA1(j+1) | workers: epilogue(j) (TMEM H[j&1] -> act -> hi/lo tiles) -> sync(j) ...
+// Roles as in fast_mlp.cu: warps 0-15 = LayerNorm prologue + epilogues, warp 16 = issuing warp (MMAs and the weight ring).
+#include <cstdio>
+#include <cstdlib>
+
+#include "internal.h"
+#include "split_common.cuh"
+
+namespace catseg {
+
+using namespace fast;
+
+namespace {
+constexpr int SP_EPI_WARPS = 16;
+constexpr int SP_EPI_THREADS = SP_EPI_WARPS * 32;
+constexpr int SP_THREADS = SP_EPI_THREADS + 32;
+constexpr uint32_t SP_RING = 0;                                   // 3 x 32 KiB weight ring
+constexpr uint32_t SP_XH = SP_RING + 3 * WIMG_BYTES;              // LN(x) hi
+constexpr uint32_t SP_XL = SP_XH + TILE_BYTES_T;                  // LN(x) lo
+constexpr uint32_t SP_HH = SP_XL + TILE_BYTES_T;                  // hidden chunk hi
+constexpr uint32_t SP_HL = SP_HH + TILE_BYTES_T;                  // hidden chunk lo
+constexpr uint32_t SP_PAR = SP_HL + TILE_BYTES_T;                 // b2[128] g[128] b[128] floats (b1 is read from global)
+constexpr uint32_t SP_BAR = SP_PAR + 384 * 4;                     // full[3] empty[3] h[2] y[1] + tmem ptr
+constexpr uint32_t SP_SMEM = SP_BAR + 10 * 8 + 16;
+static_assert(SP_SMEM <= 232448, "shared memory budget");
+static_assert(STG_BYTES <= 4 * TILE_BYTES_T, "the fp32 staging tile aliases the operand tiles");
+constexpr uint32_t TM_H0 = 0, TM_Y = 256;
+}  // namespace
+
+template <int ACT>   // 0 = GELU (Swin), 1 = ReLU (class layer)
+__global__ void __launch_bounds__(SP_THREADS, 1)
+mlp_split_kernel(const float* __restrict__ Xin, const float* __restrict__ Xres, float* __restrict__ Xout, long long ntok,
+                 MlpSplitW w) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + SP_BAR);        // [3]
+  uint64_t* bar_empty = bar_full + 3;                                      // [3]
+  uint64_t* bar_h = bar_full + 6;                                          // [2] H0 / H1 ready
+  uint64_t* bar_y = bar_full + 8;                                          // an fc2 chain has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 9);
+  float* s_b2 = reinterpret_cast<float*>(smem + SP_PAR);
+  float* s_g = s_b2 + 128;
+  float* s_be = s_g + 128;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool issuer = __shfl_sync(0xffffffffu, warp, 0) == SP_EPI_WARPS;   // warp-uniform role
+
+  const long long npass = (ntok + 127) / 128;
+  long long my_pass = 0;
+  for (long long p = blockIdx.x; p < npass; p += gridDim.x) ++my_pass;
+
+  if (tid < 128) { s_b2[tid] = w.b2[tid]; s_g[tid] = w.ln_g[tid]; s_be[tid] = w.ln_b[tid]; }
+  if (tid == 0) {
+    for (int i = 0; i < 9; ++i) umma::mbar_init(&bar_full[i], 1);
+    umma::mbar_fence_init();
+  }
+  if (warp == 0) umma::tmem_alloc<512>(tmem_slot);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tm = *tmem_slot;
+  const uint32_t sb = umma::smem_u32(smem);
+  const uint64_t d_xh = umma::make_smem_desc(sb + SP_XH, LBO_T, 128), d_xl = umma::make_smem_desc(sb + SP_XL, LBO_T, 128);
+  const uint64_t d_hh = umma::make_smem_desc(sb + SP_HH, LBO_T, 128), d_hl = umma::make_smem_desc(sb + SP_HL, LBO_T, 128);
+  const uint64_t d_w0 = umma::make_smem_desc(sb + SP_RING, LBO_W, 128);
+
+  split::WeightRing<3, WIMG_BYTES> ring;
+  ring.init(smem + SP_RING, bar_full, bar_empty, w.wimg, 16, my_pass * 16);
+  if (issuer) ring.prime();
+  // one product chain A W^T with A = a_hi + a_lo and W = (next two ring images: hi, lo): 24 MMAs
+  auto chain = [&](uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, bool acc) {
+    uint32_t off = ring.acquire();
+    uint64_t wd = d_w0 + (uint64_t)(off >> 4);
+    if (umma::elect_one()) {
+      issue_gemm_k128_desc(d_tmem, a_hi, LBO_T, wd, LBO_W, IDESC_128x128, acc);
+      issue_gemm_k128_desc(d_tmem, a_lo, LBO_T, wd, LBO_W, IDESC_128x128, true);
+    }
+    __syncwarp();
+    ring.release();
+    off = ring.acquire();
+    wd = d_w0 + (uint64_t)(off >> 4);
+    if (umma::elect_one()) issue_gemm_k128_desc(d_tmem, a_hi, LBO_T, wd, LBO_W, IDESC_128x128, true);
+    __syncwarp();
+    ring.release();
+  };
+
+  const int q = warp & 3, cq = (warp >> 2) & 3;          // TMEM lane quarter, column quarter (32 columns)
+  const int row = q * 32 + lane;
+  float* stage = reinterpret_cast<float*>(smem + SP_XH);
+  const uint32_t lane_addr = tm + ((uint32_t)(q * 32) << 16);
+  uint32_t ph_h[2] = {0u, 0u}, ph_y = 0u;
+
+  for (long long p = blockIdx.x; p < npass; p += gridDim.x) {
+    const long long row0 = p * 128;
+    if (!issuer) {
+      const long long nrow0 = (p + gridDim.x) * 128;      // next pass: 512 lines of 128 bytes into L2
+      const long long r = nrow0 + (tid >> 2);
+      if (r < ntok) umma::prefetch_l2(Xin + r * 128 + (tid & 3) * 32);
+      const long long nv = ntok - row0;
+      split::ln_rows_to_tile_split(Xin + row0 * 128, 128, nv >= 128 ? 128 : (int)nv, smem + SP_XH, smem + SP_XL, s_g, s_be,
+                                   warp, SP_EPI_WARPS, lane);
+      umma::fence_proxy_async();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (issuer) {
+      umma::fence_after_sync();
+      chain(tm + TM_H0, d_xh, d_xl, false);
+      if (umma::elect_one()) umma::mma_commit(&bar_h[0]);
+      __syncwarp();
+      chain(tm + TM_H0 + 128, d_xh, d_xl, false);
+      if (umma::elect_one()) umma::mma_commit(&bar_h[1]);
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const int hb = j & 1;
+      if (!issuer) {
+        umma::mbar_wait(&bar_h[hb], ph_h[hb]); ph_h[hb] ^= 1u;
+        umma::fence_after_sync();
+        uint4 phi[4], plo[4];
+        {
+          float v[32];
+          umma::tmem_ld32(lane_addr + TM_H0 + hb * 128 + cq * 32, v);
+          const float4* bb = reinterpret_cast<const float4*>(w.b1 + j * 128 + cq * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b4 = __ldg(bb + i);
+            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = ACT == 0 ? split::gelu_precise(v[i]) : fmaxf(v[i], 0.0f);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            umma::split_h2(v[c * 8 + 0], v[c * 8 + 1], phi[c].x, plo[c].x);
+            umma::split_h2(v[c * 8 + 2], v[c * 8 + 3], phi[c].y, plo[c].y);
+            umma::split_h2(v[c * 8 + 4], v[c * 8 + 5], phi[c].z, plo[c].z);
+            umma::split_h2(v[c * 8 + 6], v[c * 8 + 7], phi[c].w, plo[c].w);
+          }
+        }
+        if (j > 0) {                                       // the hidden tiles are free once fc2 of chunk j-1 has completed
+          umma::mbar_wait(bar_y, ph_y); ph_y ^= 1u;
+          umma::fence_after_sync();
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          *reinterpret_cast<uint4*>(smem + SP_HH + (cq * 4 + c) * LBO_T + row * 16) = phi[c];
+          *reinterpret_cast<uint4*>(smem + SP_HL + (cq * 4 + c) * LBO_T + row * 16) = plo[c];
+        }
+        umma::fence_proxy_async();
+      }
+      umma::fence_before_sync();
+      __syncthreads();                                     // hidden tiles written; every warp has read H[hb]
+      if (issuer) {
+        umma::fence_after_sync();
+        chain(tm + TM_Y, d_hh, d_hl, j > 0);
+        if (umma::elect_one()) umma::mma_commit(bar_y);
+        __syncwarp();
+        if (j + 2 < 4) {                                   // H[hb] is free: fc1 of chunk j+2
+          chain(tm + TM_H0 + hb * 128, d_xh, d_xl, false);
+          if (umma::elect_one()) umma::mma_commit(&bar_h[hb]);
+          __syncwarp();
+        }
+      }
+    }
+    // ---- Y epilogue: residual rows (coalesced, warp per row) are fetched before waiting for the last fc2 chain
+    float4 xres[8];
+    if (!issuer) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long long r = row0 + warp * 8 + i;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < ntok) {
+          a = ld4(Xin + r * 128 + lane * 4);
+          if (Xres != nullptr) a = f4add(a, ld4(Xres + r * 128 + lane * 4));
+        }
+        xres[i] = a;
+      }
+      umma::mbar_wait(bar_y, ph_y); ph_y ^= 1u;
+      umma::fence_after_sync();
+      float v[32];
+      umma::tmem_ld32(lane_addr + TM_Y + cq * 32, v);
+      const float* bb = s_b2 + cq * 32;
+      float* sp = stage + row * STG_LD + cq * 32;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) st4(sp + i, make_float4(v[i] + bb[i], v[i + 1] + bb[i + 1], v[i + 2] + bb[i + 2], v[i + 3] + bb[i + 3]));
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (!issuer) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long long r = row0 + warp * 8 + i;
+        if (r < ntok) st4(Xout + r * 128 + lane * 4, f4add(xres[i], ld4(stage + (warp * 8 + i) * STG_LD + lane * 4)));
+      }
+    }
+    __syncthreads();
+    umma::fence_after_sync();          // TMEM and the operand tiles may be overwritten by the next pass
+  }
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc<512>(tm);
+}
+
+cudaError_t launch_mlp_split(const float* Xin, const float* Xres, float* Xout, long long ntok, const MlpSplitW& w, int act,
+                             int num_sms, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(mlp_split_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(mlp_split_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM);
+  if (e != cudaSuccess) return e;
+  const long long npass = (ntok + 127) / 128;
+  const int grid = (int)(npass < num_sms ? npass : num_sms);
+  if (grid <= 0) return cudaSuccess;
+  if (act == 0) mlp_split_kernel<0><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w);
+  else mlp_split_kernel<1><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w);
+  return cudaGetLastError();
+}
+
+// ---- weight image packing: hi / lo fp16 images (canonical dense 128x128) <- W[r0 + r][c0 + k], ld = row stride
+__global__ void pack_wimg_split_kernel(__half* __restrict__ dhi, __half* __restrict__ dlo, const float* __restrict__ W, int ld,
+                                       int r0, int c0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 128 * 128) return;
+  const int r = i >> 7, k = i & 127;
+  const float v = W[(long long)(r0 + r) * ld + c0 + k];
+  const __half h = __float2half_rn(v);
+  const int o = (k >> 3) * (128 * 8) + r * 8 + (k & 7);
+  dhi[o] = h;
+  if (dlo != nullptr) dlo[o] = __float2half_rn(v - __half2float(h));
+}
+cudaError_t launch_pack_wimg_split(__half* dhi, __half* dlo, const float* W, int ld, int r0, int c0, cudaStream_t st) {
+  pack_wimg_split_kernel<<<64, 256, 0, st>>>(dhi, dlo, W, ld, r0, c0);
+  return cudaGetLastError();
+}
+
+cudaError_t pack_mlp_split(__half* dst, const float* W1, const float* W2, cudaStream_t st) {
+  // consumption order of mlp_split_kernel: (fc1, chunk) and (fc2, chunk) pairs, each as a hi and a lo image
+  static const int kind[8] = {1, 1, 2, 1, 2, 1, 2, 2}, chunk[8] = {0, 1, 0, 2, 1, 3, 2, 3};
+  for (int i = 0; i < 8; ++i) {
+    __half* hi = dst + (size_t)(2 * i) * 128 * 128;
+    __half* lo = hi + 128 * 128;
+    cudaError_t e = kind[i] == 1 ? launch_pack_wimg_split(hi, lo, W1, 128, chunk[i] * 128, 0, st)
+                                 : launch_pack_wimg_split(hi, lo, W2, 512, 0, chunk[i] * 128, st);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace catseg

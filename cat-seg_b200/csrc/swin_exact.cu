@@ -270,15 +270,13 @@ swin_block_exact_kernel(float* __restrict__ X, const float* __restrict__ ag_qk, 
 
 cudaError_t launch_swin_block_exact(float* X, const float* ag_qk, int nslice, int Te, int shift,
                                     const SwinBlockW& w, int with_mlp, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // per-device function attribute: set on every launch (cheap), a process-wide flag would miss other devices
     cudaError_t e = cudaFuncSetAttribute(swin_block_exact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)SWIN_SMEM);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(swin_block_exact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)SWIN_SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   if (with_mlp) swin_block_exact_kernel<true><<<nslice * 4, 512, SWIN_SMEM, st>>>(X, ag_qk, Te, shift, w);
   else swin_block_exact_kernel<false><<<nslice * 4, 512, SWIN_SMEM, st>>>(X, ag_qk, Te, shift, w);

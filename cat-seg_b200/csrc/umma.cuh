@@ -12,6 +12,7 @@
 // Descriptor bit layout per cute/arch/mma_sm100_desc.hpp (SmemDescriptor / InstrDescriptor).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -43,13 +44,29 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_major
          | ((uint32_t)(M >> 4) << 24);// m_dim
 }
 
+// kind::f16 with FP16 x FP16 -> FP32 operands (a_format = b_format = 0).  The aggregation kernels use fp16
+// operands: 11 significant bits instead of bf16's 8 (raw argmax agreement with the fp32 reference 98 % instead of
+// 87 % on random-init weights, tools/precision_study.py), and a hi+lo fp16 pair carries 22 bits for the PRECISE
+// mode.  Every operand of these kernels is a normalised activation, a probability or a weight: far inside fp16's
+// range (65504); conversions saturate instead of overflowing to infinity.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_major = 0, int b_major = 0) {
+  return (1u << 4)                    // c_format = F32; a_format = b_format = F16 (0)
+         | ((uint32_t)a_major << 15) | ((uint32_t)b_major << 16)
+         | ((uint32_t)(N >> 3) << 17) // n_dim
+         | ((uint32_t)(M >> 4) << 24);// m_dim
+}
+
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
-__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
       :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {       // same instruction: the operand format is in idesc
+  mma_f16_ss(d_tmem, a_desc, b_desc, idesc, accumulate);
 }
 // Makes the mbarrier track completion of all prior tcgen05.mma of this thread (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
@@ -189,6 +206,25 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// ---- fp16 operand helpers.  op16 is the 16-bit operand type of the aggregation kernels.
+typedef __half op16;
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {       // (lo, hi) -> one 32-bit word, saturating
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t v) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significant bits (lo may be subnormal: absolute error <= 3e-8)
+__device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_h2(a, b);
+  const float2 h = unpack_h2(hi);
+  lo = pack_h2(a - h.x, b - h.y);
+}
+__device__ __forceinline__ op16 f2op(float v) { return __float2half_rn(v); }
+__device__ __forceinline__ float op2f(op16 v) { return __half2float(v); }
+
 // byte offset of (row r, K-chunk c) in a canonical tile with `rows` rows
 __device__ __forceinline__ uint32_t canon_off(int r, int c, int rows) { return (uint32_t)(c * rows * 16 + r * 16); }
 

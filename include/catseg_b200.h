@@ -35,16 +35,23 @@ extern "C" {
 #define CATSEG_ERR_CUDA (-4)        /* CUDA runtime / launch error */
 #define CATSEG_ERR_WEIGHTS (-5)     /* unknown / missing / mis-sized parameter */
 
-/* precision: 0 = EXACT (fp32 CUDA-core arithmetic end to end: the parity gate); otherwise a bit mask
- * of the stages that run on the FAST path (bf16 tcgen05 operands, fp32 accumulate, fp32 residual
- * stream).  CATSEG_PRECISION_FAST selects every stage that has a fast kernel. */
+/* precision: 0 = EXACT (fp32 CUDA-core arithmetic end to end); otherwise a bit mask of the stages that
+ * run on the tensor cores (tcgen05, fp16 operands, fp32 accumulate, fp32 residual stream).
+ *   FAST    = one fp16 term per operand (11 significant bits).
+ *   PRECISE = CATSEG_PRECISE_SPLIT set: the value path uses hi + lo fp16 operand pairs (3 MMAs per product,
+ *             ~22 bits), the attention-weight path stays single (cat-seg_b200/csrc/split_common.cuh):
+ *             the mode that meets north_star's >= 99.9 % argmax agreement with the fp32 reference.
+ * CATSEG_PRECISION_FAST / CATSEG_PRECISION_PRECISE select every stage that has a kernel of that kind; a
+ * stage without one runs the EXACT kernel. */
 #define CATSEG_PRECISION_EXACT 0
 #define CATSEG_FAST_SWIN_MLP 1   /* FFN half of the Swin blocks */
 #define CATSEG_FAST_SWIN_ATTN 2  /* window-attention half of the Swin blocks */
 #define CATSEG_FAST_CLASS 4      /* class-aggregation layers */
 #define CATSEG_FAST_DECODER 8    /* upsampling decoder */
 #define CATSEG_FAST_PREP 16      /* 7x7 cost embedding (fp32-accurate split) and the 3x3 guidance projections */
-#define CATSEG_PRECISION_FAST 0x7fffffff
+#define CATSEG_PRECISE_SPLIT 0x100 /* modifier: selected stages use hi+lo fp16 operand pairs */
+#define CATSEG_PRECISION_FAST 0x1f
+#define CATSEG_PRECISION_PRECISE (0x1f | CATSEG_PRECISE_SPLIT)
 
 typedef struct catseg_handle catseg_handle;
 typedef void* catseg_stream; /* cudaStream_t */

@@ -52,8 +52,9 @@ def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
 def argmax_agreement(logits: torch.Tensor, ref: torch.Tensor):
     """(raw agreement, margin-filtered agreement, filtered fraction, max abs err) over pixels.
 
-    Margin filter: pixels whose reference top1-top2 margin exceeds 2x the max
-    absolute logit error cannot legitimately flip."""
+    `raw` is the number north_star gates on.  The margin-filtered value (pixels whose reference top1-top2
+    margin exceeds 2x the max absolute logit error) is a SANITY check only: such pixels cannot flip by
+    construction, so it can only fail on an indexing bug; `frac` says how many pixels it covers."""
     err = (logits - ref).abs().max().item()
     a, r = logits.argmax(dim=1), ref.argmax(dim=1)
     raw = (a == r).float().mean().item()
@@ -63,3 +64,4 @@ def argmax_agreement(logits: torch.Tensor, ref: torch.Tensor):
     safe = (top2[:, 0] - top2[:, 1]) > 2 * err
     filt = (a == r)[safe].float().mean().item() if safe.any() else 1.0
     return raw, filt, safe.float().mean().item(), err
+

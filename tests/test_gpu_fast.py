@@ -1,9 +1,11 @@
-"""GPU (-m gpu): the FAST path (bf16 tcgen05 operands, fp32 accumulate, fp32 residual stream).
+"""GPU (-m gpu): the FAST path (tcgen05, ONE fp16 term per operand, fp32 accumulate, fp32 residual stream).
 
-Stated bf16 tolerance (north_star): logits max-abs <= 6e-2 and rel-L2 <= 3e-2 against the fp32 oracle with the
-synthetic weights of cat_seg_b200.synth; the -100 mask must be exactly equal; argmax agreement on pixels whose
-oracle margin exceeds 2x the max error must be 100 % (SURVEY.md §0.9 explains why raw agreement cannot reach
-99.9 % with bf16 operands on random-init weights — the EXACT path is the 99.9 % gate)."""
+Stated tolerance: logits max-abs <= 8e-3 and rel-L2 <= 4e-3 against the fp32 oracle with the synthetic weights of
+cat_seg_b200.synth (the CPU emulation of single fp16 operands gives 1.2e-3 / 1.1e-3, tools/precision_study.py); the
+-100 mask must be exactly equal.  Single 16-bit operands cannot meet the 99.9 % raw argmax gate on random-init
+weights (margins ~1e-5): this mode asserts a raw-agreement FLOOR (RAW_FLOOR; the emulation gives 98 %)
+next to the logits tolerance; the gate itself is met by the PRECISE mode
+(tests/test_gpu_precise.py), which is what bench.py runs."""
 import pytest
 import torch
 
@@ -14,7 +16,7 @@ from cat_seg_b200.synth import make_inputs, make_state_dict
 from oracle.aggregator_oracle import aggregator_forward
 
 pytestmark = pytest.mark.gpu
-FAST_MAXABS, FAST_RELL2 = 6e-2, 3e-2
+FAST_MAXABS, FAST_RELL2, RAW_FLOOR = 8e-3, 4e-3, 0.90
 
 
 def _run(cfg, B, T, seed, precision, same_text=False):
@@ -36,7 +38,9 @@ def test_fast_matches_oracle_within_bf16_tolerance(precision, case):
     kept = ref != -100.0
     raw, filt, frac, err = argmax_agreement(y, ref)
     assert err <= FAST_MAXABS and rel_l2(y[kept], ref[kept]) <= FAST_RELL2, (precision, err, rel_l2(y[kept], ref[kept]))
-    assert filt == 1.0, (raw, filt, frac)
+    print(f"{precision}: max-abs {err:.3e} argmax raw {raw:.4f} margin-safe fraction {frac:.3f}")
+    assert raw >= RAW_FLOOR, (precision, raw)
+    assert filt == 1.0      # sanity only: cannot fail unless indexing is broken (a margin-safe pixel cannot flip)
 
 
 def test_fast_large_tile_counts():
