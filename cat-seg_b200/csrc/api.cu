@@ -26,7 +26,7 @@ thread_local std::string g_create_error;
 
 constexpr int kImplementedFast = CATSEG_FAST_SWIN_MLP | CATSEG_FAST_SWIN_ATTN | CATSEG_FAST_DECODER | CATSEG_FAST_CLASS | CATSEG_FAST_PREP;   // stages that have a tcgen05 kernel in this build
 // stages that have a PRECISE (hi + lo fp16 operand pair) kernel; the others run the EXACT kernel in that mode
-constexpr int kImplementedSplit = CATSEG_FAST_SWIN_MLP | CATSEG_FAST_PREP;
+constexpr int kImplementedSplit = CATSEG_FAST_SWIN_MLP | CATSEG_FAST_CLASS | CATSEG_FAST_DECODER | CATSEG_FAST_PREP;
 constexpr int kMaxProfForwards = 64;
 constexpr int kMaxSegments = 40;
 
@@ -46,6 +46,8 @@ struct catseg_handle {
   __half* wimg_split = nullptr;      // hi/lo fp16 weight images of the PRECISE kernels
   size_t wimg_split_elems = 0;
   std::vector<MlpSplitW> swin_mlp_split;   // [L*2]
+  std::vector<ClassSplitW> class_split;    // [L]
+  std::vector<MlpSplitW> class_mlp_split;  // [L]
   int num_sms = 148;
   std::vector<MlpFastW> swin_mlp_fast;   // [L*2]
   std::vector<SwinAttnFastW> swin_attn_fast;   // [L*2]
@@ -523,7 +525,7 @@ extern "C" int catseg_finalize_params(catseg_handle* h, catseg_stream stream) {
   if (h->split && h->fast_mask) {
     const int L = h->cfg.num_layers;
     const size_t kImg = 128 * 128;
-    const size_t need = (size_t)L * 2 * 16 * kImg;
+    const size_t need = (size_t)L * 2 * 16 * kImg + (size_t)L * 22 * kImg;
     if (!h->wimg_split || h->wimg_split_elems < need) {
       if (h->wimg_split) cudaFree(h->wimg_split);
       h->wimg_split = nullptr;
@@ -541,6 +543,23 @@ extern "C" int catseg_finalize_params(catseg_handle* h, catseg_stream stream) {
         const SwinBlockW& sw = h->swin[l * 2 + k];
         h->swin_mlp_split[l * 2 + k] = MlpSplitW{img, sw.ln2_g, sw.ln2_b, sw.b1, sw.b2};
       }
+    const int tg = h->cfg.text_guidance_proj_dim;
+    h->class_split.assign(L, ClassSplitW{});
+    h->class_mlp_split.assign(L, MlpSplitW{});
+    for (int l = 0; l < L; ++l) {
+      snprintf(b, sizeof(b), "layers.%d.attention", l);
+      std::string a(b);
+      __half* img = h->wimg_split + (size_t)L * 2 * 16 * kImg + (size_t)l * 22 * kImg;
+      CUDA_OK(h, launch_pack_wimg_split(img + 0 * kImg, nullptr, raw_of(h, a + ".attention.k.weight"), 128 + tg, 0, 0, st));
+      CUDA_OK(h, launch_pack_wimg_split(img + 1 * kImg, nullptr, raw_of(h, a + ".attention.k.weight"), 128 + tg, 0, 128, st));
+      CUDA_OK(h, launch_pack_wimg_split(img + 2 * kImg, img + 3 * kImg, raw_of(h, a + ".attention.v.weight"), 128, 0, 0, st));
+      CUDA_OK(h, launch_pack_wimg_split(img + 4 * kImg, nullptr, raw_of(h, a + ".attention.q.weight"), 128 + tg, 0, 0, st));
+      CUDA_OK(h, launch_pack_wimg_split(img + 5 * kImg, nullptr, raw_of(h, a + ".attention.q.weight"), 128 + tg, 0, 128, st));
+      CUDA_OK(h, pack_mlp_split(img + 6 * kImg, raw_of(h, a + ".MLP.0.weight"), raw_of(h, a + ".MLP.2.weight"), st));
+      const ClassLayerW& cw = h->cls[l];
+      h->class_split[l] = ClassSplitW{img, img + 4 * kImg, cw.ln1_g, cw.ln1_b, cw.bqk, cw.bv};
+      h->class_mlp_split[l] = MlpSplitW{img + 6 * kImg, cw.ln2_g, cw.ln2_b, cw.b1, cw.b2};
+    }
   }
   if ((h->fast_mask & CATSEG_FAST_CLASS) && !h->split) {
     const int L = h->cfg.num_layers, tg = h->cfg.text_guidance_proj_dim;
@@ -565,20 +584,21 @@ extern "C" int catseg_finalize_params(catseg_handle* h, catseg_stream stream) {
       h->class_fast[l] = ClassFastW{img, ap, cw.ln1_g, cw.ln1_b, cw.ln2_g, cw.ln2_b, cw.bqk, cw.bv, cw.b1, cw.b2};
     }
   }
-  if ((h->fast_mask & CATSEG_FAST_DECODER) && !h->split) {
+  if (h->fast_mask & CATSEG_FAST_DECODER) {
     const catseg_config& c = h->cfg;
+    const int nw = h->split ? 2 : 1;
     DecoderDims dd{c.feature_resolution[0], c.feature_resolution[1], 128, 128 - c.decoder_guidance_proj_dims[0],
                    c.decoder_guidance_proj_dims[0], c.decoder_dims[0], c.decoder_dims[0] - c.decoder_guidance_proj_dims[1],
                    c.decoder_guidance_proj_dims[1], c.decoder_dims[1]};
     if (dd.D1 != 64 || dd.D2 != 32)
       return fail(h, CATSEG_ERR_UNSUPPORTED, "the fast decoder is built for decoder_dims (64, 32)");
-    if (!h->dec_fast_store) CUDA_OK(h, cudaMalloc(&h->dec_fast_store, decoder_fast_weight_bytes(dd)));
+    if (!h->dec_fast_store) CUDA_OK(h, cudaMalloc(&h->dec_fast_store, decoder_fast_weight_bytes(dd, nw)));
     cudaError_t e = decoder_fast_pack(dd, raw_of(h, "decoder1.up.weight"), raw_of(h, "decoder1.up.bias"),
                                       raw_of(h, "decoder1.conv.double_conv.0.weight"),
                                       raw_of(h, "decoder1.conv.double_conv.3.weight"), raw_of(h, "decoder2.up.weight"),
                                       raw_of(h, "decoder2.up.bias"), raw_of(h, "decoder2.conv.double_conv.0.weight"),
                                       raw_of(h, "decoder2.conv.double_conv.3.weight"), raw_of(h, "head.weight"),
-                                      h->dec_fast_store, &h->dec_fast, st);
+                                      h->dec_fast_store, &h->dec_fast, nw, st);
     if (e != cudaSuccess) return fail(h, CATSEG_ERR_CUDA, "decoder_fast_pack: %s", cudaGetErrorString(e));
     CUDA_OK(h, cudaMemcpyAsync(&h->head_bias_host, raw_of(h, "head.bias"), sizeof(float), cudaMemcpyDeviceToHost, st));
   }
@@ -619,7 +639,7 @@ struct Plan {
   DecoderDims dd;
   // workspace offsets (floats)
   size_t imgn, textn, corr, cmax, classes, tmean, text_g, cg_qk, pad_state, app_g, app_gn, ag_qk, dg0, dg1, X,
-      Xp, Xp2, state, timg, dec, agw, classes_loc, total;
+      Xp, Xp2, X1, state, timg, dec, agw, classes_loc, total;
 };
 
 Plan make_plan(const catseg_handle* h, int B, int T) {
@@ -662,13 +682,15 @@ Plan make_plan(const catseg_handle* h, int B, int T) {
     p.Xp = take((size_t)nslice * p.npix * 128);
     p.Xp2 = take((size_t)nslice * p.npix * 128);
   }
+  if (h->split && (h->fast_mask & CATSEG_FAST_CLASS) && !p.pooled)
+    p.X1 = take((size_t)nslice * p.npix * 128);            // PRECISE class layer: x1 = x + attention, input of its MLP kernel
   p.state = take((size_t)B * p.npix * kStateFloats);
   p.timg = take((size_t)B * ((p.Te + 127) / 128) * 8192);   // bf16 text-guidance images (FAST class path)
   {
     size_t fe = decoder_exact_scratch_floats(p.dd, p.dec_chunk);
     if (h->fast_mask & CATSEG_FAST_DECODER) {
       p.dec_chunk = nslice < 1024 ? nslice : 1024;
-      fe = (decoder_fast_scratch_bytes(p.dd, B, p.dec_chunk) + 3) / 4;
+      fe = ((h->split ? decoder_split_scratch_bytes(p.dd, B, p.dec_chunk) : decoder_fast_scratch_bytes(p.dd, B, p.dec_chunk)) + 3) / 4;
     }
     p.dec = take(fe);
   }
@@ -858,13 +880,19 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
     const float* xin = p.pooled ? ws + p.Xp : X;
     float* xout = p.pooled ? ws + p.Xp2 : X;
     const int omode = p.pooled ? 1 : 0;
-    if (class_fast) RUN(launch_class_state_fast(xin, timg, ws + p.state, B, Te, p.npix, p.S, h->class_fast[l], h->num_sms, st));
+    if (class_fast && h->split) RUN(launch_class_state_split(xin, timg, ws + p.state, B, Te, p.npix, p.S, h->class_split[l], h->num_sms, st));
+    else if (class_fast) RUN(launch_class_state_fast(xin, timg, ws + p.state, B, Te, p.npix, p.S, h->class_fast[l], h->num_sms, st));
     else RUN(launch_class_state_exact(xin, cg, ws + p.state, B, Te, p.npix, p.S, h->cls[l], st));
     if (sharded) {                                         // the only exchange step of the path: sum of the per-pixel state
       int rc = allreduce(ar_ctx, ws + p.state, (size_t)B * p.npix * kStateFloats, stream);
       if (rc != 0) return fail(h, CATSEG_ERR_CUDA, "class-shard all-reduce callback failed (%d)", rc);
     }
-    if (class_fast)
+    if (class_fast && h->split) {
+      // x1 = x + attention -> X1 (pooled: Xp2), then the token MLP kernel adds MLP(LN2(x1)) and the outer residual (model.py:423)
+      float* x1 = p.pooled ? ws + p.Xp2 : ws + p.X1;
+      RUN(launch_class_apply_split(xin, x1, timg, ws + p.state, pad, B, Te, p.npix, p.S, h->class_split[l], h->num_sms, st));
+      RUN(launch_mlp_split(x1, p.pooled ? nullptr : X, xout, (long long)nslice * p.npix, h->class_mlp_split[l], 1, h->num_sms, st));
+    } else if (class_fast)
       RUN(launch_class_apply_fast(xin, xout, timg, ws + p.state, pad, B, Te, p.npix, p.S, omode, h->class_fast[l], h->num_sms, st));
     else
       RUN(launch_class_apply_exact(xin, xout, cg, ws + p.state, pad, B, Te, p.npix, p.S, omode, h->cls[l], st));
@@ -889,8 +917,9 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
   if (h->fast_mask & CATSEG_FAST_DECODER) {
     if (taps && (taps->up1 || taps->up2))
       return fail(h, CATSEG_ERR_UNSUPPORTED, "up1/up2 taps are only available with the exact decoder");
-    cudaError_t e = run_decoder_fast(X, ws + p.dg0, ws + p.dg1, out_ids, logits, B, T_out, Te, p.dd, h->dec_fast, h->dec,
-                                     h->head_bias_host, ws + p.dec, p.dec_chunk, h->num_sms, &nl, st);
+    cudaError_t e = (h->split ? run_decoder_split : run_decoder_fast)(X, ws + p.dg0, ws + p.dg1, out_ids, logits, B, T_out, Te, p.dd,
+                                                                       h->dec_fast, h->dec, h->head_bias_host, ws + p.dec,
+                                                                       p.dec_chunk, h->num_sms, &nl, st);
     if (e != cudaSuccess) return fail(h, CATSEG_ERR_CUDA, "fast decoder: %s", cudaGetErrorString(e));
   } else {
     cudaError_t e = run_decoder_exact(X, ws + p.dg0, ws + p.dg1, out_ids, logits, B, T_out, Te, p.dd, h->dec,

@@ -21,6 +21,7 @@ constexpr uint32_t LBO_T = 128 * 16 + 16;       // thread-written 128-row tiles,
 constexpr uint32_t TILE_BYTES_T = 16 * LBO_T;   // 128 features = 16 chunks
 constexpr uint32_t WIMG_BYTES = 16 * LBO_W;     // one 128x128 fp16 weight image = 32 KiB
 constexpr uint32_t IDESC_128x128 = umma::make_idesc_f16(128, 128);
+constexpr uint32_t IDESC_BF16_128x128 = umma::make_idesc_bf16(128, 128);   // the 7x7 embedding keeps its hi+lo bf16 split (fast_prep.cu)
 
 // 8 k-steps of a [128 x 128] x [N x 128]^T GEMM from PRE-BUILT base descriptors: the issuing thread only adds the
 // K-step offset to the address field (building a descriptor from scratch costs ~50-100 cycles in one thread,

@@ -41,6 +41,7 @@ struct BandConvParams {
                              // [B][NB][4 parities][NTILES][NREAL/4][128 rows][4] fp32, else nullptr
   int Te;
   __half* out;        // [S][Wout*Wout][NREAL]
+  float* out32;       // PRECISE: the same tensor in fp32
   float* out_stats;          // [S][NB][G_out][2]
   float* logits;             // HEAD: [B][T][Wout*Wout]
   const int32_t* classes;    // HEAD: [B*Te] (absolute slice index)
@@ -51,7 +52,9 @@ struct BandConvParams {
   long long* dbg;            // optional phase timing (CATSEG_PHASE_TIMING=1)
 };
 
-template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD, int CTAS = 2>
+// SPLIT = PRECISE mode (split_common.cuh): the staged band exists as a hi and a lo fp16 image, every weight image as a hi
+// and a lo image, each tap issues three products (hi*hi, lo*hi, hi*lo), and the intermediates in HBM are fp32.
+template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD, int CTAS = 2, bool SPLIT = false>
 struct BandCfg {
   static constexpr int PW = WIN_ + 2, NP = (BR + 2) * PW, P0 = PW + 1;
   static constexpr int MROWS = (BR - 1) * PW + WIN_, NTILES = (MROWS + 127) / 128;
@@ -60,20 +63,22 @@ struct BandCfg {
   static constexpr int OVER = P0 + NTILES * 128 + PW + 2 - NP;
   static constexpr uint32_t IMG_BYTES = ((KCH * LBO_I + (OVER > 0 ? OVER * 16 : 0)) + 127) / 128 * 128;
   static constexpr int NTAP = UPS ? 4 : 9, NPG = UPS ? 4 : 1, NIMG = NTAP * NPG;
+  static constexpr int NW = SPLIT ? 2 : 1;                               // images per weight / per staged band (hi, lo)
   static constexpr uint32_t WBYTES = NOUT * CIN * 2, LBO_WT = NOUT * 16;
   // two CTAs per SM (half-height bands, <= 113 KiB and <= 256 TMEM columns each): one CTA's staging / epilogue
   // overlaps the other's MMAs.  Small weight sets stay resident, larger ones stream through a ring.
   // (the whole weight set may stay in shared memory when, together with the band image, it fits half an SM)
-  static constexpr bool RESIDENT = NIMG * WBYTES <= 24 * 1024 || IMG_BYTES + NIMG * WBYTES <= (CTAS == 2 ? 108 : 200) * 1024;
+  static constexpr bool RESIDENT = NW * NIMG * WBYTES <= 24 * 1024 ||
+                                   NW * (IMG_BYTES + NIMG * WBYTES) <= (CTAS == 2 ? 108 : (SPLIT ? 214 : 200)) * 1024;
   // streaming ring: 48 KiB deep (96 KiB when the CTA owns the SM), so that the prefetch distance (in MMA time) exceeds the
   // ~1 us L2->SMEM latency
-  static constexpr int NSLOT = RESIDENT ? NIMG : (int)((CTAS == 2 ? 48 : 96) * 1024 / WBYTES);
+  static constexpr int NSLOT = RESIDENT ? NW * NIMG : (int)((CTAS == 2 ? 48 : 96) * 1024 / WBYTES);
   // worker warps (staging + epilogues): 8 per CTA with two CTAs per SM, 16 when the CTA owns the SM; one more warp issues
   static constexpr int NWW = CTAS == 2 ? 8 : 16, NWT = NWW * 32, THREADS = NWT + 32, NTG = NWW / 4;
   static constexpr int NB = WIN_ / BR;                 // bands per slice
   static constexpr int WOUT = UPS ? 2 * WIN_ : WIN_;
   static constexpr int GOUT = HEAD ? 1 : NREAL / 16;
-  static constexpr uint32_t SM_W = IMG_BYTES;
+  static constexpr uint32_t SM_W = NW * IMG_BYTES;
   static constexpr uint32_t SM_SC = SM_W + NSLOT * WBYTES;            // scale[CIN], shift[CIN]
   static constexpr uint32_t SM_ST = SM_SC + 2 * CIN * 4;              // [NWW warps][GOUT][2]
   static constexpr uint32_t SM_BAR = (SM_ST + NWW * GOUT * 2 * 4 + 15) / 16 * 16;
@@ -84,6 +89,7 @@ struct BandCfg {
   static constexpr int TMEM_COLS = CTAS == 2 ? 256 : 512;
   static_assert(NTILES * NOUT <= TMEM_COLS && NTILES <= 16, "TMEM columns");
   static_assert(SMEM <= (CTAS == 2 ? 113 * 1024 : 227 * 1024), "shared memory budget");
+  static_assert(!SPLIT || (IN_F32 && CTAS == 1), "PRECISE stages read fp32 activations and own the SM");
   static_assert(WIN_ % BR == 0 && CIN % 16 == 0 && NOUT % 16 == 0, "shape");
 };
 
@@ -93,9 +99,9 @@ struct BandCfg {
 // The composed (UPS) stages compute four output parities from the same staged image: with two accumulator sets the MMAs
 // of parity pg+1 run under the epilogue of parity pg.
 
-template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD, int CTAS>
+template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD, int CTAS, bool SPLIT>
 __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_conv_kernel(BandConvParams p) {
-  using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS>;
+  using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS, SPLIT>;
   extern __shared__ __align__(1024) uint8_t smem[];
   float* s_scale = reinterpret_cast<float*>(smem + C::SM_SC);
   float* s_shift = s_scale + CIN;
@@ -112,7 +118,7 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
   const long long nitems = (long long)p.nslice * C::NB;
   long long mine = 0;
   for (long long i = blockIdx.x; i < nitems; i += gridDim.x) ++mine;
-  const long long total_loads = C::RESIDENT ? 1 : mine * C::NIMG;
+  const long long total_loads = C::RESIDENT ? 1 : mine * C::NIMG * C::NW;
 
   if (tid == 0) {
     for (int i = 0; i < 2 * C::NSLOT + 32; ++i) umma::mbar_init(&bar_full[i], 1);
@@ -131,14 +137,14 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
       int s = (int)(n % C::NSLOT);
       umma::mbar_expect_tx(&bar_full[s], C::WBYTES);
       umma::bulk_g2s(smem + C::SM_W + s * C::WBYTES,
-                     reinterpret_cast<const uint8_t*>(p.wimg) + (n % C::NIMG) * C::WBYTES, C::WBYTES, &bar_full[s]);
+                     reinterpret_cast<const uint8_t*>(p.wimg) + (n % (C::NIMG * C::NW)) * C::WBYTES, C::WBYTES, &bar_full[s]);
     }
   };
   if (issuer) {
     if (umma::elect_one()) {
       if (C::RESIDENT) {
-        umma::mbar_expect_tx(&bar_full[0], C::NIMG * C::WBYTES);
-        umma::bulk_g2s(smem + C::SM_W, p.wimg, C::NIMG * C::WBYTES, &bar_full[0]);
+        umma::mbar_expect_tx(&bar_full[0], C::NW * C::NIMG * C::WBYTES);
+        umma::bulk_g2s(smem + C::SM_W, p.wimg, C::NW * C::NIMG * C::WBYTES, &bar_full[0]);
       } else {
         for (int i = 0; i < C::NSLOT - 1; ++i) issue_load(i);
       }
@@ -168,12 +174,22 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
             int off;
             if (UPS) off = ((tap >> 1) + pa - 1) * C::PW + ((tap & 1) + pb - 1);
             else off = (tap / 3 - 1) * C::PW + (tap % 3 - 1);
-            const uint64_t b_desc = umma::make_smem_desc(sb + C::SM_W + (uint32_t)(pg * C::NTAP + tap) * C::WBYTES, C::LBO_WT, 128);
+            const uint64_t b_desc = umma::make_smem_desc(sb + C::SM_W + (uint32_t)((pg * C::NTAP + tap) * C::NW) * C::WBYTES, C::LBO_WT, 128);
             const uint64_t a_tile = a_desc0 + (uint64_t)(uint32_t)(C::P0 + off + t * 128);
 #pragma unroll
             for (int k = 0; k < C::KSTEPS; ++k)
               umma::mma_f16_ss(tm + set * ACC_COLS + t * NOUT, a_tile + (uint64_t)(k * 2 * (C::LBO_I >> 4)),
                                 b_desc + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC, (tap > 0 || k > 0) ? 1u : 0u);
+            if constexpr (SPLIT) {
+#pragma unroll
+              for (int k = 0; k < C::KSTEPS; ++k)      // lo activations x hi weights
+                umma::mma_f16_ss(tm + set * ACC_COLS + t * NOUT, a_tile + (uint64_t)((C::IMG_BYTES >> 4) + k * 2 * (C::LBO_I >> 4)),
+                                 b_desc + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC, 1u);
+#pragma unroll
+              for (int k = 0; k < C::KSTEPS; ++k)      // hi activations x lo weights
+                umma::mma_f16_ss(tm + set * ACC_COLS + t * NOUT, a_tile + (uint64_t)(k * 2 * (C::LBO_I >> 4)),
+                                 b_desc + (uint64_t)((C::WBYTES >> 4) + k * 2 * (C::LBO_WT >> 4)), C::IDESC, 1u);
+            }
           }
           umma::mma_commit(&bar_acc[set * 16 + t]);
         }
@@ -182,19 +198,14 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
       return;
     }
 #pragma unroll 1
-    for (int tap = 0; tap < C::NTAP; ++tap) {
+    for (int tw = 0; tw < C::NTAP * C::NW; ++tw) {
+      const int tap = tw / C::NW, wlo = tw % C::NW;           // wlo = 1: the lo weight image of this tap (hi activations only)
       int off;
       if (UPS) off = ((tap >> 1) + pa - 1) * C::PW + ((tap & 1) + pb - 1);
       else off = (tap / 3 - 1) * C::PW + (tap % 3 - 1);
-      uint32_t wb;
-      int slot = 0;
-      if (C::RESIDENT) {
-        wb = sb + C::SM_W + (uint32_t)(pg * C::NTAP + tap) * C::WBYTES;
-      } else {
-        slot = (int)(nimg % C::NSLOT);
-        umma::mbar_wait(&bar_full[slot], (uint32_t)((nimg / C::NSLOT) & 1));
-        wb = sb + C::SM_W + (uint32_t)slot * C::WBYTES;
-      }
+      const int slot = (int)(nimg % C::NSLOT);
+      umma::mbar_wait(&bar_full[slot], (uint32_t)((nimg / C::NSLOT) & 1));
+      const uint32_t wb = sb + C::SM_W + (uint32_t)slot * C::WBYTES;
       // descriptors are built once and advanced by integer adds on the (address >> 4) field
       const uint64_t b_desc = umma::make_smem_desc(wb, C::LBO_WT, 128);
       if (umma::elect_one()) {
@@ -204,13 +215,19 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
 #pragma unroll
           for (int k = 0; k < C::KSTEPS; ++k)
             umma::mma_f16_ss(tm + set * ACC_COLS + t * NOUT, a_tile + (uint64_t)(k * 2 * (C::LBO_I >> 4)),
-                              b_desc + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC, (tap > 0 || k > 0) ? 1u : 0u);
+                              b_desc + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC, (tw > 0 || k > 0) ? 1u : 0u);
+          if (SPLIT && wlo == 0) {
+#pragma unroll
+            for (int k = 0; k < C::KSTEPS; ++k)
+              umma::mma_f16_ss(tm + set * ACC_COLS + t * NOUT, a_tile + (uint64_t)((C::IMG_BYTES >> 4) + k * 2 * (C::LBO_I >> 4)),
+                               b_desc + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC, 1u);
+          }
           a_tile += 128;
         }
-        if (!C::RESIDENT) umma::mma_commit(&bar_empty[slot]);
+        umma::mma_commit(&bar_empty[slot]);
       }
       __syncwarp();
-      if (!C::RESIDENT) {
+      {
         // refill the slot of the PREVIOUS image (its MMAs were committed one step ago)
         const long long nn = nimg + C::NSLOT - 1;
         if (nimg > 0 && nn < total_loads)
@@ -307,7 +324,7 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
           const int idx = base + u * C::NWT;
           if (idx >= NCHUNK) continue;
           const int pp = idx / C::KCH;
-          uint4 val = make_uint4(0u, 0u, 0u, 0u);
+          uint4 val = make_uint4(0u, 0u, 0u, 0u), vlo = make_uint4(0u, 0u, 0u, 0u);
           if (inb[u]) {
             float v[8];
             if (IN_F32) {
@@ -323,10 +340,18 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.0f);
             }
-            val = make_uint4(umma::pack_h2(v[0], v[1]), umma::pack_h2(v[2], v[3]), umma::pack_h2(v[4], v[5]),
-                             umma::pack_h2(v[6], v[7]));
+            if constexpr (SPLIT) {
+              umma::split_h2(v[0], v[1], val.x, vlo.x);
+              umma::split_h2(v[2], v[3], val.y, vlo.y);
+              umma::split_h2(v[4], v[5], val.z, vlo.z);
+              umma::split_h2(v[6], v[7], val.w, vlo.w);
+            } else {
+              val = make_uint4(umma::pack_h2(v[0], v[1]), umma::pack_h2(v[2], v[3]), umma::pack_h2(v[4], v[5]),
+                               umma::pack_h2(v[6], v[7]));
+            }
           }
           *reinterpret_cast<uint4*>(smem + c * C::LBO_I + pp * 16) = val;
+          if constexpr (SPLIT) *reinterpret_cast<uint4*>(smem + C::IMG_BYTES + c * C::LBO_I + pp * 16) = vlo;
         }
       }
       umma::fence_proxy_async();
@@ -407,12 +432,18 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
                   for (int i = 0; i < 16; ++i) { float x = v[g * 16 + i]; s += x; ss = fmaf(x, x, ss); }
                   st_sum[c0 / 16 + g] += s; st_sq[c0 / 16 + g] += ss;
                 }
-                __half* o = p.out + ((long long)sl * (C::WOUT * C::WOUT) + opix) * NREAL + c0;
+                if constexpr (SPLIT) {
+                  float* o = p.out32 + ((long long)sl * (C::WOUT * C::WOUT) + opix) * NREAL + c0;
 #pragma unroll
-                for (int i = 0; i < 32; i += 8)
-                  *reinterpret_cast<uint4*>(o + i) =
-                      make_uint4(umma::pack_h2(v[i], v[i + 1]), umma::pack_h2(v[i + 2], v[i + 3]),
-                                 umma::pack_h2(v[i + 4], v[i + 5]), umma::pack_h2(v[i + 6], v[i + 7]));
+                  for (int i = 0; i < 32; i += 4) st4(o + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+                } else {
+                  __half* o = p.out + ((long long)sl * (C::WOUT * C::WOUT) + opix) * NREAL + c0;
+#pragma unroll
+                  for (int i = 0; i < 32; i += 8)
+                    *reinterpret_cast<uint4*>(o + i) =
+                        make_uint4(umma::pack_h2(v[i], v[i + 1]), umma::pack_h2(v[i + 2], v[i + 3]),
+                                   umma::pack_h2(v[i + 4], v[i + 5]), umma::pack_h2(v[i + 6], v[i + 7]));
+                }
               }
             }
           }
@@ -476,9 +507,9 @@ static cudaError_t launch_gn_finalize(const float* stats, int nb, int cin, float
 
 // Additive map E [B][Wout*Wout][NREAL] -> accumulator-tile order of the consuming composed stage (see BandConvParams::emap):
 // rows that are halo columns or beyond the band are zero.
-template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD, int CTAS>
+template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD, int CTAS, bool SPLIT>
 __global__ void relayout_emap_kernel(const float* __restrict__ E, float* __restrict__ Et, int B) {
-  using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS>;
+  using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS, SPLIT>;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;          // one float4 each
   const long long total = (long long)B * C::NB * 4 * C::NTILES * (NREAL / 4) * 128;
   if (i >= total) return;
@@ -499,22 +530,22 @@ __global__ void relayout_emap_kernel(const float* __restrict__ E, float* __restr
   }
   st4(Et + i * 4, v);
 }
-template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD, int CTAS = 2>
+template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD, int CTAS = 2, bool SPLIT = false>
 static size_t emap_tiled_floats(int B) {
-  using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS>;
+  using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS, SPLIT>;
   return (size_t)B * C::NB * 4 * C::NTILES * NREAL * 128;
 }
-template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD, int CTAS = 2>
+template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD, int CTAS = 2, bool SPLIT = false>
 static cudaError_t launch_relayout_emap(const float* E, float* Et, int B, cudaStream_t st) {
-  const long long total = (long long)emap_tiled_floats<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS>(B) / 4;
-  relayout_emap_kernel<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(E, Et, B);
+  const long long total = (long long)emap_tiled_floats<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS, SPLIT>(B) / 4;
+  relayout_emap_kernel<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS, SPLIT><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(E, Et, B);
   return cudaGetLastError();
 }
 
-template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD, int CTAS = 2>
+template <int CIN, int NOUT, int NREAL, bool UPS, bool IN_F32, int WIN_, int BR, bool HEAD, int CTAS = 2, bool SPLIT = false>
 static cudaError_t launch_band(const BandConvParams& p, int num_sms, cudaStream_t st) {
-  using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS>;
-  auto kern = band_conv_kernel<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS>;
+  using C = BandCfg<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS, SPLIT>;
+  auto kern = band_conv_kernel<CIN, NOUT, NREAL, UPS, IN_F32, WIN_, BR, HEAD, CTAS, SPLIT>;
   {   // per-device function attribute: set on every launch (cheap), a process-wide flag would miss other devices
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) return e;
@@ -550,19 +581,25 @@ static cudaError_t launch_band(const BandConvParams& p, int num_sms, cudaStream_
 // weight preparation (runs once in catseg_finalize_params)
 
 // image[(k/8)*NOUT*8 + n*8 + k%8] = W3[n][ci0 + k][tap]   (n < nreal, else 0)
-__global__ void pack_tap_img_kernel(__half* dst, const float* W3, int Cin3, int ci0, int CIN, int NOUT, int nreal) {
+// nw = 1: one fp16 image per tap; nw = 2 (PRECISE): a hi and a lo image per tap, stored as consecutive pairs
+__device__ __forceinline__ void store_wimg(__half* dst, long long img, int per, int idx, float v, int nw) {
+  const __half h = __float2half_rn(v);
+  dst[img * nw * per + idx] = h;
+  if (nw == 2) dst[(img * 2 + 1) * per + idx] = __float2half_rn(v - __half2float(h));
+}
+__global__ void pack_tap_img_kernel(__half* dst, const float* W3, int Cin3, int ci0, int CIN, int NOUT, int nreal, int nw) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int per = NOUT * CIN;
   if (i >= 9 * per) return;
   int tap = i / per, r = i % per, n = r / CIN, k = r % CIN;
   float v = n < nreal ? W3[((long long)n * Cin3 + ci0 + k) * 9 + tap] : 0.0f;
-  dst[(long long)tap * per + (k >> 3) * NOUT * 8 + n * 8 + (k & 7)] = __float2half_rn(v);
+  store_wimg(dst, tap, per, (k >> 3) * NOUT * 8 + n * 8 + (k & 7), v, nw);
 }
 
 // composed ConvTranspose(k2,s2) o conv3x3:  image index (a*2+b)*4 + (u*2+v), element [co][ci]
 //   Wc = sum_{dy,dx -> (u,v)} sum_cu Wup[ci][cu][a'][b'] * W3[co][cu][dy+1][dx+1]
 __global__ void compose_up_img_kernel(__half* dst, const float* Wup, const float* W3, int Ci, int Cup, int Cin3,
-                                      int Co) {
+                                      int Co, int nw) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int per = Co * Ci;
   if (i >= 16 * per) return;
@@ -579,7 +616,7 @@ __global__ void compose_up_img_kernel(__half* dst, const float* Wup, const float
         acc = fmaf(Wup[(((long long)ci * Cup + cu) * 2 + ay) * 2 + ax], W3[((long long)co * Cin3 + cu) * 9 + (dy + 1) * 3 + dx + 1], acc);
     }
   }
-  dst[(long long)img * per + (ci >> 3) * Co * 8 + co * 8 + (ci & 7)] = __float2half_rn(acc);
+  store_wimg(dst, img, per, (ci >> 3) * Co * 8 + co * 8 + (ci & 7), acc, nw);
 }
 
 // bias map of the composed conv: Bmap[Y][X][co] = sum_{valid dy,dx} sum_cu bup[cu] W3[co][cu][dy+1][dx+1]
@@ -604,13 +641,13 @@ __global__ void pack_guid_w_kernel(float* dst, const float* W3, int Cup, int Cg,
   dst[i] = W3[((long long)co * Cin3 + Cup + cg) * 9 + tap];
 }
 
-size_t decoder_fast_weight_bytes(const DecoderDims& d) {
+size_t decoder_fast_weight_bytes(const DecoderDims& d, int nw) {
   size_t b = 0;
-  b += (size_t)16 * d.D1 * d.C0 * 2;      // D1 composed
-  b += (size_t)9 * d.D1 * d.D1 * 2;       // D2
-  b += (size_t)16 * d.D2 * d.D1 * 2;      // D3 composed
-  b += (size_t)9 * d.D2 * d.D2 * 2;       // D4
-  b += (size_t)9 * 16 * d.D2 * 2;         // D5 head (N padded to 16)
+  b += (size_t)16 * d.D1 * d.C0 * 2 * nw;      // D1 composed
+  b += (size_t)9 * d.D1 * d.D1 * 2 * nw;       // D2
+  b += (size_t)16 * d.D2 * d.D1 * 2 * nw;      // D3 composed
+  b += (size_t)9 * d.D2 * d.D2 * 2 * nw;       // D4
+  b += (size_t)9 * 16 * d.D2 * 2 * nw;         // D5 head (N padded to 16)
   b += (size_t)(4 * d.H * d.W * d.D1 + 16 * d.H * d.W * d.D2) * 4;   // bias maps
   b += (size_t)(9 * d.G1 * d.D1 + 9 * d.G2 * d.D2) * 4;              // guidance conv weights
   return (b + 255) / 256 * 256;
@@ -618,27 +655,27 @@ size_t decoder_fast_weight_bytes(const DecoderDims& d) {
 
 cudaError_t decoder_fast_pack(const DecoderDims& d, const float* up1_w, const float* up1_b, const float* c1a_w,
                               const float* c1b_w, const float* up2_w, const float* up2_b, const float* c2a_w,
-                              const float* c2b_w, const float* head_w, void* storage, DecoderFastW* out,
+                              const float* c2b_w, const float* head_w, void* storage, DecoderFastW* out, int nw,
                               cudaStream_t st) {
   if (d.C0 != 128 || d.D1 != 64 || d.D2 != 32 || d.H != 24 || d.W != 24 || d.G1 % 4 || d.G2 % 4)
     return cudaErrorInvalidValue;      // the band kernels are instantiated for the shipped decoder geometry
   uint8_t* ptr = reinterpret_cast<uint8_t*>(storage);
   auto take = [&](size_t bytes) { uint8_t* r = ptr; ptr += bytes; return r; };
-  __half* w1 = reinterpret_cast<__half*>(take((size_t)16 * d.D1 * d.C0 * 2));
-  __half* w2 = reinterpret_cast<__half*>(take((size_t)9 * d.D1 * d.D1 * 2));
-  __half* w3 = reinterpret_cast<__half*>(take((size_t)16 * d.D2 * d.D1 * 2));
-  __half* w4 = reinterpret_cast<__half*>(take((size_t)9 * d.D2 * d.D2 * 2));
-  __half* w5 = reinterpret_cast<__half*>(take((size_t)9 * 16 * d.D2 * 2));
+  __half* w1 = reinterpret_cast<__half*>(take((size_t)16 * d.D1 * d.C0 * 2 * nw));
+  __half* w2 = reinterpret_cast<__half*>(take((size_t)9 * d.D1 * d.D1 * 2 * nw));
+  __half* w3 = reinterpret_cast<__half*>(take((size_t)16 * d.D2 * d.D1 * 2 * nw));
+  __half* w4 = reinterpret_cast<__half*>(take((size_t)9 * d.D2 * d.D2 * 2 * nw));
+  __half* w5 = reinterpret_cast<__half*>(take((size_t)9 * 16 * d.D2 * 2 * nw));
   float* bm1 = reinterpret_cast<float*>(take((size_t)4 * d.H * d.W * d.D1 * 4));
   float* bm2 = reinterpret_cast<float*>(take((size_t)16 * d.H * d.W * d.D2 * 4));
   float* wg1 = reinterpret_cast<float*>(take((size_t)9 * d.G1 * d.D1 * 4));
   float* wg2 = reinterpret_cast<float*>(take((size_t)9 * d.G2 * d.D2 * 4));
   auto blocks = [](long long n) { return (unsigned)((n + 255) / 256); };
-  compose_up_img_kernel<<<blocks(16LL * d.D1 * d.C0), 256, 0, st>>>(w1, up1_w, c1a_w, d.C0, d.U1, d.U1 + d.G1, d.D1);
-  pack_tap_img_kernel<<<blocks(9LL * d.D1 * d.D1), 256, 0, st>>>(w2, c1b_w, d.D1, 0, d.D1, d.D1, d.D1);
-  compose_up_img_kernel<<<blocks(16LL * d.D2 * d.D1), 256, 0, st>>>(w3, up2_w, c2a_w, d.D1, d.U2, d.U2 + d.G2, d.D2);
-  pack_tap_img_kernel<<<blocks(9LL * d.D2 * d.D2), 256, 0, st>>>(w4, c2b_w, d.D2, 0, d.D2, d.D2, d.D2);
-  pack_tap_img_kernel<<<blocks(9LL * 16 * d.D2), 256, 0, st>>>(w5, head_w, d.D2, 0, d.D2, 16, 1);
+  compose_up_img_kernel<<<blocks(16LL * d.D1 * d.C0), 256, 0, st>>>(w1, up1_w, c1a_w, d.C0, d.U1, d.U1 + d.G1, d.D1, nw);
+  pack_tap_img_kernel<<<blocks(9LL * d.D1 * d.D1), 256, 0, st>>>(w2, c1b_w, d.D1, 0, d.D1, d.D1, d.D1, nw);
+  compose_up_img_kernel<<<blocks(16LL * d.D2 * d.D1), 256, 0, st>>>(w3, up2_w, c2a_w, d.D1, d.U2, d.U2 + d.G2, d.D2, nw);
+  pack_tap_img_kernel<<<blocks(9LL * d.D2 * d.D2), 256, 0, st>>>(w4, c2b_w, d.D2, 0, d.D2, d.D2, d.D2, nw);
+  pack_tap_img_kernel<<<blocks(9LL * 16 * d.D2), 256, 0, st>>>(w5, head_w, d.D2, 0, d.D2, 16, 1, nw);
   up_bias_map_kernel<<<blocks(4LL * d.H * d.W * d.D1), 256, 0, st>>>(bm1, up1_b, c1a_w, d.U1, d.U1 + d.G1, d.D1, 2 * d.W);
   up_bias_map_kernel<<<blocks(16LL * d.H * d.W * d.D2), 256, 0, st>>>(bm2, up2_b, c2a_w, d.U2, d.U2 + d.G2, d.D2, 4 * d.W);
   pack_guid_w_kernel<<<blocks(9LL * d.G1 * d.D1), 256, 0, st>>>(wg1, c1a_w, d.U1, d.G1, d.U1 + d.G1, d.D1);
@@ -681,6 +718,12 @@ struct MapAddStore {
 #define D4W 32, 32, 32, false, false, 96, 12, false, 1
 #define D5N 32, 16, 16, false, false, 96, 6, true, 2
 #define D5W 32, 16, 16, false, false, 96, 12, true, 1
+// PRECISE shapes: one 17-warp CTA per SM, fp32 activations in and out
+#define D1S 128, 64, 64, true, true, 24, 6, false, 1, true
+#define D2S 64, 64, 64, false, true, 48, 6, false, 1, true
+#define D3S 64, 32, 32, true, true, 48, 4, false, 1, true
+#define D4S 32, 32, 32, false, true, 96, 6, false, 1, true
+#define D5S 32, 16, 16, false, true, 96, 6, true, 1, true
 static int dec_wide_mask() {
   static int m = -1;
   if (m < 0) {
@@ -699,6 +742,17 @@ size_t decoder_fast_scratch_bytes(const DecoderDims& d, int B, int chunk) {
   b += (size_t)chunk * (2 * 4 * hw * d.D1 + 2 * 16 * hw * d.D2) * 2;     // c1a c1b c2a c2b (fp16)
   b += (size_t)chunk * (4 * 4 + 8 * 4 + 12 * 2 + 16 * 2) * 2 * 4 + 4096; // band statistics
   b += (size_t)chunk * 64 * 2 * 4 + 256;                                  // GroupNorm (scale, shift) of the current producer
+  return (b + 255) / 256 * 256;
+}
+
+size_t decoder_split_scratch_bytes(const DecoderDims& d, int B, int chunk) {
+  size_t hw = (size_t)d.H * d.W;
+  size_t b = 0;
+  b += (size_t)B * (4 * hw * d.D1 + 16 * hw * d.D2) * 4;                 // E1, E2
+  b += (emap_tiled_floats<D1S>(B) + emap_tiled_floats<D3S>(B)) * 4 + 512;
+  b += (size_t)chunk * (2 * 4 * hw * d.D1 + 2 * 16 * hw * d.D2) * 4;     // c1a c1b c2a c2b (fp32)
+  b += (size_t)chunk * (4 * 4 + 8 * 4 + 12 * 2 + 16 * 2) * 2 * 4 + 4096; // band statistics (>= NB * G per stage)
+  b += (size_t)chunk * 64 * 2 * 4 + 256;
   return (b + 255) / 256 * 256;
 }
 
@@ -767,6 +821,64 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
     p.in = c2b; p.in_stats = s2b; p.nb_in = nb4; p.gamma = wx.gn2b_g; p.beta = wx.gn2b_b;
     p.wimg = w.w5; p.emap = nullptr; p.out = nullptr; p.out_stats = nullptr;
     if (wide & 16) CKF((launch_band<D5W>(p, num_sms, st))); else CKF((launch_band<D5N>(p, num_sms, st)));
+  }
+  if (launches) *launches += nl;
+  return cudaSuccess;
+}
+
+// PRECISE decoder: the same five band-convolution stages with hi + lo fp16 operand pairs and fp32 intermediates
+cudaError_t run_decoder_split(const float* X, const float* dg0, const float* dg1, const int32_t* classes,
+                              float* logits, int B, int T, int Te, const DecoderDims& d, const DecoderFastW& w,
+                              const DecoderW& wx, float head_bias, void* scratch, int chunk, int num_sms,
+                              int* launches, cudaStream_t st) {
+  const int hw = d.H * d.W;
+  int nl = 0;
+  uint8_t* ptr = reinterpret_cast<uint8_t*>(scratch);
+  auto take = [&](size_t bytes) { uint8_t* r = ptr; ptr += (bytes + 255) / 256 * 256; return r; };
+  float* E1 = reinterpret_cast<float*>(take((size_t)B * 4 * hw * d.D1 * 4));
+  float* E2 = reinterpret_cast<float*>(take((size_t)B * 16 * hw * d.D2 * 4));
+  float* E1t = reinterpret_cast<float*>(take(emap_tiled_floats<D1S>(B) * 4));
+  float* E2t = reinterpret_cast<float*>(take(emap_tiled_floats<D3S>(B) * 4));
+  float* c1a = reinterpret_cast<float*>(take((size_t)chunk * 4 * hw * d.D1 * 4));
+  float* c1b = reinterpret_cast<float*>(take((size_t)chunk * 4 * hw * d.D1 * 4));
+  float* c2a = reinterpret_cast<float*>(take((size_t)chunk * 16 * hw * d.D2 * 4));
+  float* c2b = reinterpret_cast<float*>(take((size_t)chunk * 16 * hw * d.D2 * 4));
+  float* s1a = reinterpret_cast<float*>(take((size_t)chunk * BandCfg<D1S>::NB * 4 * 2 * 4));
+  float* s1b = reinterpret_cast<float*>(take((size_t)chunk * BandCfg<D2S>::NB * 4 * 2 * 4));
+  float* s2a = reinterpret_cast<float*>(take((size_t)chunk * BandCfg<D3S>::NB * 2 * 2 * 4));
+  float* s2b = reinterpret_cast<float*>(take((size_t)chunk * BandCfg<D4S>::NB * 2 * 2 * 4));
+  float* gss = reinterpret_cast<float*>(take((size_t)chunk * 64 * 2 * 4));
+  {
+    GuidConvA a{dg0, d.G1, 2 * d.H, 2 * d.W};
+    CKF(launch_igemm(a, w.wg1, 0, 1, B * 4 * hw, d.D1, 9 * d.G1, MapAddStore{E1, w.bmap1, 4 * hw, d.D1}, st));
+    GuidConvA a2{dg1, d.G2, 4 * d.H, 4 * d.W};
+    CKF(launch_igemm(a2, w.wg2, 0, 1, B * 16 * hw, d.D2, 9 * d.G2, MapAddStore{E2, w.bmap2, 16 * hw, d.D2}, st));
+    CKF((launch_relayout_emap<D1S>(E1, E1t, B, st)));
+    CKF((launch_relayout_emap<D3S>(E2, E2t, B, st)));
+  }
+  const int nslice = B * Te;
+  for (int s0 = 0; s0 < nslice; s0 += chunk) {
+    const int n = nslice - s0 < chunk ? nslice - s0 : chunk;
+    BandConvParams p{};
+    p.Te = Te; p.slice0 = s0; p.nslice = n; p.T = T; p.classes = classes; p.logits = logits; p.head_bias = head_bias;
+    p.in = X + (long long)s0 * hw * d.C0; p.in_stats = nullptr; p.wimg = w.w1; p.emap = E1t; p.out32 = c1a; p.out_stats = s1a;
+    CKF((launch_band<D1S>(p, num_sms, st)));
+    CKF(launch_gn_finalize(s1a, BandCfg<D1S>::NB, 64, (float)(4 * hw * 16), wx.gn1a_g, wx.gn1a_b, gss, n, st));
+    p.in = c1a; p.in_stats = s1a; p.in_ss = gss; p.nb_in = BandCfg<D1S>::NB; p.in_count = (float)(4 * hw * 16); p.gamma = wx.gn1a_g; p.beta = wx.gn1a_b;
+    p.wimg = w.w2; p.emap = nullptr; p.out32 = c1b; p.out_stats = s1b;
+    CKF((launch_band<D2S>(p, num_sms, st)));
+    CKF(launch_gn_finalize(s1b, BandCfg<D2S>::NB, 64, (float)(4 * hw * 16), wx.gn1b_g, wx.gn1b_b, gss, n, st));
+    p.in = c1b; p.in_stats = s1b; p.nb_in = BandCfg<D2S>::NB; p.gamma = wx.gn1b_g; p.beta = wx.gn1b_b;
+    p.wimg = w.w3; p.emap = E2t; p.out32 = c2a; p.out_stats = s2a;
+    CKF((launch_band<D3S>(p, num_sms, st)));
+    CKF(launch_gn_finalize(s2a, BandCfg<D3S>::NB, 32, (float)(16 * hw * 16), wx.gn2a_g, wx.gn2a_b, gss, n, st));
+    p.in = c2a; p.in_stats = s2a; p.nb_in = BandCfg<D3S>::NB; p.in_count = (float)(16 * hw * 16); p.gamma = wx.gn2a_g; p.beta = wx.gn2a_b;
+    p.wimg = w.w4; p.emap = nullptr; p.out32 = c2b; p.out_stats = s2b;
+    CKF((launch_band<D4S>(p, num_sms, st)));
+    CKF(launch_gn_finalize(s2b, BandCfg<D4S>::NB, 32, (float)(16 * hw * 16), wx.gn2b_g, wx.gn2b_b, gss, n, st));
+    p.in = c2b; p.in_stats = s2b; p.nb_in = BandCfg<D4S>::NB; p.gamma = wx.gn2b_g; p.beta = wx.gn2b_b;
+    p.wimg = w.w5; p.emap = nullptr; p.out32 = nullptr; p.out_stats = nullptr;
+    CKF((launch_band<D5S>(p, num_sms, st)));
   }
   if (launches) *launches += nl;
   return cudaSuccess;

@@ -88,8 +88,8 @@ embed_fast_kernel(const float* __restrict__ corr, const int32_t* __restrict__ cl
 #pragma unroll
     for (int dy = 0; dy < 7; ++dy) {
       const uint64_t a = d_a + (uint64_t)(uint32_t)(EM_P0 + t * 128 + (dy - 3) * EM_PW);
-      umma::mma_bf16_ss(tm + acc * 128, a, d_b + (uint64_t)((2 * dy) * (EM_BIMG >> 4)), IDESC_128x128, dy > 0 ? 1u : 0u);
-      umma::mma_bf16_ss(tm + acc * 128, a, d_b + (uint64_t)((2 * dy + 1) * (EM_BIMG >> 4)), IDESC_128x128, 1u);
+      umma::mma_bf16_ss(tm + acc * 128, a, d_b + (uint64_t)((2 * dy) * (EM_BIMG >> 4)), IDESC_BF16_128x128, dy > 0 ? 1u : 0u);
+      umma::mma_bf16_ss(tm + acc * 128, a, d_b + (uint64_t)((2 * dy + 1) * (EM_BIMG >> 4)), IDESC_BF16_128x128, 1u);
     }
     umma::mma_commit(&bar_acc[acc]);
   };

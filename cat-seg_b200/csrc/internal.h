@@ -174,22 +174,40 @@ cudaError_t launch_class_apply_fast(const float* X, float* Xout, const __half* t
                                     const ClassFastW& w, int num_sms, cudaStream_t st);
 cudaError_t launch_pack_text_img(const float* tg, __half* timg, int B, int Te, cudaStream_t st);
 
+// ---------------------------------------------------------------- split_class.cu (PRECISE)
+struct ClassSplitW {
+  const __half* wimg_kv;   // 4 images in ring order: Wk (LN(x) part), Wk (guidance part), Wv hi, Wv lo
+  const __half* wimg_q;    // 2 images: Wq (LN(x) part), Wq (guidance part)
+  const float *ln1_g, *ln1_b, *bqk, *bv;
+};
+cudaError_t launch_class_state_split(const float* X, const __half* timg, float* state, int B, int Te, int npix, int S,
+                                     const ClassSplitW& w, int num_sms, cudaStream_t st);
+// X1[b][t][p] = x + attention (model.py:412); the MLP half follows in launch_mlp_split
+cudaError_t launch_class_apply_split(const float* X, float* X1, const __half* timg, const float* state, const float* pad_state,
+                                     int B, int Te, int npix, int S, const ClassSplitW& w, int num_sms, cudaStream_t st);
+
 // ---------------------------------------------------------------- fast_decoder.cu
 struct DecoderFastW {
   const __half *w1, *w2, *w3, *w4, *w5;   // UMMA weight images per stage (fast_decoder.cu)
   const float *bmap1, *bmap2;                    // [4HW][D1], [16HW][D2] transposed-conv bias maps
   const float *wg1, *wg2;                        // [9*G1][D1], [9*G2][D2] guidance conv weights (fp32 GEMM)
 };
-size_t decoder_fast_weight_bytes(const DecoderDims& d);
+size_t decoder_fast_weight_bytes(const DecoderDims& d, int nw);   // nw = 2: hi + lo images (PRECISE)
 cudaError_t decoder_fast_pack(const DecoderDims& d, const float* up1_w, const float* up1_b, const float* c1a_w,
                               const float* c1b_w, const float* up2_w, const float* up2_b, const float* c2a_w,
-                              const float* c2b_w, const float* head_w, void* storage, DecoderFastW* out,
+                              const float* c2b_w, const float* head_w, void* storage, DecoderFastW* out, int nw,
                               cudaStream_t st);
 size_t decoder_fast_scratch_bytes(const DecoderDims& d, int B, int chunk);
 cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1, const int32_t* classes,
                              float* logits, int B, int T, int Te, const DecoderDims& d, const DecoderFastW& w,
                              const DecoderW& wx, float head_bias, void* scratch, int chunk, int num_sms,
                              int* launches, cudaStream_t st);
+
+size_t decoder_split_scratch_bytes(const DecoderDims& d, int B, int chunk);
+cudaError_t run_decoder_split(const float* X, const float* dg0, const float* dg1, const int32_t* classes,
+                              float* logits, int B, int T, int Te, const DecoderDims& d, const DecoderFastW& w,
+                              const DecoderW& wx, float head_bias, void* scratch, int chunk, int num_sms,
+                              int* launches, cudaStream_t st);
 
 // ---------------------------------------------------------------- stitch.cu
 cudaError_t launch_stitch(const float* win_logits, int T, int S, int kernel, int stride, int out_res, int height,
