@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -26,7 +27,7 @@ thread_local std::string g_create_error;
 
 constexpr int kImplementedFast = CATSEG_FAST_SWIN_MLP | CATSEG_FAST_SWIN_ATTN | CATSEG_FAST_DECODER | CATSEG_FAST_CLASS | CATSEG_FAST_PREP;   // stages that have a tcgen05 kernel in this build
 // stages that have a PRECISE (hi + lo fp16 operand pair) kernel; the others run the EXACT kernel in that mode
-constexpr int kImplementedSplit = CATSEG_FAST_SWIN_MLP | CATSEG_FAST_CLASS | CATSEG_FAST_DECODER | CATSEG_FAST_PREP;
+constexpr int kImplementedSplit = CATSEG_FAST_SWIN_MLP | CATSEG_FAST_SWIN_ATTN | CATSEG_FAST_CLASS | CATSEG_FAST_DECODER | CATSEG_FAST_PREP;
 constexpr int kMaxProfForwards = 64;
 constexpr int kMaxSegments = 40;
 
@@ -46,6 +47,9 @@ struct catseg_handle {
   __half* wimg_split = nullptr;      // hi/lo fp16 weight images of the PRECISE kernels
   size_t wimg_split_elems = 0;
   std::vector<MlpSplitW> swin_mlp_split;   // [L*2]
+  std::vector<SwinAttn2W> swin_attn2;      // [L*2]  second-generation window attention (both modes)
+  __half* wimg_attn2 = nullptr;
+  int attn_version = 1;                    // 1: fast_swin_attn.cu (FAST only), 2: swin_attn2.cu
   std::vector<ClassSplitW> class_split;    // [L]
   std::vector<MlpSplitW> class_mlp_split;  // [L]
   int num_sms = 148;
@@ -206,6 +210,10 @@ extern "C" int catseg_create(const catseg_config* cfg, catseg_handle** out) {
   catseg_handle* h = new catseg_handle();
   h->cfg = c;
   h->split = (c.precision & CATSEG_PRECISE_SPLIT) != 0;
+  {
+    const char* e = getenv("CATSEG_ATTN_V");          // A/B switch for the FAST mode; the PRECISE mode only exists in version 2
+    h->attn_version = (h->split || (e && e[0] == '2')) ? 2 : 1;
+  }
   h->fast_mask = c.precision & (h->split ? kImplementedSplit : kImplementedFast);
   cudaGetDevice(&h->device);
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
@@ -231,6 +239,7 @@ extern "C" int catseg_destroy(catseg_handle* h) {
   if (!h) return CATSEG_OK;
   for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
   if (h->wimg_split) cudaFree(h->wimg_split);
+  if (h->wimg_attn2) cudaFree(h->wimg_attn2);
   if (h->raw) cudaFree(h->raw);
   if (h->packed) cudaFree(h->packed);
   if (h->wimg) cudaFree(h->wimg);
@@ -522,12 +531,29 @@ extern "C" int catseg_finalize_params(catseg_handle* h, catseg_stream stream) {
         h->swin_attn_fast[l * 2 + k] = SwinAttnFastW{aimg, sw.ln1_g, sw.ln1_b, sw.bv, sw.bproj};
       }
   }
+  if ((h->fast_mask & CATSEG_FAST_SWIN_ATTN) && h->attn_version == 2) {
+    const int L = h->cfg.num_layers, ag = h->cfg.appearance_guidance_proj_dim;
+    if (!h->wimg_attn2) CUDA_OK(h, cudaMalloc(&h->wimg_attn2, (size_t)L * 2 * kSwinAttn2Halfs * sizeof(__half)));
+    h->swin_attn2.assign(L * 2, SwinAttn2W{});
+    char b[160];
+    for (int l = 0; l < L; ++l)
+      for (int k = 0; k < 2; ++k) {
+        snprintf(b, sizeof(b), "layers.%d.swin_block.block_%d", l, k + 1);
+        std::string q(b);
+        __half* img = h->wimg_attn2 + (size_t)(l * 2 + k) * kSwinAttn2Halfs;
+        CUDA_OK(h, pack_swin_attn2(img, raw_of(h, q + ".attn.q.weight"), raw_of(h, q + ".attn.k.weight"),
+                                   raw_of(h, q + ".attn.v.weight"), raw_of(h, q + ".attn.proj.weight"), 128 + ag, st));
+        const SwinBlockW& sw = h->swin[l * 2 + k];
+        h->swin_attn2[l * 2 + k] = SwinAttn2W{img, sw.ln1_g, sw.ln1_b, sw.bv, sw.bproj};
+      }
+  }
   if (h->split && h->fast_mask) {
     const int L = h->cfg.num_layers;
     const size_t kImg = 128 * 128;
     const size_t need = (size_t)L * 2 * 16 * kImg + (size_t)L * 22 * kImg;
     if (!h->wimg_split || h->wimg_split_elems < need) {
       if (h->wimg_split) cudaFree(h->wimg_split);
+  if (h->wimg_attn2) cudaFree(h->wimg_attn2);
       h->wimg_split = nullptr;
       CUDA_OK(h, cudaMalloc(&h->wimg_split, need * sizeof(__half)));
       h->wimg_split_elems = need;
@@ -674,7 +700,9 @@ Plan make_plan(const catseg_handle* h, int B, int T) {
   p.app_g = take((size_t)B * p.HW * 128);
   p.app_gn = take((size_t)B * p.HW * 128);
   p.ag_qk = take((size_t)p.L * 2 * B * p.HW * 256);
-  p.agw = (h->fast_mask & CATSEG_FAST_SWIN_ATTN) ? take((size_t)p.L * 2 * B * 16 * 144 * 64 / 2) : 0;   // bf16 window tiles
+  // guidance terms in window order: version 1 = fp16 tiles [B][4][4 heads][144][64], version 2 = fp32 [B][4][256][144]
+  p.agw = (h->fast_mask & CATSEG_FAST_SWIN_ATTN) ? take(h->attn_version == 2 ? (size_t)p.L * 2 * B * 4 * 256 * 144
+                                                                               : (size_t)p.L * 2 * B * 16 * 144 * 64 / 2) : 0;
   p.dg0 = take((size_t)B * 4 * p.HW * p.dd.G1);
   p.dg1 = take((size_t)B * 16 * p.HW * p.dd.G2);
   p.X = take((size_t)nslice * p.HW * 128);
@@ -857,7 +885,11 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
       const float* agk = ws + p.ag_qk + (size_t)(l * 2 + k) * B * p.HW * 256;
       const int shift = k == 0 ? 0 : c.window_size / 2;
       seg.begin(CATSEG_STAGE_SWIN);
-      if (attn_fast) {
+      if (attn_fast && h->attn_version == 2) {
+        float* agT = ws + p.agw + (size_t)(l * 2 + k) * B * 4 * 256 * 144;
+        RUN(launch_pack_ag_windows_T(agk, agT, B, shift, st));
+        RUN(launch_swin_attn2(X, agT, nslice, Te, shift, h->swin_attn2[l * 2 + k], h->split, h->num_sms, st));
+      } else if (attn_fast) {
         __half* agw = reinterpret_cast<__half*>(ws + p.agw) + (size_t)(l * 2 + k) * B * 16 * 144 * 64;
         RUN(launch_pack_ag_windows(agk, agw, B, shift, st));
         RUN(launch_swin_attn_fast(X, agw, nslice, Te, shift, h->swin_attn_fast[l * 2 + k], h->num_sms, st));

@@ -57,6 +57,14 @@ struct SwinAttnFastW {
   const float *ln_g, *ln_b, *bv, *bproj;
 };
 
+// Second-generation window attention (swin_attn2.cu), FAST and PRECISE: fp16 images Wq | Wk | Wv hi | Wv lo (4 x 32 KiB),
+// then per head the proj slice hi | lo (4 x 16 KiB).
+struct SwinAttn2W {
+  const __half* wimg;
+  const float *ln_g, *ln_b, *bv, *bproj;
+};
+constexpr size_t kSwinAttn2Halfs = 4 * 128 * 128 + 4 * 8192;
+
 constexpr int kStateFloats = 4 * 32 * 32 + 128;   // per (image, pixel): KV[4][32][32] then Ksum[128]
 
 // ---------------------------------------------------------------- prep.cu
@@ -121,6 +129,14 @@ cudaError_t launch_swin_attn_fast(float* X, const __half* agw, int nslice, int T
 cudaError_t launch_pack_ag_windows(const float* ag_qk, __half* out, int B, int shift, cudaStream_t st);
 cudaError_t launch_pack_qkv_head_img(__half* dst, const float* Wq, const float* Wk, const float* Wv, int ldqk,
                                      int h, cudaStream_t st);
+
+// ---------------------------------------------------------------- swin_attn2.cu
+// agT: fp32 guidance terms [B][4 windows][256 features][144 tok] of this block (launch_pack_ag_windows_T, same shift)
+cudaError_t launch_swin_attn2(float* X, const float* agT, int nslice, int Te, int shift, const SwinAttn2W& w, bool split,
+                              int num_sms, cudaStream_t st);
+cudaError_t launch_pack_ag_windows_T(const float* ag_qk, float* out, int B, int shift, cudaStream_t st);
+cudaError_t pack_swin_attn2(__half* dst, const float* Wq, const float* Wk, const float* Wv, const float* Wp, int ldqk,
+                            cudaStream_t st);
 
 // ---------------------------------------------------------------- class_exact.cu
 cudaError_t launch_class_pad_state(const ClassLayerW& w, int Tg, float* pad_state, int n_pad, int S,
