@@ -553,7 +553,6 @@ extern "C" int catseg_finalize_params(catseg_handle* h, catseg_stream stream) {
     const size_t need = (size_t)L * 2 * 16 * kImg + (size_t)L * 22 * kImg;
     if (!h->wimg_split || h->wimg_split_elems < need) {
       if (h->wimg_split) cudaFree(h->wimg_split);
-  if (h->wimg_attn2) cudaFree(h->wimg_attn2);
       h->wimg_split = nullptr;
       CUDA_OK(h, cudaMalloc(&h->wimg_split, need * sizeof(__half)));
       h->wimg_split_elems = need;
@@ -896,7 +895,8 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
       }
       else RUN(launch_swin_block_exact(X, agk, nslice, Te, shift, h->swin[l * 2 + k], mlp_fast ? 0 : 1, st));
       seg.end();
-      if (mlp_fast) {
+      static const bool dbg_skip_mlp = getenv("CATSEG_DBG_SKIP_MLP") != nullptr;
+      if (mlp_fast && !dbg_skip_mlp) {
         seg.begin(CATSEG_STAGE_SWIN_MLP);
         if (h->split) RUN(launch_mlp_split(X, nullptr, X, (long long)nslice * p.HW, h->swin_mlp_split[l * 2 + k], 0, h->num_sms, st));
         else RUN(launch_mlp_fast(X, (long long)nslice * p.HW, h->swin_mlp_fast[l * 2 + k], 0, h->num_sms, st));

@@ -59,7 +59,7 @@ constexpr uint32_t IDESC_PV = umma::make_idesc_f16(128, 32, 0, 0);      // O = P
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(A2_THREADS, 1)
-swin_attn2_kernel(float* __restrict__ X, const float* __restrict__ agT, int nwin_total, int Te, int shift, SwinAttn2W w) {
+swin_attn2_kernel(float* __restrict__ X, const float* __restrict__ agT, int nwin_total, int Te, int shift, SwinAttn2W w, int dbgmask) {
   extern __shared__ __align__(1024) uint8_t smem[];
   int* tokpix = reinterpret_cast<int*>(smem + SM_MISC);
   float* red = reinterpret_cast<float*>(tokpix + 144);        // row max per key quarter [4][144]
@@ -191,8 +191,8 @@ swin_attn2_kernel(float* __restrict__ X, const float* __restrict__ agT, int nwin
       if (umma::elect_one()) {
         issue_gemm_k128_desc(tm + TM_VT, d_wvh, LBO_W, d_xh, LBO_X, IDESC_T, false);
         if (SPLIT) {
-          issue_gemm_k128_desc(tm + TM_VT, d_wvh, LBO_W, d_xl, LBO_X, IDESC_T, true);
-          issue_gemm_k128_desc(tm + TM_VT, d_wvl, LBO_W, d_xh, LBO_X, IDESC_T, true);
+          if (!(dbgmask & 1)) issue_gemm_k128_desc(tm + TM_VT, d_wvh, LBO_W, d_xl, LBO_X, IDESC_T, true);
+          if (!(dbgmask & 2)) issue_gemm_k128_desc(tm + TM_VT, d_wvl, LBO_W, d_xh, LBO_X, IDESC_T, true);
         }
         umma::mma_commit(bar_a);
       }
@@ -394,7 +394,7 @@ swin_attn2_kernel(float* __restrict__ X, const float* __restrict__ agT, int nwin
             for (int k = 0; k < 9; ++k)
               umma::mma_f16_ss(tm + (mt ? TM_O1 : TM_O0), d_p + (uint64_t)((mt * 128 * 16 + k * 2 * LBO_P) >> 4),
                                vh + (uint64_t)((k * 1024) >> 4), IDESC_PV, k > 0);
-            if (SPLIT) {
+            if (SPLIT && !(dbgmask & 4)) {
 #pragma unroll
               for (int k = 0; k < 9; ++k)
                 umma::mma_f16_ss(tm + (mt ? TM_O1 : TM_O0), d_p + (uint64_t)((mt * 128 * 16 + k * 2 * LBO_P) >> 4),
@@ -481,10 +481,12 @@ swin_attn2_kernel(float* __restrict__ X, const float* __restrict__ agT, int nwin
 #pragma unroll
           for (int k = 0; k < 2; ++k)
             umma::mma_f16_ss(tm + TM_Y, d_wph + (uint64_t)(k * 2 * (LBO_W >> 4)), oh + (uint64_t)(k * 2 * (LBO_P >> 4)), IDESC_T, (h > 0 || k > 0) ? 1u : 0u);
-          if (SPLIT) {
+          if (SPLIT && !(dbgmask & 8)) {
 #pragma unroll
             for (int k = 0; k < 2; ++k)
               umma::mma_f16_ss(tm + TM_Y, d_wph + (uint64_t)(k * 2 * (LBO_W >> 4)), ol + (uint64_t)(k * 2 * (LBO_P >> 4)), IDESC_T, 1u);
+          }
+          if (SPLIT && !(dbgmask & 16)) {
 #pragma unroll
             for (int k = 0; k < 2; ++k)
               umma::mma_f16_ss(tm + TM_Y, d_wpl + (uint64_t)(k * 2 * (LBO_W >> 4)), oh + (uint64_t)(k * 2 * (LBO_P >> 4)), IDESC_T, 1u);
@@ -542,8 +544,14 @@ cudaError_t launch_swin_attn2(float* X, const float* agT, int nslice, int Te, in
   const int nwin = nslice * 4;
   const int grid = nwin < num_sms ? nwin : num_sms;
   if (grid <= 0) return cudaSuccess;
-  if (split) swin_attn2_kernel<true><<<grid, A2_THREADS, A2_SMEM, st>>>(X, agT, nwin, Te, shift, w);
-  else swin_attn2_kernel<false><<<grid, A2_THREADS, A2_SMEM, st>>>(X, agT, nwin, Te, shift, w);
+  static int dbgmask = -1;
+  if (dbgmask < 0) { const char* e2 = getenv("CATSEG_A2_DBG"); dbgmask = e2 ? atoi(e2) : 0; }
+  static int force = -1;
+  if (force < 0) { const char* e3 = getenv("CATSEG_A2_FORCE_SPLIT"); force = e3 ? atoi(e3) : 0; }
+  if (force == 1) split = true;
+  if (force == 2) split = false;
+  if (split) swin_attn2_kernel<true><<<grid, A2_THREADS, A2_SMEM, st>>>(X, agT, nwin, Te, shift, w, dbgmask);
+  else swin_attn2_kernel<false><<<grid, A2_THREADS, A2_SMEM, st>>>(X, agT, nwin, Te, shift, w, dbgmask);
   return cudaGetLastError();
 }
 
