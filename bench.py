@@ -1,12 +1,14 @@
 #!/usr/bin/env python
 """Benchmark of the CAT-Seg hot path (Aggregator.forward: cost volume -> logits) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4] [--precision precise]
 
-A step = one boundary call on one batch of synthetic inputs of the workload
-(default: BASELINE.json's headline config, ViT-L/14 A-847, 16 images of 336x336 per GPU -> cfg4).
-N > 1 (launched by torchrun): images are sharded over ranks (the reference's own data-parallel
-inference mode); no data-path collective, weak scaling.
+A step = one boundary call on one batch of synthetic inputs of the workload (default: BASELINE.json's headline
+config, ViT-L/14 A-847, 16 images of 336x336 per GPU -> cfg4) in the PRECISE precision: the tensor-core mode that
+meets north_star's >= 99.9 % raw argmax gate (the same run prints the parity block that shows it).
+N > 1 (launched by torchrun): `value` = images sharded over ranks (the reference's own data-parallel inference mode,
+SURVEY.md 8e(1); no data-path collective, weak scaling); the same line carries a `strong` record: the SAME 16 images on
+every rank with the kept classes sharded and the linear-attention state all-reduced (north_star's class split).
 Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for every field.
 """
 from __future__ import annotations
@@ -33,37 +35,50 @@ METRIC, UNIT = "vitl_a847_aggregator_images_per_sec", "images/s"
 
 
 # ----------------------------------------------------------------------------- work model
-def stage_flops(cfg, B, T):
-    """Reference-algorithm FLOPs (2 x MACs of model.py as written) per boundary call, per stage."""
+def stage_flops(cfg, B, T, executed=False):
+    """FLOPs (2 x MACs) per boundary call, per stage.  executed=False: the reference algorithm as written (model.py);
+    executed=True: what the kernels compute once the results-preserving algebra of SURVEY.md §7.2 is applied (guidance
+    half of q/k precomputed, padding classes folded into a constant, composed transposed conv): every product counted
+    ONCE, i.e. the hi/lo operand-pair products of the PRECISE mode are not credited."""
     Te = min(T, cfg.pad_len) if cfg.pad_len > 0 else T
     S = cfg.pad_len if (cfg.pad_len > 0 and Te < cfg.pad_len) else Te
     C, hw = cfg.text_guidance_dim, 576
     npix = hw // (cfg.pooling_size[0] * cfg.pooling_size[1])
     sl = B * Te
-    swin_attn = hw * (2 * 256 * 128 + 128 * 128 + 128 * 128) + 4 * 4 * 2 * 144 * 144 * 32   # q,k (K=256), v, proj, QK^T, PV
+    qk_in = 128 if executed else 256
+    swin_attn = hw * (2 * qk_in * 128 + 128 * 128 + 128 * 128) + 4 * 4 * 2 * 144 * 144 * 32   # q,k, v, proj, QK^T, PV
     swin_mlp = hw * 2 * 128 * 512
-    class_tok = 2 * 256 * 128 + 128 * 128 + 2 * 128 * 512 + 4 * (32 * 32 + 32 * 32 + 32)
-    dec = 48 * 48 * (96 * 128 + 9 * 64 * 128 + 9 * 64 * 64) + 96 * 96 * (48 * 64 + 9 * 32 * 64 + 9 * 32 * 32 + 9 * 32)
-    corr = B * T * cfg.prompt_channel * hw * C * (2 if T > Te else 1)
+    class_tok = 2 * qk_in * 128 + 128 * 128 + 2 * 128 * 512 + 4 * (32 * 32 + 32 * 32 + 32)
+    if executed:
+        dec = 48 * 48 * (4 * 128 * 64 + 9 * 64 * 64) + 96 * 96 * (4 * 64 * 32 + 9 * 32 * 32 + 9 * 32)
+    else:
+        dec = 48 * 48 * (96 * 128 + 9 * 64 * 128 + 9 * 64 * 64) + 96 * 96 * (48 * 64 + 9 * 32 * 64 + 9 * 32 * 32 + 9 * 32)
+    corr = B * T * cfg.prompt_channel * hw * C * (2 if (T > Te and not executed) else 1)
     prep = corr + B * (hw * 128 * C * 9 + 2304 * 32 * 256 * 9 + 9216 * 16 * 128 * 9) + sl * C * 128
     m = {
         "prep": prep, "embed": sl * hw * 128 * 49 * cfg.prompt_channel,
         "swin": sl * swin_attn * 2 * cfg.num_layers,
         "swin_mlp": sl * swin_mlp * 2 * cfg.num_layers,
-        "class": B * npix * S * class_tok * cfg.num_layers,
+        "class": B * npix * (Te if executed else S) * class_tok * cfg.num_layers,
         "decoder": sl * dec,
     }
     return {k: 2.0 * v for k, v in m.items()}
 
 
-# (kernel name, launches per boundary call) of the stages whose time is one kernel type launched repeatedly
-STAGE_KERNELS = {
-    "swin": ("swin_attn_fast_kernel", lambda cfg: 2 * cfg.num_layers),
-    "swin_mlp": ("mlp_fast_kernel<GELU>", lambda cfg: 2 * cfg.num_layers),
-    "class": ("class_state_fast_kernel + class_apply_fast_kernel", lambda cfg: cfg.num_layers),
-    "decoder": ("band_conv_kernel x5 (D1..D5)", lambda cfg: 1),
-    "prep": ("prep kernels", lambda cfg: 1), "embed": ("igemm_kernel<EmbedA>", lambda cfg: 1),
-}
+# tensor-pipe MACs ISSUED per window by swin_attn2_kernel (two query tiles of 128 rows, hi/lo products included)
+def attn_issued_flops(sl, L, split):
+    v = 3 if split else 1
+    per_win = 144 * 128 * 128 * (2 + v) + 4 * 256 * 144 * 32 * (1 + (2 if split else 1)) + 144 * 128 * 128 * v
+    return 2.0 * per_win * 4 * sl * 2 * L
+
+
+# (kernel name per precision, launches per boundary call) of the stages whose time is one kernel launched repeatedly
+def stage_kernel(stage, precision, attn_v2):
+    fast = not precision.startswith("precise")
+    return {
+        "swin": ("swin_attn_fast_kernel" if (fast and not attn_v2) else "swin_attn2_kernel<%d>" % (0 if fast else 1)),
+        "swin_mlp": "mlp_fast_kernel<GELU>" if fast else "mlp_split_kernel<GELU>",
+    }[stage]
 
 
 def ncu_traffic(kernel, workload):
@@ -129,19 +144,50 @@ def get_cfg(name):
     return (vitb() if w["model"] == "vitb" else vitl()), w["B"], w["T"]
 
 
-def cpu_port_rate(cfg, T, seed=0, repeats=1):
-    """The oracle (CPU fp32 port of the reference) on ONE image of the workload, all host threads."""
-    from oracle.aggregator_oracle import aggregator_forward
+def describe(name, cfg, B, T, sliding):
+    return (f"{name}: CAT-Seg {'ViT-L/14 336x336' if cfg.text_guidance_dim == 768 else 'ViT-B/16 384x384'}, T={T} classes "
+            f"(Te={min(T, cfg.pad_len)} kept), B={B} {'sliding windows of one 640x640 image' if sliding else 'images'}/GPU, "
+            f"L=2, pool [1,1], P=1")
+
+
+def cpu_reference(cfg, T, seed=0, B=1):
+    """The reference's own Aggregator (unmodified model.py from oracle/_ref or /root/reference; kind "reference") -- or,
+    if that file is absent, the oracle port (kind "port") -- on B images of the workload with all host threads.
+    Returns (logits, seconds, cores, kind, state_dict, inputs)."""
+    from oracle import ref_loader
     torch.set_num_threads(os.cpu_count() or 1)
     sd = make_state_dict(cfg, seed)
-    img, text, g = make_inputs(cfg, 1, T, seed)
-    ts = []
-    for _ in range(repeats):
+    img, text, g = make_inputs(cfg, B, T, seed)
+    if ref_loader.reference_available():
+        ref = ref_loader.build_reference_aggregator(cfg.ctor_kwargs(), sd)
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            y = ref(img, text, g)
+            dt = time.perf_counter() - t0
+        kind = "reference"
+    else:
+        from oracle.aggregator_oracle import aggregator_forward
         t0 = time.perf_counter()
-        aggregator_forward(sd, cfg.oracle_cfg(), img, text, g)
-        ts.append(time.perf_counter() - t0)
-    t = statistics.median(ts)
-    return 1.0 / t, t, torch.get_num_threads()
+        y = aggregator_forward(sd, cfg.oracle_cfg(), img, text, g)
+        dt = time.perf_counter() - t0
+        kind = "port"
+    return y, dt, torch.get_num_threads(), kind, sd, (img, text, g)
+
+
+def parity_block(y, ref):
+    """§8d "parity report, same run": GPU logits vs the CPU reference on identical inputs."""
+    y, ref = y.float().cpu(), ref.float()
+    mask_equal = bool(((y == -100.0) == (ref == -100.0)).all())
+    kept = ref != -100.0
+    err = (y[kept] - ref[kept]).abs().max().item()
+    rl2 = ((y[kept].double() - ref[kept].double()).norm() / ref[kept].double().norm()).item()
+    a, r = y.argmax(dim=1), ref.argmax(dim=1)
+    raw = (a == r).float().mean().item()
+    top2 = ref.topk(2, dim=1)[0]
+    safe = (top2[:, 0] - top2[:, 1]) > 2 * err
+    filt = (a == r)[safe].float().mean().item() if bool(safe.any()) else None
+    return {"max_abs": err, "rel_l2": rl2, "mask_equal": mask_equal, "argmax_raw": raw, "argmax_filtered": filt,
+            "safe_frac": safe.float().mean().item(), "pixels": int(a.numel())}
 
 
 def dist_env():
@@ -150,31 +196,30 @@ def dist_env():
 
 # ----------------------------------------------------------------------------- reference arm
 def run_reference(args):
+    """The reference's own CPU implementation of the path (oracle/_ref/model.py = the unmodified file, imported through
+    oracle/ref_loader.py), all host threads.  One step = ONE image of the workload (not the repo arm's 16): a 16-image
+    CPU step takes ~30-150 s, so K steps would not end "within a few minutes"; throughput is per image either way."""
     rank, _, world = dist_env()
     if rank != 0:
         return
     cfg, B, T = get_cfg(args.workload)
-    steps, warm = args.steps, args.warmup
-    from oracle.aggregator_oracle import aggregator_forward
-    torch.set_num_threads(os.cpu_count() or 1)
-    sd = make_state_dict(cfg, 0)
-    img, text, g = make_inputs(cfg, 1, T, 0)
-    for _ in range(min(warm, 1)):
-        aggregator_forward(sd, cfg.oracle_cfg(), img, text, g)
-    ts = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        aggregator_forward(sd, cfg.oracle_cfg(), img, text, g)
-        ts.append(time.perf_counter() - t0)
+    steps, warm = args.steps, min(args.warmup, 1)
+    ts, kind, cores = [], "port", 0
+    for i in range(warm + steps):
+        _, dt, cores, kind, _, _ = cpu_reference(cfg, T, seed=0, B=1)
+        if i >= warm:
+            ts.append(dt)
     tot = sum(ts)
     val = steps / tot
-    sample = f"1 image of {args.workload} (B=1,T={T}) per step; CPU fp32 oracle port of model.py:683-725"
+    sample = (f"1 image of {args.workload} (B=1, T={T}) per step; "
+              + ("the reference's unmodified cat_seg/modeling/transformer/model.py Aggregator (oracle/_ref), torch CPU fp32"
+                 if kind == "reference" else "CPU fp32 oracle port of model.py:683-725 (oracle/_ref/model.py absent)"))
     out = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(warm, 1), "ms_per_step": 1e3 * tot / steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": 1e3 * tot / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: CAT-Seg ViT-L/14 A-847, T={T}, pool [1,1]", "sample": sample},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "config": {"workload": describe(args.workload, cfg, 1, T, False), "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -182,6 +227,137 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- our arm
+class Arm:
+    """One (workload, precision, parallel mode) measurement on this rank's GPU."""
+
+    def __init__(self, workload, precision, dev, rank, world, class_par=False, batch=0, cuda_graph=False):
+        from cat_seg_b200.aggregator import Aggregator
+        self.workload, self.precision, self.dev, self.rank, self.world = workload, precision, dev, rank, world
+        self.cfg, self.B, self.T = get_cfg(workload)
+        if batch:
+            self.B = batch
+        self.class_par = class_par and world > 1
+        self.sliding = workload == "cfg5"           # 5 windows of one 640x640 image + stitch/argmax per step
+        self.sd = make_state_dict(self.cfg, 0)
+        self.model = Aggregator(**self.cfg.ctor_kwargs(), precision=precision)
+        self.model.load_state_dict(self.sd, strict=False)
+        self.model = self.model.to(dev)
+        img, text, g = make_inputs(self.cfg, self.B, self.T, seed=0 if self.class_par else rank)
+        self.host = [t.pin_memory() for t in (img, text, g[1], g[2])]
+        self.d_img, self.d_text, self.d_g1, self.d_g2 = [t.to(dev) for t in self.host]
+        self.graph_run = None
+        self.cuda_graph = cuda_graph and not self.class_par
+
+    def step(self):
+        from cat_seg_b200 import sliding_window as sw
+        a = (self.d_img, self.d_text, [self.d_img, self.d_g1, self.d_g2])
+        if self.graph_run is not None:
+            y = self.graph_run(*a)
+        elif self.class_par:
+            y = self.model.forward_class_sharded(*a)
+        else:
+            y = self.model(*a)
+        if self.sliding:
+            return sw.stitch(y, 640, 640, want_probs=False, want_labels=True)[1]
+        return y
+
+    def barrier(self):
+        torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(self.dev)
+
+    def resident(self, steps, warmup, sample_clocks=False):
+        """Inputs resident in HBM: CUDA events around exactly `steps` steps, max over ranks."""
+        from cat_seg_b200 import distributed as cdist
+        if self.cuda_graph:
+            from cat_seg_b200.host_pipeline import GraphRunner
+            self.graph_run = GraphRunner(self.model, self.d_img, self.d_text, [self.d_img, self.d_g1, self.d_g2])
+        for _ in range(warmup):
+            self.step()
+        self.barrier()
+        self.model.set_profiling(self.graph_run is None)
+        self.model.stage_times(reset=True)
+        sampler = ClockSampler(self.dev.index or 0)
+        if sample_clocks and self.rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for _ in range(steps):
+            self.step()
+        e1.record()
+        self.barrier()
+        clocks = sampler.stop() if (sample_clocks and self.rank == 0) else None
+        ms = e0.elapsed_time(e1)
+        stage_ms, calls = self.model.stage_times(reset=True)
+        self.model.set_profiling(False)
+        launches = self.model.last_launch_count() * steps
+        ms = cdist.max_over_ranks([ms], self.dev)[0]
+        return {"ms": ms, "stage_ms": stage_ms, "calls": calls, "launches": launches, "clocks": clocks}
+
+    def e2e(self, steps, warmup, full_logits=False):
+        """End to end through the public API: every step uploads ITS OWN pinned host inputs (copy stream, two device
+        slots: the upload of step i+1 overlaps the kernels of step i, as a prefetching data loader does), runs the boundary
+        call and reads the result back to pinned host memory: per-image argmax labels (what the evaluator consumes,
+        train_net.py:58) or, with full_logits, the whole [B,T,96,96] fp32 logits tensor.  The host waits for the result
+        of step i-1 while step i is queued; results alternate between two pinned buffers."""
+        from cat_seg_b200 import distributed as cdist
+        from cat_seg_b200 import sliding_window as sw
+        from cat_seg_b200.host_pipeline import HostPipeline
+        B, T, dev = self.B, self.T, self.dev
+        if self.sliding:
+            shape, dt = (640 * 640,), torch.int32
+        elif full_logits:
+            shape, dt = (B, T, 96 * 96), torch.float32
+        else:
+            shape, dt = (B, 96 * 96), torch.int32
+        out_host = [torch.empty(shape, dtype=dt).pin_memory() for _ in range(2)]
+        pipe = HostPipeline(self.model, dev)
+        done = [torch.cuda.Event() for _ in range(2)]
+
+        def run(n):
+            ticket = pipe.upload(self.host)
+            for i in range(n):
+                nxt = pipe.upload(self.host) if i + 1 < n else None
+                if self.class_par:
+                    a_, b_, c_, d_ = pipe.slots[ticket]
+                    torch.cuda.current_stream(dev).wait_event(pipe.uploaded[ticket])
+                    yy = self.model.forward_class_sharded(a_, b_, [a_, c_, d_])
+                    ev_ = torch.cuda.Event(); ev_.record(); pipe.consumed[ticket] = ev_
+                else:
+                    yy = pipe.run(ticket)
+                if self.sliding:
+                    out_host[i & 1].copy_(sw.stitch(yy, 640, 640, want_probs=False, want_labels=True)[1].view(-1), non_blocking=True)
+                elif full_logits:
+                    out_host[i & 1].copy_(yy.view(B, T, -1), non_blocking=True)
+                else:
+                    out_host[i & 1].copy_(sw.argmax_batched(yy.view(B, T, -1)), non_blocking=True)
+                done[i & 1].record()
+                if i > 0:
+                    done[(i - 1) & 1].synchronize()          # the caller consumes the previous step's result
+                ticket = nxt
+            done[(n - 1) & 1].synchronize()
+
+        run(max(1, min(warmup, 2)))
+        self.barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        run(steps)
+        f1.record()
+        self.barrier()
+        ms = cdist.max_over_ranks([f0.elapsed_time(f1)], dev)[0]
+        h2d = sum(t.numel() * t.element_size() for t in self.host)
+        return {"ms": ms, "h2d": h2d, "d2h": out_host[0].numel() * out_host[0].element_size()}
+
+    def units(self):
+        return 1 if self.sliding else self.B
+
+    def forward_one(self, inputs):
+        img, text, g = inputs
+        return self.model(img.to(self.dev), text.to(self.dev), [x.to(self.dev) for x in g])
+
+
 def run_ours(args):
     rank, local, world = dist_env()
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
@@ -189,160 +365,139 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     from cat_seg_b200 import distributed as cdist
     cdist.init_from_env("nccl", dev)
-    from cat_seg_b200.aggregator import Aggregator
-    from cat_seg_b200 import sliding_window as sw
-    from cat_seg_b200.host_pipeline import HostPipeline
-
-    cfg, B, T = get_cfg(args.workload)
-    if args.batch:
-        B = args.batch
-    sd = make_state_dict(cfg, 0)
-    model = Aggregator(**cfg.ctor_kwargs(), precision=args.precision)
-    model.load_state_dict(sd, strict=False)
-    model = model.to(dev)
+    steps, warm = args.steps, args.warmup
     class_par = args.parallel == "class" and world > 1
-    img, text, g = make_inputs(cfg, B, T, seed=0 if class_par else rank)
-    host = [t.pin_memory() for t in (img, text, g[1], g[2])]
-    d_img, d_text, d_g1, d_g2 = [t.to(dev) for t in host]
 
-    sliding = args.workload == "cfg5"           # 5 windows of one 640x640 image + stitch/argmax per step
+    arm = Arm(args.workload, args.precision, dev, rank, world, class_par=class_par, batch=args.batch, cuda_graph=args.cuda_graph)
+    cfg, B, T = arm.cfg, arm.B, arm.T
+    res = arm.resident(steps, warm, sample_clocks=True)
+    e2e = arm.e2e(steps, warm)
+    e2e_logits = arm.e2e(max(2, steps // 2), 1, full_logits=True) if (not arm.sliding and not args.no_extra) else None
+    nrep = 1 if class_par else world                # class-sharded: all ranks work on the same images
+    value = nrep * arm.units() * steps / (res["ms"] / 1e3)
+    e2e_value = nrep * arm.units() * steps / (e2e["ms"] / 1e3)
 
-    graph_run = None
-
-    def step_resident():
-        if graph_run is not None:
-            y = graph_run(d_img, d_text, [d_img, d_g1, d_g2])
-            return sw.stitch(y, 640, 640, want_probs=False, want_labels=True)[1] if sliding else y
-        if class_par:
-            y = model.forward_class_sharded(d_img, d_text, [d_img, d_g1, d_g2])
-        else:
-            y = model(d_img, d_text, [d_img, d_g1, d_g2])
-        if sliding:
-            return sw.stitch(y, 640, 640, want_probs=False, want_labels=True)[1]
-        return y
-
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize(dev)
-
-    if args.cuda_graph and not class_par:
-        from cat_seg_b200.host_pipeline import GraphRunner
-        graph_run = GraphRunner(model, d_img, d_text, [d_img, d_g1, d_g2])
-    for _ in range(args.warmup):
-        y = step_resident()
-    barrier()
-    model.set_profiling(graph_run is None)
-    model.stage_times(reset=True)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        y = step_resident()
-    e1.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = e0.elapsed_time(e1)
-    stage_ms, calls = model.stage_times(reset=True)
-    model.set_profiling(False)
-    launches = model.last_launch_count() * args.steps
-
-    # ---- end to end: pinned host inputs -> device, boundary call, per-image argmax labels -> host
-    labels_host = (torch.empty(640 * 640, dtype=torch.int32) if sliding else torch.empty(B, 96 * 96, dtype=torch.int32)).pin_memory()
-
-    # Each step uploads ITS OWN inputs (K uploads inside the timed region); the upload of step i+1 is issued before
-    # step i computes (copy stream, two device slots), and the host waits for the labels of step i-1 while step i
-    # is queued, so the PCIe copies overlap the kernels the way a prefetching data loader does.
-    pipe = HostPipeline(model, dev)
-    done = [torch.cuda.Event() for _ in range(2)]
-
-    def e2e_run(nsteps):
-        ticket = pipe.upload(host)
-        for i in range(nsteps):
-            nxt = pipe.upload(host) if i + 1 < nsteps else None
-            if class_par:
-                a_, b_, c_, d_ = pipe.slots[ticket]
-                torch.cuda.current_stream(dev).wait_event(pipe.uploaded[ticket])
-                yy = model.forward_class_sharded(a_, b_, [a_, c_, d_])
-                ev_ = torch.cuda.Event(); ev_.record(); pipe.consumed[ticket] = ev_
-            else:
-                yy = pipe.run(ticket)
-            if sliding:
-                labels_host.copy_(sw.stitch(yy, 640, 640, want_probs=False, want_labels=True)[1].view(-1), non_blocking=True)
-            else:
-                labels_host.copy_(sw.argmax_batched(yy.view(B, T, -1)), non_blocking=True)
-            done[i & 1].record()
-            if i > 0:
-                done[(i - 1) & 1].synchronize()          # the caller consumes the previous step's labels
-            ticket = nxt
-        done[(nsteps - 1) & 1].synchronize()
-
-    e2e_run(max(1, min(args.warmup, 2)))
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    e2e_run(args.steps)
-    f1.record()
-    barrier()
-    ms_e2e = f0.elapsed_time(f1)
-
-    ms, ms_e2e = cdist.max_over_ranks([ms, ms_e2e], dev)
+    # ---- strong scaling of north_star's class split, same process, same images on every rank (N > 1 only)
+    strong = None
+    if world > 1 and not class_par and not arm.sliding and not args.no_extra:
+        sarm = Arm(args.workload, args.precision, dev, rank, world, class_par=True, batch=args.batch)
+        if sarm.model.kept_classes(T) % world == 0:
+            sres = sarm.resident(steps, warm)
+            se2e = sarm.e2e(steps, warm)
+            n1_ms = res["ms"] / steps                # one rank, the same B images, no sharding: the weak run's step time
+            strong = {
+                "scaling": "strong", "value": sarm.units() * steps / (sres["ms"] / 1e3), "unit": UNIT,
+                "ms_per_step": sres["ms"] / steps, "n1_ms_per_step": n1_ms, "speedup_vs_1gpu": n1_ms / (sres["ms"] / steps),
+                "e2e_value": sarm.units() * steps / (se2e["ms"] / 1e3),
+                "stage_ms_per_step": {k: v / max(sres["calls"], 1) for k, v in sres["stage_ms"].items()},
+                "collective": "ncclAllReduce (sum) of the linear-attention state [B,576,4224] fp32 once per class layer, "
+                              "then one all-gather of the logit planes; the class stage time above includes the all-reduces",
+                "config": f"kept classes sharded over {world} ranks ({sarm.model.kept_classes(T) // world} per rank), the same "
+                          f"{B} images on every rank"}
+        del sarm
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
         return
 
-    units = 1 if sliding else B                 # images per step per rank
-    nrep = 1 if class_par else world                # class-sharded: all ranks work on the same images
-    value = nrep * units * args.steps / (ms / 1e3)
-    e2e_value = nrep * units * args.steps / (ms_e2e / 1e3)
     pk = peaks()
-    fl = stage_flops(cfg, B, T)
+    stage_ms, calls = res["stage_ms"], res["calls"]
+    split = args.precision.startswith("precise")
+    attn_v2 = split or os.environ.get("CATSEG_ATTN_V", "1") == "2"
+    fl_ref = stage_flops(cfg, B, T)
+    fl_exe = stage_flops(cfg, B, T, executed=True)
     if class_par:                                   # each rank executes 1/world of the per-(image, class) work
-        fl = {k: (v if k == "prep" else v / world) for k, v in fl.items()}
+        fl_ref = {k: (v if k == "prep" else v / world) for k, v in fl_ref.items()}
+        fl_exe = {k: (v if k == "prep" else v / world) for k, v in fl_exe.items()}
     if stage_ms.get("swin_mlp", 0.0) == 0.0:      # exact path: the FFN half runs inside the Swin block kernel
-        fl["swin"] += fl["swin_mlp"]
-    # the dominant KERNEL: among the stages that are one kernel launched n times (the class and decoder stages are
-    # sequences of different kernels; each of those kernels is shorter than the window-attention kernel, see profiles/)
+        fl_ref["swin"] += fl_ref["swin_mlp"]; fl_exe["swin"] += fl_exe["swin_mlp"]
+    # the dominant KERNEL: among the stages that are one kernel launched 2L times (class and decoder stages are sequences
+    # of different, individually shorter kernels: profiles/)
     single = [k for k in ("swin", "swin_mlp") if stage_ms.get(k, 0.0) > 0.0]
     top = max(single, key=lambda k: stage_ms[k]) if single else max(stage_ms, key=lambda k: stage_ms[k])
-    kname, nl_fn = STAGE_KERNELS[top]
-    n_per_call = nl_fn(cfg)
+    n_per_call = 2 * cfg.num_layers
     per_launch_ms = stage_ms[top] / max(calls, 1) / n_per_call
-    achieved = fl[top] / n_per_call / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
+    kname = stage_kernel(top, args.precision, attn_v2) if top in ("swin", "swin_mlp") else top
+    exe_per_launch = fl_exe[top] / n_per_call
+    achieved = exe_per_launch / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
+    issued = None
+    if top == "swin" and attn_v2:
+        issued = attn_issued_flops(B * min(T, cfg.pad_len), cfg.num_layers, split) / n_per_call / (1 if not class_par else world)
+    elif top == "swin_mlp":
+        issued = exe_per_launch * (3 if split else 1)
+    tot_ms = res["ms"] / steps
     roof = {"bound": "tensor", "kernel": kname, "stage": top, "launches_per_step": n_per_call, "achieved": achieved,
             "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
             "traffic": ncu_traffic(kname, args.workload), "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json)",
-            "flops_per_launch": fl[top] / n_per_call, "flops_basis": "reference algorithm as written (SURVEY.md 6.2)",
+            "flops_per_launch": exe_per_launch,
+            "flops_basis": "EXECUTED algorithmic FLOPs per launch (SURVEY.md 8d): reference FLOPs minus the algebraically skipped "
+                           "guidance half of q/k; each product counted once (PRECISE issues up to 3 MMAs per product)",
+            "tensor_issued_tflops": (issued / (per_launch_ms * 1e-3) / 1e12) if issued else None,
+            "tensor_issued_frac": (issued / (per_launch_ms * 1e-3) / 1e12 / pk["tflops"]) if issued else None,
             "ms_per_launch": per_launch_ms,
             "stage_ms_per_step": {k: v / max(calls, 1) for k, v in stage_ms.items()},
-            "stage_tflops": {k: (fl[k] / (stage_ms[k] / max(calls, 1) * 1e-3) / 1e12 if stage_ms[k] > 0 else None)
-                             for k in stage_ms}}
-    cpu = None
+            "stage_tflops_executed": {k: (fl_exe[k] / (stage_ms[k] / max(calls, 1) * 1e-3) / 1e12 if stage_ms[k] > 0 else None)
+                                      for k in stage_ms},
+            "whole_step": {"reference_algorithm_tflops": sum(fl_ref.values()) / (tot_ms * 1e-3) / 1e12,
+                           "executed_tflops": sum(fl_exe.values()) / (tot_ms * 1e-3) / 1e12,
+                           "frac_of_peak_reference_flops": sum(fl_ref.values()) / (tot_ms * 1e-3) / 1e12 / pk["tflops"]}}
+
+    # ---- parity report + CPU baseline, same run: ONE image of the workload, GPU vs the reference's own Aggregator
+    cpu, parity, secondary, others = None, None, None, None
     if world == 1 and not args.no_cpu_baseline:
-        rate, sec, cores = cpu_port_rate(cfg, T)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"1 image of {args.workload} (B=1,T={T}), CPU fp32 oracle, {sec:.1f} s"}
-    h2d = sum(t.numel() * t.element_size() for t in host)
+        ref_y, sec, cores, kind, _, inputs = cpu_reference(cfg, T, seed=0, B=1)
+        cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"1 image of {args.workload} (B=1,T={T}), {'unmodified reference model.py' if kind == 'reference' else 'CPU fp32 oracle port'}, "
+                         f"torch CPU fp32, {sec:.1f} s"}
+        parity = parity_block(arm.forward_one(inputs), ref_y)
+        parity["precision"] = args.precision
+        parity["against"] = kind
+        if not args.no_extra and not args.precision.startswith("fast"):
+            # the single-term FAST mode on the same workload (not the headline: it does not meet the argmax gate)
+            farm = Arm(args.workload, "fast", dev, rank, world, batch=args.batch)
+            fres = farm.resident(steps, warm)
+            secondary = {"precision": "fast", "value": farm.units() * steps / (fres["ms"] / 1e3), "unit": UNIT,
+                         "ms_per_step": fres["ms"] / steps,
+                         "stage_ms_per_step": {k: v / max(fres["calls"], 1) for k, v in fres["stage_ms"].items()},
+                         "parity": parity_block(farm.forward_one(inputs), ref_y) if not farm.sliding else None}
+            del farm
+    if world == 1 and not args.no_extra and args.workload == "cfg4" and not args.batch:
+        # the other BASELINE.json configs, same precision, device-resident value + parity on one image each
+        others = {}
+        for wl in ("cfg1", "cfg2", "cfg3", "cfg5"):
+            oarm = Arm(wl, args.precision, dev, rank, world)
+            ores = oarm.resident(max(3, steps // 2), 3)
+            rec = {"workload": describe(wl, oarm.cfg, oarm.B, oarm.T, oarm.sliding),
+                   "value": oarm.units() * max(3, steps // 2) / (ores["ms"] / 1e3), "unit": UNIT,
+                   "ms_per_step": ores["ms"] / max(3, steps // 2)}
+            if wl in ("cfg1", "cfg2") and not args.no_cpu_baseline:
+                ry, rsec, rc, rkind, _, rin = cpu_reference(oarm.cfg, oarm.T, seed=0, B=1)
+                rec["parity"] = parity_block(oarm.forward_one(rin), ry)
+                rec["cpu_baseline"] = {"value": 1.0 / rsec, "unit": UNIT, "cores": rc, "kind": rkind, "sample": f"1 image, {rsec:.1f} s"}
+            others[wl] = rec
+            del oarm
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if class_par else "weak", "vs_baseline": None,
-        "dtype": "f32" if args.precision == "exact" else "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: CAT-Seg {'ViT-L/14 336x336' if cfg.text_guidance_dim == 768 else 'ViT-B/16 384x384'}, "
-                               f"T={T} classes (Te={min(T, cfg.pad_len)} kept), B={B} "
-                               f"{'sliding windows of one 640x640 image' if sliding else 'images'}/GPU, L=2, pool [1,1], P=1",
-                   "precision": args.precision, "parallelism": (f"kept classes sharded over {world} ranks, all-reduce of the linear-attention state per class layer (NCCL), "
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+        "ms_per_step": res["ms"] / steps, "higher_is_better": True, "scaling": "strong" if class_par else "weak", "vs_baseline": None,
+        "dtype": "f32" if args.precision == "exact" else "f16",
+        "data": "synthetic",
+        "config": {"workload": describe(args.workload, cfg, B, T, arm.sliding),
+                   "precision": args.precision + {"precise": " (tcgen05, hi+lo fp16 operand pairs on the value path, fp32 accumulate)",
+                                                  "fast": " (tcgen05, one fp16 term per operand, fp32 accumulate)",
+                                                  "exact": " (fp32 CUDA cores)"}.get(args.precision, ""),
+                   "parallelism": (f"kept classes sharded over {world} ranks, all-reduce of the linear-attention state per class layer (NCCL), "
                                    f"all-gather of the logit planes" if class_par else f"images sharded over {world} rank(s)"),
                    "l2": "activations (1.2 GB/step) exceed the 126 MB L2; no explicit flush",
-                   "e2e_result": "stitched argmax labels [640,640] int32" if sliding else "per-image argmax labels [B,96,96] int32"},
-        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": labels_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches,
+                   "e2e_result": "stitched argmax labels [640,640] int32" if arm.sliding else "per-image argmax labels [B,96,96] int32 "
+                                 "(the evaluator's consumer, train_net.py:58); e2e_logits returns the full [B,T,96,96] fp32 tensor"},
+        "clocks": res["clocks"], "roofline": roof, "cpu_baseline": cpu, "parity": parity,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
+                "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["ms"] / steps},
+        "e2e_logits": ({"value": nrep * arm.units() * max(2, steps // 2) / (e2e_logits["ms"] / 1e3), "unit": UNIT,
+                        "h2d_bytes_per_step": e2e_logits["h2d"], "d2h_bytes_per_step": e2e_logits["d2h"],
+                        "ms_per_step": e2e_logits["ms"] / max(2, steps // 2)} if e2e_logits else None),
+        "gpu_launches": res["launches"],
+        "secondary": secondary, "strong": strong, "other_workloads": others,
     }
     print(json.dumps(out), flush=True)
     if world > 1:
@@ -356,9 +511,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(BENCH_CONFIGS))
-    ap.add_argument("--precision", default="fast", help="exact | fast | fast:<stage>[,<stage>]")
+    ap.add_argument("--precision", default="precise", help="precise | fast | exact | <mode>:<stage>[,<stage>]")
     ap.add_argument("--batch", type=int, default=0, help="override images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary (fast), e2e_logits, strong-scaling and other-workload records")
     ap.add_argument("--cuda-graph", action="store_true", help="replay the boundary call from a CUDA graph (value only; small batches)")
     ap.add_argument("--parallel", default="image", choices=["image", "class"],
                     help="image: each rank gets its own images (weak scaling, no exchange); class: every rank gets the SAME "

@@ -131,8 +131,10 @@ static void build_param_table(catseg_handle* h) {
     add_param(h, std::string(b) + ".weight", ag); add_param(h, std::string(b) + ".bias", ag);
     snprintf(b, sizeof(b), "layers.%d.attention", l);
     std::string a(b);
-    add_param(h, a + ".padding_tokens", hid);
-    add_param(h, a + ".padding_guidance", tg);
+    if (c.pad_len > 0) {        // the reference registers them as None when pad_len == 0 (model.py:371-373): absent from its state_dict
+      add_param(h, a + ".padding_tokens", hid);
+      add_param(h, a + ".padding_guidance", tg);
+    }
     add_param(h, a + ".attention.q.weight", (int64_t)hid * (hid + tg)); add_param(h, a + ".attention.q.bias", hid);
     add_param(h, a + ".attention.k.weight", (int64_t)hid * (hid + tg)); add_param(h, a + ".attention.k.bias", hid);
     add_param(h, a + ".attention.v.weight", (int64_t)hid * hid); add_param(h, a + ".attention.v.bias", hid);
@@ -396,8 +398,8 @@ void pack_all(Packer& pk) {
     pk.tr(w2, 128, 0, a + ".MLP.2.weight", 512, 0, 128, 512);
     w.w2_t = w2;
     w.b2 = pk.copy(a + ".MLP.2.bias", 128);
-    w.pad_tok = pk.copy(a + ".padding_tokens", 128);
-    w.pad_g = pk.copy(a + ".padding_guidance", tg);
+    w.pad_tok = c.pad_len > 0 ? pk.copy(a + ".padding_tokens", 128) : nullptr;    // n_pad is 0 without them
+    w.pad_g = c.pad_len > 0 ? pk.copy(a + ".padding_guidance", tg) : nullptr;
   }
   // conv1: [128][P*49] -> [P*49][128]
   {

@@ -46,8 +46,9 @@ def param_shapes(cfg: AggregatorConfig) -> "OrderedDict[str, Tuple[int, ...]]":
             s[f"{q}.mlp.fc2.weight"] = (hid, 4 * hid); s[f"{q}.mlp.fc2.bias"] = (hid,)
         s[f"{p}.guidance_norm.weight"] = (ag,); s[f"{p}.guidance_norm.bias"] = (ag,)
         a = f"layers.{l}.attention"
-        s[f"{a}.padding_tokens"] = (1, 1, hid)
-        s[f"{a}.padding_guidance"] = (1, 1, tg)
+        if cfg.pad_len > 0:                      # None (absent from the state_dict) in the reference when pad_len == 0
+            s[f"{a}.padding_tokens"] = (1, 1, hid)
+            s[f"{a}.padding_guidance"] = (1, 1, tg)
         s[f"{a}.attention.q.weight"] = (hid, hid + tg); s[f"{a}.attention.q.bias"] = (hid,)
         s[f"{a}.attention.k.weight"] = (hid, hid + tg); s[f"{a}.attention.k.bias"] = (hid,)
         s[f"{a}.attention.v.weight"] = (hid, hid); s[f"{a}.attention.v.bias"] = (hid,)

@@ -7,7 +7,9 @@ before loading the file by path.  ``timm.layers.Mlp`` (ti
 requirements.txt:7) is Linear -> act -> Dropout -> Linear -> Dropout with attribute names
 fc1/act/drop1/fc2/drop2.
 
-/root/reference does not exist on the GPU box; callers must check ``reference_available()``.
+/root/reference does not exist on the GPU box: ``build_ref()`` (run by ``__graft_entry__.build()`` in the build
+container) leaves an unmodified copy of model.py in the git-ignored ``oracle/_ref/``, which travels with the
+snapshot; callers must still check ``reference_available()``.
 """
 from __future__ import annotations
 
@@ -20,12 +22,35 @@ from itertools import repeat
 
 import torch.nn as nn
 
-REF_MODEL_PATH = os.environ.get(
-    "CATSEG_REFERENCE_MODEL", "/root/reference/cat_seg/modeling/transformer/model.py")
+_SRC = "/root/reference/cat_seg/modeling/transformer/model.py"
+_REF_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+# oracle/_ref/model.py: an UNMODIFIED copy made at build time by build_ref() (git-ignored, travels to the GPU box with
+# gpurun like the built .so): bench.py --impl reference times the reference's own file there.
+_COPY = os.path.join(_REF_DIR, "model.py")
+
+
+def build_ref() -> bool:
+    """Build step (``__graft_entry__.build``): copy the reference's model.py, unmodified, into oracle/_ref/ when
+    /root/reference is present.  Returns True if oracle/_ref/model.py exists afterwards."""
+    import shutil
+    if os.path.isfile(_SRC):
+        os.makedirs(_REF_DIR, exist_ok=True)
+        shutil.copyfile(_SRC, _COPY)
+    return os.path.isfile(_COPY)
+
+
+def _model_path() -> str:
+    env = os.environ.get("CATSEG_REFERENCE_MODEL")
+    if env:
+        return env
+    return _SRC if os.path.isfile(_SRC) else _COPY
+
+
+REF_MODEL_PATH = _model_path()
 
 
 def reference_available() -> bool:
-    return os.path.isfile(REF_MODEL_PATH)
+    return os.path.isfile(_model_path())
 
 
 def _ntuple(n):
@@ -59,8 +84,9 @@ def load_reference_module():
     global _CACHED
     if _CACHED is not None:
         return _CACHED
-    if not reference_available():
-        raise FileNotFoundError(REF_MODEL_PATH)
+    path = _model_path()
+    if not os.path.isfile(path):
+        raise FileNotFoundError(path)
     if "timm.layers" not in sys.modules:
         layers = types.ModuleType("timm.layers")
         layers.Mlp, layers.DropPath, layers.PatchEmbed = _Mlp, nn.Identity, object
@@ -69,7 +95,7 @@ def load_reference_module():
         timm = types.ModuleType("timm")
         timm.layers = layers
         sys.modules["timm"], sys.modules["timm.layers"] = timm, layers
-    spec = importlib.util.spec_from_file_location("catseg_reference_model", REF_MODEL_PATH)
+    spec = importlib.util.spec_from_file_location("catseg_reference_model", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     _CACHED = mod

@@ -5,7 +5,10 @@ with the same torch ops the reference uses (nn.Unfold / nn.Fold / F.interpolate)
 ``sem_seg_postprocess`` (not vendored in the reference: crop to ``img_size``, bilinear
 ``align_corners=False`` resize to ``(height, width)``) and the evaluator's ``argmax(dim=0)``
 (train_net.py:58).  ``CATSeg`` itself cannot be imported here (needs detectron2 + CLIP weights,
-SURVEY.md §8c), so this oracle is pinned by construction: it *is* the reference's op sequence.
+SURVEY.md §8c).  Pinning: tests/golden/make_stitch_golden.py extracts the reference's own statements
+(cat_seg_model.py:158-176, 206-218) with ``ast``, executes them with a stub ``self`` and writes
+tests/golden/stitch_*.npz; tests/test_stitch_golden.py requires this oracle to reproduce those fixtures BIT
+EXACTLY (windows, stitched probabilities, labels), and the CUDA kernel to match them within 2e-6.
 """
 from __future__ import annotations
 

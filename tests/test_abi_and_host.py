@@ -63,7 +63,7 @@ def test_unsupported_configs_fail_loudly():
         Aggregator(attention_type="full")
 
 
-@pytest.mark.parametrize("cfg", [vitb(), vitl(), vitb(prompt_channel=3, num_layers=1)])
+@pytest.mark.parametrize("cfg", [vitb(), vitl(), vitb(prompt_channel=3, num_layers=1), vitb(pad_len=0)])
 def test_state_dict_contract(cfg):
     m = Aggregator(**cfg.ctor_kwargs())
     sd = make_state_dict(cfg, 0)
@@ -79,6 +79,15 @@ def test_state_dict_contract(cfg):
         assert set(ref.state_dict()) == set(m.state_dict())
         for k, v in ref.state_dict().items():
             assert torch.equal(m.state_dict()[k], v), k
+
+
+def test_precision_specs():
+    assert _lib.precision_mask("exact") == 0
+    assert _lib.precision_mask("fast") == 0x1F and _lib.precision_mask("precise") == 0x11F
+    assert _lib.precision_mask("precise:class,decoder") == 0x100 | 4 | 8
+    assert _lib.precision_mask("fast:swin_attn") == 2
+    with pytest.raises(ValueError):
+        _lib.precision_mask("bf16")
 
 
 def test_sliding_window_index_logic_matches_oracle():
