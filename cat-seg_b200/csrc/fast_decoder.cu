@@ -89,7 +89,7 @@ struct BandCfg {
   static constexpr int TMEM_COLS = CTAS == 2 ? 256 : 512;
   static_assert(NTILES * NOUT <= TMEM_COLS && NTILES <= 16, "TMEM columns");
   static_assert(SMEM <= (CTAS == 2 ? 113 * 1024 : 227 * 1024), "shared memory budget");
-  static_assert(!SPLIT || (IN_F32 && CTAS == 1), "PRECISE stages read fp32 activations and own the SM");
+  static_assert(!SPLIT || IN_F32, "PRECISE stages read fp32 activations");
   static_assert(WIN_ % BR == 0 && CIN % 16 == 0 && NOUT % 16 == 0, "shape");
 };
 
@@ -724,6 +724,20 @@ struct MapAddStore {
 #define D3S 64, 32, 32, true, true, 48, 4, false, 1, true
 #define D4S 32, 32, 32, false, true, 96, 6, false, 1, true
 #define D5S 32, 16, 16, false, true, 96, 6, true, 1, true
+// ... and two 9-warp CTAs per SM with short bands (one CTA's staging / epilogue under the other's MMAs); CATSEG_DECS_NARROW is
+// a bit mask (bit i = stage D(i+1) uses the narrow shape), read once, for A/B measurements
+#define D2T 64, 64, 64, false, true, 48, 2, false, 2, true
+#define D3T 64, 32, 32, true, true, 48, 2, false, 2, true
+#define D4T 32, 32, 32, false, true, 96, 3, false, 2, true
+#define D5T 32, 16, 16, false, true, 96, 3, true, 2, true
+static int decs_narrow_mask() {
+  static int m = -1;
+  if (m < 0) {
+    const char* e = getenv("CATSEG_DECS_NARROW");
+    m = e ? atoi(e) & 30 : 0;
+  }
+  return m;
+}
 static int dec_wide_mask() {
   static int m = -1;
   if (m < 0) {
@@ -749,9 +763,9 @@ size_t decoder_split_scratch_bytes(const DecoderDims& d, int B, int chunk) {
   size_t hw = (size_t)d.H * d.W;
   size_t b = 0;
   b += (size_t)B * (4 * hw * d.D1 + 16 * hw * d.D2) * 4;                 // E1, E2
-  b += (emap_tiled_floats<D1S>(B) + emap_tiled_floats<D3S>(B)) * 4 + 512;
+  b += (emap_tiled_floats<D1S>(B) + max_sz(emap_tiled_floats<D3S>(B), emap_tiled_floats<D3T>(B))) * 4 + 512;
   b += (size_t)chunk * (2 * 4 * hw * d.D1 + 2 * 16 * hw * d.D2) * 4;     // c1a c1b c2a c2b (fp32)
-  b += (size_t)chunk * (4 * 4 + 8 * 4 + 12 * 2 + 16 * 2) * 2 * 4 + 4096; // band statistics (>= NB * G per stage)
+  b += (size_t)chunk * (4 * 4 + 24 * 4 + 24 * 2 + 32 * 2) * 2 * 4 + 4096; // band statistics (max NB * G per stage over both shapes)
   b += (size_t)chunk * 64 * 2 * 4 + 256;
   return (b + 255) / 256 * 256;
 }
@@ -833,20 +847,25 @@ cudaError_t run_decoder_split(const float* X, const float* dg0, const float* dg1
                               int* launches, cudaStream_t st) {
   const int hw = d.H * d.W;
   int nl = 0;
+  const int narrow = decs_narrow_mask();
   uint8_t* ptr = reinterpret_cast<uint8_t*>(scratch);
   auto take = [&](size_t bytes) { uint8_t* r = ptr; ptr += (bytes + 255) / 256 * 256; return r; };
   float* E1 = reinterpret_cast<float*>(take((size_t)B * 4 * hw * d.D1 * 4));
   float* E2 = reinterpret_cast<float*>(take((size_t)B * 16 * hw * d.D2 * 4));
   float* E1t = reinterpret_cast<float*>(take(emap_tiled_floats<D1S>(B) * 4));
-  float* E2t = reinterpret_cast<float*>(take(emap_tiled_floats<D3S>(B) * 4));
+  float* E2t = reinterpret_cast<float*>(take(max_sz(emap_tiled_floats<D3S>(B), emap_tiled_floats<D3T>(B)) * 4));
   float* c1a = reinterpret_cast<float*>(take((size_t)chunk * 4 * hw * d.D1 * 4));
   float* c1b = reinterpret_cast<float*>(take((size_t)chunk * 4 * hw * d.D1 * 4));
   float* c2a = reinterpret_cast<float*>(take((size_t)chunk * 16 * hw * d.D2 * 4));
   float* c2b = reinterpret_cast<float*>(take((size_t)chunk * 16 * hw * d.D2 * 4));
-  float* s1a = reinterpret_cast<float*>(take((size_t)chunk * BandCfg<D1S>::NB * 4 * 2 * 4));
-  float* s1b = reinterpret_cast<float*>(take((size_t)chunk * BandCfg<D2S>::NB * 4 * 2 * 4));
-  float* s2a = reinterpret_cast<float*>(take((size_t)chunk * BandCfg<D3S>::NB * 2 * 2 * 4));
-  float* s2b = reinterpret_cast<float*>(take((size_t)chunk * BandCfg<D4S>::NB * 2 * 2 * 4));
+  const int nb1 = BandCfg<D1S>::NB;
+  const int nb2 = (narrow & 2) ? BandCfg<D2T>::NB : BandCfg<D2S>::NB;
+  const int nb3 = (narrow & 4) ? BandCfg<D3T>::NB : BandCfg<D3S>::NB;
+  const int nb4 = (narrow & 8) ? BandCfg<D4T>::NB : BandCfg<D4S>::NB;
+  float* s1a = reinterpret_cast<float*>(take((size_t)chunk * nb1 * 4 * 2 * 4));
+  float* s1b = reinterpret_cast<float*>(take((size_t)chunk * nb2 * 4 * 2 * 4));
+  float* s2a = reinterpret_cast<float*>(take((size_t)chunk * nb3 * 2 * 2 * 4));
+  float* s2b = reinterpret_cast<float*>(take((size_t)chunk * nb4 * 2 * 2 * 4));
   float* gss = reinterpret_cast<float*>(take((size_t)chunk * 64 * 2 * 4));
   {
     GuidConvA a{dg0, d.G1, 2 * d.H, 2 * d.W};
@@ -854,7 +873,7 @@ cudaError_t run_decoder_split(const float* X, const float* dg0, const float* dg1
     GuidConvA a2{dg1, d.G2, 4 * d.H, 4 * d.W};
     CKF(launch_igemm(a2, w.wg2, 0, 1, B * 16 * hw, d.D2, 9 * d.G2, MapAddStore{E2, w.bmap2, 16 * hw, d.D2}, st));
     CKF((launch_relayout_emap<D1S>(E1, E1t, B, st)));
-    CKF((launch_relayout_emap<D3S>(E2, E2t, B, st)));
+    if (narrow & 4) CKF((launch_relayout_emap<D3T>(E2, E2t, B, st))); else CKF((launch_relayout_emap<D3S>(E2, E2t, B, st)));
   }
   const int nslice = B * Te;
   for (int s0 = 0; s0 < nslice; s0 += chunk) {
@@ -863,22 +882,22 @@ cudaError_t run_decoder_split(const float* X, const float* dg0, const float* dg1
     p.Te = Te; p.slice0 = s0; p.nslice = n; p.T = T; p.classes = classes; p.logits = logits; p.head_bias = head_bias;
     p.in = X + (long long)s0 * hw * d.C0; p.in_stats = nullptr; p.wimg = w.w1; p.emap = E1t; p.out32 = c1a; p.out_stats = s1a;
     CKF((launch_band<D1S>(p, num_sms, st)));
-    CKF(launch_gn_finalize(s1a, BandCfg<D1S>::NB, 64, (float)(4 * hw * 16), wx.gn1a_g, wx.gn1a_b, gss, n, st));
-    p.in = c1a; p.in_stats = s1a; p.in_ss = gss; p.nb_in = BandCfg<D1S>::NB; p.in_count = (float)(4 * hw * 16); p.gamma = wx.gn1a_g; p.beta = wx.gn1a_b;
+    CKF(launch_gn_finalize(s1a, nb1, 64, (float)(4 * hw * 16), wx.gn1a_g, wx.gn1a_b, gss, n, st));
+    p.in = c1a; p.in_stats = s1a; p.in_ss = gss; p.nb_in = nb1; p.in_count = (float)(4 * hw * 16); p.gamma = wx.gn1a_g; p.beta = wx.gn1a_b;
     p.wimg = w.w2; p.emap = nullptr; p.out32 = c1b; p.out_stats = s1b;
-    CKF((launch_band<D2S>(p, num_sms, st)));
-    CKF(launch_gn_finalize(s1b, BandCfg<D2S>::NB, 64, (float)(4 * hw * 16), wx.gn1b_g, wx.gn1b_b, gss, n, st));
-    p.in = c1b; p.in_stats = s1b; p.nb_in = BandCfg<D2S>::NB; p.gamma = wx.gn1b_g; p.beta = wx.gn1b_b;
+    if (narrow & 2) CKF((launch_band<D2T>(p, num_sms, st))); else CKF((launch_band<D2S>(p, num_sms, st)));
+    CKF(launch_gn_finalize(s1b, nb2, 64, (float)(4 * hw * 16), wx.gn1b_g, wx.gn1b_b, gss, n, st));
+    p.in = c1b; p.in_stats = s1b; p.nb_in = nb2; p.gamma = wx.gn1b_g; p.beta = wx.gn1b_b;
     p.wimg = w.w3; p.emap = E2t; p.out32 = c2a; p.out_stats = s2a;
-    CKF((launch_band<D3S>(p, num_sms, st)));
-    CKF(launch_gn_finalize(s2a, BandCfg<D3S>::NB, 32, (float)(16 * hw * 16), wx.gn2a_g, wx.gn2a_b, gss, n, st));
-    p.in = c2a; p.in_stats = s2a; p.nb_in = BandCfg<D3S>::NB; p.in_count = (float)(16 * hw * 16); p.gamma = wx.gn2a_g; p.beta = wx.gn2a_b;
+    if (narrow & 4) CKF((launch_band<D3T>(p, num_sms, st))); else CKF((launch_band<D3S>(p, num_sms, st)));
+    CKF(launch_gn_finalize(s2a, nb3, 32, (float)(16 * hw * 16), wx.gn2a_g, wx.gn2a_b, gss, n, st));
+    p.in = c2a; p.in_stats = s2a; p.nb_in = nb3; p.in_count = (float)(16 * hw * 16); p.gamma = wx.gn2a_g; p.beta = wx.gn2a_b;
     p.wimg = w.w4; p.emap = nullptr; p.out32 = c2b; p.out_stats = s2b;
-    CKF((launch_band<D4S>(p, num_sms, st)));
-    CKF(launch_gn_finalize(s2b, BandCfg<D4S>::NB, 32, (float)(16 * hw * 16), wx.gn2b_g, wx.gn2b_b, gss, n, st));
-    p.in = c2b; p.in_stats = s2b; p.nb_in = BandCfg<D4S>::NB; p.gamma = wx.gn2b_g; p.beta = wx.gn2b_b;
+    if (narrow & 8) CKF((launch_band<D4T>(p, num_sms, st))); else CKF((launch_band<D4S>(p, num_sms, st)));
+    CKF(launch_gn_finalize(s2b, nb4, 32, (float)(16 * hw * 16), wx.gn2b_g, wx.gn2b_b, gss, n, st));
+    p.in = c2b; p.in_stats = s2b; p.nb_in = nb4; p.gamma = wx.gn2b_g; p.beta = wx.gn2b_b;
     p.wimg = w.w5; p.emap = nullptr; p.out32 = nullptr; p.out_stats = nullptr;
-    CKF((launch_band<D5S>(p, num_sms, st)));
+    if (narrow & 16) CKF((launch_band<D5T>(p, num_sms, st))); else CKF((launch_band<D5S>(p, num_sms, st)));
   }
   if (launches) *launches += nl;
   return cudaSuccess;
