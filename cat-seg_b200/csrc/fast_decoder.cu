@@ -29,6 +29,8 @@ namespace catseg {
 
 using namespace fast;
 
+static __device__ unsigned kBackoffNs = 200;     // CATSEG_DEC_BACKOFF_NS (A/B)
+
 struct BandConvParams {
   const void* in;            // [S][Win*Win][CIN]  fp32 (IN_F32) or fp16
   const float* in_stats;     // [S][nb_in][G_in][2] partial (sum, sumsq); nullptr: no GroupNorm on the input
@@ -63,16 +65,21 @@ struct BandCfg {
   static constexpr int OVER = P0 + NTILES * 128 + PW + 2 - NP;
   static constexpr uint32_t IMG_BYTES = ((KCH * LBO_I + (OVER > 0 ? OVER * 16 : 0)) + 127) / 128 * 128;
   static constexpr int NTAP = UPS ? 4 : 9, NPG = UPS ? 4 : 1, NIMG = NTAP * NPG;
-  static constexpr int NW = SPLIT ? 2 : 1;                               // images per weight / per staged band (hi, lo)
-  static constexpr uint32_t WBYTES = NOUT * CIN * 2, LBO_WT = NOUT * 16;
+  static constexpr int NW = SPLIT ? 2 : 1;                               // terms per weight / per staged band (hi, lo)
+  // SPLIT: the hi and lo terms of a tap's weights form ONE image with 2 NOUT rows (B operand rows = N): the product
+  // Ah [Wh | Wl] is a single MMA of N = 2 NOUT (its two column halves are summed in the epilogue), Al Wh a second one of
+  // N = NOUT on the first NOUT rows: two MMAs instead of three per k-step, both at a wider N (the N <= 64 MMAs of this
+  // decoder sit at the ~46-cycle operand-read floor), and half as many ring images to wait for.
+  static constexpr int NACC = NW * NOUT;                                 // accumulator columns per M tile
+  static constexpr uint32_t WBYTES = NW * NOUT * CIN * 2, LBO_WT = NW * NOUT * 16;
   // two CTAs per SM (half-height bands, <= 113 KiB and <= 256 TMEM columns each): one CTA's staging / epilogue
   // overlaps the other's MMAs.  Small weight sets stay resident, larger ones stream through a ring.
   // (the whole weight set may stay in shared memory when, together with the band image, it fits half an SM)
-  static constexpr bool RESIDENT = NW * NIMG * WBYTES <= 24 * 1024 ||
-                                   NW * (IMG_BYTES + NIMG * WBYTES) <= (CTAS == 2 ? 108 : (SPLIT ? 214 : 200)) * 1024;
+  static constexpr bool RESIDENT = NIMG * WBYTES <= 24 * 1024 ||
+                                   NW * IMG_BYTES + NIMG * WBYTES <= (CTAS == 2 ? 108 : (SPLIT ? 214 : 200)) * 1024;
   // streaming ring: 48 KiB deep (96 KiB when the CTA owns the SM), so that the prefetch distance (in MMA time) exceeds the
   // ~1 us L2->SMEM latency
-  static constexpr int NSLOT = RESIDENT ? NW * NIMG : (int)((CTAS == 2 ? 48 : 96) * 1024 / WBYTES);
+  static constexpr int NSLOT = RESIDENT ? NIMG : (int)((CTAS == 2 ? 48 : 96) * 1024 / WBYTES);
   // worker warps (staging + epilogues): 8 per CTA with two CTAs per SM, 16 when the CTA owns the SM; one more warp issues
   static constexpr int NWW = CTAS == 2 ? 8 : 16, NWT = NWW * 32, THREADS = NWT + 32, NTG = NWW / 4;
   static constexpr int NB = WIN_ / BR;                 // bands per slice
@@ -83,11 +90,12 @@ struct BandCfg {
   static constexpr uint32_t SM_ST = SM_SC + 2 * CIN * 4;              // [NWW warps][GOUT][2]
   static constexpr uint32_t SM_BAR = (SM_ST + NWW * GOUT * 2 * 4 + 15) / 16 * 16;
   static constexpr uint32_t SMEM = SM_BAR + (2 * NSLOT + 33) * 8 + 16;   // ring barriers + [2 sets][16 tiles] accumulator barriers
-  static constexpr uint32_t IDESC = umma::make_idesc_f16(128, NOUT);
+  static constexpr uint32_t IDESC = umma::make_idesc_f16(128, NACC);     // A (hi) x the whole image
+  static constexpr uint32_t IDESC_LO = umma::make_idesc_f16(128, NOUT);  // SPLIT: A (lo) x the hi rows
   // CTAS = CTAs per SM: 2 (half-height bands; one CTA's staging / epilogue overlaps the other's MMAs) or 1 (a band as
   // tall as the shared memory allows: fewer M-tile remainders and one pass over a streamed weight set per band)
   static constexpr int TMEM_COLS = CTAS == 2 ? 256 : 512;
-  static_assert(NTILES * NOUT <= TMEM_COLS && NTILES <= 16, "TMEM columns");
+  static_assert(NTILES * NACC <= TMEM_COLS && NTILES <= 16, "TMEM columns");
   static_assert(SMEM <= (CTAS == 2 ? 113 * 1024 : 227 * 1024), "shared memory budget");
   static_assert(!SPLIT || IN_F32, "PRECISE stages read fp32 activations");
   static_assert(WIN_ % BR == 0 && CIN % 16 == 0 && NOUT % 16 == 0, "shape");
@@ -112,13 +120,13 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q4 = warp & 3, tgrp = (warp >> 2) % C::NTG;
   const bool issuer = __shfl_sync(0xffffffffu, warp, 0) == C::NWW;           // warp-uniform role
-  constexpr int ACC_COLS = C::NTILES * NOUT;
+  constexpr int ACC_COLS = C::NTILES * C::NACC;
   constexpr int SETS = (C::NPG > 1 && 2 * ACC_COLS <= C::TMEM_COLS) ? 2 : 1;
 
   const long long nitems = (long long)p.nslice * C::NB;
   long long mine = 0;
   for (long long i = blockIdx.x; i < nitems; i += gridDim.x) ++mine;
-  const long long total_loads = C::RESIDENT ? 1 : mine * C::NIMG * C::NW;
+  const long long total_loads = C::RESIDENT ? 1 : mine * C::NIMG;
 
   if (tid == 0) {
     for (int i = 0; i < 2 * C::NSLOT + 32; ++i) umma::mbar_init(&bar_full[i], 1);
@@ -137,14 +145,14 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
       int s = (int)(n % C::NSLOT);
       umma::mbar_expect_tx(&bar_full[s], C::WBYTES);
       umma::bulk_g2s(smem + C::SM_W + s * C::WBYTES,
-                     reinterpret_cast<const uint8_t*>(p.wimg) + (n % (C::NIMG * C::NW)) * C::WBYTES, C::WBYTES, &bar_full[s]);
+                     reinterpret_cast<const uint8_t*>(p.wimg) + (n % C::NIMG) * C::WBYTES, C::WBYTES, &bar_full[s]);
     }
   };
   if (issuer) {
     if (umma::elect_one()) {
       if (C::RESIDENT) {
-        umma::mbar_expect_tx(&bar_full[0], C::NW * C::NIMG * C::WBYTES);
-        umma::bulk_g2s(smem + C::SM_W, p.wimg, C::NW * C::NIMG * C::WBYTES, &bar_full[0]);
+        umma::mbar_expect_tx(&bar_full[0], C::NIMG * C::WBYTES);
+        umma::bulk_g2s(smem + C::SM_W, p.wimg, C::NIMG * C::WBYTES, &bar_full[0]);
       } else {
         for (int i = 0; i < C::NSLOT - 1; ++i) issue_load(i);
       }
@@ -152,6 +160,7 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
     __syncwarp();
   }
   long long nimg = 0;          // streaming: images consumed so far by this CTA (issuing warp, all lanes)
+  long long iacc_full = 0, iacc_issue = 0, iacc_empty = 0;   // CATSEG_PHASE_TIMING: issuing warp, streaming mode
   uint32_t ph_acc[2] = {0, 0};
   bool w_ready = false;
   long long t_last = clock64(), pacc0 = 0, pacc1 = 0, pacc2 = 0, pacc3 = 0, pacc4 = 0, nit_dbg = 0;
@@ -174,21 +183,17 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
             int off;
             if (UPS) off = ((tap >> 1) + pa - 1) * C::PW + ((tap & 1) + pb - 1);
             else off = (tap / 3 - 1) * C::PW + (tap % 3 - 1);
-            const uint64_t b_desc = umma::make_smem_desc(sb + C::SM_W + (uint32_t)((pg * C::NTAP + tap) * C::NW) * C::WBYTES, C::LBO_WT, 128);
+            const uint64_t b_desc = umma::make_smem_desc(sb + C::SM_W + (uint32_t)(pg * C::NTAP + tap) * C::WBYTES, C::LBO_WT, 128);
             const uint64_t a_tile = a_desc0 + (uint64_t)(uint32_t)(C::P0 + off + t * 128);
 #pragma unroll
             for (int k = 0; k < C::KSTEPS; ++k)
-              umma::mma_f16_ss(tm + set * ACC_COLS + t * NOUT, a_tile + (uint64_t)(k * 2 * (C::LBO_I >> 4)),
+              umma::mma_f16_ss(tm + set * ACC_COLS + t * C::NACC, a_tile + (uint64_t)(k * 2 * (C::LBO_I >> 4)),
                                 b_desc + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC, (tap > 0 || k > 0) ? 1u : 0u);
             if constexpr (SPLIT) {
 #pragma unroll
-              for (int k = 0; k < C::KSTEPS; ++k)      // lo activations x hi weights
-                umma::mma_f16_ss(tm + set * ACC_COLS + t * NOUT, a_tile + (uint64_t)((C::IMG_BYTES >> 4) + k * 2 * (C::LBO_I >> 4)),
-                                 b_desc + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC, 1u);
-#pragma unroll
-              for (int k = 0; k < C::KSTEPS; ++k)      // hi activations x lo weights
-                umma::mma_f16_ss(tm + set * ACC_COLS + t * NOUT, a_tile + (uint64_t)(k * 2 * (C::LBO_I >> 4)),
-                                 b_desc + (uint64_t)((C::WBYTES >> 4) + k * 2 * (C::LBO_WT >> 4)), C::IDESC, 1u);
+              for (int k = 0; k < C::KSTEPS; ++k)      // lo activations x hi weights (the first NOUT rows of the image)
+                umma::mma_f16_ss(tm + set * ACC_COLS + t * C::NACC, a_tile + (uint64_t)((C::IMG_BYTES >> 4) + k * 2 * (C::LBO_I >> 4)),
+                                 b_desc + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC_LO, 1u);
             }
           }
           umma::mma_commit(&bar_acc[set * 16 + t]);
@@ -198,13 +203,14 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
       return;
     }
 #pragma unroll 1
-    for (int tw = 0; tw < C::NTAP * C::NW; ++tw) {
-      const int tap = tw / C::NW, wlo = tw % C::NW;           // wlo = 1: the lo weight image of this tap (hi activations only)
+    for (int tap = 0; tap < C::NTAP; ++tap) {
       int off;
       if (UPS) off = ((tap >> 1) + pa - 1) * C::PW + ((tap & 1) + pb - 1);
       else off = (tap / 3 - 1) * C::PW + (tap % 3 - 1);
       const int slot = (int)(nimg % C::NSLOT);
+      const long long ti0 = clock64();
       umma::mbar_wait(&bar_full[slot], (uint32_t)((nimg / C::NSLOT) & 1));
+      const long long ti1 = clock64();
       const uint32_t wb = sb + C::SM_W + (uint32_t)slot * C::WBYTES;
       // descriptors are built once and advanced by integer adds on the (address >> 4) field
       const uint64_t b_desc = umma::make_smem_desc(wb, C::LBO_WT, 128);
@@ -214,19 +220,20 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
         for (int t = 0; t < C::NTILES; ++t) {
 #pragma unroll
           for (int k = 0; k < C::KSTEPS; ++k)
-            umma::mma_f16_ss(tm + set * ACC_COLS + t * NOUT, a_tile + (uint64_t)(k * 2 * (C::LBO_I >> 4)),
-                              b_desc + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC, (tw > 0 || k > 0) ? 1u : 0u);
-          if (SPLIT && wlo == 0) {
+            umma::mma_f16_ss(tm + set * ACC_COLS + t * C::NACC, a_tile + (uint64_t)(k * 2 * (C::LBO_I >> 4)),
+                              b_desc + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC, (tap > 0 || k > 0) ? 1u : 0u);
+          if (SPLIT) {
 #pragma unroll
             for (int k = 0; k < C::KSTEPS; ++k)
-              umma::mma_f16_ss(tm + set * ACC_COLS + t * NOUT, a_tile + (uint64_t)((C::IMG_BYTES >> 4) + k * 2 * (C::LBO_I >> 4)),
-                               b_desc + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC, 1u);
+              umma::mma_f16_ss(tm + set * ACC_COLS + t * C::NACC, a_tile + (uint64_t)((C::IMG_BYTES >> 4) + k * 2 * (C::LBO_I >> 4)),
+                               b_desc + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC_LO, 1u);
           }
           a_tile += 128;
         }
         umma::mma_commit(&bar_empty[slot]);
       }
       __syncwarp();
+      const long long ti2 = clock64();
       {
         // refill the slot of the PREVIOUS image (its MMAs were committed one step ago)
         const long long nn = nimg + C::NSLOT - 1;
@@ -236,6 +243,7 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
         __syncwarp();
         ++nimg;
       }
+      iacc_full += ti1 - ti0; iacc_issue += ti2 - ti1; iacc_empty += clock64() - ti2;
     }
     if (umma::elect_one()) {
 #pragma unroll
@@ -391,14 +399,20 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
         constexpr int NCH = HEAD ? 1 : NREAL / 32;
         constexpr bool SPLIT_CH = C::NTG > 2 && NCH > 1;
         for (int t = SPLIT_CH ? (tgrp / NCH) % (C::NTG / NCH) : tgrp; t < C::NTILES; t += SPLIT_CH ? C::NTG / NCH : C::NTG) {
-          umma::mbar_wait(&bar_acc[set * 16 + t], ph_acc[set]);
+          if (SPLIT) umma::mbar_wait_backoff(&bar_acc[set * 16 + t], ph_acc[set], kBackoffNs);
+          else umma::mbar_wait(&bar_acc[set * 16 + t], ph_acc[set]);
           umma::fence_after_sync();
           if (t == 0) BPH(1);
           bool valid; long long opix;
           tile_geom(t, valid, opix);
           if constexpr (HEAD) {
             float v[8];
-            umma::tmem_ld8(acc_addr + t * NOUT, v);
+            umma::tmem_ld8(acc_addr + t * C::NACC, v);
+            if constexpr (SPLIT) {
+              float v2[8];
+              umma::tmem_ld8(acc_addr + t * C::NACC + NOUT, v2);
+              v[0] += v2[0];
+            }
             if (valid) {
               int cls = p.classes[gslice];
               p.logits[((long long)b * p.T + cls) * (C::WOUT * C::WOUT) + opix] = v[0] + p.head_bias;
@@ -417,7 +431,13 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
 #pragma unroll
                 for (int i = 0; i < 8; ++i) e4[i] = ld4(e + i * 512);
               }
-              umma::tmem_ld32(acc_addr + t * NOUT + c0, v);
+              umma::tmem_ld32(acc_addr + t * C::NACC + c0, v);
+              if constexpr (SPLIT) {                           // + Ah Wl, accumulated in the second column half
+                float v2[32];
+                umma::tmem_ld32(acc_addr + t * C::NACC + NOUT + c0, v2);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += v2[i];
+              }
               if (valid) {
                 if constexpr (UPS) {
 #pragma unroll
@@ -473,6 +493,7 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
     ++nit_dbg;
   }
   if (p.dbg != nullptr && blockIdx.x == 0 && tid == 0) { p.dbg[0] = pacc0; p.dbg[1] = pacc1; p.dbg[2] = pacc2; p.dbg[3] = pacc3; p.dbg[4] = nit_dbg; p.dbg[5] = pacc4; }
+  if (p.dbg != nullptr && blockIdx.x == 0 && tid == C::NWT) { p.dbg[6] = iacc_full; p.dbg[7] = iacc_issue; p.dbg[8] = iacc_empty; }
 #undef BPH
   umma::fence_before_sync();
   __syncthreads();
@@ -558,16 +579,18 @@ static cudaError_t launch_band(const BandConvParams& p, int num_sms, cudaStream_
   if (dbg_on < 0) {
     const char* e = getenv("CATSEG_PHASE_TIMING");
     dbg_on = (e && e[0] == '1') ? 1 : 0;
-    if (dbg_on) { cudaMalloc(&dbg, 8 * sizeof(long long)); cudaMemset(dbg, 0, 8 * sizeof(long long)); }
+    if (dbg_on) { cudaMalloc(&dbg, 16 * sizeof(long long)); cudaMemset(dbg, 0, 16 * sizeof(long long)); }
+    if (const char* b = getenv("CATSEG_DEC_BACKOFF_NS")) { unsigned v = (unsigned)atoi(b); cudaMemcpyToSymbol(kBackoffNs, &v, sizeof(v)); }
   }
   BandConvParams q = p;
   q.dbg = dbg_on ? dbg : nullptr;
   kern<<<grid, C::THREADS, C::SMEM, st>>>(q);
   if (dbg_on) {
-    long long hb[8];
+    long long hb[16];
     cudaStreamSynchronize(st);
     cudaMemcpy(hb, dbg, sizeof(hb), cudaMemcpyDeviceToHost);
     double n = hb[4] > 0 ? (double)hb[4] : 1.0;
+    if (!C::RESIDENT) fprintf(stderr, "[issuing warp, per band: wait-weights %.0f | issue %.0f | wait-prev-image+refill %.0f] ", hb[6] / n, hb[7] / n, hb[8] / n);
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::THREADS, C::SMEM);
     fprintf(stderr, "[occupancy %d CTAs/SM, smem %u] ", occ, (unsigned)C::SMEM);
@@ -581,11 +604,13 @@ static cudaError_t launch_band(const BandConvParams& p, int num_sms, cudaStream_
 // weight preparation (runs once in catseg_finalize_params)
 
 // image[(k/8)*NOUT*8 + n*8 + k%8] = W3[n][ci0 + k][tap]   (n < nreal, else 0)
-// nw = 1: one fp16 image per tap; nw = 2 (PRECISE): a hi and a lo image per tap, stored as consecutive pairs
-__device__ __forceinline__ void store_wimg(__half* dst, long long img, int per, int idx, float v, int nw) {
+// Element (n, k) of weight image `img` with `nout` output rows: nw = 1: one fp16 image [nout x cin]; nw = 2 (PRECISE): one
+// image with 2 nout rows, rows [0, nout) = hi term, [nout, 2 nout) = lo term (BandCfg::WBYTES).
+__device__ __forceinline__ void store_wimg(__half* dst, long long img, int nout, int cin, int n, int k, float v, int nw) {
   const __half h = __float2half_rn(v);
-  dst[img * nw * per + idx] = h;
-  if (nw == 2) dst[(img * 2 + 1) * per + idx] = __float2half_rn(v - __half2float(h));
+  __half* base = dst + img * (long long)(nw * nout * cin) + (k >> 3) * (nw * nout * 8) + (k & 7);
+  base[n * 8] = h;
+  if (nw == 2) base[(nout + n) * 8] = __float2half_rn(v - __half2float(h));
 }
 __global__ void pack_tap_img_kernel(__half* dst, const float* W3, int Cin3, int ci0, int CIN, int NOUT, int nreal, int nw) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -593,7 +618,7 @@ __global__ void pack_tap_img_kernel(__half* dst, const float* W3, int Cin3, int 
   if (i >= 9 * per) return;
   int tap = i / per, r = i % per, n = r / CIN, k = r % CIN;
   float v = n < nreal ? W3[((long long)n * Cin3 + ci0 + k) * 9 + tap] : 0.0f;
-  store_wimg(dst, tap, per, (k >> 3) * NOUT * 8 + n * 8 + (k & 7), v, nw);
+  store_wimg(dst, tap, NOUT, CIN, n, k, v, nw);
 }
 
 // composed ConvTranspose(k2,s2) o conv3x3:  image index (a*2+b)*4 + (u*2+v), element [co][ci]
@@ -616,7 +641,7 @@ __global__ void compose_up_img_kernel(__half* dst, const float* Wup, const float
         acc = fmaf(Wup[(((long long)ci * Cup + cu) * 2 + ay) * 2 + ax], W3[((long long)co * Cin3 + cu) * 9 + (dy + 1) * 3 + dx + 1], acc);
     }
   }
-  store_wimg(dst, img, per, (ci >> 3) * Co * 8 + co * 8 + (ci & 7), acc, nw);
+  store_wimg(dst, img, Co, Ci, co, ci, acc, nw);
 }
 
 // bias map of the composed conv: Bmap[Y][X][co] = sum_{valid dy,dx} sum_cu bup[cu] W3[co][cu][dy+1][dx+1]
@@ -719,7 +744,7 @@ struct MapAddStore {
 #define D5N 32, 16, 16, false, false, 96, 6, true, 2
 #define D5W 32, 16, 16, false, false, 96, 12, true, 1
 // PRECISE shapes: one 17-warp CTA per SM, fp32 activations in and out
-#define D1S 128, 64, 64, true, true, 24, 6, false, 1, true
+#define D1S 128, 64, 64, true, true, 24, 4, false, 1, true
 #define D2S 64, 64, 64, false, true, 48, 6, false, 1, true
 #define D3S 64, 32, 32, true, true, 48, 4, false, 1, true
 #define D4S 32, 32, 32, false, true, 96, 6, false, 1, true
@@ -734,7 +759,7 @@ static int decs_narrow_mask() {
   static int m = -1;
   if (m < 0) {
     const char* e = getenv("CATSEG_DECS_NARROW");
-    m = e ? atoi(e) & 30 : 0;
+    m = e ? atoi(e) & 28 : 0;
   }
   return m;
 }

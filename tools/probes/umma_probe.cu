@@ -94,7 +94,7 @@ __global__ void gemm_probe(const float* A, const float* B, float* D, int N, int 
   if (t < 32) tmem_dealloc<256>(tm);
 }
 
-__global__ void tc_throughput(float* out, int iters, long long* cycles, int N, int lbo_a, int lbo_b, int commit_every = 0) {
+__global__ void tc_throughput(float* out, int iters, long long* cycles, int N, int lbo_a, int lbo_b, int commit_every = 0, int a_shift = 0, int b_shift = 0) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint64_t bar2;
@@ -108,7 +108,7 @@ __global__ void tc_throughput(float* out, int iters, long long* cycles, int N, i
   long long t0 = clock64();
   if (t == 0) {
     uint32_t idesc = make_idesc_bf16(128, N);
-    uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 40000);
+    uint32_t a0 = smem_u32(smem) + a_shift, b0 = smem_u32(smem + 40000) + b_shift;
     uint64_t da0 = make_smem_desc(a0, lbo_a, 128), db0 = make_smem_desc(b0, lbo_b, 128);
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -384,6 +384,20 @@ int main(int argc, char** argv) {
         long long c[2]; CHECK(cudaMemcpy(c, cyc2, 16, cudaMemcpyDeviceToHost));
         printf("PROBE issue cost (%s): %.1f cycles per MMA end-to-end, %.1f cycles per MMA spent issuing (8-MMA GEMMs + commit)\n",
                mode == 0 ? "if (tid == 0)" : "warp 0 + elect.sync", (double)c[0] / (2000.0 * 8), (double)c[1] / (2000.0 * 8));
+      }
+    } else if (id == 26) {
+      // row-shifted operand starts (implicit-GEMM convolution taps): does an A / B tile whose first row is not a multiple
+      // of 8 rows (start address not 128-byte aligned) cost extra shared-memory wavefronts?
+      size_t smem = 100000;
+      CHECK(cudaFuncSetAttribute(tc_throughput, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int cfgs[][5] = {{64, 2064, 1024, 0, 0}, {64, 2064, 1024, 16, 0}, {64, 2064, 1024, 64, 0}, {64, 2064, 1024, 128, 0}, {64, 2064, 1024, 816, 0},
+                             {64, 2048, 1024, 0, 0}, {64, 2048, 1024, 16, 0}, {64, 6416, 1024, 816, 0}, {64, 6416, 1024, 800, 0},
+                             {32, 2064, 512, 0, 0}, {32, 2064, 512, 16, 0}, {128, 2064, 2048, 0, 0}, {128, 2064, 2048, 16, 0}, {256, 2064, 4096, 0, 0}, {256, 2064, 4096, 16, 0},
+                             {64, 2064, 1024, 0, 16}, {144, 2048, 2320, 0, 16}};
+      for (auto& c5 : cfgs) {
+        tc_throughput<<<prop.multiProcessorCount, 128, smem>>>(out, iters, cyc, c5[0], c5[1], c5[2], 0, c5[3], c5[4]); CHECK(cudaDeviceSynchronize());
+        long long c; CHECK(cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost));
+        printf("PROBE tcgen05 M128 N%d lboA=%d lboB=%d A-start +%d B, B-start +%d B: %.1f cycles per MMA(K=16)\n", c5[0], c5[1], c5[2], c5[3], c5[4], (double)c / (4.0 * iters));
       }
     } else if (id == 20) {
       size_t smem = 100000;
