@@ -70,6 +70,7 @@ _SIGS = [
     ("catseg_param_numel", C.c_int64, [C.c_void_p, C.c_int]),
     ("catseg_set_param", C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int]),
     ("catseg_finalize_params", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("catseg_set_vocabulary", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     ("catseg_kept_classes", C.c_int, [C.c_void_p, C.c_int]),
     ("catseg_workspace_bytes", C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     ("catseg_forward", C.c_int, [C.c_void_p] + [C.c_void_p] * 7 + [C.c_size_t, C.c_int, C.c_int, C.c_void_p]),

@@ -74,6 +74,8 @@ class Aggregator(nn.Module):
         self._handle_device: Optional[torch.device] = None
         self._synced: Dict[str, tuple] = {}
         self._workspace: Optional[torch.Tensor] = None
+        self._vocab: Optional[torch.Tensor] = None        # [T,P,C] class embeddings of the current vocabulary
+        self._vocab_pushed = False
 
     # ------------------------------------------------------------------ parameter tree
     def _register(self, dotted: str, value, buffer: bool = False) -> None:
@@ -121,6 +123,7 @@ class Aggregator(nn.Module):
             raise RuntimeError(f"catseg_create failed ({rc}): {lib.catseg_last_error(None).decode()}")
         self._handle, self._handle_device = h, device
         self._synced = {}
+        self._vocab_pushed = False
         n = lib.catseg_num_params(h)
         names = [lib.catseg_param_name(h, i).decode() for i in range(n)]
         if names != self._names:
@@ -147,6 +150,34 @@ class Aggregator(nn.Module):
             if rc != 0:
                 raise self._lib_error(rc)
 
+    def set_vocabulary(self, text_feats: Optional[torch.Tensor]) -> None:
+        """Registers the class embeddings of a vocabulary once (``[T,P,C]`` or the predictor's cached ``[T,1,C]``,
+        cat_seg_predictor.py:190-224); ``forward(img_feats, None, guidance)`` then skips the per-call text work
+        (normalisation, text-guidance projection, guidance half of the class-attention q/k).  ``None`` forgets it."""
+        if text_feats is None:
+            self._vocab = None
+        else:
+            t = text_feats.detach()
+            if t.dim() == 4:
+                t = t[0]
+            if t.dim() != 3 or t.shape[1] != self.cfg.prompt_channel or t.shape[2] != self.cfg.text_guidance_dim:
+                raise ValueError(f"vocabulary must be [T,{self.cfg.prompt_channel},{self.cfg.text_guidance_dim}], got {tuple(text_feats.shape)}")
+            self._vocab = t.to(dtype=torch.float32).contiguous()
+        self._vocab_pushed = False
+
+    def _push_vocabulary(self, dev) -> int:
+        lib = _lib.load()
+        if self._vocab is None:
+            raise RuntimeError("text_feats is None and no vocabulary is set (Aggregator.set_vocabulary)")
+        if not self._vocab_pushed:
+            v = self._vocab.to(dev)
+            rc = lib.catseg_set_vocabulary(self._handle, C.c_void_p(v.data_ptr()), v.shape[0],
+                                           C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            if rc != 0:
+                raise self._lib_error(rc)
+            self._vocab, self._vocab_pushed = v, True         # keeps the source alive until the copy has run
+        return self._vocab.shape[0]
+
     def kept_classes(self, T: int) -> int:
         return self.pad_len if (self.pad_len > 0 and T > self.pad_len) else T
 
@@ -158,7 +189,12 @@ class Aggregator(nn.Module):
         B, Cc, H, W = img_feats.shape
         if (H, W) != tuple(c.feature_resolution):
             raise ValueError(f"img_feats grid {(H, W)} != feature_resolution {c.feature_resolution}")
-        if text_feats.dim() != 4 or text_feats.shape[0] != B or text_feats.shape[2] != c.prompt_channel \
+        if text_feats is None:
+            if self._vocab is None:
+                raise RuntimeError("text_feats is None and no vocabulary is set (Aggregator.set_vocabulary)")
+            if Cc != c.text_guidance_dim:
+                raise ValueError(f"img_feats channels {Cc} != text_guidance_dim {c.text_guidance_dim}")
+        elif text_feats.dim() != 4 or text_feats.shape[0] != B or text_feats.shape[2] != c.prompt_channel \
                 or text_feats.shape[3] != c.text_guidance_dim or Cc != c.text_guidance_dim:
             raise ValueError(f"text_feats {tuple(text_feats.shape)} / img_feats {tuple(img_feats.shape)} mismatch")
         if len(guidance) != 3:
@@ -168,7 +204,7 @@ class Aggregator(nn.Module):
         for g, e in zip(guidance, exp):
             if tuple(g.shape) != e:
                 raise ValueError(f"appearance guidance shape {tuple(g.shape)} != {e}")
-        return B, text_feats.shape[1], H, W
+        return B, (text_feats.shape[1] if text_feats is not None else self._vocab.shape[0]), H, W
 
     @staticmethod
     def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -184,7 +220,13 @@ class Aggregator(nn.Module):
         with torch.cuda.device(dev):
             self._ensure_handle(dev)
             self.sync_weights()
-            img, text = self._f32c(img_feats), self._f32c(text_feats)
+            img = self._f32c(img_feats)
+            if text_feats is None:
+                self._push_vocabulary(dev)
+                text_ptr = C.c_void_p(None)
+            else:
+                text = self._f32c(text_feats)
+                text_ptr = C.c_void_p(text.data_ptr())
             g = [self._f32c(x) for x in appearance_guidance]
             need = lib.catseg_workspace_bytes(self._handle, B, T)
             if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
@@ -192,7 +234,7 @@ class Aggregator(nn.Module):
                 self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
             logits = torch.empty(B, T, 4 * H, 4 * W, dtype=torch.float32, device=dev)
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            args = [self._handle] + [C.c_void_p(t.data_ptr()) for t in (img, text, g[0], g[1], g[2], logits)] + \
+            args = [self._handle, C.c_void_p(img.data_ptr()), text_ptr] + [C.c_void_p(t.data_ptr()) for t in (g[0], g[1], g[2], logits)] + \
                    [C.c_void_p(self._workspace.data_ptr()), self._workspace.numel(), B, T]
             if taps is None:
                 rc = lib.catseg_forward(*args, stream)

@@ -63,6 +63,16 @@ struct catseg_handle {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   __nv_bfloat16* prep_img = nullptr;            // FAST_PREP: embedding images, then the three guidance-conv image sets
   const __nv_bfloat16 *embed_img = nullptr, *gconv_img[3] = {nullptr, nullptr, nullptr};   // nullptr: shape not covered -> fp32 kernel
+  // persistent per-vocabulary text object (catseg_set_vocabulary; cat_seg_predictor.py:190-224 caches the class
+  // embeddings once per vocabulary, the reference Aggregator then re-derives everything below from them on every call)
+  struct Vocab {
+    int T = 0;
+    bool valid = false;        // false after a weight update: re-derived by the next forward
+    float* store = nullptr;    // text [T,P,C] | textn [T,P,C] | inv_norm [T*P] | tmean [T,Ct] | text_g [T,128] | cg_qk [L][T,256]
+    size_t floats = 0;
+    float *text = nullptr, *textn = nullptr, *inv_norm = nullptr, *tmean = nullptr, *text_g = nullptr, *cg_qk = nullptr;
+    int32_t* iota = nullptr;   // [T]
+  } vocab;
   bool finalized = false;
   std::string err;
   int device = 0;
@@ -242,6 +252,8 @@ extern "C" int catseg_destroy(catseg_handle* h) {
   for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
   if (h->wimg_split) cudaFree(h->wimg_split);
   if (h->wimg_attn2) cudaFree(h->wimg_attn2);
+  if (h->vocab.store) cudaFree(h->vocab.store);
+  if (h->vocab.iota) cudaFree(h->vocab.iota);
   if (h->raw) cudaFree(h->raw);
   if (h->packed) cudaFree(h->packed);
   if (h->wimg) cudaFree(h->wimg);
@@ -653,6 +665,7 @@ extern "C" int catseg_finalize_params(catseg_handle* h, catseg_stream stream) {
   }
   CUDA_OK(h, cudaStreamSynchronize(st));
   h->finalized = true;
+  h->vocab.valid = false;          // text_g / cg_qk depend on the weights: re-derived by the next forward
   return CATSEG_OK;
 }
 
@@ -666,7 +679,7 @@ struct Plan {
   DecoderDims dd;
   // workspace offsets (floats)
   size_t imgn, textn, corr, cmax, classes, tmean, text_g, cg_qk, pad_state, app_g, app_gn, ag_qk, dg0, dg1, X,
-      Xp, Xp2, X1, state, timg, dec, agw, classes_loc, total;
+      Xp, Xp2, X1, state, timg, dec, agw, classes_loc, inv_t, inv_i, rmaxp, total;
 };
 
 Plan make_plan(const catseg_handle* h, int B, int T) {
@@ -692,6 +705,9 @@ Plan make_plan(const catseg_handle* h, int B, int T) {
   p.textn = take((size_t)B * T * p.P * p.Ct);
   p.corr = take((size_t)B * T * p.P * p.HW);
   p.cmax = take((size_t)B * T);
+  p.inv_t = take((size_t)B * T * p.P);                     // 1 / ||text row||   (tcgen05 cost volume: normalisation as scales)
+  p.inv_i = take((size_t)B * p.HW);                        // 1 / ||img pixel||
+  p.rmaxp = take((size_t)B * T * p.P * 2 * ((p.HW + 127) / 128));   // per-class partial maxima from the GEMM epilogue
   p.classes = take((size_t)B * p.Te);
   p.classes_loc = take((size_t)2 * B * p.Te);   // class-sharded mode: local slice of the kept list, then local plane ids
   p.tmean = take((size_t)B * p.Te * p.Ct);
@@ -768,6 +784,57 @@ extern "C" size_t catseg_workspace_bytes(const catseg_handle* h, int B, int T) {
       CUDA_OK(h, cudaMemcpyAsync((dst), (src), (size_t)(nfloats) * sizeof(float), cudaMemcpyDeviceToDevice, st)); \
   } while (0)
 
+// Everything Aggregator.forward derives from the class embeddings alone (model.py:650, 701, 712-715 and the guidance
+// half of the class-attention q/k projections), computed ONCE per vocabulary for all T classes.
+static int derive_vocabulary(catseg_handle* h, cudaStream_t st, int* launches) {
+  const catseg_config& c = h->cfg;
+  auto& v = h->vocab;
+  const int T = v.T, P = c.prompt_channel, Ct = c.text_guidance_dim, L = c.num_layers;
+  const bool truncated = c.pad_len > 0 && T > c.pad_len;
+  int nl = 0;
+  RUN(launch_inv_norm_rows(v.text, v.inv_norm, (long long)T * P, Ct, st));
+  RUN(launch_normalize_rows(v.text, v.textn, (long long)T * P, Ct, st));
+  RUN(launch_iota_classes(v.iota, 1, T, st));
+  RUN(launch_text_mean(truncated ? v.textn : v.text, v.iota, v.tmean, 1, T, T, P, Ct, st));
+  RUN(launch_linear(v.tmean, h->tproj_wt, h->tproj_b, v.text_g, T, 128, Ct, 1, st));
+  for (int l = 0; l < L; ++l)
+    RUN(launch_linear(v.text_g, h->cls[l].wg_qk_t, h->cls[l].bqk, v.cg_qk + (size_t)l * T * 256, T, 256, 128, 0, st));
+  v.valid = true;
+  if (launches) *launches += nl;
+  return CATSEG_OK;
+}
+
+extern "C" int catseg_set_vocabulary(catseg_handle* h, const float* text_feats, int T, catseg_stream stream) {
+  if (!h || T < 0) return CATSEG_ERR_INVALID;
+  auto& v = h->vocab;
+  if (T == 0 || !text_feats) { v.T = 0; v.valid = false; return CATSEG_OK; }           // forget the vocabulary
+  if (T > 6144) return fail(h, CATSEG_ERR_UNSUPPORTED, "T > 6144 classes");
+  const catseg_config& c = h->cfg;
+  const size_t P = c.prompt_channel, Ct = c.text_guidance_dim, L = c.num_layers;
+  auto al = [](size_t n) { return (n + 63) / 64 * 64; };
+  const size_t need = 2 * al(T * P * Ct) + al(T * P) + al(T * Ct) + al((size_t)T * 128) + al(L * T * 256);
+  if (v.floats < need) {
+    if (v.store) cudaFree(v.store);
+    v.store = nullptr; v.floats = 0;
+    CUDA_OK(h, cudaMalloc(&v.store, need * sizeof(float)));
+    v.floats = need;
+    if (v.iota) cudaFree(v.iota);
+    v.iota = nullptr;
+    CUDA_OK(h, cudaMalloc(&v.iota, 6144 * sizeof(int32_t)));
+  }
+  float* q = v.store;
+  v.text = q; q += al(T * P * Ct);
+  v.textn = q; q += al(T * P * Ct);
+  v.inv_norm = q; q += al(T * P);
+  v.tmean = q; q += al(T * Ct);
+  v.text_g = q; q += al((size_t)T * 128);
+  v.cg_qk = q;
+  CUDA_OK(h, cudaMemcpyAsync(v.text, text_feats, (size_t)T * P * Ct * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  v.T = T;
+  v.valid = false;                 // derived on the first forward (needs finalised weights), ordered on that call's stream
+  return CATSEG_OK;
+}
+
 // The forward proper.  shard_world == 1: logits is [B,T,4H,4W].  shard_world > 1 (class-sharded): logits is the compact
 // local buffer [B, Te/world, 4H, 4W], every per-(image, class) stage runs on this rank's slice of the kept classes and the
 // linear-attention state is summed over the group through `allreduce` between the state and apply kernels.
@@ -776,9 +843,12 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
                         const catseg_taps* taps, int shard_rank, int shard_world, catseg_allreduce_fn allreduce, void* ar_ctx,
                         int32_t* kept_out, catseg_stream stream) {
   if (!h) return CATSEG_ERR_INVALID;
-  if (!img || !text || !g0 || !g1 || !g2 || !logits || !workspace) return fail(h, CATSEG_ERR_INVALID, "null tensor pointer");
+  if (!img || !g0 || !g1 || !g2 || !logits || !workspace) return fail(h, CATSEG_ERR_INVALID, "null tensor pointer");
   if (B <= 0 || T <= 0) return fail(h, CATSEG_ERR_INVALID, "B and T must be positive (got %d, %d)", B, T);
   if (!h->finalized) return fail(h, CATSEG_ERR_WEIGHTS, "catseg_finalize_params has not been called");
+  const bool use_vocab = text == nullptr;
+  if (use_vocab && (h->vocab.T != T || h->vocab.store == nullptr))
+    return fail(h, CATSEG_ERR_INVALID, "text_feats is NULL but no vocabulary of %d classes is set (catseg_set_vocabulary)", T);
   if (h->cfg.text_guidance_dim != h->cfg.appearance_guidance_dim)
     return fail(h, CATSEG_ERR_UNSUPPORTED, "img_feats channels (appearance_guidance_dim) must equal text_guidance_dim");
   const Plan p = make_plan(h, B, T);
@@ -806,23 +876,77 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
   // ---------------- PREP: cost volume, class selection, guidance projections (model.py:693-715)
   seg.begin(CATSEG_STAGE_PREP);
   CUDA_OK(h, cudaEventRecord(h->ev_fork, st));
-  RUN(launch_normalize_img(img, ws + p.imgn, B, p.C, p.HW, st));
-  RUN(launch_normalize_rows(text, ws + p.textn, (long long)B * T * p.P, p.Ct, st));
-  RUN(launch_cost_volume(ws + p.textn, ws + p.imgn, ws + p.corr, B, T * p.P, p.C, p.HW, st));
-  if (p.truncated) {
-    RUN(launch_class_max(ws + p.corr, ws + p.cmax, (long long)B * T, p.P * p.HW, st));
-    RUN(launch_select_classes(ws + p.cmax, classes_all, B, T, p.Te, st));
+  const bool prep_fast = (h->fast_mask & CATSEG_FAST_PREP) != 0;
+  if (use_vocab && !h->vocab.valid) {                     // first call after catseg_set_vocabulary / a weight update
+    int rc = derive_vocabulary(h, st, &nl);
+    if (rc != CATSEG_OK) return rc;
+  }
+  // Cost volume (model.py:648-652).  Tensor-core path (FAST / PRECISE front end): ONE tcgen05 GEMM on the raw embeddings
+  // with hi+lo fp16 operand pairs (fp32-accurate, gemm_split.cu); both L2 normalisations are row / column scales of its
+  // epilogue, which also reduces the per-class maximum the top-k selection needs (:695).  When classes are truncated and
+  // nobody taps the volume, the first pass writes NO volume at all (maxima only) and a second pass computes just the kept
+  // classes' slices (the reference recomputes them too, :702): the raw [B,P,T,H,W] volume never reaches HBM.
+  const long long text_bs = use_vocab ? 0 : (long long)T * p.P * p.Ct;    // text batch stride (0: one vocabulary for all images)
+  const float* text_src = use_vocab ? h->vocab.text : text;
+  const float* textn = use_vocab ? h->vocab.textn : ws + p.textn;
+  bool corr_compact = false;                                               // corr holds [B][Te] kept slices instead of [B][T]
+  if (prep_fast) {
+    const int ntn = (p.HW + 127) / 128;
+    const float* inv_t = use_vocab ? h->vocab.inv_norm : ws + p.inv_t;
+    if (!use_vocab) RUN(launch_inv_norm_rows(text, ws + p.inv_t, (long long)B * T * p.P, p.Ct, st));
+    RUN(launch_inv_norm_pixels(img, ws + p.inv_i, B, p.C, p.HW, st));
+    GemmSplitParams g{};
+    g.A = text_src; g.a_row = p.Ct; g.a_k = 1; g.a_batch = text_bs;
+    g.B = img; g.b_row = 1; g.b_k = p.HW; g.b_batch = (long long)p.C * p.HW;
+    g.M = T * p.P; g.N = p.HW; g.K = p.C; g.batch = B;
+    g.row_scale = inv_t; g.rs_batch = use_vocab ? 0 : (long long)T * p.P;
+    g.col_scale = ws + p.inv_i; g.cs_batch = p.HW;
+    const bool two_pass = p.truncated && !(taps && taps->corr);
+    if (!two_pass) { g.C = ws + p.corr; g.c_row = p.HW; g.c_batch = (long long)T * p.P * p.HW; }
+    if (p.truncated) g.row_max = ws + p.rmaxp;
+    RUN(launch_gemm_split(g, st));
+    if (p.truncated) {
+      RUN(launch_class_max(ws + p.rmaxp, ws + p.cmax, (long long)B * T, p.P * 2 * ntn, st));
+      RUN(launch_select_classes(ws + p.cmax, classes_all, B, T, p.Te, st));
+      if (two_pass) {                                      // kept slices only: rows gathered through the kept-class list
+        if (p.P != 1) return fail(h, CATSEG_ERR_UNSUPPORTED, "two-pass cost volume needs prompt_channel == 1");
+        g.a_index = classes_all; g.ai_batch = p.Te; g.M = p.Te; g.row_max = nullptr;
+        g.C = ws + p.corr; g.c_row = p.HW; g.c_batch = (long long)p.Te * p.HW;
+        RUN(launch_gemm_split(g, st));
+        corr_compact = true;
+      }
+    } else {
+      RUN(launch_iota_classes(classes_all, B, p.Te, st));
+    }
+    if (p.truncated && !use_vocab) RUN(launch_normalize_rows(text, ws + p.textn, (long long)B * T * p.P, p.Ct, st));   // text guidance input (:701)
   } else {
-    RUN(launch_iota_classes(classes_all, B, p.Te, st));
+    RUN(launch_normalize_img(img, ws + p.imgn, B, p.C, p.HW, st));
+    if (!use_vocab) RUN(launch_normalize_rows(text, ws + p.textn, (long long)B * T * p.P, p.Ct, st));
+    RUN(launch_cost_volume(textn, text_bs, ws + p.imgn, ws + p.corr, B, T * p.P, p.C, p.HW, st));
+    if (p.truncated) {
+      RUN(launch_class_max(ws + p.corr, ws + p.cmax, (long long)B * T, p.P * p.HW, st));
+      RUN(launch_select_classes(ws + p.cmax, classes_all, B, T, p.Te, st));
+    } else {
+      RUN(launch_iota_classes(classes_all, B, p.Te, st));
+    }
   }
   if (sharded) RUN(launch_slice_classes(classes_all, classes, B, p.Te, shard_rank * Te, Te, st));
   if (kept_out) CUDA_OK(h, cudaMemcpyAsync(kept_out, classes_all, (size_t)B * p.Te * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-  RUN(launch_text_mean(p.truncated ? ws + p.textn : text, classes, ws + p.tmean, B, T, Te, p.P, p.Ct, st));
-  RUN(launch_linear(ws + p.tmean, h->tproj_wt, h->tproj_b, ws + p.text_g, (long long)B * Te, 128, p.Ct, 1, st));
-  for (int l = 0; l < p.L; ++l) {
-    RUN(launch_linear(ws + p.text_g, h->cls[l].wg_qk_t, h->cls[l].bqk, ws + p.cg_qk + (size_t)l * B * Te * 256,
-                      (long long)B * Te, 256, 128, 0, st));
-    RUN(launch_class_pad_state(h->cls[l], 128, ws + p.pad_state + (size_t)l * kStateFloats, p.n_pad, p.S, st));
+  if (use_vocab) {
+    // the text guidance of a vocabulary is derived once (derive_vocabulary): per call the kept classes only pick their rows
+    RUN(launch_gather_rows(h->vocab.text_g, classes, ws + p.text_g, (long long)B * Te, 128, st));
+    for (int l = 0; l < p.L; ++l) {
+      RUN(launch_gather_rows(h->vocab.cg_qk + (size_t)l * T * 256, classes, ws + p.cg_qk + (size_t)l * B * Te * 256, (long long)B * Te, 256, st));
+      RUN(launch_class_pad_state(h->cls[l], 128, ws + p.pad_state + (size_t)l * kStateFloats, p.n_pad, p.S, st));
+    }
+  } else {
+    RUN(launch_text_mean(p.truncated ? ws + p.textn : text, classes, ws + p.tmean, B, T, Te, p.P, p.Ct, st));
+    RUN(launch_linear(ws + p.tmean, h->tproj_wt, h->tproj_b, ws + p.text_g, (long long)B * Te, 128, p.Ct, 1, st));
+    for (int l = 0; l < p.L; ++l) {
+      RUN(launch_linear(ws + p.text_g, h->cls[l].wg_qk_t, h->cls[l].bqk, ws + p.cg_qk + (size_t)l * B * Te * 256,
+                        (long long)B * Te, 256, 128, 0, st));
+      RUN(launch_class_pad_state(h->cls[l], 128, ws + p.pad_state + (size_t)l * kStateFloats, p.n_pad, p.S, st));
+    }
   }
   const bool class_fast = (h->fast_mask & CATSEG_FAST_CLASS) != 0;
   __half* timg = reinterpret_cast<__half*>(ws + p.timg);
@@ -830,7 +954,6 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
   // The guidance projections only depend on the inputs: they run on an internal stream beside the cost volume / class
   // selection / text chain (small, latency-bound kernels) and are joined before the embedding.  Externally the call is
   // still ordered on `stream`.
-  const bool prep_fast = (h->fast_mask & CATSEG_FAST_PREP) != 0;
   // the single-term guidance projections are class independent (they cancel in the argmax) but would cap the logits
   // parity of the PRECISE mode at ~1e-2: that mode keeps them on the fp32 kernels
   const bool gconv_fast = prep_fast && !h->split;
@@ -871,10 +994,20 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
 
   // ---------------- EMBED (model.py:704)
   seg.begin(CATSEG_STAGE_EMBED);
-  if (prep_fast && h->embed_img)
-    RUN(launch_cost_embed_fast(ws + p.corr, classes, h->embed_img, h->conv1_b, X, B, T, Te, h->num_sms, st));
-  else
-    RUN(launch_cost_embed(ws + p.corr, classes, h->conv1_wt, h->conv1_b, X, B, T, Te, p.P, p.H, p.W, st));
+  {
+    // compact volume ([B][p.Te] kept slices): slice s of image b is row (rank offset + j) of that image's block
+    const int32_t* eids = classes;
+    int eT = T;
+    if (corr_compact) {
+      int32_t* ids = reinterpret_cast<int32_t*>(ws + p.classes_loc) + (size_t)B * p.Te;     // scratch behind the local class list
+      RUN(launch_iota_range(ids, B, Te, sharded ? shard_rank * Te : 0, st));
+      eids = ids; eT = p.Te;
+    }
+    if (prep_fast && h->embed_img)
+      RUN(launch_cost_embed_fast(ws + p.corr, eids, h->embed_img, h->conv1_b, X, B, eT, Te, h->num_sms, st));
+    else
+      RUN(launch_cost_embed(ws + p.corr, eids, h->conv1_wt, h->conv1_b, X, B, eT, Te, p.P, p.H, p.W, st));
+  }
   seg.end();
   TAP(taps->embed, X, (size_t)nslice * p.HW * 128);
 

@@ -70,8 +70,13 @@ constexpr int kStateFloats = 4 * 32 * 32 + 128;   // per (image, pixel): KV[4][3
 // ---------------------------------------------------------------- prep.cu
 cudaError_t launch_normalize_img(const float* img, float* out, int B, int C, int HW, cudaStream_t st);
 cudaError_t launch_normalize_rows(const float* in, float* out, long long rows, int C, cudaStream_t st);
-cudaError_t launch_cost_volume(const float* textn, const float* imgn, float* corr, int B, int TP, int C, int HW,
-                               cudaStream_t st);
+// text_batch_stride = 0: one set of class embeddings for every image (vocabulary mode)
+cudaError_t launch_cost_volume(const float* textn, long long text_batch_stride, const float* imgn, float* corr, int B, int TP,
+                               int C, int HW, cudaStream_t st);
+cudaError_t launch_iota_range(int32_t* ids, int B, int Te, int offset, cudaStream_t st);
+cudaError_t launch_inv_norm_rows(const float* in, float* out, long long rows, int C, cudaStream_t st);
+cudaError_t launch_inv_norm_pixels(const float* img, float* out, int B, int C, int HW, cudaStream_t st);
+cudaError_t launch_gather_rows(const float* src, const int32_t* idx, float* dst, long long n, int width, cudaStream_t st);
 cudaError_t launch_class_max(const float* corr, float* cmax, long long rows, int n, cudaStream_t st);
 cudaError_t launch_select_classes(const float* cmax, int32_t* classes, int B, int T, int Te, cudaStream_t st);
 cudaError_t launch_text_mean(const float* src, const int32_t* classes, float* out, int B, int T, int Te, int P,
@@ -92,6 +97,23 @@ cudaError_t launch_fill(float* p, float v, long long n, cudaStream_t st);
 cudaError_t launch_iota_classes(int32_t* classes, int B, int Te, cudaStream_t st);
 // dst[b][j] = src[b][first + j], j < n (class-sharded mode: this rank's slice of the kept-class list)
 cudaError_t launch_slice_classes(const int32_t* src, int32_t* dst, int B, int Te, int first, int n, cudaStream_t st);
+
+// ---------------------------------------------------------------- gemm_split.cu
+// C[b][m][n] = epilogue(sum_k A[b][rowidx(m)][k] * B[b][n][k]), fp32 in / out, hi+lo fp16 operand pairs on tcgen05 (fp32-accurate)
+struct GemmSplitParams {
+  const float* A; long long a_row, a_k, a_batch;     // element strides (floats)
+  const float* B; long long b_row, b_k, b_batch;
+  float* C; long long c_row, c_batch;                // may be nullptr (only row_max wanted)
+  int M, N, K, batch;
+  const int32_t* a_index; long long ai_batch;        // optional row indirection of A (and of row_scale): row m -> a_index[b][m]
+  const float* bias;                                 // [N]
+  const float* row_scale; long long rs_batch;        // [batch][rows of A]
+  const float* col_scale; long long cs_batch;        // [batch][N]
+  const float* residual; long long r_row, r_batch;   // added after the activation; r_row = 0 broadcasts one row
+  int act;                                           // 0 none, 1 ReLU, 2 QuickGELU
+  float* row_max;                                    // [batch][M][2 * ceil(N / 128)] partial maxima over 64-column spans
+};
+cudaError_t launch_gemm_split(const GemmSplitParams& p, cudaStream_t st);
 
 // ---------------------------------------------------------------- fast_prep.cu
 // 7x7 cost embedding for P = 1 on a 24x24 grid; bimg = 14 images packed by launch_pack_embed_img from Wt [49][128]

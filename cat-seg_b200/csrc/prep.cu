@@ -42,10 +42,58 @@ cudaError_t launch_normalize_rows(const float* in, float* out, long long rows, i
   return cudaGetLastError();
 }
 
+// ---- 1 / max(||row||_2, 1e-12) of rows of length C (the scale F.normalize applies, model.py:650): one warp per row
+__global__ void inv_norm_rows_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int C) {
+  long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* src = in + r * C;
+  float ss = 0.0f;
+  for (int c = lane; c < C; c += 32) { float v = __ldg(src + c); ss = fmaf(v, v, ss); }
+  ss = warp_sum(ss);
+  if (lane == 0) out[r] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+}
+cudaError_t launch_inv_norm_rows(const float* in, float* out, long long rows, int C, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  inv_norm_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(in, out, rows, C);
+  return cudaGetLastError();
+}
+// ---- the same for the pixels of img [B][C][HW] (model.py:649): out[b][p]
+__global__ void inv_norm_pixels_kernel(const float* __restrict__ img, float* __restrict__ out, int C, int HW) {
+  int b = blockIdx.y;
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const float* src = img + (long long)b * C * HW + p;
+  float ss = 0.0f;
+  for (int c = 0; c < C; ++c) { float v = __ldg(src + (long long)c * HW); ss = fmaf(v, v, ss); }
+  out[(long long)b * HW + p] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+}
+cudaError_t launch_inv_norm_pixels(const float* img, float* out, int B, int C, int HW, cudaStream_t st) {
+  dim3 grid((HW + 127) / 128, B);
+  inv_norm_pixels_kernel<<<grid, 128, 0, st>>>(img, out, C, HW);
+  return cudaGetLastError();
+}
+// ---- dst[i][:] = src[idx[i]][:] (rows of `width` floats, width % 4 == 0): the per-image kept classes pick their rows of
+// a per-vocabulary table
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, float* __restrict__ dst,
+                                   long long n, int width4) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * width4) return;
+  long long r = i / width4;
+  int c = (int)(i % width4);
+  st4(dst + (r * width4 + c) * 4, ld4(src + ((long long)idx[r] * width4 + c) * 4));
+}
+cudaError_t launch_gather_rows(const float* src, const int32_t* idx, float* dst, long long n, int width, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  long long tot = n * (width / 4);
+  gather_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, idx, dst, n, width / 4);
+  return cudaGetLastError();
+}
+
 // ---- einsum('bchw,btpc->bpthw') (model.py:651) as a batched GEMM: corr[b][t*P+p][hw]
-cudaError_t launch_cost_volume(const float* textn, const float* imgn, float* corr, int B, int TP, int C, int HW,
-                               cudaStream_t st) {
-  DenseA a{textn, (long long)TP * C, C};
+cudaError_t launch_cost_volume(const float* textn, long long text_batch_stride, const float* imgn, float* corr, int B, int TP,
+                               int C, int HW, cudaStream_t st) {
+  DenseA a{textn, text_batch_stride, C};
   BiasActStore e{corr, (long long)TP * HW, HW, nullptr, 0};
   return launch_igemm(a, imgn, (long long)C * HW, B, TP, HW, C, e, st);
 }
@@ -102,6 +150,16 @@ __global__ void iota_classes_kernel(int32_t* classes, int n, int Te) {
 cudaError_t launch_iota_classes(int32_t* classes, int B, int Te, cudaStream_t st) {
   int n = B * Te;
   iota_classes_kernel<<<(n + 255) / 256, 256, 0, st>>>(classes, n, Te);
+  return cudaGetLastError();
+}
+
+__global__ void iota_range_kernel(int32_t* ids, int n, int Te, int offset) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ids[i] = offset + i % Te;
+}
+cudaError_t launch_iota_range(int32_t* ids, int B, int Te, int offset, cudaStream_t st) {
+  int n = B * Te;
+  iota_range_kernel<<<(n + 255) / 256, 256, 0, st>>>(ids, n, Te, offset);
   return cudaGetLastError();
 }
 

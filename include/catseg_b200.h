@@ -118,6 +118,13 @@ int catseg_set_param(catseg_handle* h, const char* name, const float* src, int64
 /* Packs every parameter into kernel layouts; fails if a parameter is missing. */
 int catseg_finalize_params(catseg_handle* h, catseg_stream stream);
 
+/* Persistent per-vocabulary text object (cat_seg_predictor.py:190-224 caches the class embeddings
+ * of a vocabulary, model.py:650,701,712-715 re-derives from them on every call).  text_feats [T,P,C] fp32 (device) is
+ * copied; its normalisation scales, the text-guidance projection and the guidance half of the class-attention q/k
+ * projections are derived once (re-derived after a weight update).  Afterwards catseg_forward* may be called with
+ * text_feats == NULL and the same T: per call the kept classes only gather their rows.  T = 0 forgets the vocabulary. */
+int catseg_set_vocabulary(catseg_handle* h, const float* text_feats, int T, catseg_stream stream);
+
 /* Number of kept classes for T input classes: min(T, pad_len) when pad_len > 0 (model.py:694). */
 int catseg_kept_classes(const catseg_handle* h, int T);
 size_t catseg_workspace_bytes(const catseg_handle* h, int B, int T);

@@ -55,3 +55,46 @@ def test_precise_argmax_gate(name, case):
     cfg, B, T, seed = case
     y, ref = _run(cfg, B, T, seed, "precise", same_text=True)
     _check(y, ref, name)
+
+
+@pytest.mark.parametrize("precision", ["precise", "fast", "exact"])
+@pytest.mark.parametrize("case", [(vitb(), 2, 5, True), (vitl(), 2, 300, True), (vitb(prompt_channel=3), 1, 4, True)])
+def test_vocabulary_object_matches_per_call_text(precision, case):
+    """the persistent per-vocabulary object (class embeddings registered once; per call the kept
+    classes gather their rows) gives the SAME logits as passing the repeated text_feats on every call, and a weight
+    update re-derives it."""
+    cfg, B, T, _ = case
+    sd = make_state_dict(cfg, 11)
+    img, text, g = make_inputs(cfg, B, T, 11, same_text=True)
+    m = Aggregator(**cfg.ctor_kwargs(), precision=precision)
+    m.load_state_dict(sd, strict=False)
+    m = m.cuda()
+    cu = (img.cuda(), text.cuda(), [x.cuda() for x in g])
+    y_call = m(*cu).clone()
+    m.set_vocabulary(text[0])
+    y_vocab = m(cu[0], None, cu[2]).clone()
+    assert bool(((y_call == -100.0) == (y_vocab == -100.0)).all())
+    assert (y_call - y_vocab).abs().max().item() <= 2e-6, (y_call - y_vocab).abs().max().item()
+    ref = aggregator_forward(sd, cfg.oracle_cfg(), img, text, g)
+    assert (y_vocab.cpu() - ref)[ref != -100.0].abs().max().item() <= (8e-3 if precision == "fast" else 1e-4)
+    # weight update: the derived tables follow
+    with torch.no_grad():
+        m.text_guidance_projection._modules["0"].weight.mul_(1.5)
+    y2 = m(cu[0], None, cu[2])
+    y2_call = m(*cu)
+    assert (y2 - y2_call).abs().max().item() <= 2e-6 and (y2 - y_vocab).abs().max().item() > 1e-4
+
+
+def test_cost_volume_on_tensor_cores_matches_oracle():
+    """north_star item (1): the cost-volume contraction on tcgen05 (hi+lo fp16 operand pairs, normalisations and the
+    per-class maximum in the epilogue) reproduces the fp32 volume and the oracle's kept-class decision bit for bit."""
+    cfg = vitl()
+    sd = make_state_dict(cfg, 5)
+    img, text, g = make_inputs(cfg, 2, 300, 5, same_text=False)
+    _, st = aggregator_forward(sd, cfg.oracle_cfg(), img, text, g, return_stages=True)
+    m = Aggregator(**cfg.ctor_kwargs(), precision="precise:prep")
+    m.load_state_dict(sd, strict=False)
+    _, taps = m.cuda()(img.cuda(), text.cuda(), [x.cuda() for x in g], taps=["corr", "classes", "embed"])
+    assert (taps["corr"].cpu() - st["corr"]).abs().max().item() <= 5e-7          # cosines in [-1, 1]
+    assert torch.equal(taps["classes"].cpu().long(), st["classes"])
+    assert (taps["embed"].cpu() - st["embed"]).abs().max().item() <= 2e-5 * max(1.0, st["embed"].abs().max().item())
