@@ -63,6 +63,8 @@ struct catseg_handle {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   __nv_bfloat16* prep_img = nullptr;            // FAST_PREP: embedding images, then the three guidance-conv image sets
   const __nv_bfloat16 *embed_img = nullptr, *gconv_img[3] = {nullptr, nullptr, nullptr};   // nullptr: shape not covered -> fp32 kernel
+  __half* gconv_split_store = nullptr;          // PRECISE: fp16 [Wh | Wl] images of the three guidance convolutions
+  const __half* gconv_split_img[3] = {nullptr, nullptr, nullptr};
   // persistent per-vocabulary text object (catseg_set_vocabulary; cat_seg_predictor.py:190-224 caches the class
   // embeddings once per vocabulary, the reference Aggregator then re-derives everything below from them on every call)
   struct Vocab {
@@ -252,6 +254,7 @@ extern "C" int catseg_destroy(catseg_handle* h) {
   for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
   if (h->wimg_split) cudaFree(h->wimg_split);
   if (h->wimg_attn2) cudaFree(h->wimg_attn2);
+  if (h->gconv_split_store) cudaFree(h->gconv_split_store);
   if (h->vocab.store) cudaFree(h->vocab.store);
   if (h->vocab.iota) cudaFree(h->vocab.iota);
   if (h->raw) cudaFree(h->raw);
@@ -662,6 +665,18 @@ extern "C" int catseg_finalize_params(catseg_handle* h, catseg_stream stream) {
         h->gconv_img[i] = h->prep_img + off[i];
       }
     }
+    if (h->split) {
+      size_t soff[4] = {0, 0, 0, 0};
+      for (int i = 0; i < 3; ++i) soff[i + 1] = soff[i] + (size_t)2 * ci[i] * 9 * co[i];
+      if (!h->gconv_split_store) CUDA_OK(h, cudaMalloc(&h->gconv_split_store, soff[3] * sizeof(__half)));
+      for (int i = 0; i < 3; ++i) {
+        h->gconv_split_img[i] = nullptr;
+        if (ci[i] > 0 && co[i] > 0 && gconv_fast_supported(i, ci[i], H << i, W << i, co[i]) && ci[i] % gconv_split_kc(i) == 0) {
+          CUDA_OK(h, launch_pack_gconv_img_split(h->gconv_split_store + soff[i], wt[i], ci[i], co[i], gconv_split_kc(i), st));
+          h->gconv_split_img[i] = h->gconv_split_store + soff[i];
+        }
+      }
+    }
   }
   CUDA_OK(h, cudaStreamSynchronize(st));
   h->finalized = true;
@@ -961,7 +976,9 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
     cudaStream_t mainst = st;
     CUDA_OK(h, cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));     // ev_fork was recorded at the start of the stage
     cudaStream_t st = h->aux_stream;             // shadows: the launches below go to the internal stream
-    if (gconv_fast && h->gconv_img[0]) RUN(launch_gconv_fast(0, g0, h->gconv_img[0], h->gproj_b, ws + p.app_g, B, p.Cg, st));
+    const bool gsplit = prep_fast && h->split;
+    if (gsplit && h->gconv_split_img[0]) RUN(launch_gconv_split(0, g0, h->gconv_split_img[0], h->gproj_b, ws + p.app_g, B, p.Cg, st));
+    else if (gconv_fast && h->gconv_img[0]) RUN(launch_gconv_fast(0, g0, h->gconv_img[0], h->gproj_b, ws + p.app_g, B, p.Cg, st));
     else RUN(launch_conv3x3_nchw(g0, h->gproj_wt, h->gproj_b, ws + p.app_g, B, p.Cg, p.H, p.W, 128, st));
     for (int l = 0; l < p.L; ++l) {
       RUN(launch_layernorm128(ws + p.app_g, ws + p.app_gn, h->gnorm_g[l], h->gnorm_b[l], (long long)B * p.HW, st));
@@ -969,12 +986,16 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
         RUN(launch_linear(ws + p.app_gn, h->swin[l * 2 + k].wg_qk_t, h->swin[l * 2 + k].bqk,
                           ws + p.ag_qk + (size_t)(l * 2 + k) * B * p.HW * 256, (long long)B * p.HW, 256, 128, 0, st));
     }
-    if (gconv_fast && h->gconv_img[1])
+    if (gsplit && h->gconv_split_img[1])
+      RUN(launch_gconv_split(1, g1, h->gconv_split_img[1], h->dgp_b[0], ws + p.dg0, B, c.decoder_guidance_dims[0], st));
+    else if (gconv_fast && h->gconv_img[1])
       RUN(launch_gconv_fast(1, g1, h->gconv_img[1], h->dgp_b[0], ws + p.dg0, B, c.decoder_guidance_dims[0], st));
     else
       RUN(launch_conv3x3_nchw(g1, h->dgp_wt[0], h->dgp_b[0], ws + p.dg0, B, c.decoder_guidance_dims[0], 2 * p.H, 2 * p.W,
                               p.dd.G1, st));
-    if (gconv_fast && h->gconv_img[2])
+    if (gsplit && h->gconv_split_img[2])
+      RUN(launch_gconv_split(2, g2, h->gconv_split_img[2], h->dgp_b[1], ws + p.dg1, B, c.decoder_guidance_dims[1], st));
+    else if (gconv_fast && h->gconv_img[2])
       RUN(launch_gconv_fast(2, g2, h->gconv_img[2], h->dgp_b[1], ws + p.dg1, B, c.decoder_guidance_dims[1], st));
     else
       RUN(launch_conv3x3_nchw(g2, h->dgp_wt[1], h->dgp_b[1], ws + p.dg1, B, c.decoder_guidance_dims[1], 4 * p.H, 4 * p.W,

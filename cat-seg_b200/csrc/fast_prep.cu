@@ -213,28 +213,35 @@ cudaError_t launch_cost_embed_fast(const float* corr, const int32_t* classes, co
 }
 
 // ================================================================================================ guidance 3x3 conv
-template <int NOUT, int WIN_, int BR, int KC>
+// SPLIT (PRECISE front end): fp16 hi + lo staging images, one weight image [Wh rows | Wl rows] per tap (2 NOUT rows):
+// Ah [Wh | Wl] is one MMA of N = 2 NOUT whose column halves are summed in the epilogue, Al Wh a second one of N = NOUT
+// (the scheme of the PRECISE decoder, fast_decoder.cu); fp32-accurate projections at two MMAs per k-step.
+template <int NOUT, int WIN_, int BR, int KC, bool SPLIT = false>
 struct GConvCfg {
   static constexpr int PW = WIN_ + 2, NP = (BR + 2) * PW, P0 = PW + 1;
   static constexpr int MROWS = (BR - 1) * PW + WIN_, NTILES = (MROWS + 127) / 128;
   static constexpr int ROWS = (P0 + NTILES * 128 + PW + 1 + 7) / 8 * 8;     // rows any tap view may touch
+  static constexpr int NW = SPLIT ? 2 : 1;
   static constexpr uint32_t LBO_I = ROWS * 16;
-  static constexpr uint32_t A_BYTES = (KC / 8) * LBO_I;
-  static constexpr uint32_t LBO_WT = NOUT * 16;
-  static constexpr uint32_t WIMG = NOUT * KC * 2, W_BYTES = 9 * WIMG;
+  static constexpr uint32_t A_TERM = (KC / 8) * LBO_I;                      // one staged term (hi or lo)
+  static constexpr uint32_t A_BYTES = NW * A_TERM;
+  static constexpr uint32_t LBO_WT = NW * NOUT * 16;
+  static constexpr uint32_t WIMG = NW * NOUT * KC * 2, W_BYTES = 9 * WIMG;
+  static constexpr int NACC = NW * NOUT;
   static constexpr uint32_t SM_A = 0, SM_W = 2 * A_BYTES, SM_BAR = SM_W + 2 * W_BYTES;
   static constexpr uint32_t SMEM = SM_BAR + 8 * 8 + 16;
   static constexpr int NB = WIN_ / BR;
-  static constexpr uint32_t IDESC = umma::make_idesc_bf16(128, NOUT);
-  static_assert(NTILES * NOUT <= 256 && SMEM <= 232448 && WIN_ % BR == 0 && KC % 16 == 0, "guidance conv shape");
+  static constexpr uint32_t IDESC = SPLIT ? umma::make_idesc_f16(128, NACC) : umma::make_idesc_bf16(128, NOUT);
+  static constexpr uint32_t IDESC_LO = umma::make_idesc_f16(128, NOUT);
+  static_assert(NTILES * NACC <= 256 && SMEM <= 232448 && WIN_ % BR == 0 && KC % 16 == 0, "guidance conv shape");
   static_assert(A_BYTES % 128 == 0 && W_BYTES % 16 == 0, "alignment");
 };
 
-template <int NOUT, int WIN_, int BR, int KC>
+template <int NOUT, int WIN_, int BR, int KC, bool SPLIT>
 __global__ void __launch_bounds__(256, 1)
-gconv_fast_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict__ wimg, const float* __restrict__ bias,
+gconv_fast_kernel(const float* __restrict__ in, const void* __restrict__ wimg, const float* __restrict__ bias,
                   float* __restrict__ out, int Ci) {
-  using C = GConvCfg<NOUT, WIN_, BR, KC>;
+  using C = GConvCfg<NOUT, WIN_, BR, KC, SPLIT>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + C::SM_BAR);      // [2] weights of chunk landed
   uint64_t* bar_free = bar_full + 2;                                        // [2] MMAs of chunk done
@@ -267,7 +274,7 @@ gconv_fast_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict_
     __syncwarp();
   }
   // rows beyond the staged band (only reachable by discarded accumulator rows) are zeroed once in both buffers
-  for (int i = tid; i < 2 * (KC / 8) * (C::ROWS - C::NP); i += 256) {
+  for (int i = tid; i < 2 * C::NW * (KC / 8) * (C::ROWS - C::NP); i += 256) {
     const int bufk = i / (C::ROWS - C::NP), r = C::NP + i % (C::ROWS - C::NP);
     *reinterpret_cast<uint4*>(smem + C::SM_A + bufk * C::LBO_I + r * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
@@ -304,9 +311,19 @@ gconv_fast_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict_
         const int idx = base + u * 256;
         if (idx < NITEM) {
           const int pp = idx % C::NP, k8 = idx / C::NP;
-          *reinterpret_cast<uint4*>(abuf + k8 * C::LBO_I + pp * 16) =
-              make_uint4(umma::pack_bf16x2(v[u][0], v[u][1]), umma::pack_bf16x2(v[u][2], v[u][3]),
-                         umma::pack_bf16x2(v[u][4], v[u][5]), umma::pack_bf16x2(v[u][6], v[u][7]));
+          if constexpr (SPLIT) {
+            uint4 hi, lo;
+            umma::split_h2(v[u][0], v[u][1], hi.x, lo.x);
+            umma::split_h2(v[u][2], v[u][3], hi.y, lo.y);
+            umma::split_h2(v[u][4], v[u][5], hi.z, lo.z);
+            umma::split_h2(v[u][6], v[u][7], hi.w, lo.w);
+            *reinterpret_cast<uint4*>(abuf + k8 * C::LBO_I + pp * 16) = hi;
+            *reinterpret_cast<uint4*>(abuf + C::A_TERM + k8 * C::LBO_I + pp * 16) = lo;
+          } else {
+            *reinterpret_cast<uint4*>(abuf + k8 * C::LBO_I + pp * 16) =
+                make_uint4(umma::pack_bf16x2(v[u][0], v[u][1]), umma::pack_bf16x2(v[u][2], v[u][3]),
+                           umma::pack_bf16x2(v[u][4], v[u][5]), umma::pack_bf16x2(v[u][6], v[u][7]));
+          }
         }
       }
     }
@@ -328,8 +345,14 @@ gconv_fast_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict_
             const uint64_t ad = a0 + (uint64_t)(uint32_t)(C::P0 + off + t * 128);
 #pragma unroll
             for (int k = 0; k < KC / 16; ++k)
-              umma::mma_bf16_ss(tm + t * NOUT, ad + (uint64_t)(k * 2 * (C::LBO_I >> 4)),
+              umma::mma_bf16_ss(tm + t * C::NACC, ad + (uint64_t)(k * 2 * (C::LBO_I >> 4)),
                                 bd + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC, (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            if constexpr (SPLIT) {
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k)      // lo activations x the hi rows of the image
+                umma::mma_f16_ss(tm + t * C::NACC, ad + (uint64_t)((C::A_TERM >> 4) + k * 2 * (C::LBO_I >> 4)),
+                                 bd + (uint64_t)(k * 2 * (C::LBO_WT >> 4)), C::IDESC_LO, 1u);
+            }
           }
         }
         umma::mma_commit(&bar_free[buf]);
@@ -351,7 +374,13 @@ gconv_fast_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict_
 #pragma unroll
     for (int c0 = 0; c0 < NOUT; c0 += 16) {
       float v[16];
-      umma::tmem_ld16(lane_addr + t * NOUT + c0, v);
+      umma::tmem_ld16(lane_addr + t * C::NACC + c0, v);
+      if constexpr (SPLIT) {
+        float v2[16];
+        umma::tmem_ld16(lane_addr + t * C::NACC + NOUT + c0, v2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += v2[i];
+      }
       if (valid) {
 #pragma unroll
         for (int i = 0; i < 16; i += 4)
@@ -378,24 +407,53 @@ __global__ void pack_gconv_img_kernel(__nv_bfloat16* __restrict__ dst, const flo
   dst[((size_t)c * 9 + tap) * ((size_t)Co * KC) + (size_t)(k >> 3) * (Co * 8) + n * 8 + (k & 7)] =
       __float2bfloat16(Wt[((long long)ci * 9 + tap) * Co + n]);
 }
+// PRECISE: per channel chunk c, 9 tap images [2 Co x KC] fp16: rows [0, Co) = hi term, [Co, 2 Co) = lo term
+__global__ void pack_gconv_img_split_kernel(__half* __restrict__ dst, const float* __restrict__ Wt, int Ci, int Co, int KC) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Ci * 9 * Co) return;
+  const int k = (int)(i % KC);
+  long long r = i / KC;
+  const int n = (int)(r % Co); r /= Co;
+  const int tap = (int)(r % 9);
+  const int c = (int)(r / 9);
+  const int ci = c * KC + k;
+  const float w = Wt[((long long)ci * 9 + tap) * Co + n];
+  const __half h = __float2half_rn(w);
+  __half* base = dst + ((size_t)c * 9 + tap) * ((size_t)2 * Co * KC) + (size_t)(k >> 3) * (2 * Co * 8) + (k & 7);
+  base[n * 8] = h;
+  base[(Co + n) * 8] = __float2half_rn(w - __half2float(h));
+}
+cudaError_t launch_pack_gconv_img_split(__half* dst, const float* Wt, int Ci, int Co, int KC, cudaStream_t st) {
+  const long long n = (long long)Ci * 9 * Co;
+  pack_gconv_img_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dst, Wt, Ci, Co, KC);
+  return cudaGetLastError();
+}
 cudaError_t launch_pack_gconv_img(__nv_bfloat16* dst, const float* Wt, int Ci, int Co, int KC, cudaStream_t st) {
   const long long n = (long long)Ci * 9 * Co;
   pack_gconv_img_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dst, Wt, Ci, Co, KC);
   return cudaGetLastError();
 }
 
-template <int NOUT, int WIN_, int BR, int KC>
-static cudaError_t run_gconv(const float* in, const __nv_bfloat16* wimg, const float* bias, float* out, int B, int Ci,
+template <int NOUT, int WIN_, int BR, int KC, bool SPLIT = false>
+static cudaError_t run_gconv(const float* in, const void* wimg, const float* bias, float* out, int B, int Ci,
                              cudaStream_t st) {
-  using C = GConvCfg<NOUT, WIN_, BR, KC>;
+  using C = GConvCfg<NOUT, WIN_, BR, KC, SPLIT>;
   {   // per-device function attribute: set on every launch (cheap), a process-wide flag would miss other devices
-    cudaError_t e = cudaFuncSetAttribute(gconv_fast_kernel<NOUT, WIN_, BR, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gconv_fast_kernel<NOUT, WIN_, BR, KC, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C::SMEM);
     if (e != cudaSuccess) return e;
   }
   if (Ci % KC != 0) return cudaErrorInvalidValue;
-  gconv_fast_kernel<NOUT, WIN_, BR, KC><<<B * C::NB, 256, C::SMEM, st>>>(in, wimg, bias, out, Ci);
+  gconv_fast_kernel<NOUT, WIN_, BR, KC, SPLIT><<<B * C::NB, 256, C::SMEM, st>>>(in, wimg, bias, out, Ci);
   return cudaGetLastError();
+}
+
+int gconv_split_kc(int which) { return which == 0 ? 16 : 32; }
+cudaError_t launch_gconv_split(int which, const float* in, const __half* wimg, const float* bias, float* out, int B, int Ci,
+                               cudaStream_t st) {
+  if (which == 0) return run_gconv<128, 24, 4, 16, true>(in, wimg, bias, out, B, Ci, st);
+  if (which == 1) return run_gconv<32, 48, 2, 32, true>(in, wimg, bias, out, B, Ci, st);
+  return run_gconv<16, 96, 2, 32, true>(in, wimg, bias, out, B, Ci, st);
 }
 
 int gconv_fast_kc(int which) { return which == 0 ? 32 : 64; }

@@ -126,6 +126,11 @@ bool gconv_fast_supported(int which, int Ci, int H, int W, int Co);
 cudaError_t launch_pack_gconv_img(__nv_bfloat16* dst, const float* Wt, int Ci, int Co, int KC, cudaStream_t st);
 cudaError_t launch_gconv_fast(int which, const float* in, const __nv_bfloat16* wimg, const float* bias, float* out, int B,
                               int Ci, cudaStream_t st);
+// PRECISE: fp16 hi+lo operand pairs (fp32-accurate); images from launch_pack_gconv_img_split with KC = gconv_split_kc(which)
+int gconv_split_kc(int which);
+cudaError_t launch_pack_gconv_img_split(__half* dst, const float* Wt, int Ci, int Co, int KC, cudaStream_t st);
+cudaError_t launch_gconv_split(int which, const float* in, const __half* wimg, const float* bias, float* out, int B, int Ci,
+                               cudaStream_t st);
 
 // ---------------------------------------------------------------- swin_exact.cu
 // with_mlp = 0 stops after x1 = shortcut + proj(attn) (the FFN half then runs in fast_mlp.cu)

@@ -99,3 +99,23 @@ def test_cost_volume_on_tensor_cores_matches_oracle():
     assert (taps["corr"].cpu() - st["corr"]).abs().max().item() <= 5e-7          # cosines in [-1, 1]
     assert torch.equal(taps["classes"].cpu().long(), st["classes"])
     assert (taps["embed"].cpu() - st["embed"]).abs().max().item() <= 2e-5 * max(1.0, st["embed"].abs().max().item())
+
+
+@pytest.mark.parametrize("case", [(vitb(), 2, 5), (vitl(), 1, 7)])
+def test_precise_front_end_stages(case):
+    """PRECISE front end: the 7x7 embedding and the three 3x3 guidance projections (tcgen05, hi+lo operand pairs) are
+    fp32-accurate against the oracle's stage tensors."""
+    cfg, B, T = case
+    sd = make_state_dict(cfg, 8)
+    img, text, g = make_inputs(cfg, B, T, 8, same_text=False)
+    _, st = aggregator_forward(sd, cfg.oracle_cfg(), img, text, g, return_stages=True)
+    m = Aggregator(**cfg.ctor_kwargs(), precision="precise:prep")
+    m.load_state_dict(sd, strict=False)
+    names = ["embed", "app_guidance", "dec_guidance0", "dec_guidance1", "text_guidance"]
+    _, taps = m.cuda()(img.cuda(), text.cuda(), [x.cuda() for x in g], taps=names)
+    for n in names:
+        got, r = taps[n].cpu(), st[n]
+        if n.startswith("dec_guidance"):
+            r = r.permute(0, 2, 3, 1).reshape(got.shape)            # oracle keeps NCHW, kernels NHWC
+        err = (got - r).abs().max().item()
+        assert err <= 2e-5 * max(1.0, r.abs().max().item()), (n, err)
