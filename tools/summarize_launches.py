@@ -25,7 +25,7 @@ def main(path):
         except ValueError:
             pass
     ids = sorted(L)
-    starts = [i for i in ids if "normalize_img" in L[i]["name"]]
+    starts = [i for i in ids if "normalize_img" in L[i]["name"] or "inv_norm_pixels" in L[i]["name"]]
     last, end = starts[-1], ids[-1] + 1
     if len(starts) > 1 and end - last < last - starts[-2]:      # the capture stopped inside the last forward: use the one before
         last, end = starts[-2], starts[-1]
