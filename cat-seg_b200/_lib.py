@@ -36,6 +36,13 @@ class CatsegTaps(C.Structure):
     ]
 
 
+class ClipDenseWeights(C.Structure):
+    _fields_ = [("width", C.c_int32), ("out_dim", C.c_int32)] + [(n, C.c_void_p) for n in (
+        "ln_1_weight", "ln_1_bias", "v_proj_weight", "v_proj_bias", "out_proj_weight", "out_proj_bias",
+        "ln_2_weight", "ln_2_bias", "c_fc_weight", "c_fc_bias", "c_proj_weight", "c_proj_bias",
+        "ln_post_weight", "ln_post_bias", "proj")]
+
+
 STAGES = ("prep", "embed", "swin", "class", "decoder", "swin_mlp")
 FAST_BITS = {"swin_mlp": 1, "swin_attn": 2, "class": 4, "decoder": 8, "prep": 16}
 
@@ -88,6 +95,9 @@ _SIGS = [
     ("catseg_guidance_upsample", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                            C.c_int, C.c_void_p]),
     ("catseg_strip_cls_nchw", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("catseg_clip_dense_workspace_bytes", C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("catseg_clip_dense_last_block", C.c_int, [C.POINTER(ClipDenseWeights), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 ]
 # int (*catseg_allreduce_fn)(void* ctx, float* buf, size_t count, catseg_stream stream)
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)

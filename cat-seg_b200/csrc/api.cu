@@ -1206,6 +1206,42 @@ extern "C" int catseg_strip_cls_nchw(const float* feats, float* out, int B, int 
   return CATSEG_OK;
 }
 
+extern "C" size_t catseg_clip_dense_workspace_bytes(int L, int N, int width, int prompt) {
+  if (L <= 0 || N <= 0 || width <= 0 || prompt < 0 || prompt >= L) return 0;
+  return clip_dense_workspace_floats(L, N, width, prompt) * sizeof(float);
+}
+
+extern "C" int catseg_clip_dense_last_block(const catseg_clip_dense_weights* w, const float* x, int L, int N, int prompt,
+                                            float* block_out, float* feats_out, void* workspace, size_t workspace_bytes,
+                                            catseg_stream stream) {
+  auto bad = [](const char* m) { g_create_error = m; return CATSEG_ERR_INVALID; };
+  if (!w || !x || !workspace) return bad("clip_dense: null pointer");
+  if (!block_out && !feats_out) return bad("clip_dense: no output requested");
+  if (L <= 0 || N <= 0 || prompt < 0 || prompt >= L) return bad("clip_dense: bad L / N / prompt");
+  if (w->width <= 0 || w->width % 8 || (feats_out && w->out_dim <= 0)) return bad("clip_dense: width must be a positive multiple of 8");
+  if ((long long)(L - prompt) * N > 0x7fffffffLL / 4096) return bad("clip_dense: too many tokens");
+  if (!w->ln_1_weight || !w->ln_1_bias || !w->v_proj_weight || !w->v_proj_bias || !w->out_proj_weight || !w->out_proj_bias ||
+      !w->ln_2_weight || !w->ln_2_bias || !w->c_fc_weight || !w->c_fc_bias || !w->c_proj_weight || !w->c_proj_bias ||
+      (feats_out && (!w->ln_post_weight || !w->ln_post_bias || !w->proj)))
+    return bad("clip_dense: missing parameter");
+  if (workspace_bytes < catseg_clip_dense_workspace_bytes(L, N, w->width, prompt)) {
+    g_create_error = "clip_dense: workspace too small";
+    return CATSEG_ERR_WORKSPACE;
+  }
+  ClipDenseW k{};
+  k.width = w->width; k.out_dim = w->out_dim;
+  k.ln1_g = w->ln_1_weight; k.ln1_b = w->ln_1_bias;
+  k.v_w = w->v_proj_weight; k.v_b = w->v_proj_bias;
+  k.out_proj_w = w->out_proj_weight; k.out_proj_b = w->out_proj_bias;
+  k.ln2_g = w->ln_2_weight; k.ln2_b = w->ln_2_bias;
+  k.c_fc_w = w->c_fc_weight; k.c_fc_b = w->c_fc_bias;
+  k.c_proj_w = w->c_proj_weight; k.c_proj_b = w->c_proj_bias;
+  k.ln_post_g = w->ln_post_weight; k.ln_post_b = w->ln_post_bias; k.proj = w->proj;
+  cudaError_t e = run_clip_dense_block(k, x, L, N, prompt, block_out, feats_out, reinterpret_cast<float*>(workspace), (cudaStream_t)stream);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return CATSEG_ERR_CUDA; }
+  return CATSEG_OK;
+}
+
 extern "C" int catseg_argmax(const float* scores, int T, int64_t npix, int32_t* labels_out, catseg_stream stream) {
   return catseg_argmax_batched(scores, 1, T, npix, labels_out, stream);
 }

@@ -126,8 +126,8 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gemm_split_kernel(GemmSplitPara
             if (p.col_scale != nullptr) x *= __ldg(p.col_scale + (long long)b * p.cs_batch + n);
             if (p.bias != nullptr) x += __ldg(p.bias + n);
             if (p.act == 1) x = fmaxf(x, 0.0f);
-            else if (p.act == 2) x = x / (1.0f + __expf(-1.702f * x));           // QuickGELU: x * sigmoid(1.702 x)
-            if (p.residual != nullptr) x += __ldg(p.residual + (long long)b * p.r_batch + (long long)m * p.r_row + n);
+            else if (p.act == 2) x = x / (1.0f + expf(-1.702f * x));           // QuickGELU: x * sigmoid(1.702 x)
+            if (p.residual != nullptr) x += __ldg(p.residual + (long long)b * p.r_batch + (long long)(p.r_mod > 0 ? m % p.r_mod : m) * p.r_row + n);
             v[i] = x;
             rmax = fmaxf(rmax, x);
           }

@@ -110,10 +110,30 @@ struct GemmSplitParams {
   const float* row_scale; long long rs_batch;        // [batch][rows of A]
   const float* col_scale; long long cs_batch;        // [batch][N]
   const float* residual; long long r_row, r_batch;   // added after the activation; r_row = 0 broadcasts one row
+  int r_mod;                                         // > 0: the residual row is m % r_mod (a block of rows broadcast cyclically)
   int act;                                           // 0 none, 1 ReLU, 2 QuickGELU
   float* row_max;                                    // [batch][M][2 * ceil(N / 128)] partial maxima over 64-column spans
 };
 cudaError_t launch_gemm_split(const GemmSplitParams& p, cudaStream_t st);
+
+// ---------------------------------------------------------------- clip_dense.cu
+// CLIP ResidualAttentionBlock.forward_dense + ln_post + proj (model_vpt.py:219-240, 300-312); all fp32 device pointers in the
+// reference's own parameter layouts
+struct ClipDenseW {
+  int width, out_dim;
+  const float *ln1_g, *ln1_b;
+  const float *v_w, *v_b;                  // [width][width], [width]: the v third of the attention input projection
+  const float *out_proj_w, *out_proj_b;    // [width][width], [width]
+  const float *ln2_g, *ln2_b;
+  const float *c_fc_w, *c_fc_b;            // [4 width][width], [4 width]
+  const float *c_proj_w, *c_proj_b;        // [width][4 width], [width]
+  const float *ln_post_g, *ln_post_b;
+  const float* proj;                       // [width][out_dim]
+};
+size_t clip_dense_workspace_floats(int L, int N, int D, int prompt);
+// x [L][N][width]; block_out [L - prompt][N][width] (optional); feats_out [N][L - prompt][out_dim] (optional)
+cudaError_t run_clip_dense_block(const ClipDenseW& w, const float* x, int L, int N, int prompt, float* block_out,
+                                 float* feats_out, float* ws, cudaStream_t st);
 
 // ---------------------------------------------------------------- fast_prep.cu
 // 7x7 cost embedding for P = 1 on a 24x24 grid; bimg = 14 images packed by launch_pack_embed_img from Wt [49][128]

@@ -142,3 +142,31 @@ def make_pyramid_inputs(width: int, B: int, seed: int = 0, grid: int = 24, feat_
     w2 = uni((width, 128, 4, 4), (1.0 / (128 * 16)) ** 0.5)
     b2 = uni((128,), (1.0 / (128 * 16)) ** 0.5)
     return clip, la, lb, w1, b1, w2, b2
+
+
+CLIP_DENSE_KEYS = ("ln_1.weight", "ln_1.bias", "attn.q_proj_weight", "attn.k_proj_weight", "attn.v_proj_weight", "attn.in_proj_bias", "attn.out_proj.weight",
+                   "attn.out_proj.bias", "ln_2.weight", "ln_2.bias", "mlp.c_fc.weight", "mlp.c_fc.bias",
+                   "mlp.c_proj.weight", "mlp.c_proj.bias")
+
+
+def make_clip_dense_inputs(width: int, L: int, N: int, out_dim: int, seed: int = 0):
+    """Seeded synthetic input and parameters of the CLIP dense last block (model_vpt.py:186-240, 283-284): x [L, N, width]
+    (the input of the last resblock, LND) and a dict with the resblock's own state_dict keys (the fork splits in_proj_weight into q/k/v_proj_weight, :169-178) plus ``ln_post.*`` and ``proj``.
+    Magnitudes follow CLIP's initialisation (model_vpt.py:399-419): attn std width^-0.5, fc std (2 width)^-0.5, proj std
+    width^-0.5; LayerNorm affine is randomised (the defaults 1 / 0 would hide a swapped or missing affine)."""
+    g = torch.Generator().manual_seed(9876 + seed)
+    def nrm(shape, std):
+        return torch.randn(shape, generator=g) * std
+    sd = {
+        "ln_1.weight": 1.0 + 0.1 * torch.randn(width, generator=g), "ln_1.bias": 0.1 * torch.randn(width, generator=g),
+        "attn.q_proj_weight": nrm((width, width), width ** -0.5), "attn.k_proj_weight": nrm((width, width), width ** -0.5),
+        "attn.v_proj_weight": nrm((width, width), width ** -0.5), "attn.in_proj_bias": nrm((3 * width,), 0.02),
+        "attn.out_proj.weight": nrm((width, width), width ** -0.5), "attn.out_proj.bias": nrm((width,), 0.02),
+        "ln_2.weight": 1.0 + 0.1 * torch.randn(width, generator=g), "ln_2.bias": 0.1 * torch.randn(width, generator=g),
+        "mlp.c_fc.weight": nrm((4 * width, width), (2 * width) ** -0.5), "mlp.c_fc.bias": nrm((4 * width,), 0.02),
+        "mlp.c_proj.weight": nrm((width, 4 * width), width ** -0.5), "mlp.c_proj.bias": nrm((width,), 0.02),
+        "ln_post.weight": 1.0 + 0.1 * torch.randn(width, generator=g), "ln_post.bias": 0.1 * torch.randn(width, generator=g),
+        "proj": nrm((width, out_dim), width ** -0.5),
+    }
+    x = torch.randn(L, N, width, generator=g)
+    return x, sd

@@ -187,6 +187,35 @@ int catseg_guidance_upsample(const float* tokens, const float* weight, const flo
                              int cout, int kernel, int grid, catseg_stream stream);
 int catseg_strip_cls_nchw(const float* feats, float* out, int B, int C, int grid, catseg_stream stream);
 
+/* CLIP dense last block, the producer of img_feats on the other side of the boundary:
+ * ResidualAttentionBlock.forward_dense (cat_seg/third_party/model_vpt.py:219-240) and the dense branch of
+ * VisualTransformer.forward after the transformer (:300-312: permute, ln_post, @ proj).
+ *   weights: device fp32 pointers in the reference's own parameter layouts, named after the state_dict keys
+ *            (transformer.resblocks.<last>.{ln_1,attn.v_proj_weight,attn.in_proj_bias,attn.out_proj,ln_2,mlp.c_fc,mlp.c_proj},
+ *            ln_post, proj); of the attention input projection only the v third is read (the reference computes q and k and
+ *            discards them, :231-233): v_proj_weight = attn.v_proj_weight (:177; rows [2 width, 3 width) of a stock CLIP
+ *            in_proj_weight), v_proj_bias = attn.in_proj_bias + 2 width.
+ *   x          [L][N][width] fp32: the input of the last resblock (LND).
+ *   prompt     number of VPT prompt tokens after CLS that the block drops (:238-239; 0 in the shipped configs).
+ *   block_out  optional [L - prompt][N][width]: forward_dense's return value.
+ *   feats_out  optional [N][L - prompt][out_dim]: ln_post + proj of it = `clip_features` of cat_seg_model.py:176.
+ * All GEMMs run on tcgen05 with hi + lo fp16 operand pairs (fp32-accurate).  Stateless: no handle. */
+typedef struct catseg_clip_dense_weights {
+  int32_t width, out_dim;
+  const float *ln_1_weight, *ln_1_bias;
+  const float *v_proj_weight, *v_proj_bias;       /* [width][width], [width] */
+  const float *out_proj_weight, *out_proj_bias;   /* [width][width], [width] */
+  const float *ln_2_weight, *ln_2_bias;
+  const float *c_fc_weight, *c_fc_bias;           /* [4 width][width], [4 width] */
+  const float *c_proj_weight, *c_proj_bias;       /* [width][4 width], [width] */
+  const float *ln_post_weight, *ln_post_bias;     /* may be NULL when feats_out is NULL */
+  const float* proj;                              /* [width][out_dim] */
+} catseg_clip_dense_weights;
+size_t catseg_clip_dense_workspace_bytes(int L, int N, int width, int prompt);
+int catseg_clip_dense_last_block(const catseg_clip_dense_weights* w, const float* x, int L, int N, int prompt,
+                                 float* block_out, float* feats_out, void* workspace, size_t workspace_bytes,
+                                 catseg_stream stream);
+
 /* Library identity, e.g. "catseg_b200 0.1 sm_100a". */
 const char* catseg_version(void);
 

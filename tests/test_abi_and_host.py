@@ -128,3 +128,24 @@ def test_committed_launch_summary_is_reproducible():
     assert r.stdout.strip() == open(txt).read().strip()
     # the kernels named in the summary are the ones the library exports today (decoder shapes included)
     assert "swin_attn_fast_kernel" in r.stdout and "band_conv_kernel<64, 64, 64, 0, 0, 48, 12, 0, 1>" in r.stdout
+
+
+def test_clip_dense_module_loads_clip_visual_state_dict():
+    """DenseLastBlock keeps the reference's parameter names (model_vpt.py:169-200, 283-284); a stock CLIP in_proj_weight is
+    split into q/k/v_proj_weight the way the fork does at load time (:523)."""
+    from cat_seg_b200.clip_dense import DenseLastBlock
+    from cat_seg_b200.synth import CLIP_DENSE_KEYS, make_clip_dense_inputs
+    _, sd = make_clip_dense_inputs(64, 5, 1, 32, 0)
+    m = DenseLastBlock(64, 32)
+    assert sorted(m.state_dict()) == sorted(list(CLIP_DENSE_KEYS) + ["ln_post.weight", "ln_post.bias", "proj"])
+    m.load_state_dict(sd, strict=True)
+    visual = {f"transformer.resblocks.11.{k}": v for k, v in sd.items() if k in CLIP_DENSE_KEYS and "_proj_weight" not in k}
+    visual["transformer.resblocks.11.attn.in_proj_weight"] = torch.cat(
+        [sd["attn.q_proj_weight"], sd["attn.k_proj_weight"], sd["attn.v_proj_weight"]], dim=0)
+    visual["transformer.resblocks.3.ln_1.weight"] = torch.zeros(64)
+    visual.update({"ln_post.weight": sd["ln_post.weight"], "ln_post.bias": sd["ln_post.bias"], "proj": sd["proj"]})
+    m2 = DenseLastBlock.from_clip_visual(visual)
+    for k, v in m.state_dict().items():
+        assert torch.equal(m2.state_dict()[k], v), k
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(5, 1, 64))                      # CPU tensor: the product path has no fallback

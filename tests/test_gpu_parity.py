@@ -249,3 +249,55 @@ def test_guidance_pyramid_rejects_bad_arguments():
         strip_cls_nchw(torch.zeros(1, 500, 8, device="cuda"))
     with pytest.raises(ValueError):
         upsample_tokens(torch.zeros(577, 1, 8, device="cuda"), torch.zeros(9, 4, 2, 2), torch.zeros(4))
+
+
+# ---- CLIP dense last block: C-ABI kernels vs the oracle and the reference's golden
+@pytest.mark.parametrize("name", ["w64_L10_N2", "w64_L12_N3_prompt2", "w768_L577_N1"])
+def test_clip_dense_matches_reference_golden(name):
+    import os
+    from cat_seg_b200.clip_dense import DenseLastBlock
+    from cat_seg_b200.synth import make_clip_dense_inputs
+    from oracle.clip_dense_oracle import dense_last_block
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "clip_dense.npz"))
+    width, heads, L, N, od, prompt, seed = (int(v) for v in gold[f"{name}/cfg"])
+    x, sd = make_clip_dense_inputs(width, L, N, od, seed)
+    m = DenseLastBlock(width, od, prompt_length=prompt)
+    m.load_state_dict(sd, strict=True)                                # the reference's own parameter names
+    block_out, feats = m.cuda()(x.cuda())
+    ref_v, ref_f = dense_last_block(sd, x, prompt, double=True)       # float64-accumulated oracle
+    # hi+lo fp16 operand pairs (~2^-21 per product) accumulated by the tensor core in fp32 over up to 3 x 4 width terms: the
+    # stated tolerance is rel-L2 <= 2e-5, max-abs <= 5e-5 of the output scale (measured at width 768: 7.9e-6 rel-L2; the
+    # reference's own fp32-vs-fp64 difference is ~5e-7)
+    for got, ref, key in ((block_out.cpu(), ref_v, "block_out"), (feats.cpu(), ref_f, "feats")):
+        assert got.shape == ref.shape
+        err = (got - ref).abs().max().item()
+        assert err <= 5e-5 * max(1.0, ref.abs().max().item()), (key, err)
+        assert rel_l2(got, ref) <= 2e-5, (key, rel_l2(got, ref))
+        np.testing.assert_allclose(got.contiguous().flatten()[::53].numpy(), gold[f"{name}/{key}/sub"], rtol=0,
+                                   atol=6e-5 * max(1.0, ref.abs().max().item()))
+
+
+def test_clip_dense_vitl_batch_properties():
+    """ViT-L/14 size (width 1024, 577 tokens, 4 images): token-wise independence (any subset of images gives the same rows,
+    bit for bit) and agreement with the oracle on a sub-sampled set of tokens."""
+    from cat_seg_b200.clip_dense import DenseLastBlock
+    from cat_seg_b200.synth import make_clip_dense_inputs
+    from oracle.clip_dense_oracle import dense_last_block
+    x, sd = make_clip_dense_inputs(1024, 577, 4, 768, 3)
+    m = DenseLastBlock(1024, 768)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    _, feats = m(x.cuda(), want_block_out=False)
+    _, feats1 = m(x[:, 1:2].contiguous().cuda(), want_block_out=False)
+    assert torch.equal(feats[1:2], feats1)
+    _, ref_f = dense_last_block(sd, x[:, 2:3], 0)
+    assert (feats[2:3].cpu() - ref_f).abs().max().item() <= 1e-4 * max(1.0, ref_f.abs().max().item())
+
+
+def test_clip_dense_rejects_bad_arguments():
+    from cat_seg_b200.clip_dense import DenseLastBlock
+    m = DenseLastBlock(64, 32)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(10, 2, 64))                                     # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        m.cuda()(torch.zeros(10, 2, 48, device="cuda"))

@@ -103,3 +103,48 @@ def test_guidance_oracle_matches_live_conv_transpose():
         x = tokens_to_nchw(tok)
         np.testing.assert_allclose(conv_transpose_stride_eq_kernel(x, w, b).numpy(),
                                    F.conv_transpose2d(x, w, b, stride=k).numpy(), rtol=0, atol=2e-5)
+
+
+# ---- CLIP dense last block (model_vpt.py:219-240, 300-312)
+CLIP_DENSE_CASES = ("w64_L10_N2", "w64_L12_N3_prompt2", "w768_L577_N1")
+
+
+@pytest.mark.parametrize("name", CLIP_DENSE_CASES)
+def test_clip_dense_oracle_matches_reference_golden(name):
+    import os
+    from cat_seg_b200.synth import make_clip_dense_inputs
+    from oracle.clip_dense_oracle import dense_last_block
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "clip_dense.npz"))
+    width, heads, L, N, od, prompt, seed = (int(v) for v in gold[f"{name}/cfg"])
+    x, sd = make_clip_dense_inputs(width, L, N, od, seed)
+    out = dict(zip(("block_out", "feats"), dense_last_block(sd, x, prompt)))
+    for k, t in out.items():
+        assert tuple(t.shape) == tuple(gold[f"{name}/{k}/shape"])
+        # same fp32 ops as the reference classes up to BLAS summation order
+        np.testing.assert_allclose(t.contiguous().flatten()[::53].numpy(), gold[f"{name}/{k}/sub"], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(fingerprint(t), gold[f"{name}/{k}/fp"], rtol=1e-5)
+
+
+def test_clip_dense_oracle_matches_live_reference():
+    """With /root/reference present (build container) the unmodified model_vpt.py classes are run live."""
+    import importlib.util
+    import os
+    ref_path = "/root/reference/cat_seg/third_party/model_vpt.py"
+    if not os.path.exists(ref_path):
+        pytest.skip("reference tree not present (GPU box)")
+    from cat_seg_b200.synth import CLIP_DENSE_KEYS, make_clip_dense_inputs
+    from oracle.clip_dense_oracle import dense_last_block
+    spec = importlib.util.spec_from_file_location("ref_model_vpt_live", ref_path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    x, sd = make_clip_dense_inputs(96, 17, 2, 24, 5)
+    blk = ref.ResidualAttentionBlock(96, 4).eval()
+    blk.load_state_dict({k: sd[k] for k in CLIP_DENSE_KEYS}, strict=True)
+    ln_post = ref.LayerNorm(96)
+    ln_post.load_state_dict({"weight": sd["ln_post.weight"], "bias": sd["ln_post.bias"]})
+    for prompt in (0, 3):
+        with torch.no_grad():
+            v = blk.forward_dense(x, prompt)
+            f = ln_post(v.permute(1, 0, 2)) @ sd["proj"]
+        ov, of = dense_last_block(sd, x, prompt)
+        assert (ov - v).abs().max().item() <= 5e-6 and (of - f).abs().max().item() <= 5e-6
