@@ -85,6 +85,15 @@ _SIGS = [
      [C.c_size_t, C.c_int, C.c_int, C.POINTER(CatsegTaps), C.c_void_p]),
     ("catseg_forward_class_sharded", C.c_int, [C.c_void_p] + [C.c_void_p] * 8 +
      [C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("catseg_exchange_buffer_bytes", C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    ("catseg_forward_class_sharded_a2a", C.c_int, [C.c_void_p] + [C.c_void_p] * 8 +
+     [C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t, C.c_void_p,
+      C.c_void_p, C.c_void_p]),
+    ("catseg_peer_alloc", C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    ("catseg_peer_free", C.c_int, [C.c_void_p]),
+    ("catseg_peer_export", C.c_int, [C.c_void_p, C.c_char_p]),
+    ("catseg_peer_open", C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    ("catseg_peer_close", C.c_int, [C.c_void_p]),
     ("catseg_set_profiling", C.c_int, [C.c_void_p, C.c_int]),
     ("catseg_stage_times", C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),
     ("catseg_last_launch_count", C.c_int, [C.c_void_p]),
@@ -101,6 +110,8 @@ _SIGS = [
 ]
 # int (*catseg_allreduce_fn)(void* ctx, float* buf, size_t count, catseg_stream stream)
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+# int (*catseg_barrier_fn)(void* ctx, catseg_stream stream)
+BARRIER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
 EXPORTED_SYMBOLS = tuple(s[0] for s in _SIGS)
 
 

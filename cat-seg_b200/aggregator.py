@@ -74,6 +74,7 @@ class Aggregator(nn.Module):
         self._handle_device: Optional[torch.device] = None
         self._synced: Dict[str, tuple] = {}
         self._workspace: Optional[torch.Tensor] = None
+        self._peer = None          # PeerExchange of the all-to-all class split
         self._vocab: Optional[torch.Tensor] = None        # [T,P,C] class embeddings of the current vocabulary
         self._vocab_pushed = False
 
@@ -248,18 +249,26 @@ class Aggregator(nn.Module):
             return logits, out
 
     def forward_class_sharded(self, img_feats: torch.Tensor, text_feats: torch.Tensor,
-                              appearance_guidance: Sequence[torch.Tensor], group=None) -> torch.Tensor:
+                              appearance_guidance: Sequence[torch.Tensor], group=None, exchange: str = "allreduce",
+                              gather: bool = True) -> torch.Tensor:
         """Class-sharded forward over a torch.distributed process group (NCCL): every rank passes the SAME inputs,
-        computes the kept classes [r*Te/world, (r+1)*Te/world) and receives the full [B,T,4H,4W] logits.  The only
-        exchange inside the path is one all-reduce (sum) of the linear-attention state per class layer
-        (model.py:282-283), issued from the library through a callback on the current stream; the
-        local logit planes are all-gathered and scattered to their class ids afterwards."""
+        computes the kept classes [r*Te/world, (r+1)*Te/world) and receives the full [B,T,4H,4W] logits.
+        exchange="allreduce": activations stay class-sharded; the only exchange inside the path is one all-reduce (sum) of
+        the linear-attention state per class layer (model.py:282-283; SURVEY.md 8e "cheaper equivalent"), issued from the
+        library through a callback on the current stream.
+        exchange="alltoall": north_star's prescription: the residual stream is transposed class-sharded
+        <-> pixel-sharded around each class layer by kernels that store straight into the peers' buffers over NVLink
+        (CUDA IPC mappings, ``PeerExchange``); the callback is a one-element all-reduce that orders those stores.
+        The local logit planes are all-gathered and scattered to their class ids afterwards (gather=False returns the
+        compact local planes and the kept-class list instead)."""
         import torch.distributed as dist
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         B, T, H, W = self._check(img_feats, text_feats, appearance_guidance)
         Te = self.kept_classes(T)
         if Te % world:
             raise RuntimeError(f"kept classes ({Te}) must be a multiple of the shard group size ({world})")
+        if exchange not in ("allreduce", "alltoall"):
+            raise ValueError(f"exchange must be 'allreduce' or 'alltoall', got {exchange!r}")
         lib = _lib.load()
         dev = img_feats.device
         with torch.cuda.device(dev):
@@ -275,25 +284,46 @@ class Aggregator(nn.Module):
             local = torch.empty(B, Te // world, 4 * H, 4 * W, dtype=torch.float32, device=dev)
             kept = torch.empty(B, Te, dtype=torch.int32, device=dev)
             errors = []
-
-            def _allreduce(_ctx, buf, count, _stream):      # called by the library between class_state and class_apply
-                try:
-                    off = int(buf) - ws.data_ptr()
-                    dist.all_reduce(ws[off:off + 4 * count].view(torch.float32), op=dist.ReduceOp.SUM, group=group)
-                    return 0
-                except Exception as e:                      # never let an exception cross the C ABI
-                    errors.append(e)
-                    return 1
-
-            cb = _lib.ALLREDUCE_FN(_allreduce)
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            rc = lib.catseg_forward_class_sharded(
-                self._handle, *[C.c_void_p(t.data_ptr()) for t in (img, text, g[0], g[1], g[2], local, kept)],
-                C.c_void_p(ws.data_ptr()), ws.numel(), B, T, rank, world, C.cast(cb, C.c_void_p), None, stream)
+            ptrs = [C.c_void_p(t.data_ptr()) for t in (img, text, g[0], g[1], g[2], local, kept)]
+
+            if exchange == "allreduce":
+                def _allreduce(_ctx, buf, count, _stream):      # called by the library between class_state and class_apply
+                    try:
+                        off = int(buf) - ws.data_ptr()
+                        dist.all_reduce(ws[off:off + 4 * count].view(torch.float32), op=dist.ReduceOp.SUM, group=group)
+                        return 0
+                    except Exception as e:                      # never let an exception cross the C ABI
+                        errors.append(e)
+                        return 1
+
+                cb = _lib.ALLREDUCE_FN(_allreduce)
+                rc = lib.catseg_forward_class_sharded(self._handle, *ptrs, C.c_void_p(ws.data_ptr()), ws.numel(), B, T, rank, world,
+                                                      C.cast(cb, C.c_void_p), None, stream)
+            else:
+                nbytes = lib.catseg_exchange_buffer_bytes(self._handle, B, T, world)
+                if self._peer is None or self._peer.nbytes < nbytes or self._peer.group is not group:
+                    self._peer = None
+                    self._peer = PeerExchange(nbytes, dev, group)
+                peer = self._peer
+
+                def _barrier(_ctx, _stream):                    # orders the peer stores of the transposition kernels
+                    try:
+                        dist.all_reduce(peer.flag, group=group)
+                        return 0
+                    except Exception as e:
+                        errors.append(e)
+                        return 1
+
+                cb = _lib.BARRIER_FN(_barrier)
+                rc = lib.catseg_forward_class_sharded_a2a(self._handle, *ptrs, C.c_void_p(ws.data_ptr()), ws.numel(), B, T, rank, world,
+                                                          peer.xb, peer.pb, peer.nbytes, C.cast(cb, C.c_void_p), None, stream)
             if errors:
                 raise errors[0]
             if rc != 0:
                 raise self._lib_error(rc)
+            if not gather:
+                return local, kept
             gathered = torch.empty(world, *local.shape, dtype=torch.float32, device=dev)
             dist.all_gather_into_tensor(gathered, local, group=group)
             return assemble_class_sharded(gathered, kept, T)
@@ -350,6 +380,62 @@ class Aggregator(nn.Module):
                 _lib._LIB.catseg_destroy(self._handle)
         except Exception:
             pass
+
+
+class PeerExchange:
+    """Two peer-visible buffers per rank (class-sharded X, pixel-sharded P) for the all-to-all class split: allocated by the
+    library with cudaMalloc, published as CUDA IPC handles over the process group, mapped on every other rank of the node.
+    ``xb`` / ``pb`` are the ctypes pointer arrays catseg_forward_class_sharded_a2a takes (entry r = rank r's buffer)."""
+
+    def __init__(self, nbytes: int, device: torch.device, group=None):
+        import torch.distributed as dist
+        lib = _lib.load()
+        self.nbytes, self.group, self.device = int(nbytes), group, device
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        self._lib, self._own, self._opened = lib, [], []
+        handles = []
+        with torch.cuda.device(device):
+            for _ in range(2):
+                p = C.c_void_p()
+                if lib.catseg_peer_alloc(self.nbytes, C.byref(p)) != 0:
+                    raise RuntimeError("catseg_peer_alloc failed: " + lib.catseg_last_error(None).decode())
+                self._own.append(p.value)
+                hbuf = C.create_string_buffer(64)
+                if lib.catseg_peer_export(C.c_void_p(p.value), hbuf) != 0:
+                    raise RuntimeError("catseg_peer_export failed: " + lib.catseg_last_error(None).decode())
+                handles.append(hbuf.raw)
+            everyone = [None] * world
+            dist.all_gather_object(everyone, handles, group=group)
+            self.xb, self.pb = (C.c_void_p * world)(), (C.c_void_p * world)()
+            for r in range(world):
+                for k, arr in enumerate((self.xb, self.pb)):
+                    if r == rank:
+                        arr[r] = self._own[k]
+                    else:
+                        q = C.c_void_p()
+                        if lib.catseg_peer_open(everyone[r][k], C.byref(q)) != 0:
+                            raise RuntimeError(f"catseg_peer_open (rank {r}) failed: " + lib.catseg_last_error(None).decode())
+                        self._opened.append(q.value)
+                        arr[r] = q.value
+            self.flag = torch.zeros(1, dtype=torch.float32, device=device)
+
+    def close(self):
+        if self._lib is None:
+            return
+        import torch.distributed as dist
+        try:
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.device(self.device):
+                for q in self._opened:
+                    self._lib.catseg_peer_close(C.c_void_p(q))
+                self._opened = []
+                if dist.is_initialized():
+                    dist.barrier(self.group)          # nobody frees while a peer still has the mapping open
+                for p in self._own:
+                    self._lib.catseg_peer_free(C.c_void_p(p))
+                self._own = []
+        finally:
+            self._lib = None
 
 
 def assemble_class_sharded(gathered: torch.Tensor, kept: torch.Tensor, T: int) -> torch.Tensor:

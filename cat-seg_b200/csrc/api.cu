@@ -853,9 +853,18 @@ extern "C" int catseg_set_vocabulary(catseg_handle* h, const float* text_feats, 
 // The forward proper.  shard_world == 1: logits is [B,T,4H,4W].  shard_world > 1 (class-sharded): logits is the compact
 // local buffer [B, Te/world, 4H, 4W], every per-(image, class) stage runs on this rank's slice of the kept classes and the
 // linear-attention state is summed over the group through `allreduce` between the state and apply kernels.
+// Exchange step of the class-sharded mode.  allreduce: activations stay class-sharded, the linear-attention state is summed.
+// a2a (north_star's prescription): activations are transposed class-sharded <-> pixel-sharded around each
+// class layer by kernels that store straight into the peers' buffers over NVLink (xb / pb: every rank's buffers, indexed by
+// rank, opened through CUDA IPC by the host); `barrier` orders those peer stores against their consumers.
+struct ShardExchange {
+  catseg_allreduce_fn allreduce; void* ar_ctx;
+  float* const* xb; float* const* pb; size_t buf_bytes; catseg_barrier_fn barrier; void* bar_ctx;
+};
+
 static int forward_impl(catseg_handle* h, const float* img, const float* text, const float* g0, const float* g1,
                         const float* g2, float* logits, void* workspace, size_t workspace_bytes, int B, int T,
-                        const catseg_taps* taps, int shard_rank, int shard_world, catseg_allreduce_fn allreduce, void* ar_ctx,
+                        const catseg_taps* taps, int shard_rank, int shard_world, const ShardExchange* xc,
                         int32_t* kept_out, catseg_stream stream) {
   if (!h) return CATSEG_ERR_INVALID;
   if (!img || !g0 || !g1 || !g2 || !logits || !workspace) return fail(h, CATSEG_ERR_INVALID, "null tensor pointer");
@@ -878,13 +887,27 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
   Seg seg{h, st, h->profiling};
   const bool sharded = shard_world > 1;
   if (sharded) {
-    if (shard_rank < 0 || shard_rank >= shard_world || !allreduce) return fail(h, CATSEG_ERR_INVALID, "bad shard rank/world/allreduce");
+    if (shard_rank < 0 || shard_rank >= shard_world || !xc || (!xc->allreduce && !xc->barrier))
+      return fail(h, CATSEG_ERR_INVALID, "bad shard rank/world/exchange");
     if (p.Te % shard_world) return fail(h, CATSEG_ERR_UNSUPPORTED, "kept classes (%d) must be a multiple of the shard group size (%d)", p.Te, shard_world);
     if (taps) return fail(h, CATSEG_ERR_UNSUPPORTED, "taps are not available in class-sharded mode");
   }
   const int Te = p.Te / shard_world;                     // classes processed by this rank
   const int nslice = B * Te;
+  const bool a2a = sharded && xc->barrier != nullptr;
   float* X = ws + p.X;
+  float* PB = nullptr;                                   // a2a: this rank's pixel-sharded buffer [B][p.Te][HW / world][128]
+  const int npl = p.HW / shard_world;                    // a2a: pixels per image owned by this rank in the class layers
+  if (a2a) {
+    if (p.pooled) return fail(h, CATSEG_ERR_UNSUPPORTED, "the all-to-all exchange needs pooling_size [1,1]");
+    if (p.HW % shard_world) return fail(h, CATSEG_ERR_UNSUPPORTED, "H*W (%d) must be a multiple of the shard group size (%d)", p.HW, shard_world);
+    if (shard_world > kMaxShard) return fail(h, CATSEG_ERR_UNSUPPORTED, "at most %d ranks in the all-to-all exchange", kMaxShard);
+    if (!(h->split && (h->fast_mask & CATSEG_FAST_CLASS))) return fail(h, CATSEG_ERR_UNSUPPORTED, "the all-to-all exchange is implemented for the PRECISE class layer");
+    if (!xc->xb || !xc->pb || xc->buf_bytes < (size_t)nslice * p.HW * 128 * sizeof(float))
+      return fail(h, CATSEG_ERR_WORKSPACE, "exchange buffers too small: need %zu bytes each", (size_t)nslice * p.HW * 128 * sizeof(float));
+    X = xc->xb[shard_rank];                              // the residual stream lives in the peer-visible buffer
+    PB = xc->pb[shard_rank];
+  }
   int32_t* classes_all = reinterpret_cast<int32_t*>(ws + p.classes);          // [B][p.Te] kept class ids (ascending)
   int32_t* classes = sharded ? reinterpret_cast<int32_t*>(ws + p.classes_loc) : classes_all;   // [B][Te]
 
@@ -965,7 +988,16 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
   }
   const bool class_fast = (h->fast_mask & CATSEG_FAST_CLASS) != 0;
   __half* timg = reinterpret_cast<__half*>(ws + p.timg);
-  if (class_fast) RUN(launch_pack_text_img(ws + p.text_g, timg, B, Te, st));
+  if (a2a) {
+    // the class layers of this mode see ALL kept classes (at this rank's pixels): text guidance of the whole kept list
+    if (use_vocab) {
+      RUN(launch_gather_rows(h->vocab.text_g, classes_all, ws + p.text_g, (long long)B * p.Te, 128, st));
+    } else {
+      RUN(launch_text_mean(p.truncated ? ws + p.textn : text, classes_all, ws + p.tmean, B, T, p.Te, p.P, p.Ct, st));
+      RUN(launch_linear(ws + p.tmean, h->tproj_wt, h->tproj_b, ws + p.text_g, (long long)B * p.Te, 128, p.Ct, 1, st));
+    }
+    RUN(launch_pack_text_img(ws + p.text_g, timg, B, p.Te, st));
+  } else if (class_fast) RUN(launch_pack_text_img(ws + p.text_g, timg, B, Te, st));
   // The guidance projections only depend on the inputs: they run on an internal stream beside the cost volume / class
   // selection / text chain (small, latency-bound kernels) and are joined before the embedding.  Externally the call is
   // still ordered on `stream`.
@@ -1064,6 +1096,22 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
     seg.begin(CATSEG_STAGE_CLASS);
     const float* cg = ws + p.cg_qk + (size_t)l * B * Te * 256;
     const float* pad = ws + p.pad_state + (size_t)l * kStateFloats;
+    if (a2a) {
+      // class-sharded X -> pixel-sharded PB of every rank (peer stores over NVLink), the class layer on all p.Te classes at
+      // this rank's pixels (no reduction needed: every class of a pixel is local), and back
+      PeerPtrs xbp{}, pbp{};
+      for (int r = 0; r < shard_world; ++r) { xbp.p[r] = xc->xb[r]; pbp.p[r] = xc->pb[r]; }
+      RUN(launch_shard_c2p(X, pbp, B, Te, p.Te, p.HW, shard_rank, shard_world, st));
+      if (xc->barrier(xc->bar_ctx, stream) != 0) return fail(h, CATSEG_ERR_CUDA, "class-shard barrier callback failed");
+      float* x1 = ws + p.X1;
+      RUN(launch_class_state_split(PB, timg, ws + p.state, B, p.Te, npl, p.S, h->class_split[l], h->num_sms, st));
+      RUN(launch_class_apply_split(PB, x1, timg, ws + p.state, pad, B, p.Te, npl, p.S, h->class_split[l], h->num_sms, st));
+      RUN(launch_mlp_split(x1, PB, PB, (long long)B * p.Te * npl, h->class_mlp_split[l], 1, h->num_sms, st));
+      RUN(launch_shard_p2c(PB, xbp, B, Te, p.Te, p.HW, shard_rank, shard_world, st));
+      if (xc->barrier(xc->bar_ctx, stream) != 0) return fail(h, CATSEG_ERR_CUDA, "class-shard barrier callback failed");
+      seg.end();
+      continue;
+    }
     if (p.pooled) RUN(launch_avgpool_tokens(X, ws + p.Xp, nslice, p.H, p.W, c.pooling_size[0], c.pooling_size[1], st));
     const float* xin = p.pooled ? ws + p.Xp : X;
     float* xout = p.pooled ? ws + p.Xp2 : X;
@@ -1072,7 +1120,7 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
     else if (class_fast) RUN(launch_class_state_fast(xin, timg, ws + p.state, B, Te, p.npix, p.S, h->class_fast[l], h->num_sms, st));
     else RUN(launch_class_state_exact(xin, cg, ws + p.state, B, Te, p.npix, p.S, h->cls[l], st));
     if (sharded) {                                         // the only exchange step of the path: sum of the per-pixel state
-      int rc = allreduce(ar_ctx, ws + p.state, (size_t)B * p.npix * kStateFloats, stream);
+      int rc = xc->allreduce(xc->ar_ctx, ws + p.state, (size_t)B * p.npix * kStateFloats, stream);
       if (rc != 0) return fail(h, CATSEG_ERR_CUDA, "class-shard all-reduce callback failed (%d)", rc);
     }
     if (class_fast && h->split) {
@@ -1125,8 +1173,7 @@ extern "C" int catseg_forward_taps(catseg_handle* h, const float* img, const flo
                                    const float* g1, const float* g2, float* logits, void* workspace,
                                    size_t workspace_bytes, int B, int T, const catseg_taps* taps,
                                    catseg_stream stream) {
-  return forward_impl(h, img, text, g0, g1, g2, logits, workspace, workspace_bytes, B, T, taps, 0, 1, nullptr, nullptr, nullptr,
-                      stream);
+  return forward_impl(h, img, text, g0, g1, g2, logits, workspace, workspace_bytes, B, T, taps, 0, 1, nullptr, nullptr, stream);
 }
 
 extern "C" int catseg_forward_class_sharded(catseg_handle* h, const float* img, const float* text, const float* g0,
@@ -1135,8 +1182,64 @@ extern "C" int catseg_forward_class_sharded(catseg_handle* h, const float* img, 
                                             int shard_rank, int shard_world, catseg_allreduce_fn allreduce, void* ctx,
                                             catseg_stream stream) {
   if (shard_world < 1) return CATSEG_ERR_INVALID;
+  ShardExchange xc{allreduce, ctx, nullptr, nullptr, 0, nullptr, nullptr};
   return forward_impl(h, img, text, g0, g1, g2, logits_local, workspace, workspace_bytes, B, T, nullptr, shard_rank, shard_world,
-                      allreduce, ctx, kept_classes_out, stream);
+                      &xc, kept_classes_out, stream);
+}
+
+extern "C" size_t catseg_exchange_buffer_bytes(const catseg_handle* h, int B, int T, int shard_world) {
+  if (!h || B <= 0 || T <= 0 || shard_world < 1) return 0;
+  const Plan p = make_plan(h, B, T);
+  if (p.Te % shard_world) return 0;
+  return (size_t)B * (p.Te / shard_world) * p.HW * 128 * sizeof(float);
+}
+
+extern "C" int catseg_forward_class_sharded_a2a(catseg_handle* h, const float* img, const float* text, const float* g0,
+                                                const float* g1, const float* g2, float* logits_local,
+                                                int32_t* kept_classes_out, void* workspace, size_t workspace_bytes, int B, int T,
+                                                int shard_rank, int shard_world, float* const* xbuf_peers,
+                                                float* const* pbuf_peers, size_t buf_bytes, catseg_barrier_fn barrier, void* ctx,
+                                                catseg_stream stream) {
+  if (shard_world < 1 || !barrier) return CATSEG_ERR_INVALID;
+  ShardExchange xc{nullptr, nullptr, xbuf_peers, pbuf_peers, buf_bytes, barrier, ctx};
+  return forward_impl(h, img, text, g0, g1, g2, logits_local, workspace, workspace_bytes, B, T, nullptr, shard_rank, shard_world,
+                      &xc, kept_classes_out, stream);
+}
+
+// Peer-visible device memory for the all-to-all exchange: plain cudaMalloc allocations (CUDA IPC cannot export a sub-range
+// of a caching allocator's pool), exported / opened with the CUDA IPC handle API.
+extern "C" int catseg_peer_alloc(size_t bytes, void** out) {
+  if (!out || bytes == 0) return CATSEG_ERR_INVALID;
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return CATSEG_ERR_CUDA; }
+  return CATSEG_OK;
+}
+extern "C" int catseg_peer_free(void* ptr) {
+  cudaError_t e = cudaFree(ptr);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return CATSEG_ERR_CUDA; }
+  return CATSEG_OK;
+}
+extern "C" int catseg_peer_export(const void* ptr, uint8_t handle_out[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!ptr || !handle_out) return CATSEG_ERR_INVALID;
+  cudaIpcMemHandle_t hd;
+  cudaError_t e = cudaIpcGetMemHandle(&hd, const_cast<void*>(ptr));
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return CATSEG_ERR_CUDA; }
+  memcpy(handle_out, &hd, 64);
+  return CATSEG_OK;
+}
+extern "C" int catseg_peer_open(const uint8_t handle[64], void** out) {
+  if (!handle || !out) return CATSEG_ERR_INVALID;
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(out, hd, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return CATSEG_ERR_CUDA; }
+  return CATSEG_OK;
+}
+extern "C" int catseg_peer_close(void* ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return CATSEG_ERR_CUDA; }
+  return CATSEG_OK;
 }
 
 extern "C" int catseg_forward(catseg_handle* h, const float* img, const float* text, const float* g0,

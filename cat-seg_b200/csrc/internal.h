@@ -116,6 +116,12 @@ struct GemmSplitParams {
 };
 cudaError_t launch_gemm_split(const GemmSplitParams& p, cudaStream_t st);
 
+// ---------------------------------------------------------------- shard_exchange.cu
+constexpr int kMaxShard = 8;
+struct PeerPtrs { float* p[kMaxShard]; };      // one buffer per rank of the shard group (peer-mapped device pointers)
+cudaError_t launch_shard_c2p(const float* X, const PeerPtrs& pb, int B, int Tl, int Te, int HW, int rank, int world, cudaStream_t st);
+cudaError_t launch_shard_p2c(const float* P, const PeerPtrs& xb, int B, int Tl, int Te, int HW, int rank, int world, cudaStream_t st);
+
 // ---------------------------------------------------------------- clip_dense.cu
 // CLIP ResidualAttentionBlock.forward_dense + ln_post + proj (model_vpt.py:219-240, 300-312); all fp32 device pointers in the
 // reference's own parameter layouts

@@ -154,6 +154,33 @@ int catseg_forward_class_sharded(catseg_handle* h, const float* img_feats, const
                                  void* workspace, size_t workspace_bytes, int B, int T, int shard_rank, int shard_world,
                                  catseg_allreduce_fn allreduce, void* ctx, catseg_stream stream);
 
+/* The same class split with north_star's exchange: instead of summing the state, the residual stream is
+ * transposed class-sharded [B, Te/world, HW, 128] <-> pixel-sharded [B, Te, HW/world, 128] around each class layer
+ * (model.py:404-413 couples all classes of one pixel).  The transposition is one kernel per direction that stores straight
+ * into the owning peer's buffer over NVLink: every rank allocates two buffers of catseg_exchange_buffer_bytes() with
+ * catseg_peer_alloc, publishes them with catseg_peer_export (64-byte CUDA IPC handles, exchanged by the host, e.g.
+ * torch.distributed.all_gather_object) and maps the others' with catseg_peer_open.
+ *   xbuf_peers / pbuf_peers  [world] device pointers (HOST arrays), entry r = rank r's class-sharded / pixel-sharded buffer
+ *                            (entry shard_rank = this rank's own allocation).
+ *   barrier(ctx, stream)     must return only after enqueueing, on `stream`, a barrier over the shard group's streams
+ *                            (e.g. a one-element ncclAllReduce): it orders the peer stores against their consumers.  It is
+ *                            called twice per class layer.
+ * PRECISE precision, pooling_size [1,1], HW % world == 0, world <= 8. */
+typedef int (*catseg_barrier_fn)(void* ctx, catseg_stream stream);
+size_t catseg_exchange_buffer_bytes(const catseg_handle* h, int B, int T, int shard_world);
+int catseg_forward_class_sharded_a2a(catseg_handle* h, const float* img_feats, const float* text_feats, const float* g0,
+                                     const float* g1, const float* g2, float* logits_local, int32_t* kept_classes_out,
+                                     void* workspace, size_t workspace_bytes, int B, int T, int shard_rank, int shard_world,
+                                     float* const* xbuf_peers, float* const* pbuf_peers, size_t buf_bytes,
+                                     catseg_barrier_fn barrier, void* ctx, catseg_stream stream);
+/* Peer-visible device memory (cudaMalloc + CUDA IPC): alloc / free on the owner, export -> 64-byte handle, open / close on
+ * the other processes of the node (peer access is enabled lazily by the open). */
+int catseg_peer_alloc(size_t bytes, void** ptr_out);
+int catseg_peer_free(void* ptr);
+int catseg_peer_export(const void* ptr, uint8_t handle_out[64]);
+int catseg_peer_open(const uint8_t handle[64], void** ptr_out);
+int catseg_peer_close(void* ptr);
+
 /* Per-stage CUDA-event timing of catseg_forward on its own stream (for the roofline report). */
 int catseg_set_profiling(catseg_handle* h, int enable);
 /* Synchronises the recorded events; ms[CATSEG_STAGE_COUNT] = total ms per stage since the last

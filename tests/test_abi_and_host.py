@@ -19,7 +19,7 @@ from oracle.ref_loader import build_reference_aggregator, reference_available
 def _header_symbols():
     src = open(os.path.join(ROOT, "include", "catseg_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(catseg_[a-z_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(catseg_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_library_exports_every_header_symbol():
