@@ -26,6 +26,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+
 import torch  # noqa: E402
 
 from cat_seg_b200.config import BENCH_CONFIGS, vitb, vitl  # noqa: E402
@@ -454,7 +457,7 @@ def run_ours(args):
             "ms_per_launch": per_launch_ms,
             "stage_ms_per_step": {k: v / max(calls, 1) for k, v in stage_ms.items()},
             "stage_tflops_executed": {k: (fl_exe[k] / (stage_ms[k] / max(calls, 1) * 1e-3) / 1e12 if stage_ms[k] > 0 else None)
-                                      for k in stage_ms},
+                                      for k in stage_ms if k in fl_exe},
             "whole_step": {"reference_algorithm_tflops": sum(fl_ref.values()) / (tot_ms * 1e-3) / 1e12,
                            "executed_tflops": sum(fl_exe.values()) / (tot_ms * 1e-3) / 1e12,
                            "frac_of_peak_reference_flops": sum(fl_ref.values()) / (tot_ms * 1e-3) / 1e12 / pk["tflops"]}}

@@ -43,7 +43,7 @@ class ClipDenseWeights(C.Structure):
         "ln_post_weight", "ln_post_bias", "proj")]
 
 
-STAGES = ("prep", "embed", "swin", "class", "decoder", "swin_mlp")
+STAGES = ("prep", "embed", "swin", "class", "decoder", "swin_mlp", "exchange")
 FAST_BITS = {"swin_mlp": 1, "swin_attn": 2, "class": 4, "decoder": 8, "prep": 16}
 
 
@@ -89,6 +89,8 @@ _SIGS = [
     ("catseg_forward_class_sharded_a2a", C.c_int, [C.c_void_p] + [C.c_void_p] * 8 +
      [C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t, C.c_void_p,
       C.c_void_p, C.c_void_p]),
+    ("catseg_assemble_class_sharded", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                C.c_int64, C.c_void_p]),
     ("catseg_peer_alloc", C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     ("catseg_peer_free", C.c_int, [C.c_void_p]),
     ("catseg_peer_export", C.c_int, [C.c_void_p, C.c_char_p]),

@@ -442,6 +442,19 @@ def assemble_class_sharded(gathered: torch.Tensor, kept: torch.Tensor, T: int) -
     """gathered [world, B, Te/world, h, w]: rank r's planes are the kept classes kept[:, r*Te/world:(r+1)*Te/world];
     kept [B, Te] class ids.  Returns [B, T, h, w] with -100 for classes that were not kept (model.py:721-724)."""
     world, B, tl, h, w = gathered.shape
+    if gathered.is_cuda:                              # one pass in the CUDA library: copy a gathered plane or fill -100
+        lib = _lib.load()
+        g = gathered.contiguous()
+        k = kept.to(device=g.device, dtype=torch.int32).contiguous()
+        out = torch.empty(B, T, h, w, dtype=torch.float32, device=g.device)
+        pos = torch.empty(B * T, dtype=torch.int32, device=g.device)
+        with torch.cuda.device(g.device):
+            rc = lib.catseg_assemble_class_sharded(C.c_void_p(g.data_ptr()), C.c_void_p(k.data_ptr()), C.c_void_p(pos.data_ptr()),
+                                                   C.c_void_p(out.data_ptr()), world, B, tl, T, h * w,
+                                                   C.c_void_p(torch.cuda.current_stream(g.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"catseg_assemble_class_sharded failed ({rc}): {lib.catseg_last_error(None).decode()}")
+        return out
     planes = gathered.permute(1, 0, 2, 3, 4).reshape(B, world * tl, h, w)
     out = torch.full((B, T, h, w), -100.0, dtype=gathered.dtype, device=gathered.device)
     out[torch.arange(B, device=gathered.device)[:, None], kept.long()] = planes

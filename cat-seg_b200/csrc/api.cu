@@ -29,7 +29,7 @@ constexpr int kImplementedFast = CATSEG_FAST_SWIN_MLP | CATSEG_FAST_SWIN_ATTN | 
 // stages that have a PRECISE (hi + lo fp16 operand pair) kernel; the others run the EXACT kernel in that mode
 constexpr int kImplementedSplit = CATSEG_FAST_SWIN_MLP | CATSEG_FAST_SWIN_ATTN | CATSEG_FAST_CLASS | CATSEG_FAST_DECODER | CATSEG_FAST_PREP;
 constexpr int kMaxProfForwards = 64;
-constexpr int kMaxSegments = 40;
+constexpr int kMaxSegments = 48;
 
 }  // namespace
 
@@ -948,8 +948,9 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
       RUN(launch_select_classes(ws + p.cmax, classes_all, B, T, p.Te, st));
       if (two_pass) {                                      // kept slices only: rows gathered through the kept-class list
         if (p.P != 1) return fail(h, CATSEG_ERR_UNSUPPORTED, "two-pass cost volume needs prompt_channel == 1");
-        g.a_index = classes_all; g.ai_batch = p.Te; g.M = p.Te; g.row_max = nullptr;
-        g.C = ws + p.corr; g.c_row = p.HW; g.c_batch = (long long)p.Te * p.HW;
+        // (class-sharded: only this rank's slice of the kept list; the rows land at their position in the [B][p.Te] block)
+        g.a_index = classes_all + (sharded ? shard_rank * Te : 0); g.ai_batch = p.Te; g.M = sharded ? Te : p.Te; g.row_max = nullptr;
+        g.C = ws + p.corr + (sharded ? (size_t)shard_rank * Te * p.HW : 0); g.c_row = p.HW; g.c_batch = (long long)p.Te * p.HW;
         RUN(launch_gemm_split(g, st));
         corr_compact = true;
       }
@@ -1101,12 +1102,18 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
       // this rank's pixels (no reduction needed: every class of a pixel is local), and back
       PeerPtrs xbp{}, pbp{};
       for (int r = 0; r < shard_world; ++r) { xbp.p[r] = xc->xb[r]; pbp.p[r] = xc->pb[r]; }
+      seg.end();
+      seg.begin(CATSEG_STAGE_EXCHANGE);
       RUN(launch_shard_c2p(X, pbp, B, Te, p.Te, p.HW, shard_rank, shard_world, st));
       if (xc->barrier(xc->bar_ctx, stream) != 0) return fail(h, CATSEG_ERR_CUDA, "class-shard barrier callback failed");
+      seg.end();
+      seg.begin(CATSEG_STAGE_CLASS);
       float* x1 = ws + p.X1;
       RUN(launch_class_state_split(PB, timg, ws + p.state, B, p.Te, npl, p.S, h->class_split[l], h->num_sms, st));
       RUN(launch_class_apply_split(PB, x1, timg, ws + p.state, pad, B, p.Te, npl, p.S, h->class_split[l], h->num_sms, st));
       RUN(launch_mlp_split(x1, PB, PB, (long long)B * p.Te * npl, h->class_mlp_split[l], 1, h->num_sms, st));
+      seg.end();
+      seg.begin(CATSEG_STAGE_EXCHANGE);
       RUN(launch_shard_p2c(PB, xbp, B, Te, p.Te, p.HW, shard_rank, shard_world, st));
       if (xc->barrier(xc->bar_ctx, stream) != 0) return fail(h, CATSEG_ERR_CUDA, "class-shard barrier callback failed");
       seg.end();
@@ -1120,8 +1127,12 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
     else if (class_fast) RUN(launch_class_state_fast(xin, timg, ws + p.state, B, Te, p.npix, p.S, h->class_fast[l], h->num_sms, st));
     else RUN(launch_class_state_exact(xin, cg, ws + p.state, B, Te, p.npix, p.S, h->cls[l], st));
     if (sharded) {                                         // the only exchange step of the path: sum of the per-pixel state
+      seg.end();
+      seg.begin(CATSEG_STAGE_EXCHANGE);
       int rc = xc->allreduce(xc->ar_ctx, ws + p.state, (size_t)B * p.npix * kStateFloats, stream);
       if (rc != 0) return fail(h, CATSEG_ERR_CUDA, "class-shard all-reduce callback failed (%d)", rc);
+      seg.end();
+      seg.begin(CATSEG_STAGE_CLASS);
     }
     if (class_fast && h->split) {
       // x1 = x + attention -> X1 (pooled: Xp2), then the token MLP kernel adds MLP(LN2(x1)) and the outer residual (model.py:423)
@@ -1204,6 +1215,16 @@ extern "C" int catseg_forward_class_sharded_a2a(catseg_handle* h, const float* i
   ShardExchange xc{nullptr, nullptr, xbuf_peers, pbuf_peers, buf_bytes, barrier, ctx};
   return forward_impl(h, img, text, g0, g1, g2, logits_local, workspace, workspace_bytes, B, T, nullptr, shard_rank, shard_world,
                       &xc, kept_classes_out, stream);
+}
+
+extern "C" int catseg_assemble_class_sharded(const float* gathered, const int32_t* kept_classes, int32_t* pos_scratch, float* logits,
+                                             int shard_world, int B, int T_local, int T, int64_t npix, catseg_stream stream) {
+  if (!gathered || !kept_classes || !pos_scratch || !logits || shard_world < 1 || B <= 0 || T_local <= 0 || T <= 0 || npix <= 0)
+    return CATSEG_ERR_INVALID;
+  cudaError_t e = launch_assemble_class_sharded(gathered, kept_classes, pos_scratch, logits, shard_world, B, T_local, T, npix,
+                                                (cudaStream_t)stream);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return e == cudaErrorInvalidValue ? CATSEG_ERR_INVALID : CATSEG_ERR_CUDA; }
+  return CATSEG_OK;
 }
 
 // Peer-visible device memory for the all-to-all exchange: plain cudaMalloc allocations (CUDA IPC cannot export a sub-range

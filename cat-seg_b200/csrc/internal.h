@@ -122,6 +122,9 @@ struct PeerPtrs { float* p[kMaxShard]; };      // one buffer per rank of the sha
 cudaError_t launch_shard_c2p(const float* X, const PeerPtrs& pb, int B, int Tl, int Te, int HW, int rank, int world, cudaStream_t st);
 cudaError_t launch_shard_p2c(const float* P, const PeerPtrs& xb, int B, int Tl, int Te, int HW, int rank, int world, cudaStream_t st);
 
+cudaError_t launch_assemble_class_sharded(const float* gathered, const int32_t* kept, int32_t* pos_scratch, float* out, int world,
+                                          int B, int Tl, int T, long long npix, cudaStream_t st);
+
 // ---------------------------------------------------------------- clip_dense.cu
 // CLIP ResidualAttentionBlock.forward_dense + ln_post + proj (model_vpt.py:219-240, 300-312); all fp32 device pointers in the
 // reference's own parameter layouts

@@ -50,4 +50,42 @@ cudaError_t launch_shard_p2c(const float* P, const PeerPtrs& xb, int B, int Tl, 
   return cudaGetLastError();
 }
 
+
+// ---- final assembly of the class-sharded logits (model.py:721-724): gathered [world][B][Tl][npix] (rank-major local planes),
+// kept [B][world Tl] class ids -> out [B][T][npix], -100 for classes that were not kept.  One pass: every output plane is
+// either a copy of one gathered plane or a constant fill.
+__global__ void invert_kept_kernel(const int32_t* __restrict__ kept, int32_t* __restrict__ pos, int B, int Te, int T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Te) return;
+  const int b = i / Te, c = kept[i];
+  if (c >= 0 && c < T) pos[b * T + c] = i - b * Te;
+}
+__global__ void assemble_planes_kernel(const float* __restrict__ gathered, const int32_t* __restrict__ pos, float* __restrict__ out,
+                                       int B, int Tl, int T, long long npix4) {
+  const int plane = blockIdx.y;                        // b * T + t
+  const int b = plane / T;
+  const int j = pos[plane];
+  float4* o = reinterpret_cast<float4*>(out) + (long long)plane * npix4;
+  if (j < 0) {
+    const float4 f = make_float4(-100.f, -100.f, -100.f, -100.f);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix4; i += (long long)gridDim.x * blockDim.x) o[i] = f;
+  } else {
+    const int r = j / Tl, jl = j - r * Tl;
+    const float4* g = reinterpret_cast<const float4*>(gathered) + (((long long)r * B + b) * Tl + jl) * npix4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix4; i += (long long)gridDim.x * blockDim.x) o[i] = g[i];
+  }
+}
+cudaError_t launch_assemble_class_sharded(const float* gathered, const int32_t* kept, int32_t* pos_scratch, float* out, int world,
+                                          int B, int Tl, int T, long long npix, cudaStream_t st) {
+  if (npix % 4 || (long long)B * T > 65535) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(pos_scratch, 0xff, (size_t)B * T * sizeof(int32_t), st);
+  if (e != cudaSuccess) return e;
+  const int Te = world * Tl;
+  invert_kept_kernel<<<(B * Te + 255) / 256, 256, 0, st>>>(kept, pos_scratch, B, Te, T);
+  const long long npix4 = npix / 4;
+  const int gx = (int)((npix4 + 1023) / 1024) < 4 ? (int)((npix4 + 1023) / 1024) : 4;
+  assemble_planes_kernel<<<dim3(gx > 0 ? gx : 1, B * T), 256, 0, st>>>(gathered, pos_scratch, out, B, Tl, T, npix4);
+  return cudaGetLastError();
+}
+
 }  // namespace catseg

@@ -102,7 +102,8 @@ enum {
   CATSEG_STAGE_CLASS = 3,  /* all class-attention layers */
   CATSEG_STAGE_DECODER = 4,
   CATSEG_STAGE_SWIN_MLP = 5, /* FFN half of all Swin blocks when it runs as its own kernel (fast path) */
-  CATSEG_STAGE_COUNT = 6
+  CATSEG_STAGE_EXCHANGE = 6, /* class-sharded modes: the state all-reduce, or the peer transpositions + barriers */
+  CATSEG_STAGE_COUNT = 7
 };
 
 int catseg_create(const catseg_config* cfg, catseg_handle** out);
@@ -173,6 +174,11 @@ int catseg_forward_class_sharded_a2a(catseg_handle* h, const float* img_feats, c
                                      void* workspace, size_t workspace_bytes, int B, int T, int shard_rank, int shard_world,
                                      float* const* xbuf_peers, float* const* pbuf_peers, size_t buf_bytes,
                                      catseg_barrier_fn barrier, void* ctx, catseg_stream stream);
+/* Final assembly after the all-gather of the local planes: gathered [world][B][T_local][npix] (rank-major), kept_classes
+ * [B][world*T_local] -> logits [B][T][npix] with -100 for classes that were not kept (model.py:721-724).  pos_scratch: B*T
+ * int32 of device scratch.  npix % 4 == 0, B*T <= 65535. */
+int catseg_assemble_class_sharded(const float* gathered, const int32_t* kept_classes, int32_t* pos_scratch, float* logits,
+                                  int shard_world, int B, int T_local, int T, int64_t npix, catseg_stream stream);
 /* Peer-visible device memory (cudaMalloc + CUDA IPC): alloc / free on the owner, export -> 64-byte handle, open / close on
  * the other processes of the node (peer access is enabled lazily by the open). */
 int catseg_peer_alloc(size_t bytes, void** ptr_out);

@@ -56,6 +56,10 @@ def _worker(rank: int, world: int, port: int, q, model: str, B: int, T: int):
             res = {k: (v - ref).abs().max().item() for k, v in out.items()}
             res["mask_equal"] = all(bool(((v == -100.0) == (ref == -100.0)).all()) for v in out.values())
             res["again_equal"] = bool(torch.equal(again, out["alltoall"]))
+            # the CUDA assembly kernel (copy a gathered plane / fill -100) against the torch restatement
+            stacked = torch.stack(parts)
+            res["assemble_equal"] = bool(torch.equal(assemble_class_sharded(stacked.cuda(), kept2, T).cpu(),
+                                                     assemble_class_sharded(stacked, kept2.cpu(), T)))
         dist.barrier()
         if m._peer is not None:
             m._peer.close()
@@ -86,4 +90,4 @@ def test_class_sharded_two_ranks_one_gpu(model, B, T):
     assert res["alltoall"] == 0.0, res
     # all-reduce: only the fp32 summation order of the linear-attention state differs
     assert res["allreduce"] <= 2e-5, res
-    assert res["mask_equal"] and res["again_equal"], res
+    assert res["mask_equal"] and res["again_equal"] and res["assemble_equal"], res
