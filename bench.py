@@ -26,8 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner / warnings off stdout: rank 0 prints ONE JSON line
 
 import torch  # noqa: E402
 

@@ -250,7 +250,7 @@ class Aggregator(nn.Module):
 
     def forward_class_sharded(self, img_feats: torch.Tensor, text_feats: torch.Tensor,
                               appearance_guidance: Sequence[torch.Tensor], group=None, exchange: str = "allreduce",
-                              gather: bool = True) -> torch.Tensor:
+                              gather: bool = True, barrier: str = "device") -> torch.Tensor:
         """Class-sharded forward over a torch.distributed process group (NCCL): every rank passes the SAME inputs,
         computes the kept classes [r*Te/world, (r+1)*Te/world) and receives the full [B,T,4H,4W] logits.
         exchange="allreduce": activations stay class-sharded; the only exchange inside the path is one all-reduce (sum) of
@@ -258,7 +258,8 @@ class Aggregator(nn.Module):
         library through a callback on the current stream.
         exchange="alltoall": north_star's prescription: the residual stream is transposed class-sharded
         <-> pixel-sharded around each class layer by kernels that store straight into the peers' buffers over NVLink
-        (CUDA IPC mappings, ``PeerExchange``); the callback is a one-element all-reduce that orders those stores.
+        (CUDA IPC mappings, ``PeerExchange``); those stores are ordered by a flag barrier through the same peer memory
+        (barrier="device", one single-warp kernel) or by a one-element all-reduce of the group (barrier="collective").
         The local logit planes are all-gathered and scattered to their class ids afterwards (gather=False returns the
         compact local planes and the kept-class list instead)."""
         import torch.distributed as dist
@@ -315,9 +316,12 @@ class Aggregator(nn.Module):
                         errors.append(e)
                         return 1
 
+                if barrier not in ("device", "collective"):
+                    raise ValueError(f"barrier must be 'device' or 'collective', got {barrier!r}")
                 cb = _lib.BARRIER_FN(_barrier)
                 rc = lib.catseg_forward_class_sharded_a2a(self._handle, *ptrs, C.c_void_p(ws.data_ptr()), ws.numel(), B, T, rank, world,
-                                                          peer.xb, peer.pb, peer.nbytes, C.cast(cb, C.c_void_p), None, stream)
+                                                          peer.xb, peer.pb, peer.nbytes,
+                                                          C.cast(cb, C.c_void_p) if barrier == "collective" else None, None, stream)
             if errors:
                 raise errors[0]
             if rc != 0:

@@ -862,6 +862,11 @@ struct ShardExchange {
   float* const* xb; float* const* pb; size_t buf_bytes; catseg_barrier_fn barrier; void* bar_ctx;
 };
 
+// peer buffer = [residual-stream data][per-class maxima B*T floats][barrier flag block]
+static size_t exchange_data_floats(const Plan& p, int world) { return ((size_t)p.B * (p.Te / world) * p.HW * 128 + 63) / 64 * 64; }
+static size_t exchange_cmax_floats(int B, int T) { return ((size_t)B * T + 63) / 64 * 64; }
+static size_t exchange_extra_bytes(int B, int T) { return exchange_cmax_floats(B, T) * sizeof(float) + 256; }
+
 static int forward_impl(catseg_handle* h, const float* img, const float* text, const float* g0, const float* g1,
                         const float* g2, float* logits, void* workspace, size_t workspace_bytes, int B, int T,
                         const catseg_taps* taps, int shard_rank, int shard_world, const ShardExchange* xc,
@@ -887,14 +892,14 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
   Seg seg{h, st, h->profiling};
   const bool sharded = shard_world > 1;
   if (sharded) {
-    if (shard_rank < 0 || shard_rank >= shard_world || !xc || (!xc->allreduce && !xc->barrier))
+    if (shard_rank < 0 || shard_rank >= shard_world || !xc || (!xc->allreduce && !xc->xb))
       return fail(h, CATSEG_ERR_INVALID, "bad shard rank/world/exchange");
     if (p.Te % shard_world) return fail(h, CATSEG_ERR_UNSUPPORTED, "kept classes (%d) must be a multiple of the shard group size (%d)", p.Te, shard_world);
     if (taps) return fail(h, CATSEG_ERR_UNSUPPORTED, "taps are not available in class-sharded mode");
   }
   const int Te = p.Te / shard_world;                     // classes processed by this rank
   const int nslice = B * Te;
-  const bool a2a = sharded && xc->barrier != nullptr;
+  const bool a2a = sharded && xc->allreduce == nullptr;
   float* X = ws + p.X;
   float* PB = nullptr;                                   // a2a: this rank's pixel-sharded buffer [B][p.Te][HW / world][128]
   const int npl = p.HW / shard_world;                    // a2a: pixels per image owned by this rank in the class layers
@@ -903,11 +908,27 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
     if (p.HW % shard_world) return fail(h, CATSEG_ERR_UNSUPPORTED, "H*W (%d) must be a multiple of the shard group size (%d)", p.HW, shard_world);
     if (shard_world > kMaxShard) return fail(h, CATSEG_ERR_UNSUPPORTED, "at most %d ranks in the all-to-all exchange", kMaxShard);
     if (!(h->split && (h->fast_mask & CATSEG_FAST_CLASS))) return fail(h, CATSEG_ERR_UNSUPPORTED, "the all-to-all exchange is implemented for the PRECISE class layer");
-    if (!xc->xb || !xc->pb || xc->buf_bytes < (size_t)nslice * p.HW * 128 * sizeof(float))
-      return fail(h, CATSEG_ERR_WORKSPACE, "exchange buffers too small: need %zu bytes each", (size_t)nslice * p.HW * 128 * sizeof(float));
+    const size_t need_x = exchange_data_floats(p, shard_world) * sizeof(float) + exchange_extra_bytes(B, T);
+    if (!xc->xb || !xc->pb || xc->buf_bytes < need_x)
+      return fail(h, CATSEG_ERR_WORKSPACE, "exchange buffers too small: need %zu bytes each", need_x);
     X = xc->xb[shard_rank];                              // the residual stream lives in the peer-visible buffer
     PB = xc->pb[shard_rank];
   }
+  PeerPtrs cmaxp{};                                      // a2a: every rank's [B][T] table of per-class maxima
+  PeerFlags flagp{};
+  if (a2a)
+    for (int r = 0; r < shard_world; ++r) {
+      cmaxp.p[r] = xc->pb[r] + exchange_data_floats(p, shard_world);
+      flagp.p[r] = reinterpret_cast<uint32_t*>(cmaxp.p[r] + exchange_cmax_floats(B, T));
+    }
+  // orders the peer stores of one rank against their consumers on the others: the host's collective (callback) or, without
+  // one, a flag barrier through peer memory
+  auto xbarrier = [&]() -> int {
+    if (xc->barrier) return xc->barrier(xc->bar_ctx, stream);
+    if (launch_peer_barrier(flagp, shard_rank, shard_world, st) != cudaSuccess) return 1;
+    ++nl;
+    return 0;
+  };
   int32_t* classes_all = reinterpret_cast<int32_t*>(ws + p.classes);          // [B][p.Te] kept class ids (ascending)
   int32_t* classes = sharded ? reinterpret_cast<int32_t*>(ws + p.classes_loc) : classes_all;   // [B][Te]
 
@@ -942,10 +963,28 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
     const bool two_pass = p.truncated && !(taps && taps->corr);
     if (!two_pass) { g.C = ws + p.corr; g.c_row = p.HW; g.c_batch = (long long)T * p.P * p.HW; }
     if (p.truncated) g.row_max = ws + p.rmaxp;
-    RUN(launch_gemm_split(g, st));
+    const float* cmax_all = ws + p.cmax;
+    if (a2a && two_pass) {
+      // first pass sharded over the RAW classes (SURVEY.md 8e "partitioning"): this rank reduces the maxima of classes
+      // [t0, t0 + Tr), stores them into every rank's [B][T] table (peer stores) and all ranks select from the full table
+      const int base = T / shard_world, extra = T % shard_world;
+      const int t0 = shard_rank * base + (shard_rank < extra ? shard_rank : extra), Tr = base + (shard_rank < extra ? 1 : 0);
+      GemmSplitParams g1 = g;
+      g1.A = g.A + (long long)t0 * p.P * p.Ct; g1.M = Tr * p.P;
+      g1.row_scale = g.row_scale + (long long)t0 * p.P;
+      if (Tr > 0) {
+        RUN(launch_gemm_split(g1, st));
+        RUN(launch_class_max(ws + p.rmaxp, ws + p.cmax, (long long)B * Tr, p.P * 2 * ntn, st));
+        RUN(launch_shard_put_cmax(ws + p.cmax, cmaxp, B, Tr, T, t0, shard_world, st));
+      }
+      if (xbarrier() != 0) return fail(h, CATSEG_ERR_CUDA, "class-shard barrier failed");
+      cmax_all = cmaxp.p[shard_rank];
+    } else {
+      RUN(launch_gemm_split(g, st));
+      if (p.truncated) RUN(launch_class_max(ws + p.rmaxp, ws + p.cmax, (long long)B * T, p.P * 2 * ntn, st));
+    }
     if (p.truncated) {
-      RUN(launch_class_max(ws + p.rmaxp, ws + p.cmax, (long long)B * T, p.P * 2 * ntn, st));
-      RUN(launch_select_classes(ws + p.cmax, classes_all, B, T, p.Te, st));
+      RUN(launch_select_classes(cmax_all, classes_all, B, T, p.Te, st));
       if (two_pass) {                                      // kept slices only: rows gathered through the kept-class list
         if (p.P != 1) return fail(h, CATSEG_ERR_UNSUPPORTED, "two-pass cost volume needs prompt_channel == 1");
         // (class-sharded: only this rank's slice of the kept list; the rows land at their position in the [B][p.Te] block)
@@ -1105,7 +1144,7 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
       seg.end();
       seg.begin(CATSEG_STAGE_EXCHANGE);
       RUN(launch_shard_c2p(X, pbp, B, Te, p.Te, p.HW, shard_rank, shard_world, st));
-      if (xc->barrier(xc->bar_ctx, stream) != 0) return fail(h, CATSEG_ERR_CUDA, "class-shard barrier callback failed");
+      if (xbarrier() != 0) return fail(h, CATSEG_ERR_CUDA, "class-shard barrier failed");
       seg.end();
       seg.begin(CATSEG_STAGE_CLASS);
       float* x1 = ws + p.X1;
@@ -1115,7 +1154,7 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
       seg.end();
       seg.begin(CATSEG_STAGE_EXCHANGE);
       RUN(launch_shard_p2c(PB, xbp, B, Te, p.Te, p.HW, shard_rank, shard_world, st));
-      if (xc->barrier(xc->bar_ctx, stream) != 0) return fail(h, CATSEG_ERR_CUDA, "class-shard barrier callback failed");
+      if (xbarrier() != 0) return fail(h, CATSEG_ERR_CUDA, "class-shard barrier failed");
       seg.end();
       continue;
     }
@@ -1202,7 +1241,7 @@ extern "C" size_t catseg_exchange_buffer_bytes(const catseg_handle* h, int B, in
   if (!h || B <= 0 || T <= 0 || shard_world < 1) return 0;
   const Plan p = make_plan(h, B, T);
   if (p.Te % shard_world) return 0;
-  return (size_t)B * (p.Te / shard_world) * p.HW * 128 * sizeof(float);
+  return exchange_data_floats(p, shard_world) * sizeof(float) + exchange_extra_bytes(B, T);
 }
 
 extern "C" int catseg_forward_class_sharded_a2a(catseg_handle* h, const float* img, const float* text, const float* g0,
@@ -1211,7 +1250,7 @@ extern "C" int catseg_forward_class_sharded_a2a(catseg_handle* h, const float* i
                                                 int shard_rank, int shard_world, float* const* xbuf_peers,
                                                 float* const* pbuf_peers, size_t buf_bytes, catseg_barrier_fn barrier, void* ctx,
                                                 catseg_stream stream) {
-  if (shard_world < 1 || !barrier) return CATSEG_ERR_INVALID;
+  if (shard_world < 1 || !xbuf_peers || !pbuf_peers) return CATSEG_ERR_INVALID;
   ShardExchange xc{nullptr, nullptr, xbuf_peers, pbuf_peers, buf_bytes, barrier, ctx};
   return forward_impl(h, img, text, g0, g1, g2, logits_local, workspace, workspace_bytes, B, T, nullptr, shard_rank, shard_world,
                       &xc, kept_classes_out, stream);
@@ -1232,6 +1271,7 @@ extern "C" int catseg_assemble_class_sharded(const float* gathered, const int32_
 extern "C" int catseg_peer_alloc(size_t bytes, void** out) {
   if (!out || bytes == 0) return CATSEG_ERR_INVALID;
   cudaError_t e = cudaMalloc(out, bytes);
+  if (e == cudaSuccess) e = cudaMemset(*out, 0, bytes);       // the barrier flag block starts at epoch 0
   if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return CATSEG_ERR_CUDA; }
   return CATSEG_OK;
 }

@@ -119,6 +119,9 @@ cudaError_t launch_gemm_split(const GemmSplitParams& p, cudaStream_t st);
 // ---------------------------------------------------------------- shard_exchange.cu
 constexpr int kMaxShard = 8;
 struct PeerPtrs { float* p[kMaxShard]; };      // one buffer per rank of the shard group (peer-mapped device pointers)
+struct PeerFlags { uint32_t* p[kMaxShard]; };   // every rank's barrier flag block (kMaxShard + 2 words)
+cudaError_t launch_peer_barrier(const PeerFlags& f, int rank, int world, cudaStream_t st);
+cudaError_t launch_shard_put_cmax(const float* loc, const PeerPtrs& dst, int B, int Tr, int T, int t0, int world, cudaStream_t st);
 cudaError_t launch_shard_c2p(const float* X, const PeerPtrs& pb, int B, int Tl, int Te, int HW, int rank, int world, cudaStream_t st);
 cudaError_t launch_shard_p2c(const float* P, const PeerPtrs& xb, int B, int Tl, int Te, int HW, int rank, int world, cudaStream_t st);
 

@@ -163,9 +163,12 @@ int catseg_forward_class_sharded(catseg_handle* h, const float* img_feats, const
  * torch.distributed.all_gather_object) and maps the others' with catseg_peer_open.
  *   xbuf_peers / pbuf_peers  [world] device pointers (HOST arrays), entry r = rank r's class-sharded / pixel-sharded buffer
  *                            (entry shard_rank = this rank's own allocation).
- *   barrier(ctx, stream)     must return only after enqueueing, on `stream`, a barrier over the shard group's streams
- *                            (e.g. a one-element ncclAllReduce): it orders the peer stores against their consumers.  It is
- *                            called twice per class layer.
+ *   barrier(ctx, stream)     NULL: the library synchronises the group itself with a flag barrier through the peer buffers
+ *                            (one single-warp kernel per barrier).  Otherwise it must enqueue, on `stream`, a barrier over
+ *                            the shard group's streams (e.g. a one-element ncclAllReduce).  A barrier orders the peer
+ *                            stores against their consumers: one after the sharded class selection, two per class layer.
+ * With T > pad_len the first cost-volume pass is sharded over the raw classes too: every rank reduces the maxima of T/world
+ * classes and stores them into every rank's table (model.py:695-696 then selects from identical tables).
  * PRECISE precision, pooling_size [1,1], HW % world == 0, world <= 8. */
 typedef int (*catseg_barrier_fn)(void* ctx, catseg_stream stream);
 size_t catseg_exchange_buffer_bytes(const catseg_handle* h, int B, int T, int shard_world);

@@ -38,8 +38,9 @@ def _worker(rank: int, world: int, port: int, q, model: str, B: int, T: int):
         m = m.cuda()
         a = (img.cuda(), text.cuda(), [x.cuda() for x in g])
         out = {}
-        for exchange in ("alltoall", "allreduce"):
-            local, kept = m.forward_class_sharded(*a, exchange=exchange, gather=False)
+        for exchange in ("alltoall", "alltoall/collective", "allreduce"):
+            local, kept = m.forward_class_sharded(*a, exchange=exchange.split("/")[0], gather=False,
+                                                  barrier="collective" if exchange.endswith("collective") else "device")
             torch.cuda.synchronize()
             parts = [torch.empty_like(local.cpu()) for _ in range(world)]
             dist.all_gather(parts, local.cpu())
@@ -87,7 +88,7 @@ def test_class_sharded_two_ranks_one_gpu(model, B, T):
         assert err is None, f"rank {rank}:\n{err}"
     res = [r for rank, r, _ in results if rank == 0][0]
     # all-to-all: every kernel sees the same operands in the same order as the unsharded run -> bit exact
-    assert res["alltoall"] == 0.0, res
+    assert res["alltoall"] == 0.0 and res["alltoall/collective"] == 0.0, res
     # all-reduce: only the fp32 summation order of the linear-attention state differs
     assert res["allreduce"] <= 2e-5, res
     assert res["mask_equal"] and res["again_equal"] and res["assemble_equal"], res
