@@ -26,7 +26,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner / warnings off stdout: rank 0 prints ONE JSON line
+# rank 0 prints ONE JSON line on stdout: everything else that libraries write to file descriptor 1 (NCCL's version banner, ...)
+# is sent to stderr; the JSON line goes to a private duplicate of the original stdout
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 import torch  # noqa: E402
 
@@ -225,7 +228,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_REAL_STDOUT, flush=True)
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -519,7 +522,7 @@ def run_ours(args):
         "gpu_launches": res["launches"],
         "secondary": secondary, "strong": strong, "other_workloads": others,
     }
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_REAL_STDOUT, flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -601,6 +601,124 @@ static cudaError_t launch_band(const BandConvParams& p, int num_sms, cudaStream_
 }
 
 // ------------------------------------------------------------------------------------------------
+// PRECISE head: conv3x3 32 -> 1 (+ bias) on relu(GroupNorm(c2b)), fp32 on the CUDA cores (model.py:634, 679).
+// One output channel makes this stage a 288-term dot product per pixel: on the tensor pipe (band_conv_kernel<.., HEAD>) it
+// pays for an N = 16 MMA tile plus the hi/lo operand pairs and ran at 0.85 ms per 1024 slices; as an fp32 stencil it is bound
+// by reading c2b once from HBM.  CTA = (slice, band of 6 rows): the band + halo is staged normalised in shared memory
+// ([8 rows][98 cols][32 ch] fp32, 16-byte chunks XOR-swizzled by bit 3 of the column so that the two pixel groups of an
+// LDS.128 phase hit disjoint banks); thread = 8 pixels x 8 channels with its 72 weights in registers, four threads reduce.
+namespace {
+constexpr int HB_BR = 6, HB_W = 96, HB_C = 32, HB_PW = 98, HB_THREADS = 288, HB_NB = HB_W / HB_BR;
+constexpr int HB_SMEM = (HB_BR + 2) * HB_PW * HB_C * 4;
+}  // namespace
+
+__global__ void __launch_bounds__(HB_THREADS, 2)
+head_conv_f32_kernel(const float* __restrict__ in, const float* __restrict__ in_ss, const float* __restrict__ wt, float bias,
+                     const int32_t* __restrict__ classes, float* __restrict__ logits, int slice0, int nslice, int Te, int T) {
+  extern __shared__ float4 hb_sm[];                    // [(BR + 2) * PW pixels][8 chunks of 4 channels]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cg = lane & 3, G = warp * 8 + (lane >> 2);   // channel group (8 channels), pixel group (8 pixels of one row)
+  const int ry = G / 12, x0 = (G % 12) * 8;
+  float w[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[t][k] = __ldg(wt + t * HB_C + cg * 8 + k);
+  const int q = tid & 7;                               // staging: this thread always handles channel chunk q (288 % 8 == 0)
+  const long long nitems = (long long)nslice * HB_NB;
+  for (long long it = blockIdx.x; it < nitems; it += gridDim.x) {
+    const int sl = (int)(it / HB_NB), band = (int)(it % HB_NB);
+    const int y_first = band * HB_BR - 1;
+    {
+      // raw rows -> shared memory with cp.async (every chunk of the band in flight at once: a register-staged loop kept one
+      // load per thread in flight and was latency bound), then GroupNorm + ReLU in place; conv padding is zero AFTER the ReLU
+      const float4* ss = reinterpret_cast<const float4*>(in_ss + ((long long)sl * HB_C + q * 4) * 2);
+      const float4 s01 = __ldg(ss), s23 = __ldg(ss + 1);                 // (scale, shift) of channels 4q .. 4q+3
+      // chunk i = tid + 288 k  <->  pixel p = (tid >> 3) + 36 k: (row, column) advance incrementally, no division in the loop
+      constexpr int NPIX = (HB_BR + 2) * HB_PW, STEP = HB_THREADS / 8;
+      const int p0 = tid >> 3;
+      const float* src_sl = in + (long long)sl * HB_W * HB_W * HB_C + q * 4;
+      {
+        int r = p0 / HB_PW, c = p0 - r * HB_PW;
+        for (int p = p0; p < NPIX; p += STEP) {
+          const int y = y_first + r, x = c - 1;
+          if ((unsigned)y < (unsigned)HB_W && (unsigned)x < (unsigned)HB_W) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&hb_sm[p * 8 + (q ^ ((c >> 3) & 1))]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src_sl + (y * HB_W + x) * HB_C) : "memory");
+          }
+          c += STEP;
+          if (c >= HB_PW) { c -= HB_PW; ++r; }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      {
+        int r = p0 / HB_PW, c = p0 - r * HB_PW;
+        for (int p = p0; p < NPIX; p += STEP) {                          // the same thread owns the same chunks: no barrier needed
+          const int y = y_first + r, x = c - 1;
+          float4* cell = &hb_sm[p * 8 + (q ^ ((c >> 3) & 1))];
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if ((unsigned)y < (unsigned)HB_W && (unsigned)x < (unsigned)HB_W) {
+            v = *cell;
+            v.x = fmaxf(fmaf(v.x, s01.x, s01.y), 0.0f); v.y = fmaxf(fmaf(v.y, s01.z, s01.w), 0.0f);
+            v.z = fmaxf(fmaf(v.z, s23.x, s23.y), 0.0f); v.w = fmaxf(fmaf(v.w, s23.z, s23.w), 0.0f);
+          }
+          *cell = v;
+          c += STEP;
+          if (c >= HB_PW) { c -= HB_PW; ++r; }
+        }
+      }
+    }
+    __syncthreads();
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+#pragma unroll
+    for (int tr = 0; tr < 3; ++tr) {
+#pragma unroll
+      for (int j = 0; j < 10; ++j) {
+        const int col = x0 + j, p = (ry + tr) * HB_PW + col, s = (col >> 3) & 1;
+        const float4 a = hb_sm[p * 8 + ((2 * cg) ^ s)], b = hb_sm[p * 8 + ((2 * cg + 1) ^ s)];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int px = j - kx;                       // output pixel whose tap (tr, kx) reads padded column x0 + j
+          if (px >= 0 && px < 8) {
+            const float* ww = w[tr * 3 + kx];
+            float d = acc[px];
+            d = fmaf(a.x, ww[0], d); d = fmaf(a.y, ww[1], d); d = fmaf(a.z, ww[2], d); d = fmaf(a.w, ww[3], d);
+            d = fmaf(b.x, ww[4], d); d = fmaf(b.y, ww[5], d); d = fmaf(b.z, ww[6], d); d = fmaf(b.w, ww[7], d);
+            acc[px] = d;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 1);
+      acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 2);
+    }
+    if (cg == 0) {
+      const int gs = slice0 + sl, b = gs / Te, cls = classes[gs];
+      float* o = logits + ((long long)b * T + cls) * (HB_W * HB_W) + (band * HB_BR + ry) * HB_W + x0;
+      st4(o, make_float4(acc[0] + bias, acc[1] + bias, acc[2] + bias, acc[3] + bias));
+      st4(o + 4, make_float4(acc[4] + bias, acc[5] + bias, acc[6] + bias, acc[7] + bias));
+    }
+    __syncthreads();                                   // the band image is rebuilt by the next item
+  }
+}
+
+static cudaError_t launch_head_conv_f32(const float* in, const float* in_ss, const float* wt, float bias, const int32_t* classes,
+                                        float* logits, int slice0, int nslice, int Te, int T, int num_sms, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(head_conv_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_SMEM);
+  if (e != cudaSuccess) return e;
+  const long long nitems = (long long)nslice * HB_NB;
+  const int grid = (int)(nitems < 2LL * num_sms ? nitems : 2LL * num_sms);
+  if (grid <= 0) return cudaSuccess;
+  head_conv_f32_kernel<<<grid, HB_THREADS, HB_SMEM, st>>>(in, in_ss, wt, bias, classes, logits, slice0, nslice, Te, T);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight preparation (runs once in catseg_finalize_params)
 
 // image[(k/8)*NOUT*8 + n*8 + k%8] = W3[n][ci0 + k][tap]   (n < nreal, else 0)
@@ -922,7 +1040,11 @@ cudaError_t run_decoder_split(const float* X, const float* dg0, const float* dg1
     CKF(launch_gn_finalize(s2b, nb4, 32, (float)(16 * hw * 16), wx.gn2b_g, wx.gn2b_b, gss, n, st));
     p.in = c2b; p.in_stats = s2b; p.nb_in = nb4; p.gamma = wx.gn2b_g; p.beta = wx.gn2b_b;
     p.wimg = w.w5; p.emap = nullptr; p.out32 = nullptr; p.out_stats = nullptr;
-    if (narrow & 16) CKF((launch_band<D5T>(p, num_sms, st))); else CKF((launch_band<D5S>(p, num_sms, st)));
+    static const bool head_tc = getenv("CATSEG_DEC_HEAD_TC") != nullptr;       // A/B: the tensor-core head stage
+    if (d.D2 == HB_C && 4 * d.W == HB_W && 4 * d.H == HB_W && !head_tc)
+      CKF(launch_head_conv_f32(c2b, gss, wx.head_w, head_bias, classes, logits, s0, n, Te, T, num_sms, st));
+    else if (narrow & 16) CKF((launch_band<D5T>(p, num_sms, st)));
+    else CKF((launch_band<D5S>(p, num_sms, st)));
   }
   if (launches) *launches += nl;
   return cudaSuccess;

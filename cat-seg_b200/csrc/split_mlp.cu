@@ -39,7 +39,7 @@ constexpr uint32_t TM_H0 = 0, TM_Y = 256;
 template <int ACT>   // 0 = GELU (Swin), 1 = ReLU (class layer)
 __global__ void __launch_bounds__(SP_THREADS, 1)
 mlp_split_kernel(const float* __restrict__ Xin, const float* __restrict__ Xres, float* __restrict__ Xout, long long ntok,
-                 MlpSplitW w) {
+                 MlpSplitW w, int dbg_nostream) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + SP_BAR);        // [3]
   uint64_t* bar_empty = bar_full + 3;                                      // [3]
@@ -73,6 +73,7 @@ mlp_split_kernel(const float* __restrict__ Xin, const float* __restrict__ Xres, 
 
   split::WeightRing<3, WIMG_BYTES> ring;
   ring.init(smem + SP_RING, bar_full, bar_empty, w.wimg, 16, my_pass * 16);
+  ring.dbg_nostream = dbg_nostream;
   if (issuer) ring.prime();
   // one product chain A W^T with A = a_hi + a_lo and W = (next two ring images: hi, lo): 24 MMAs
   auto chain = [&](uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, bool acc) {
@@ -217,8 +218,10 @@ cudaError_t launch_mlp_split(const float* Xin, const float* Xres, float* Xout, l
   const long long npass = (ntok + 127) / 128;
   const int grid = (int)(npass < num_sms ? npass : num_sms);
   if (grid <= 0) return cudaSuccess;
-  if (act == 0) mlp_split_kernel<0><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w);
-  else mlp_split_kernel<1><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w);
+  static int dbg = -1;
+  if (dbg < 0) { const char* e2 = getenv("CATSEG_DBG_NOSTREAM"); dbg = e2 ? atoi(e2) : 0; }
+  if (act == 0) mlp_split_kernel<0><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w, dbg);
+  else mlp_split_kernel<1><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w, dbg);
   return cudaGetLastError();
 }
 
