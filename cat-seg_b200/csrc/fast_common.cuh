@@ -75,10 +75,11 @@ __device__ __forceinline__ void ln_rows_to_tile(const float* __restrict__ src, l
 // nullptr when only the single-term operand is needed (q/k path, tools/precision_study.py).
 __device__ __forceinline__ void ln_rows_to_tile_split(const float* __restrict__ src, long long row_stride, int nvalid,
                                                       uint8_t* tile_hi, uint8_t* tile_lo, const float* __restrict__ gamma,
-                                                      const float* __restrict__ beta, int warp, int nwarps, int lane) {
+                                                      const float* __restrict__ beta, int warp, int nwarps, int lane,
+                                                      int tile_rows = TILE) {
   const float4 g = ld4(gamma + lane * 4), be = ld4(beta + lane * 4);
   constexpr int R = 8;
-  for (int r0 = warp * R; r0 < TILE; r0 += nwarps * R) {
+  for (int r0 = warp * R; r0 < tile_rows; r0 += nwarps * R) {
     float4 x[R];
 #pragma unroll
     for (int i = 0; i < R; ++i) {

@@ -36,10 +36,16 @@ static_assert(STG_BYTES <= 4 * TILE_BYTES_T, "the fp32 staging tile aliases the 
 constexpr uint32_t TM_H0 = 0, TM_Y = 256;
 }  // namespace
 
-template <int ACT>   // 0 = GELU (Swin), 1 = ReLU (class layer)
+// Q0FREE: the tcgen05.mma issue rate collapses when the issuing warp shares its scheduler with ALU-bound warps (probe:
+// 16 MMAs take 11 K cycles to ISSUE next to three busy warps on the same scheduler, 1.2 K alone) -- and TMEM lane quarter q
+// can only be read by warps with warp % 4 == q, i.e. by warps of scheduler q.  With Q0FREE a pass holds 96 tokens in tile
+// rows 32..127: the warps of scheduler 0 have no rows and only keep the barriers company, the issuing warp (16 % 4 == 0) has
+// that scheduler to itself.  A quarter of every MMA is dead rows; the tensor pipe has the head-room (it is ~30 % busy).
+template <int ACT, bool Q0FREE>   // ACT: 0 = GELU (Swin), 1 = ReLU (class layer)
 __global__ void __launch_bounds__(SP_THREADS, 1)
 mlp_split_kernel(const float* __restrict__ Xin, const float* __restrict__ Xres, float* __restrict__ Xout, long long ntok,
-                 MlpSplitW w, int dbg_nostream) {
+                 MlpSplitW w, int dbg_nostream, long long* dbg) {
+  static_assert(SP_EPI_WARPS == 16, "warp 16 (the issuing warp) must land on scheduler 0");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + SP_BAR);        // [3]
   uint64_t* bar_empty = bar_full + 3;                                      // [3]
@@ -52,7 +58,8 @@ mlp_split_kernel(const float* __restrict__ Xin, const float* __restrict__ Xres, 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool issuer = __shfl_sync(0xffffffffu, warp, 0) == SP_EPI_WARPS;   // warp-uniform role
 
-  const long long npass = (ntok + 127) / 128;
+  constexpr int ROW0 = Q0FREE ? 32 : 0, TP = 128 - ROW0;      // first tile row in use, tokens per pass
+  const long long npass = (ntok + TP - 1) / TP;
   long long my_pass = 0;
   for (long long p = blockIdx.x; p < npass; p += gridDim.x) ++my_pass;
 
@@ -94,23 +101,38 @@ mlp_split_kernel(const float* __restrict__ Xin, const float* __restrict__ Xres, 
 
   const int q = warp & 3, cq = (warp >> 2) & 3;          // TMEM lane quarter, column quarter (32 columns)
   const int row = q * 32 + lane;
+  const bool worker = !issuer && (!Q0FREE || q != 0);     // warps that own tile rows
+  const int aw = Q0FREE ? (q - 1) + 3 * cq : warp;        // index among the NAW working warps (row-wise phases: 8 rows each)
+  constexpr int NAW = Q0FREE ? 12 : 16;
   float* stage = reinterpret_cast<float*>(smem + SP_XH);
   const uint32_t lane_addr = tm + ((uint32_t)(q * 32) << 16);
   uint32_t ph_h[2] = {0u, 0u}, ph_y = 0u;
 
+  // CATSEG_PHASE_TIMING=1: cycles per phase, accumulated by thread 32 (a working warp) and by the issuing warp of CTA 0
+  long long pt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_last = clock64(), npass_dbg = 0;
+  const bool timer = dbg != nullptr && blockIdx.x == 0 && (tid == 32 || tid == SP_EPI_THREADS);
+#define MPH(i) do { if (timer) { const long long _t = clock64(); pt[i] += _t - t_last; t_last = _t; } } while (0)
   for (long long p = blockIdx.x; p < npass; p += gridDim.x) {
-    const long long row0 = p * 128;
+    const long long row0 = p * TP;
+    ++npass_dbg;
     if (!issuer) {
-      const long long nrow0 = (p + gridDim.x) * 128;      // next pass: 512 lines of 128 bytes into L2
+      const long long nrow0 = (p + gridDim.x) * TP;       // next pass: 4 lines of 128 bytes per token row into L2
       const long long r = nrow0 + (tid >> 2);
-      if (r < ntok) umma::prefetch_l2(Xin + r * 128 + (tid & 3) * 32);
+      if ((tid >> 2) < TP && r < ntok) {
+        umma::prefetch_l2(Xin + r * 128 + (tid & 3) * 32);
+        if (Xres != nullptr) umma::prefetch_l2(Xres + r * 128 + (tid & 3) * 32);   // read once, in the Y epilogue
+      }
+    }
+    if (worker) {
       const long long nv = ntok - row0;
-      split::ln_rows_to_tile_split(Xin + row0 * 128, 128, nv >= 128 ? 128 : (int)nv, smem + SP_XH, smem + SP_XL, s_g, s_be,
-                                   warp, SP_EPI_WARPS, lane);
+      split::ln_rows_to_tile_split(Xin + row0 * 128, 128, nv >= TP ? TP : (int)nv, smem + SP_XH + ROW0 * 16, smem + SP_XL + ROW0 * 16,
+                                   s_g, s_be, aw, NAW, lane, TP);
       umma::fence_proxy_async();
     }
+    MPH(0);                                                // LayerNorm prologue
     umma::fence_before_sync();
     __syncthreads();
+    MPH(1);                                                // barrier after the prologue
     if (issuer) {
       umma::fence_after_sync();
       chain(tm + TM_H0, d_xh, d_xl, false);
@@ -123,9 +145,10 @@ mlp_split_kernel(const float* __restrict__ Xin, const float* __restrict__ Xres, 
 #pragma unroll 1
     for (int j = 0; j < 4; ++j) {
       const int hb = j & 1;
-      if (!issuer) {
+      if (worker) {
         umma::mbar_wait(&bar_h[hb], ph_h[hb]); ph_h[hb] ^= 1u;
         umma::fence_after_sync();
+        MPH(2);                                            // wait for H[j]
         uint4 phi[4], plo[4];
         {
           float v[32];
@@ -146,19 +169,23 @@ mlp_split_kernel(const float* __restrict__ Xin, const float* __restrict__ Xres, 
             umma::split_h2(v[c * 8 + 6], v[c * 8 + 7], phi[c].w, plo[c].w);
           }
         }
+        MPH(3);                                            // activation + split
         if (j > 0) {                                       // the hidden tiles are free once fc2 of chunk j-1 has completed
           umma::mbar_wait(bar_y, ph_y); ph_y ^= 1u;
           umma::fence_after_sync();
         }
+        MPH(4);                                            // wait for fc2(j-1)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           *reinterpret_cast<uint4*>(smem + SP_HH + (cq * 4 + c) * LBO_T + row * 16) = phi[c];
           *reinterpret_cast<uint4*>(smem + SP_HL + (cq * 4 + c) * LBO_T + row * 16) = plo[c];
         }
         umma::fence_proxy_async();
+        MPH(5);                                            // hidden tile stores
       }
       umma::fence_before_sync();
       __syncthreads();                                     // hidden tiles written; every warp has read H[hb]
+      MPH(6);                                              // chunk barrier (issuing warp: waiting for the workers)
       if (issuer) {
         umma::fence_after_sync();
         chain(tm + TM_Y, d_hh, d_hl, j > 0);
@@ -169,14 +196,15 @@ mlp_split_kernel(const float* __restrict__ Xin, const float* __restrict__ Xres, 
           if (umma::elect_one()) umma::mma_commit(&bar_h[hb]);
           __syncwarp();
         }
+        MPH(7);                                            // issuing warp: issuing the chains of this step
       }
     }
     // ---- Y epilogue: residual rows (coalesced, warp per row) are fetched before waiting for the last fc2 chain
     float4 xres[8];
-    if (!issuer) {
+    if (worker) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const long long r = row0 + warp * 8 + i;
+        const long long r = row0 + aw * 8 + i;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < ntok) {
           a = ld4(Xin + r * 128 + lane * 4);
@@ -186,6 +214,7 @@ mlp_split_kernel(const float* __restrict__ Xin, const float* __restrict__ Xres, 
       }
       umma::mbar_wait(bar_y, ph_y); ph_y ^= 1u;
       umma::fence_after_sync();
+      MPH(8);                                              // residual loads + wait for the last fc2 chain
       float v[32];
       umma::tmem_ld32(lane_addr + TM_Y + cq * 32, v);
       const float* bb = s_b2 + cq * 32;
@@ -195,15 +224,22 @@ mlp_split_kernel(const float* __restrict__ Xin, const float* __restrict__ Xres, 
     }
     umma::fence_before_sync();
     __syncthreads();
-    if (!issuer) {
+    if (worker) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const long long r = row0 + warp * 8 + i;
-        if (r < ntok) st4(Xout + r * 128 + lane * 4, f4add(xres[i], ld4(stage + (warp * 8 + i) * STG_LD + lane * 4)));
+        const long long r = row0 + aw * 8 + i;
+        if (r < ntok) st4(Xout + r * 128 + lane * 4, f4add(xres[i], ld4(stage + (ROW0 + aw * 8 + i) * STG_LD + lane * 4)));
       }
     }
     __syncthreads();
     umma::fence_after_sync();          // TMEM and the operand tiles may be overwritten by the next pass
+    MPH(9);                                                // Y epilogue: staging, barrier, coalesced stores, barrier
+  }
+#undef MPH
+  if (timer) {
+    long long* o = dbg + (tid == 32 ? 0 : 16);
+    for (int i = 0; i < 10; ++i) o[i] = pt[i];
+    o[10] = npass_dbg;
   }
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc<512>(tm);
@@ -211,17 +247,42 @@ mlp_split_kernel(const float* __restrict__ Xin, const float* __restrict__ Xres, 
 
 cudaError_t launch_mlp_split(const float* Xin, const float* Xres, float* Xout, long long ntok, const MlpSplitW& w, int act,
                              int num_sms, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(mlp_split_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(mlp_split_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM);
-  if (e != cudaSuccess) return e;
-  const long long npass = (ntok + 127) / 128;
+  static int q0free = -1;
+  if (q0free < 0) { const char* e3 = getenv("CATSEG_MLP_Q0FREE"); q0free = e3 ? atoi(e3) : 0; }
+  cudaError_t e = cudaSuccess;
+  for (auto* fn : {(const void*)mlp_split_kernel<0, false>, (const void*)mlp_split_kernel<1, false>,
+                   (const void*)mlp_split_kernel<0, true>, (const void*)mlp_split_kernel<1, true>})
+    if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM)) != cudaSuccess) return e;
+  const int tp = q0free ? 96 : 128;
+  const long long npass = (ntok + tp - 1) / tp;
   const int grid = (int)(npass < num_sms ? npass : num_sms);
   if (grid <= 0) return cudaSuccess;
   static int dbg = -1;
   if (dbg < 0) { const char* e2 = getenv("CATSEG_DBG_NOSTREAM"); dbg = e2 ? atoi(e2) : 0; }
-  if (act == 0) mlp_split_kernel<0><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w, dbg);
-  else mlp_split_kernel<1><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w, dbg);
+  static long long* tdbg = nullptr;
+  static int timing = -1;
+  if (timing < 0) {
+    const char* e4 = getenv("CATSEG_PHASE_TIMING");
+    timing = (e4 && e4[0] == '1') ? 1 : 0;
+    if (timing) { cudaMalloc(&tdbg, 32 * sizeof(long long)); cudaMemset(tdbg, 0, 32 * sizeof(long long)); }
+  }
+  if (q0free) {
+    if (act == 0) mlp_split_kernel<0, true><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w, dbg, tdbg);
+    else mlp_split_kernel<1, true><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w, dbg, tdbg);
+  } else {
+    if (act == 0) mlp_split_kernel<0, false><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w, dbg, tdbg);
+    else mlp_split_kernel<1, false><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w, dbg, tdbg);
+  }
+  if (timing) {
+    long long hb[32];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hb, tdbg, sizeof(hb), cudaMemcpyDeviceToHost);
+    const double n = hb[10] > 0 ? (double)hb[10] : 1.0;
+    fprintf(stderr, "[mlp_split act=%d q0free=%d, cycles per pass over %lld passes] worker: LN %.0f | bar %.0f | wait-H %.0f | act+split %.0f | "
+            "wait-fc2 %.0f | H stores %.0f | chunk bar %.0f | resid+wait-Y %.0f | Y epilogue %.0f  || issuer: idle-before-pass %.0f | bar %.0f | "
+            "chunk-bar wait %.0f | issue %.0f | tail %.0f\n", act, q0free, hb[10], hb[0] / n, hb[1] / n, hb[2] / n, hb[3] / n, hb[4] / n,
+            hb[5] / n, hb[6] / n, hb[8] / n, hb[9] / n, hb[16] / n, hb[17] / n, hb[22] / n, hb[23] / n, hb[25] / n);
+  }
   return cudaGetLastError();
 }
 
