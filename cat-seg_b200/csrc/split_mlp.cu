@@ -41,7 +41,7 @@ constexpr uint32_t TM_H0 = 0, TM_Y = 256;
 // can only be read by warps with warp % 4 == q, i.e. by warps of scheduler q.  With Q0FREE a pass holds 96 tokens in tile
 // rows 32..127: the warps of scheduler 0 have no rows and only keep the barriers company, the issuing warp (16 % 4 == 0) has
 // that scheduler to itself.  A quarter of every MMA is dead rows; the tensor pipe has the head-room (it is ~30 % busy).
-template <int ACT, bool Q0FREE>   // ACT: 0 = GELU (Swin), 1 = ReLU (class layer)
+template <int ACT, bool Q0FREE, bool TIMING>   // ACT: 0 = GELU (Swin), 1 = ReLU (class layer); TIMING: phase-timing build
 __global__ void __launch_bounds__(SP_THREADS, 1)
 mlp_split_kernel(const float* __restrict__ Xin, const float* __restrict__ Xres, float* __restrict__ Xout, long long ntok,
                  MlpSplitW w, int dbg_nostream, long long* dbg) {
@@ -109,12 +109,12 @@ mlp_split_kernel(const float* __restrict__ Xin, const float* __restrict__ Xres, 
   uint32_t ph_h[2] = {0u, 0u}, ph_y = 0u;
 
   // CATSEG_PHASE_TIMING=1: cycles per phase, accumulated by thread 32 (a working warp) and by the issuing warp of CTA 0
-  long long pt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_last = clock64(), npass_dbg = 0;
-  const bool timer = dbg != nullptr && blockIdx.x == 0 && (tid == 32 || tid == SP_EPI_THREADS);
-#define MPH(i) do { if (timer) { const long long _t = clock64(); pt[i] += _t - t_last; t_last = _t; } } while (0)
+  long long pt[TIMING ? 10 : 1] = {}, t_last = TIMING ? clock64() : 0, npass_dbg = 0;
+  const bool timer = TIMING && dbg != nullptr && blockIdx.x == 0 && (tid == 32 || tid == SP_EPI_THREADS);
+#define MPH(i) do { if constexpr (TIMING) { if (timer) { const long long _t = clock64(); pt[i] += _t - t_last; t_last = _t; } } } while (0)
   for (long long p = blockIdx.x; p < npass; p += gridDim.x) {
     const long long row0 = p * TP;
-    ++npass_dbg;
+    if constexpr (TIMING) ++npass_dbg;
     if (!issuer) {
       const long long nrow0 = (p + gridDim.x) * TP;       // next pass: 4 lines of 128 bytes per token row into L2
       const long long r = nrow0 + (tid >> 2);
@@ -236,10 +236,12 @@ mlp_split_kernel(const float* __restrict__ Xin, const float* __restrict__ Xres, 
     MPH(9);                                                // Y epilogue: staging, barrier, coalesced stores, barrier
   }
 #undef MPH
-  if (timer) {
-    long long* o = dbg + (tid == 32 ? 0 : 16);
-    for (int i = 0; i < 10; ++i) o[i] = pt[i];
-    o[10] = npass_dbg;
+  if constexpr (TIMING) {
+    if (timer) {
+      long long* o = dbg + (tid == 32 ? 0 : 16);
+      for (int i = 0; i < 10; ++i) o[i] = pt[i];
+      o[10] = npass_dbg;
+    }
   }
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc<512>(tm);
@@ -247,18 +249,6 @@ mlp_split_kernel(const float* __restrict__ Xin, const float* __restrict__ Xres, 
 
 cudaError_t launch_mlp_split(const float* Xin, const float* Xres, float* Xout, long long ntok, const MlpSplitW& w, int act,
                              int num_sms, cudaStream_t st) {
-  static int q0free = -1;
-  if (q0free < 0) { const char* e3 = getenv("CATSEG_MLP_Q0FREE"); q0free = e3 ? atoi(e3) : 0; }
-  cudaError_t e = cudaSuccess;
-  for (auto* fn : {(const void*)mlp_split_kernel<0, false>, (const void*)mlp_split_kernel<1, false>,
-                   (const void*)mlp_split_kernel<0, true>, (const void*)mlp_split_kernel<1, true>})
-    if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM)) != cudaSuccess) return e;
-  const int tp = q0free ? 96 : 128;
-  const long long npass = (ntok + tp - 1) / tp;
-  const int grid = (int)(npass < num_sms ? npass : num_sms);
-  if (grid <= 0) return cudaSuccess;
-  static int dbg = -1;
-  if (dbg < 0) { const char* e2 = getenv("CATSEG_DBG_NOSTREAM"); dbg = e2 ? atoi(e2) : 0; }
   static long long* tdbg = nullptr;
   static int timing = -1;
   if (timing < 0) {
@@ -266,12 +256,28 @@ cudaError_t launch_mlp_split(const float* Xin, const float* Xres, float* Xout, l
     timing = (e4 && e4[0] == '1') ? 1 : 0;
     if (timing) { cudaMalloc(&tdbg, 32 * sizeof(long long)); cudaMemset(tdbg, 0, 32 * sizeof(long long)); }
   }
-  if (q0free) {
-    if (act == 0) mlp_split_kernel<0, true><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w, dbg, tdbg);
-    else mlp_split_kernel<1, true><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w, dbg, tdbg);
+  static int q0free = -1;
+  if (q0free < 0) { const char* e3 = getenv("CATSEG_MLP_Q0FREE"); q0free = e3 ? atoi(e3) : 0; }
+  cudaError_t e = cudaSuccess;
+  for (auto* fn : {(const void*)mlp_split_kernel<0, false, false>, (const void*)mlp_split_kernel<1, false, false>,
+                   (const void*)mlp_split_kernel<0, true, false>, (const void*)mlp_split_kernel<1, true, false>,
+                   (const void*)mlp_split_kernel<0, false, true>, (const void*)mlp_split_kernel<1, false, true>})
+    if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM)) != cudaSuccess) return e;
+  const int tp = (q0free && !timing) ? 96 : 128;
+  const long long npass = (ntok + tp - 1) / tp;
+  const int grid = (int)(npass < num_sms ? npass : num_sms);
+  if (grid <= 0) return cudaSuccess;
+  static int dbg = -1;
+  if (dbg < 0) { const char* e2 = getenv("CATSEG_DBG_NOSTREAM"); dbg = e2 ? atoi(e2) : 0; }
+  if (timing) {
+    if (act == 0) mlp_split_kernel<0, false, true><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w, dbg, tdbg);
+    else mlp_split_kernel<1, false, true><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w, dbg, tdbg);
+  } else if (q0free) {
+    if (act == 0) mlp_split_kernel<0, true, false><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w, dbg, tdbg);
+    else mlp_split_kernel<1, true, false><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w, dbg, tdbg);
   } else {
-    if (act == 0) mlp_split_kernel<0, false><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w, dbg, tdbg);
-    else mlp_split_kernel<1, false><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w, dbg, tdbg);
+    if (act == 0) mlp_split_kernel<0, false, false><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w, dbg, tdbg);
+    else mlp_split_kernel<1, false, false><<<grid, SP_THREADS, SP_SMEM, st>>>(Xin, Xres, Xout, ntok, w, dbg, tdbg);
   }
   if (timing) {
     long long hb[32];

@@ -340,15 +340,19 @@ swin_attn2_kernel(float* __restrict__ X, const float* __restrict__ agT, int nwin
         {
           mx = fmaxf(fmaxf(red[row], red[144 + row]), fmaxf(red[288 + row], red[432 + row]));
           const float mb = mx * 1.4426950408889634f;
+          // The normaliser is the sum of the ROUNDED weights (what the P V MMAs multiply): numerator and denominator then see
+          // the same fp16 values and their rounding errors act on (v - o) only (tools/precision_study.py; split_common.cuh)
           float sum = 0.0f;
 #pragma unroll
-          for (int i = 0; i < 36; ++i) { sv[i] = umma::ex2_approx(fmaf(sv[i], 1.4426950408889634f, -mb)); sum += sv[i]; }
+          for (int i = 0; i < 36; ++i) sv[i] = umma::ex2_approx(fmaf(sv[i], 1.4426950408889634f, -mb));
           uint8_t* prow = smem + SM_P + row * 16;
 #pragma unroll
           for (int i = 0; i < 36; i += 4) {
             const int key = kq * 36 + i;
-            *reinterpret_cast<uint2*>(prow + (key >> 3) * LBO_P + (key & 7) * 2) =
-                make_uint2(umma::pack_h2(sv[i], sv[i + 1]), umma::pack_h2(sv[i + 2], sv[i + 3]));
+            const uint32_t p01 = umma::pack_h2(sv[i], sv[i + 1]), p23 = umma::pack_h2(sv[i + 2], sv[i + 3]);
+            *reinterpret_cast<uint2*>(prow + (key >> 3) * LBO_P + (key & 7) * 2) = make_uint2(p01, p23);
+            const float2 r01 = umma::unpack_h2(p01), r23 = umma::unpack_h2(p23);
+            sum += (r01.x + r01.y) + (r23.x + r23.y);
           }
           rsum[kq * 144 + row] = sum;
         }
@@ -363,13 +367,15 @@ swin_attn2_kernel(float* __restrict__ X, const float* __restrict__ agT, int nwin
           const float mb = mx1 * 1.4426950408889634f;
           float sum = 0.0f;
 #pragma unroll
-          for (int i = 0; i < 9; ++i) { tv[i] = umma::ex2_approx(fmaf(tv[i], 1.4426950408889634f, -mb)); sum += tv[i]; }
+          for (int i = 0; i < 9; ++i) tv[i] = umma::ex2_approx(fmaf(tv[i], 1.4426950408889634f, -mb));
           if (lane < 16) {
             uint8_t* prow = smem + SM_P + qrow * 16;
 #pragma unroll
             for (int i = 0; i < 9; ++i) {
               const int key = key0 + i;
-              *reinterpret_cast<__half*>(prow + (key >> 3) * LBO_P + (key & 7) * 2) = __float2half_rn(tv[i]);
+              const __half ph = __float2half_rn(tv[i]);
+              *reinterpret_cast<__half*>(prow + (key >> 3) * LBO_P + (key & 7) * 2) = ph;
+              sum += __half2float(ph);                       // sum of the rounded weights (see tile 0)
             }
             sum1[part * 16 + r1] = sum;
           }
