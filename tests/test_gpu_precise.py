@@ -14,7 +14,7 @@ from cat_seg_b200.synth import make_inputs, make_state_dict
 from oracle.aggregator_oracle import aggregator_forward
 
 pytestmark = pytest.mark.gpu
-PRECISE_MAXABS, PRECISE_RELL2, ARGMAX_GATE = 1e-4, 5e-5, 0.999
+PRECISE_MAXABS, PRECISE_RELL2, ARGMAX_GATE = 5e-5, 2.5e-5, 0.999      # measured on cfg4: 8.8e-6 / 5.8e-6 / 0.9999
 
 
 def _run(cfg, B, T, seed, precision, same_text=False):
