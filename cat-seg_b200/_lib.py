@@ -101,6 +101,9 @@ _SIGS = [
     ("catseg_last_launch_count", C.c_int, [C.c_void_p]),
     ("catseg_stitch_argmax", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("catseg_stitch_scratch_bytes", C.c_size_t, [C.c_int]),
+    ("catseg_stitch_argmax_ws", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     ("catseg_argmax", C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     ("catseg_argmax_batched", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     ("catseg_guidance_upsample", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -1334,15 +1334,30 @@ extern "C" int catseg_stage_times(catseg_handle* h, float* ms, int* calls, int r
 
 extern "C" int catseg_last_launch_count(const catseg_handle* h) { return h ? h->last_launches : 0; }
 
+static int stitch_impl(const float* win_logits, int T, int S, int kernel, int stride, int out_res, int height, int width,
+                       float* probs_out, int32_t* labels_out, void* scratch, size_t scratch_bytes, catseg_stream stream) {
+  if (!win_logits || T <= 0 || S <= 0 || height <= 0 || width <= 0) return CATSEG_ERR_INVALID;
+  if (!probs_out && !labels_out) return CATSEG_ERR_INVALID;
+  if (scratch && scratch_bytes < (size_t)T * sizeof(uint32_t)) return CATSEG_ERR_WORKSPACE;
+  cudaError_t e = launch_stitch(win_logits, T, S, kernel, stride, out_res, height, width, probs_out, labels_out,
+                                reinterpret_cast<uint32_t*>(scratch), (cudaStream_t)stream);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return e == cudaErrorInvalidValue ? CATSEG_ERR_INVALID : CATSEG_ERR_CUDA; }
+  return CATSEG_OK;
+}
+
 extern "C" int catseg_stitch_argmax(const float* win_logits, int T, int S, int kernel, int stride, int out_res,
                                     int height, int width, float* probs_out, int32_t* labels_out,
                                     catseg_stream stream) {
-  if (!win_logits || T <= 0 || S <= 0 || height <= 0 || width <= 0) return CATSEG_ERR_INVALID;
-  if (!probs_out && !labels_out) return CATSEG_ERR_INVALID;
-  cudaError_t e = launch_stitch(win_logits, T, S, kernel, stride, out_res, height, width, probs_out, labels_out,
-                                (cudaStream_t)stream);
-  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return e == cudaErrorInvalidValue ? CATSEG_ERR_INVALID : CATSEG_ERR_CUDA; }
-  return CATSEG_OK;
+  return stitch_impl(win_logits, T, S, kernel, stride, out_res, height, width, probs_out, labels_out, nullptr, 0, stream);
+}
+
+extern "C" size_t catseg_stitch_scratch_bytes(int T) { return T > 0 ? (size_t)T * sizeof(uint32_t) : 0; }
+
+extern "C" int catseg_stitch_argmax_ws(const float* win_logits, int T, int S, int kernel, int stride, int out_res,
+                                       int height, int width, float* probs_out, int32_t* labels_out, void* scratch,
+                                       size_t scratch_bytes, catseg_stream stream) {
+  if (!scratch) return CATSEG_ERR_INVALID;
+  return stitch_impl(win_logits, T, S, kernel, stride, out_res, height, width, probs_out, labels_out, scratch, scratch_bytes, stream);
 }
 
 extern "C" int catseg_argmax_batched(const float* scores, int batch, int T, int64_t npix, int32_t* labels_out,

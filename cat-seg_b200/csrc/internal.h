@@ -285,8 +285,9 @@ cudaError_t run_decoder_split(const float* X, const float* dg0, const float* dg1
                               int* launches, cudaStream_t st);
 
 // ---------------------------------------------------------------- stitch.cu
+// scratch_mask: T uint32 of device scratch (enables the skipping of dropped-class planes), or nullptr
 cudaError_t launch_stitch(const float* win_logits, int T, int S, int kernel, int stride, int out_res, int height,
-                          int width, float* probs_out, int32_t* labels_out, cudaStream_t st);
+                          int width, float* probs_out, int32_t* labels_out, uint32_t* scratch_mask, cudaStream_t st);
 cudaError_t launch_argmax(const float* scores, int batch, int T, long long npix, int32_t* labels, cudaStream_t st);
 // guidance_pyramid.cu: ConvTranspose2d(stride == kernel) from hooked CLIP tokens, CLS strip + NCHW transpose
 cudaError_t launch_guidance_upsample(const float* tokens, const float* weight, const float* bias, float* out, int B,

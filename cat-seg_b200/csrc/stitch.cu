@@ -112,7 +112,7 @@ __global__ void stitch_kernel(const float* __restrict__ win_logits, int T, int S
 // the same fp32 expression order as stitch_kernel above; what changes is that the four global-view samples per
 // stitched value (and, when postprocess resizes, the four stitched values per output pixel) are shared through shared
 // memory instead of being recomputed by every thread: ~2 instead of 8 sigmoid(bilinear) evaluations per pixel and class.
-constexpr int ST_TILE = 16, ST_RMAX = 36, ST_GMAX = 26, ST_MAXT = 4;
+constexpr int ST_TILE = 16, ST_RMAX = 36, ST_GMAX = 26, ST_MAXT = 4, ST_G = 8;
 
 // sigmoid on the MUFU pipe: ex2.approx + rcp.approx.  |error| <= ~1e-7 on a probability (relative 3e-7 on exp for
 // |x| <= 10, damped by p(1-p) <= 1/4); the parity tolerance on stitched probabilities is 2e-6 (tests/test_gpu_parity.py).
@@ -120,11 +120,42 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f,
 
 struct LerpE { int o0, o1; float l0, l1; };      // like Lerp, with the row indices pre-multiplied where useful
 
-__global__ void __launch_bounds__(ST_TILE * ST_TILE)
+// Which (window, class) planes are dropped classes?  The Aggregator writes exactly -100.0 into every pixel of a class
+// that the top-256 truncation dropped (model.py:721-724), bilinear interpolation of a constant plane stays within
+// rounding of -100, and sigmoid of that is exactly 0.0 in fp32 (exp(100) overflows): a plane whose S*S values ALL equal
+// -100.0 contributes exactly nothing.  With T = 847 about 70 % of the planes are such planes.  One CTA per class scans its
+// nwin planes (the whole logits tensor is read once: 156 MB for five windows of A-847) and writes a bit mask.
+__global__ void __launch_bounds__(256) plane_live_kernel(const float* __restrict__ win_logits, int T, int nwin, int plane4,
+                                                         uint32_t* __restrict__ mask) {
+  const int t = blockIdx.x;
+  __shared__ uint32_t s_m;
+  if (threadIdx.x == 0) s_m = 0u;
+  __syncthreads();
+  uint32_t m = 0u;
+  for (int w = 0; w < nwin; ++w) {
+    const float4* p = reinterpret_cast<const float4*>(win_logits) + ((long long)w * T + t) * plane4;
+    bool live = false;
+    for (int i = threadIdx.x; i < plane4; i += 256) {
+      const float4 v = __ldg(p + i);
+      live |= (v.x != -100.0f) | (v.y != -100.0f) | (v.z != -100.0f) | (v.w != -100.0f);
+    }
+    if (__any_sync(0xffffffffu, live)) m |= 1u << w;
+  }
+  if ((threadIdx.x & 31) == 0 && m) atomicOr(&s_m, m);
+  __syncthreads();
+  if (threadIdx.x == 0) mask[t] = s_m;
+}
+
+// `mask` (optional): bit w of mask[t] = plane (w, t) is live (plane_live_kernel); nullptr = every plane is evaluated.
+__global__ void __launch_bounds__(ST_TILE * ST_TILE, 3)
 stitch_tiled_kernel(const float* __restrict__ win_logits, int T, int S, int kernel, int stride, int out_res, int ntile,
-                    int height, int width, float* __restrict__ probs_out, int32_t* __restrict__ labels_out) {
-  __shared__ float s_g[ST_GMAX * ST_GMAX];
-  __shared__ float s_v[ST_RMAX * ST_RMAX];
+                    int height, int width, float* __restrict__ probs_out, int32_t* __restrict__ labels_out,
+                    const uint32_t* __restrict__ mask) {
+  extern __shared__ __align__(16) float st_dyn[];                     // s_g | s_v | live class ids [T] (uint16)
+  float* s_g = st_dyn;
+  float* s_v = st_dyn + ST_G * ST_GMAX * ST_GMAX;
+  uint16_t* s_live = reinterpret_cast<uint16_t*>(s_v + ST_G * ST_RMAX * ST_RMAX);
+  __shared__ int s_nlive;
   // class-independent interpolation tables (built once per CTA)
   __shared__ LerpE s_gy[ST_GMAX], s_gx[ST_GMAX];                     // kernel-grid patch row/col -> source rows (x S) / cols
   __shared__ LerpE s_ty[ST_RMAX][ST_MAXT], s_tx[ST_RMAX][ST_MAXT];   // out_res patch row/col x tile -> source rows (x S) / cols; o0 < 0: not covered
@@ -196,55 +227,117 @@ stitch_tiled_kernel(const float* __restrict__ win_logits, int T, int S, int kern
       einv[k] = (cnt & (cnt - 1)) == 0 ? 1.0f / (float)cnt : -(float)cnt;
     }
   }
+  // ---- live classes of this image (mask != 0), ascending; dropped classes have stitched value exactly 0 everywhere
+  int nlive = 0;
+  if (mask != nullptr) {
+    if (tid == 0) {
+      int n = 0;
+      for (int t = 0; t < T; ++t) if (__ldg(mask + t) != 0u) s_live[n++] = (uint16_t)t;
+      s_nlive = n;
+    }
+    __syncthreads();
+    nlive = s_nlive;
+  } else {
+    nlive = T;
+  }
   float best = -INFINITY;
   int best_t = 0;
-  for (int t = 0; t < T; ++t) {
-    // ---- phase A: global view on the kernel grid
-    const float* gp = win_logits + ((long long)(ntile * ntile) * T + t) * plane;
+  if (mask != nullptr) {
+    // first-maximum rule with the skipped classes: their value 0.0 can only win from the front of the class axis (every
+    // stitched value is >= 0, and a later class needs a strictly larger one)
+    if (nlive == 0 || s_live[0] != 0) { best = 0.0f; best_t = 0; }
+    if (probs_out != nullptr && live) {
+      int k = 0;
+      for (int t = 0; t < T; ++t) {
+        if (k < nlive && s_live[k] == t) { ++k; continue; }
+        probs_out[(long long)t * height * width + (long long)oy * width + ox] = 0.0f;
+      }
+    }
+  }
+  // ST_G classes per round: one barrier pair per round instead of per class, and ST_G times as many independent loads in
+  // flight (the loop is latency bound: every class brings new planes from L2)
+  for (int l0 = 0; l0 < nlive; l0 += ST_G) {
+    int tt[ST_G];
+    uint32_t mm[ST_G];
 #pragma unroll
-    for (int k = 0; k < NA; ++k)
-      if (ea[k] >= 0) s_g[tid + k * ST_TILE * ST_TILE] = sample(gp, s_gy[ea[k] >> 8], s_gx[ea[k] & 255]);
+    for (int c = 0; c < ST_G; ++c) {
+      const int l = l0 + c;
+      tt[c] = l < nlive ? (mask != nullptr ? (int)s_live[l] : l) : -1;
+      mm[c] = tt[c] < 0 ? 0u : (mask != nullptr ? __ldg(mask + tt[c]) : 0xffffffffu);
+    }
+    // ---- phase A: global view on the kernel grid (not needed when the global window dropped the class).  The interpolation
+    //      entry of a sample is class independent: it is fetched once and applied to the ST_G classes of the round
+    const long long gplane0 = (long long)(ntile * ntile) * T * plane;
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+      if (ea[k] < 0) continue;
+      const LerpE a = s_gy[ea[k] >> 8], b = s_gx[ea[k] & 255];
+#pragma unroll
+      for (int c = 0; c < ST_G; ++c)
+        if ((mm[c] >> (ntile * ntile)) & 1u)
+          s_g[c * (ST_GMAX * ST_GMAX) + tid + k * ST_TILE * ST_TILE] = sample(win_logits + gplane0 + (long long)tt[c] * plane, a, b);
+    }
     __syncthreads();
     // ---- phase B: stitched value on the out_res grid
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
       if (eb[k] < 0) continue;
       const int ry = eb[k] >> 8, rx = eb[k] & 255;
-      float acc = 0.0f;
+      float acc[ST_G];
+#pragma unroll
+      for (int c = 0; c < ST_G; ++c) acc[c] = 0.0f;
       for (int ty = ntile - 1; ty >= 0; --ty) {
         const LerpE a = s_ty[ry][ty];
         if (a.o0 < 0) continue;
         for (int tx = ntile - 1; tx >= 0; --tx) {
           const LerpE b = s_tx[rx][tx];
           if (b.o0 < 0) continue;
-          acc += sample(win_logits + ((long long)(ty * ntile + tx) * T + t) * plane, a, b);
+          const int w = ty * ntile + tx;
+          const float* wp = win_logits + (long long)w * T * plane;
+#pragma unroll
+          for (int c = 0; c < ST_G; ++c)
+            if ((mm[c] >> w) & 1u) acc[c] += sample(wp + (long long)tt[c] * plane, a, b);     // a dropped plane adds exactly 0.0
         }
       }
-      acc = einv[k] > 0.0f ? acc * einv[k] : acc / -einv[k];
       const LerpE a = s_vy[ry], b = s_vx[rx];
-      const float g = a.l0 * (b.l0 * s_g[a.o0 + b.o0] + b.l1 * s_g[a.o0 + b.o1]) + a.l1 * (b.l0 * s_g[a.o1 + b.o0] + b.l1 * s_g[a.o1 + b.o1]);
-      s_v[tid + k * ST_TILE * ST_TILE] = (acc + g) * 0.5f;
+#pragma unroll
+      for (int c = 0; c < ST_G; ++c) {
+        if (mm[c] == 0u) continue;
+        const float* sg = s_g + c * (ST_GMAX * ST_GMAX);
+        const float av = einv[k] > 0.0f ? acc[c] * einv[k] : acc[c] / -einv[k];
+        const float g = ((mm[c] >> (ntile * ntile)) & 1u)
+                            ? a.l0 * (b.l0 * sg[a.o0 + b.o0] + b.l1 * sg[a.o0 + b.o1]) + a.l1 * (b.l0 * sg[a.o1 + b.o0] + b.l1 * sg[a.o1 + b.o1])
+                            : 0.0f;
+        s_v[c * (ST_RMAX * ST_RMAX) + tid + k * ST_TILE * ST_TILE] = (av + g) * 0.5f;
+      }
     }
     __syncthreads();
     // ---- phase C: this thread's output pixel
     if (live) {
-      float v;
-      if (identity) {
-        v = s_v[(oy - Ya) * RX + (ox - Xa)];
-      } else {
-        const float* v0 = s_v + (pa.i0 - Ya) * RX - Xa;
-        const float* v1 = s_v + (pa.i1 - Ya) * RX - Xa;
-        v = pa.l0 * (pb.l0 * v0[pb.i0] + pb.l1 * v0[pb.i1]) + pa.l1 * (pb.l0 * v1[pb.i0] + pb.l1 * v1[pb.i1]);
+#pragma unroll
+      for (int c = 0; c < ST_G; ++c) {
+        if (mm[c] == 0u) continue;
+        const float* sv = s_v + c * (ST_RMAX * ST_RMAX);
+        float v;
+        if (identity) {
+          v = sv[(oy - Ya) * RX + (ox - Xa)];
+        } else {
+          const float* v0 = sv + (pa.i0 - Ya) * RX - Xa;
+          const float* v1 = sv + (pa.i1 - Ya) * RX - Xa;
+          v = pa.l0 * (pb.l0 * v0[pb.i0] + pb.l1 * v0[pb.i1]) + pa.l1 * (pb.l0 * v1[pb.i0] + pb.l1 * v1[pb.i1]);
+        }
+        if (probs_out) probs_out[(long long)tt[c] * height * width + (long long)oy * width + ox] = v;
+        if (v > best) { best = v; best_t = tt[c]; }
       }
-      if (probs_out) probs_out[(long long)t * height * width + (long long)oy * width + ox] = v;
-      if (v > best) { best = v; best_t = t; }
     }
+    // (the next round's phase A writes s_g only, which phase B of this round has finished reading before the barrier above;
+    //  its phase B writes s_v after the next barrier, by which time every thread has left this phase C)
   }
   if (live && labels_out) labels_out[(long long)oy * width + ox] = best_t;
 }
 
 cudaError_t launch_stitch(const float* win_logits, int T, int S, int kernel, int stride, int out_res, int height,
-                          int width, float* probs_out, int32_t* labels_out, cudaStream_t st) {
+                          int width, float* probs_out, int32_t* labels_out, uint32_t* scratch_mask, cudaStream_t st) {
   if (kernel > out_res || stride <= 0 || (out_res - kernel) % stride != 0) return cudaErrorInvalidValue;
   int ntile = (out_res - kernel) / stride + 1;
   long long n = (long long)height * width;
@@ -255,8 +348,14 @@ cudaError_t launch_stitch(const float* win_logits, int T, int S, int kernel, int
   const int gmax = (int)(rmax * (double)kernel / (double)out_res) + 3;
   if (rmax <= ST_RMAX && gmax <= ST_GMAX && ntile <= ST_MAXT) {
     dim3 grid((unsigned)((width + ST_TILE - 1) / ST_TILE), (unsigned)((height + ST_TILE - 1) / ST_TILE));
-    stitch_tiled_kernel<<<grid, ST_TILE * ST_TILE, 0, st>>>(win_logits, T, S, kernel, stride, out_res, ntile, height, width,
-                                                           probs_out, labels_out);
+    const int nwin = ntile * ntile + 1;
+    const bool use_mask = scratch_mask != nullptr && nwin <= 32 && T <= 6000 && (S * S) % 4 == 0 && (reinterpret_cast<uintptr_t>(win_logits) & 15) == 0;
+    if (use_mask) plane_live_kernel<<<T, 256, 0, st>>>(win_logits, T, nwin, S * S / 4, scratch_mask);
+    const size_t dyn = (size_t)ST_G * (ST_GMAX * ST_GMAX + ST_RMAX * ST_RMAX) * sizeof(float) + (use_mask ? (size_t)T * 2 : 0);
+    cudaError_t e = cudaFuncSetAttribute(stitch_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    stitch_tiled_kernel<<<grid, ST_TILE * ST_TILE, dyn, st>>>(win_logits, T, S, kernel, stride, out_res, ntile, height, width,
+                                                             probs_out, labels_out, use_mask ? scratch_mask : nullptr);
   } else {                                       // extreme down-scaling: one thread per pixel recomputes everything
     stitch_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(win_logits, T, S, kernel, stride, out_res, ntile,
                                                                height, width, probs_out, labels_out);

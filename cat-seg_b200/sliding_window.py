@@ -52,8 +52,11 @@ def make_windows(image: torch.Tensor, kernel: int = KERNEL, overlap: float = OVE
 
 
 def stitch(win_logits: torch.Tensor, height: int = OUT_RES, width: int = OUT_RES, kernel: int = KERNEL,
-           overlap: float = OVERLAP, out_res: int = OUT_RES, want_probs: bool = False, want_labels: bool = True):
-    """win_logits [ntile+1, T, S, S] (CUDA fp32) -> (probs [T,height,width] or None, labels int32 [height,width] or None)."""
+           overlap: float = OVERLAP, out_res: int = OUT_RES, want_probs: bool = False, want_labels: bool = True,
+           skip_dropped: bool = True):
+    """win_logits [ntile+1, T, S, S] (CUDA fp32) -> (probs [T,height,width] or None, labels int32 [height,width] or None).
+    skip_dropped: planes that hold -100 everywhere (classes dropped by the top-256 truncation; their sigmoid is exactly 0)
+    are found by a pre-pass and skipped -- the result is bit-identical, only faster."""
     if not win_logits.is_cuda:
         raise RuntimeError("catseg_b200.stitch runs on CUDA tensors only (no CPU fallback)")
     lib = _lib.load()
@@ -67,10 +70,14 @@ def stitch(win_logits: torch.Tensor, height: int = OUT_RES, width: int = OUT_RES
     probs = torch.empty(T, height, width, dtype=torch.float32, device=dev) if want_probs else None
     labels = torch.empty(height, width, dtype=torch.int32, device=dev) if want_labels else None
     with torch.cuda.device(dev):
-        rc = lib.catseg_stitch_argmax(C.c_void_p(x.data_ptr()), T, S, kernel, stride, out_res, height, width,
-                                      C.c_void_p(probs.data_ptr()) if want_probs else None,
-                                      C.c_void_p(labels.data_ptr()) if want_labels else None,
-                                      C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        args = [C.c_void_p(x.data_ptr()), T, S, kernel, stride, out_res, height, width,
+                C.c_void_p(probs.data_ptr()) if want_probs else None, C.c_void_p(labels.data_ptr()) if want_labels else None]
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        if skip_dropped:
+            scratch = torch.empty(lib.catseg_stitch_scratch_bytes(T), dtype=torch.uint8, device=dev)
+            rc = lib.catseg_stitch_argmax_ws(*args, C.c_void_p(scratch.data_ptr()), scratch.numel(), stream)
+        else:
+            rc = lib.catseg_stitch_argmax(*args, stream)
     if rc != 0:
         raise RuntimeError(f"catseg_stitch_argmax failed ({rc}): {lib.catseg_last_error(None).decode()}")
     return probs, labels

@@ -130,6 +130,29 @@ def test_stitch_matches_oracle():
         assert torch.equal(sw.argmax(ref_p.cuda()).cpu().long(), ref_l)
 
 
+def test_stitch_skipping_dropped_planes_is_bit_identical():
+    """The pre-pass that finds planes holding -100 everywhere (dropped classes) and skips them must not change a single bit:
+    classes dropped in every window, in some windows only, in the global view only, and a live plane that merely STARTS with
+    -100 values."""
+    g = torch.Generator().manual_seed(17)
+    T = 23
+    logits = torch.randn(5, T, 96, 96, generator=g) * 2
+    logits[:, 3] = -100.0                       # dropped everywhere
+    logits[0, 5] = -100.0                       # dropped in one tile
+    logits[1:4, 6] = -100.0                     # dropped in three tiles
+    logits[4, 7] = -100.0                       # dropped in the global view only
+    logits[:4, 8] = -100.0                      # live in the global view only
+    logits[2, 9, :40] = -100.0                  # NOT a dropped plane: only its first rows are -100
+    logits[:, 0] = -100.0                       # class 0 dropped: the first-maximum rule must still see its zeros
+    x = logits.cuda()
+    for (h, w) in [(640, 640), (500, 375)]:
+        p0, l0 = sw.stitch(x, h, w, want_probs=True, want_labels=True, skip_dropped=False)
+        p1, l1 = sw.stitch(x, h, w, want_probs=True, want_labels=True, skip_dropped=True)
+        assert torch.equal(p0, p1) and torch.equal(l0, l1)
+        l2 = sw.stitch(x, h, w, want_probs=False, want_labels=True, skip_dropped=True)[1]
+        assert torch.equal(l2, l0)
+
+
 def test_argmax_batched_matches_torch():
     g = torch.Generator().manual_seed(3)
     s = torch.randn(3, 37, 50, 7, generator=g)
