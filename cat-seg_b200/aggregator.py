@@ -303,9 +303,11 @@ class Aggregator(nn.Module):
                                                       C.cast(cb, C.c_void_p), None, stream)
             else:
                 nbytes = lib.catseg_exchange_buffer_bytes(self._handle, B, T, world)
-                if self._peer is None or self._peer.nbytes < nbytes or self._peer.group is not group:
-                    self._peer = None
-                    self._peer = PeerExchange(nbytes, dev, group)
+                lbytes = lib.catseg_exchange_logits_bytes(self._handle, B, T) if gather else 0
+                if self._peer is None or self._peer.nbytes < nbytes or self._peer.lbytes < lbytes or self._peer.group is not group:
+                    if self._peer is not None:
+                        self._peer.close()
+                    self._peer = PeerExchange(nbytes, dev, group, logits_bytes=lbytes)
                 peer = self._peer
 
                 def _barrier(_ctx, _stream):                    # orders the peer stores of the transposition kernels
@@ -320,8 +322,12 @@ class Aggregator(nn.Module):
                     raise ValueError(f"barrier must be 'device' or 'collective', got {barrier!r}")
                 cb = _lib.BARRIER_FN(_barrier)
                 rc = lib.catseg_forward_class_sharded_a2a(self._handle, *ptrs, C.c_void_p(ws.data_ptr()), ws.numel(), B, T, rank, world,
-                                                          peer.xb, peer.pb, peer.nbytes,
+                                                          peer.xb, peer.pb, peer.nbytes, peer.lb if gather else None,
                                                           C.cast(cb, C.c_void_p) if barrier == "collective" else None, None, stream)
+                if rc == 0 and not errors and gather:
+                    # peer-direct: every rank's buffer already holds the complete [B,T,4H,4W] logits (a view of the peer
+                    # buffer: it is overwritten by the next call)
+                    return peer.logits_view(B, T, 4 * H, 4 * W)
             if errors:
                 raise errors[0]
             if rc != 0:
@@ -391,17 +397,18 @@ class PeerExchange:
     library with cudaMalloc, published as CUDA IPC handles over the process group, mapped on every other rank of the node.
     ``xb`` / ``pb`` are the ctypes pointer arrays catseg_forward_class_sharded_a2a takes (entry r = rank r's buffer)."""
 
-    def __init__(self, nbytes: int, device: torch.device, group=None):
+    def __init__(self, nbytes: int, device: torch.device, group=None, logits_bytes: int = 0):
         import torch.distributed as dist
         lib = _lib.load()
-        self.nbytes, self.group, self.device = int(nbytes), group, device
+        self.nbytes, self.lbytes, self.group, self.device = int(nbytes), int(logits_bytes), group, device
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         self._lib, self._own, self._opened = lib, [], []
         handles = []
+        sizes = [self.nbytes, self.nbytes] + ([self.lbytes] if self.lbytes else [])
         with torch.cuda.device(device):
-            for _ in range(2):
+            for nb in sizes:
                 p = C.c_void_p()
-                if lib.catseg_peer_alloc(self.nbytes, C.byref(p)) != 0:
+                if lib.catseg_peer_alloc(nb, C.byref(p)) != 0:
                     raise RuntimeError("catseg_peer_alloc failed: " + lib.catseg_last_error(None).decode())
                 self._own.append(p.value)
                 hbuf = C.create_string_buffer(64)
@@ -410,9 +417,9 @@ class PeerExchange:
                 handles.append(hbuf.raw)
             everyone = [None] * world
             dist.all_gather_object(everyone, handles, group=group)
-            self.xb, self.pb = (C.c_void_p * world)(), (C.c_void_p * world)()
+            self.xb, self.pb, self.lb = (C.c_void_p * world)(), (C.c_void_p * world)(), (C.c_void_p * world)()
             for r in range(world):
-                for k, arr in enumerate((self.xb, self.pb)):
+                for k, arr in enumerate((self.xb, self.pb, self.lb)[:len(sizes)]):
                     if r == rank:
                         arr[r] = self._own[k]
                     else:
@@ -422,6 +429,21 @@ class PeerExchange:
                         self._opened.append(q.value)
                         arr[r] = q.value
             self.flag = torch.zeros(1, dtype=torch.float32, device=device)
+
+    def logits_view(self, *shape) -> torch.Tensor:
+        """This rank's full-logits peer buffer as a torch tensor (no copy; CUDA array interface)."""
+        n = 1
+        for d in shape:
+            n *= d
+        assert 4 * n <= self.lbytes
+
+        class _Holder:
+            pass
+
+        holder = _Holder()
+        holder.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (self._own[2], False), "version": 2}
+        holder.owner = self
+        return torch.as_tensor(holder, device=self.device)
 
     def close(self):
         if self._lib is None:

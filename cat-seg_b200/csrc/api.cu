@@ -60,7 +60,7 @@ struct catseg_handle {
   DecoderFastW dec_fast{};
   float head_bias_host = 0.0f;
   cudaStream_t aux_stream = nullptr;            // fork/join inside catseg_forward: guidance projections run beside the cost volume
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;   // join2: decoder guidance + additive maps ready
   __nv_bfloat16* prep_img = nullptr;            // FAST_PREP: embedding images, then the three guidance-conv image sets
   const __nv_bfloat16 *embed_img = nullptr, *gconv_img[3] = {nullptr, nullptr, nullptr};   // nullptr: shape not covered -> fp32 kernel
   __half* gconv_split_store = nullptr;          // PRECISE: fp16 [Wh | Wl] images of the three guidance convolutions
@@ -240,7 +240,8 @@ extern "C" int catseg_create(const catseg_config* cfg, catseg_handle** out) {
   // everything catseg_forward needs besides the caller's buffers is created here: the library does not allocate on the hot path
   if (cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming) != cudaSuccess) {
     catseg_destroy(h);
     return fail(nullptr, CATSEG_ERR_CUDA, "stream / event creation failed");
   }
@@ -265,6 +266,7 @@ extern "C" int catseg_destroy(catseg_handle* h) {
   if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_join2) cudaEventDestroy(h->ev_join2);
   delete h;
   return CATSEG_OK;
 }
@@ -860,6 +862,7 @@ extern "C" int catseg_set_vocabulary(catseg_handle* h, const float* text_feats, 
 struct ShardExchange {
   catseg_allreduce_fn allreduce; void* ar_ctx;
   float* const* xb; float* const* pb; size_t buf_bytes; catseg_barrier_fn barrier; void* bar_ctx;
+  float* const* lb;      // optional: every rank's FULL logits buffer [B][T][16 HW]; the head kernel stores into all of them
 };
 
 // peer buffer = [residual-stream data][per-class maxima B*T floats][barrier flag block]
@@ -872,7 +875,7 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
                         const catseg_taps* taps, int shard_rank, int shard_world, const ShardExchange* xc,
                         int32_t* kept_out, catseg_stream stream) {
   if (!h) return CATSEG_ERR_INVALID;
-  if (!img || !g0 || !g1 || !g2 || !logits || !workspace) return fail(h, CATSEG_ERR_INVALID, "null tensor pointer");
+  if (!img || !g0 || !g1 || !g2 || !workspace || (!logits && !(xc && xc->lb))) return fail(h, CATSEG_ERR_INVALID, "null tensor pointer");
   if (B <= 0 || T <= 0) return fail(h, CATSEG_ERR_INVALID, "B and T must be positive (got %d, %d)", B, T);
   if (!h->finalized) return fail(h, CATSEG_ERR_WEIGHTS, "catseg_finalize_params has not been called");
   const bool use_vocab = text == nullptr;
@@ -1049,6 +1052,9 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
     CUDA_OK(h, cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));     // ev_fork was recorded at the start of the stage
     cudaStream_t st = h->aux_stream;             // shadows: the launches below go to the internal stream
     const bool gsplit = prep_fast && h->split;
+    // peer-direct logits: this rank's full buffer is pre-filled with -100 here (dropped classes, model.py:721); the peers'
+    // head kernels store the kept planes much later, after barriers that this stream's join precedes
+    if (a2a && xc->lb && p.truncated) RUN(launch_fill(xc->lb[shard_rank], -100.0f, (long long)B * T * 16 * p.HW, st));
     if (gsplit && h->gconv_split_img[0]) RUN(launch_gconv_split(0, g0, h->gconv_split_img[0], h->gproj_b, ws + p.app_g, B, p.Cg, st));
     else if (gconv_fast && h->gconv_img[0]) RUN(launch_gconv_fast(0, g0, h->gconv_img[0], h->gproj_b, ws + p.app_g, B, p.Cg, st));
     else RUN(launch_conv3x3_nchw(g0, h->gproj_wt, h->gproj_b, ws + p.app_g, B, p.Cg, p.H, p.W, 128, st));
@@ -1058,6 +1064,10 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
         RUN(launch_linear(ws + p.app_gn, h->swin[l * 2 + k].wg_qk_t, h->swin[l * 2 + k].bqk,
                           ws + p.ag_qk + (size_t)(l * 2 + k) * B * p.HW * 256, (long long)B * p.HW, 256, 128, 0, st));
     }
+    // the Swin blocks only need the projected appearance guidance: join here; the decoder guidance (and, PRECISE, the
+    // decoder's per-image additive maps) stay on the internal stream and are joined right before the decoder
+    CUDA_OK(h, cudaEventRecord(h->ev_join, st));
+    CUDA_OK(h, cudaStreamWaitEvent(mainst, h->ev_join, 0));
     if (gsplit && h->gconv_split_img[1])
       RUN(launch_gconv_split(1, g1, h->gconv_split_img[1], h->dgp_b[0], ws + p.dg0, B, c.decoder_guidance_dims[0], st));
     else if (gconv_fast && h->gconv_img[1])
@@ -1072,8 +1082,12 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
     else
       RUN(launch_conv3x3_nchw(g2, h->dgp_wt[1], h->dgp_b[1], ws + p.dg1, B, c.decoder_guidance_dims[1], 4 * p.H, 4 * p.W,
                               p.dd.G2, st));
-    CUDA_OK(h, cudaEventRecord(h->ev_join, st));
-    CUDA_OK(h, cudaStreamWaitEvent(mainst, h->ev_join, 0));
+    if ((h->fast_mask & CATSEG_FAST_DECODER) && h->split) {
+      cudaError_t e = decoder_split_prepare(ws + p.dg0, ws + p.dg1, B, p.dd, h->dec_fast, ws + p.dec, &nl, st);
+      if (e != cudaSuccess) return fail(h, CATSEG_ERR_CUDA, "decoder maps: %s", cudaGetErrorString(e));
+    }
+    CUDA_OK(h, cudaEventRecord(h->ev_join2, st));
+    if (taps) CUDA_OK(h, cudaStreamWaitEvent(mainst, h->ev_join2, 0));     // the taps below copy the decoder guidance
   }
   seg.end();
   if (taps) {
@@ -1188,11 +1202,17 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
   }
 
   // ---------------- decoder + scatter (model.py:720-724)
+  CUDA_OK(h, cudaStreamWaitEvent(st, h->ev_join2, 0));       // decoder guidance / additive maps from the internal stream
   seg.begin(CATSEG_STAGE_DECODER);
   // class-sharded: the output is the compact local buffer [B][Te][16 HW]: plane ids are 0..Te-1 and T_out = Te
   const int32_t* out_ids = classes;
   int T_out = T;
-  if (sharded) {
+  PeerPtrs lpeers{};
+  const int nlp = (a2a && xc->lb) ? shard_world : 0;
+  for (int r = 0; r < nlp; ++r) lpeers.p[r] = xc->lb[r];
+  if (nlp > 0) {
+    // every rank's full [B][T][16 HW] buffer receives this rank's planes at their class ids (no all-gather, no assembly)
+  } else if (sharded) {
     int32_t* ids = reinterpret_cast<int32_t*>(ws + p.classes_loc) + (size_t)B * p.Te;
     RUN(launch_iota_classes(ids, B, Te, st));
     out_ids = ids;
@@ -1203,10 +1223,17 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
   if (h->fast_mask & CATSEG_FAST_DECODER) {
     if (taps && (taps->up1 || taps->up2))
       return fail(h, CATSEG_ERR_UNSUPPORTED, "up1/up2 taps are only available with the exact decoder");
-    cudaError_t e = (h->split ? run_decoder_split : run_decoder_fast)(X, ws + p.dg0, ws + p.dg1, out_ids, logits, B, T_out, Te, p.dd,
-                                                                       h->dec_fast, h->dec, h->head_bias_host, ws + p.dec,
-                                                                       p.dec_chunk, h->num_sms, &nl, st);
+    cudaError_t e = h->split ? run_decoder_split(X, ws + p.dg0, ws + p.dg1, out_ids, logits, B, T_out, Te, p.dd, h->dec_fast, h->dec,
+                                                 h->head_bias_host, ws + p.dec, p.dec_chunk, h->num_sms, &nl, nlp > 0 ? &lpeers : nullptr,
+                                                 nlp, st)
+                             : run_decoder_fast(X, ws + p.dg0, ws + p.dg1, out_ids, logits, B, T_out, Te, p.dd, h->dec_fast, h->dec,
+                                                h->head_bias_host, ws + p.dec, p.dec_chunk, h->num_sms, &nl, st);
     if (e != cudaSuccess) return fail(h, CATSEG_ERR_CUDA, "fast decoder: %s", cudaGetErrorString(e));
+    if (nlp > 0) {                                         // the peers' planes have landed in this rank's buffer after this barrier
+      seg.end();
+      seg.begin(CATSEG_STAGE_EXCHANGE);
+      if (xbarrier() != 0) return fail(h, CATSEG_ERR_CUDA, "class-shard barrier failed");
+    }
   } else {
     cudaError_t e = run_decoder_exact(X, ws + p.dg0, ws + p.dg1, out_ids, logits, B, T_out, Te, p.dd, h->dec,
                                       ws + p.dec, p.dec_chunk, taps ? taps->up1 : nullptr,
@@ -1232,9 +1259,15 @@ extern "C" int catseg_forward_class_sharded(catseg_handle* h, const float* img, 
                                             int shard_rank, int shard_world, catseg_allreduce_fn allreduce, void* ctx,
                                             catseg_stream stream) {
   if (shard_world < 1) return CATSEG_ERR_INVALID;
-  ShardExchange xc{allreduce, ctx, nullptr, nullptr, 0, nullptr, nullptr};
+  ShardExchange xc{allreduce, ctx, nullptr, nullptr, 0, nullptr, nullptr, nullptr};
   return forward_impl(h, img, text, g0, g1, g2, logits_local, workspace, workspace_bytes, B, T, nullptr, shard_rank, shard_world,
                       &xc, kept_classes_out, stream);
+}
+
+extern "C" size_t catseg_exchange_logits_bytes(const catseg_handle* h, int B, int T) {
+  if (!h || B <= 0 || T <= 0) return 0;
+  const Plan p = make_plan(h, B, T);
+  return (size_t)B * T * 16 * p.HW * sizeof(float);
 }
 
 extern "C" size_t catseg_exchange_buffer_bytes(const catseg_handle* h, int B, int T, int shard_world) {
@@ -1248,10 +1281,10 @@ extern "C" int catseg_forward_class_sharded_a2a(catseg_handle* h, const float* i
                                                 const float* g1, const float* g2, float* logits_local,
                                                 int32_t* kept_classes_out, void* workspace, size_t workspace_bytes, int B, int T,
                                                 int shard_rank, int shard_world, float* const* xbuf_peers,
-                                                float* const* pbuf_peers, size_t buf_bytes, catseg_barrier_fn barrier, void* ctx,
-                                                catseg_stream stream) {
+                                                float* const* pbuf_peers, size_t buf_bytes, float* const* logits_peers,
+                                                catseg_barrier_fn barrier, void* ctx, catseg_stream stream) {
   if (shard_world < 1 || !xbuf_peers || !pbuf_peers) return CATSEG_ERR_INVALID;
-  ShardExchange xc{nullptr, nullptr, xbuf_peers, pbuf_peers, buf_bytes, barrier, ctx};
+  ShardExchange xc{nullptr, nullptr, xbuf_peers, pbuf_peers, buf_bytes, barrier, ctx, logits_peers};
   return forward_impl(h, img, text, g0, g1, g2, logits_local, workspace, workspace_bytes, B, T, nullptr, shard_rank, shard_world,
                       &xc, kept_classes_out, stream);
 }

@@ -614,7 +614,8 @@ constexpr int HB_SMEM = (HB_BR + 2) * HB_PW * HB_C * 4;
 
 __global__ void __launch_bounds__(HB_THREADS, 2)
 head_conv_f32_kernel(const float* __restrict__ in, const float* __restrict__ in_ss, const float* __restrict__ wt, float bias,
-                     const int32_t* __restrict__ classes, float* __restrict__ logits, int slice0, int nslice, int Te, int T) {
+                     const int32_t* __restrict__ classes, float* __restrict__ logits, int slice0, int nslice, int Te, int T,
+                     PeerPtrs lpeers, int nlp) {
   extern __shared__ float4 hb_sm[];                    // [(BR + 2) * PW pixels][8 chunks of 4 channels]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cg = lane & 3, G = warp * 8 + (lane >> 2);   // channel group (8 channels), pixel group (8 pixels of one row)
@@ -699,22 +700,31 @@ head_conv_f32_kernel(const float* __restrict__ in, const float* __restrict__ in_
     }
     if (cg == 0) {
       const int gs = slice0 + sl, b = gs / Te, cls = classes[gs];
-      float* o = logits + ((long long)b * T + cls) * (HB_W * HB_W) + (band * HB_BR + ry) * HB_W + x0;
-      st4(o, make_float4(acc[0] + bias, acc[1] + bias, acc[2] + bias, acc[3] + bias));
-      st4(o + 4, make_float4(acc[4] + bias, acc[5] + bias, acc[6] + bias, acc[7] + bias));
+      const long long off = ((long long)b * T + cls) * (HB_W * HB_W) + (band * HB_BR + ry) * HB_W + x0;
+      const float4 o0 = make_float4(acc[0] + bias, acc[1] + bias, acc[2] + bias, acc[3] + bias);
+      const float4 o1 = make_float4(acc[4] + bias, acc[5] + bias, acc[6] + bias, acc[7] + bias);
+      if (nlp == 0) {
+        st4(logits + off, o0); st4(logits + off + 4, o1);
+      } else {                                           // class-sharded, peer-direct: the plane goes to every rank's full buffer
+        for (int r = 0; r < nlp; ++r) { st4(lpeers.p[r] + off, o0); st4(lpeers.p[r] + off + 4, o1); }
+      }
     }
     __syncthreads();                                   // the band image is rebuilt by the next item
   }
 }
 
 static cudaError_t launch_head_conv_f32(const float* in, const float* in_ss, const float* wt, float bias, const int32_t* classes,
-                                        float* logits, int slice0, int nslice, int Te, int T, int num_sms, cudaStream_t st) {
+                                        float* logits, int slice0, int nslice, int Te, int T, int num_sms, const PeerPtrs* lpeers,
+                                        int nlp, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(head_conv_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_SMEM);
   if (e != cudaSuccess) return e;
   const long long nitems = (long long)nslice * HB_NB;
   const int grid = (int)(nitems < 2LL * num_sms ? nitems : 2LL * num_sms);
   if (grid <= 0) return cudaSuccess;
-  head_conv_f32_kernel<<<grid, HB_THREADS, HB_SMEM, st>>>(in, in_ss, wt, bias, classes, logits, slice0, nslice, Te, T);
+  PeerPtrs lp{};
+  if (lpeers != nullptr) lp = *lpeers;
+  head_conv_f32_kernel<<<grid, HB_THREADS, HB_SMEM, st>>>(in, in_ss, wt, bias, classes, logits, slice0, nslice, Te, T, lp,
+                                                          lpeers != nullptr ? nlp : 0);
   return cudaGetLastError();
 }
 
@@ -983,11 +993,36 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
   return cudaSuccess;
 }
 
+// Per-image additive maps of the PRECISE decoder (guidance convolution + transposed-conv bias, tile ordered): they depend
+// on the decoder guidance only, so the caller computes them on its internal stream beside the aggregation layers.  Uses
+// the head of the scratch area exactly as run_decoder_split lays it out.
+cudaError_t decoder_split_prepare(const float* dg0, const float* dg1, int B, const DecoderDims& d, const DecoderFastW& w,
+                                  void* scratch, int* launches, cudaStream_t st) {
+  const int hw = d.H * d.W;
+  int nl = 0;
+  const int narrow = decs_narrow_mask();
+  uint8_t* ptr = reinterpret_cast<uint8_t*>(scratch);
+  auto take = [&](size_t bytes) { uint8_t* r = ptr; ptr += (bytes + 255) / 256 * 256; return r; };
+  float* E1 = reinterpret_cast<float*>(take((size_t)B * 4 * hw * d.D1 * 4));
+  float* E2 = reinterpret_cast<float*>(take((size_t)B * 16 * hw * d.D2 * 4));
+  float* E1t = reinterpret_cast<float*>(take(emap_tiled_floats<D1S>(B) * 4));
+  float* E2t = reinterpret_cast<float*>(take(max_sz(emap_tiled_floats<D3S>(B), emap_tiled_floats<D3T>(B)) * 4));
+  GuidConvA a{dg0, d.G1, 2 * d.H, 2 * d.W};
+  CKF(launch_igemm(a, w.wg1, 0, 1, B * 4 * hw, d.D1, 9 * d.G1, MapAddStore{E1, w.bmap1, 4 * hw, d.D1}, st));
+  GuidConvA a2{dg1, d.G2, 4 * d.H, 4 * d.W};
+  CKF(launch_igemm(a2, w.wg2, 0, 1, B * 16 * hw, d.D2, 9 * d.G2, MapAddStore{E2, w.bmap2, 16 * hw, d.D2}, st));
+  CKF((launch_relayout_emap<D1S>(E1, E1t, B, st)));
+  if (narrow & 4) CKF((launch_relayout_emap<D3T>(E2, E2t, B, st))); else CKF((launch_relayout_emap<D3S>(E2, E2t, B, st)));
+  if (launches) *launches += nl;
+  return cudaSuccess;
+}
+
 // PRECISE decoder: the same five band-convolution stages with hi + lo fp16 operand pairs and fp32 intermediates
+// (decoder_split_prepare must have run on the same scratch area)
 cudaError_t run_decoder_split(const float* X, const float* dg0, const float* dg1, const int32_t* classes,
                               float* logits, int B, int T, int Te, const DecoderDims& d, const DecoderFastW& w,
                               const DecoderW& wx, float head_bias, void* scratch, int chunk, int num_sms,
-                              int* launches, cudaStream_t st) {
+                              int* launches, const PeerPtrs* lpeers, int nlp, cudaStream_t st) {
   const int hw = d.H * d.W;
   int nl = 0;
   const int narrow = decs_narrow_mask();
@@ -1010,14 +1045,7 @@ cudaError_t run_decoder_split(const float* X, const float* dg0, const float* dg1
   float* s2a = reinterpret_cast<float*>(take((size_t)chunk * nb3 * 2 * 2 * 4));
   float* s2b = reinterpret_cast<float*>(take((size_t)chunk * nb4 * 2 * 2 * 4));
   float* gss = reinterpret_cast<float*>(take((size_t)chunk * 64 * 2 * 4));
-  {
-    GuidConvA a{dg0, d.G1, 2 * d.H, 2 * d.W};
-    CKF(launch_igemm(a, w.wg1, 0, 1, B * 4 * hw, d.D1, 9 * d.G1, MapAddStore{E1, w.bmap1, 4 * hw, d.D1}, st));
-    GuidConvA a2{dg1, d.G2, 4 * d.H, 4 * d.W};
-    CKF(launch_igemm(a2, w.wg2, 0, 1, B * 16 * hw, d.D2, 9 * d.G2, MapAddStore{E2, w.bmap2, 16 * hw, d.D2}, st));
-    CKF((launch_relayout_emap<D1S>(E1, E1t, B, st)));
-    if (narrow & 4) CKF((launch_relayout_emap<D3T>(E2, E2t, B, st))); else CKF((launch_relayout_emap<D3S>(E2, E2t, B, st)));
-  }
+  (void)E1; (void)E2; (void)dg0; (void)dg1;            // the additive maps E1t / E2t were computed by decoder_split_prepare
   const int nslice = B * Te;
   for (int s0 = 0; s0 < nslice; s0 += chunk) {
     const int n = nslice - s0 < chunk ? nslice - s0 : chunk;
@@ -1041,8 +1069,9 @@ cudaError_t run_decoder_split(const float* X, const float* dg0, const float* dg1
     p.in = c2b; p.in_stats = s2b; p.nb_in = nb4; p.gamma = wx.gn2b_g; p.beta = wx.gn2b_b;
     p.wimg = w.w5; p.emap = nullptr; p.out32 = nullptr; p.out_stats = nullptr;
     static const bool head_tc = getenv("CATSEG_DEC_HEAD_TC") != nullptr;       // A/B: the tensor-core head stage
+    if (lpeers != nullptr && (head_tc || !(d.D2 == HB_C && 4 * d.W == HB_W && 4 * d.H == HB_W))) return cudaErrorNotSupported;
     if (d.D2 == HB_C && 4 * d.W == HB_W && 4 * d.H == HB_W && !head_tc)
-      CKF(launch_head_conv_f32(c2b, gss, wx.head_w, head_bias, classes, logits, s0, n, Te, T, num_sms, st));
+      CKF(launch_head_conv_f32(c2b, gss, wx.head_w, head_bias, classes, logits, s0, n, Te, T, num_sms, lpeers, nlp, st));
     else if (narrow & 16) CKF((launch_band<D5T>(p, num_sms, st)));
     else CKF((launch_band<D5S>(p, num_sms, st)));
   }

@@ -65,6 +65,9 @@ struct SwinAttn2W {
 };
 constexpr size_t kSwinAttn2Halfs = 4 * 128 * 128 + 4 * 8192;
 
+constexpr int kMaxShard = 8;
+struct PeerPtrs { float* p[kMaxShard]; };      // one buffer per rank of the shard group (peer-mapped device pointers)
+
 constexpr int kStateFloats = 4 * 32 * 32 + 128;   // per (image, pixel): KV[4][32][32] then Ksum[128]
 
 // ---------------------------------------------------------------- prep.cu
@@ -117,8 +120,6 @@ struct GemmSplitParams {
 cudaError_t launch_gemm_split(const GemmSplitParams& p, cudaStream_t st);
 
 // ---------------------------------------------------------------- shard_exchange.cu
-constexpr int kMaxShard = 8;
-struct PeerPtrs { float* p[kMaxShard]; };      // one buffer per rank of the shard group (peer-mapped device pointers)
 struct PeerFlags { uint32_t* p[kMaxShard]; };   // every rank's barrier flag block (kMaxShard + 2 words)
 cudaError_t launch_peer_barrier(const PeerFlags& f, int rank, int world, cudaStream_t st);
 cudaError_t launch_shard_put_cmax(const float* loc, const PeerPtrs& dst, int B, int Tr, int T, int t0, int world, cudaStream_t st);
@@ -279,10 +280,13 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
                              int* launches, cudaStream_t st);
 
 size_t decoder_split_scratch_bytes(const DecoderDims& d, int B, int chunk);
+cudaError_t decoder_split_prepare(const float* dg0, const float* dg1, int B, const DecoderDims& d, const DecoderFastW& w,
+                                  void* scratch, int* launches, cudaStream_t st);
+// lpeers (optional, class-sharded peer-direct mode): every rank's full logits buffer; the head kernel stores into all of them
 cudaError_t run_decoder_split(const float* X, const float* dg0, const float* dg1, const int32_t* classes,
                               float* logits, int B, int T, int Te, const DecoderDims& d, const DecoderFastW& w,
                               const DecoderW& wx, float head_bias, void* scratch, int chunk, int num_sms,
-                              int* launches, cudaStream_t st);
+                              int* launches, const PeerPtrs* lpeers, int nlp, cudaStream_t st);
 
 // ---------------------------------------------------------------- stitch.cu
 // scratch_mask: T uint32 of device scratch (enables the skipping of dropped-class planes), or nullptr

@@ -115,32 +115,46 @@ cudaError_t launch_class_max(const float* corr, float* cmax, long long rows, int
 
 // ---- top-Te class selection (model.py:696).  topk(sorted=False) leaves the order of the kept set
 // unspecified and the result is invariant to it: we keep ascending class id; ties
-// at the cut go to the lower id.  One block per image; rank by counting.
-__global__ void select_classes_kernel(const float* __restrict__ cmax, int32_t* __restrict__ classes, int T, int Te) {
-  extern __shared__ float sm[];
-  float* sc = sm;                              // [T]
-  int* keep = reinterpret_cast<int*>(sm + T);  // [T]
-  int b = blockIdx.x;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) sc[t] = cmax[(long long)b * T + t];
+// at the cut go to the lower id.  One block of 1024 threads per image: rank by counting (the scores sit in shared memory
+// and are compared four at a time), then an ordered compaction by warp ballots and a scan of the warp counts.
+__global__ void __launch_bounds__(1024) select_classes_kernel(const float* __restrict__ cmax, int32_t* __restrict__ classes, int T,
+                                                              int Te) {
+  extern __shared__ __align__(16) float sc[];  // [T rounded up to 4], padded with -inf (never counted: -inf > v is false)
+  __shared__ int s_wcnt[32], s_base;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T4 = (T + 3) & ~3;
+  for (int t = tid; t < T4; t += 1024) sc[t] = t < T ? cmax[(long long)b * T + t] : -INFINITY;
+  if (tid == 0) s_base = 0;
   __syncthreads();
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    float v = sc[t];
-    int rank = 0;
-    for (int u = 0; u < T; ++u) {
-      float w = sc[u];
-      rank += (w > v) || (w == v && u < t);
+  for (int t0 = 0; t0 < T; t0 += 1024) {       // classes in ascending order, 1024 per pass
+    const int t = t0 + tid;
+    bool keep = false;
+    if (t < T) {
+      const float v = sc[t];
+      int rank = 0;
+      for (int u = 0; u < T4; u += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(sc + u);
+        rank += (w.x > v) || (w.x == v && u < t);
+        rank += (w.y > v) || (w.y == v && u + 1 < t);
+        rank += (w.z > v) || (w.z == v && u + 2 < t);
+        rank += (w.w > v) || (w.w == v && u + 3 < t);
+      }
+      keep = rank < Te;
     }
-    keep[t] = rank < Te;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int n = 0;
-    for (int t = 0; t < T && n < Te; ++t)
-      if (keep[t]) classes[(long long)b * Te + n++] = t;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_wcnt[warp] = __popc(bal);
+    __syncthreads();
+    int pos = s_base;
+    for (int w = 0; w < warp; ++w) pos += s_wcnt[w];
+    pos += __popc(bal & ((1u << lane) - 1u));
+    if (keep && pos < Te) classes[(long long)b * Te + pos] = t;
+    __syncthreads();
+    if (tid == 0) { int n = 0; for (int w = 0; w < 32; ++w) n += s_wcnt[w]; s_base += n; }
+    __syncthreads();
   }
 }
 cudaError_t launch_select_classes(const float* cmax, int32_t* classes, int B, int T, int Te, cudaStream_t st) {
-  select_classes_kernel<<<B, 256, (size_t)T * 8, st>>>(cmax, classes, T, Te);
+  select_classes_kernel<<<B, 1024, (size_t)((T + 3) & ~3) * 4, st>>>(cmax, classes, T, Te);
   return cudaGetLastError();
 }
 __global__ void iota_classes_kernel(int32_t* classes, int n, int Te) {

@@ -170,13 +170,20 @@ int catseg_forward_class_sharded(catseg_handle* h, const float* img_feats, const
  * With T > pad_len the first cost-volume pass is sharded over the raw classes too: every rank reduces the maxima of T/world
  * classes and stores them into every rank's table (model.py:695-696 then selects from identical tables).
  * PRECISE precision, pooling_size [1,1], HW % world == 0, world <= 8. */
+/*   logits_peers             NULL: the result is logits_local (compact planes, as above).  Otherwise [world] device pointers
+ *                            (HOST array) to every rank's FULL logits buffer [B, T, 4H, 4W] (catseg_exchange_logits_bytes,
+ *                            catseg_peer_alloc): the head kernel stores each of this rank's planes into all of them at its
+ *                            class id, the library pre-fills its own buffer with -100 and ends with a barrier -- every rank
+ *                            holds the complete logits when the call's work on `stream` is done, with no all-gather and no
+ *                            assembly pass.  logits_local may then be NULL. */
 typedef int (*catseg_barrier_fn)(void* ctx, catseg_stream stream);
 size_t catseg_exchange_buffer_bytes(const catseg_handle* h, int B, int T, int shard_world);
+size_t catseg_exchange_logits_bytes(const catseg_handle* h, int B, int T);
 int catseg_forward_class_sharded_a2a(catseg_handle* h, const float* img_feats, const float* text_feats, const float* g0,
                                      const float* g1, const float* g2, float* logits_local, int32_t* kept_classes_out,
                                      void* workspace, size_t workspace_bytes, int B, int T, int shard_rank, int shard_world,
                                      float* const* xbuf_peers, float* const* pbuf_peers, size_t buf_bytes,
-                                     catseg_barrier_fn barrier, void* ctx, catseg_stream stream);
+                                     float* const* logits_peers, catseg_barrier_fn barrier, void* ctx, catseg_stream stream);
 /* Final assembly after the all-gather of the local planes: gathered [world][B][T_local][npix] (rank-major), kept_classes
  * [B][world*T_local] -> logits [B][T][npix] with -100 for classes that were not kept (model.py:721-724).  pos_scratch: B*T
  * int32 of device scratch.  npix % 4 == 0, B*T <= 65535. */

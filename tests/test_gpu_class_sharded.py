@@ -51,12 +51,24 @@ def _worker(rank: int, world: int, port: int, q, model: str, B: int, T: int):
         parts = [torch.empty_like(local2.cpu()) for _ in range(world)]
         dist.all_gather(parts, local2.cpu())
         again = assemble_class_sharded(torch.stack(parts), kept2.cpu(), T)
+        # peer-direct result: every rank's buffer holds the full logits (head kernel stores into all ranks, no all-gather)
+        full = m.forward_class_sharded(*a, exchange="alltoall").clone()
+        torch.cuda.synchronize()
+        full2 = m.forward_class_sharded(*a, exchange="alltoall").clone()     # buffers re-used
+        torch.cuda.synchronize()
         res = None
+        same_full = bool(torch.equal(full, full2))
+        if rank != 0:
+            ref_r = m(*a)
+            same_full = same_full and bool(torch.equal(full, ref_r))           # every rank, not only rank 0, has the result
+        flags = [None] * world
+        dist.all_gather_object(flags, same_full)
         if rank == 0:
             ref = m(*a).cpu()
+            out["peer_direct"] = full.cpu()
             res = {k: (v - ref).abs().max().item() for k, v in out.items()}
             res["mask_equal"] = all(bool(((v == -100.0) == (ref == -100.0)).all()) for v in out.values())
-            res["again_equal"] = bool(torch.equal(again, out["alltoall"]))
+            res["again_equal"] = bool(torch.equal(again, out["alltoall"])) and all(flags)
             # the CUDA assembly kernel (copy a gathered plane / fill -100) against the torch restatement
             stacked = torch.stack(parts)
             res["assemble_equal"] = bool(torch.equal(assemble_class_sharded(stacked.cuda(), kept2, T).cpu(),
@@ -88,7 +100,7 @@ def test_class_sharded_two_ranks_one_gpu(model, B, T):
         assert err is None, f"rank {rank}:\n{err}"
     res = [r for rank, r, _ in results if rank == 0][0]
     # all-to-all: every kernel sees the same operands in the same order as the unsharded run -> bit exact
-    assert res["alltoall"] == 0.0 and res["alltoall/collective"] == 0.0, res
+    assert res["alltoall"] == 0.0 and res["alltoall/collective"] == 0.0 and res["peer_direct"] == 0.0, res
     # all-reduce: only the fp32 summation order of the linear-attention state differs
     assert res["allreduce"] <= 2e-5, res
     assert res["mask_equal"] and res["again_equal"] and res["assemble_equal"], res
