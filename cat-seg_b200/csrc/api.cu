@@ -1013,7 +1013,11 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
   }
   if (sharded) RUN(launch_slice_classes(classes_all, classes, B, p.Te, shard_rank * Te, Te, st));
   if (kept_out) CUDA_OK(h, cudaMemcpyAsync(kept_out, classes_all, (size_t)B * p.Te * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-  if (use_vocab) {
+  if (a2a) {
+    // the class layers of this mode run on ALL kept classes at this rank's pixels: their text guidance is derived below
+    for (int l = 0; l < p.L; ++l)
+      RUN(launch_class_pad_state(h->cls[l], 128, ws + p.pad_state + (size_t)l * kStateFloats, p.n_pad, p.S, st));
+  } else if (use_vocab) {
     // the text guidance of a vocabulary is derived once (derive_vocabulary): per call the kept classes only pick their rows
     RUN(launch_gather_rows(h->vocab.text_g, classes, ws + p.text_g, (long long)B * Te, 128, st));
     for (int l = 0; l < p.L; ++l) {
@@ -1052,9 +1056,6 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
     CUDA_OK(h, cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));     // ev_fork was recorded at the start of the stage
     cudaStream_t st = h->aux_stream;             // shadows: the launches below go to the internal stream
     const bool gsplit = prep_fast && h->split;
-    // peer-direct logits: this rank's full buffer is pre-filled with -100 here (dropped classes, model.py:721); the peers'
-    // head kernels store the kept planes much later, after barriers that this stream's join precedes
-    if (a2a && xc->lb && p.truncated) RUN(launch_fill(xc->lb[shard_rank], -100.0f, (long long)B * T * 16 * p.HW, st));
     if (gsplit && h->gconv_split_img[0]) RUN(launch_gconv_split(0, g0, h->gconv_split_img[0], h->gproj_b, ws + p.app_g, B, p.Cg, st));
     else if (gconv_fast && h->gconv_img[0]) RUN(launch_gconv_fast(0, g0, h->gconv_img[0], h->gproj_b, ws + p.app_g, B, p.Cg, st));
     else RUN(launch_conv3x3_nchw(g0, h->gproj_wt, h->gproj_b, ws + p.app_g, B, p.Cg, p.H, p.W, 128, st));
@@ -1068,6 +1069,9 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
     // decoder's per-image additive maps) stay on the internal stream and are joined right before the decoder
     CUDA_OK(h, cudaEventRecord(h->ev_join, st));
     CUDA_OK(h, cudaStreamWaitEvent(mainst, h->ev_join, 0));
+    // peer-direct logits: this rank's full buffer is pre-filled with -100 here (dropped classes, model.py:721); the peers'
+    // head kernels store the kept planes much later, after barriers that the second join of this stream precedes
+    if (a2a && xc->lb && p.truncated) RUN(launch_fill(xc->lb[shard_rank], -100.0f, (long long)B * T * 16 * p.HW, st));
     if (gsplit && h->gconv_split_img[1])
       RUN(launch_gconv_split(1, g1, h->gconv_split_img[1], h->dgp_b[0], ws + p.dg0, B, c.decoder_guidance_dims[0], st));
     else if (gconv_fast && h->gconv_img[1])
@@ -1168,6 +1172,9 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
       seg.end();
       seg.begin(CATSEG_STAGE_EXCHANGE);
       RUN(launch_shard_p2c(PB, xbp, B, Te, p.Te, p.HW, shard_rank, shard_world, st));
+      // peer-direct logits: arriving at the last barrier must imply that this rank's -100 pre-fill (internal stream) is
+      // complete, because the peers' head kernels store into this rank's buffer any time after it
+      if (xc->lb && l == p.L - 1) CUDA_OK(h, cudaStreamWaitEvent(st, h->ev_join2, 0));
       if (xbarrier() != 0) return fail(h, CATSEG_ERR_CUDA, "class-shard barrier failed");
       seg.end();
       continue;
