@@ -299,7 +299,7 @@ __global__ void __launch_bounds__((CTAS == 2 ? 8 : 16) * 32 + 32, CTAS) band_con
     //      256 % KCH == 0, so a thread always handles the same 8-channel group: its GroupNorm scale/shift live in registers.
     if (!issuer) {
       const int y_first = band * BR - 1;
-      constexpr int U = IN_F32 ? 4 : 8;
+      constexpr int U = 8;                      // chunks in flight per thread (fp32 input: 2 x 16 bytes each)
       constexpr int NCHUNK = C::NP * C::KCH;
       static_assert(C::NWT % C::KCH == 0, "a thread keeps its channel group");
       const int c = tid % C::KCH;
