@@ -82,7 +82,7 @@ def stage_kernel(stage, precision, attn_v2):
     fast = not precision.startswith("precise")
     return {
         "swin": ("swin_attn_fast_kernel" if (fast and not attn_v2) else "swin_attn2_kernel<%d>" % (0 if fast else 1)),
-        "swin_mlp": "mlp_fast_kernel<GELU>" if fast else "mlp_split_kernel<GELU>",
+        "swin_mlp": "mlp_fast_kernel<GELU>" if fast else "mlp_split_kernel<0, 0, 0>",
     }[stage]
 
 
