@@ -492,7 +492,7 @@ def run_ours(args):
             rec = {"workload": describe(wl, oarm.cfg, oarm.B, oarm.T, oarm.sliding),
                    "value": oarm.units() * max(3, steps // 2) / (ores["ms"] / 1e3), "unit": UNIT,
                    "ms_per_step": ores["ms"] / max(3, steps // 2)}
-            if wl in ("cfg1", "cfg2") and not args.no_cpu_baseline:
+            if wl in ("cfg1", "cfg2", "cfg3") and not args.no_cpu_baseline:
                 ry, rsec, rc, rkind, _, rin = cpu_reference(oarm.cfg, oarm.T, seed=0, B=1)
                 rec["parity"] = parity_block(oarm.forward_one(rin), ry)
                 rec["cpu_baseline"] = {"value": 1.0 / rsec, "unit": UNIT, "cores": rc, "kind": rkind, "sample": f"1 image, {rsec:.1f} s"}
