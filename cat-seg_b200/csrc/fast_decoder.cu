@@ -79,7 +79,9 @@ struct BandCfg {
                                    NW * IMG_BYTES + NIMG * WBYTES <= (CTAS == 2 ? 108 : (SPLIT ? 214 : 200)) * 1024;
   // streaming ring: 48 KiB deep (96 KiB when the CTA owns the SM), so that the prefetch distance (in MMA time) exceeds the
   // ~1 us L2->SMEM latency
-  static constexpr int NSLOT = RESIDENT ? NIMG : (int)((CTAS == 2 ? 48 : 96) * 1024 / WBYTES);
+  // (a band image that leaves less than 96 KiB gets a 64 KiB ring: taller bands amortise more than the shallower prefetch costs)
+  static constexpr int RING_KB = CTAS == 2 ? 48 : (NW * IMG_BYTES + 98 * 1024 <= 227 * 1024 ? 96 : 64);
+  static constexpr int NSLOT = RESIDENT ? NIMG : (int)(RING_KB * 1024 / WBYTES);
   // worker warps (staging + epilogues): 8 per CTA with two CTAs per SM, 16 when the CTA owns the SM; one more warp issues
   static constexpr int NWW = CTAS == 2 ? 8 : 16, NWT = NWW * 32, THREADS = NWT + 32, NTG = NWW / 4;
   static constexpr int NB = WIN_ / BR;                 // bands per slice
@@ -873,9 +875,9 @@ struct MapAddStore {
 #define D5W 32, 16, 16, false, false, 96, 12, true, 1
 // PRECISE shapes: one 17-warp CTA per SM, fp32 activations in and out
 #define D1S 128, 64, 64, true, true, 24, 4, false, 1, true
-#define D2S 64, 64, 64, false, true, 48, 6, false, 1, true
+#define D2S 64, 64, 64, false, true, 48, 8, false, 1, true
 #define D3S 64, 32, 32, true, true, 48, 4, false, 1, true
-#define D4S 32, 32, 32, false, true, 96, 6, false, 1, true
+#define D4S 32, 32, 32, false, true, 96, 8, false, 1, true
 #define D5S 32, 16, 16, false, true, 96, 6, true, 1, true
 // ... and two 9-warp CTAs per SM with short bands (one CTA's staging / epilogue under the other's MMAs); CATSEG_DECS_NARROW is
 // a bit mask (bit i = stage D(i+1) uses the narrow shape), read once, for A/B measurements

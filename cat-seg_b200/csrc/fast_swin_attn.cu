@@ -337,14 +337,17 @@ swin_attn_fast_kernel(float* __restrict__ X, const __half* __restrict__ agw, int
           // (packed FFMA2 / FADD2 for the exponent arguments and the row sum were measured: 8 % slower here)
           float sum = 0.0f;
 #pragma unroll
-          for (int i = 0; i < 36; ++i) { sv[i] = umma::ex2_approx(fmaf(sv[i], 1.4426950408889634f, -mb)); sum += sv[i]; }
-          // 36 keys = 4.5 chunks of 8: quarter kq starts at chunk 4.5 kq -> write 72-byte span as 8-byte pieces
+          for (int i = 0; i < 36; ++i) sv[i] = umma::ex2_approx(fmaf(sv[i], 1.4426950408889634f, -mb));
+          // 36 keys = 4.5 chunks of 8: quarter kq starts at chunk 4.5 kq -> write 72-byte span as 8-byte pieces.
+          // The normaliser is the sum of the ROUNDED fp16 weights the P V MMAs multiply (see swin_attn2.cu)
           uint8_t* prow = smem + SM_P + row * 16;
 #pragma unroll
           for (int i = 0; i < 36; i += 4) {
             const int key = kq * 36 + i;                      // multiple of 4
-            *reinterpret_cast<uint2*>(prow + (key >> 3) * LBO_X + (key & 7) * 2) =
-                make_uint2(umma::pack_h2(sv[i], sv[i + 1]), umma::pack_h2(sv[i + 2], sv[i + 3]));
+            const uint32_t p01 = umma::pack_h2(sv[i], sv[i + 1]), p23 = umma::pack_h2(sv[i + 2], sv[i + 3]);
+            *reinterpret_cast<uint2*>(prow + (key >> 3) * LBO_X + (key & 7) * 2) = make_uint2(p01, p23);
+            const float2 r01 = umma::unpack_h2(p01), r23 = umma::unpack_h2(p23);
+            sum += (r01.x + r01.y) + (r23.x + r23.y);
           }
           rsum[kq * 144 + row] = sum;
         }
@@ -361,13 +364,15 @@ swin_attn_fast_kernel(float* __restrict__ X, const __half* __restrict__ agw, int
           const float mb = mx1 * 1.4426950408889634f;
           float sum = 0.0f;
 #pragma unroll
-          for (int i = 0; i < 9; ++i) { tv[i] = umma::ex2_approx(fmaf(tv[i], 1.4426950408889634f, -mb)); sum += tv[i]; }
+          for (int i = 0; i < 9; ++i) tv[i] = umma::ex2_approx(fmaf(tv[i], 1.4426950408889634f, -mb));
           if (lane < 16) {
             uint8_t* prow = smem + SM_P + qrow * 16;
 #pragma unroll
             for (int i = 0; i < 9; ++i) {
               const int key = key0 + i;
-              *reinterpret_cast<__half*>(prow + (key >> 3) * LBO_X + (key & 7) * 2) = __float2half_rn(tv[i]);
+              const __half ph = __float2half_rn(tv[i]);
+              *reinterpret_cast<__half*>(prow + (key >> 3) * LBO_X + (key & 7) * 2) = ph;
+              sum += __half2float(ph);
             }
             sum1[part * 16 + r1] = sum;
           }
