@@ -876,7 +876,7 @@ struct MapAddStore {
 // PRECISE shapes: one 17-warp CTA per SM, fp32 activations in and out
 #define D1S 128, 64, 64, true, true, 24, 4, false, 1, true
 #define D2S 64, 64, 64, false, true, 48, 8, false, 1, true
-#define D3S 64, 32, 32, true, true, 48, 4, false, 1, true
+#define D3S 64, 32, 32, true, true, 48, 8, false, 1, true
 #define D4S 32, 32, 32, false, true, 96, 8, false, 1, true
 #define D5S 32, 16, 16, false, true, 96, 6, true, 1, true
 // ... and two 9-warp CTAs per SM with short bands (one CTA's staging / epilogue under the other's MMAs); CATSEG_DECS_NARROW is
