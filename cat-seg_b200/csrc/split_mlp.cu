@@ -205,12 +205,9 @@ mlp_split_kernel(const float* __restrict__ Xin, const float* __restrict__ Xres, 
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const long long r = row0 + aw * 8 + i;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < ntok) {
-          a = ld4(Xin + r * 128 + lane * 4);
-          if (Xres != nullptr) a = f4add(a, ld4(Xres + r * 128 + lane * 4));
-        }
-        xres[i] = a;
+        // (the second residual, Xres, is fetched in the store loop below: added here, every row's pair of loads had to land
+        //  before the next pair was issued -- 8 serialised L2 round trips, 6 K cycles per pass in the class MLP)
+        xres[i] = r < ntok ? ld4(Xin + r * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       umma::mbar_wait(bar_y, ph_y); ph_y ^= 1u;
       umma::fence_after_sync();
@@ -225,6 +222,16 @@ mlp_split_kernel(const float* __restrict__ Xin, const float* __restrict__ Xres, 
     umma::fence_before_sync();
     __syncthreads();
     if (worker) {
+      if (Xres != nullptr) {
+        float4 x2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const long long r = row0 + aw * 8 + i;
+          x2[i] = r < ntok ? ld4(Xres + r * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xres[i] = f4add(xres[i], x2[i]);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const long long r = row0 + aw * 8 + i;
