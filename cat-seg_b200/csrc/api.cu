@@ -60,7 +60,7 @@ struct catseg_handle {
   DecoderFastW dec_fast{};
   float head_bias_host = 0.0f;
   cudaStream_t aux_stream = nullptr;            // fork/join inside catseg_forward: guidance projections run beside the cost volume
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;   // join2: decoder guidance + additive maps ready
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_sel = nullptr;   // join2: decoder guidance + additive maps ready
   __nv_bfloat16* prep_img = nullptr;            // FAST_PREP: embedding images, then the three guidance-conv image sets
   const __nv_bfloat16 *embed_img = nullptr, *gconv_img[3] = {nullptr, nullptr, nullptr};   // nullptr: shape not covered -> fp32 kernel
   __half* gconv_split_store = nullptr;          // PRECISE: fp16 [Wh | Wl] images of the three guidance convolutions
@@ -241,7 +241,8 @@ extern "C" int catseg_create(const catseg_config* cfg, catseg_handle** out) {
   if (cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_sel, cudaEventDisableTiming) != cudaSuccess) {
     catseg_destroy(h);
     return fail(nullptr, CATSEG_ERR_CUDA, "stream / event creation failed");
   }
@@ -267,6 +268,7 @@ extern "C" int catseg_destroy(catseg_handle* h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev_join2) cudaEventDestroy(h->ev_join2);
+  if (h->ev_sel) cudaEventDestroy(h->ev_sel);
   delete h;
   return CATSEG_OK;
 }
@@ -1013,38 +1015,9 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
   }
   if (sharded) RUN(launch_slice_classes(classes_all, classes, B, p.Te, shard_rank * Te, Te, st));
   if (kept_out) CUDA_OK(h, cudaMemcpyAsync(kept_out, classes_all, (size_t)B * p.Te * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-  if (a2a) {
-    // the class layers of this mode run on ALL kept classes at this rank's pixels: their text guidance is derived below
-    for (int l = 0; l < p.L; ++l)
-      RUN(launch_class_pad_state(h->cls[l], 128, ws + p.pad_state + (size_t)l * kStateFloats, p.n_pad, p.S, st));
-  } else if (use_vocab) {
-    // the text guidance of a vocabulary is derived once (derive_vocabulary): per call the kept classes only pick their rows
-    RUN(launch_gather_rows(h->vocab.text_g, classes, ws + p.text_g, (long long)B * Te, 128, st));
-    for (int l = 0; l < p.L; ++l) {
-      RUN(launch_gather_rows(h->vocab.cg_qk + (size_t)l * T * 256, classes, ws + p.cg_qk + (size_t)l * B * Te * 256, (long long)B * Te, 256, st));
-      RUN(launch_class_pad_state(h->cls[l], 128, ws + p.pad_state + (size_t)l * kStateFloats, p.n_pad, p.S, st));
-    }
-  } else {
-    RUN(launch_text_mean(p.truncated ? ws + p.textn : text, classes, ws + p.tmean, B, T, Te, p.P, p.Ct, st));
-    RUN(launch_linear(ws + p.tmean, h->tproj_wt, h->tproj_b, ws + p.text_g, (long long)B * Te, 128, p.Ct, 1, st));
-    for (int l = 0; l < p.L; ++l) {
-      RUN(launch_linear(ws + p.text_g, h->cls[l].wg_qk_t, h->cls[l].bqk, ws + p.cg_qk + (size_t)l * B * Te * 256,
-                        (long long)B * Te, 256, 128, 0, st));
-      RUN(launch_class_pad_state(h->cls[l], 128, ws + p.pad_state + (size_t)l * kStateFloats, p.n_pad, p.S, st));
-    }
-  }
   const bool class_fast = (h->fast_mask & CATSEG_FAST_CLASS) != 0;
   __half* timg = reinterpret_cast<__half*>(ws + p.timg);
-  if (a2a) {
-    // the class layers of this mode see ALL kept classes (at this rank's pixels): text guidance of the whole kept list
-    if (use_vocab) {
-      RUN(launch_gather_rows(h->vocab.text_g, classes_all, ws + p.text_g, (long long)B * p.Te, 128, st));
-    } else {
-      RUN(launch_text_mean(p.truncated ? ws + p.textn : text, classes_all, ws + p.tmean, B, T, p.Te, p.P, p.Ct, st));
-      RUN(launch_linear(ws + p.tmean, h->tproj_wt, h->tproj_b, ws + p.text_g, (long long)B * p.Te, 128, p.Ct, 1, st));
-    }
-    RUN(launch_pack_text_img(ws + p.text_g, timg, B, p.Te, st));
-  } else if (class_fast) RUN(launch_pack_text_img(ws + p.text_g, timg, B, Te, st));
+  CUDA_OK(h, cudaEventRecord(h->ev_sel, st));            // the kept-class list (and the normalised text) are ready
   // The guidance projections only depend on the inputs: they run on an internal stream beside the cost volume / class
   // selection / text chain (small, latency-bound kernels) and are joined before the embedding.  Externally the call is
   // still ordered on `stream`.
@@ -1069,6 +1042,39 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
     // decoder's per-image additive maps) stay on the internal stream and are joined right before the decoder
     CUDA_OK(h, cudaEventRecord(h->ev_join, st));
     CUDA_OK(h, cudaStreamWaitEvent(mainst, h->ev_join, 0));
+    // the text guidance of the kept classes is first needed by the class layers: it is derived here, off the critical chain
+    // (cost volume -> selection -> embedding), once the selection has been made on the caller's stream
+    CUDA_OK(h, cudaStreamWaitEvent(st, h->ev_sel, 0));
+    if (a2a) {
+      // the class layers of this mode run on ALL kept classes at this rank's pixels: their text guidance is derived below
+      for (int l = 0; l < p.L; ++l)
+        RUN(launch_class_pad_state(h->cls[l], 128, ws + p.pad_state + (size_t)l * kStateFloats, p.n_pad, p.S, st));
+    } else if (use_vocab) {
+      // the text guidance of a vocabulary is derived once (derive_vocabulary): per call the kept classes only pick their rows
+      RUN(launch_gather_rows(h->vocab.text_g, classes, ws + p.text_g, (long long)B * Te, 128, st));
+      for (int l = 0; l < p.L; ++l) {
+        RUN(launch_gather_rows(h->vocab.cg_qk + (size_t)l * T * 256, classes, ws + p.cg_qk + (size_t)l * B * Te * 256, (long long)B * Te, 256, st));
+        RUN(launch_class_pad_state(h->cls[l], 128, ws + p.pad_state + (size_t)l * kStateFloats, p.n_pad, p.S, st));
+      }
+    } else {
+      RUN(launch_text_mean(p.truncated ? ws + p.textn : text, classes, ws + p.tmean, B, T, Te, p.P, p.Ct, st));
+      RUN(launch_linear(ws + p.tmean, h->tproj_wt, h->tproj_b, ws + p.text_g, (long long)B * Te, 128, p.Ct, 1, st));
+      for (int l = 0; l < p.L; ++l) {
+        RUN(launch_linear(ws + p.text_g, h->cls[l].wg_qk_t, h->cls[l].bqk, ws + p.cg_qk + (size_t)l * B * Te * 256,
+                          (long long)B * Te, 256, 128, 0, st));
+        RUN(launch_class_pad_state(h->cls[l], 128, ws + p.pad_state + (size_t)l * kStateFloats, p.n_pad, p.S, st));
+      }
+    }
+    if (a2a) {
+      // the class layers of this mode see ALL kept classes (at this rank's pixels): text guidance of the whole kept list
+      if (use_vocab) {
+        RUN(launch_gather_rows(h->vocab.text_g, classes_all, ws + p.text_g, (long long)B * p.Te, 128, st));
+      } else {
+        RUN(launch_text_mean(p.truncated ? ws + p.textn : text, classes_all, ws + p.tmean, B, T, p.Te, p.P, p.Ct, st));
+        RUN(launch_linear(ws + p.tmean, h->tproj_wt, h->tproj_b, ws + p.text_g, (long long)B * p.Te, 128, p.Ct, 1, st));
+      }
+      RUN(launch_pack_text_img(ws + p.text_g, timg, B, p.Te, st));
+    } else if (class_fast) RUN(launch_pack_text_img(ws + p.text_g, timg, B, Te, st));
     // peer-direct logits: this rank's full buffer is pre-filled with -100 here (dropped classes, model.py:721); the peers'
     // head kernels store the kept planes much later, after barriers that the second join of this stream precedes
     if (a2a && xc->lb && p.truncated) RUN(launch_fill(xc->lb[shard_rank], -100.0f, (long long)B * T * 16 * p.HW, st));
@@ -1151,6 +1157,7 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
       if (k == 0) TAP(taps->swin_b1[l], X, (size_t)nslice * p.HW * 128);
       else TAP(taps->swin_b2[l], X, (size_t)nslice * p.HW * 128);
     }
+    if (l == 0) CUDA_OK(h, cudaStreamWaitEvent(st, h->ev_join2, 0));   // text guidance (internal stream)
     seg.begin(CATSEG_STAGE_CLASS);
     const float* cg = ws + p.cg_qk + (size_t)l * B * Te * 256;
     const float* pad = ws + p.pad_state + (size_t)l * kStateFloats;

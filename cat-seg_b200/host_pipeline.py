@@ -56,18 +56,23 @@ class GraphRunner:
         logits = run(img2, text2, [g0b, g1b, g2b])             # same shapes
     """
 
-    def __init__(self, model, img_feats, text_feats, appearance_guidance, warmup: int = 2):
+    def __init__(self, model, img_feats, text_feats, appearance_guidance, warmup: int = 2, call=None):
+        """call(model, img, text, guidance) -> tensor: the entry point to capture (default: the boundary call itself), e.g.
+        ``lambda m, a, b, g: m.forward_class_sharded(a, b, g, exchange="alltoall")`` -- the all-to-all class split has no host
+        callback on its data path (peer stores + flag barriers), so every rank can replay its own graph."""
         self.model = model
+        if call is None:
+            call = lambda m, a, b, g: m(a, b, g)      # noqa: E731
         self.static_in = [img_feats.clone(), text_feats.clone()] + [g.clone() for g in appearance_guidance]
         side = torch.cuda.Stream(img_feats.device)
         side.wait_stream(torch.cuda.current_stream(img_feats.device))
         with torch.cuda.stream(side):                       # warm-up outside capture: lazy handle/stream/attribute setup
             for _ in range(max(1, warmup)):
-                model(self.static_in[0], self.static_in[1], self.static_in[2:])
+                call(model, self.static_in[0], self.static_in[1], self.static_in[2:])
         torch.cuda.current_stream(img_feats.device).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.static_out = model(self.static_in[0], self.static_in[1], self.static_in[2:])
+            self.static_out = call(model, self.static_in[0], self.static_in[1], self.static_in[2:])
 
     def __call__(self, img_feats, text_feats, appearance_guidance):
         for dst, src in zip(self.static_in, [img_feats, text_feats] + list(appearance_guidance)):
