@@ -36,6 +36,29 @@ class HostPipeline:
             self.uploaded[s].record(self.copy_stream)
         return s
 
+    def upload_sharded(self, host: Sequence[torch.Tensor], rank: int, world: int, group=None) -> int:
+        """Class-sharded serving: every rank needs the SAME inputs.  Instead of ``world`` identical PCIe uploads, rank r
+        uploads rows [r B/world, (r+1) B/world) of every tensor and the shards are all-gathered over NVLink (in place, on the
+        copy stream): 1/world of the host traffic per rank.  All tensors must have the batch as their leading dimension,
+        divisible by ``world``."""
+        import torch.distributed as dist
+        s = self.n % self.depth
+        self.n += 1
+        if self.slots[s] is None:
+            self.slots[s] = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host]
+        with torch.cuda.stream(self.copy_stream):
+            if self.consumed[s] is not None:
+                self.copy_stream.wait_event(self.consumed[s])
+            for d, h in zip(self.slots[s], host):
+                n = d.shape[0] // world
+                if n * world != d.shape[0]:
+                    raise ValueError(f"batch {d.shape[0]} is not divisible by the group size {world}")
+                shard = d[rank * n:(rank + 1) * n]
+                shard.copy_(h[rank * n:(rank + 1) * n], non_blocking=True)
+                dist.all_gather_into_tensor(d, shard, group=group)          # in place: shard is d's own slice
+            self.uploaded[s].record(self.copy_stream)
+        return s
+
     def run(self, ticket: int) -> torch.Tensor:
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(self.uploaded[ticket])
