@@ -88,7 +88,8 @@ _SIGS = [
     ("catseg_exchange_buffer_bytes", C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     ("catseg_forward_class_sharded_a2a", C.c_int, [C.c_void_p] + [C.c_void_p] * 8 +
      [C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t,
-      C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p]),
+      C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("catseg_exchange_guidance_bytes", C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     ("catseg_exchange_logits_bytes", C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     ("catseg_assemble_class_sharded", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                                 C.c_int64, C.c_void_p]),

@@ -304,10 +304,13 @@ class Aggregator(nn.Module):
             else:
                 nbytes = lib.catseg_exchange_buffer_bytes(self._handle, B, T, world)
                 lbytes = lib.catseg_exchange_logits_bytes(self._handle, B, T) if gather else 0
-                if self._peer is None or self._peer.nbytes < nbytes or self._peer.lbytes < lbytes or self._peer.group is not group:
+                # guidance sharded by image: needs the library's own flag barrier (it also runs on the internal stream)
+                gbytes = lib.catseg_exchange_guidance_bytes(self._handle, B, T) if (barrier == "device" and B % world == 0) else 0
+                if (self._peer is None or self._peer.nbytes < nbytes or self._peer.lbytes < lbytes or self._peer.gbytes < gbytes
+                        or self._peer.group is not group):
                     if self._peer is not None:
                         self._peer.close()
-                    self._peer = PeerExchange(nbytes, dev, group, logits_bytes=lbytes)
+                    self._peer = PeerExchange(nbytes, dev, group, logits_bytes=lbytes, guidance_bytes=gbytes)
                 peer = self._peer
 
                 def _barrier(_ctx, _stream):                    # orders the peer stores of the transposition kernels
@@ -323,6 +326,7 @@ class Aggregator(nn.Module):
                 cb = _lib.BARRIER_FN(_barrier)
                 rc = lib.catseg_forward_class_sharded_a2a(self._handle, *ptrs, C.c_void_p(ws.data_ptr()), ws.numel(), B, T, rank, world,
                                                           peer.xb, peer.pb, peer.nbytes, peer.lb if gather else None,
+                                                          peer.gb if gbytes else None, peer.gbytes,
                                                           C.cast(cb, C.c_void_p) if barrier == "collective" else None, None, stream)
                 if rc == 0 and not errors and gather:
                     # peer-direct: every rank's buffer already holds the complete [B,T,4H,4W] logits (a view of the peer
@@ -397,14 +401,16 @@ class PeerExchange:
     library with cudaMalloc, published as CUDA IPC handles over the process group, mapped on every other rank of the node.
     ``xb`` / ``pb`` are the ctypes pointer arrays catseg_forward_class_sharded_a2a takes (entry r = rank r's buffer)."""
 
-    def __init__(self, nbytes: int, device: torch.device, group=None, logits_bytes: int = 0):
+    def __init__(self, nbytes: int, device: torch.device, group=None, logits_bytes: int = 0, guidance_bytes: int = 0):
         import torch.distributed as dist
         lib = _lib.load()
-        self.nbytes, self.lbytes, self.group, self.device = int(nbytes), int(logits_bytes), group, device
+        self.nbytes, self.lbytes, self.gbytes = int(nbytes), int(logits_bytes), int(guidance_bytes)
+        self.group, self.device = group, device
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         self._lib, self._own, self._opened = lib, [], []
         handles = []
-        sizes = [self.nbytes, self.nbytes] + ([self.lbytes] if self.lbytes else [])
+        # buffers: class-sharded X, pixel-sharded P, full logits (optional), guidance (optional); absent ones are 256 bytes
+        sizes = [self.nbytes, self.nbytes, max(self.lbytes, 256), max(self.gbytes, 256)]
         with torch.cuda.device(device):
             for nb in sizes:
                 p = C.c_void_p()
@@ -417,9 +423,9 @@ class PeerExchange:
                 handles.append(hbuf.raw)
             everyone = [None] * world
             dist.all_gather_object(everyone, handles, group=group)
-            self.xb, self.pb, self.lb = (C.c_void_p * world)(), (C.c_void_p * world)(), (C.c_void_p * world)()
+            self.xb, self.pb, self.lb, self.gb = ((C.c_void_p * world)() for _ in range(4))
             for r in range(world):
-                for k, arr in enumerate((self.xb, self.pb, self.lb)[:len(sizes)]):
+                for k, arr in enumerate((self.xb, self.pb, self.lb, self.gb)):
                     if r == rank:
                         arr[r] = self._own[k]
                     else:

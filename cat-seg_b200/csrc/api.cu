@@ -865,8 +865,11 @@ struct ShardExchange {
   catseg_allreduce_fn allreduce; void* ar_ctx;
   float* const* xb; float* const* pb; size_t buf_bytes; catseg_barrier_fn barrier; void* bar_ctx;
   float* const* lb;      // optional: every rank's FULL logits buffer [B][T][16 HW]; the head kernel stores into all of them
+  float* const* gb;      // optional: every rank's guidance buffer [Swin guidance terms | decoder additive maps | flags]: the
+  size_t gb_bytes;       // class-independent front end is then sharded by image and the results are pushed to the peers
 };
 
+static size_t guidance_agq_floats(const Plan& p) { return ((size_t)p.L * 2 * p.B * p.HW * 256 + 63) / 64 * 64; }
 // peer buffer = [residual-stream data][per-class maxima B*T floats][barrier flag block]
 static size_t exchange_data_floats(const Plan& p, int world) { return ((size_t)p.B * (p.Te / world) * p.HW * 128 + 63) / 64 * 64; }
 static size_t exchange_cmax_floats(int B, int T) { return ((size_t)B * T + 63) / 64 * 64; }
@@ -918,6 +921,26 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
       return fail(h, CATSEG_ERR_WORKSPACE, "exchange buffers too small: need %zu bytes each", need_x);
     X = xc->xb[shard_rank];                              // the residual stream lives in the peer-visible buffer
     PB = xc->pb[shard_rank];
+  }
+  // class-independent front end sharded by image (guidance projections, Swin guidance terms, decoder additive maps): rank r
+  // computes images [r B/world, (r+1) B/world) into its own peer-visible buffer and pushes the slices to every peer
+  const bool gshard = a2a && xc->gb != nullptr && B % shard_world == 0 && h->split && (h->fast_mask & CATSEG_FAST_DECODER) &&
+                      (xc->barrier == nullptr);     // the internal stream needs the library's own flag barrier
+  const int gBl = gshard ? B / shard_world : B, gb0 = gshard ? shard_rank * gBl : 0;
+  PeerPtrs gbp{};
+  PeerFlags flagp2{};
+  float* agq_base = ws + p.ag_qk;
+  void* emap_area_ptr = ws + p.dec;
+  if (gshard) {
+    const size_t need_g = guidance_agq_floats(p) * sizeof(float) + decoder_split_emap_bytes(p.dd, B) + 256;
+    if (xc->gb_bytes < need_g) return fail(h, CATSEG_ERR_WORKSPACE, "guidance exchange buffer too small: need %zu bytes", need_g);
+    for (int r = 0; r < shard_world; ++r) {
+      gbp.p[r] = xc->gb[r];
+      flagp2.p[r] = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(xc->gb[r]) + guidance_agq_floats(p) * sizeof(float) +
+                                                decoder_split_emap_bytes(p.dd, B));
+    }
+    agq_base = xc->gb[shard_rank];
+    emap_area_ptr = xc->gb[shard_rank] + guidance_agq_floats(p);
   }
   PeerPtrs cmaxp{};                                      // a2a: every rank's [B][T] table of per-class maxima
   PeerFlags flagp{};
@@ -1029,14 +1052,25 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
     CUDA_OK(h, cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));     // ev_fork was recorded at the start of the stage
     cudaStream_t st = h->aux_stream;             // shadows: the launches below go to the internal stream
     const bool gsplit = prep_fast && h->split;
-    if (gsplit && h->gconv_split_img[0]) RUN(launch_gconv_split(0, g0, h->gconv_split_img[0], h->gproj_b, ws + p.app_g, B, p.Cg, st));
-    else if (gconv_fast && h->gconv_img[0]) RUN(launch_gconv_fast(0, g0, h->gconv_img[0], h->gproj_b, ws + p.app_g, B, p.Cg, st));
-    else RUN(launch_conv3x3_nchw(g0, h->gproj_wt, h->gproj_b, ws + p.app_g, B, p.Cg, p.H, p.W, 128, st));
+    const float* g0l = g0 + (size_t)gb0 * p.Cg * p.HW;      // guidance sharded by image: this rank's images only
+    if (gsplit && h->gconv_split_img[0]) RUN(launch_gconv_split(0, g0l, h->gconv_split_img[0], h->gproj_b, ws + p.app_g, gBl, p.Cg, st));
+    else if (gconv_fast && h->gconv_img[0]) RUN(launch_gconv_fast(0, g0l, h->gconv_img[0], h->gproj_b, ws + p.app_g, gBl, p.Cg, st));
+    else RUN(launch_conv3x3_nchw(g0l, h->gproj_wt, h->gproj_b, ws + p.app_g, gBl, p.Cg, p.H, p.W, 128, st));
     for (int l = 0; l < p.L; ++l) {
-      RUN(launch_layernorm128(ws + p.app_g, ws + p.app_gn, h->gnorm_g[l], h->gnorm_b[l], (long long)B * p.HW, st));
+      RUN(launch_layernorm128(ws + p.app_g, ws + p.app_gn, h->gnorm_g[l], h->gnorm_b[l], (long long)gBl * p.HW, st));
       for (int k = 0; k < 2; ++k)
         RUN(launch_linear(ws + p.app_gn, h->swin[l * 2 + k].wg_qk_t, h->swin[l * 2 + k].bqk,
-                          ws + p.ag_qk + (size_t)(l * 2 + k) * B * p.HW * 256, (long long)B * p.HW, 256, 128, 0, st));
+                          agq_base + (size_t)(l * 2 + k) * B * p.HW * 256 + (size_t)gb0 * p.HW * 256, (long long)gBl * p.HW, 256, 128, 0, st));
+    }
+    if (gshard) {                                          // push this rank's slices of the Swin guidance terms to the peers
+      PeerSegs sg{};
+      for (int blk = 0; blk < p.L * 2 && blk < 8; ++blk) {
+        sg.off[blk] = (long long)((size_t)blk * B * p.HW * 256 + (size_t)gb0 * p.HW * 256);
+        sg.n[blk] = (long long)gBl * p.HW * 256;
+      }
+      sg.nseg = p.L * 2;
+      RUN(launch_peer_bcast(gbp, sg, shard_rank, shard_world, st));
+      RUN(launch_peer_barrier(flagp2, shard_rank, shard_world, st));
     }
     // the Swin blocks only need the projected appearance guidance: join here; the decoder guidance (and, PRECISE, the
     // decoder's per-image additive maps) stay on the internal stream and are joined right before the decoder
@@ -1078,23 +1112,35 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
     // peer-direct logits: this rank's full buffer is pre-filled with -100 here (dropped classes, model.py:721); the peers'
     // head kernels store the kept planes much later, after barriers that the second join of this stream precedes
     if (a2a && xc->lb && p.truncated) RUN(launch_fill(xc->lb[shard_rank], -100.0f, (long long)B * T * 16 * p.HW, st));
+    const float* g1l = g1 + (size_t)gb0 * c.decoder_guidance_dims[0] * 4 * p.HW;
+    const float* g2l = g2 + (size_t)gb0 * c.decoder_guidance_dims[1] * 16 * p.HW;
     if (gsplit && h->gconv_split_img[1])
-      RUN(launch_gconv_split(1, g1, h->gconv_split_img[1], h->dgp_b[0], ws + p.dg0, B, c.decoder_guidance_dims[0], st));
+      RUN(launch_gconv_split(1, g1l, h->gconv_split_img[1], h->dgp_b[0], ws + p.dg0, gBl, c.decoder_guidance_dims[0], st));
     else if (gconv_fast && h->gconv_img[1])
-      RUN(launch_gconv_fast(1, g1, h->gconv_img[1], h->dgp_b[0], ws + p.dg0, B, c.decoder_guidance_dims[0], st));
+      RUN(launch_gconv_fast(1, g1l, h->gconv_img[1], h->dgp_b[0], ws + p.dg0, gBl, c.decoder_guidance_dims[0], st));
     else
-      RUN(launch_conv3x3_nchw(g1, h->dgp_wt[0], h->dgp_b[0], ws + p.dg0, B, c.decoder_guidance_dims[0], 2 * p.H, 2 * p.W,
+      RUN(launch_conv3x3_nchw(g1l, h->dgp_wt[0], h->dgp_b[0], ws + p.dg0, gBl, c.decoder_guidance_dims[0], 2 * p.H, 2 * p.W,
                               p.dd.G1, st));
     if (gsplit && h->gconv_split_img[2])
-      RUN(launch_gconv_split(2, g2, h->gconv_split_img[2], h->dgp_b[1], ws + p.dg1, B, c.decoder_guidance_dims[1], st));
+      RUN(launch_gconv_split(2, g2l, h->gconv_split_img[2], h->dgp_b[1], ws + p.dg1, gBl, c.decoder_guidance_dims[1], st));
     else if (gconv_fast && h->gconv_img[2])
-      RUN(launch_gconv_fast(2, g2, h->gconv_img[2], h->dgp_b[1], ws + p.dg1, B, c.decoder_guidance_dims[1], st));
+      RUN(launch_gconv_fast(2, g2l, h->gconv_img[2], h->dgp_b[1], ws + p.dg1, gBl, c.decoder_guidance_dims[1], st));
     else
-      RUN(launch_conv3x3_nchw(g2, h->dgp_wt[1], h->dgp_b[1], ws + p.dg1, B, c.decoder_guidance_dims[1], 4 * p.H, 4 * p.W,
+      RUN(launch_conv3x3_nchw(g2l, h->dgp_wt[1], h->dgp_b[1], ws + p.dg1, gBl, c.decoder_guidance_dims[1], 4 * p.H, 4 * p.W,
                               p.dd.G2, st));
     if ((h->fast_mask & CATSEG_FAST_DECODER) && h->split) {
-      cudaError_t e = decoder_split_prepare(ws + p.dg0, ws + p.dg1, B, p.dd, h->dec_fast, ws + p.dec, &nl, st);
+      cudaError_t e = decoder_split_prepare(ws + p.dg0, ws + p.dg1, B, gb0, gBl, p.dd, h->dec_fast, emap_area_ptr, &nl, st);
       if (e != cudaSuccess) return fail(h, CATSEG_ERR_CUDA, "decoder maps: %s", cudaGetErrorString(e));
+      if (gshard) {                                        // push this rank's slices of the tile-ordered additive maps
+        size_t o1, o2, per1, per2;
+        decoder_split_emap_slices(p.dd, B, &o1, &o2, &per1, &per2);
+        PeerSegs sg{};
+        sg.off[0] = (long long)(guidance_agq_floats(p) + o1 + (size_t)gb0 * per1); sg.n[0] = (long long)gBl * per1;
+        sg.off[1] = (long long)(guidance_agq_floats(p) + o2 + (size_t)gb0 * per2); sg.n[1] = (long long)gBl * per2;
+        sg.nseg = 2;
+        RUN(launch_peer_bcast(gbp, sg, shard_rank, shard_world, st));
+        RUN(launch_peer_barrier(flagp2, shard_rank, shard_world, st));
+      }
     }
     CUDA_OK(h, cudaEventRecord(h->ev_join2, st));
     if (taps) CUDA_OK(h, cudaStreamWaitEvent(mainst, h->ev_join2, 0));     // the taps below copy the decoder guidance
@@ -1133,7 +1179,7 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
     for (int k = 0; k < 2; ++k) {
       const bool attn_fast = (h->fast_mask & CATSEG_FAST_SWIN_ATTN) != 0;
       const bool mlp_fast = attn_fast || (h->fast_mask & CATSEG_FAST_SWIN_MLP) != 0;
-      const float* agk = ws + p.ag_qk + (size_t)(l * 2 + k) * B * p.HW * 256;
+      const float* agk = agq_base + (size_t)(l * 2 + k) * B * p.HW * 256;
       const int shift = k == 0 ? 0 : c.window_size / 2;
       seg.begin(CATSEG_STAGE_SWIN);
       if (attn_fast && h->attn_version == 2) {
@@ -1239,11 +1285,13 @@ static int forward_impl(catseg_handle* h, const float* img, const float* text, c
       return fail(h, CATSEG_ERR_UNSUPPORTED, "up1/up2 taps are only available with the exact decoder");
     cudaError_t e = h->split ? run_decoder_split(X, ws + p.dg0, ws + p.dg1, out_ids, logits, B, T_out, Te, p.dd, h->dec_fast, h->dec,
                                                  h->head_bias_host, ws + p.dec, p.dec_chunk, h->num_sms, &nl, nlp > 0 ? &lpeers : nullptr,
-                                                 nlp, st)
+                                                 nlp, gshard ? emap_area_ptr : nullptr, st)
                              : run_decoder_fast(X, ws + p.dg0, ws + p.dg1, out_ids, logits, B, T_out, Te, p.dd, h->dec_fast, h->dec,
                                                 h->head_bias_host, ws + p.dec, p.dec_chunk, h->num_sms, &nl, st);
     if (e != cudaSuccess) return fail(h, CATSEG_ERR_CUDA, "fast decoder: %s", cudaGetErrorString(e));
-    if (nlp > 0) {                                         // the peers' planes have landed in this rank's buffer after this barrier
+    if (nlp > 0 || gshard) {
+      // peer-direct logits: the peers' planes have landed in this rank's buffer after this barrier.  Guidance sharded by
+      // image: no peer may start the next call's pushes into this rank's guidance buffer before this decoder has read it
       seg.end();
       seg.begin(CATSEG_STAGE_EXCHANGE);
       if (xbarrier() != 0) return fail(h, CATSEG_ERR_CUDA, "class-shard barrier failed");
@@ -1273,9 +1321,15 @@ extern "C" int catseg_forward_class_sharded(catseg_handle* h, const float* img, 
                                             int shard_rank, int shard_world, catseg_allreduce_fn allreduce, void* ctx,
                                             catseg_stream stream) {
   if (shard_world < 1) return CATSEG_ERR_INVALID;
-  ShardExchange xc{allreduce, ctx, nullptr, nullptr, 0, nullptr, nullptr, nullptr};
+  ShardExchange xc{allreduce, ctx, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0};
   return forward_impl(h, img, text, g0, g1, g2, logits_local, workspace, workspace_bytes, B, T, nullptr, shard_rank, shard_world,
                       &xc, kept_classes_out, stream);
+}
+
+extern "C" size_t catseg_exchange_guidance_bytes(const catseg_handle* h, int B, int T) {
+  if (!h || B <= 0 || T <= 0) return 0;
+  const Plan p = make_plan(h, B, T);
+  return guidance_agq_floats(p) * sizeof(float) + decoder_split_emap_bytes(p.dd, B) + 256;
 }
 
 extern "C" size_t catseg_exchange_logits_bytes(const catseg_handle* h, int B, int T) {
@@ -1296,9 +1350,10 @@ extern "C" int catseg_forward_class_sharded_a2a(catseg_handle* h, const float* i
                                                 int32_t* kept_classes_out, void* workspace, size_t workspace_bytes, int B, int T,
                                                 int shard_rank, int shard_world, float* const* xbuf_peers,
                                                 float* const* pbuf_peers, size_t buf_bytes, float* const* logits_peers,
-                                                catseg_barrier_fn barrier, void* ctx, catseg_stream stream) {
+                                                float* const* gbuf_peers, size_t gbuf_bytes, catseg_barrier_fn barrier, void* ctx,
+                                                catseg_stream stream) {
   if (shard_world < 1 || !xbuf_peers || !pbuf_peers) return CATSEG_ERR_INVALID;
-  ShardExchange xc{nullptr, nullptr, xbuf_peers, pbuf_peers, buf_bytes, barrier, ctx, logits_peers};
+  ShardExchange xc{nullptr, nullptr, xbuf_peers, pbuf_peers, buf_bytes, barrier, ctx, logits_peers, gbuf_peers, gbuf_bytes};
   return forward_impl(h, img, text, g0, g1, g2, logits_local, workspace, workspace_bytes, B, T, nullptr, shard_rank, shard_world,
                       &xc, kept_classes_out, stream);
 }

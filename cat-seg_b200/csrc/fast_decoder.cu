@@ -996,25 +996,53 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
 }
 
 // Per-image additive maps of the PRECISE decoder (guidance convolution + transposed-conv bias, tile ordered): they depend
-// on the decoder guidance only, so the caller computes them on its internal stream beside the aggregation layers.  Uses
-// the head of the scratch area exactly as run_decoder_split lays it out.
-cudaError_t decoder_split_prepare(const float* dg0, const float* dg1, int B, const DecoderDims& d, const DecoderFastW& w,
-                                  void* scratch, int* launches, cudaStream_t st) {
+// on the decoder guidance only, so the caller computes them on its internal stream beside the aggregation layers.  The
+// map area [E1 | E2 | E1t | E2t] (laid out for B images, image major) is the head of the decoder scratch, or -- class split
+// with the guidance sharded by image -- a peer-visible buffer: then only images [b0, b0 + Bl) are computed here (dg0 / dg1
+// point at image b0) and the E1t / E2t slices of the other images arrive from their owners.
+namespace {
+struct EmapArea { float *E1, *E2, *E1t, *E2t; size_t bytes, e1t_off, e2t_off, per1, per2; };
+EmapArea emap_area(void* base, int B, const DecoderDims& d) {
+  const int hw = d.H * d.W;
+  const int narrow = decs_narrow_mask();
+  uint8_t* ptr = reinterpret_cast<uint8_t*>(base);
+  uint8_t* p0 = ptr;
+  auto take = [&](size_t bytes) { uint8_t* r = ptr; ptr += (bytes + 255) / 256 * 256; return r; };
+  EmapArea a{};
+  a.E1 = reinterpret_cast<float*>(take((size_t)B * 4 * hw * d.D1 * 4));
+  a.E2 = reinterpret_cast<float*>(take((size_t)B * 16 * hw * d.D2 * 4));
+  a.E1t = reinterpret_cast<float*>(take(emap_tiled_floats<D1S>(B) * 4));
+  a.E2t = reinterpret_cast<float*>(take(max_sz(emap_tiled_floats<D3S>(B), emap_tiled_floats<D3T>(B)) * 4));
+  a.bytes = (size_t)(ptr - p0);
+  a.e1t_off = (size_t)(reinterpret_cast<uint8_t*>(a.E1t) - p0) / 4;
+  a.e2t_off = (size_t)(reinterpret_cast<uint8_t*>(a.E2t) - p0) / 4;
+  a.per1 = emap_tiled_floats<D1S>(1);
+  a.per2 = (narrow & 4) ? emap_tiled_floats<D3T>(1) : emap_tiled_floats<D3S>(1);
+  return a;
+}
+}  // namespace
+
+size_t decoder_split_emap_bytes(const DecoderDims& d, int B) { return emap_area(nullptr, B, d).bytes; }
+void decoder_split_emap_slices(const DecoderDims& d, int B, size_t* e1t_off, size_t* e2t_off, size_t* per1, size_t* per2) {
+  const EmapArea a = emap_area(nullptr, B, d);
+  *e1t_off = a.e1t_off; *e2t_off = a.e2t_off; *per1 = a.per1; *per2 = a.per2;
+}
+
+cudaError_t decoder_split_prepare(const float* dg0, const float* dg1, int B, int b0, int Bl, const DecoderDims& d,
+                                  const DecoderFastW& w, void* area, int* launches, cudaStream_t st) {
   const int hw = d.H * d.W;
   int nl = 0;
   const int narrow = decs_narrow_mask();
-  uint8_t* ptr = reinterpret_cast<uint8_t*>(scratch);
-  auto take = [&](size_t bytes) { uint8_t* r = ptr; ptr += (bytes + 255) / 256 * 256; return r; };
-  float* E1 = reinterpret_cast<float*>(take((size_t)B * 4 * hw * d.D1 * 4));
-  float* E2 = reinterpret_cast<float*>(take((size_t)B * 16 * hw * d.D2 * 4));
-  float* E1t = reinterpret_cast<float*>(take(emap_tiled_floats<D1S>(B) * 4));
-  float* E2t = reinterpret_cast<float*>(take(max_sz(emap_tiled_floats<D3S>(B), emap_tiled_floats<D3T>(B)) * 4));
-  GuidConvA a{dg0, d.G1, 2 * d.H, 2 * d.W};
-  CKF(launch_igemm(a, w.wg1, 0, 1, B * 4 * hw, d.D1, 9 * d.G1, MapAddStore{E1, w.bmap1, 4 * hw, d.D1}, st));
-  GuidConvA a2{dg1, d.G2, 4 * d.H, 4 * d.W};
-  CKF(launch_igemm(a2, w.wg2, 0, 1, B * 16 * hw, d.D2, 9 * d.G2, MapAddStore{E2, w.bmap2, 16 * hw, d.D2}, st));
-  CKF((launch_relayout_emap<D1S>(E1, E1t, B, st)));
-  if (narrow & 4) CKF((launch_relayout_emap<D3T>(E2, E2t, B, st))); else CKF((launch_relayout_emap<D3S>(E2, E2t, B, st)));
+  const EmapArea a = emap_area(area, B, d);
+  float* E1 = a.E1 + (size_t)b0 * 4 * hw * d.D1;
+  float* E2 = a.E2 + (size_t)b0 * 16 * hw * d.D2;
+  GuidConvA ga{dg0, d.G1, 2 * d.H, 2 * d.W};
+  CKF(launch_igemm(ga, w.wg1, 0, 1, Bl * 4 * hw, d.D1, 9 * d.G1, MapAddStore{E1, w.bmap1, 4 * hw, d.D1}, st));
+  GuidConvA ga2{dg1, d.G2, 4 * d.H, 4 * d.W};
+  CKF(launch_igemm(ga2, w.wg2, 0, 1, Bl * 16 * hw, d.D2, 9 * d.G2, MapAddStore{E2, w.bmap2, 16 * hw, d.D2}, st));
+  CKF((launch_relayout_emap<D1S>(E1, a.E1t + (size_t)b0 * a.per1, Bl, st)));
+  if (narrow & 4) CKF((launch_relayout_emap<D3T>(E2, a.E2t + (size_t)b0 * a.per2, Bl, st)));
+  else CKF((launch_relayout_emap<D3S>(E2, a.E2t + (size_t)b0 * a.per2, Bl, st)));
   if (launches) *launches += nl;
   return cudaSuccess;
 }
@@ -1024,16 +1052,17 @@ cudaError_t decoder_split_prepare(const float* dg0, const float* dg1, int B, con
 cudaError_t run_decoder_split(const float* X, const float* dg0, const float* dg1, const int32_t* classes,
                               float* logits, int B, int T, int Te, const DecoderDims& d, const DecoderFastW& w,
                               const DecoderW& wx, float head_bias, void* scratch, int chunk, int num_sms,
-                              int* launches, const PeerPtrs* lpeers, int nlp, cudaStream_t st) {
+                              int* launches, const PeerPtrs* lpeers, int nlp, const void* ext_area, cudaStream_t st) {
   const int hw = d.H * d.W;
   int nl = 0;
   const int narrow = decs_narrow_mask();
   uint8_t* ptr = reinterpret_cast<uint8_t*>(scratch);
   auto take = [&](size_t bytes) { uint8_t* r = ptr; ptr += (bytes + 255) / 256 * 256; return r; };
-  float* E1 = reinterpret_cast<float*>(take((size_t)B * 4 * hw * d.D1 * 4));
-  float* E2 = reinterpret_cast<float*>(take((size_t)B * 16 * hw * d.D2 * 4));
-  float* E1t = reinterpret_cast<float*>(take(emap_tiled_floats<D1S>(B) * 4));
-  float* E2t = reinterpret_cast<float*>(take(max_sz(emap_tiled_floats<D3S>(B), emap_tiled_floats<D3T>(B)) * 4));
+  // the additive maps were computed by decoder_split_prepare into the head of the scratch area or into `ext_area`
+  const EmapArea ea = emap_area(ext_area != nullptr ? const_cast<void*>(ext_area) : scratch, B, d);
+  ptr += ea.bytes;
+  const float* E1t = ea.E1t;
+  const float* E2t = ea.E2t;
   float* c1a = reinterpret_cast<float*>(take((size_t)chunk * 4 * hw * d.D1 * 4));
   float* c1b = reinterpret_cast<float*>(take((size_t)chunk * 4 * hw * d.D1 * 4));
   float* c2a = reinterpret_cast<float*>(take((size_t)chunk * 16 * hw * d.D2 * 4));
@@ -1047,7 +1076,7 @@ cudaError_t run_decoder_split(const float* X, const float* dg0, const float* dg1
   float* s2a = reinterpret_cast<float*>(take((size_t)chunk * nb3 * 2 * 2 * 4));
   float* s2b = reinterpret_cast<float*>(take((size_t)chunk * nb4 * 2 * 2 * 4));
   float* gss = reinterpret_cast<float*>(take((size_t)chunk * 64 * 2 * 4));
-  (void)E1; (void)E2; (void)dg0; (void)dg1;            // the additive maps E1t / E2t were computed by decoder_split_prepare
+  (void)dg0; (void)dg1;
   const int nslice = B * Te;
   for (int s0 = 0; s0 < nslice; s0 += chunk) {
     const int n = nslice - s0 < chunk ? nslice - s0 : chunk;

@@ -122,6 +122,9 @@ cudaError_t launch_gemm_split(const GemmSplitParams& p, cudaStream_t st);
 // ---------------------------------------------------------------- shard_exchange.cu
 struct PeerFlags { uint32_t* p[kMaxShard]; };   // every rank's barrier flag block (kMaxShard + 2 words)
 cudaError_t launch_peer_barrier(const PeerFlags& f, int rank, int world, cudaStream_t st);
+// copies nseg segments (float offsets / counts relative to the buffer base, multiples of 4) of this rank's buffer to every peer
+struct PeerSegs { long long off[8]; long long n[8]; int nseg; };
+cudaError_t launch_peer_bcast(const PeerPtrs& bufs, const PeerSegs& segs, int rank, int world, cudaStream_t st);
 cudaError_t launch_shard_put_cmax(const float* loc, const PeerPtrs& dst, int B, int Tr, int T, int t0, int world, cudaStream_t st);
 cudaError_t launch_shard_c2p(const float* X, const PeerPtrs& pb, int B, int Tl, int Te, int HW, int rank, int world, cudaStream_t st);
 cudaError_t launch_shard_p2c(const float* P, const PeerPtrs& xb, int B, int Tl, int Te, int HW, int rank, int world, cudaStream_t st);
@@ -280,13 +283,17 @@ cudaError_t run_decoder_fast(const float* X, const float* dg0, const float* dg1,
                              int* launches, cudaStream_t st);
 
 size_t decoder_split_scratch_bytes(const DecoderDims& d, int B, int chunk);
-cudaError_t decoder_split_prepare(const float* dg0, const float* dg1, int B, const DecoderDims& d, const DecoderFastW& w,
-                                  void* scratch, int* launches, cudaStream_t st);
+// additive-map area [E1 | E2 | E1t | E2t] for B images (the head of the decoder scratch, or a peer-visible buffer)
+size_t decoder_split_emap_bytes(const DecoderDims& d, int B);
+void decoder_split_emap_slices(const DecoderDims& d, int B, size_t* e1t_off, size_t* e2t_off, size_t* per1, size_t* per2);
+// computes the maps of images [b0, b0 + Bl) (dg0 / dg1 point at image b0) into `area`
+cudaError_t decoder_split_prepare(const float* dg0, const float* dg1, int B, int b0, int Bl, const DecoderDims& d,
+                                  const DecoderFastW& w, void* area, int* launches, cudaStream_t st);
 // lpeers (optional, class-sharded peer-direct mode): every rank's full logits buffer; the head kernel stores into all of them
 cudaError_t run_decoder_split(const float* X, const float* dg0, const float* dg1, const int32_t* classes,
                               float* logits, int B, int T, int Te, const DecoderDims& d, const DecoderFastW& w,
                               const DecoderW& wx, float head_bias, void* scratch, int chunk, int num_sms,
-                              int* launches, const PeerPtrs* lpeers, int nlp, cudaStream_t st);
+                              int* launches, const PeerPtrs* lpeers, int nlp, const void* ext_area, cudaStream_t st);
 
 // ---------------------------------------------------------------- stitch.cu
 // scratch_mask: T uint32 of device scratch (enables the skipping of dropped-class planes), or nullptr

@@ -85,6 +85,23 @@ cudaError_t launch_peer_barrier(const PeerFlags& f, int rank, int world, cudaStr
   return cudaGetLastError();
 }
 
+// segments of this rank's buffer -> the same offsets of every other rank's buffer (peer stores, 16 bytes per thread and step)
+__global__ void peer_bcast_kernel(PeerPtrs bufs, PeerSegs segs, int rank, int world) {
+  const float4* src = reinterpret_cast<const float4*>(bufs.p[rank]);
+  for (int sgi = 0; sgi < segs.nseg; ++sgi) {
+    const long long o4 = segs.off[sgi] >> 2, n4 = segs.n[sgi] >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      const float4 v = src[o4 + i];
+      for (int r = 0; r < world; ++r)
+        if (r != rank) reinterpret_cast<float4*>(bufs.p[r])[o4 + i] = v;
+    }
+  }
+}
+cudaError_t launch_peer_bcast(const PeerPtrs& bufs, const PeerSegs& segs, int rank, int world, cudaStream_t st) {
+  peer_bcast_kernel<<<296, 256, 0, st>>>(bufs, segs, rank, world);
+  return cudaGetLastError();
+}
+
 // local per-class maxima [B][Tr] -> columns [t0, t0 + Tr) of every rank's [B][T] table
 __global__ void shard_put_cmax_kernel(const float* __restrict__ loc, PeerPtrs dst, int B, int Tr, int T, int t0, int world) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -179,11 +179,18 @@ int catseg_forward_class_sharded(catseg_handle* h, const float* img_feats, const
 typedef int (*catseg_barrier_fn)(void* ctx, catseg_stream stream);
 size_t catseg_exchange_buffer_bytes(const catseg_handle* h, int B, int T, int shard_world);
 size_t catseg_exchange_logits_bytes(const catseg_handle* h, int B, int T);
+/*   guidance_peers           NULL, or [world] device pointers (HOST array) to every rank's guidance buffer
+ *                            (catseg_exchange_guidance_bytes, catseg_peer_alloc): the class-independent front end (guidance
+ *                            projections, Swin guidance terms, decoder additive maps) is then sharded by IMAGE -- rank r
+ *                            computes images [r B/world, (r+1) B/world) and pushes its slices to every peer -- instead of
+ *                            being repeated for all B images on every rank.  Needs B % world == 0 and barrier == NULL. */
+size_t catseg_exchange_guidance_bytes(const catseg_handle* h, int B, int T);
 int catseg_forward_class_sharded_a2a(catseg_handle* h, const float* img_feats, const float* text_feats, const float* g0,
                                      const float* g1, const float* g2, float* logits_local, int32_t* kept_classes_out,
                                      void* workspace, size_t workspace_bytes, int B, int T, int shard_rank, int shard_world,
                                      float* const* xbuf_peers, float* const* pbuf_peers, size_t buf_bytes,
-                                     float* const* logits_peers, catseg_barrier_fn barrier, void* ctx, catseg_stream stream);
+                                     float* const* logits_peers, float* const* guidance_peers, size_t guidance_bytes,
+                                     catseg_barrier_fn barrier, void* ctx, catseg_stream stream);
 /* Final assembly after the all-gather of the local planes: gathered [world][B][T_local][npix] (rank-major), kept_classes
  * [B][world*T_local] -> logits [B][T][npix] with -100 for classes that were not kept (model.py:721-724).  pos_scratch: B*T
  * int32 of device scratch.  npix % 4 == 0, B*T <= 65535. */
