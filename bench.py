@@ -416,6 +416,8 @@ def run_ours(args):
                 except Exception as e:              # noqa: BLE001 -- the eager record stands
                     recs[exch]["cuda_graph"] = {"error": str(e)[:200]}
                 sarm.graph_run = None
+            if exch == "alltoall":
+                recs[exch]["barriers_healthy"] = bool(sarm.model.class_shard_healthy(sarm.B, sarm.T))
             if sarm.model._peer is not None:
                 sarm.model._peer.close()
             del sarm

@@ -90,6 +90,7 @@ _SIGS = [
      [C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t,
       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("catseg_exchange_guidance_bytes", C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    ("catseg_exchange_timed_out", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     ("catseg_exchange_logits_bytes", C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     ("catseg_assemble_class_sharded", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                                 C.c_int64, C.c_void_p]),

@@ -342,6 +342,23 @@ class Aggregator(nn.Module):
             dist.all_gather_into_tensor(gathered, local, group=group)
             return assemble_class_sharded(gathered, kept, T)
 
+    def class_shard_healthy(self, B: int, T: int, group=None) -> bool:
+        """False if one of this rank's flag barriers of the all-to-all class split ever timed out (a peer died or stalled for
+        seconds): every result since then is invalid.  Synchronises the device; call it at the end of a job, not per step."""
+        import torch.distributed as dist
+        if self._peer is None:
+            return True
+        out = C.c_int(0)
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        with torch.cuda.device(self._peer.device):
+            torch.cuda.synchronize(self._peer.device)
+            rc = _lib.load().catseg_exchange_timed_out(self._handle, C.c_void_p(self._peer.pb[rank]),
+                                                       C.c_void_p(self._peer.gb[rank]) if self._peer.gbytes else None, B, T, world,
+                                                       C.byref(out))
+        if rc != 0:
+            raise self._lib_error(rc)
+        return out.value == 0
+
     def _make_taps(self, names, B, T, H, W, dev):
         c = self.cfg
         Te, HW, hid = self.kept_classes(T), H * W, c.hidden_dim

@@ -1332,6 +1332,25 @@ extern "C" size_t catseg_exchange_guidance_bytes(const catseg_handle* h, int B, 
   return guidance_agq_floats(p) * sizeof(float) + decoder_split_emap_bytes(p.dd, B) + 256;
 }
 
+// 1 if a flag barrier of this rank ever gave up waiting (a peer died or fell > ~4 s behind): results since then are invalid.
+// Synchronous (one 4-byte device-to-host copy per buffer); meant for the end of a job or a test, not for the hot path.
+extern "C" int catseg_exchange_timed_out(const catseg_handle* h, const float* pbuf_self, const float* gbuf_self, int B, int T,
+                                         int shard_world, int* timed_out) {
+  if (!h || !pbuf_self || !timed_out || B <= 0 || T <= 0 || shard_world < 1) return CATSEG_ERR_INVALID;
+  const Plan p = make_plan(h, B, T);
+  if (p.Te % shard_world) return CATSEG_ERR_INVALID;
+  uint32_t v = 0, v2 = 0;
+  const uint32_t* f1 = reinterpret_cast<const uint32_t*>(pbuf_self + exchange_data_floats(p, shard_world) + exchange_cmax_floats(B, T));
+  if (cudaMemcpy(&v, f1 + kMaxShard + 1, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return CATSEG_ERR_CUDA;
+  if (gbuf_self) {
+    const uint32_t* f2 = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(gbuf_self) + guidance_agq_floats(p) * sizeof(float) +
+                                                           decoder_split_emap_bytes(p.dd, B));
+    if (cudaMemcpy(&v2, f2 + kMaxShard + 1, sizeof(v2), cudaMemcpyDeviceToHost) != cudaSuccess) return CATSEG_ERR_CUDA;
+  }
+  *timed_out = (v | v2) != 0 ? 1 : 0;
+  return CATSEG_OK;
+}
+
 extern "C" size_t catseg_exchange_logits_bytes(const catseg_handle* h, int B, int T) {
   if (!h || B <= 0 || T <= 0) return 0;
   const Plan p = make_plan(h, B, T);

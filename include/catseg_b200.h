@@ -185,6 +185,10 @@ size_t catseg_exchange_logits_bytes(const catseg_handle* h, int B, int T);
  *                            computes images [r B/world, (r+1) B/world) and pushes its slices to every peer -- instead of
  *                            being repeated for all B images on every rank.  Needs B % world == 0 and barrier == NULL. */
 size_t catseg_exchange_guidance_bytes(const catseg_handle* h, int B, int T);
+/* *timed_out = 1 if one of this rank's flag barriers ever gave up waiting (~4 s: a peer died): results since then are invalid.
+ * pbuf_self / gbuf_self: this rank's own pixel-sharded and (optional) guidance buffers.  Synchronous; not for the hot path. */
+int catseg_exchange_timed_out(const catseg_handle* h, const float* pbuf_self, const float* gbuf_self, int B, int T,
+                              int shard_world, int* timed_out);
 int catseg_forward_class_sharded_a2a(catseg_handle* h, const float* img_feats, const float* text_feats, const float* g0,
                                      const float* g1, const float* g2, float* logits_local, int32_t* kept_classes_out,
                                      void* workspace, size_t workspace_bytes, int B, int T, int shard_rank, int shard_world,

@@ -73,6 +73,7 @@ def _worker(rank: int, world: int, port: int, q, model: str, B: int, T: int):
             stacked = torch.stack(parts)
             res["assemble_equal"] = bool(torch.equal(assemble_class_sharded(stacked.cuda(), kept2, T).cpu(),
                                                      assemble_class_sharded(stacked, kept2.cpu(), T)))
+        assert m.class_shard_healthy(B, T), "a flag barrier timed out"
         dist.barrier()
         if m._peer is not None:
             m._peer.close()
