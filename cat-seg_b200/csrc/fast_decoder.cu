@@ -874,7 +874,7 @@ struct MapAddStore {
 #define D5N 32, 16, 16, false, false, 96, 6, true, 2
 #define D5W 32, 16, 16, false, false, 96, 12, true, 1
 // PRECISE shapes: one 17-warp CTA per SM, fp32 activations in and out
-#define D1S 128, 64, 64, true, true, 24, 4, false, 1, true
+#define D1S 128, 64, 64, true, true, 24, 8, false, 1, true
 #define D2S 64, 64, 64, false, true, 48, 8, false, 1, true
 #define D3S 64, 32, 32, true, true, 48, 8, false, 1, true
 #define D4S 32, 32, 32, false, true, 96, 8, false, 1, true
