@@ -8,8 +8,9 @@
 //     epilogue and the per-class maximum over the pixels reduced there as well (model.py:648-652, 695);
 //   * the token-wise linears of the CLIP dense last block (model_vpt.py:219-240, 306-312) with bias / QuickGELU /
 //     residual epilogues.
-// One CTA = one 128 x 128 output tile; K is consumed in chunks of 64 through two shared-memory buffers: the threads
-// stage chunk c+1 while the tensor pipe works on chunk c.
+// One CTA = one 128 x 128 output tile; K is consumed in chunks of 32 through two shared-memory buffers: the threads
+// stage chunk c+1 while the tensor pipe works on chunk c; 64 KiB per CTA, so three CTAs share an SM and one CTA's staging
+// overlaps the others' MMAs and epilogues.
 #include "internal.h"
 #include "split_common.cuh"
 
@@ -19,14 +20,14 @@ using namespace fast;
 
 namespace {
 constexpr int GS_THREADS = 256;
-constexpr int GS_KC = 64;                                      // K per chunk: 8 canonical 8-element chunks
-constexpr uint32_t GS_TILE = 8 * LBO_W;                        // one 128 x 64 fp16 tile = 16 KiB
+constexpr int GS_KC = 32;                                      // K per chunk: 4 canonical 8-element chunks (64 KiB per CTA: 3 CTAs per SM)
+constexpr uint32_t GS_TILE = (GS_KC / 8) * LBO_W;              // one 128 x 32 fp16 tile = 8 KiB
 constexpr uint32_t GS_BUF = 4 * GS_TILE;                       // A hi | A lo | B hi | B lo
 constexpr uint32_t GS_BAR = 2 * GS_BUF;
 constexpr uint32_t GS_SMEM = GS_BAR + 4 * 8 + 16;
 }  // namespace
 
-__global__ void __launch_bounds__(GS_THREADS, 1) gemm_split_kernel(GemmSplitParams p) {
+__global__ void __launch_bounds__(GS_THREADS, 3) gemm_split_kernel(GemmSplitParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar_free = reinterpret_cast<uint64_t*>(smem + GS_BAR);     // [2] the MMAs that read buffer i have completed
   uint64_t* bar_done = bar_free + 2;
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gemm_split_kernel(GemmSplitPara
   auto stage = [&](const float* src, long long s_row, long long s_k, int row0, int nrows, int k0, uint8_t* hi, uint8_t* lo,
                    const int32_t* index) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < GS_KC / 16; ++i) {
       const int item = tid + i * GS_THREADS, r = item & 127, c = item >> 7;
       const int k = k0 + c * 8;
       float v[8];
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gemm_split_kernel(GemmSplitPara
         const uint64_t d_ah = umma::make_smem_desc(a, LBO_W, 128), d_al = umma::make_smem_desc(a + GS_TILE, LBO_W, 128);
         const uint64_t d_bh = umma::make_smem_desc(a + 2 * GS_TILE, LBO_W, 128), d_bl = umma::make_smem_desc(a + 3 * GS_TILE, LBO_W, 128);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < GS_KC / 16; ++k) {
           const uint64_t o = (uint64_t)(k * 2 * (LBO_W >> 4));
           umma::mma_f16_ss(tm, d_ah + o, d_bh + o, IDESC_128x128, (c > 0 || k > 0) ? 1u : 0u);
           umma::mma_f16_ss(tm, d_al + o, d_bh + o, IDESC_128x128, 1u);
