@@ -753,7 +753,11 @@ Plan make_plan(const catseg_handle* h, int B, int T) {
   {
     size_t fe = decoder_exact_scratch_floats(p.dd, p.dec_chunk);
     if (h->fast_mask & CATSEG_FAST_DECODER) {
-      p.dec_chunk = nslice < 1024 ? nslice : 1024;
+      static const int chunk_env = [] { const char* e = getenv("CATSEG_DEC_CHUNK"); return e ? atoi(e) : 0; }();   // A/B
+      // one chunk for up to 4096 slices (fp32 intermediates: 3.5 MB per slice, 14.5 GB at 4096 -- B200 has 180 GB): fewer launch
+      // tails; smaller chunks that would keep the intermediates in the 126 MB L2 were measured SLOWER (148: 19.6 ms, 4096: 17.65 ms)
+      const int want = chunk_env > 0 ? chunk_env : 4096;
+      p.dec_chunk = nslice < want ? nslice : want;
       fe = ((h->split ? decoder_split_scratch_bytes(p.dd, B, p.dec_chunk) : decoder_fast_scratch_bytes(p.dd, B, p.dec_chunk)) + 3) / 4;
     }
     p.dec = take(fe);
