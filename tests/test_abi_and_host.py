@@ -128,6 +128,13 @@ def test_committed_launch_summary_is_reproducible():
     assert r.stdout.strip() == open(txt).read().strip()
     # the kernels named in the summary are the ones the library exports today (decoder shapes included)
     assert "swin_attn_fast_kernel" in r.stdout and "band_conv_kernel<64, 64, 64, 0, 0, 48, 12, 0, 1>" in r.stdout
+    # round 2: the PRECISE launch list and its summary
+    csv2 = os.path.join(root, "profiles", "r02_ncu_launches_cfg4_b16_precise.csv")
+    txt2 = os.path.join(root, "profiles", "r02_ncu_launch_summary_cfg4_b16_precise.txt")
+    r2 = subprocess.run([sys.executable, os.path.join(root, "tools", "summarize_launches.py"), csv2], capture_output=True, text=True)
+    assert r2.returncode == 0, r2.stderr
+    assert r2.stdout.strip() == open(txt2).read().strip()
+    assert "swin_attn2_kernel<1>" in r2.stdout and "mlp_split_kernel" in r2.stdout and "head_conv_f32_kernel" in r2.stdout
 
 
 def test_clip_dense_module_loads_clip_visual_state_dict():
