@@ -97,5 +97,33 @@ __device__ __forceinline__ float gelu_precise(float x) {
   return x * (x < 0.0f ? q : 1.0f - q);
 }
 
+// The same function on two values at once, on packed fp32 pairs (FFMA2 / FMUL2 on sm_100a: half the issue slots of the
+// scalar form, which is what bounds this epilogue), rearranged as  GELU(x) = max(x, 0) - |x| q(|x|),  q = erfc(|x| / sqrt 2) / 2:
+// no compare / select / 1 - q, the 1/2 folded into the polynomial.  14 issue slots + 4 MUFU per PAIR (scalar form: 15 + 2 per
+// element); max-abs error against float64 over [-8, 8]: 3.3e-7.  (b0, b1) is the bias to add first; x0 / x1 are updated in place.
+__device__ __forceinline__ void gelu_precise_pair(float& x0, float& x1, float b0, float b1) {
+  const unsigned long long X = add2(pk2(x0, x1), pk2(b0, b1));
+  float a0, a1;
+  unpk2(X, a0, a1);
+  const unsigned long long NA = pk2(-fabsf(a0), -fabsf(a1));                       // -|x|
+  constexpr float pz = -0.3275911f * 0.70710678118654752440f;
+  float d0, d1, t0, t1;
+  unpk2(fma2(NA, pk2(pz, pz), pk2(1.0f, 1.0f)), d0, d1);                           // 1 + p |x| / sqrt 2
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const unsigned long long T = pk2(t0, t1);
+  constexpr float c5 = 0.5f * 1.061405429f, c4 = 0.5f * -1.453152027f, c3 = 0.5f * 1.421413741f, c2 = 0.5f * -0.284496736f,
+                  c1 = 0.5f * 0.254829592f, ke = -0.72134752044448170368f;
+  unsigned long long P = fma2(T, pk2(c5, c5), pk2(c4, c4));
+  P = fma2(P, T, pk2(c3, c3));
+  P = fma2(P, T, pk2(c2, c2));
+  P = fma2(P, T, pk2(c1, c1));
+  float e0, e1;
+  unpk2(mul2(mul2(X, X), pk2(ke, ke)), e0, e1);                                    // -x^2 / 2 * log2(e)
+  const unsigned long long E = pk2(umma::ex2_approx(e0), umma::ex2_approx(e1));
+  const unsigned long long Q = mul2(mul2(P, T), E);                                // q(|x|)
+  unpk2(fma2(NA, Q, pk2(fmaxf(a0, 0.0f), fmaxf(a1, 0.0f))), x0, x1);
+}
+
 }  // namespace split
 }  // namespace catseg

@@ -157,10 +157,17 @@ mlp_split_kernel(const float* __restrict__ Xin, const float* __restrict__ Xres, 
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 b4 = __ldg(bb + i);
-            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+            if constexpr (ACT == 0) {                         // GELU on packed pairs (bias added inside)
+              split::gelu_precise_pair(v[4 * i], v[4 * i + 1], b4.x, b4.y);
+              split::gelu_precise_pair(v[4 * i + 2], v[4 * i + 3], b4.z, b4.w);
+            } else {
+              v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+            }
           }
+          if constexpr (ACT != 0) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = ACT == 0 ? split::gelu_precise(v[i]) : fmaxf(v[i], 0.0f);
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+          }
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             umma::split_h2(v[c * 8 + 0], v[c * 8 + 1], phi[c].x, plo[c].x);

@@ -128,6 +128,47 @@ __global__ void tc_throughput(float* out, int iters, long long* cycles, int N, i
   if (t < 32) tmem_dealloc<512>(tm);
 }
 
+// Commit probe (test 27): what does a tcgen05.commit in the MMA stream cost?  Thread 0 issues groups of `group` MMAs
+// (M128, N, K16) and commits after every group according to `mode`:
+//   0 no commit at all | 1 commit to ONE mbarrier nobody waits on | 2 commits round-robin over 8 mbarriers |
+//   3 one mbarrier, warp 1 waits for every phase | 4 a single commit BEFORE the first MMA, none afterwards
+__global__ void commit_probe(float* out, int ngroups, long long* cycles, int N, int group, int mode) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint64_t bars[8];
+  __shared__ uint32_t tmem_base;
+  int t = threadIdx.x;
+  for (int i = t; i < 20000; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (t == 0) { mbar_init(&bar, 1); for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1); mbar_fence_init(); }
+  if (t < 32) tmem_alloc<512>(&tmem_base);
+  fence_proxy_async(); fence_before_sync(); __syncthreads(); fence_after_sync();
+  uint32_t tm = tmem_base;
+  const int lbo_a = 2064, lbo_b = N * 16;
+  long long t0 = clock64();
+  if (t == 0) {
+    uint32_t idesc = make_idesc_bf16(128, N);
+    uint64_t da0 = make_smem_desc(smem_u32(smem), lbo_a, 128), db0 = make_smem_desc(smem_u32(smem + 40000), lbo_b, 128);
+    if (mode == 4) mma_commit(&bars[0]);
+    for (int g = 0; g < ngroups; ++g) {
+      for (int i = 0; i < group; ++i)
+        mma_bf16_ss(tm + (g & 1) * 256, da0 + (uint64_t)((i & 3) * 2 * (lbo_a >> 4)), db0 + (uint64_t)((i & 3) * 2 * (lbo_b >> 4)), idesc, 1);
+      if (mode == 1 || mode == 3) mma_commit(&bars[0]);
+      else if (mode == 2) mma_commit(&bars[g & 7]);
+    }
+    mma_commit(&bar);
+  } else if (t == 32 && mode == 3) {
+    for (int g = 0; g < ngroups; ++g) (void)mbar_wait_bounded(&bars[0], (uint32_t)(g & 1), 1 << 12);   // bounded: a missed phase must not hang
+  }
+  mbar_wait(&bar, 0);
+  long long t1 = clock64();
+  fence_after_sync();
+  if (t == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+  float v[16];
+  if (t < 128) { tmem_ld16(tm + ((uint32_t)((t >> 5) * 32) << 16), v); if (v[0] == 12345.f) out[t] = v[0]; }
+  fence_before_sync(); __syncthreads();
+  if (t < 32) tmem_dealloc<512>(tm);
+}
+
 // Contention probe: thread 0 issues a long MMA chain (M128 N128) while the other warps generate (mode bit 0) TMEM loads
 // from other columns, (bit 1) shared-memory store+load traffic, (bit 2) global loads.  Reports cycles per MMA.
 __global__ void contention(float* out, const float* gsrc, int nmma, long long* cycles, int mode, int random_data = 0) {
@@ -385,6 +426,23 @@ int main(int argc, char** argv) {
         printf("PROBE issue cost (%s): %.1f cycles per MMA end-to-end, %.1f cycles per MMA spent issuing (8-MMA GEMMs + commit)\n",
                mode == 0 ? "if (tid == 0)" : "warp 0 + elect.sync", (double)c[0] / (2000.0 * 8), (double)c[1] / (2000.0 * 8));
       }
+    } else if (id == 27) {
+      size_t smem = 100000;
+      CHECK(cudaFuncSetAttribute(commit_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int total = 8192;                       // MMAs per run
+      const int Ns[] = {128, 64, 256};
+      const int groups[] = {4, 8, 16, 32, 64, 256, 1024};
+      for (int N : Ns)
+        for (int mode = 0; mode < 5; ++mode)
+          for (int group : groups) {
+            if ((mode == 0 || mode == 4) && group != 16) continue;
+            if (N != 128 && (mode == 2 || mode == 3 || (group != 8 && group != 32 && group != 256))) { if (!(mode == 0 || mode == 4)) continue; }
+            commit_probe<<<prop.multiProcessorCount, 128, smem>>>(out, total / group, cyc, N, group, mode); CHECK(cudaDeviceSynchronize());
+            long long c; CHECK(cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost));
+            printf("PROBE commit N=%d mode=%d (%s) group=%d MMAs: %.1f cycles per MMA\n", N, mode,
+                   mode == 0 ? "no commit" : mode == 1 ? "one barrier, no waiter" : mode == 2 ? "8 barriers round-robin" : mode == 3 ? "one barrier, a waiting warp" : "single commit up front",
+                   group, (double)c / total);
+          }
     } else if (id == 26) {
       // row-shifted operand starts (implicit-GEMM convolution taps): does an A / B tile whose first row is not a multiple
       // of 8 rows (start address not 128-byte aligned) cost extra shared-memory wavefronts?
