@@ -451,7 +451,10 @@ int main(int argc, char** argv) {
       const int cfgs[][5] = {{64, 2064, 1024, 0, 0}, {64, 2064, 1024, 16, 0}, {64, 2064, 1024, 64, 0}, {64, 2064, 1024, 128, 0}, {64, 2064, 1024, 816, 0},
                              {64, 2048, 1024, 0, 0}, {64, 2048, 1024, 16, 0}, {64, 6416, 1024, 816, 0}, {64, 6416, 1024, 800, 0},
                              {32, 2064, 512, 0, 0}, {32, 2064, 512, 16, 0}, {128, 2064, 2048, 0, 0}, {128, 2064, 2048, 16, 0}, {256, 2064, 4096, 0, 0}, {256, 2064, 4096, 16, 0},
-                             {64, 2064, 1024, 0, 16}, {144, 2048, 2320, 0, 16}};
+                             {64, 2064, 1024, 0, 16}, {144, 2048, 2320, 0, 16},
+                             // decoder D1 / D2 shapes: the lo MMA (N = 64) reads the first 64 rows of a 128-row [Wh | Wl] image (lboB = 2048)
+                             {64, 2064, 2048, 0, 0}, {64, 4240, 2048, 432, 0}, {128, 4240, 2048, 432, 0}, {64, 8080, 2048, 816, 0}, {128, 8080, 2048, 816, 0},
+                             {32, 8080, 1024, 816, 0}, {64, 8080, 1024, 816, 0}};
       for (auto& c5 : cfgs) {
         tc_throughput<<<prop.multiProcessorCount, 128, smem>>>(out, iters, cyc, c5[0], c5[1], c5[2], 0, c5[3], c5[4]); CHECK(cudaDeviceSynchronize());
         long long c; CHECK(cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost));
