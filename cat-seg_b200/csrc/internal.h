@@ -194,7 +194,7 @@ cudaError_t launch_pack_qkv_head_img(__half* dst, const float* Wq, const float* 
                                      int h, cudaStream_t st);
 
 // ---------------------------------------------------------------- swin_attn2.cu
-// agT: fp32 guidance terms [B][4 windows][18 token groups][256 features][8 tok] of this block (launch_pack_ag_windows_T, same shift)
+// agT: fp32 guidance terms [B][4 windows][18 token groups][2 halves][256 features][4 tok] of this block (launch_pack_ag_windows_T, same shift)
 cudaError_t launch_swin_attn2(float* X, const float* agT, int nslice, int Te, int shift, const SwinAttn2W& w, bool split,
                               int num_sms, cudaStream_t st);
 cudaError_t launch_pack_ag_windows_T(const float* ag_qk, float* out, int B, int shift, cudaStream_t st);

@@ -8,7 +8,7 @@
 // one M = 128 GEMM per head with 32 dead rows).
 //   phase 1   Q^T K^T V^T (128 x 144 each) = Wq|Wk|Wv . LN1(x)^T            TMEM [0,432)
 //             q / k: one fp16 term (attention weights, tools/precision_study.py); v: hi+lo pairs, 3 products (PRECISE)
-//   epilogue  + guidance term (fp32, read from L2 in coalesced 1 KiB pieces: class independent, shared by the 256 classes of an image)
+//   epilogue  + guidance term (fp32, read from L2 in coalesced 512-byte pieces: class independent, shared by the 256 classes of an image)
 //             -> per-head images [token group][32 d][8 tok]: MN-major A/B operands of S = Q K^T and K-major B of O = P V
 //   per head  S (two query tiles; queries 128..143 replicated into all four TMEM lane quarters so that all 16 warps share
 //             the second tile) -> softmax with the -100 shift mask by index arithmetic -> P (single term) -> O = P (Vh + Vl)
@@ -203,17 +203,18 @@ swin_attn2_kernel(float* __restrict__ X, const float* __restrict__ agT, int nwin
     //      group) units are dealt round-robin to the four groups.  The guidance terms of the first units are fetched
     //      (fp32, [image][window][256 features][144 tokens]) BEFORE waiting for the MMAs.
     {
-      // guidance terms [image][window][18 token groups][256 features][8 tokens]: the 32 lanes (= 32 features) of a warp read
-      // 1 KiB contiguous per unit (with the token axis innermost per feature, every lane touched its own 128-byte line:
-      // 64 lines per unit, ~9 K LSU cycles per window)
-      const float* ag0 = agT + ((long long)b * 4 + win) * (18 * 256 * 8) + (q4 * 32 + lane) * 8;
+      // guidance terms [image][window][18 token groups][2 halves][256 features][4 tokens]: the 32 lanes (= 32 features) of a
+      // warp read 512 contiguous bytes per load, 1 KiB per unit (with the token axis innermost per feature every lane touched
+      // its own 128-byte line: 64 lines per unit, ~9 K LSU cycles per window; with 8 tokens per feature innermost each 16-byte
+      // load still fetched every sector twice)
+      const float* ag0 = agT + ((long long)b * 4 + win) * (18 * 256 * 8) + (q4 * 32 + lane) * 4;
       constexpr int NU = 14, D = 4;
       float4 ga[D][2];
       auto fetch = [&](int i, float4* dst) {
         const int u = grp + 4 * i;
         if (u < 36) {                                  // q (u < 18) and k units carry a guidance term
-          const float* p = ag0 + ((u % 18) * 256 + (u >= 18 ? 128 : 0)) * 8;
-          dst[0] = ld4(p); dst[1] = ld4(p + 4);
+          const float* p = ag0 + ((u % 18) * 512 + (u >= 18 ? 128 : 0)) * 4;
+          dst[0] = ld4(p); dst[1] = ld4(p + 256 * 4);
         }
       };
 #pragma unroll
@@ -564,19 +565,20 @@ cudaError_t launch_swin_attn2(float* X, const float* agT, int nslice, int Te, in
   return cudaGetLastError();
 }
 
-// ag_qk fp32 [B][576][256] (q 128 | k 128 guidance terms per pixel, biases folded in) -> fp32 [B][4 windows][18 token groups][256][8 tok]
+// ag_qk fp32 [B][576][256] (q 128 | k 128 guidance terms per pixel, biases folded in) -> fp32 [B][4 windows][18 token groups][2][256][4 tok]
 // in window-token order with the cyclic shift applied (SwinTransformerBlock.forward, model.py:195-205)
 __global__ void pack_ag_windows_T_kernel(const float* __restrict__ ag, float* __restrict__ out, int B, int shift) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * 4 * 256 * NTOK) return;
-  // output index i = (((b * 4 + win) * 18 + tg) * 256 + f) * 8 + t8   (token = 8 tg + t8)
-  const int t8 = (int)(i & 7);
-  long long r = i >> 3;
+  // output index i = ((((b * 4 + win) * 18 + tg) * 2 + h) * 256 + f) * 4 + t4   (token = 8 tg + 4 h + t4)
+  const int t4 = (int)(i & 3);
+  long long r = i >> 2;
   const int f = (int)(r & 255); r >>= 8;
+  const int h = (int)(r & 1); r >>= 1;
   const int tg = (int)(r % 18); r /= 18;
   const int win = (int)(r & 3);
   const int b = (int)(r >> 2);
-  const int tok = tg * 8 + t8;
+  const int tok = tg * 8 + h * 4 + t4;
   const int sy = (win >> 1) * WIN + tok / WIN, sx = (win & 1) * WIN + tok % WIN;
   const int pix = ((sy + shift) % GRID) * GRID + (sx + shift) % GRID;
   out[i] = ag[((long long)b * (GRID * GRID) + pix) * 256 + f];
